@@ -1,0 +1,182 @@
+/* include/lqro.h -- C ABI of the B200-native LQR-Obstacles hot path (liblqro.so).
+ *
+ * The reference (hihixuyang/LQR-Obstacles) has no plugin/FFI layer: its boundary is the set of free
+ * functions its main loop calls every time step.  Each entry point below names the reference
+ * function(s) it replaces (aliases as in SURVEY.md: MAIN = QuadrotorHoverController/
+ * LQRObstaclesPositionControl(Working).cpp, AGENT = QuadrotorHoverController/Agent.cpp).
+ * The C++ shims carrying the reference's own signatures are in include/lqro_dropin.hpp and call
+ * only what is declared here.
+ *
+ * Conventions: every function returns 0 on success and a negative LQRO_E_* code on failure; nothing
+ * throws or aborts.  The caller owns every host buffer; the context owns all device memory, streams,
+ * events and the NCCL communicator.  One context per GPU per process; calls on one context must be
+ * serialised by the caller (the reference is single-threaded), different contexts are independent.
+ * There is NO CPU fallback: without a CUDA device lqro_create fails with LQRO_E_CUDA.
+ *
+ * Matrices are row-major FP64.  An agent's state is the reference's 16-vector
+ * [p(3) v(3) r(3) w(3) rotor forces(4)] (MAIN:341-345, simulator2.h:4).
+ */
+#ifndef LQRO_H
+#define LQRO_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQRO_X_DIM 16
+#define LQRO_U_DIM 4
+#define LQRO_V_DIM 3
+
+#define LQRO_OK            0
+#define LQRO_E_ARG        -1   /* bad argument */
+#define LQRO_E_CUDA       -2   /* CUDA runtime error / no device (see lqro_last_error) */
+#define LQRO_E_STATE      -3   /* call order (e.g. step before set_dynamics) */
+#define LQRO_E_NCCL       -4   /* NCCL not available / communicator error */
+#define LQRO_E_LIMIT      -5   /* a configured capacity was exceeded */
+
+/* hull_input: what the convex hull is computed on (MAIN:765-767 prints the cloud with 6
+ * significant digits before qconvex reads it). */
+#define LQRO_HULL_TEXT6    0   /* reference behaviour: strtod(printf("%g")) of every coordinate */
+#define LQRO_HULL_FP64     1   /* un-rounded FP64 cloud */
+
+/* per-pair status written by a step */
+#define LQRO_PAIR_NONE     0   /* <= 4 reachable points or empty slot: no plane (MAIN:1393) */
+#define LQRO_PAIR_OUTSIDE  1   /* relative velocity outside the obstacle: GJK plane (MAIN:1399) */
+#define LQRO_PAIR_INSIDE   2   /* inside: nearest-hull-facet plane (MAIN:1396) */
+#define LQRO_PAIR_DEGENERATE 0x100 /* OR-ed in: the hull met a round-off-band decision / internal limit */
+
+typedef struct lqro_ctx lqro_ctx;
+
+/* One POD carries what the reference keeps in #defines and globals (MAIN:30-36, 1102, 1367). */
+typedef struct lqro_config {
+  int device;            /* CUDA device ordinal */
+  int n_agents;          /* N: agents whose state is visible to this context (global count) */
+  int local_begin;       /* first agent owned by this context (0 on one GPU) */
+  int n_local;           /* agents owned (0 => n_agents - local_begin) */
+  int max_neighbors;     /* K: neighbour slots per agent (reference: N-1, every other agent) */
+  int horizon;           /* H = OBSTACLE_STEPS (30) */
+  int n_samples;         /* P = NUM_POINTS (50) */
+  double xy_radius;      /* XYRADIUS 0.26 */
+  double z_radius;       /* ZRADIUS 0.75 */
+  double max_speed;      /* reachable-velocity sphere radius, MAIN:1367 (30) */
+  double lp_radius;      /* maxSpeed_ of calculateNewV, MAIN:1102 (100) */
+  int hull_input;        /* LQRO_HULL_TEXT6 | LQRO_HULL_FP64 */
+  int fix_facet0_normal; /* 1: nearest facet 0 yields facet 0's normal; 0 is not offered on the device
+                            (the reference then keeps the previous pair's normal, a sequential
+                            cross-pair dependency) */
+  int max_hull_pairs;    /* capacity of the inside-case work queue per step (0 => n_local*K) */
+  int hull_slots;        /* concurrent hull workspaces (0 => default) */
+} lqro_config;
+
+/* Fills the reference's compile-time constants (MAIN:30-36, 1102, 1367). */
+void lqro_default_config(lqro_config* cfg);
+
+int lqro_create(const lqro_config* cfg, lqro_ctx** out);
+int lqro_destroy(lqro_ctx* ctx);
+const char* lqro_last_error(const lqro_ctx* ctx);  /* ctx may be NULL: error of the last failed lqro_create */
+const char* lqro_version(void);
+
+/* ---- (1) dynamics / gains ------------------------------------------------------------------- */
+
+/* Replaces the Riccati part of controlMatrices (MAIN:512-543): for each of n_batch problems the
+ * velocity-LQR gains L (4x16), E (4x3) and the position-LQR gains Lh (3x16), Eh (3x3) of the
+ * linearised model A (16x16), B (16x4) with weights Qv = qv*I3, Qp = qp*I3, R = r*I4, Qx = 0, c = 0,
+ * by `iters` fixed-point iterations on the device (warp per problem).  Host pointers. */
+int lqro_solve_gains(lqro_ctx* ctx, int n_batch, const double* A, const double* B, double qv, double qp, double r,
+                     int iters, double* L, double* E, double* Lh, double* Eh);
+
+/* Replaces findFG (MAIN:653-662) x H and the pair-independent half of createObstacle (MAIN:684-685):
+ * builds on the device, in the reference's operation order, NF_k = -(C F_k) and T_k = (C G_k)^-1 for
+ * k = 1..H with F_k = (A+BL)^k, G_k = sum_{m<k} (A+BL)^m B E.  Must precede any step. Host pointers. */
+int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E);
+
+/* Copies the tables back (parity checks): NF H*3*16, T H*3*3, sphere samples P*3 (createSpheres,
+ * MAIN:665-680).  Any pointer may be NULL. */
+int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* spheres);
+
+/* ---- (2)-(4) the per-timestep path ------------------------------------------------------------ */
+
+/* One avoidance step for the agents this context owns: for every owned agent i and neighbour slot
+ * kk (j = nbr[i_local*K + kk], j < 0 = empty) createObstacle x H, findReachableObstacle, pointInHull /
+ * run_gjk / convexHull, createHalfPlanes (MAIN:1381-1403), then calculateNewV (MAIN:1406).
+ * HOST buffers; the copies to and from the device are part of the call.
+ *   x      n_agents*16  state ESTIMATES of all agents (Quadrotor::x, MAIN:1385)
+ *   vpref  n_local*3    preferred velocities (Quadrotor::vGoal)
+ *   nbr    n_local*K    neighbour agent ids (global), planes are generated in slot order
+ *   newV   n_local*3    out: Quadrotor::newV */
+int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, const int* nbr, double* newV);
+
+/* Same with DEVICE pointers, asynchronous on the context's stream (or `stream` if non-NULL, a
+ * cudaStream_t).  d_x may be NULL to use the context's own state buffer (see lqro_device_state). */
+int lqro_step_device(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV,
+                     void* stream);
+int lqro_synchronize(lqro_ctx* ctx);
+/* Make the context launch on a caller-owned cudaStream_t (e.g. the harness's stream, so its events see
+ * the kernels).  NULL restores the context's own stream. */
+int lqro_set_stream(lqro_ctx* ctx, void* stream);
+
+/* Per-pair results of the last step (host pointers, any may be NULL):
+ *   planes n_local*K*6 float (point xyz, normal xyz; createHalfPlanes, MAIN:1085-1098)
+ *   status n_local*K   int   (LQRO_PAIR_*)
+ *   nreach n_local*K   int   (points surviving findReachableObstacle)
+ *   dist   n_local*K   double (distance before the 0.5 of MAIN:1401)
+ *   nfacets n_local*K  int   (hull facets, inside pairs only) */
+int lqro_get_pair_results(lqro_ctx* ctx, float* planes, int* status, int* nreach, double* dist, int* nfacets);
+
+/* counters of the last step: [0] pairs evaluated, [1] pairs with a plane, [2] inside (hull) pairs,
+ * [3] degenerate hulls, [4] hull queue overflow, [5] kernels launched by the step */
+int lqro_get_counters(lqro_ctx* ctx, long long* out6);
+
+/* ---- per-stage entry points (unit parity; host pointers) -------------------------------------- */
+
+/* createObstacle x H for one pair (MAIN:683-688): q = H*P*3 candidate points, k-major. */
+int lqro_candidates(lqro_ctx* ctx, const double* xi, const double* xj, double* q);
+/* findReachableObstacle (MAIN:691-706): ascending indices of reachable points; returns count in *n_out. */
+int lqro_reachable(lqro_ctx* ctx, const double* q, int n, const double* xi, const double* xj, int* idx, int* n_out);
+/* run_gjk (MAIN:712-746): squared distance, witness on the cloud, G-test count. */
+int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_hull, int* iterations);
+/* qconvex n + Fv (MAIN:762-806) for one cloud given as-is (no rounding applied here): facets in qhull
+ * order, planes nf*4, verts nf*3 (first vertex = apex).  *nf_io: in capacity, out count. */
+int lqro_convex_hull(lqro_ctx* ctx, const double* pts, int n, double* planes, int* verts, int* nf_io, int* degenerate);
+/* convexHull (MAIN:809-838): 6-digit rounding per hull_input, hull, nearest facet. */
+int lqro_hull_escape(lqro_ctx* ctx, const double* pts, int n, const double* vrel, double* distance, double* normal,
+                     int* best_facet, int* n_facets);
+/* calculateNewV (MAIN:1101-1112) for `batch` independent agents: planes batch*max_planes*6 floats,
+ * counts batch, goal batch*3 FP64, newV batch*3 FP64. */
+int lqro_new_velocity(lqro_ctx* ctx, int batch, int max_planes, const float* planes, const int* counts,
+                      const double* goal, double* newV);
+/* RVO-form Agent::update (AGENT:176-180), FP32: vel = newVel; pos += vel*dt.  Host pointers, n*3 each. */
+int lqro_agent_update(lqro_ctx* ctx, int n, float* pos, float* vel, const float* newVel, float dt);
+/* printf("%g")/strtod round trip of MAIN:765-767 applied to n doubles on the device. */
+int lqro_round6(lqro_ctx* ctx, const double* in, int n, double* out);
+
+/* ---- multi-GPU: agents partitioned, one all-gather of the state per step --------------------- */
+
+/* 128-byte NCCL unique id (rank 0 creates it, the caller ships it to the other ranks). */
+int lqro_comm_unique_id(void* id128);
+int lqro_comm_init(lqro_ctx* ctx, int rank, int world, const void* id128);
+/* Device pointer to the context's n_agents*16 state buffer; each rank writes its own block
+ * [local_begin, local_begin+n_local) there (lqro_upload_local_state or its own kernels). */
+int lqro_device_state(lqro_ctx* ctx, double** d_x);
+int lqro_upload_local_state(lqro_ctx* ctx, const double* x_local);
+/* The sharded step with HOST buffers (multi-GPU form of lqro_step): uploads this rank's block of the
+ * state (x_local n_local*16), all-gathers it, runs the step for the owned agents, downloads newV.
+ * With no communicator it equals lqro_step (n_local == n_agents). */
+int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const double* vpref, const int* nbr, double* newV);
+/* ncclAllGather of the per-rank blocks into every rank's state buffer (in place), on the context's stream.
+ * With no communicator (single GPU) it is a no-op. Blocks must be equal-sized (n_local identical). */
+int lqro_allgather_state(lqro_ctx* ctx);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* Peak-rate micro-benchmarks used for the roofline denominators that MEASURED_PEAKS.json lacks:
+ * chains of independent DFMA / FFMA on every SM; returns TFLOP/s (2 flop per FMA). */
+int lqro_measure_fp64_peak(lqro_ctx* ctx, double* tflops);
+int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops);
+/* Device time (ms) of the kernels of the last step: [0] pair kernel, [1] hull kernel, [2] LP kernel,
+ * [3] whole step (kernels only, measured with CUDA events on the launching stream). */
+int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQRO_H */

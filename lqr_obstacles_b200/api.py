@@ -1,0 +1,291 @@
+"""ctypes mirror of include/lqro.h.  Names follow the reference's functions for the path
+(obstacle creation, half-plane creation, new-velocity calculation, agent update)."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+c_int, c_double, c_float, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_void_p
+
+HULL_TEXT6, HULL_FP64 = 0, 1
+PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE = 0, 1, 2, 0x100
+
+
+class LqroError(RuntimeError):
+    pass
+
+
+class Config(ctypes.Structure):
+    _fields_ = [
+        ("device", c_int), ("n_agents", c_int), ("local_begin", c_int), ("n_local", c_int), ("max_neighbors", c_int),
+        ("horizon", c_int), ("n_samples", c_int), ("xy_radius", c_double), ("z_radius", c_double), ("max_speed", c_double),
+        ("lp_radius", c_double), ("hull_input", c_int), ("fix_facet0_normal", c_int), ("max_hull_pairs", c_int),
+        ("hull_slots", c_int),
+    ]
+
+
+_lib = None
+
+EXPORTS = [
+    "lqro_default_config", "lqro_create", "lqro_destroy", "lqro_last_error", "lqro_version", "lqro_solve_gains",
+    "lqro_set_dynamics", "lqro_get_tables", "lqro_step", "lqro_step_device", "lqro_synchronize", "lqro_set_stream",
+    "lqro_step_sharded", "lqro_get_pair_results",
+    "lqro_get_counters", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
+    "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
+    "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
+]
+
+
+def load_library(path=None):
+    """Load liblqro.so.  Raises if the CUDA library has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.SO
+    if not os.path.exists(path):
+        raise LqroError("liblqro.so is missing (%s): build it with `python -m lqr_obstacles_b200.build`; "
+                        "there is no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    lib.lqro_last_error.restype = ctypes.c_char_p
+    lib.lqro_last_error.argtypes = [c_void_p]
+    lib.lqro_version.restype = ctypes.c_char_p
+    lib.lqro_default_config.argtypes = [ctypes.POINTER(Config)]
+    lib.lqro_default_config.restype = None
+    lib.lqro_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(c_void_p)]
+    lib.lqro_destroy.argtypes = [c_void_p]
+    lib.lqro_solve_gains.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_double, c_double, c_double, c_int] + [c_void_p] * 4
+    lib.lqro_set_dynamics.argtypes = [c_void_p] * 5
+    lib.lqro_get_tables.argtypes = [c_void_p] * 4
+    lib.lqro_step.argtypes = [c_void_p] * 5
+    lib.lqro_step_device.argtypes = [c_void_p] * 6
+    lib.lqro_synchronize.argtypes = [c_void_p]
+    lib.lqro_set_stream.argtypes = [c_void_p, c_void_p]
+    lib.lqro_step_sharded.argtypes = [c_void_p] * 5
+    lib.lqro_get_pair_results.argtypes = [c_void_p] * 6
+    lib.lqro_get_counters.argtypes = [c_void_p, c_void_p]
+    lib.lqro_candidates.argtypes = [c_void_p] * 4
+    lib.lqro_reachable.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lqro_gjk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.lqro_convex_hull.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lqro_hull_escape.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lqro_new_velocity.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.lqro_agent_update.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float]
+    lib.lqro_round6.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    lib.lqro_comm_unique_id.argtypes = [c_void_p]
+    lib.lqro_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    lib.lqro_device_state.argtypes = [c_void_p, ctypes.POINTER(c_void_p)]
+    lib.lqro_upload_local_state.argtypes = [c_void_p, c_void_p]
+    lib.lqro_allgather_state.argtypes = [c_void_p]
+    lib.lqro_measure_fp64_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
+    lib.lqro_measure_fp32_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
+    lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
+    if path == _build.SO:
+        _lib = lib
+    return lib
+
+
+def default_config(**kw):
+    lib = load_library()
+    c = Config()
+    lib.lqro_default_config(ctypes.byref(c))
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return a.ctypes.data_as(c_void_p)
+    return c_void_p(int(a))  # raw address (e.g. torch tensor data_ptr())
+
+
+class Lqro:
+    """One context = one GPU.  Method names are the reference's entry points."""
+
+    def __init__(self, **cfg):
+        self.lib = load_library()
+        self.cfg = default_config(**cfg)
+        h = c_void_p()
+        rc = self.lib.lqro_create(ctypes.byref(self.cfg), ctypes.byref(h))
+        if rc != 0:
+            raise LqroError("lqro_create failed (%d): %s" % (rc, self.lib.lqro_last_error(None).decode()))
+        self.h = h
+        self.N = self.cfg.n_agents
+        self.NL = self.cfg.n_local if self.cfg.n_local > 0 else self.N - self.cfg.local_begin
+        self.K, self.H, self.P = self.cfg.max_neighbors, self.cfg.horizon, self.cfg.n_samples
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lqro_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LqroError("liblqro error %d: %s" % (rc, self.lib.lqro_last_error(self.h).decode()))
+
+    # -- (1) controlMatrices / findFG
+    def solve_gains(self, A, B, qv=100.0, qp=0.1, r=5.0, iters=300):
+        A = np.ascontiguousarray(A, dtype=np.float64).reshape(-1, 16, 16)
+        B = np.ascontiguousarray(B, dtype=np.float64).reshape(-1, 16, 4)
+        nb = len(A)
+        L, E, Lh, Eh = np.zeros((nb, 4, 16)), np.zeros((nb, 4, 3)), np.zeros((nb, 3, 16)), np.zeros((nb, 3, 3))
+        self._ck(self.lib.lqro_solve_gains(self.h, nb, _p(A), _p(B), qv, qp, r, iters, _p(L), _p(E), _p(Lh), _p(Eh)))
+        return L, E, Lh, Eh
+
+    def set_dynamics(self, A, B, L, E):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self._ck(self.lib.lqro_set_dynamics(self.h, _p(f(A)), _p(f(B)), _p(f(L)), _p(f(E))))
+
+    def tables(self):
+        NF, T, sph = np.zeros((self.H, 3, 16)), np.zeros((self.H, 3, 3)), np.zeros((self.P, 3))
+        self._ck(self.lib.lqro_get_tables(self.h, _p(NF), _p(T), _p(sph)))
+        return NF, T, sph
+
+    # -- (2)-(4) the step
+    def step(self, x, vpref, nbr, newV=None):
+        """Host buffers (numpy or raw pinned addresses): the copies are inside the call."""
+        if newV is None:
+            newV = np.zeros((self.NL, 3))
+        self._ck(self.lib.lqro_step(self.h, _p(x), _p(vpref), _p(nbr), _p(newV)))
+        return newV
+
+    def step_device(self, d_x, d_vpref, d_nbr, d_newV, stream=None):
+        self._ck(self.lib.lqro_step_device(self.h, _p(d_x), _p(d_vpref), _p(d_nbr), _p(d_newV), stream))
+
+    def step_sharded(self, x_local, vpref, nbr, newV=None):
+        if newV is None:
+            newV = np.zeros((self.NL, 3))
+        self._ck(self.lib.lqro_step_sharded(self.h, _p(x_local), _p(vpref), _p(nbr), _p(newV)))
+        return newV
+
+    def set_stream(self, stream):
+        self._ck(self.lib.lqro_set_stream(self.h, None if stream is None else c_void_p(int(stream))))
+
+    def synchronize(self):
+        self._ck(self.lib.lqro_synchronize(self.h))
+
+    def pair_results(self):
+        NP = self.NL * self.K
+        planes = np.zeros((self.NL, self.K, 6), dtype=np.float32)
+        status = np.zeros((self.NL, self.K), dtype=np.int32)
+        nreach = np.zeros((self.NL, self.K), dtype=np.int32)
+        dist = np.zeros((self.NL, self.K))
+        nfac = np.zeros((self.NL, self.K), dtype=np.int32)
+        self._ck(self.lib.lqro_get_pair_results(self.h, _p(planes), _p(status), _p(nreach), _p(dist), _p(nfac)))
+        return dict(planes=planes, status=status, nreach=nreach, dist=dist, nfacets=nfac)
+
+    def counters(self):
+        c = np.zeros(6, dtype=np.int64)
+        self._ck(self.lib.lqro_get_counters(self.h, _p(c)))
+        return dict(pairs=int(c[0]), planes=int(c[1]), inside=int(c[2]), degenerate=int(c[3]), hull_overflow=int(c[4]),
+                    launches=int(c[5]))
+
+    def last_step_ms(self):
+        t = np.zeros(4, dtype=np.float32)
+        self._ck(self.lib.lqro_last_step_ms(self.h, _p(t)))
+        return dict(pairs=float(t[0]), hull=float(t[1]), lp=float(t[2]), total=float(t[3]))
+
+    # -- per-stage
+    def createObstacle(self, xi, xj):
+        q = np.zeros((self.H * self.P, 3))
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self._ck(self.lib.lqro_candidates(self.h, _p(f(xi)), _p(f(xj)), _p(q)))
+        return q
+
+    def findReachableObstacle(self, q, xi, xj):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        idx = np.zeros(max(len(q), 1), dtype=np.int32)
+        n = c_int()
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self._ck(self.lib.lqro_reachable(self.h, _p(q), len(q), _p(f(xi)), _p(f(xj)), _p(idx), ctypes.byref(n)))
+        return idx[: n.value].copy()
+
+    def run_gjk(self, vrel, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        sq, it = c_double(), c_int()
+        w = np.zeros(3)
+        self._ck(self.lib.lqro_gjk(self.h, _p(np.ascontiguousarray(vrel, dtype=np.float64)), _p(pts), len(pts), ctypes.byref(sq),
+                                   _p(w), ctypes.byref(it)))
+        return sq.value, w, it.value
+
+    def convex_hull(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        cap = 2 * len(pts) + 64
+        planes, verts = np.zeros((cap, 4)), np.zeros((cap, 3), dtype=np.int32)
+        nf, deg = c_int(cap), c_int()
+        self._ck(self.lib.lqro_convex_hull(self.h, _p(pts), len(pts), _p(planes), _p(verts), ctypes.byref(nf), ctypes.byref(deg)))
+        return planes[: nf.value].copy(), verts[: nf.value].copy(), deg.value
+
+    def convexHull(self, pts, vrel):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        d, best, nf = c_double(), c_int(), c_int()
+        nrm = np.zeros(3)
+        self._ck(self.lib.lqro_hull_escape(self.h, _p(pts), len(pts), _p(np.ascontiguousarray(vrel, dtype=np.float64)),
+                                           ctypes.byref(d), _p(nrm), ctypes.byref(best), ctypes.byref(nf)))
+        return d.value, nrm, best.value, nf.value
+
+    def calculateNewV(self, planes, counts, goal):
+        planes = np.ascontiguousarray(planes, dtype=np.float32)
+        batch, maxp = planes.shape[0], planes.shape[1]
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        goal = np.ascontiguousarray(goal, dtype=np.float64)
+        out = np.zeros((batch, 3))
+        self._ck(self.lib.lqro_new_velocity(self.h, batch, maxp, _p(planes), _p(counts), _p(goal), _p(out)))
+        return out
+
+    def agent_update(self, pos, vel, newVel, dt):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).copy()
+        vel = np.ascontiguousarray(vel, dtype=np.float32).copy()
+        newVel = np.ascontiguousarray(newVel, dtype=np.float32)
+        self._ck(self.lib.lqro_agent_update(self.h, len(pos), _p(pos), _p(vel), _p(newVel), dt))
+        return pos, vel
+
+    def round6(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        out = np.zeros_like(a)
+        self._ck(self.lib.lqro_round6(self.h, _p(a), a.size, _p(out)))
+        return out
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        lib = load_library()
+        buf = (ctypes.c_char * 128)()
+        rc = lib.lqro_comm_unique_id(buf)
+        if rc != 0:
+            raise LqroError("lqro_comm_unique_id failed: %d" % rc)
+        return bytes(buf)
+
+    def comm_init(self, rank, world, uid):
+        buf = (ctypes.c_char * 128).from_buffer_copy(uid)
+        self._ck(self.lib.lqro_comm_init(self.h, rank, world, buf))
+
+    def device_state(self):
+        p = c_void_p()
+        self._ck(self.lib.lqro_device_state(self.h, ctypes.byref(p)))
+        return p.value
+
+    def upload_local_state(self, x_local):
+        self._ck(self.lib.lqro_upload_local_state(self.h, _p(x_local)))
+
+    def allgather_state(self):
+        self._ck(self.lib.lqro_allgather_state(self.h))
+
+    def measure_peaks(self):
+        a, b = c_double(), c_double()
+        self._ck(self.lib.lqro_measure_fp64_peak(self.h, ctypes.byref(a)))
+        self._ck(self.lib.lqro_measure_fp32_peak(self.h, ctypes.byref(b)))
+        return a.value, b.value

@@ -1,0 +1,678 @@
+// lqro_api.cu -- context, launch logic and the extern "C" ABI declared in include/lqro.h.
+// Single translation unit: the kernels live in the .cuh files included below.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lqro.h"
+#include "lqro_common.cuh"
+#include "lqro_gjk.cuh"
+#include "lqro_pair.cuh"
+#include "lqro_hull.cuh"
+#include "lqro_lp.cuh"
+#include "lqro_riccati.cuh"
+
+// ---- minimal NCCL surface, resolved at run time (no link-time dependency; the process may already
+//      hold a libnccl, e.g. the one bundled with PyTorch) ------------------------------------------
+typedef struct { char internal[128]; } lqro_ncclUniqueId;
+typedef void* lqro_ncclComm_t;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(lqro_ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(lqro_ncclComm_t*, int, lqro_ncclUniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, lqro_ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(lqro_ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+static bool load_nccl() {
+  if (g_nccl.ok) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD); if (h) break; }   // reuse a loaded one first
+  if (!h) for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+  if (!h) return false;
+  g_nccl.handle = h;
+  g_nccl.GetUniqueId = (int (*)(lqro_ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(lqro_ncclComm_t*, int, lqro_ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, lqro_ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(lqro_ncclComm_t))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy;
+  return g_nccl.ok;
+}
+
+// ---- context ---------------------------------------------------------------------------------------
+struct lqro_ctx {
+  lqro_config cfg;
+  LqroParams prm;
+  LqroTables tb;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool have_dynamics = false, stepped = false;
+  // tables / dynamics
+  double *d_dyn = nullptr;   // A(256) B(64) L(64) E(12)
+  double *d_NFt = nullptr, *d_NF = nullptr, *d_T = nullptr, *d_sph = nullptr;
+  // step buffers
+  double *d_x = nullptr, *d_vpref = nullptr, *d_newV = nullptr, *d_dist = nullptr;
+  int *d_nbr = nullptr, *d_status = nullptr, *d_nreach = nullptr, *d_nfacets = nullptr, *d_nplanes = nullptr;
+  float *d_planes = nullptr, *d_planes_c = nullptr, *d_proj = nullptr;
+  int* d_ctr = nullptr;       // [0] pair work counter [1] hull count [2] hull work counter [3] degenerate [4..7] spare
+  int* d_hull_items = nullptr;
+  char* d_hull_ws = nullptr;
+  size_t hull_ws_stride = 0;
+  int hull_slots = 0, hull_cap = 0, cap_pts = 0;
+  // launch geometry
+  int pair_warps = 0, pair_blocks = 0; size_t pair_smem = 0;
+  int hull_wpb = 2, hull_blocks = 0; size_t hull_smem = 0;
+  // stage scratch (grown on demand)
+  char* d_scratch = nullptr; size_t scratch_bytes = 0;
+  char* d_stage_ws = nullptr; int stage_ws_pts = 0;
+  // multi-GPU
+  lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
+  long long launches = 0;
+  std::string err;
+};
+
+static std::string g_create_err;
+
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      char b__[512];                                                                                  \
+      snprintf(b__, sizeof b__, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      if (ctx) ctx->err = b__; else g_create_err = b__;                                               \
+      return LQRO_E_CUDA;                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+static int fail(lqro_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg; else g_create_err = msg;
+  return code;
+}
+
+extern "C" const char* lqro_version(void) { return "lqro 0.1 (sm_100a)"; }
+
+extern "C" void lqro_default_config(lqro_config* c) {
+  memset(c, 0, sizeof *c);
+  c->device = 0;
+  c->n_agents = 6;          // NUM_QUADS, MAIN:30
+  c->local_begin = 0;
+  c->n_local = 0;
+  c->max_neighbors = 5;
+  c->horizon = 30;          // OBSTACLE_STEPS, MAIN:33
+  c->n_samples = 50;        // NUM_POINTS, MAIN:34
+  c->xy_radius = 0.26;      // MAIN:35
+  c->z_radius = 0.75;       // MAIN:36
+  c->max_speed = 30.0;      // MAIN:1367
+  c->lp_radius = 100.0;     // MAIN:1102
+  c->hull_input = LQRO_HULL_TEXT6;
+  c->fix_facet0_normal = 1;
+  c->max_hull_pairs = 0;
+  c->hull_slots = 0;
+}
+
+extern "C" const char* lqro_last_error(const lqro_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+static int ensure_scratch(lqro_ctx* ctx, size_t bytes) {
+  if (ctx->scratch_bytes >= bytes) return LQRO_OK;
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+  CU(cudaMalloc(&ctx->d_scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_destroy(lqro_ctx* ctx) {
+  if (!ctx) return LQRO_OK;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+  void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
+                  ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
+                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
+  lqro_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, LQRO_E_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n_agents < 1 || cfg->max_neighbors < 1 || cfg->horizon < 1 || cfg->n_samples < 1 || cfg->horizon * cfg->n_samples > 8192 ||
+      !(cfg->max_speed > 0) || cfg->local_begin < 0 || cfg->local_begin >= cfg->n_agents)
+    return fail(nullptr, LQRO_E_ARG, "bad configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, LQRO_E_CUDA, "no CUDA device: liblqro has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LQRO_E_ARG, "bad device ordinal");
+  CU(cudaSetDevice(cfg->device));
+  ctx = new lqro_ctx();
+  ctx->cfg = *cfg;
+  if (ctx->cfg.n_local <= 0) ctx->cfg.n_local = cfg->n_agents - cfg->local_begin;
+  if (ctx->cfg.local_begin + ctx->cfg.n_local > cfg->n_agents) { delete ctx; return fail(nullptr, LQRO_E_ARG, "local block exceeds n_agents"); }
+  const int N = cfg->n_agents, NL = ctx->cfg.n_local, K = cfg->max_neighbors, H = cfg->horizon, P = cfg->n_samples;
+  LqroParams& p = ctx->prm;
+  p.N = N; p.local_begin = cfg->local_begin; p.n_local = NL; p.K = K; p.H = H; p.P = P; p.HP = H * P;
+  p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
+  p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete ctx; return fail(nullptr, LQRO_E_CUDA, "cudaGetDeviceProperties failed"); }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  auto bail = [&](int code) { lqro_destroy(ctx); return code; };
+#define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); return bail(LQRO_E_CUDA); } } while (0)
+  CUC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  for (auto& e : ctx->ev) CUC(cudaEventCreate(&e));
+  CUC(cudaMalloc(&ctx->d_dyn, sizeof(double) * (256 + 64 + 64 + 12)));
+  CUC(cudaMalloc(&ctx->d_NFt, sizeof(double) * 48 * H));
+  CUC(cudaMalloc(&ctx->d_NF, sizeof(double) * 48 * H));
+  CUC(cudaMalloc(&ctx->d_T, sizeof(double) * 9 * H));
+  CUC(cudaMalloc(&ctx->d_sph, sizeof(double) * 3 * P));
+  const size_t NP = (size_t)NL * K;
+  CUC(cudaMalloc(&ctx->d_x, sizeof(double) * 16 * (size_t)N));
+  CUC(cudaMalloc(&ctx->d_vpref, sizeof(double) * 3 * (size_t)NL));
+  CUC(cudaMalloc(&ctx->d_newV, sizeof(double) * 3 * (size_t)NL));
+  CUC(cudaMalloc(&ctx->d_nbr, sizeof(int) * NP));
+  CUC(cudaMalloc(&ctx->d_status, sizeof(int) * NP));
+  CUC(cudaMalloc(&ctx->d_nreach, sizeof(int) * NP));
+  CUC(cudaMalloc(&ctx->d_nfacets, sizeof(int) * NP));
+  CUC(cudaMalloc(&ctx->d_nplanes, sizeof(int) * (size_t)NL));
+  CUC(cudaMalloc(&ctx->d_dist, sizeof(double) * NP));
+  CUC(cudaMalloc(&ctx->d_planes, sizeof(float) * 6 * NP));
+  CUC(cudaMalloc(&ctx->d_planes_c, sizeof(float) * 6 * NP));
+  CUC(cudaMalloc(&ctx->d_proj, sizeof(float) * 6 * NP));
+  CUC(cudaMalloc(&ctx->d_ctr, sizeof(int) * 16));
+  CUC(cudaMemset(ctx->d_ctr, 0, sizeof(int) * 16));
+  CUC(cudaMemset(ctx->d_status, 0, sizeof(int) * NP));
+  CUC(cudaMemset(ctx->d_nfacets, 0, sizeof(int) * NP));
+  CUC(cudaMemset(ctx->d_nreach, 0, sizeof(int) * NP));
+  CUC(cudaMemset(ctx->d_dist, 0, sizeof(double) * NP));
+  CUC(cudaMemset(ctx->d_planes, 0, sizeof(float) * 6 * NP));
+  ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)(NP < 0x7fffffff ? NP : 0x7fffffff);
+  CUC(cudaMalloc(&ctx->d_hull_items, sizeof(int) * (size_t)ctx->hull_cap));
+  // sphere samples: createSpheres, MAIN:665-680 (one-off table; radii doubled for the Minkowski sum)
+  {
+    std::vector<double> sph(3 * (size_t)P);
+    const double dlong = M_PI * (3.0 - sqrt(5.0));
+    const double dz = 2.0 / P;
+    double longt = 0, z = 1.0 - dz / 2.0;
+    for (int i = 0; i < P; ++i) {
+      sph[3 * i + 0] = 2 * cfg->xy_radius * cos(longt) * sqrt(1 - z * z);
+      sph[3 * i + 1] = 2 * cfg->xy_radius * sin(longt) * sqrt(1 - z * z);
+      sph[3 * i + 2] = 2 * cfg->z_radius * z;
+      z -= dz;
+      longt += dlong;
+    }
+    CUC(cudaMemcpy(ctx->d_sph, sph.data(), sizeof(double) * 3 * P, cudaMemcpyHostToDevice));
+  }
+  ctx->tb.NFt = ctx->d_NFt; ctx->tb.T = ctx->d_T; ctx->tb.sph = ctx->d_sph;
+  // launch geometry of the pair kernel: as many warps per block as the opt-in shared memory holds
+  {
+    const size_t tbl = sizeof(double) * pair_block_table_doubles(H, P);
+    const size_t per = sizeof(double) * pair_warp_doubles(H, P);
+    int wp = (int)((ctx->smem_optin - tbl) / per);
+    if (wp > 8) wp = 8;
+    if (wp < 1) { g_create_err = "H*P too large for shared memory"; return bail(LQRO_E_LIMIT); }
+    ctx->pair_warps = wp;
+    ctx->pair_smem = tbl + per * wp;
+    ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM (shared memory allows exactly one)
+    CUC(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pair_smem));
+    const size_t stage = tbl + per;
+    CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+    ctx->hull_wpb = 2;
+    ctx->hull_smem = tbl + per * ctx->hull_wpb + sizeof(HullCtl) * ctx->hull_wpb + 16;
+    CUC(cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->hull_smem));
+    int per_sm = (int)(ctx->smem_optin / ctx->hull_smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int slots = cfg->hull_slots > 0 ? cfg->hull_slots : ctx->sm_count * per_sm * ctx->hull_wpb;
+    slots = (slots + ctx->hull_wpb - 1) / ctx->hull_wpb * ctx->hull_wpb;
+    ctx->hull_slots = slots;
+    ctx->hull_blocks = slots / ctx->hull_wpb;
+    ctx->cap_pts = H * P;
+    ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
+    CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * (size_t)slots));
+  }
+  CUC(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * ((sizeof(RiccatiWs) + 7) / 8) * 8)));
+#undef CUC
+  *out = ctx;
+  return LQRO_OK;
+}
+
+// ---- (1) gains and tables ---------------------------------------------------------------------------
+extern "C" int lqro_solve_gains(lqro_ctx* ctx, int nb, const double* A, const double* B, double qv, double qp, double r, int iters,
+                                double* L, double* E, double* Lh, double* Eh) {
+  if (!ctx || nb < 1 || !A || !B || !L || !E || !Lh || !Eh || iters < 1) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t nin = (size_t)nb * (256 + 64), nout = (size_t)nb * (64 + 12 + 48 + 9);
+  int rc = ensure_scratch(ctx, sizeof(double) * (nin + nout));
+  if (rc) return rc;
+  double* dA = (double*)ctx->d_scratch; double* dB = dA + (size_t)nb * 256;
+  double* dL = dB + (size_t)nb * 64; double* dE = dL + (size_t)nb * 64; double* dLh = dE + (size_t)nb * 12; double* dEh = dLh + (size_t)nb * 48;
+  CU(cudaMemcpyAsync(dA, A, sizeof(double) * 256 * nb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dB, B, sizeof(double) * 64 * nb, cudaMemcpyHostToDevice, ctx->stream));
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * ((sizeof(RiccatiWs) + 7) / 8) * 8;
+  k_riccati<<<(nb + wpb - 1) / wpb, wpb * 32, smem, ctx->stream>>>(nb, dA, dB, qv, qp, r, iters, dL, dE, dLh, dEh);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(L, dL, sizeof(double) * 64 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(E, dE, sizeof(double) * 12 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(Lh, dLh, sizeof(double) * 48 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(Eh, dEh, sizeof(double) * 9 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E) {
+  if (!ctx || !A || !B || !L || !E) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  double* d = ctx->d_dyn;
+  CU(cudaMemcpyAsync(d, A, sizeof(double) * 256, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + 256, B, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + 320, L, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + 384, E, sizeof(double) * 12, cudaMemcpyHostToDevice, ctx->stream));
+  k_horizon_tables<<<1, 256, 0, ctx->stream>>>(d, d + 256, d + 320, d + 384, ctx->prm.H, ctx->d_NFt, ctx->d_NF, ctx->d_T);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_dynamics = true;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* sph) {
+  if (!ctx) return LQRO_E_ARG;
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (NF) CU(cudaMemcpy(NF, ctx->d_NF, sizeof(double) * 48 * ctx->prm.H, cudaMemcpyDeviceToHost));
+  if (T) CU(cudaMemcpy(T, ctx->d_T, sizeof(double) * 9 * ctx->prm.H, cudaMemcpyDeviceToHost));
+  if (sph) CU(cudaMemcpy(sph, ctx->d_sph, sizeof(double) * 3 * ctx->prm.P, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
+// ---- the step ----------------------------------------------------------------------------------------
+static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV, cudaStream_t st) {
+  const LqroParams& p = ctx->prm;
+  PairOutputs po{ctx->d_planes, ctx->d_status, ctx->d_nreach, ctx->d_dist, ctx->d_nfacets};
+  HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
+  CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
+  CU(cudaEventRecord(ctx->ev[0], st));
+  k_pairs<<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, ctx->d_ctr + 0, hq);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[1], st));
+  k_hull<<<ctx->hull_blocks, ctx->hull_wpb * 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws,
+                                                                      ctx->hull_ws_stride, ctx->cap_pts, ctx->d_ctr);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[2], st));
+  k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,
+                                                          ctx->d_planes_c, ctx->d_proj, d_newV, ctx->d_nplanes);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[3], st));
+  ctx->launches = 3;
+  ctx->stepped = true;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_step_device(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV, void* stream) {
+  if (!ctx || !d_vpref || !d_newV) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  return launch_step(ctx, d_x ? d_x : ctx->d_x, d_vpref, d_nbr ? d_nbr : ctx->d_nbr, d_newV, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, const int* nbr, double* newV) {
+  if (!ctx || !x || !vpref || !newV) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const LqroParams& p = ctx->prm;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
+  if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  int rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_set_stream(lqro_ctx* ctx, void* stream) {
+  if (!ctx) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_synchronize(lqro_ctx* ctx) {
+  if (!ctx) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_get_pair_results(lqro_ctx* ctx, float* planes, int* status, int* nreach, double* dist, int* nfacets) {
+  if (!ctx) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const size_t NP = (size_t)ctx->prm.n_local * ctx->prm.K;
+  if (planes) CU(cudaMemcpy(planes, ctx->d_planes, sizeof(float) * 6 * NP, cudaMemcpyDeviceToHost));
+  if (status) CU(cudaMemcpy(status, ctx->d_status, sizeof(int) * NP, cudaMemcpyDeviceToHost));
+  if (nreach) CU(cudaMemcpy(nreach, ctx->d_nreach, sizeof(int) * NP, cudaMemcpyDeviceToHost));
+  if (dist) CU(cudaMemcpy(dist, ctx->d_dist, sizeof(double) * NP, cudaMemcpyDeviceToHost));
+  if (nfacets) CU(cudaMemcpy(nfacets, ctx->d_nfacets, sizeof(int) * NP, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_get_counters(lqro_ctx* ctx, long long* out6) {
+  if (!ctx || !out6) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int c[8];
+  CU(cudaMemcpy(c, ctx->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+  const size_t NP = (size_t)ctx->prm.n_local * ctx->prm.K;
+  std::vector<int> st(NP);
+  CU(cudaMemcpy(st.data(), ctx->d_status, sizeof(int) * NP, cudaMemcpyDeviceToHost));
+  long long withplane = 0;
+  for (size_t i = 0; i < NP; ++i) withplane += (st[i] & 0xff) != 0;
+  out6[0] = (long long)NP;
+  out6[1] = withplane;
+  out6[2] = c[1];
+  out6[3] = c[3];
+  out6[4] = c[1] > ctx->hull_cap ? c[1] - ctx->hull_cap : 0;
+  out6[5] = ctx->launches;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_last_step_ms(lqro_ctx* ctx, float* out4) {
+  if (!ctx || !out4) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaEventSynchronize(ctx->ev[3]));
+  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev[1]));
+  CU(cudaEventElapsedTime(out4 + 1, ctx->ev[1], ctx->ev[2]));
+  CU(cudaEventElapsedTime(out4 + 2, ctx->ev[2], ctx->ev[3]));
+  CU(cudaEventElapsedTime(out4 + 3, ctx->ev[0], ctx->ev[3]));
+  return LQRO_OK;
+}
+
+// ---- per-stage entry points ---------------------------------------------------------------------------
+extern "C" int lqro_candidates(lqro_ctx* ctx, const double* xi, const double* xj, double* q) {
+  if (!ctx || !xi || !xj || !q) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const int HP = ctx->prm.HP;
+  int rc = ensure_scratch(ctx, sizeof(double) * (32 + 3 * (size_t)HP));
+  if (rc) return rc;
+  double* dxi = (double*)ctx->d_scratch; double* dxj = dxi + 16; double* dq = dxj + 16;
+  CU(cudaMemcpyAsync(dxi, xi, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dxj, xj, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t smem = sizeof(double) * (pair_block_table_doubles(ctx->prm.H, ctx->prm.P) + pair_warp_doubles(ctx->prm.H, ctx->prm.P));
+  k_stage_candidates<<<1, 32, smem, ctx->stream>>>(ctx->prm, ctx->tb, dxi, dxj, dq);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(q, dq, sizeof(double) * 3 * HP, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_reachable(lqro_ctx* ctx, const double* q, int n, const double* xi, const double* xj, int* idx, int* n_out) {
+  if (!ctx || !q || n < 0 || !xi || !xj || !idx || !n_out) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_scratch(ctx, sizeof(double) * (32 + 3 * (size_t)n) + sizeof(int) * ((size_t)n + 4));
+  if (rc) return rc;
+  double* dxi = (double*)ctx->d_scratch; double* dxj = dxi + 16; double* dq = dxj + 16;
+  int* didx = (int*)(dq + 3 * (size_t)n); int* dn = didx + n;
+  CU(cudaMemcpyAsync(dxi, xi, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dxj, xj, sizeof(double) * 16, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) CU(cudaMemcpyAsync(dq, q, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_stage_reachable<<<1, 32, 0, ctx->stream>>>(ctx->prm, dq, n, dxi, dxj, didx, dn);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(n_out, dn, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n) CU(cudaMemcpyAsync(idx, didx, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_hull, int* iterations) {
+  if (!ctx || !vrel || !pts || n < 1 || !sqdist) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_scratch(ctx, sizeof(double) * (16 + 6 * (size_t)n) + 16);
+  if (rc) return rc;
+  double* dv = (double*)ctx->d_scratch; double* dout = dv + 4; double* dp = dout + 8; double* dscr = dp + 3 * (size_t)n;
+  int* dit = (int*)(dscr + 3 * (size_t)n);
+  CU(cudaMemcpyAsync(dv, vrel, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_stage_gjk<<<1, 32, 0, ctx->stream>>>(dv, dp, n, dscr, dout, dit);
+  CU(cudaGetLastError());
+  double out[8]; int it = 0;
+  CU(cudaMemcpyAsync(out, dout, sizeof(double) * 7, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&it, dit, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *sqdist = out[0];
+  if (wpt_hull) { wpt_hull[0] = out[1]; wpt_hull[1] = out[2]; wpt_hull[2] = out[3]; }
+  if (iterations) *iterations = it;
+  return LQRO_OK;
+}
+
+static int run_stage_hull(lqro_ctx* ctx, const double* pts, int n, int mode, double* planes, int* verts, int maxf, int* info5,
+                          const double* vrel, double* escape4) {
+  if (n > ctx->stage_ws_pts) {
+    if (ctx->d_stage_ws) cudaFree(ctx->d_stage_ws);
+    ctx->d_stage_ws = nullptr; ctx->stage_ws_pts = 0;
+    CU(cudaMalloc(&ctx->d_stage_ws, hull_ws_bytes(n)));
+    ctx->stage_ws_pts = n;
+  }
+  const int cap = ctx->stage_ws_pts;
+  const size_t nf_cap = 2 * (size_t)n + 64;
+  int rc = ensure_scratch(ctx, sizeof(double) * (6 * (size_t)n + 4 * nf_cap + 16) + sizeof(int) * (3 * nf_cap + 16));
+  if (rc) return rc;
+  double* dp = (double*)ctx->d_scratch; double* du = dp + 3 * (size_t)n; double* dpl = du + 3 * (size_t)n;
+  double* dv = dpl + 4 * nf_cap; double* desc = dv + 4;
+  int* dvt = (int*)(desc + 4); int* dinfo = dvt + 3 * nf_cap;
+  CU(cudaMemcpyAsync(dp, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (vrel) CU(cudaMemcpyAsync(dv, vrel, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
+  k_stage_hull<<<1, 32, 0, ctx->stream>>>(dp, n, mode, ctx->d_stage_ws, cap, dpl, dvt, (int)nf_cap, dinfo, vrel ? dv : nullptr, desc, du);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(info5, dinfo, sizeof(int) * 5, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int nf = info5[0];
+  if (nf > maxf) nf = maxf;
+  if (planes && nf > 0) CU(cudaMemcpy(planes, dpl, sizeof(double) * 4 * nf, cudaMemcpyDeviceToHost));
+  if (verts && nf > 0) CU(cudaMemcpy(verts, dvt, sizeof(int) * 3 * nf, cudaMemcpyDeviceToHost));
+  if (escape4 && vrel) CU(cudaMemcpy(escape4, desc, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_convex_hull(lqro_ctx* ctx, const double* pts, int n, double* planes, int* verts, int* nf_io, int* degenerate) {
+  if (!ctx || !pts || n < 4 || !nf_io) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int info[5];
+  int rc = run_stage_hull(ctx, pts, n, 0, planes, verts, *nf_io, info, nullptr, nullptr);
+  if (rc) return rc;
+  if (degenerate) *degenerate = info[1];
+  if (info[2]) { *nf_io = 0; return fail(ctx, LQRO_E_LIMIT, "hull failed (flat input or internal limit)"); }
+  *nf_io = info[0];
+  return LQRO_OK;
+}
+
+extern "C" int lqro_hull_escape(lqro_ctx* ctx, const double* pts, int n, const double* vrel, double* distance, double* normal,
+                                int* best_facet, int* n_facets) {
+  if (!ctx || !pts || n < 4 || !vrel || !distance || !normal) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int info[5]; double esc[4];
+  int rc = run_stage_hull(ctx, pts, n, ctx->prm.hull_input == LQRO_HULL_TEXT6 ? 1 : 0, nullptr, nullptr, 0, info, vrel, esc);
+  if (rc) return rc;
+  if (info[2]) return fail(ctx, LQRO_E_LIMIT, "hull failed (flat input or internal limit)");
+  *distance = esc[0]; normal[0] = esc[1]; normal[1] = esc[2]; normal[2] = esc[3];
+  if (best_facet) *best_facet = info[4];
+  if (n_facets) *n_facets = info[0];
+  return LQRO_OK;
+}
+
+extern "C" int lqro_new_velocity(lqro_ctx* ctx, int batch, int max_planes, const float* planes, const int* counts, const double* goal,
+                                 double* newV) {
+  if (!ctx || batch < 1 || max_planes < 1 || !planes || !counts || !goal || !newV) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t np = (size_t)batch * max_planes * 6;
+  int rc = ensure_scratch(ctx, sizeof(float) * 3 * np + sizeof(double) * 6 * (size_t)batch + sizeof(int) * (size_t)batch + 64);
+  if (rc) return rc;
+  double* dgoal = (double*)ctx->d_scratch; double* dnew = dgoal + 3 * (size_t)batch;
+  float* dpl = (float*)(dnew + 3 * (size_t)batch); float* dpc = dpl + np; float* dpr = dpc + np;
+  int* dcnt = (int*)(dpr + np);
+  CU(cudaMemcpyAsync(dpl, planes, sizeof(float) * np, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dcnt, counts, sizeof(int) * batch, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dgoal, goal, sizeof(double) * 3 * batch, cudaMemcpyHostToDevice, ctx->stream));
+  k_new_velocity<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(batch, max_planes, dpl, nullptr, dcnt, dgoal, ctx->prm.lp_radius, dpc, dpr, dnew, nullptr);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(newV, dnew, sizeof(double) * 3 * batch, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_agent_update(lqro_ctx* ctx, int n, float* pos, float* vel, const float* newVel, float dt) {
+  if (!ctx || n < 1 || !pos || !vel || !newVel) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t n3 = 3 * (size_t)n;
+  int rc = ensure_scratch(ctx, sizeof(float) * 3 * n3);
+  if (rc) return rc;
+  float* dp = (float*)ctx->d_scratch; float* dv = dp + n3; float* dn = dv + n3;
+  CU(cudaMemcpyAsync(dp, pos, sizeof(float) * n3, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dn, newVel, sizeof(float) * n3, cudaMemcpyHostToDevice, ctx->stream));
+  k_agent_update<<<(int)((n3 + 255) / 256), 256, 0, ctx->stream>>>((int)n3, dp, dv, dn, dt);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pos, dp, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(vel, dv, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_round6(lqro_ctx* ctx, const double* in, int n, double* out) {
+  if (!ctx || !in || !out || n < 1) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_scratch(ctx, sizeof(double) * 2 * (size_t)n);
+  if (rc) return rc;
+  double* di = (double*)ctx->d_scratch; double* dout = di + n;
+  CU(cudaMemcpyAsync(di, in, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_round6<<<(n + 255) / 256, 256, 0, ctx->stream>>>(di, n, dout);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------------
+extern "C" int lqro_comm_unique_id(void* id128) {
+  if (!id128) return LQRO_E_ARG;
+  if (!load_nccl()) { g_create_err = "libnccl not found"; return LQRO_E_NCCL; }
+  lqro_ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return LQRO_E_NCCL;
+  memcpy(id128, &id, 128);
+  return LQRO_OK;
+}
+
+extern "C" int lqro_comm_init(lqro_ctx* ctx, int rank, int world, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!load_nccl()) return fail(ctx, LQRO_E_NCCL, "libnccl not found");
+  if ((size_t)ctx->prm.n_local * world != (size_t)ctx->prm.N || ctx->prm.local_begin != rank * ctx->prm.n_local)
+    return fail(ctx, LQRO_E_ARG, "agents must be split in equal contiguous blocks, block r owned by rank r");
+  CU(cudaSetDevice(ctx->cfg.device));
+  lqro_ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  int rc = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
+  if (rc != 0) return fail(ctx, LQRO_E_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank failed");
+  ctx->rank = rank; ctx->world = world;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_device_state(lqro_ctx* ctx, double** d_x) {
+  if (!ctx || !d_x) return LQRO_E_ARG;
+  *d_x = ctx->d_x;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_upload_local_state(lqro_ctx* ctx, const double* x_local) {
+  if (!ctx || !x_local) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaMemcpyAsync(ctx->d_x + 16 * (size_t)ctx->prm.local_begin, x_local, sizeof(double) * 16 * (size_t)ctx->prm.n_local,
+                     cudaMemcpyHostToDevice, ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_allgather_state(lqro_ctx* ctx);
+extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const double* vpref, const int* nbr, double* newV) {
+  if (!ctx || !x_local || !vpref || !newV) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const LqroParams& p = ctx->prm;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->d_x + 16 * (size_t)p.local_begin, x_local, sizeof(double) * 16 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
+  if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  int rc = lqro_allgather_state(ctx);
+  if (rc) return rc;
+  rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_allgather_state(lqro_ctx* ctx) {
+  if (!ctx) return LQRO_E_ARG;
+  if (!ctx->comm) return LQRO_OK;  // single GPU
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t cnt = 16 * (size_t)ctx->prm.n_local;
+  const int ncclFloat64 = 8;
+  int rc = g_nccl.AllGather(ctx->d_x + cnt * ctx->rank, ctx->d_x, cnt, ncclFloat64, ctx->comm, ctx->stream);
+  if (rc != 0) return fail(ctx, LQRO_E_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllGather failed");
+  return LQRO_OK;
+}
+
+// ---- measurement helpers ------------------------------------------------------------------------------
+template <typename T, typename Kern>
+static int measure_peak(lqro_ctx* ctx, Kern kern, double* tflops) {
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  int rc = ensure_scratch(ctx, sizeof(T) * (size_t)blocks * threads);
+  if (rc) return rc;
+  T* d = (T*)ctx->d_scratch;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    kern<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double flop = 2.0 * 8.0 * iters * (double)blocks * threads;
+  *tflops = flop / (best * 1e-3) / 1e12;
+  return LQRO_OK;
+}
+extern "C" int lqro_measure_fp64_peak(lqro_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  return measure_peak<double>(ctx, k_peak_fp64, tflops);
+}
+extern "C" int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  return measure_peak<float>(ctx, k_peak_fp32, tflops);
+}

@@ -1,0 +1,50 @@
+// lqro_common.cuh -- shared definitions of the sm_100a LQR-Obstacles kernels.
+//
+// ARITHMETIC CONTRACT.  The whole library is compiled with -fmad=false: nvcc never contracts a*b+c,
+// so every FP64/FP32 product and sum below is rounded separately, exactly like the reference built
+// for x86-64 SSE2 (no FMA).  That is what makes the discrete decisions of the path (reachable masks,
+// GJK simplex sequences, hull facet sets, LP branches) bit-identical to the CPU.  Double division and
+// sqrt are IEEE-rounded on the device; float division/sqrt are too (-prec-div/-prec-sqrt default true,
+// no --use_fast_math).  Where a kernel wants a fused multiply-add for speed on a path that provably
+// cannot change a decision it calls fma()/fmaf() explicitly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LQRO_XD 16
+#define LQRO_WARP 32
+#define LQRO_FULL 0xffffffffu
+
+// Everything a kernel needs to know about the problem (filled by the host, passed by value).
+struct LqroParams {
+  int N;            // agents visible
+  int local_begin;  // first owned agent
+  int n_local;      // owned agents
+  int K;            // neighbour slots per agent
+  int H;            // horizon samples
+  int P;            // ellipsoid samples
+  int HP;           // H*P
+  double max_speed; // reachable sphere radius
+  double r2;        // max_speed^2 (the reference evaluates pow(xr,2) at run time: xr*xr)
+  double inv_r2;    // 1/r2, only for the conservative fast test
+  float lp_radius;
+  int hull_input;
+  int fix_facet0;
+};
+
+// Device tables of one dynamics class (pair independent, built once by k_horizon_tables):
+//   NFt  [16][3H]  NFt[m][k*3+c] = -(C F_k)(c, m)       (transposed for conflict-free shared loads)
+//   T    [H][9]    (C G_k)^-1, row major
+//   sph  [P][3]    samples of the doubled ellipsoid
+struct LqroTables {
+  const double* NFt;
+  const double* T;
+  const double* sph;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// 3-term dot product in the reference's association: (a0*b0 + a1*b1) + a2*b2   (GJK.h:36-38, MAT:218-231)
+__device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return a0 * b0 + a1 * b1 + a2 * b2;
+}

@@ -1,0 +1,828 @@
+// lqro_hull.cuh -- in-kernel convex hull for the "relative velocity inside the obstacle" case,
+// replacing the reference's qconvex.exe spawn + text files (convexHull MAIN:809-838,
+// convexHullFiles MAIN:762-806) and the 6-significant-digit text rendering of the cloud (MAIN:765-767).
+//
+// WHY IT REPLAYS QHULL'S ORDER.  The reference measures the escape distance of facet f from the FIRST
+// vertex qhull lists for f (MAIN:799-802), taken from the un-rounded cloud while the normal comes from
+// the 6-digit cloud: different vertices of one facet give distances differing by ~1e-5 relative, and
+// ties/argmin follow qhull's facet order.  Both orders are artefacts of Quickhull's processing order
+// (a facet lists its vertices by decreasing creation id, so the first one is the apex it was built
+// from; facets are listed in creation order).  To agree with the reference to 1e-9 this kernel is a
+// GPU Quickhull that processes points in qhull's order: same initial simplex (qh_maxsimplex), same
+// first-fit partition (qh_partitionall), FIFO furthest-point processing (qh_nextfurthest), breadth-
+// first visible set (qh_findhorizon), cone facets in visible/neighbour order (qh_makenew_simplicial)
+// and the directed-walk partition of qh_findbest / qh_findbestnew.  Restated from qhull's published
+// algorithm; checked facet-for-facet against oracle/hull_cpu.cpp (itself pinned on the reference's
+// fixture and on scipy/qhull).  Merging / coplanar handling is not restated: such inputs raise the
+// degenerate flag.
+//
+// Mapping: one warp per hull.  O(points) work -- plane distances during partition, extreme-point
+// scans, the final nearest-facet scan -- is spread over the lanes; the list surgery that defines the
+// order is done by lane 0.  The un-rounded cloud stays in shared memory, the rounded cloud, the facet
+// pool and the outside lists live in a per-warp global workspace (L1/L2 resident).
+#pragma once
+#include "lqro_common.cuh"
+#include "lqro_pair.cuh"
+
+#define LQRO_HULL_MAXNEW 256  // cone facets per insertion handled by the per-lane visited bit set
+
+// ---- strtod(printf("%g", x)): nearest double to the 6-significant-digit decimal rendering of x ------
+__device__ inline double pow10_exact(int k) {  // 10^k, exact for 0 <= k <= 22
+  const double t[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                        1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  return t[k];
+}
+// value of |x| * 10^s as an unevaluated sum hi + lo (exact when 10^|s| is exact and the quotient case
+// is avoided; for s < 0 the quotient is correctly rounded and lo carries the exact remainder sign)
+__device__ inline void scale10(double ax, int s, double& hi, double& lo) {
+  if (s >= 0) {
+    double p = (s <= 22) ? pow10_exact(s) : pow10_exact(22);
+    hi = ax * p;
+    lo = fma(ax, p, -hi);
+    int rest = s - 22;
+    while (rest > 0) {  // |x| < 1e-17: beyond exact powers, double-double product (error ~1e-32 relative)
+      const int st = rest > 22 ? 22 : rest;
+      const double p2 = pow10_exact(st);
+      const double h2 = hi * p2;
+      const double l2 = fma(hi, p2, -h2) + lo * p2;
+      hi = h2 + l2;
+      lo = l2 - (hi - h2);
+      rest -= st;
+    }
+  } else {
+    const double p = pow10_exact(-s > 22 ? 22 : -s);
+    hi = ax / p;
+    lo = -fma(hi, p, -ax) / p;  // remainder (ax - hi*p) / p, sign-exact
+  }
+}
+__device__ inline double round6_dev(double x) {
+  if (x == 0.0 || !(fabs(x) < 1.7976931348623157e308)) return x;
+  const double ax = fabs(x);
+  int e2;
+  frexp(ax, &e2);
+  int e = (int)floor((e2 - 1) * 0.30102999566398120);  // floor(log10) estimate, off by at most one
+  double hi, lo;
+  for (int it = 0; it < 3; ++it) {
+    scale10(ax, 5 - e, hi, lo);
+    if (hi < 100000.0 || (hi == 100000.0 && lo < 0.0)) { --e; continue; }
+    if (hi > 1000000.0 || (hi == 1000000.0 && lo >= 0.0)) { ++e; continue; }
+    break;
+  }
+  // round hi + lo to the nearest integer, ties to even (printf rounds the exact binary value)
+  double r = rint(hi);
+  const double diff = (hi - r) + lo;  // exact: |hi - r| <= 0.5 and lo is tiny
+  if (diff > 0.5 || (diff == 0.5 && fmod(r, 2.0) != 0.0)) r += 1.0;
+  else if (diff < -0.5 || (diff == -0.5 && fmod(r, 2.0) != 0.0)) r -= 1.0;
+  const int s = 5 - e;
+  double v;
+  if (s >= 0) {
+    if (s <= 22) v = r / pow10_exact(s);  // both exact -> correctly rounded quotient == strtod
+    else { v = r / pow10_exact(22); int rest = s - 22; while (rest > 0) { const int st = rest > 22 ? 22 : rest; v /= pow10_exact(st); rest -= st; } }
+  } else {
+    v = r * pow10_exact(-s > 22 ? 22 : -s);  // exact product for |x| < 1e20
+  }
+  return x < 0 ? -v : v;
+}
+
+__global__ void k_round6(const double* __restrict__ in, int n, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = round6_dev(in[t]);
+}
+
+// ---- workspace ---------------------------------------------------------------------------------
+struct HFacet {
+  double n[3], off;
+  double furthestdist;
+  int v[3];    // vertex ids, decreasing
+  int nb[3];   // neighbour opposite v[i]
+  int prev, next;
+  int ohead, olast, oprev;  // outside list (furthest last)
+  int tag;     // scratch: BFS visit id / cone-local index
+  int replace;
+  unsigned char toporient, visible, isnew, pad;
+};
+
+struct HullWs {
+  double *hx, *hy, *hz;  // hull input coordinates [cap_pts]
+  double* pdist;         // [cap_pts]
+  int *pnext, *pbest, *plist, *pstart, *vpoint;  // [cap_pts] (+8 for vpoint)
+  HFacet* F;             // [cap_f]; F[0] is the list sentinel
+  int *order, *newf, *vis, *freel;  // [cap_f]
+  int cap_pts, cap_f;
+};
+
+__host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
+  const size_t cap_f = 2 * (size_t)cap_pts + 64;
+  size_t b = 0;
+  b += 4 * sizeof(double) * (size_t)cap_pts;        // hx hy hz pdist
+  b += 5 * sizeof(int) * ((size_t)cap_pts + 8);      // pnext pbest plist pstart vpoint
+  b = (b + 15) & ~(size_t)15;
+  b += sizeof(HFacet) * cap_f;
+  b += 4 * sizeof(int) * cap_f;                      // order newf vis freel
+  return (b + 255) & ~(size_t)255;
+}
+__device__ inline void hull_ws_carve(char* base, int cap_pts, HullWs& w) {
+  const size_t cap_f = 2 * (size_t)cap_pts + 64;
+  w.cap_pts = cap_pts; w.cap_f = (int)cap_f;
+  double* d = reinterpret_cast<double*>(base);
+  w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts; w.pdist = d + 3 * (size_t)cap_pts;
+  int* ip = reinterpret_cast<int*>(d + 4 * (size_t)cap_pts);
+  const size_t ci = (size_t)cap_pts + 8;
+  w.pnext = ip; w.pbest = ip + ci; w.plist = ip + 2 * ci; w.pstart = ip + 3 * ci; w.vpoint = ip + 4 * ci;
+  size_t off = 4 * sizeof(double) * (size_t)cap_pts + 5 * sizeof(int) * ci;
+  off = (off + 15) & ~(size_t)15;
+  w.F = reinterpret_cast<HFacet*>(base + off);
+  int* jp = reinterpret_cast<int*>(base + off + sizeof(HFacet) * cap_f);
+  w.order = jp; w.newf = jp + cap_f; w.vis = jp + 2 * cap_f; w.freel = jp + 3 * cap_f;
+}
+
+// per-warp control block in shared memory (written by lane 0, read by all after __syncwarp)
+struct HullCtl {
+  double DISTround, MINvisible, MINoutside, MAXcoplanar, NEARzero1, NEARzero2;
+  double interior[3];
+  double apex[3];
+  int facet_list, facet_next, newfacet_list;
+  int nfree, pool_used, nverts;
+  int nvis, nnew, nlist;
+  int degenerate, fail;
+  int sharp, trigger_pos;
+  int nfacets_out;
+  int ninserted;
+  int maxpoints[6];
+  int simplex[4];
+};
+
+__device__ __forceinline__ double hdist(const HFacet& f, double x, double y, double z) {  // qh_distplane
+  return f.off + x * f.n[0] + y * f.n[1] + z * f.n[2];
+}
+__device__ __forceinline__ double hull_distoutside(const HullCtl& c) { return 2 * c.MINoutside; }  // qh_DISToutside, max_outside = 0
+__device__ __forceinline__ double hull_searchdist(const HullCtl& c) {
+  return 2 * c.DISTround + (c.MINvisible > c.MAXcoplanar ? c.MINvisible : c.MAXcoplanar);
+}
+
+// list surgery (lane 0): qh_appendfacet / qh_removefacet
+__device__ inline void hl_append(HullWs& w, HullCtl& c, int f) {
+  const int tail = 0;
+  if (tail == c.newfacet_list) c.newfacet_list = f;
+  if (tail == c.facet_next) c.facet_next = f;
+  w.F[f].prev = w.F[tail].prev;
+  w.F[f].next = tail;
+  if (w.F[tail].prev >= 0) w.F[w.F[tail].prev].next = f; else c.facet_list = f;
+  w.F[tail].prev = f;
+}
+__device__ inline void hl_remove(HullWs& w, HullCtl& c, int f) {
+  const int nx = w.F[f].next, pv = w.F[f].prev;
+  if (f == c.newfacet_list) c.newfacet_list = nx;
+  if (f == c.facet_next) c.facet_next = nx;
+  if (pv >= 0) { w.F[pv].next = nx; w.F[nx].prev = pv; }
+  else { c.facet_list = nx; w.F[nx].prev = -1; }
+}
+__device__ inline int hl_newfacet(HullWs& w, HullCtl& c) {
+  int f;
+  if (c.nfree > 0) f = w.freel[--c.nfree];
+  else if (c.pool_used < w.cap_f) f = c.pool_used++;
+  else { c.fail = 1; return -1; }
+  HFacet& F = w.F[f];
+  F.prev = F.next = -1; F.ohead = F.olast = F.oprev = -1; F.furthestdist = 0; F.tag = 0; F.replace = -1;
+  F.toporient = F.visible = F.isnew = 0;
+  return f;
+}
+// outside-list append with qhull's "furthest stays last" rule (qh_partitionpoint)
+__device__ inline void hl_outside_add(HullWs& w, int f, int p, double d) {
+  HFacet& F = w.F[f];
+  if (F.olast < 0) { F.ohead = F.olast = p; F.oprev = -1; w.pnext[p] = -1; F.furthestdist = d; }
+  else if (F.furthestdist < d) { w.pnext[F.olast] = p; F.oprev = F.olast; F.olast = p; w.pnext[p] = -1; F.furthestdist = d; }
+  else {  // qh_setappend2ndlast
+    if (F.oprev >= 0) w.pnext[F.oprev] = p; else F.ohead = p;
+    w.pnext[p] = F.olast; F.oprev = p;
+  }
+}
+
+// qh_setfacetplane -> qh_sethyperplane_det (3-d) + qh_normalize2
+__device__ inline void hull_setplane(HullWs& w, int fi) {
+  HFacet& f = w.F[fi];
+  const int a = w.vpoint[f.v[0]], b = w.vpoint[f.v[1]], c = w.vpoint[f.v[2]];
+  const double p0x = w.hx[a], p0y = w.hy[a], p0z = w.hz[a];
+  const double dX1 = w.hx[b] - p0x, dY1 = w.hy[b] - p0y, dZ1 = w.hz[b] - p0z;
+  const double dX2 = w.hx[c] - p0x, dY2 = w.hy[c] - p0y, dZ2 = w.hz[c] - p0z;
+  const double n0 = dY2 * dZ1 - dZ2 * dY1;
+  const double n1 = dX1 * dZ2 - dZ1 * dX2;
+  const double n2 = dX2 * dY1 - dY2 * dX1;
+  double norm = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+  if (!f.toporient) norm = -norm;
+  f.n[0] = n0 / norm; f.n[1] = n1 / norm; f.n[2] = n2 / norm;
+  f.off = -(p0x * f.n[0] + p0y * f.n[1] + p0z * f.n[2]);
+}
+
+__device__ inline double hdet2(double a1, double a2, double b1, double b2) { return a1 * b2 - a2 * b1; }
+__device__ inline double hdet3(double a1, double a2, double a3, double b1, double b2, double b3, double c1, double c2, double c3) {
+  return a1 * hdet2(b2, b3, c2, c3) - b1 * hdet2(a2, a3, c2, c3) + c1 * hdet2(a2, a3, b2, b3);
+}
+// qh_detsimplex on the first k coordinates (k = current simplex size)
+__device__ inline double hull_detsimplex(const HullWs& w, const HullCtl& c, int apex, const int* simplex, int k, bool* nearzero) {
+  const double ax = w.hx[apex], ay = w.hy[apex], az = w.hz[apex];
+  double r[3][3];
+  for (int i = 0; i < k; ++i) {
+    const int p = simplex[i];
+    r[i][0] = w.hx[p] - ax; r[i][1] = w.hy[p] - ay; r[i][2] = w.hz[p] - az;
+  }
+  double det;
+  if (k == 2) { det = hdet2(r[0][0], r[0][1], r[1][0], r[1][1]); *nearzero = fabs(det) < c.NEARzero1; }
+  else { det = hdet3(r[0][0], r[0][1], r[0][2], r[1][0], r[1][1], r[1][2], r[2][0], r[2][1], r[2][2]); *nearzero = fabs(det) < c.NEARzero2; }
+  return det;
+}
+
+// qh_findbesthorizon restricted to what can change a non-degenerate outcome: hill-climb over the
+// neighbours (new or old) of the best facet while one is strictly better (band = SEARCHdist).
+__device__ inline int hull_findbesthorizon(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* bestdist,
+                                           int* degenerate) {
+  int seen[24];
+  int nseen = 0, best = start;
+  int stack[24];
+  int nstack = 0;
+  const double searchdist = hull_searchdist(c);
+  double minsearch = *bestdist - searchdist;
+  seen[nseen++] = start;
+  int facet = start;
+  while (true) {
+    const HFacet& F = w.F[facet];
+    int nextfacet = -1;
+    for (int k = 0; k < 3; ++k) {
+      const int nb = F.nb[k];
+      bool was = false;
+      for (int q = 0; q < nseen; ++q) if (seen[q] == nb) was = true;
+      if (was) continue;
+      if (nseen < 24) seen[nseen++] = nb; else { *degenerate = 1; return best; }
+      const double d = hdist(w.F[nb], x, y, z);
+      if (d > *bestdist) {
+        best = nb;
+        if (d > *bestdist + searchdist) nstack = 0;
+        *bestdist = d;
+        minsearch = d - searchdist;
+      } else if (d < minsearch) continue;
+      if (nextfacet >= 0) { if (nstack < 24) stack[nstack++] = nextfacet; else { *degenerate = 1; return best; } }
+      nextfacet = nb;
+    }
+    facet = nextfacet;
+    if (facet >= 0) continue;
+    if (nstack == 0) break;
+    facet = stack[--nstack];
+  }
+  return best;
+}
+
+// qh_findbestnew: exhaustive over the cone facets (list order == newf[] order), cyclically from `start`
+__device__ inline int hull_findbestnew(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+                                       bool* isoutside, int* degenerate) {
+  double bestdist = -8.9884656743115785e307;
+  int best = -1;
+  const double distoutside = hull_distoutside(c);
+  const int m = c.nnew;
+  const int s0 = w.F[start].isnew ? w.F[start].tag : 0;
+  for (int q = 0; q < m; ++q) {
+    int idx = s0 + q; if (idx >= m) idx -= m;
+    const int f = w.newf[idx];
+    const double d = hdist(w.F[f], x, y, z);
+    if (d > bestdist) {
+      best = f;
+      if (d >= distoutside) { *dist = d; *isoutside = true; return best; }
+      bestdist = d;
+    }
+  }
+  best = hull_findbesthorizon(w, c, x, y, z, best >= 0 ? best : start, &bestdist, degenerate);
+  *dist = bestdist;
+  *isoutside = !(bestdist < c.MINoutside);
+  return best;
+}
+
+// qh_findbest(point, start, !bestoutside, isnewfacets): directed walk over the cone facets.
+// trigger: the walk ended below -DISTround (the caller applies qhull's sharp-cone rule).
+__device__ inline int hull_findbest_walk(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+                                         bool* isoutside, bool* trigger, int* degenerate) {
+  unsigned long long vm[LQRO_HULL_MAXNEW / 64];
+#pragma unroll
+  for (int q = 0; q < LQRO_HULL_MAXNEW / 64; ++q) vm[q] = 0ull;
+  *trigger = false;
+  *isoutside = true;
+  double d = hdist(w.F[start], x, y, z);
+  if (d >= c.MINoutside) { *dist = d; return start; }
+  double bestdist = d;
+  int best = start;
+  { const int t = w.F[start].tag; vm[t >> 6] |= 1ull << (t & 63); }
+  int facet = start;
+  while (facet >= 0) {
+    const HFacet& F = w.F[facet];
+    int nextf = -1;
+    for (int k = 0; k < 3; ++k) {
+      const int nb = F.nb[k];
+      const HFacet& NB = w.F[nb];
+      if (!NB.isnew) continue;
+      const int t = NB.tag;
+      if (vm[t >> 6] & (1ull << (t & 63))) continue;
+      vm[t >> 6] |= 1ull << (t & 63);
+      d = hdist(NB, x, y, z);
+      if (d > bestdist) {
+        if (d >= c.MINoutside) { *dist = d; return nb; }
+        best = nb; bestdist = d; nextf = nb;
+        break;
+      }
+    }
+    facet = nextf;
+  }
+  *dist = bestdist;
+  if (bestdist < -c.DISTround) { *trigger = true; return best; }  // caller decides (sharp / not sharp)
+  best = hull_findbesthorizon(w, c, x, y, z, best, &bestdist, degenerate);
+  *dist = bestdist;
+  *isoutside = !(bestdist < c.MINoutside);
+  return best;
+}
+
+// Build the hull of the n points in w.hx/hy/hz.  On return (all lanes): c.fail / c.degenerate set,
+// w.order[0..c.nfacets_out) = facets in qhull list order.
+__device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
+  const int lane = lane_id();
+  if (lane == 0) {
+    c.degenerate = 0; c.fail = 0; c.nfree = 0; c.pool_used = 1; c.nverts = 0; c.ninserted = 0; c.nfacets_out = 0;
+    c.facet_list = 0; c.facet_next = 0; c.newfacet_list = -1;
+    w.F[0].prev = -1; w.F[0].next = -1; w.F[0].isnew = 0; w.F[0].visible = 0;
+    if (n < 4 || n > w.cap_pts) c.fail = 1;
+  }
+  __syncwarp();
+  if (c.fail) return;
+  // ---- qh_maxmin: first index attaining the max / min of each coordinate
+  double mxv[3], mnv[3];
+  int mxi[3], mni[3];
+  for (int k = 0; k < 3; ++k) { mxv[k] = -1.7976931348623157e308; mnv[k] = 1.7976931348623157e308; mxi[k] = mni[k] = 0x7fffffff; }
+  for (int i = lane; i < n; i += 32) {
+    const double v[3] = {w.hx[i], w.hy[i], w.hz[i]};
+    for (int k = 0; k < 3; ++k) {
+      if (v[k] > mxv[k]) { mxv[k] = v[k]; mxi[k] = i; }
+      if (v[k] < mnv[k]) { mnv[k] = v[k]; mni[k] = i; }
+    }
+  }
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double ov = __shfl_xor_sync(LQRO_FULL, mxv[k], off); int oi = __shfl_xor_sync(LQRO_FULL, mxi[k], off);
+      if (ov > mxv[k] || (ov == mxv[k] && oi < mxi[k])) { mxv[k] = ov; mxi[k] = oi; }
+      ov = __shfl_xor_sync(LQRO_FULL, mnv[k], off); oi = __shfl_xor_sync(LQRO_FULL, mni[k], off);
+      if (ov < mnv[k] || (ov == mnv[k] && oi < mni[k])) { mnv[k] = ov; mni[k] = oi; }
+    }
+  }
+  if (lane == 0) {
+    // round-off constants: qh_maxmin, qh_distround, qh_detroundoff with 'C-0' pre-merging defaults
+    double MAXabs = 0, MAXsum = 0;
+    for (int k = 0; k < 3; ++k) {
+      const double maxcoord = mxv[k] > -mnv[k] ? mxv[k] : -mnv[k];
+      if (maxcoord > MAXabs) MAXabs = maxcoord;
+      MAXsum += maxcoord;
+      c.maxpoints[2 * k] = mxi[k]; c.maxpoints[2 * k + 1] = mni[k];
+      if (k == 1) c.NEARzero1 = 80 * MAXsum * 2.220446049250313e-16;
+      if (k == 2) c.NEARzero2 = 80 * MAXsum * 2.220446049250313e-16;
+    }
+    double maxdistsum = sqrt(3.0) * MAXabs;
+    if (MAXsum < maxdistsum) maxdistsum = MAXsum;
+    c.DISTround = 2.220446049250313e-16 * (3 * maxdistsum * 1.01 + MAXabs);
+    c.MINvisible = 2 * c.DISTround;
+    c.MAXcoplanar = c.MINvisible;
+    c.MINoutside = 2 * c.MINvisible;
+    // ---- qh_maxsimplex over the extreme points
+    int ns = 0;
+    {
+      double maxc = -1.7976931348623157e308, minc = 1.7976931348623157e308; int maxx = -1, minx = -1;
+      for (int i = 0; i < 6; ++i) {
+        const double px = w.hx[c.maxpoints[i]];
+        if (maxc < px) { maxc = px; maxx = c.maxpoints[i]; }
+        if (minc > px) { minc = px; minx = c.maxpoints[i]; }
+      }
+      c.simplex[ns++] = minx;
+      if (maxx != minx) c.simplex[ns++] = maxx;
+      if (ns < 2) c.fail = 1;
+    }
+    for (int k = ns; k < 4 && !c.fail; ++k) {
+      int maxpoint = -1; double maxdet = -1.7976931348623157e308; bool maxnz = false;
+      for (int i = 0; i < 6; ++i) {
+        const int p = c.maxpoints[i];
+        bool in = false;
+        for (int s = 0; s < k; ++s) if (c.simplex[s] == p) in = true;
+        if (in) continue;
+        bool nz; const double det = fabs(hull_detsimplex(w, c, p, c.simplex, k, &nz));
+        if (det > maxdet) { maxdet = det; maxpoint = p; maxnz = nz; }
+      }
+      if (maxpoint < 0 || maxnz) {  // qhull searches all points (rare: flat extreme set)
+        for (int p = 0; p < n; ++p) {
+          bool in = false;
+          for (int s = 0; s < k; ++s) if (c.simplex[s] == p) in = true;
+          if (in) continue;
+          bool nz; const double det = fabs(hull_detsimplex(w, c, p, c.simplex, k, &nz));
+          if (det > maxdet) { maxdet = det; maxpoint = p; maxnz = nz; }
+        }
+      }
+      if (maxpoint < 0 || maxnz) { c.fail = 1; break; }
+      c.simplex[k] = maxpoint;
+    }
+    if (!c.fail) {
+      // ---- qh_initialvertices / qh_createsimplex / qh_initialhull
+      for (int i = 0; i < 4; ++i) w.vpoint[i] = c.simplex[i];
+      c.nverts = 4;
+      const int vd[4] = {3, 2, 1, 0};
+      int fid[4];
+      bool top = true;
+      for (int i = 0; i < 4; ++i) {
+        const int f = hl_newfacet(w, c); fid[i] = f;
+        int q = 0;
+        for (int j = 0; j < 4; ++j) if (j != i) w.F[f].v[q++] = vd[j];
+        w.F[f].toporient = top ? 1 : 0;
+        hl_append(w, c, f);
+        top = !top;
+      }
+      for (int i = 0; i < 4; ++i) { int q = 0; for (int j = 0; j < 4; ++j) if (j != i) w.F[fid[i]].nb[q++] = fid[j]; }
+      c.facet_next = c.facet_list;
+      for (int k = 0; k < 3; ++k) {
+        double s = 0;
+        for (int j = 0; j < 4; ++j) { const int p = w.vpoint[vd[j]]; s += (k == 0 ? w.hx[p] : (k == 1 ? w.hy[p] : w.hz[p])); }
+        c.interior[k] = s / 4;
+      }
+      hull_setplane(w, fid[0]);
+      if (hdist(w.F[fid[0]], c.interior[0], c.interior[1], c.interior[2]) > 0)
+        for (int i = 0; i < 4; ++i) w.F[fid[i]].toporient ^= 1;
+      for (int i = 0; i < 4; ++i) hull_setplane(w, fid[i]);
+      for (int i = 0; i < 4; ++i)
+        if (!(hdist(w.F[fid[i]], c.interior[0], c.interior[1], c.interior[2]) < -c.DISTround)) c.degenerate = 1;
+      c.simplex[0] = fid[0]; c.simplex[1] = fid[1]; c.simplex[2] = fid[2]; c.simplex[3] = fid[3];  // reuse: initial facet ids
+    }
+  }
+  __syncwarp();
+  if (c.fail) return;
+  // ---- qh_partitionall: first facet (list order) a point is outside of; distances in parallel
+  {
+    const double distoutside = hull_distoutside(c);
+    const int v0 = w.vpoint[0], v1 = w.vpoint[1], v2 = w.vpoint[2], v3 = w.vpoint[3];
+    int deg = 0;
+    for (int i = lane; i < n; i += 32) {
+      int bestf = -1; double bd = 0;
+      if (i != v0 && i != v1 && i != v2 && i != v3) {
+        const double x = w.hx[i], y = w.hy[i], z = w.hz[i];
+        for (int q = 0; q < 4; ++q) {
+          const double d = hdist(w.F[c.simplex[q]], x, y, z);
+          if (fabs(d) < 2 * distoutside) deg = 1;
+          if (d >= distoutside) { bestf = c.simplex[q]; bd = d; break; }
+        }
+      }
+      w.pbest[i] = bestf; w.pdist[i] = bd;
+    }
+    deg = __any_sync(LQRO_FULL, deg);
+    __syncwarp();
+    if (lane == 0) {
+      if (deg) c.degenerate = 1;
+      // build each facet's list: points in index order, every record placed at the end of its reign
+      for (int q = 0; q < 4; ++q) {
+        const int f = c.simplex[q];
+        int bestpoint = -1; double bestdist = 0;
+        HFacet& F = w.F[f];
+        int tail = -1;
+        for (int i = 0; i < n; ++i) {
+          if (w.pbest[i] != f) continue;
+          const double d = w.pdist[i];
+          int emit = -1;
+          if (bestpoint < 0) { bestpoint = i; bestdist = d; }
+          else if (d > bestdist) { emit = bestpoint; bestpoint = i; bestdist = d; }
+          else emit = i;
+          if (emit >= 0) { if (tail < 0) F.ohead = emit; else w.pnext[tail] = emit; tail = emit; }
+        }
+        if (bestpoint >= 0) {
+          if (tail < 0) F.ohead = bestpoint; else w.pnext[tail] = bestpoint;
+          F.oprev = tail; F.olast = bestpoint; w.pnext[bestpoint] = -1; F.furthestdist = bestdist;
+        }
+      }
+      // ---- qh_furthestnext: facet with the furthest outside point moves to the front
+      int bestfacet = -1; double bestdist = -1.7976931348623157e308;
+      for (int f = c.facet_list; f != 0; f = w.F[f].next)
+        if (w.F[f].olast >= 0 && w.F[f].furthestdist > bestdist) { bestfacet = f; bestdist = w.F[f].furthestdist; }
+      if (bestfacet >= 0 && bestfacet != c.facet_list) {
+        hl_remove(w, c, bestfacet);
+        const int head = c.facet_list;
+        w.F[bestfacet].prev = -1; w.F[bestfacet].next = head; w.F[head].prev = bestfacet;
+        c.facet_list = bestfacet;
+      }
+      c.facet_next = c.facet_list;
+    }
+    __syncwarp();
+  }
+  // ---- qh_buildhull
+  while (true) {
+    if (lane == 0) {
+      // qh_nextfurthest
+      int facet;
+      while ((facet = c.facet_next) != 0) {
+        if (w.F[facet].olast < 0) { c.facet_next = w.F[facet].next; continue; }
+        break;
+      }
+      c.nvis = 0; c.nnew = 0; c.nlist = 0;
+      if (facet != 0) {
+        HFacet& F0 = w.F[facet];
+        const int furthest = F0.olast;
+        if (F0.oprev >= 0) { w.pnext[F0.oprev] = -1; F0.olast = F0.oprev; } else { F0.ohead = -1; F0.olast = -1; }
+        ++c.ninserted;
+        const double ax = w.hx[furthest], ay = w.hy[furthest], az = w.hz[furthest];
+        c.apex[0] = ax; c.apex[1] = ay; c.apex[2] = az;
+        // qh_findhorizon: breadth-first over neighbours, visible facets move to the list end
+        hl_remove(w, c, facet); hl_append(w, c, facet);
+        F0.visible = 1; F0.replace = -1;
+        const int vid = c.ninserted;  // unique per insertion (tags of live facets are <= earlier ids or cone indices reset below)
+        w.vis[c.nvis++] = facet;
+        F0.tag = -vid;
+        for (int vi = 0; vi < c.nvis; ++vi) {
+          const int vf = w.vis[vi];
+          for (int k = 0; k < 3; ++k) {
+            const int nb = w.F[vf].nb[k];
+            HFacet& NB = w.F[nb];
+            if (NB.tag == -vid) continue;
+            NB.tag = -vid;
+            const double d = hdist(NB, ax, ay, az);
+            if (d > c.MINvisible) {
+              hl_remove(w, c, nb); hl_append(w, c, nb);
+              NB.visible = 1; NB.replace = -1;
+              w.vis[c.nvis++] = nb;
+            } else if (d > -c.MAXcoplanar) c.degenerate = 1;  // coplanar horizon: qhull would merge
+          }
+        }
+        // qh_makenewfacets / qh_makenew_simplicial
+        c.newfacet_list = 0;
+        const int apex = c.nverts;
+        w.vpoint[c.nverts++] = furthest;
+        for (int vi = 0; vi < c.nvis && !c.fail; ++vi) {
+          const int vf = w.vis[vi];
+          int last_new = -1;
+          for (int k = 0; k < 3; ++k) {
+            const int nb = w.F[vf].nb[k];
+            if (w.F[nb].visible) continue;
+            int horizonskip = -1;
+            for (int q = 0; q < 3; ++q) if (w.F[nb].nb[q] == vf) { horizonskip = q; break; }
+            const int nf = hl_newfacet(w, c);
+            if (nf < 0 || horizonskip < 0 || c.nnew >= LQRO_HULL_MAXNEW) { c.fail = 1; break; }
+            HFacet& HZ = w.F[nb];
+            HFacet& NF = w.F[nf];
+            NF.v[0] = apex;
+            int q2 = 1;
+            for (int q = 0; q < 3; ++q) if (q != horizonskip) NF.v[q2++] = HZ.v[q];
+            NF.toporient = HZ.toporient ? (horizonskip & 1) : ((horizonskip & 1) ^ 1);
+            NF.nb[0] = nb; NF.nb[1] = NF.nb[2] = -1;
+            NF.isnew = 1;
+            NF.tag = c.nnew;  // cone-local index
+            hl_append(w, c, nf);
+            HZ.nb[horizonskip] = nf;
+            w.newf[c.nnew++] = nf;
+            last_new = nf;
+          }
+          if (last_new >= 0) w.F[vf].replace = last_new;
+        }
+      } else {
+        c.nvis = -1;  // done
+      }
+    }
+    __syncwarp();
+    if (c.nvis < 0 || c.fail) break;
+    const int nnew = c.nnew;
+    // qh_makenewplanes + qh_matchnewfacets (lane per cone facet)
+    for (int q = lane; q < nnew; q += 32) hull_setplane(w, w.newf[q]);
+    __syncwarp();
+    int deg = 0;
+    for (int q = lane; q < nnew; q += 32) {
+      HFacet& fa = w.F[w.newf[q]];
+      if (!(hdist(fa, c.interior[0], c.interior[1], c.interior[2]) < 0)) deg = 1;
+      for (int s = 1; s <= 2; ++s) {
+        const int wv = fa.v[3 - s];  // the neighbour opposite v[s] shares the ridge {apex, v[3-s]}
+        int found = -1;
+        for (int b = 0; b < nnew; ++b) {
+          if (b == q) continue;
+          const HFacet& fb = w.F[w.newf[b]];
+          if (fb.v[1] == wv || fb.v[2] == wv) { found = w.newf[b]; break; }
+        }
+        if (found < 0) deg = 2;
+        fa.nb[s] = found;
+      }
+    }
+    deg = __reduce_max_sync(LQRO_FULL, deg);
+    __syncwarp();
+    if (lane == 0) {
+      if (deg == 1) c.degenerate = 1;
+      if (deg == 2) c.fail = 1;
+      // qh_sharpnewfacets
+      c.sharp = 0;
+      if (nnew > 0) {
+        const HFacet& f0 = w.F[w.newf[0]];
+        const bool q0 = f0.n[0] > 0, q1 = f0.n[1] > 0, q2 = f0.n[2] > 0;
+        for (int q = 1; q < nnew && !c.sharp; ++q) {
+          const HFacet& f = w.F[w.newf[q]];
+          if (q0 != (f.n[0] > 0) || q1 != (f.n[1] > 0) || q2 != (f.n[2] > 0)) c.sharp = 1;
+        }
+      }
+      // qh_partitionvisible, pass 1: the points to re-partition in qhull's processing order
+      int nl = 0;
+      for (int vi = 0; vi < c.nvis; ++vi) {
+        HFacet& VF = w.F[w.vis[vi]];
+        const int start = VF.replace >= 0 ? VF.replace : c.newfacet_list;
+        for (int p = VF.ohead; p >= 0; p = w.pnext[p]) { w.plist[nl] = p; w.pstart[nl] = start; ++nl; }
+        VF.ohead = VF.olast = VF.oprev = -1;
+      }
+      c.nlist = nl;
+      c.trigger_pos = 0x7fffffff;
+    }
+    __syncwarp();
+    if (c.fail) break;
+    const int nl = c.nlist;
+    if (nl > 0 && nnew > 0) {
+      // pass 2 (parallel): directed walk of every point.  w.pnext[p] is free while p is off every
+      // list: it carries the "walk ended below -DISTround" mark.
+      int mytrig = 0x7fffffff, ldeg = 0;
+      for (int q = lane; q < nl; q += 32) {
+        const int p = w.plist[q];
+        double d; bool outside, trig;
+        const int best = hull_findbest_walk(w, c, w.hx[p], w.hy[p], w.hz[p], w.pstart[q], &d, &outside, &trig, &ldeg);
+        if (trig) outside = false;
+        w.pbest[q] = outside ? best : -1 - best;  // negative: not (yet) outside
+        w.pdist[q] = d;
+        w.pnext[p] = trig ? 1 : 0;
+        if (trig && q < mytrig) mytrig = q;
+      }
+      mytrig = (int)__reduce_min_sync(LQRO_FULL, (unsigned)mytrig);
+      __syncwarp();
+      // pass 3 (parallel): walks that ended below -DISTround.  Sharp cone: from the first such point on
+      // (processing order) qhull switches to the exhaustive search (qh.findbestnew stays set for the
+      // rest of this partition); otherwise each such walk finishes with its horizon test.
+      if (mytrig != 0x7fffffff) {
+        for (int q = lane; q < nl; q += 32) {
+          const int p = w.plist[q];
+          const double x = w.hx[p], y = w.hy[p], z = w.hz[p];
+          double d = w.pdist[q]; bool outside;
+          int best;
+          if (c.sharp) {
+            if (q < mytrig) continue;
+            int start = w.pstart[q];
+            if (q == mytrig) start = -1 - w.pbest[q];
+            best = hull_findbestnew(w, c, x, y, z, start, &d, &outside, &ldeg);
+          } else {
+            if (!w.pnext[p]) continue;
+            best = hull_findbesthorizon(w, c, x, y, z, -1 - w.pbest[q], &d, &ldeg);
+            outside = !(d < c.MINoutside);
+          }
+          w.pbest[q] = outside ? best : -1 - best;
+          w.pdist[q] = d;
+        }
+      }
+      ldeg = __any_sync(LQRO_FULL, ldeg);
+      __syncwarp();
+      if (lane == 0) {
+        if (ldeg) c.degenerate = 1;
+        // pass 4: append in processing order (qh_partitionpoint)
+        for (int q = 0; q < nl; ++q) {
+          const int b = w.pbest[q];
+          const double d = w.pdist[q];
+          if (fabs(d) < 4 * c.MINoutside) c.degenerate = 1;
+          if (b < 0) continue;  // inside / coplanar: dropped
+          const bool wasempty = w.F[b].olast < 0;
+          hl_outside_add(w, b, w.plist[q], d);
+          if (wasempty && !w.F[b].isnew) { hl_remove(w, c, b); hl_append(w, c, b); }
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      // qh_deletevisible + qh_resetlists
+      for (int vi = 0; vi < c.nvis; ++vi) {
+        const int vf = w.vis[vi];
+        hl_remove(w, c, vf);
+        w.F[vf].visible = 0; w.F[vf].isnew = 0; w.F[vf].tag = 0;
+        w.freel[c.nfree++] = vf;
+      }
+      for (int q = 0; q < c.nnew; ++q) { w.F[w.newf[q]].isnew = 0; w.F[w.newf[q]].tag = 0; }
+      c.newfacet_list = -1;
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && !c.fail) {
+    int nf = 0;
+    for (int f = c.facet_list; f != 0; f = w.F[f].next) w.order[nf++] = f;
+    c.nfacets_out = nf;
+  }
+  __syncwarp();
+}
+
+// Nearest facet to v_rel in qhull's facet order (MAIN:825-837, with normal = facet 0's when it wins):
+// distance_f = |n_f . (v_rel - p_f)|, p_f = first listed vertex of f from the UN-ROUNDED cloud (ux,uy,uz).
+__device__ inline void hull_nearest_facet(const HullWs& w, const HullCtl& c, const double* ux, const double* uy, const double* uz,
+                                          double vr0, double vr1, double vr2, double* distance, double* normal, int* best_facet) {
+  const int lane = lane_id();
+  double bd = 1.7976931348623157e308;
+  int bi = 0x7fffffff;
+  for (int q = lane; q < c.nfacets_out; q += 32) {
+    const HFacet& F = w.F[w.order[q]];
+    const int p = w.vpoint[F.v[0]];
+    const double d = fabs(F.n[0] * (vr0 - ux[p]) + F.n[1] * (vr1 - uy[p]) + F.n[2] * (vr2 - uz[p]));
+    if (d < bd) { bd = d; bi = q; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(LQRO_FULL, bd, off);
+    const int oi = __shfl_xor_sync(LQRO_FULL, bi, off);
+    if (ov < bd || (ov == bd && oi < bi)) { bd = ov; bi = oi; }
+  }
+  *distance = bd;
+  *best_facet = bi;
+  const HFacet& F = w.F[w.order[bi]];
+  normal[0] = F.n[0]; normal[1] = F.n[1]; normal[2] = F.n[2];
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+// Inside-case pairs queued by k_pairs: regenerate the reachable cloud (same code, same bits), render
+// it to 6 digits, hull it, pick the nearest facet, write the plane.  One warp per queued pair;
+// warps take hull workspaces by index (grid is sized to the number of workspaces).
+__global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+                                             PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
+                                             size_t ws_stride, int cap_pts, int* __restrict__ counters) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairWarpSmem pw;
+  load_block_tables(smem, tb, p.H, p.P);
+  carve_pair_smem(smem, warp, p.H, p.P, sNFt, sT, sphx, sphy, sphz, pw);
+  HullCtl* ctl = reinterpret_cast<HullCtl*>(smem + pair_block_table_doubles(p.H, p.P) + (size_t)wpb * pair_warp_doubles(p.H, p.P)) + warp;
+  HullWs w;
+  hull_ws_carve(ws_base + ws_stride * (size_t)(blockIdx.x * wpb + warp), cap_pts, w);
+  int nq = *hq.count;
+  if (nq > hq.capacity) nq = hq.capacity;
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(work_counter, 1);
+    item = __shfl_sync(LQRO_FULL, item, 0);
+    if (item >= nq) break;
+    const int pair = hq.items[item];
+    const int il = pair / p.K;
+    const int i = p.local_begin + il;
+    const int j = nbr[pair];
+    if (lane < 16) {
+      const double a = x[(size_t)i * 16 + lane], b = x[(size_t)j * 16 + lane];
+      pw.xi[lane] = a;
+      pw.dx[lane] = a - b;
+    }
+    __syncwarp();
+    const int n = warp_reachable_cloud(p, sNFt, sT, sphx, sphy, sphz, pw);
+    for (int m = lane; m < n; m += 32) {
+      if (p.hull_input == 0) { w.hx[m] = round6_dev(pw.px[m]); w.hy[m] = round6_dev(pw.py[m]); w.hz[m] = round6_dev(pw.pz[m]); }
+      else { w.hx[m] = pw.px[m]; w.hy[m] = pw.py[m]; w.hz[m] = pw.pz[m]; }
+    }
+    __syncwarp();
+    hull_build(w, *ctl, n);
+    if (ctl->fail) {
+      if (lane == 0) { out.status[pair] = 0x100; out.nfacets[pair] = 0; atomicAdd(counters + 3, 1); }  // no plane
+      __syncwarp();
+      continue;
+    }
+    double distance, normal[3]; int bestf;
+    hull_nearest_facet(w, *ctl, pw.px, pw.py, pw.pz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
+    if (lane == 0) {
+      write_plane(out.planes + 6 * (size_t)pair, pw.xi + 3, distance, normal[0], normal[1], normal[2], true);
+      out.dist[pair] = distance;
+      out.nfacets[pair] = ctl->nfacets_out;
+      out.status[pair] = 2 | (ctl->degenerate ? 0x100 : 0);
+      if (ctl->degenerate) atomicAdd(counters + 3, 1);
+    }
+    __syncwarp();
+  }
+}
+
+// Stage kernel: hull of an arbitrary cloud (AoS pts in global memory).  mode bit 0: apply the 6-digit
+// rendering first.  Outputs facets in qhull order (planes nf*4, verts nf*3 as point indices); when
+// vrel != NULL also the nearest-facet result (escape[0] = distance, [1..3] = normal) and best facet.
+__global__ void __launch_bounds__(32) k_stage_hull(const double* __restrict__ pts, int n, int mode, char* __restrict__ ws_base, int cap_pts,
+                                                   double* __restrict__ planes, int* __restrict__ verts, int maxf, int* __restrict__ info /*nf, degenerate, fail, ninserted, best*/,
+                                                   const double* __restrict__ vrel, double* __restrict__ escape, double* __restrict__ uscratch /*3n*/) {
+  __shared__ HullCtl ctl;
+  const int lane = lane_id();
+  HullWs w;
+  hull_ws_carve(ws_base, cap_pts, w);
+  double* ux = uscratch; double* uy = uscratch + n; double* uz = uscratch + 2 * (size_t)n;
+  for (int m = lane; m < n && m < cap_pts; m += 32) {
+    const double a = pts[3 * m], b = pts[3 * m + 1], c = pts[3 * m + 2];
+    ux[m] = a; uy[m] = b; uz[m] = c;
+    if (mode & 1) { w.hx[m] = round6_dev(a); w.hy[m] = round6_dev(b); w.hz[m] = round6_dev(c); }
+    else { w.hx[m] = a; w.hy[m] = b; w.hz[m] = c; }
+  }
+  __syncwarp();
+  hull_build(w, ctl, n);
+  if (lane == 0) { info[0] = ctl.fail ? 0 : ctl.nfacets_out; info[1] = ctl.degenerate; info[2] = ctl.fail; info[3] = ctl.ninserted; info[4] = -1; }
+  __syncwarp();
+  if (ctl.fail) return;
+  for (int q = lane; q < ctl.nfacets_out && q < maxf; q += 32) {
+    const HFacet& F = w.F[w.order[q]];
+    if (planes) { planes[4 * q] = F.n[0]; planes[4 * q + 1] = F.n[1]; planes[4 * q + 2] = F.n[2]; planes[4 * q + 3] = F.off; }
+    if (verts) { verts[3 * q] = w.vpoint[F.v[0]]; verts[3 * q + 1] = w.vpoint[F.v[1]]; verts[3 * q + 2] = w.vpoint[F.v[2]]; }
+  }
+  if (vrel) {
+    double distance, normal[3]; int bestf;
+    hull_nearest_facet(w, ctl, ux, uy, uz, vrel[0], vrel[1], vrel[2], &distance, normal, &bestf);
+    if (lane == 0) { escape[0] = distance; escape[1] = normal[0]; escape[2] = normal[1]; escape[3] = normal[2]; info[4] = bestf; }
+  }
+}

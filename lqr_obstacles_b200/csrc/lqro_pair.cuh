@@ -1,0 +1,370 @@
+// lqro_pair.cuh -- horizon tables and the per-pair LQR-obstacle kernel.
+//
+//   k_horizon_tables : findFG x H (MAIN:653-662) + the pair-independent half of createObstacle
+//                      (MAIN:684-685), once per dynamics class.
+//   k_pairs          : for every (agent, neighbour slot): createObstacle x H (MAIN:683-688),
+//                      findReachableObstacle (MAIN:691-706), pointInHull/run_gjk (MAIN:712-758) and,
+//                      for the outside case, createHalfPlanes (MAIN:1085-1098).  Inside pairs are queued
+//                      for k_hull (lqro_hull.cuh).
+//
+// Data layout in HBM: agent state AoS x[N][16] FP64 (one 128-byte line per agent: a pair costs one
+// line for the neighbour), neighbour ids nbr[n_local][K] int32, outputs planes[n_local][K][6] FP32,
+// status/nreach[n_local][K] int32, dist[n_local][K] FP64.  Tables live in shared memory.
+#pragma once
+#include "lqro_common.cuh"
+#include "lqro_gjk.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// 3x3 inverse exactly as the reference's operator! (MAT:603-671): Gauss-Jordan, full pivoting with
+// row/column permutation vectors, the same update order.
+__device__ inline void inverse3_ref(const double* q, double* out) {
+  const int n = 3;
+  double m[9], inv[9];
+  int rp[3], cp[3];
+  for (int i = 0; i < 9; ++i) { m[i] = q[i]; inv[i] = 0.0; }
+  for (int i = 0; i < n; ++i) { inv[i * n + i] = 1.0; rp[i] = i; cp[i] = i; }
+  for (int k = 0; k < n; ++k) {
+    double maximum = 0;
+    int mr = k, mc = k;
+    for (int i = k; i < n; ++i)
+      for (int j = k; j < n; ++j) {
+        const double a = fabs(m[rp[i] * n + cp[j]]);
+        if (a > maximum) { maximum = a; mr = i; mc = j; }
+      }
+    int t = rp[k]; rp[k] = rp[mr]; rp[mr] = t;
+    t = cp[k]; cp[k] = cp[mc]; cp[mc] = t;
+    for (int i = k + 1; i < n; ++i) {
+      const double factor = m[rp[i] * n + cp[k]] / m[rp[k] * n + cp[k]];
+      for (int j = k + 1; j < n; ++j) m[rp[i] * n + cp[j]] -= factor * m[rp[k] * n + cp[j]];
+      for (int j = 0; j < k; ++j) inv[rp[i] * n + rp[j]] -= factor * inv[rp[k] * n + rp[j]];
+      inv[rp[i] * n + rp[k]] = -factor;
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    const double quotient = m[rp[k] * n + cp[k]];
+    for (int j = 0; j < n; ++j) inv[rp[k] * n + j] /= quotient;
+    for (int i = 0; i < k; ++i) {
+      const double factor = m[rp[i] * n + cp[k]];
+      for (int j = 0; j < n; ++j) inv[rp[i] * n + j] -= factor * inv[rp[k] * n + j];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) out[cp[i] * n + j] = inv[rp[i] * n + j];
+}
+
+// One block of 256 threads; thread t owns element (t/16, t%16) of the 16x16 products.  Each output
+// element is one left-to-right sum (MAT:218-231), so the thread-parallel product is bit-identical to
+// the reference's triple loop.
+//   out: NFt [16][3H] (transposed), NF [H][3][16] (reference order, for the parity API), T [H][9].
+__global__ void __launch_bounds__(256) k_horizon_tables(const double* __restrict__ A, const double* __restrict__ B,
+                                                        const double* __restrict__ L, const double* __restrict__ E, int H,
+                                                        double* __restrict__ NFt, double* __restrict__ NF,
+                                                        double* __restrict__ T) {
+  __shared__ double sAt[256], sBt[48], sF[256], sG[48], sF2[256], sG2[48];
+  const int t = threadIdx.x;
+  const int i = t >> 4, j = t & 15;
+  {
+    double bl = 0;  // (B*L)(i,j)
+    for (int k = 0; k < 4; ++k) bl += B[i * 4 + k] * L[k * 16 + j];
+    sAt[t] = A[t] + bl;  // Atilde = A + (B*L), MAIN:655
+    sF[t] = (i == j) ? 1.0 : 0.0;
+  }
+  if (t < 48) {
+    const int bi = t / 3, bj = t % 3;
+    double be = 0;  // Btilde = B*E, MAIN:658
+    for (int k = 0; k < 4; ++k) be += B[bi * 4 + k] * E[k * 3 + bj];
+    sBt[t] = be;
+    sG[t] = 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < H; ++k) {
+    {
+      double f = 0;  // F = Atilde*F, MAIN:660
+      for (int m = 0; m < 16; ++m) f += sAt[i * 16 + m] * sF[m * 16 + j];
+      sF2[t] = f;
+    }
+    if (t < 48) {
+      const int gi = t / 3, gj = t % 3;
+      double g = 0;  // G = Atilde*G + Btilde, MAIN:661
+      for (int m = 0; m < 16; ++m) g += sAt[gi * 16 + m] * sG[m * 3 + gj];
+      sG2[t] = g + sBt[t];
+    }
+    __syncthreads();
+    sF[t] = sF2[t];
+    if (t < 48) sG[t] = sG2[t];
+    __syncthreads();
+    if (t < 48) {  // rows 0..2 of -F: (-P)*F with P = [I3 0], MAIN:685
+      const int c = t >> 4, m = t & 15;
+      const double v = -sF[c * 16 + m];
+      NF[(k * 3 + c) * 16 + m] = v;
+      NFt[m * (3 * H) + k * 3 + c] = v;
+    }
+    if (t == 0) {  // Transform = !(P*G), MAIN:684
+      double cg[9];
+      for (int e = 0; e < 9; ++e) cg[e] = sG[e];  // rows 0..2 of G (16x3 row major)
+      inverse3_ref(cg, T + 9 * k);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PairOutputs {
+  float* planes;   // [n_local*K][6]
+  int* status;     // [n_local*K]
+  int* nreach;     // [n_local*K]
+  double* dist;    // [n_local*K]
+  int* nfacets;    // [n_local*K]
+};
+
+struct HullQueue {
+  int* items;      // pair ids of the inside case
+  int* count;      // number appended (may exceed capacity: overflow)
+  int capacity;
+};
+
+// shared-memory carve-up of one pair warp
+struct PairWarpSmem {
+  double* tr;   // [3H]   Translate_k, MAIN:685
+  double* dx;   // [16]   x_i - x_j
+  double* xi;   // [16]
+  double* px;   // [HP]   reachable cloud, SoA
+  double* py;
+  double* pz;
+  GjkState* gjk;
+};
+
+__host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P; }
+__host__ __device__ inline size_t pair_warp_doubles(int H, int P) {
+  return (size_t)3 * H + 32 + 3 * (size_t)H * P + (sizeof(GjkState) + 7) / 8;
+}
+
+// exact reachable test, MAIN:703: pow(a,2)/pow(r,2) + pow(b,2)/pow(r,2) + pow(c,2)/pow(r,2) < 1.0
+__device__ __forceinline__ bool reach_exact(double a, double b, double c, double r2) {
+  return (a * a) / r2 + (b * b) / r2 + (c * c) / r2 < 1.0;
+}
+// Same decision without the three divisions unless the sum is within 1e-9 of the threshold: the
+// fused estimate differs from the reference's rounded sum by < 2e-15 relative, so outside the band
+// both sides of the comparison agree; inside it the exact sequence is evaluated.
+__device__ __forceinline__ bool reach_test(double a, double b, double c, double r2, double inv_r2) {
+  const double est = fma(a, a, fma(b, b, c * c)) * inv_r2;
+  if (fabs(est - 1.0) > 1.0e-9) return est < 1.0;
+  return reach_exact(a, b, c, r2);
+}
+
+// Translate_k = -(C F_k) (x_i - x_j) for all k: 3H independent 16-term left-to-right sums (MAT:218-231).
+__device__ __forceinline__ void warp_translate(const double* __restrict__ sNFt, const double* __restrict__ dx, double* tr, int H) {
+  const int lane = lane_id();
+  const int n3 = 3 * H;
+  for (int e = lane; e < n3; e += 32) {
+    double t = 0;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) t += sNFt[m * n3 + e] * dx[m];
+    tr[e] = t;
+  }
+}
+
+// candidate point (k, s): Transform_k * (p_s + Translate_k), MAIN:687
+__device__ __forceinline__ void candidate_point(const double* __restrict__ sT, const double* __restrict__ sphx,
+                                                const double* __restrict__ sphy, const double* __restrict__ sphz,
+                                                const double* __restrict__ tr, int k, int s, double& q0, double& q1, double& q2) {
+  const double* Tk = sT + 9 * k;
+  const double v0 = sphx[s] + tr[3 * k], v1 = sphy[s] + tr[3 * k + 1], v2 = sphz[s] + tr[3 * k + 2];
+  q0 = Tk[0] * v0 + Tk[1] * v1 + Tk[2] * v2;
+  q1 = Tk[3] * v0 + Tk[4] * v1 + Tk[5] * v2;
+  q2 = Tk[6] * v0 + Tk[7] * v1 + Tk[8] * v2;
+}
+
+// Build the reachable cloud of one pair in shared memory (order preserved), return its size.
+// Requires w.dx (and so v_rel = dx[3..5]) to be set; fills w.tr.
+__device__ __forceinline__ int warp_reachable_cloud(const LqroParams& p, const double* sNFt, const double* sT, const double* sphx,
+                                                    const double* sphy, const double* sphz, PairWarpSmem& w) {
+  const int lane = lane_id();
+  warp_translate(sNFt, w.dx, w.tr, p.H);
+  __syncwarp();
+  const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
+  int count = 0;
+  int k = 0, s = lane;
+  while (s >= p.P) { s -= p.P; ++k; }
+  for (int base = 0; base < p.HP; base += 32) {
+    const int m = base + lane;
+    bool pass = false;
+    double q0 = 0, q1 = 0, q2 = 0;
+    if (m < p.HP) {
+      candidate_point(sT, sphx, sphy, sphz, w.tr, k, s, q0, q1, q2);
+      pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
+    }
+    const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+    if (pass) {
+      const int pos = count + __popc(mask & ((1u << lane) - 1u));
+      w.px[pos] = q0; w.py[pos] = q1; w.pz[pos] = q2;
+    }
+    count += __popc(mask);
+    s += 32;
+    while (s >= p.P) { s -= p.P; ++k; }
+  }
+  __syncwarp();
+  return count;
+}
+
+__device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, int P, const double*& sNFt, const double*& sT,
+                                                const double*& sphx, const double*& sphy, const double*& sphz, PairWarpSmem& w) {
+  sNFt = base;
+  sT = base + 16 * 3 * H;
+  sphx = sT + 9 * H;
+  sphy = sphx + P;
+  sphz = sphy + P;
+  double* wb = base + pair_block_table_doubles(H, P) + (size_t)warp * pair_warp_doubles(H, P);
+  w.tr = wb;
+  w.dx = wb + 3 * H;
+  w.xi = w.dx + 16;
+  w.px = w.xi + 16;
+  w.py = w.px + (size_t)H * P;
+  w.pz = w.py + (size_t)H * P;
+  w.gjk = reinterpret_cast<GjkState*>(w.pz + (size_t)H * P);
+}
+
+__device__ __forceinline__ void load_block_tables(double* base, const LqroTables& tb, int H, int P) {
+  const int nNF = 16 * 3 * H, nT = 9 * H;
+  for (int e = threadIdx.x; e < nNF; e += blockDim.x) base[e] = tb.NFt[e];
+  for (int e = threadIdx.x; e < nT; e += blockDim.x) base[nNF + e] = tb.T[e];
+  double* sph = base + nNF + nT;
+  for (int e = threadIdx.x; e < P; e += blockDim.x) {  // AoS [P][3] -> SoA
+    sph[e] = tb.sph[3 * e];
+    sph[P + e] = tb.sph[3 * e + 1];
+    sph[2 * P + e] = tb.sph[3 * e + 2];
+  }
+  __syncthreads();
+}
+
+// createHalfPlanes (MAIN:1085-1098) after `distance *= 0.5` (MAIN:1401); FP64 -> FP32 narrowing as in
+// Vector3(double,double,double) (V3:113-118).
+__device__ __forceinline__ void write_plane(float* pl, const double* vi, double distance, double n0, double n1, double n2, bool inside) {
+  const double half = distance * 0.5;
+  const double mult = inside ? 1.0 : -1.0;
+  const double md = mult * half;
+  pl[0] = (float)(vi[0] + md * n0);
+  pl[1] = (float)(vi[1] + md * n1);
+  pl[2] = (float)(vi[2] + md * n2);
+  pl[3] = (float)n0;
+  pl[4] = (float)n1;
+  pl[5] = (float)n2;
+}
+
+// Persistent kernel: one warp per pair, pairs handed out by an atomic counter (their cost varies
+// from "no reachable point" to a 1000-point GJK).  Dynamic shared memory = tables + per-warp clouds.
+__global__ void __launch_bounds__(256) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+                                               PairOutputs out, int* __restrict__ work_counter, HullQueue hq) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairWarpSmem w;
+  load_block_tables(smem, tb, p.H, p.P);
+  carve_pair_smem(smem, warp, p.H, p.P, sNFt, sT, sphx, sphy, sphz, w);
+  const int npairs = p.n_local * p.K;
+  while (true) {
+    int pair = 0;
+    if (lane == 0) pair = atomicAdd(work_counter, 1);
+    pair = __shfl_sync(LQRO_FULL, pair, 0);
+    if (pair >= npairs) break;
+    const int il = pair / p.K;
+    const int i = p.local_begin + il;
+    const int j = nbr[pair];
+    if (j < 0 || j == i || j >= p.N) {  // empty slot (the reference skips i == j, MAIN:1379)
+      if (lane == 0) { out.status[pair] = 0; out.nreach[pair] = 0; }
+      continue;
+    }
+    if (lane < 16) {
+      const double a = x[(size_t)i * 16 + lane], b = x[(size_t)j * 16 + lane];
+      w.xi[lane] = a;
+      w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
+    }
+    __syncwarp();
+    const int n = warp_reachable_cloud(p, sNFt, sT, sphx, sphy, sphz, w);
+    if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
+      if (lane == 0) { out.status[pair] = 0; out.nreach[pair] = n; }
+      __syncwarp();
+      continue;
+    }
+    const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
+    const double sq = gjk_warp(*w.gjk, vr0, vr1, vr2, w.px, w.py, w.pz, n, nullptr);
+    if (lane == 0) {
+      const double distance = sqrt(sq);                    // MAIN:741
+      const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
+      out.nreach[pair] = n;
+      if (!inside) {
+        const GjkState& g = *w.gjk;
+        const double n0 = (g.w1[0] - g.w2[0]) / distance;  // MAIN:743-745
+        const double n1 = (g.w1[1] - g.w2[1]) / distance;
+        const double n2 = (g.w1[2] - g.w2[2]) / distance;
+        write_plane(out.planes + 6 * (size_t)pair, w.xi + 3, distance, n0, n1, n2, false);
+        out.dist[pair] = distance;
+        out.status[pair] = 1;
+      } else {
+        out.status[pair] = 2;  // plane filled in by k_hull
+        const int slot = atomicAdd(hq.count, 1);
+        if (slot < hq.capacity) hq.items[slot] = pair;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage kernels behind the per-stage C entry points (one warp, one pair / one cloud).
+
+// mode 0: all H*P candidate points of the pair (xi, xj) -> q_out (AoS [HP][3])
+__global__ void __launch_bounds__(32) k_stage_candidates(LqroParams p, LqroTables tb, const double* __restrict__ xi,
+                                                         const double* __restrict__ xj, double* __restrict__ q_out) {
+  extern __shared__ double smem[];
+  const int lane = lane_id();
+  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairWarpSmem w;
+  load_block_tables(smem, tb, p.H, p.P);
+  carve_pair_smem(smem, 0, p.H, p.P, sNFt, sT, sphx, sphy, sphz, w);
+  if (lane < 16) w.dx[lane] = xi[lane] - xj[lane];
+  __syncwarp();
+  warp_translate(sNFt, w.dx, w.tr, p.H);
+  __syncwarp();
+  for (int m = lane; m < p.HP; m += 32) {
+    const int k = m / p.P, s = m - k * p.P;
+    double q0, q1, q2;
+    candidate_point(sT, sphx, sphy, sphz, w.tr, k, s, q0, q1, q2);
+    q_out[3 * m] = q0; q_out[3 * m + 1] = q1; q_out[3 * m + 2] = q2;
+  }
+}
+
+// reachable filter on an arbitrary cloud: idx_out ascending, *n_out count
+__global__ void __launch_bounds__(32) k_stage_reachable(LqroParams p, const double* __restrict__ q, int n, const double* __restrict__ xi,
+                                                        const double* __restrict__ xj, int* __restrict__ idx_out, int* __restrict__ n_out) {
+  const int lane = lane_id();
+  const double vr0 = xi[3] - xj[3], vr1 = xi[4] - xj[4], vr2 = xi[5] - xj[5];
+  int count = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int m = base + lane;
+    bool pass = false;
+    if (m < n) pass = reach_test(q[3 * m] - vr0, q[3 * m + 1] - vr1, q[3 * m + 2] - vr2, p.r2, p.inv_r2);
+    const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+    if (pass) idx_out[count + __popc(mask & ((1u << lane) - 1u))] = m;
+    count += __popc(mask);
+  }
+  if (lane == 0) *n_out = count;
+}
+
+// GJK on an arbitrary cloud (AoS in global memory, staged to SoA scratch)
+__global__ void __launch_bounds__(32) k_stage_gjk(const double* __restrict__ vrel, const double* __restrict__ pts, int n,
+                                                  double* __restrict__ scratch /*3n*/, double* __restrict__ out /*sqd, w2[3]*/,
+                                                  int* __restrict__ iters) {
+  __shared__ GjkState g;
+  const int lane = lane_id();
+  double* px = scratch; double* py = scratch + n; double* pz = scratch + 2 * (size_t)n;
+  for (int m = lane; m < n; m += 32) { px[m] = pts[3 * m]; py[m] = pts[3 * m + 1]; pz[m] = pts[3 * m + 2]; }
+  __syncwarp();
+  int it = 0;
+  const double sq = gjk_warp(g, vrel[0], vrel[1], vrel[2], px, py, pz, n, &it);
+  if (lane == 0) {
+    out[0] = sq; out[1] = g.w2[0]; out[2] = g.w2[1]; out[3] = g.w2[2];
+    out[4] = g.w1[0]; out[5] = g.w1[1]; out[6] = g.w1[2];
+    *iters = it;
+  }
+}
