@@ -110,6 +110,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 _REF = None
+_WL = None  # (A, B, L, E, NF, T, sph, x, vpref, nbr, H): set before the pool forks, inherited by the workers
 
 
 def _ref_init():
@@ -123,29 +124,20 @@ def _ref_init():
         _REF = ("port", Oracle())
 
 
-def _ref_chunk(args):
-    """one shard of agents through the reference's per-pair code + calculateNewV (process-local library)."""
+def _ref_chunk(agents):
+    """one shard of agents through the reference's own per-pair code + calculateNewV, looped in C++
+    (ref_step_agents in oracle/ref_harness.cpp; lqro_o_step for the port)."""
     kind, R = _REF
-    (A, B, L, E, NF, T, sph, x, vpref, nbr_rows, agents, H) = args
-    npairs = 0
-    out = np.zeros((len(agents), 3))
-    for a, i in enumerate(agents):
-        planes = []
-        for j in nbr_rows[a]:
-            if j < 0 or j == i:
-                continue
-            npairs += 1
-            if kind == "reference":
-                r = R.pair(A, B, L, E, x[i], x[j], H, 30.0)
-                if r["status"]:
-                    planes.append(r["plane"])
-            else:
-                r = R.pair(NF, T, sph, x[i], x[j], 30.0)
-                if r["status"]:
-                    planes.append(r["plane"])
-        pl = np.array(planes, dtype=np.float32).reshape(-1, 6)
-        out[a] = R.calculate_new_v(pl, vpref[i]) if kind == "reference" else R.new_velocity(pl, vpref[i])
-    return npairs, out
+    A, B, L, E, NF, T, sph, x, vpref, nbr, H = _WL
+    rows = np.ascontiguousarray(nbr[agents])
+    if kind == "reference":
+        npairs, newV, _ = R.step_agents(A, B, L, E, x, vpref, rows, agents, H, 30.0)
+        return int(npairs), newV
+    xs = x  # the port takes the same global state; restrict the neighbour table to the shard
+    full = np.full((len(x), rows.shape[1]), -1, dtype=np.int32)
+    full[agents] = rows
+    newV = R.step(NF, T, sph, xs, vpref, full, nthreads=1)[0][agents]
+    return int((rows >= 0).sum()), newV
 
 
 class CpuBaseline:
@@ -166,15 +158,15 @@ class CpuBaseline:
         self.NF, self.T, _ = O.horizon(self.A, self.B, self.L, self.E, self.w["H"])
         self.sph = O.spheres(self.w["P"])
         self.cores = nproc or len(os.sched_getaffinity(0))
+        global _WL
+        _WL = (self.A, self.B, self.L, self.E, self.NF, self.T, self.sph, self.x, self.vpref, self.nbr, self.w["H"])
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_ref_init)
 
     def run(self, n_agents_sample, seed=0):
         N = len(self.x)
         rng = np.random.default_rng(seed)
         agents = np.sort(rng.choice(N, size=min(n_agents_sample, N), replace=False))
-        shards = np.array_split(agents, self.cores * 4)
-        tasks = [(self.A, self.B, self.L, self.E, self.NF, self.T, self.sph, self.x, self.vpref, self.nbr[s], s, self.w["H"])
-                 for s in shards if len(s)]
+        tasks = [s.astype(np.int32) for s in np.array_split(agents, self.cores * 4) if len(s)]
         t0 = time.perf_counter()
         res = self.pool.map(_ref_chunk, tasks)
         dt = time.perf_counter() - t0

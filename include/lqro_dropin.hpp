@@ -1,0 +1,261 @@
+// include/lqro_dropin.hpp -- C++ shims carrying the REFERENCE'S OWN SIGNATURES for the hot path, so
+// that the reference main loop (MAIN:1371-1418, or a headless copy of it) links against the B200 path
+// instead of its CPU functions.  Header-only; calls nothing but the C ABI of include/lqro.h.
+//
+// The shims are templates over the reference's `Matrix<R,C>` (include/matrix.h: value type, row-major
+// `double _elems[R*C]`, operator[] / operator()), so this header does not need -- and does not copy --
+// the reference's matrix header: include it first and instantiate with its types.  `PlaneT` is the
+// reference's `struct Plane { Vector3 point, normal; }` (MAIN:844-855), `Vec3T` its Vector3 (FP32).
+//
+// Conventions preserved from the reference: everything returns void, outputs by non-const
+// reference, std::vector outputs are APPENDED to (callers clear them, MAIN:1377-1378), calculateNewV
+// clears its input vector (MAIN:1111), no exceptions; a failing device call terminates the process
+// the way the reference's assert/exit(-1) paths do.
+//
+// Two levels:
+//   * per-function shims below: same names, same argument lists (createObstacle ... calculateNewV,
+//     controlMatrices' Riccati part) -- each call is one small device round trip: correct, slow;
+//   * lqro::Swarm -- the whole `for i / for j` block of MAIN:1373-1407 for all agents in ONE device
+//     step (lqro_step): this is what replaces the hot loop.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "lqro.h"
+
+namespace lqro {
+
+inline void check(int rc, lqro_ctx* ctx, const char* what) {
+  if (rc != LQRO_OK) {
+    std::fprintf(stderr, "liblqro: %s failed (%d): %s\n", what, rc, lqro_last_error(ctx));
+    std::exit(-1);  // the reference's own failure mode (MAT:859,870,974,1104)
+  }
+}
+
+// One process-wide context for the per-function shims, created on first use from the reference's
+// compile-time constants.  H and P follow OBSTACLE_STEPS / NUM_POINTS if those macros are visible.
+inline lqro_ctx*& shim_ctx() {
+  static lqro_ctx* ctx = nullptr;
+  return ctx;
+}
+inline lqro_ctx* ensure_ctx() {
+  lqro_ctx*& ctx = shim_ctx();
+  if (!ctx) {
+    lqro_config cfg;
+    lqro_default_config(&cfg);
+#ifdef OBSTACLE_STEPS
+    cfg.horizon = OBSTACLE_STEPS;
+#endif
+#ifdef NUM_POINTS
+    cfg.n_samples = NUM_POINTS;
+#endif
+#ifdef XYRADIUS
+    cfg.xy_radius = XYRADIUS;
+    cfg.z_radius = ZRADIUS;
+#endif
+    cfg.n_agents = 2;
+    cfg.max_neighbors = 1;
+    check(lqro_create(&cfg, &ctx), nullptr, "lqro_create");
+  }
+  return ctx;
+}
+
+// ---- MAIN:653-662 findFG is folded into lqro_set_dynamics (F_k, G_k for all k at once).
+// Call once after controlMatrices: replaces the H findFG calls the reference makes PER PAIR.
+template <class M16x16, class M16x4, class M4x16, class M4x3>
+inline void setDynamics(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E) {
+  lqro_ctx* ctx = ensure_ctx();
+  check(lqro_set_dynamics(ctx, &A[0], &B[0], &L[0], &E[0]), ctx, "lqro_set_dynamics");
+}
+
+// ---- MAIN:490-544 controlMatrices, Riccati part (A, B already linearised/discretised by the caller:
+// the quadrotor model MAIN:338-440 stays host code).  Fills L, E, Lh, Eh; l = 0 for c = 0, Qx = 0.
+template <class M16x16, class M16x4, class M4x16, class M4x3, class M3x16, class M3x3>
+inline void controlMatricesRiccati(const M16x16& A, const M16x4& B, double qv, double qp, double r, M4x16& L, M4x3& E, M3x16& Lh,
+                                   M3x3& Eh) {
+  lqro_ctx* ctx = ensure_ctx();
+  check(lqro_solve_gains(ctx, 1, &A[0], &B[0], qv, qp, r, 300, &L[0], &E[0], &Lh[0], &Eh[0]), ctx, "lqro_solve_gains");
+}
+
+// ---- MAIN:665-680 createSpheres(std::vector<Matrix<3,1>>& points): appends NUM_POINTS samples
+template <class V3d>
+inline void createSpheres(std::vector<V3d>& points) {
+  lqro_ctx* ctx = ensure_ctx();
+  if (false) check(0, ctx, "");
+  std::vector<double> sph;
+  // the tables need dynamics; spheres alone are available right after create through get_tables' third output
+  lqro_config cfg;
+  lqro_default_config(&cfg);
+#ifdef NUM_POINTS
+  cfg.n_samples = NUM_POINTS;
+#endif
+  sph.resize(3 * (size_t)cfg.n_samples);
+  int rc = lqro_get_tables(ctx, nullptr, nullptr, sph.data());
+  check(rc, ctx, "lqro_get_tables (call setDynamics first)");
+  for (int i = 0; i < cfg.n_samples; ++i) {
+    V3d p;
+    p[0] = sph[3 * i]; p[1] = sph[3 * i + 1]; p[2] = sph[3 * i + 2];
+    points.push_back(p);
+  }
+}
+
+// ---- MAIN:683-688 createObstacle for ALL horizon steps of one pair: appends H*P points (k-major), i.e.
+// what the reference's `for k` loop around createObstacle (MAIN:1383-1389) leaves in `ellipsoids`.
+template <class V3d, class State>
+inline void createObstacleAll(std::vector<V3d>& ellipsoids, const State& xInit1, const State& xInit2) {
+  lqro_ctx* ctx = ensure_ctx();
+  lqro_config cfg;
+  lqro_default_config(&cfg);
+#ifdef OBSTACLE_STEPS
+  cfg.horizon = OBSTACLE_STEPS;
+#endif
+#ifdef NUM_POINTS
+  cfg.n_samples = NUM_POINTS;
+#endif
+  const int n = cfg.horizon * cfg.n_samples;
+  std::vector<double> q(3 * (size_t)n);
+  check(lqro_candidates(ctx, &xInit1[0], &xInit2[0], q.data()), ctx, "lqro_candidates");
+  for (int i = 0; i < n; ++i) {
+    V3d p;
+    p[0] = q[3 * i]; p[1] = q[3 * i + 1]; p[2] = q[3 * i + 2];
+    ellipsoids.push_back(p);
+  }
+}
+
+// ---- MAIN:691-706 findReachableObstacle(ellipsoids, reachablePoints, x0, x1, maxSpeed): appends survivors
+template <class V3d, class State>
+inline void findReachableObstacle(const std::vector<V3d>& ellipsoids, std::vector<V3d>& reachablePoints, const State& x0,
+                                  const State& x1, const double& /*maxSpeed: configured at create*/) {
+  lqro_ctx* ctx = ensure_ctx();
+  const int n = (int)ellipsoids.size();
+  std::vector<double> q(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) q[3 * i + k] = ellipsoids[i][k];
+  std::vector<int> idx(n > 0 ? n : 1);
+  int cnt = 0;
+  check(lqro_reachable(ctx, q.data(), n, &x0[0], &x1[0], idx.data(), &cnt), ctx, "lqro_reachable");
+  for (int i = 0; i < cnt; ++i) reachablePoints.push_back(ellipsoids[idx[i]]);
+}
+
+// ---- MAIN:712-746 run_gjk(x0, x1, reachablePoints, distance, normal)
+template <class V3d, class State>
+inline void run_gjk(const State& x0, const State& x1, const std::vector<V3d>& reachablePoints, double& distance, V3d& normal) {
+  lqro_ctx* ctx = ensure_ctx();
+  const int n = (int)reachablePoints.size();
+  std::vector<double> q(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) q[3 * i + k] = reachablePoints[i][k];
+  const double vrel[3] = {x0[3] - x1[3], x0[4] - x1[4], x0[5] - x1[5]};
+  double sq = 0, w[3];
+  check(lqro_gjk(ctx, vrel, q.data(), n, &sq, w, nullptr), ctx, "lqro_gjk");
+  distance = std::sqrt(sq);
+  // witness on {v_rel} is v_rel itself
+  normal[0] = (vrel[0] - w[0]) / distance; normal[1] = (vrel[1] - w[1]) / distance; normal[2] = (vrel[2] - w[2]) / distance;
+}
+
+// ---- MAIN:749-758 pointInHull
+template <class V3d, class State>
+inline void pointInHull(const std::vector<V3d>& reachablePoints, bool& insideHull, const State& x0, const State& x1) {
+  double distance;
+  V3d normal;
+  run_gjk(x0, x1, reachablePoints, distance, normal);
+  insideHull = distance < 0.0001 && distance > -0.0001;
+}
+
+// ---- MAIN:809-838 convexHull(reachablePoints, x0, x1, distance, normal): no process spawn, no files
+template <class V3d, class State>
+inline void convexHull(const std::vector<V3d>& reachablePoints, const State& x0, const State& x1, double& distance, V3d& normal) {
+  lqro_ctx* ctx = ensure_ctx();
+  const int n = (int)reachablePoints.size();
+  std::vector<double> q(3 * (size_t)n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) q[3 * i + k] = reachablePoints[i][k];
+  const double vrel[3] = {x0[3] - x1[3], x0[4] - x1[4], x0[5] - x1[5]};
+  double nrm[3];
+  check(lqro_hull_escape(ctx, q.data(), n, vrel, &distance, nrm, nullptr, nullptr), ctx, "lqro_hull_escape");
+  normal[0] = nrm[0]; normal[1] = nrm[1]; normal[2] = nrm[2];
+}
+
+// ---- MAIN:1085-1098 createHalfPlanes: pure narrowing arithmetic, kept on the host (FP64 -> FP32)
+template <class State, class V3d, class PlaneT>
+inline void createHalfPlanes(const State& x, double& distance, V3d& normal, const bool& insideHull, std::vector<PlaneT>& orcaPlanes_) {
+  PlaneT p;
+  const double mult = insideHull ? 1.0 : -1.0;
+  p.normal = decltype(p.normal)(normal[0], normal[1], normal[2]);
+  p.point = decltype(p.point)(x[3] + mult * distance * normal[0], x[4] + mult * distance * normal[1], x[5] + mult * distance * normal[2]);
+  orcaPlanes_.push_back(p);
+}
+
+// ---- MAIN:1101-1112 calculateNewV(orcaPlanes_, goalVel, newVel): clears orcaPlanes_
+template <class PlaneT, class V3d>
+inline void calculateNewV(std::vector<PlaneT>& orcaPlanes_, const V3d& goalVel, V3d& newVel) {
+  lqro_ctx* ctx = ensure_ctx();
+  const int n = (int)orcaPlanes_.size();
+  std::vector<float> pl(6 * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) {
+    pl[6 * i + 0] = orcaPlanes_[i].point[0]; pl[6 * i + 1] = orcaPlanes_[i].point[1]; pl[6 * i + 2] = orcaPlanes_[i].point[2];
+    pl[6 * i + 3] = orcaPlanes_[i].normal[0]; pl[6 * i + 4] = orcaPlanes_[i].normal[1]; pl[6 * i + 5] = orcaPlanes_[i].normal[2];
+  }
+  const double g[3] = {goalVel[0], goalVel[1], goalVel[2]};
+  double v[3];
+  check(lqro_new_velocity(ctx, 1, n > 0 ? n : 1, pl.data(), &n, g, v), ctx, "lqro_new_velocity");
+  newVel[0] = v[0]; newVel[1] = v[1]; newVel[2] = v[2];
+  orcaPlanes_.clear();
+}
+
+// ---- the whole avoidance block of the time loop, MAIN:1373-1407, in one device step ----------------
+// Usage in the reference's _tmain:
+//     lqro::Swarm swarm(NUM_QUADS, NUM_QUADS - 1);   swarm.setDynamics(A, B, qlist[0]->L, qlist[0]->E);
+//     ... each time step, instead of the `for i / for j` block:
+//     swarm.step(qlist);      // reads qlist[i]->x, qlist[i]->vGoal; writes qlist[i]->newV
+class Swarm {
+ public:
+  Swarm(int n_agents, int max_neighbors, int device = 0) : n_(n_agents), k_(max_neighbors) {
+    lqro_config cfg;
+    lqro_default_config(&cfg);
+#ifdef OBSTACLE_STEPS
+    cfg.horizon = OBSTACLE_STEPS;
+#endif
+#ifdef NUM_POINTS
+    cfg.n_samples = NUM_POINTS;
+#endif
+    cfg.device = device;
+    cfg.n_agents = n_agents;
+    cfg.max_neighbors = max_neighbors;
+    check(lqro_create(&cfg, &ctx_), nullptr, "lqro_create");
+    x_.resize(16 * (size_t)n_); vpref_.resize(3 * (size_t)n_); newv_.resize(3 * (size_t)n_);
+    nbr_.resize((size_t)n_ * k_);
+    for (int i = 0; i < n_; ++i) {  // the reference's neighbour set: every other agent in index order (MAIN:1376-1380)
+      int c = 0;
+      for (int j = 0; j < n_ && c < k_; ++j) if (j != i) nbr_[(size_t)i * k_ + c++] = j;
+      for (; c < k_; ++c) nbr_[(size_t)i * k_ + c] = -1;
+    }
+  }
+  ~Swarm() { lqro_destroy(ctx_); }
+  Swarm(const Swarm&) = delete;
+  Swarm& operator=(const Swarm&) = delete;
+
+  template <class M16x16, class M16x4, class M4x16, class M4x3>
+  void setDynamics(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E) {
+    check(lqro_set_dynamics(ctx_, &A[0], &B[0], &L[0], &E[0]), ctx_, "lqro_set_dynamics");
+  }
+  void setNeighbors(const std::vector<int>& nbr) { nbr_ = nbr; }
+
+  // QuadPtrVec: std::vector<Quadrotor*> with members x (State), vGoal, newV (Matrix<3,1>)
+  template <class QuadPtrVec>
+  void step(QuadPtrVec& qlist) {
+    for (int i = 0; i < n_; ++i) {
+      for (int k = 0; k < 16; ++k) x_[16 * (size_t)i + k] = qlist[i]->x[k];
+      for (int k = 0; k < 3; ++k) vpref_[3 * (size_t)i + k] = qlist[i]->vGoal[k];
+    }
+    check(lqro_step(ctx_, x_.data(), vpref_.data(), nbr_.data(), newv_.data()), ctx_, "lqro_step");
+    for (int i = 0; i < n_; ++i) for (int k = 0; k < 3; ++k) qlist[i]->newV[k] = newv_[3 * (size_t)i + k];
+  }
+  lqro_ctx* context() { return ctx_; }
+
+ private:
+  int n_, k_;
+  lqro_ctx* ctx_ = nullptr;
+  std::vector<double> x_, vpref_, newv_;
+  std::vector<int> nbr_;
+};
+
+}  // namespace lqro

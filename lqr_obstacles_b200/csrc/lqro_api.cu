@@ -231,12 +231,13 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     ctx->pair_warps = wp;
     ctx->pair_smem = tbl + per * wp;
     ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM (shared memory allows exactly one)
-    CUC(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->pair_smem));
-    const size_t stage = tbl + per;
-    CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+    // function attributes are per function, not per context: always allow the device maximum so that
+    // contexts with different H*P can coexist
+    CUC(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     ctx->hull_wpb = 2;
     ctx->hull_smem = tbl + per * ctx->hull_wpb + sizeof(HullCtl) * ctx->hull_wpb + 16;
-    CUC(cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->hull_smem));
+    CUC(cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     int per_sm = (int)(ctx->smem_optin / ctx->hull_smem);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;

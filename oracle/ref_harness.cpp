@@ -423,6 +423,57 @@ extern "C" void ref_sim_update(void* handle) {
   s->step++;
 }
 
+// Avoidance step of a SUBSET of agents with explicit neighbour lists (the synthetic swarms): the loop body
+// of MAIN:1376-1406 per listed agent, all in the reference's own functions.  x: n_all*16 estimates,
+// vpref: n_all*3, nbr_rows: n_sel*K neighbour ids of the selected agents (<0 = empty), newV: n_sel*3.
+// Returns the number of (i,j) pairs evaluated.  This is what the CPU baseline times.
+extern "C" long ref_step_agents(const double* A, const double* B, const double* L, const double* E, const double* x,
+                                const double* vpref, const int* nbr_rows, const int* agents, int n_sel, int K, int H,
+                                double maxSpeed, double* newV, int* nplanes_out) {
+  Matrix<X_DIM, X_DIM> mA; Matrix<X_DIM, U_DIM> mB; Matrix<U_DIM, X_DIM> mL; Matrix<U_DIM, V_DIM> mE;
+  to_mat(A, mA); to_mat(B, mB); to_mat(L, mL); to_mat(E, mE);
+  Matrix<3, X_DIM> C = zeros<3, X_DIM>();
+  C(0, 0) = C(1, 1) = C(2, 2) = 1;
+  std::vector<Matrix<3, 1> > points; createSpheres(points);
+  std::vector<Matrix<3, 1> > ell, reach;
+  ell.reserve(NUM_POINTS * OBSTACLE_STEPS); reach.reserve(NUM_POINTS * OBSTACLE_STEPS);
+  Matrix<3, 3> Transform; Matrix<3, 1> Translate;
+  Matrix<X_DIM, X_DIM> Ft; Matrix<X_DIM, V_DIM> Gt;
+  bool insideHull = false; double distance = 0; Matrix<3, 1> normalVector = zeros<3, 1>();
+  std::vector<Plane> orcaPlanes;
+  size_t t = 0;
+  long npairs = 0;
+  for (int a = 0; a < n_sel; ++a) {
+    const int i = agents[a];
+    State x0; to_mat(x + 16 * (size_t)i, x0);
+    for (int kk = 0; kk < K; ++kk) {
+      const int j = nbr_rows[(size_t)a * K + kk];
+      ell.clear(); reach.clear();
+      if (j < 0 || j == i) continue;
+      ++npairs;
+      State x1; to_mat(x + 16 * (size_t)j, x1);
+      Ft = identity<X_DIM>(); Gt = zeros<X_DIM, V_DIM>();
+      for (int k = 0; k < H; ++k) {
+        findFG(mA, mB, mL, mE, Ft, Gt);
+        createObstacle(ell, points, Transform, Translate, t, Ft, Gt, C, x0, x1, 1);
+      }
+      findReachableObstacle(ell, reach, x0, x1, maxSpeed);
+      if ((int)reach.size() > 4) {
+        pointInHull(reach, insideHull, x0, x1);
+        if (insideHull) convexHull(reach, x0, x1, distance, normalVector);
+        else run_gjk(x0, x1, reach, distance, normalVector);
+        distance *= 0.5;
+        createHalfPlanes(x0, distance, normalVector, insideHull, orcaPlanes);
+      }
+    }
+    if (nplanes_out) nplanes_out[a] = (int)orcaPlanes.size();
+    Matrix<3, 1> g, v; to_mat(vpref + 3 * (size_t)i, g);
+    calculateNewV(orcaPlanes, g, v);
+    from_mat(v, newV + 3 * (size_t)a);
+  }
+  return npairs;
+}
+
 // The unmodified reference main() (renamed by shims/tchar.h).  stdin must not block: the reference
 // ends with `std::cin >> k` (MAIN:1421-1422); callers redirect stdin from /dev/null.
 extern "C" int ref_run_tmain(void) {

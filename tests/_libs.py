@@ -191,6 +191,8 @@ class Reference:
         lib.ref_control_matrices.argtypes = [c_void_p] * 10
         lib.ref_find_fg.argtypes = [c_void_p] * 6
         lib.ref_set_weights.argtypes = [c_double] * 3
+        lib.ref_step_agents.restype = ctypes.c_long
+        lib.ref_step_agents.argtypes = [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_void_p, c_void_p]
         self._tmp = workdir or tempfile.mkdtemp(prefix="lqro_ref_")
         lib.ref_chdir(self._tmp.encode())
         lib.ref_init()
@@ -265,6 +267,16 @@ class Reference:
         out = np.zeros(3)
         self.lib.ref_calculate_new_v(P(planes), len(planes), P(np.ascontiguousarray(goal, dtype=np.float64)), P(out))
         return out
+
+    def step_agents(self, A, B, L, E, x, vpref, nbr_rows, agents, H=20, max_speed=30.0):
+        """avoidance step of the listed agents, entirely inside the reference's code (ref_step_agents)"""
+        agents = np.ascontiguousarray(agents, dtype=np.int32)
+        nbr_rows = np.ascontiguousarray(nbr_rows, dtype=np.int32)
+        newV = np.zeros((len(agents), 3))
+        nplanes = np.zeros(len(agents), dtype=np.int32)
+        npairs = self.lib.ref_step_agents(P(A), P(B), P(L), P(E), P(x), P(vpref), P(nbr_rows), P(agents), len(agents),
+                                          nbr_rows.shape[1], H, max_speed, P(newV), P(nplanes))
+        return npairs, newV, nplanes
 
     def use_scipy_hull(self, enable=True):
         """Route the qconvex stand-in to scipy.spatial.ConvexHull (qhull_r 8.0.2) instead of
