@@ -66,7 +66,10 @@ typedef struct lqro_config {
                             cross-pair dependency) */
   int max_hull_pairs;    /* capacity of the inside-case work queue per step (0 => n_local*K) */
   int hull_slots;        /* concurrent hull workspaces (0 => default) */
+  int flags;             /* LQRO_FLAG_* (0 = defaults) */
 } lqro_config;
+
+#define LQRO_FLAG_NO_PRUNE 1   /* evaluate every horizon step of every pair (ablation / parity of the exact pruning) */
 
 /* Fills the reference's compile-time constants (MAIN:30-36, 1102, 1367). */
 void lqro_default_config(lqro_config* cfg);

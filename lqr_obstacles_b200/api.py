@@ -11,6 +11,7 @@ c_int, c_double, c_float, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_flo
 
 HULL_TEXT6, HULL_FP64 = 0, 1
 PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE = 0, 1, 2, 0x100
+FLAG_NO_PRUNE = 1
 
 
 class LqroError(RuntimeError):
@@ -22,7 +23,7 @@ class Config(ctypes.Structure):
         ("device", c_int), ("n_agents", c_int), ("local_begin", c_int), ("n_local", c_int), ("max_neighbors", c_int),
         ("horizon", c_int), ("n_samples", c_int), ("xy_radius", c_double), ("z_radius", c_double), ("max_speed", c_double),
         ("lp_radius", c_double), ("hull_input", c_int), ("fix_facet0_normal", c_int), ("max_hull_pairs", c_int),
-        ("hull_slots", c_int),
+        ("hull_slots", c_int), ("flags", c_int),
     ]
 
 

@@ -61,7 +61,7 @@ struct lqro_ctx {
   bool have_dynamics = false, stepped = false;
   // tables / dynamics
   double *d_dyn = nullptr;   // A(256) B(64) L(64) E(12)
-  double *d_NFt = nullptr, *d_NF = nullptr, *d_T = nullptr, *d_sph = nullptr;
+  double *d_NFt = nullptr, *d_NF = nullptr, *d_T = nullptr, *d_sph = nullptr, *d_CG = nullptr, *d_prn = nullptr;
   // step buffers
   double *d_x = nullptr, *d_vpref = nullptr, *d_newV = nullptr, *d_dist = nullptr;
   int *d_nbr = nullptr, *d_status = nullptr, *d_nreach = nullptr, *d_nfacets = nullptr, *d_nplanes = nullptr;
@@ -138,7 +138,7 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
-  void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
+  void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_CG, ctx->d_prn, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
                   ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
                   ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -169,6 +169,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.N = N; p.local_begin = cfg->local_begin; p.n_local = NL; p.K = K; p.H = H; p.P = P; p.HP = H * P;
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
   p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
+  p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
+  p.box[0] = p.box[1] = p.box[2] = 0.0;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete ctx; return fail(nullptr, LQRO_E_CUDA, "cudaGetDeviceProperties failed"); }
   ctx->sm_count = prop.multiProcessorCount;
@@ -183,6 +185,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMalloc(&ctx->d_NF, sizeof(double) * 48 * H));
   CUC(cudaMalloc(&ctx->d_T, sizeof(double) * 9 * H));
   CUC(cudaMalloc(&ctx->d_sph, sizeof(double) * 3 * P));
+  CUC(cudaMalloc(&ctx->d_CG, sizeof(double) * 9 * H));
+  CUC(cudaMalloc(&ctx->d_prn, sizeof(double) * 2 * H));
   const size_t NP = (size_t)NL * K;
   CUC(cudaMalloc(&ctx->d_x, sizeof(double) * 16 * (size_t)N));
   CUC(cudaMalloc(&ctx->d_vpref, sizeof(double) * 3 * (size_t)NL));
@@ -219,8 +223,10 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
       longt += dlong;
     }
     CUC(cudaMemcpy(ctx->d_sph, sph.data(), sizeof(double) * 3 * P, cudaMemcpyHostToDevice));
+    for (int i = 0; i < P; ++i)
+      for (int k = 0; k < 3; ++k) if (fabs(sph[3 * i + k]) > p.box[k]) p.box[k] = fabs(sph[3 * i + k]);
   }
-  ctx->tb.NFt = ctx->d_NFt; ctx->tb.T = ctx->d_T; ctx->tb.sph = ctx->d_sph;
+  ctx->tb.NFt = ctx->d_NFt; ctx->tb.T = ctx->d_T; ctx->tb.sph = ctx->d_sph; ctx->tb.CG = ctx->d_CG; ctx->tb.prn = ctx->d_prn;
   // launch geometry of the pair kernel: as many warps per block as the opt-in shared memory holds
   {
     const size_t tbl = sizeof(double) * pair_block_table_doubles(H, P);
@@ -287,9 +293,48 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
   CU(cudaMemcpyAsync(d + 256, B, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d + 320, L, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d + 384, E, sizeof(double) * 12, cudaMemcpyHostToDevice, ctx->stream));
-  k_horizon_tables<<<1, 256, 0, ctx->stream>>>(d, d + 256, d + 320, d + 384, ctx->prm.H, ctx->d_NFt, ctx->d_NF, ctx->d_T);
+  k_horizon_tables<<<1, 256, 0, ctx->stream>>>(d, d + 256, d + 320, d + 384, ctx->prm.H, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_CG);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
+  // pruning constants per horizon step (see step_prunable in lqro_pair.cuh): an UPPER bound of
+  // sigma_max(C G_k) (largest eigenvalue of G'G by Jacobi sweeps, inflated by 1e-9; never below the
+  // true value, falling back to the Frobenius norm) and kappa_k = |T_k|_F * sigma_max.
+  {
+    const int H = ctx->prm.H;
+    std::vector<double> cg(9 * (size_t)H), T(9 * (size_t)H), prn(2 * (size_t)H);
+    CU(cudaMemcpy(cg.data(), ctx->d_CG, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(T.data(), ctx->d_T, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < H; ++k) {
+      const double* g = cg.data() + 9 * k;
+      double m[3][3];
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { m[i][j] = 0; for (int q = 0; q < 3; ++q) m[i][j] += g[3 * q + i] * g[3 * q + j]; }
+      double fro2 = m[0][0] + m[1][1] + m[2][2];
+      for (int sweep = 0; sweep < 30; ++sweep) {  // cyclic Jacobi on the symmetric 3x3
+        for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) {
+          if (fabs(m[a][b]) < 1e-300) continue;
+          const double th = 0.5 * atan2(2 * m[a][b], m[a][a] - m[b][b]);
+          const double c = cos(th), s2 = sin(th);
+          double r[3][3];
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[i][j] = (i == j) ? 1.0 : 0.0;
+          r[a][a] = c; r[b][b] = c; r[a][b] = -s2; r[b][a] = s2;
+          double t1[3][3], t2[3][3];
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { t1[i][j] = 0; for (int q = 0; q < 3; ++q) t1[i][j] += m[i][q] * r[q][j]; }
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { t2[i][j] = 0; for (int q = 0; q < 3; ++q) t2[i][j] += r[q][i] * t1[q][j]; }
+          for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m[i][j] = t2[i][j];
+        }
+      }
+      double lam = fmax(m[0][0], fmax(m[1][1], m[2][2]));
+      const double off = fabs(m[0][1]) + fabs(m[0][2]) + fabs(m[1][2]);
+      lam += 2 * off;                                  // Gershgorin slack for any residual off-diagonal mass
+      if (!(lam > 0) || !(lam <= fro2 * (1 + 1e-9))) lam = fro2;   // safe fallback: sigma_max <= |G|_F
+      const double smax = sqrt(lam) * (1.0 + 1e-9);
+      double tf = 0;
+      for (int e = 0; e < 9; ++e) tf += T[9 * k + e] * T[9 * k + e];
+      prn[2 * k] = ctx->prm.max_speed * smax;
+      prn[2 * k + 1] = sqrt(tf) * smax;
+    }
+    CU(cudaMemcpy(ctx->d_prn, prn.data(), sizeof(double) * 2 * H, cudaMemcpyHostToDevice));
+  }
   ctx->have_dynamics = true;
   return LQRO_OK;
 }

@@ -30,16 +30,22 @@ struct LqroParams {
   float lp_radius;
   int hull_input;
   int fix_facet0;
+  int prune;        // 1: skip horizon steps whose whole ellipsoid is provably unreachable (exact, see lqro_pair.cuh)
+  double box[3];    // max_s |p_s| per coordinate: bounding box of the ellipsoid samples
 };
 
 // Device tables of one dynamics class (pair independent, built once by k_horizon_tables):
 //   NFt  [16][3H]  NFt[m][k*3+c] = -(C F_k)(c, m)       (transposed for conflict-free shared loads)
 //   T    [H][9]    (C G_k)^-1, row major
 //   sph  [P][3]    samples of the doubled ellipsoid
+//   CG   [H][9]    C G_k (the matrix T_k inverts), row major
+//   prn  [H][2]    pruning constants: R_k = max_speed * sigma_max(C G_k) (upper bound), kappa_k = |T_k|_F * sigma_max(C G_k)
 struct LqroTables {
   const double* NFt;
   const double* T;
   const double* sph;
+  const double* CG;
+  const double* prn;
 };
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

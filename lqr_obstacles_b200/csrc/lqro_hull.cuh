@@ -744,10 +744,10 @@ __global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const 
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int wpb = blockDim.x >> 5;
-  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairTables pt;
   PairWarpSmem pw;
   load_block_tables(smem, tb, p.H, p.P);
-  carve_pair_smem(smem, warp, p.H, p.P, sNFt, sT, sphx, sphy, sphz, pw);
+  carve_pair_smem(smem, warp, p.H, p.P, pt, pw);
   HullCtl* ctl = reinterpret_cast<HullCtl*>(smem + pair_block_table_doubles(p.H, p.P) + (size_t)wpb * pair_warp_doubles(p.H, p.P)) + warp;
   HullWs w;
   hull_ws_carve(ws_base + ws_stride * (size_t)(blockIdx.x * wpb + warp), cap_pts, w);
@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const 
       pw.dx[lane] = a - b;
     }
     __syncwarp();
-    const int n = warp_reachable_cloud(p, sNFt, sT, sphx, sphy, sphz, pw);
+    const int n = warp_reachable_cloud(p, pt, pw);
     for (int m = lane; m < n; m += 32) {
       if (p.hull_input == 0) { w.hx[m] = round6_dev(pw.px[m]); w.hy[m] = round6_dev(pw.py[m]); w.hz[m] = round6_dev(pw.pz[m]); }
       else { w.hx[m] = pw.px[m]; w.hy[m] = pw.py[m]; w.hz[m] = pw.pz[m]; }

@@ -59,7 +59,7 @@ __device__ inline void inverse3_ref(const double* q, double* out) {
 __global__ void __launch_bounds__(256) k_horizon_tables(const double* __restrict__ A, const double* __restrict__ B,
                                                         const double* __restrict__ L, const double* __restrict__ E, int H,
                                                         double* __restrict__ NFt, double* __restrict__ NF,
-                                                        double* __restrict__ T) {
+                                                        double* __restrict__ T, double* __restrict__ CG) {
   __shared__ double sAt[256], sBt[48], sF[256], sG[48], sF2[256], sG2[48];
   const int t = threadIdx.x;
   const int i = t >> 4, j = t & 15;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_horizon_tables(const double* __restrict
     }
     if (t == 0) {  // Transform = !(P*G), MAIN:684
       double cg[9];
-      for (int e = 0; e < 9; ++e) cg[e] = sG[e];  // rows 0..2 of G (16x3 row major)
+      for (int e = 0; e < 9; ++e) { cg[e] = sG[e]; CG[9 * k + e] = cg[e]; }  // rows 0..2 of G (16x3 row major)
       inverse3_ref(cg, T + 9 * k);
     }
     __syncthreads();
@@ -125,6 +125,7 @@ struct HullQueue {
 
 // shared-memory carve-up of one pair warp
 struct PairWarpSmem {
+  int* klist;   // [H]    horizon steps that survive the pruning test
   double* tr;   // [3H]   Translate_k, MAIN:685
   double* dx;   // [16]   x_i - x_j
   double* xi;   // [16]
@@ -134,9 +135,9 @@ struct PairWarpSmem {
   GjkState* gjk;
 };
 
-__host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P; }
+__host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P + 9 * H + 2 * H; }
 __host__ __device__ inline size_t pair_warp_doubles(int H, int P) {
-  return (size_t)3 * H + 32 + 3 * (size_t)H * P + (sizeof(GjkState) + 7) / 8;
+  return (size_t)3 * H + 32 + 3 * (size_t)H * P + (sizeof(GjkState) + 7) / 8 + (H + 1) / 2 + 1;
 }
 
 // exact reachable test, MAIN:703: pow(a,2)/pow(r,2) + pow(b,2)/pow(r,2) + pow(c,2)/pow(r,2) < 1.0
@@ -175,23 +176,63 @@ __device__ __forceinline__ void candidate_point(const double* __restrict__ sT, c
   q2 = Tk[6] * v0 + Tk[7] * v1 + Tk[8] * v2;
 }
 
+// Block-level tables in shared memory.
+struct PairTables {
+  const double *NFt, *T, *sphx, *sphy, *sphz, *CG, *prn;
+};
+
+// EXACT PRUNING of whole horizon steps.  A candidate of step k is q = T_k u with u = p_s + tr_k, and
+// q - v_rel = T_k (u - c_k), c_k = (C G_k) v_rel, so |q - v_rel| >= |p_s + w_k| / sigma_max(C G_k) with
+// w_k = tr_k - c_k.  Every sample p_s lies in the box [-a, a] (a = per-axis max |p_s|), hence
+// min_s |p_s + w_k| >= gap_k = dist(-w_k, box).  If
+//     gap_k > R_k (1 + 1e-6) + 1e-12 kappa_k (|w_k|_1 + |c_k|_1 + 3),      R_k = max_speed sigma_max(C G_k),
+// then every exact |q - v_rel| exceeds max_speed by a relative 1e-6 plus a bound on the rounding error
+// of the reference's own evaluation of q (<= ~2^-48 |T_k|_F |u| per component, scaled into position
+// space by sigma_max: the kappa_k term), so the reference's test `sum((q-c)^2/r^2) < 1` (MAIN:703) is
+// false for all P samples of step k and the step contributes nothing to the reachable cloud.  The
+// surviving steps are evaluated with the reference's arithmetic, so the cloud is identical, bit for bit.
+__device__ __forceinline__ bool step_prunable(const LqroParams& p, const PairTables& t, const double* tr, int k, double vr0, double vr1,
+                                              double vr2) {
+  const double* G = t.CG + 9 * k;
+  const double c0 = fma(G[0], vr0, fma(G[1], vr1, G[2] * vr2));
+  const double c1 = fma(G[3], vr0, fma(G[4], vr1, G[5] * vr2));
+  const double c2 = fma(G[6], vr0, fma(G[7], vr1, G[8] * vr2));
+  const double w0 = tr[3 * k] - c0, w1 = tr[3 * k + 1] - c1, w2 = tr[3 * k + 2] - c2;
+  const double g0 = fmax(0.0, fabs(w0) - p.box[0]), g1 = fmax(0.0, fabs(w1) - p.box[1]), g2 = fmax(0.0, fabs(w2) - p.box[2]);
+  const double gap2 = fma(g0, g0, fma(g1, g1, g2 * g2));
+  const double thr = t.prn[2 * k] * (1.0 + 1.0e-6) +
+                     1.0e-12 * t.prn[2 * k + 1] * (fabs(w0) + fabs(w1) + fabs(w2) + fabs(c0) + fabs(c1) + fabs(c2) + 3.0);
+  return gap2 > thr * thr * (1.0 + 1.0e-9);
+}
+
 // Build the reachable cloud of one pair in shared memory (order preserved), return its size.
 // Requires w.dx (and so v_rel = dx[3..5]) to be set; fills w.tr.
-__device__ __forceinline__ int warp_reachable_cloud(const LqroParams& p, const double* sNFt, const double* sT, const double* sphx,
-                                                    const double* sphy, const double* sphz, PairWarpSmem& w) {
+__device__ __forceinline__ int warp_reachable_cloud(const LqroParams& p, const PairTables& t, PairWarpSmem& w) {
   const int lane = lane_id();
-  warp_translate(sNFt, w.dx, w.tr, p.H);
+  warp_translate(t.NFt, w.dx, w.tr, p.H);
   __syncwarp();
   const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
+  // surviving horizon steps, ascending (order of the cloud is k-major, MAIN:1383-1389)
+  int nk = 0;
+  for (int kb = 0; kb < p.H; kb += 32) {
+    const int k = kb + lane;
+    bool keep = false;
+    if (k < p.H) keep = !(p.prune && step_prunable(p, t, w.tr, k, vr0, vr1, vr2));
+    const unsigned mask = __ballot_sync(LQRO_FULL, keep);
+    if (keep) w.klist[nk + __popc(mask & ((1u << lane) - 1u))] = k;
+    nk += __popc(mask);
+  }
+  __syncwarp();
   int count = 0;
-  int k = 0, s = lane;
-  while (s >= p.P) { s -= p.P; ++k; }
-  for (int base = 0; base < p.HP; base += 32) {
+  const int total = nk * p.P;
+  int ki = 0, s = lane;
+  while (s >= p.P) { s -= p.P; ++ki; }
+  for (int base = 0; base < total; base += 32) {
     const int m = base + lane;
     bool pass = false;
     double q0 = 0, q1 = 0, q2 = 0;
-    if (m < p.HP) {
-      candidate_point(sT, sphx, sphy, sphz, w.tr, k, s, q0, q1, q2);
+    if (m < total) {
+      candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
       pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
     }
     const unsigned mask = __ballot_sync(LQRO_FULL, pass);
@@ -201,19 +242,20 @@ __device__ __forceinline__ int warp_reachable_cloud(const LqroParams& p, const d
     }
     count += __popc(mask);
     s += 32;
-    while (s >= p.P) { s -= p.P; ++k; }
+    while (s >= p.P) { s -= p.P; ++ki; }
   }
   __syncwarp();
   return count;
 }
 
-__device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, int P, const double*& sNFt, const double*& sT,
-                                                const double*& sphx, const double*& sphy, const double*& sphz, PairWarpSmem& w) {
-  sNFt = base;
-  sT = base + 16 * 3 * H;
-  sphx = sT + 9 * H;
-  sphy = sphx + P;
-  sphz = sphy + P;
+__device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, int P, PairTables& t, PairWarpSmem& w) {
+  t.NFt = base;
+  t.T = base + 16 * 3 * H;
+  t.sphx = t.T + 9 * H;
+  t.sphy = t.sphx + P;
+  t.sphz = t.sphy + P;
+  t.CG = t.sphz + P;
+  t.prn = t.CG + 9 * H;
   double* wb = base + pair_block_table_doubles(H, P) + (size_t)warp * pair_warp_doubles(H, P);
   w.tr = wb;
   w.dx = wb + 3 * H;
@@ -222,6 +264,7 @@ __device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, i
   w.py = w.px + (size_t)H * P;
   w.pz = w.py + (size_t)H * P;
   w.gjk = reinterpret_cast<GjkState*>(w.pz + (size_t)H * P);
+  w.klist = reinterpret_cast<int*>(w.pz + (size_t)H * P + (sizeof(GjkState) + 7) / 8);
 }
 
 __device__ __forceinline__ void load_block_tables(double* base, const LqroTables& tb, int H, int P) {
@@ -234,6 +277,9 @@ __device__ __forceinline__ void load_block_tables(double* base, const LqroTables
     sph[P + e] = tb.sph[3 * e + 1];
     sph[2 * P + e] = tb.sph[3 * e + 2];
   }
+  double* cg = sph + 3 * P;
+  for (int e = threadIdx.x; e < nT; e += blockDim.x) cg[e] = tb.CG[e];
+  for (int e = threadIdx.x; e < 2 * H; e += blockDim.x) cg[nT + e] = tb.prn[e];
   __syncthreads();
 }
 
@@ -257,10 +303,10 @@ __global__ void __launch_bounds__(256) k_pairs(LqroParams p, LqroTables tb, cons
                                                PairOutputs out, int* __restrict__ work_counter, HullQueue hq) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairTables t;
   PairWarpSmem w;
   load_block_tables(smem, tb, p.H, p.P);
-  carve_pair_smem(smem, warp, p.H, p.P, sNFt, sT, sphx, sphy, sphz, w);
+  carve_pair_smem(smem, warp, p.H, p.P, t, w);
   const int npairs = p.n_local * p.K;
   while (true) {
     int pair = 0;
@@ -280,7 +326,7 @@ __global__ void __launch_bounds__(256) k_pairs(LqroParams p, LqroTables tb, cons
       w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
     }
     __syncwarp();
-    const int n = warp_reachable_cloud(p, sNFt, sT, sphx, sphy, sphz, w);
+    const int n = warp_reachable_cloud(p, t, w);
     if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
       if (lane == 0) { out.status[pair] = 0; out.nreach[pair] = n; }
       __syncwarp();
@@ -318,18 +364,18 @@ __global__ void __launch_bounds__(32) k_stage_candidates(LqroParams p, LqroTable
                                                          const double* __restrict__ xj, double* __restrict__ q_out) {
   extern __shared__ double smem[];
   const int lane = lane_id();
-  const double *sNFt, *sT, *sphx, *sphy, *sphz;
+  PairTables t;
   PairWarpSmem w;
   load_block_tables(smem, tb, p.H, p.P);
-  carve_pair_smem(smem, 0, p.H, p.P, sNFt, sT, sphx, sphy, sphz, w);
+  carve_pair_smem(smem, 0, p.H, p.P, t, w);
   if (lane < 16) w.dx[lane] = xi[lane] - xj[lane];
   __syncwarp();
-  warp_translate(sNFt, w.dx, w.tr, p.H);
+  warp_translate(t.NFt, w.dx, w.tr, p.H);
   __syncwarp();
   for (int m = lane; m < p.HP; m += 32) {
     const int k = m / p.P, s = m - k * p.P;
     double q0, q1, q2;
-    candidate_point(sT, sphx, sphy, sphz, w.tr, k, s, q0, q1, q2);
+    candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, k, s, q0, q1, q2);
     q_out[3 * m] = q0; q_out[3 * m + 1] = q1; q_out[3 * m + 2] = q2;
   }
 }
