@@ -9,183 +9,216 @@
 // Mapping: one warp per pair.  The support scan over the cloud (the only O(n) part) is spread over
 // the 32 lanes and reduced with shuffles to (max value, lowest index) -- the reference's strict '>'
 // scan (GJK.c:786) keeps the lowest index on ties.  The simplex sub-algorithm (Johnson's deltas over
-// <= 15 subsets) is scalar work: lane 0 runs it on a per-warp state block in shared memory.
+// <= 15 subsets) is scalar work; every lane runs it redundantly on REGISTER-resident state: the subset
+// loops are templates on the simplex size and fully unrolled, so the delta / dot-product tables of
+// GJK.c:163-164 never touch memory and no lane waits for another.
 #pragma once
 #include "lqro_common.cuh"
-
-// Subsets of the <=4 simplex points as bit masks (element lists ascending): cardinality, elements
-// and non-elements.  predecessor(s, j) = s & ~(1 << elt(s, j)), successor(s, k) = s | (1 << nonelt(s, k)).
-__constant__ int c_gjk_card[16] = {0, 1, 1, 2, 1, 2, 2, 3, 1, 2, 2, 3, 2, 3, 3, 4};
-__constant__ signed char c_gjk_elt[16][4] = {
-    {0, 0, 0, 0}, {0, 0, 0, 0}, {1, 0, 0, 0}, {0, 1, 0, 0}, {2, 0, 0, 0}, {0, 2, 0, 0}, {1, 2, 0, 0}, {0, 1, 2, 0},
-    {3, 0, 0, 0}, {0, 3, 0, 0}, {1, 3, 0, 0}, {0, 1, 3, 0}, {2, 3, 0, 0}, {0, 2, 3, 0}, {1, 2, 3, 0}, {0, 1, 2, 3}};
-__constant__ signed char c_gjk_nonelt[16][4] = {
-    {0, 1, 2, 3}, {1, 2, 3, 0}, {0, 2, 3, 0}, {2, 3, 0, 0}, {0, 1, 3, 0}, {1, 3, 0, 0}, {0, 3, 0, 0}, {3, 0, 0, 0},
-    {0, 1, 2, 0}, {1, 2, 0, 0}, {0, 2, 0, 0}, {2, 0, 0, 0}, {0, 1, 0, 0}, {1, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
 
 #define LQRO_GJK_EPS 1.0e-8    // GJK.h:208
 #define LQRO_GJK_TINY 1.0e-20  // GJK.h:214
 
-struct GjkState {
-  double c2[4][3];     // cloud-side coordinates of the simplex points (the other side is always v_rel)
-  double lambdas[4];
-  double del[16][4];   // delta_values[s][element]
-  double dsum[16];     // delta[s]
+// Subsets of the <= 4 simplex points as bit masks; element lists ascending (the tables of GJK.c:88-159).
+// predecessor(s, j) = s & ~(1 << elt(s, j)), successor(s, k) = s | (1 << nonelt(s, k)).
+__host__ __device__ constexpr int gjk_card(int s) { return (s & 1) + ((s >> 1) & 1) + ((s >> 2) & 1) + ((s >> 3) & 1); }
+__host__ __device__ constexpr int gjk_elt(int s, int i) {
+  int c = 0;
+  for (int b = 0; b < 4; ++b)
+    if (s & (1 << b)) { if (c == i) return b; ++c; }
+  return 0;
+}
+__host__ __device__ constexpr int gjk_nonelt(int s, int i) {
+  int c = 0;
+  for (int b = 0; b < 4; ++b)
+    if (!(s & (1 << b))) { if (c == i) return b; ++c; }
+  return 0;
+}
+
+struct GjkRegs {
+  double c2[4][3];   // cloud-side coordinates of the simplex points (the other side is always v_rel)
+  double lam[4];
+  double del[16][4]; // delta_values[s][element]
+  double dsum[16];   // delta[s]
   double prod[4][4];
-  double w1[3], w2[3]; // witness points: on {v_rel}, on conv(cloud)
-  double disp[3];
-  double sqrd;
+  double w1[3], w2[3];
   int npts;
   int use_default;
-  int simplex2[4];
 };
 
 // GJK.c:527-581
-__device__ __forceinline__ void gjk_compute_subterms(GjkState& g, const double* vrel) {
-  const int size = g.npts;
-  double c[4][3];
-  for (int i = 0; i < size; ++i)
-    for (int j = 0; j < 3; ++j) c[i][j] = vrel[j] - g.c2[i][j];
-  for (int i = 0; i < size; ++i)
-    for (int j = i; j < size; ++j) {
-      double v = dot3(c[i][0], c[i][1], c[i][2], c[j][0], c[j][1], c[j][2]);
+template <int SIZE>
+__device__ __forceinline__ void gjk_subterms(GjkRegs& g, double v0, double v1, double v2) {
+  double c[SIZE][3];
+#pragma unroll
+  for (int i = 0; i < SIZE; ++i) { c[i][0] = v0 - g.c2[i][0]; c[i][1] = v1 - g.c2[i][1]; c[i][2] = v2 - g.c2[i][2]; }
+#pragma unroll
+  for (int i = 0; i < SIZE; ++i)
+#pragma unroll
+    for (int j = i; j < SIZE; ++j) {
+      const double v = dot3(c[i][0], c[i][1], c[i][2], c[j][0], c[j][1], c[j][2]);
       g.prod[i][j] = v;
       g.prod[j][i] = v;
     }
-  const int smax = 1 << size;
-  for (int s = 1; s < smax; ++s) {
-    const int cs = c_gjk_card[s];
-    if (cs <= 1) { g.del[s][c_gjk_elt[s][0]] = 1.0; continue; }
-    if (cs == 2) {
-      const int e0 = c_gjk_elt[s][0], e1 = c_gjk_elt[s][1];
+#pragma unroll
+  for (int s = 1; s < (1 << SIZE); ++s) {
+    const int cs = gjk_card(s);
+    if (cs <= 1) {
+      g.del[s][gjk_elt(s, 0)] = 1.0;
+    } else if (cs == 2) {
+      const int e0 = gjk_elt(s, 0), e1 = gjk_elt(s, 1);
       g.del[s][e0] = g.prod[e1][e1] - g.prod[e1][e0];
       g.del[s][e1] = g.prod[e0][e0] - g.prod[e0][e1];
-      continue;
-    }
-    for (int j = 0; j < cs; ++j) {
-      const int jelt = c_gjk_elt[s][j];
-      const int jsub = s & ~(1 << jelt);
-      const int e0 = c_gjk_elt[jsub][0];
-      const int cj = c_gjk_card[jsub];
-      double sum = 0;
-      for (int i = 0; i < cj; ++i) {
-        const int ielt = c_gjk_elt[jsub][i];
-        sum += g.del[jsub][ielt] * (g.prod[ielt][e0] - g.prod[ielt][jelt]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < cs) {
+          const int jelt = gjk_elt(s, j);
+          const int jsub = s & ~(1 << jelt);
+          const int e0 = gjk_elt(jsub, 0);
+          double sum = 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (i < gjk_card(jsub)) {
+              const int ielt = gjk_elt(jsub, i);
+              sum += g.del[jsub][ielt] * (g.prod[ielt][e0] - g.prod[ielt][jelt]);
+            }
+          }
+          g.del[s][jelt] = sum;
+        }
       }
-      g.del[s][jelt] = sum;
     }
   }
 }
 
-// GJK.c:708-736
-__device__ __forceinline__ void gjk_reset_simplex(GjkState& g, int subset) {
-  const int cs = c_gjk_card[subset];
+// GJK.c:708-736 for a compile-time subset
+template <int S>
+__device__ __forceinline__ void gjk_reset_to(GjkRegs& g) {
+  constexpr int cs = gjk_card(S);
+#pragma unroll
   for (int j = 0; j < cs; ++j) {
-    const int oldpos = c_gjk_elt[subset][j];
-    if (oldpos != j) {
-      g.simplex2[j] = g.simplex2[oldpos];
-      for (int i = 0; i < 3; ++i) g.c2[j][i] = g.c2[oldpos][i];
-    }
-    g.lambdas[j] = g.del[subset][oldpos] / g.dsum[subset];
+    const int oldpos = gjk_elt(S, j);
+    if (oldpos != j) { g.c2[j][0] = g.c2[oldpos][0]; g.c2[j][1] = g.c2[oldpos][1]; g.c2[j][2] = g.c2[oldpos][2]; }
+    g.lam[j] = g.del[S][oldpos] / g.dsum[S];
   }
   g.npts = cs;
 }
-
-// GJK.c:593-657
-__device__ __forceinline__ int gjk_default_distance(GjkState& g) {
-  const int size = g.npts;
-  const int smax = 1 << size;
-  int s, ok = 0;
-  for (s = 1; s < smax; ++s) {
-    g.dsum[s] = 0;
-    ok = 1;
-    const int cs = c_gjk_card[s];
-    for (int j = 0; ok && j < cs; ++j) {
-      const double d = g.del[s][c_gjk_elt[s][j]];
-      if (d > 0) g.dsum[s] += d; else ok = 0;
-    }
-    for (int k = 0; ok && k < size - cs; ++k) {
-      const int ne = c_gjk_nonelt[s][k];
-      if (g.del[s | (1 << ne)][ne] > 0) ok = 0;
-    }
-    if (ok && g.dsum[s] >= LQRO_GJK_TINY) break;
+__device__ __forceinline__ void gjk_reset_simplex(GjkRegs& g, int subset) {
+  switch (subset) {
+    case 1: gjk_reset_to<1>(g); break;   case 2: gjk_reset_to<2>(g); break;   case 3: gjk_reset_to<3>(g); break;
+    case 4: gjk_reset_to<4>(g); break;   case 5: gjk_reset_to<5>(g); break;   case 6: gjk_reset_to<6>(g); break;
+    case 7: gjk_reset_to<7>(g); break;   case 8: gjk_reset_to<8>(g); break;   case 9: gjk_reset_to<9>(g); break;
+    case 10: gjk_reset_to<10>(g); break; case 11: gjk_reset_to<11>(g); break; case 12: gjk_reset_to<12>(g); break;
+    case 13: gjk_reset_to<13>(g); break; case 14: gjk_reset_to<14>(g); break; case 15: gjk_reset_to<15>(g); break;
+    default: break;
   }
-  if (ok && s < smax) { gjk_reset_simplex(g, s); return 1; }
+}
+
+// GJK.c:593-657.  Returns 1 when a viable subset was found (and the simplex reset to it).
+template <int SIZE>
+__device__ __forceinline__ int gjk_default_distance(GjkRegs& g) {
+  int sel = 0;
+#pragma unroll
+  for (int s = 1; s < (1 << SIZE); ++s) {
+    if (sel == 0) {
+      const int cs = gjk_card(s);
+      double ds = 0;
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < cs && ok) {
+          const double d = g.del[s][gjk_elt(s, j)];
+          if (d > 0) ds += d; else ok = false;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < SIZE - cs && ok) {
+          const int ne = gjk_nonelt(s, k);
+          if (g.del[s | (1 << ne)][ne] > 0) ok = false;
+        }
+      }
+      g.dsum[s] = ds;
+      if (ok && ds >= LQRO_GJK_TINY) sel = s;
+    }
+  }
+  if (sel) { gjk_reset_simplex(g, sel); return 1; }
   return 0;
 }
 
 // GJK.c:663-706
-__device__ __forceinline__ void gjk_backup_distance(GjkState& g) {
-  const int size = g.npts;
-  const int smax = 1 << size;
+template <int SIZE>
+__device__ __forceinline__ void gjk_backup_distance(GjkRegs& g) {
   int bests = 0;
-  double num[16], den[16];
-  for (int s = 1; s < smax; ++s) {
-    if (g.dsum[s] <= 0) continue;
-    const int cs = c_gjk_card[s];
-    int i;
-    for (i = 0; i < cs; ++i)
-      if (g.del[s][c_gjk_elt[s][i]] <= 0) break;
-    if (i < cs) continue;
-    double acc = 0;
-    for (int j = 0; j < cs; ++j)
-      for (int k = 0; k < cs; ++k) {
-        const int ej = c_gjk_elt[s][j], ek = c_gjk_elt[s][k];
-        acc += (g.del[s][ej] * g.del[s][ek]) * g.prod[ej][ek];
-      }
-    num[s] = acc;
-    den[s] = g.dsum[s] * g.dsum[s];
-    if (bests < 1 || num[s] * den[bests] < num[bests] * den[s]) bests = s;
+  double bnum = 0, bden = 0;
+#pragma unroll
+  for (int s = 1; s < (1 << SIZE); ++s) {
+    const int cs = gjk_card(s);
+    bool viable = g.dsum[s] > 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < cs && g.del[s][gjk_elt(s, i)] <= 0) viable = false;
+    if (viable) {
+      double acc = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (j < cs && k < cs) {
+            const int ej = gjk_elt(s, j), ek = gjk_elt(s, k);
+            acc += (g.del[s][ej] * g.del[s][ek]) * g.prod[ej][ek];
+          }
+      const double den = g.dsum[s] * g.dsum[s];
+      if (bests < 1 || acc * bden < bnum * den) { bests = s; bnum = acc; bden = den; }
+    }
   }
   gjk_reset_simplex(g, bests);
 }
 
-// Scalar half of one main-loop iteration (GJK.c:374-413): sub-algorithm, witnesses, displacement.
-__device__ __forceinline__ void gjk_scalar_step(GjkState& g, const double* vrel) {
-  if (g.npts == 1) {
-    g.lambdas[0] = 1.0;
-  } else {
-    gjk_compute_subterms(g, vrel);
-    if (g.use_default) g.use_default = gjk_default_distance(g);
-    if (!g.use_default) gjk_backup_distance(g);
-  }
-  for (int d = 0; d < 3; ++d) {  // compute_point, GJK.c:851-862 (accumulated from 0)
-    double a = 0, b = 0;
-    for (int i = 0; i < g.npts; ++i) a += vrel[d] * g.lambdas[i];
-    for (int i = 0; i < g.npts; ++i) b += g.c2[i][d] * g.lambdas[i];
-    g.w1[d] = a;
-    g.w2[d] = b;
-  }
-  for (int d = 0; d < 3; ++d) g.disp[d] = g.w2[d] - g.w1[d];
-  g.sqrd = dot3(g.disp[0], g.disp[1], g.disp[2], g.disp[0], g.disp[1], g.disp[2]);
+template <int SIZE>
+__device__ __forceinline__ void gjk_simplex_step(GjkRegs& g, double v0, double v1, double v2) {
+  gjk_subterms<SIZE>(g, v0, v1, v2);
+  if (g.use_default) g.use_default = gjk_default_distance<SIZE>(g);
+  if (!g.use_default) gjk_backup_distance<SIZE>(g);
 }
 
-// Warp-cooperative GJK.  px/py/pz: the cloud (shared or global), n points.  Returns d^2 (uniform
-// across the warp); witnesses are left in g.w1 / g.w2; *iters receives the number of G-tests.
-__device__ __forceinline__ double gjk_warp(GjkState& g, const double vrel0, const double vrel1, const double vrel2,
-                                           const double* __restrict__ px, const double* __restrict__ py,
-                                           const double* __restrict__ pz, int n, int* iters) {
+// Warp-cooperative GJK.  px/py/pz: the cloud (shared or global), n points.  Returns d^2 (uniform across
+// the warp); witnesses in w1 (on {v_rel}) / w2 (on conv(cloud)); *iters = number of G-tests.
+__device__ __forceinline__ double gjk_warp(const double v0, const double v1, const double v2, const double* __restrict__ px,
+                                           const double* __restrict__ py, const double* __restrict__ pz, int n, double* w1out,
+                                           double* w2out, int* iters) {
   const int lane = lane_id();
-  const double vrel[3] = {vrel0, vrel1, vrel2};
-  if (lane == 0) {  // GJK.c:340-347
-    g.npts = 1;
-    g.simplex2[0] = 0;
-    g.lambdas[0] = 1.0;
-    g.c2[0][0] = px[0]; g.c2[0][1] = py[0]; g.c2[0][2] = pz[0];
-    g.use_default = 1;
-  }
-  __syncwarp();
+  GjkRegs g;
+  g.npts = 1;  // GJK.c:340-347
+  g.lam[0] = 1.0;
+  g.c2[0][0] = px[0]; g.c2[0][1] = py[0]; g.c2[0][2] = pz[0];
+  g.use_default = 1;
   int first_iteration = 1;
   double oldsqrd = 0.0, sqrd = 0.0;
   int max_iterations = n;  // NumVertices(obj1) * NumVertices(obj2), GJK.c:367
   int ntests = 0;
   bool exhausted = true;
   while (max_iterations-- > 0) {
-    if (lane == 0) gjk_scalar_step(g, vrel);
-    __syncwarp();
-    sqrd = g.sqrd;
+    if (g.npts == 1) g.lam[0] = 1.0;
+    else if (g.npts == 2) gjk_simplex_step<2>(g, v0, v1, v2);
+    else if (g.npts == 3) gjk_simplex_step<3>(g, v0, v1, v2);
+    else gjk_simplex_step<4>(g, v0, v1, v2);
+    // compute_point (GJK.c:851-862), accumulated from 0
+    {
+      const double vv[3] = {v0, v1, v2};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < g.npts) a += vv[d] * g.lam[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < g.npts) b += g.c2[i][d] * g.lam[i];
+        g.w1[d] = a;
+        g.w2[d] = b;
+      }
+    }
+    const double d0 = g.w2[0] - g.w1[0], d1 = g.w2[1] - g.w1[1], d2 = g.w2[2] - g.w1[2];
+    sqrd = dot3(d0, d1, d2, d0, d1, d2);
     if (sqrd < LQRO_GJK_EPS) { exhausted = false; break; }  // GJK.c:419-422
-    const double d0 = g.disp[0], d1 = g.disp[1], d2 = g.disp[2];
     const double r0 = -d0, r1 = -d1, r2 = -d2;  // reverse_displacementv
     // support of the cloud in direction r (support_simple, GJK.c:770-794)
     double best = -1.7976931348623157e308;
@@ -202,37 +235,28 @@ __device__ __forceinline__ double gjk_warp(GjkState& g, const double vrel0, cons
     }
     const double minus_minv = best;
     const int minp = besti;
-    const double maxv = dot3(vrel0, vrel1, vrel2, d0, d1, d2);  // support of the single point
+    const double maxv = dot3(v0, v1, v2, d0, d1, d2);  // support of the single point
     ++ntests;
     double g_val = sqrd + maxv + minus_minv;  // GJK.c:450
     if (g_val < 0.0) g_val = 0;
     if (g_val < LQRO_GJK_EPS) { exhausted = false; break; }
-    const int npts = g.npts;
-    if ((first_iteration || sqrd < oldsqrd) && npts <= 3) {  // GJK.c:472-487
-      __syncwarp();
-      if (lane == 0) {
-        g.simplex2[npts] = minp;
-        g.lambdas[npts] = 0.0;
-        g.c2[npts][0] = px[minp]; g.c2[npts][1] = py[minp]; g.c2[npts][2] = pz[minp];
-        g.npts = npts + 1;
-        g.use_default = 1;
-      }
-      __syncwarp();
+    if ((first_iteration || sqrd < oldsqrd) && g.npts <= 3) {  // GJK.c:472-487
+      const double nx = px[minp], ny = py[minp], nz = pz[minp];
+#pragma unroll
+      for (int i = 1; i < 4; ++i)
+        if (i == g.npts) { g.c2[i][0] = nx; g.c2[i][1] = ny; g.c2[i][2] = nz; g.lam[i] = 0.0; }
+      g.npts++;
+      g.use_default = 1;
       oldsqrd = sqrd;
       first_iteration = 0;
       continue;
     }
-    const int use_default = g.use_default;  // GJK.c:490-496
-    __syncwarp();
-    if (use_default) {
-      if (lane == 0) g.use_default = 0;
-      __syncwarp();
-    } else {
-      exhausted = false;
-      break;
-    }
+    if (g.use_default) g.use_default = 0;  // GJK.c:490-496
+    else { exhausted = false; break; }
   }
   if (iters) *iters = ntests;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { w1out[d] = g.w1[d]; w2out[d] = g.w2[d]; }
   if (exhausted) return 0.0;  // GJK.c:499
   return sqrd;
 }

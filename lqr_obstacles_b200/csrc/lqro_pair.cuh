@@ -132,12 +132,11 @@ struct PairWarpSmem {
   double* px;   // [HP]   reachable cloud, SoA
   double* py;
   double* pz;
-  GjkState* gjk;
 };
 
 __host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P + 9 * H + 2 * H; }
 __host__ __device__ inline size_t pair_warp_doubles(int H, int P) {
-  return (size_t)3 * H + 32 + 3 * (size_t)H * P + (sizeof(GjkState) + 7) / 8 + (H + 1) / 2 + 1;
+  return (size_t)3 * H + 32 + 3 * (size_t)H * P + (H + 1) / 2 + 1;
 }
 
 // exact reachable test, MAIN:703: pow(a,2)/pow(r,2) + pow(b,2)/pow(r,2) + pow(c,2)/pow(r,2) < 1.0
@@ -263,8 +262,7 @@ __device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, i
   w.px = w.xi + 16;
   w.py = w.px + (size_t)H * P;
   w.pz = w.py + (size_t)H * P;
-  w.gjk = reinterpret_cast<GjkState*>(w.pz + (size_t)H * P);
-  w.klist = reinterpret_cast<int*>(w.pz + (size_t)H * P + (sizeof(GjkState) + 7) / 8);
+  w.klist = reinterpret_cast<int*>(w.pz + (size_t)H * P);
 }
 
 __device__ __forceinline__ void load_block_tables(double* base, const LqroTables& tb, int H, int P) {
@@ -333,16 +331,16 @@ __global__ void __launch_bounds__(256) k_pairs(LqroParams p, LqroTables tb, cons
       continue;
     }
     const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
-    const double sq = gjk_warp(*w.gjk, vr0, vr1, vr2, w.px, w.py, w.pz, n, nullptr);
+    double gw1[3], gw2[3];
+    const double sq = gjk_warp(vr0, vr1, vr2, w.px, w.py, w.pz, n, gw1, gw2, nullptr);
     if (lane == 0) {
       const double distance = sqrt(sq);                    // MAIN:741
       const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
       out.nreach[pair] = n;
       if (!inside) {
-        const GjkState& g = *w.gjk;
-        const double n0 = (g.w1[0] - g.w2[0]) / distance;  // MAIN:743-745
-        const double n1 = (g.w1[1] - g.w2[1]) / distance;
-        const double n2 = (g.w1[2] - g.w2[2]) / distance;
+        const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
+        const double n1 = (gw1[1] - gw2[1]) / distance;
+        const double n2 = (gw1[2] - gw2[2]) / distance;
         write_plane(out.planes + 6 * (size_t)pair, w.xi + 3, distance, n0, n1, n2, false);
         out.dist[pair] = distance;
         out.status[pair] = 1;
@@ -401,16 +399,16 @@ __global__ void __launch_bounds__(32) k_stage_reachable(LqroParams p, const doub
 __global__ void __launch_bounds__(32) k_stage_gjk(const double* __restrict__ vrel, const double* __restrict__ pts, int n,
                                                   double* __restrict__ scratch /*3n*/, double* __restrict__ out /*sqd, w2[3]*/,
                                                   int* __restrict__ iters) {
-  __shared__ GjkState g;
   const int lane = lane_id();
   double* px = scratch; double* py = scratch + n; double* pz = scratch + 2 * (size_t)n;
   for (int m = lane; m < n; m += 32) { px[m] = pts[3 * m]; py[m] = pts[3 * m + 1]; pz[m] = pts[3 * m + 2]; }
   __syncwarp();
   int it = 0;
-  const double sq = gjk_warp(g, vrel[0], vrel[1], vrel[2], px, py, pz, n, &it);
+  double w1[3], w2[3];
+  const double sq = gjk_warp(vrel[0], vrel[1], vrel[2], px, py, pz, n, w1, w2, &it);
   if (lane == 0) {
-    out[0] = sq; out[1] = g.w2[0]; out[2] = g.w2[1]; out[3] = g.w2[2];
-    out[4] = g.w1[0]; out[5] = g.w1[1]; out[6] = g.w1[2];
+    out[0] = sq; out[1] = w2[0]; out[2] = w2[1]; out[3] = w2[2];
+    out[4] = w1[0]; out[5] = w1[1]; out[6] = w1[2];
     *iters = it;
   }
 }
