@@ -241,17 +241,17 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     // contexts with different H*P can coexist
     CUC(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    ctx->hull_wpb = 2;
-    ctx->hull_smem = tbl + per * ctx->hull_wpb + sizeof(HullCtl) * ctx->hull_wpb + 16;
-    CUC(cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    int per_sm = (int)(ctx->smem_optin / ctx->hull_smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int slots = cfg->hull_slots > 0 ? cfg->hull_slots : ctx->sm_count * per_sm * ctx->hull_wpb;
-    slots = (slots + ctx->hull_wpb - 1) / ctx->hull_wpb * ctx->hull_wpb;
-    ctx->hull_slots = slots;
-    ctx->hull_blocks = slots / ctx->hull_wpb;
+    ctx->hull_wpb = 1;
     ctx->cap_pts = H * P;
+    ctx->hull_smem = hull_block_smem_bytes(H, P);
+    if (ctx->hull_smem > ctx->smem_optin) { g_create_err = "H*P too large for the hull kernel's shared memory"; return bail(LQRO_E_LIMIT); }
+    CUC(cudaFuncSetAttribute(k_hull, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    int per_sm = (int)((ctx->smem_optin + 1024) / (ctx->hull_smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int slots = cfg->hull_slots > 0 ? cfg->hull_slots : ctx->sm_count * per_sm;
+    ctx->hull_slots = slots;
+    ctx->hull_blocks = slots;
     ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
     CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * (size_t)slots));
   }
@@ -528,12 +528,12 @@ static int run_stage_hull(lqro_ctx* ctx, const double* pts, int n, int mode, dou
   const size_t nf_cap = 2 * (size_t)n + 64;
   int rc = ensure_scratch(ctx, sizeof(double) * (6 * (size_t)n + 4 * nf_cap + 16) + sizeof(int) * (3 * nf_cap + 16));
   if (rc) return rc;
-  double* dp = (double*)ctx->d_scratch; double* du = dp + 3 * (size_t)n; double* dpl = du + 3 * (size_t)n;
+  double* dp = (double*)ctx->d_scratch; double* dpl = dp + 6 * (size_t)n;
   double* dv = dpl + 4 * nf_cap; double* desc = dv + 4;
   int* dvt = (int*)(desc + 4); int* dinfo = dvt + 3 * nf_cap;
   CU(cudaMemcpyAsync(dp, pts, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
   if (vrel) CU(cudaMemcpyAsync(dv, vrel, sizeof(double) * 3, cudaMemcpyHostToDevice, ctx->stream));
-  k_stage_hull<<<1, 32, 0, ctx->stream>>>(dp, n, mode, ctx->d_stage_ws, cap, dpl, dvt, (int)nf_cap, dinfo, vrel ? dv : nullptr, desc, du);
+  k_stage_hull<<<1, 32, 0, ctx->stream>>>(dp, n, mode, ctx->d_stage_ws, cap, dpl, dvt, (int)nf_cap, dinfo, vrel ? dv : nullptr, desc);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(info5, dinfo, sizeof(int) * 5, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));

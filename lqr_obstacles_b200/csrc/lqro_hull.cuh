@@ -90,50 +90,70 @@ __global__ void k_round6(const double* __restrict__ in, int n, double* __restric
 }
 
 // ---- workspace ---------------------------------------------------------------------------------
-struct HFacet {
+// All indices are 16-bit (H*P <= 8192 points, <= 2*H*P+64 facets): the hot structures of one hull then fit
+// in shared memory next to the tables (fast path); a hull that needs more facets than the shared pool
+// holds is re-run on the full-size pool in global memory (same code, other pointers).
+typedef short hidx;
+struct HFacet {           // 72 bytes
   double n[3], off;
   double furthestdist;
-  int v[3];    // vertex ids, decreasing
-  int nb[3];   // neighbour opposite v[i]
-  int prev, next;
-  int ohead, olast, oprev;  // outside list (furthest last)
-  int tag;     // scratch: BFS visit id / cone-local index
-  int replace;
+  hidx v[3];              // vertex ids, decreasing
+  hidx nb[3];             // neighbour opposite v[i]
+  hidx prev, next;
+  hidx ohead, olast, oprev;  // outside list (furthest last)
+  hidx tag;               // scratch: BFS visit id (negative) / cone-local index
+  hidx replace;
   unsigned char toporient, visible, isnew, pad;
 };
 
 struct HullWs {
-  double *hx, *hy, *hz;  // hull input coordinates [cap_pts]
-  double* pdist;         // [cap_pts]
-  int *pnext, *pbest, *plist, *pstart, *vpoint;  // [cap_pts] (+8 for vpoint)
-  HFacet* F;             // [cap_f]; F[0] is the list sentinel
-  int *order, *newf, *vis, *freel;  // [cap_f]
+  double *hx, *hy, *hz;   // hull input coordinates [cap_pts]            (global)
+  double *ux, *uy, *uz;   // un-rounded cloud [cap_pts]                  (global)
+  double* pdist;          // [cap_pts]
+  hidx *pnext, *pbest, *plist, *pstart, *vpoint;  // [cap_pts + 8]
+  HFacet* F;              // [cap_f]; F[0] is the list sentinel
+  hidx *order, *newf, *vis, *freel;  // [cap_f], newf [LQRO_HULL_MAXNEW]
   int cap_pts, cap_f;
 };
 
-__host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
-  const size_t cap_f = 2 * (size_t)cap_pts + 64;
+__host__ __device__ inline size_t hull_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+// bytes of the hot structures for a facet pool of cap_f (shared memory fast path, or inside the global slot)
+__host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   size_t b = 0;
-  b += 4 * sizeof(double) * (size_t)cap_pts;        // hx hy hz pdist
-  b += 5 * sizeof(int) * ((size_t)cap_pts + 8);      // pnext pbest plist pstart vpoint
-  b = (b + 15) & ~(size_t)15;
-  b += sizeof(HFacet) * cap_f;
-  b += 4 * sizeof(int) * cap_f;                      // order newf vis freel
+  b += hull_align16(sizeof(HFacet) * (size_t)cap_f);
+  b += hull_align16(sizeof(double) * (size_t)cap_pts);                  // pdist
+  b += hull_align16(sizeof(hidx) * 5 * ((size_t)cap_pts + 8));          // pnext pbest plist pstart vpoint
+  b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + LQRO_HULL_MAXNEW));  // order vis freel newf
+  return b;
+}
+__host__ __device__ inline int hull_full_facets(int cap_pts) { return 2 * cap_pts + 64; }
+// one global slot: 6 coordinate arrays + a full-size copy of the hot structures (fallback path)
+__host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
+  size_t b = hull_align16(6 * sizeof(double) * (size_t)cap_pts) + hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
   return (b + 255) & ~(size_t)255;
 }
-__device__ inline void hull_ws_carve(char* base, int cap_pts, HullWs& w) {
-  const size_t cap_f = 2 * (size_t)cap_pts + 64;
-  w.cap_pts = cap_pts; w.cap_f = (int)cap_f;
-  double* d = reinterpret_cast<double*>(base);
-  w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts; w.pdist = d + 3 * (size_t)cap_pts;
-  int* ip = reinterpret_cast<int*>(d + 4 * (size_t)cap_pts);
+__device__ inline void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs& w) {
+  w.cap_pts = cap_pts; w.cap_f = cap_f;
+  w.F = reinterpret_cast<HFacet*>(base);
+  base += hull_align16(sizeof(HFacet) * (size_t)cap_f);
+  w.pdist = reinterpret_cast<double*>(base);
+  base += hull_align16(sizeof(double) * (size_t)cap_pts);
+  hidx* ip = reinterpret_cast<hidx*>(base);
   const size_t ci = (size_t)cap_pts + 8;
   w.pnext = ip; w.pbest = ip + ci; w.plist = ip + 2 * ci; w.pstart = ip + 3 * ci; w.vpoint = ip + 4 * ci;
-  size_t off = 4 * sizeof(double) * (size_t)cap_pts + 5 * sizeof(int) * ci;
-  off = (off + 15) & ~(size_t)15;
-  w.F = reinterpret_cast<HFacet*>(base + off);
-  int* jp = reinterpret_cast<int*>(base + off + sizeof(HFacet) * cap_f);
-  w.order = jp; w.newf = jp + cap_f; w.vis = jp + 2 * cap_f; w.freel = jp + 3 * cap_f;
+  base += hull_align16(sizeof(hidx) * 5 * ci);
+  hidx* jp = reinterpret_cast<hidx*>(base);
+  w.order = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f; w.newf = jp + 3 * (size_t)cap_f;
+}
+__device__ inline void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {
+  double* d = reinterpret_cast<double*>(gbase);
+  w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
+  w.ux = d + 3 * (size_t)cap_pts; w.uy = d + 4 * (size_t)cap_pts; w.uz = d + 5 * (size_t)cap_pts;
+}
+// everything in the global slot (fallback / stage kernel)
+__device__ inline void hull_ws_carve(char* gbase, int cap_pts, HullWs& w) {
+  hull_carve_coords(gbase, cap_pts, w);
+  hull_carve_hot(gbase + hull_align16(6 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
 }
 
 // per-warp control block in shared memory (written by lane 0, read by all after __syncwarp)
@@ -181,7 +201,7 @@ __device__ inline int hl_newfacet(HullWs& w, HullCtl& c) {
   int f;
   if (c.nfree > 0) f = w.freel[--c.nfree];
   else if (c.pool_used < w.cap_f) f = c.pool_used++;
-  else { c.fail = 1; return -1; }
+  else { c.fail = 2; return -1; }  // pool exhausted
   HFacet& F = w.F[f];
   F.prev = F.next = -1; F.ohead = F.olast = F.oprev = -1; F.furthestdist = 0; F.tag = 0; F.replace = -1;
   F.toporient = F.visible = F.isnew = 0;
@@ -560,7 +580,8 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
             int horizonskip = -1;
             for (int q = 0; q < 3; ++q) if (w.F[nb].nb[q] == vf) { horizonskip = q; break; }
             const int nf = hl_newfacet(w, c);
-            if (nf < 0 || horizonskip < 0 || c.nnew >= LQRO_HULL_MAXNEW) { c.fail = 1; break; }
+            if (nf < 0) break;  // c.fail = 2 set by hl_newfacet
+            if (horizonskip < 0 || c.nnew >= LQRO_HULL_MAXNEW) { c.fail = 3; break; }
             HFacet& HZ = w.F[nb];
             HFacet& NF = w.F[nf];
             NF.v[0] = apex;
@@ -607,7 +628,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
     __syncwarp();
     if (lane == 0) {
       if (deg == 1) c.degenerate = 1;
-      if (deg == 2) c.fail = 1;
+      if (deg == 2) c.fail = 3;
       // qh_sharpnewfacets
       c.sharp = 0;
       if (nnew > 0) {
@@ -735,24 +756,44 @@ __device__ inline void hull_nearest_facet(const HullWs& w, const HullCtl& c, con
 }
 
 // ---- kernels -------------------------------------------------------------------------------------
+// shared-memory facet pool of the fast path (facets alive at once; typical LQR-obstacle hulls need < 700)
+#define LQRO_HULL_SMEM_FACETS 768
+
+__host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
+  size_t b = sizeof(double) * (pair_block_table_doubles(H, P) + 3 * (size_t)H + 32 + (H + 1) / 2 + 1);  // tables + tr, dx, xi, klist
+  b = hull_align16(b) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) + hull_align16(sizeof(HullCtl));
+  return b;
+}
+
 // Inside-case pairs queued by k_pairs: regenerate the reachable cloud (same code, same bits), render
-// it to 6 digits, hull it, pick the nearest facet, write the plane.  One warp per queued pair;
-// warps take hull workspaces by index (grid is sized to the number of workspaces).
-__global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+// it to 6 digits, hull it, pick the nearest facet, write the plane.  One warp (= one block) per queued
+// pair at a time; blocks take work items from an atomic counter and own one global workspace slot.
+__global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
                                              size_t ws_stride, int cap_pts, int* __restrict__ counters) {
   extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int wpb = blockDim.x >> 5;
+  const int lane = lane_id();
+  int nq = *hq.count;
+  if (nq > hq.capacity) nq = hq.capacity;
+  if ((int)blockIdx.x >= nq) return;  // nothing can be left for this block
   PairTables pt;
   PairWarpSmem pw;
   load_block_tables(smem, tb, p.H, p.P);
-  carve_pair_smem(smem, warp, p.H, p.P, pt, pw);
-  HullCtl* ctl = reinterpret_cast<HullCtl*>(smem + pair_block_table_doubles(p.H, p.P) + (size_t)wpb * pair_warp_doubles(p.H, p.P)) + warp;
+  // small per-warp scratch right after the tables; the cloud itself goes to the global slot
+  {
+    const int H = p.H, P = p.P;
+    pt.NFt = smem; pt.T = smem + 16 * 3 * H; pt.sphx = pt.T + 9 * H; pt.sphy = pt.sphx + P; pt.sphz = pt.sphy + P;
+    pt.CG = pt.sphz + P; pt.prn = pt.CG + 9 * H;
+    double* wb = smem + pair_block_table_doubles(H, P);
+    pw.tr = wb; pw.dx = wb + 3 * H; pw.xi = pw.dx + 16; pw.klist = reinterpret_cast<int*>(pw.xi + 16);
+  }
+  char* hot = reinterpret_cast<char*>(smem) +
+              hull_align16(sizeof(double) * (pair_block_table_doubles(p.H, p.P) + 3 * (size_t)p.H + 32 + (p.H + 1) / 2 + 1));
+  HullCtl* ctl = reinterpret_cast<HullCtl*>(hot + hull_hot_bytes(cap_pts, LQRO_HULL_SMEM_FACETS));
+  char* gslot = ws_base + ws_stride * (size_t)blockIdx.x;
   HullWs w;
-  hull_ws_carve(ws_base + ws_stride * (size_t)(blockIdx.x * wpb + warp), cap_pts, w);
-  int nq = *hq.count;
-  if (nq > hq.capacity) nq = hq.capacity;
+  hull_carve_coords(gslot, cap_pts, w);
+  pw.px = w.ux; pw.py = w.uy; pw.pz = w.uz;
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(work_counter, 1);
@@ -770,18 +811,24 @@ __global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const 
     __syncwarp();
     const int n = warp_reachable_cloud(p, pt, pw);
     for (int m = lane; m < n; m += 32) {
-      if (p.hull_input == 0) { w.hx[m] = round6_dev(pw.px[m]); w.hy[m] = round6_dev(pw.py[m]); w.hz[m] = round6_dev(pw.pz[m]); }
-      else { w.hx[m] = pw.px[m]; w.hy[m] = pw.py[m]; w.hz[m] = pw.pz[m]; }
+      if (p.hull_input == 0) { w.hx[m] = round6_dev(w.ux[m]); w.hy[m] = round6_dev(w.uy[m]); w.hz[m] = round6_dev(w.uz[m]); }
+      else { w.hx[m] = w.ux[m]; w.hy[m] = w.uy[m]; w.hz[m] = w.uz[m]; }
     }
     __syncwarp();
+    hull_carve_hot(hot, cap_pts, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures in shared memory
     hull_build(w, *ctl, n);
+    if (ctl->fail == 2) {                                       // pool too small: full-size pool in the global slot
+      hull_carve_hot(gslot + hull_align16(6 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+      hull_build(w, *ctl, n);
+      if (lane == 0) atomicAdd(counters + 5, 1);
+    }
     if (ctl->fail) {
       if (lane == 0) { out.status[pair] = 0x100; out.nfacets[pair] = 0; atomicAdd(counters + 3, 1); }  // no plane
       __syncwarp();
       continue;
     }
     double distance, normal[3]; int bestf;
-    hull_nearest_facet(w, *ctl, pw.px, pw.py, pw.pz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
+    hull_nearest_facet(w, *ctl, w.ux, w.uy, w.uz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
     if (lane == 0) {
       write_plane(out.planes + 6 * (size_t)pair, pw.xi + 3, distance, normal[0], normal[1], normal[2], true);
       out.dist[pair] = distance;
@@ -793,20 +840,20 @@ __global__ void __launch_bounds__(64) k_hull(LqroParams p, LqroTables tb, const 
   }
 }
 
-// Stage kernel: hull of an arbitrary cloud (AoS pts in global memory).  mode bit 0: apply the 6-digit
-// rendering first.  Outputs facets in qhull order (planes nf*4, verts nf*3 as point indices); when
-// vrel != NULL also the nearest-facet result (escape[0] = distance, [1..3] = normal) and best facet.
+// Stage kernel: hull of an arbitrary cloud (AoS pts in global memory), everything in the global slot.
+// mode bit 0: apply the 6-digit rendering first.  Outputs facets in qhull order (planes nf*4, verts nf*3
+// as point indices); when vrel != NULL also the nearest-facet result (escape[0] = distance,
+// [1..3] = normal) and best facet.
 __global__ void __launch_bounds__(32) k_stage_hull(const double* __restrict__ pts, int n, int mode, char* __restrict__ ws_base, int cap_pts,
                                                    double* __restrict__ planes, int* __restrict__ verts, int maxf, int* __restrict__ info /*nf, degenerate, fail, ninserted, best*/,
-                                                   const double* __restrict__ vrel, double* __restrict__ escape, double* __restrict__ uscratch /*3n*/) {
+                                                   const double* __restrict__ vrel, double* __restrict__ escape) {
   __shared__ HullCtl ctl;
   const int lane = lane_id();
   HullWs w;
   hull_ws_carve(ws_base, cap_pts, w);
-  double* ux = uscratch; double* uy = uscratch + n; double* uz = uscratch + 2 * (size_t)n;
   for (int m = lane; m < n && m < cap_pts; m += 32) {
     const double a = pts[3 * m], b = pts[3 * m + 1], c = pts[3 * m + 2];
-    ux[m] = a; uy[m] = b; uz[m] = c;
+    w.ux[m] = a; w.uy[m] = b; w.uz[m] = c;
     if (mode & 1) { w.hx[m] = round6_dev(a); w.hy[m] = round6_dev(b); w.hz[m] = round6_dev(c); }
     else { w.hx[m] = a; w.hy[m] = b; w.hz[m] = c; }
   }
@@ -822,7 +869,7 @@ __global__ void __launch_bounds__(32) k_stage_hull(const double* __restrict__ pt
   }
   if (vrel) {
     double distance, normal[3]; int bestf;
-    hull_nearest_facet(w, ctl, ux, uy, uz, vrel[0], vrel[1], vrel[2], &distance, normal, &bestf);
+    hull_nearest_facet(w, ctl, w.ux, w.uy, w.uz, vrel[0], vrel[1], vrel[2], &distance, normal, &bestf);
     if (lane == 0) { escape[0] = distance; escape[1] = normal[0]; escape[2] = normal[1]; escape[3] = normal[2]; info[4] = bestf; }
   }
 }
