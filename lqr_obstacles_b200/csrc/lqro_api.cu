@@ -186,7 +186,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMalloc(&ctx->d_T, sizeof(double) * 9 * H));
   CUC(cudaMalloc(&ctx->d_sph, sizeof(double) * 3 * P));
   CUC(cudaMalloc(&ctx->d_CG, sizeof(double) * 9 * H));
-  CUC(cudaMalloc(&ctx->d_prn, sizeof(double) * 2 * H));
+  CUC(cudaMalloc(&ctx->d_prn, sizeof(double) * LQRO_PRN * H));
   const size_t NP = (size_t)NL * K;
   CUC(cudaMalloc(&ctx->d_x, sizeof(double) * 16 * (size_t)N));
   CUC(cudaMalloc(&ctx->d_vpref, sizeof(double) * 3 * (size_t)NL));
@@ -301,7 +301,7 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
   // true value, falling back to the Frobenius norm) and kappa_k = |T_k|_F * sigma_max.
   {
     const int H = ctx->prm.H;
-    std::vector<double> cg(9 * (size_t)H), T(9 * (size_t)H), prn(2 * (size_t)H);
+    std::vector<double> cg(9 * (size_t)H), T(9 * (size_t)H), prn(LQRO_PRN * (size_t)H, 0.0);
     CU(cudaMemcpy(cg.data(), ctx->d_CG, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(T.data(), ctx->d_T, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
     for (int k = 0; k < H; ++k) {
@@ -328,12 +328,16 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
       lam += 2 * off;                                  // Gershgorin slack for any residual off-diagonal mass
       if (!(lam > 0) || !(lam <= fro2 * (1 + 1e-9))) lam = fro2;   // safe fallback: sigma_max <= |G|_F
       const double smax = sqrt(lam) * (1.0 + 1e-9);
-      double tf = 0;
-      for (int e = 0; e < 9; ++e) tf += T[9 * k + e] * T[9 * k + e];
-      prn[2 * k] = ctx->prm.max_speed * smax;
-      prn[2 * k + 1] = sqrt(tf) * smax;
+      double tf = 0, ef = 0;
+      for (int e = 0; e < 9; ++e) { tf += T[9 * k + e] * T[9 * k + e]; if (e % 4 != 0) ef += T[9 * k + e] * T[9 * k + e]; }
+      double* c = prn.data() + LQRO_PRN * (size_t)k;
+      c[0] = ctx->prm.max_speed * smax;
+      c[1] = sqrt(tf) * smax * (1.0 + 1e-9);
+      c[2] = fabs(T[9 * k + 0]); c[3] = fabs(T[9 * k + 4]); c[4] = fabs(T[9 * k + 8]);
+      c[5] = sqrt(ef) * (1.0 + 1e-9);
+      c[6] = sqrt(tf) * (1.0 + 1e-9);
     }
-    CU(cudaMemcpy(ctx->d_prn, prn.data(), sizeof(double) * 2 * H, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_prn, prn.data(), sizeof(double) * LQRO_PRN * H, cudaMemcpyHostToDevice));
   }
   ctx->have_dynamics = true;
   return LQRO_OK;

@@ -134,7 +134,8 @@ struct PairWarpSmem {
   double* pz;
 };
 
-__host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P + 9 * H + 2 * H; }
+#define LQRO_PRN 8  // doubles of pruning constants per horizon step
+__host__ __device__ inline size_t pair_block_table_doubles(int H, int P) { return (size_t)16 * 3 * H + 9 * H + 3 * P + 9 * H + LQRO_PRN * H; }
 __host__ __device__ inline size_t pair_warp_doubles(int H, int P) {
   return (size_t)3 * H + 32 + 3 * (size_t)H * P + (H + 1) / 2 + 1;
 }
@@ -181,27 +182,41 @@ struct PairTables {
 };
 
 // EXACT PRUNING of whole horizon steps.  A candidate of step k is q = T_k u with u = p_s + tr_k, and
-// q - v_rel = T_k (u - c_k), c_k = (C G_k) v_rel, so |q - v_rel| >= |p_s + w_k| / sigma_max(C G_k) with
-// w_k = tr_k - c_k.  Every sample p_s lies in the box [-a, a] (a = per-axis max |p_s|), hence
-// min_s |p_s + w_k| >= gap_k = dist(-w_k, box).  If
-//     gap_k > R_k (1 + 1e-6) + 1e-12 kappa_k (|w_k|_1 + |c_k|_1 + 3),      R_k = max_speed sigma_max(C G_k),
-// then every exact |q - v_rel| exceeds max_speed by a relative 1e-6 plus a bound on the rounding error
-// of the reference's own evaluation of q (<= ~2^-48 |T_k|_F |u| per component, scaled into position
-// space by sigma_max: the kappa_k term), so the reference's test `sum((q-c)^2/r^2) < 1` (MAIN:703) is
-// false for all P samples of step k and the step contributes nothing to the reachable cloud.  The
-// surviving steps are evaluated with the reference's arithmetic, so the cloud is identical, bit for bit.
+// q - v_rel = T_k (u - c_k) (up to the residual of the computed inverse), c_k = (C G_k) v_rel.  Every sample
+// p_s lies in the box [-a, a] (a = per-axis max |p_s|), so u - c_k lies in the box w_k + [-a, a],
+// w_k = tr_k - c_k, whose points have |coordinate i| >= g_i = max(0, |w_i| - a_i) and norm <= U = |w| + |a|.
+// Two lower bounds of |q - v_rel| over that box:
+//   (ball)     |T z| >= |z| / sigma_max(C G_k)            >= |g| / sigma_max
+//   (diagonal) |T z| >= |diag(T) z| - |offdiag(T)|_F |z|  >= sqrt(sum_i T_ii^2 g_i^2) - |offdiag(T)|_F U
+// (the second is the sharp one for this model: C G_k is diagonal up to round-off and 3-200x stiffer in x, y
+// than in z).  The step is dropped when either bound exceeds
+//     max_speed (1 + 1e-6) + 1e-11 (|T_k|_F (U + |c_k|_1 + 1) + kappa_k |v_rel|_1):
+// the second term over-estimates (by > 10^3) the rounding error of the reference's own evaluation of q
+// (<= ~2^-50 |T_k|_F |u| per component), of c_k, and the residual |T_k C G_k - I| |v_rel| of the computed
+// inverse.  Then every exact AND every rounded |q - v_rel| exceeds max_speed, the reference's test
+// `sum((q-c)^2/r^2) < 1` (MAIN:703) is false for all P samples, and step k adds nothing to the cloud.  The
+// surviving steps are evaluated with the reference's arithmetic, so the cloud is identical, bit for bit
+// (tests: GPU step with and without pruning; CPU check of the rule against the oracle).
 __device__ __forceinline__ bool step_prunable(const LqroParams& p, const PairTables& t, const double* tr, int k, double vr0, double vr1,
                                               double vr2) {
   const double* G = t.CG + 9 * k;
+  const double* c = t.prn + LQRO_PRN * k;
   const double c0 = fma(G[0], vr0, fma(G[1], vr1, G[2] * vr2));
   const double c1 = fma(G[3], vr0, fma(G[4], vr1, G[5] * vr2));
   const double c2 = fma(G[6], vr0, fma(G[7], vr1, G[8] * vr2));
   const double w0 = tr[3 * k] - c0, w1 = tr[3 * k + 1] - c1, w2 = tr[3 * k + 2] - c2;
   const double g0 = fmax(0.0, fabs(w0) - p.box[0]), g1 = fmax(0.0, fabs(w1) - p.box[1]), g2 = fmax(0.0, fabs(w2) - p.box[2]);
-  const double gap2 = fma(g0, g0, fma(g1, g1, g2 * g2));
-  const double thr = t.prn[2 * k] * (1.0 + 1.0e-6) +
-                     1.0e-12 * t.prn[2 * k + 1] * (fabs(w0) + fabs(w1) + fabs(w2) + fabs(c0) + fabs(c1) + fabs(c2) + 3.0);
-  return gap2 > thr * thr * (1.0 + 1.0e-9);
+  const double U = fabs(w0) + fabs(w1) + fabs(w2) + p.box[0] + p.box[1] + p.box[2];  // >= |z| for every z in the box
+  const double c1n = fabs(c0) + fabs(c1) + fabs(c2);
+  const double v1n = fabs(vr0) + fabs(vr1) + fabs(vr2);
+  const double need = p.max_speed * (1.0 + 1.0e-6) + 1.0e-11 * (c[6] * (U + c1n + 1.0) + c[1] * v1n);
+  // (ball) in position space: |g| > sigma_max * need
+  const double gap = sqrt(fma(g0, g0, fma(g1, g1, g2 * g2)));
+  if (gap * (1.0 - 1.0e-12) > (c[0] / p.max_speed) * need) return true;
+  // (diagonal) in velocity space
+  const double d0 = c[2] * g0, d1 = c[3] * g1, d2 = c[4] * g2;
+  const double lb = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))) * (1.0 - 1.0e-12) - c[5] * U;
+  return lb > need;
 }
 
 // Build the reachable cloud of one pair in shared memory (order preserved), return its size.
@@ -277,7 +292,7 @@ __device__ __forceinline__ void load_block_tables(double* base, const LqroTables
   }
   double* cg = sph + 3 * P;
   for (int e = threadIdx.x; e < nT; e += blockDim.x) cg[e] = tb.CG[e];
-  for (int e = threadIdx.x; e < 2 * H; e += blockDim.x) cg[nT + e] = tb.prn[e];
+  for (int e = threadIdx.x; e < LQRO_PRN * H; e += blockDim.x) cg[nT + e] = tb.prn[e];
   __syncthreads();
 }
 
