@@ -69,6 +69,7 @@ struct lqro_ctx {
   int* d_ctr = nullptr;       // [0] pair work counter [1] hull count [2] hull work counter [3] degenerate [4..7] spare
   int* d_hull_items = nullptr;
   char* d_hull_ws = nullptr;
+  double* d_pair_ovf = nullptr; size_t pair_ovf_stride = 0;
   size_t hull_ws_stride = 0;
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
@@ -140,7 +141,7 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_CG, ctx->d_prn, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
                   ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
-                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws};
+                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -152,7 +153,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   lqro_ctx* ctx = nullptr;
   if (!cfg || !out) return fail(nullptr, LQRO_E_ARG, "null argument");
   *out = nullptr;
-  if (cfg->n_agents < 1 || cfg->max_neighbors < 1 || cfg->horizon < 1 || cfg->n_samples < 1 || cfg->horizon * cfg->n_samples > 8192 ||
+  if (cfg->n_agents < 1 || cfg->max_neighbors < 1 || cfg->horizon < 1 || cfg->horizon > 64 || cfg->n_samples < 1 || cfg->horizon * cfg->n_samples > 8192 ||
       !(cfg->max_speed > 0) || cfg->local_begin < 0 || cfg->local_begin >= cfg->n_agents)
     return fail(nullptr, LQRO_E_ARG, "bad configuration");
   int ndev = 0;
@@ -230,13 +231,17 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   // launch geometry of the pair kernel: as many warps per block as the opt-in shared memory holds
   {
     const size_t tbl = sizeof(double) * pair_block_table_doubles(H, P);
-    const size_t per = sizeof(double) * pair_warp_doubles(H, P);
-    int wp = (int)((ctx->smem_optin - tbl) / per);
-    if (wp > 8) wp = 8;
-    if (wp < 1) { g_create_err = "H*P too large for shared memory"; return bail(LQRO_E_LIMIT); }
+    const size_t per = sizeof(double) * pair_warp_doubles(H, P);     // full-capacity warp scratch (stage kernels)
+    const size_t per2 = sizeof(double) * pair2_warp_doubles(H);      // pair kernel: capped cloud + overflow in HBM
+    if (tbl + per > ctx->smem_optin) { g_create_err = "H*P too large for shared memory"; return bail(LQRO_E_LIMIT); }
+    int wp = (int)((ctx->smem_optin - tbl) / per2);
+    if (wp > 16) wp = 16;
+    if (wp < 1) { g_create_err = "H too large for shared memory"; return bail(LQRO_E_LIMIT); }
     ctx->pair_warps = wp;
-    ctx->pair_smem = tbl + per * wp;
-    ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM (shared memory allows exactly one)
+    ctx->pair_smem = tbl + per2 * wp;
+    ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM
+    ctx->pair_ovf_stride = 3 * (size_t)(H * P > LQRO_PAIR_CLOUD_CAP ? H * P - LQRO_PAIR_CLOUD_CAP : 0) + 8;
+    CUC(cudaMalloc(&ctx->d_pair_ovf, sizeof(double) * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * wp));
     // function attributes are per function, not per context: always allow the device maximum so that
     // contexts with different H*P can coexist
     CUC(cudaFuncSetAttribute(k_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -304,6 +309,9 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
     std::vector<double> cg(9 * (size_t)H), T(9 * (size_t)H), prn(LQRO_PRN * (size_t)H, 0.0);
     CU(cudaMemcpy(cg.data(), ctx->d_CG, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(T.data(), ctx->d_T, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
+    std::vector<double> nf(48 * (size_t)H), nfmax(H, 0.0);
+    CU(cudaMemcpy(nf.data(), ctx->d_NF, sizeof(double) * 48 * H, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < H; ++k) for (int e = 0; e < 48; ++e) nfmax[k] = fmax(nfmax[k], fabs(nf[48 * (size_t)k + e]));
     for (int k = 0; k < H; ++k) {
       const double* g = cg.data() + 9 * k;
       double m[3][3];
@@ -336,6 +344,7 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
       c[2] = fabs(T[9 * k + 0]); c[3] = fabs(T[9 * k + 4]); c[4] = fabs(T[9 * k + 8]);
       c[5] = sqrt(ef) * (1.0 + 1e-9);
       c[6] = sqrt(tf) * (1.0 + 1e-9);
+      c[7] = nfmax[k];
     }
     CU(cudaMemcpy(ctx->d_prn, prn.data(), sizeof(double) * LQRO_PRN * H, cudaMemcpyHostToDevice));
   }
@@ -361,7 +370,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
   CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
   CU(cudaEventRecord(ctx->ev[0], st));
-  k_pairs<<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, ctx->d_ctr + 0, hq);
+  k_pairs<<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, ctx->d_ctr + 0, hq, ctx->d_pair_ovf,
+                                                                           ctx->pair_ovf_stride);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   k_hull<<<ctx->hull_blocks, ctx->hull_wpb * 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws,

@@ -181,16 +181,31 @@ __device__ __forceinline__ void gjk_simplex_step(GjkRegs& g, double v0, double v
   if (!g.use_default) gjk_backup_distance<SIZE>(g);
 }
 
-// Warp-cooperative GJK.  px/py/pz: the cloud (shared or global), n points.  Returns d^2 (uniform across
-// the warp); witnesses in w1 (on {v_rel}) / w2 (on conv(cloud)); *iters = number of G-tests.
-__device__ __forceinline__ double gjk_warp(const double v0, const double v1, const double v2, const double* __restrict__ px,
-                                           const double* __restrict__ py, const double* __restrict__ pz, int n, double* w1out,
+// The cloud of one pair: the first `cap` points in shared memory (SoA), the rest in a per-warp overflow
+// area in global memory (rare: dense scenes).  For a plain global cloud set cap = n.
+struct CloudView {
+  double *sx, *sy, *sz;   // [cap]
+  double *gx, *gy, *gz;   // [n - cap], may be null when n <= cap
+  int cap;
+  __device__ __forceinline__ void get(int m, double& x, double& y, double& z) const {
+    if (m < cap) { x = sx[m]; y = sy[m]; z = sz[m]; }
+    else { x = gx[m - cap]; y = gy[m - cap]; z = gz[m - cap]; }
+  }
+  __device__ __forceinline__ void put(int m, double x, double y, double z) const {
+    if (m < cap) { sx[m] = x; sy[m] = y; sz[m] = z; }
+    else { gx[m - cap] = x; gy[m - cap] = y; gz[m - cap] = z; }
+  }
+};
+
+// Warp-cooperative GJK on a cloud of n points.  Returns d^2 (uniform across the warp); witnesses in w1
+// (on {v_rel}) / w2 (on conv(cloud)); *iters = number of G-tests.
+__device__ __forceinline__ double gjk_warp(const double v0, const double v1, const double v2, const CloudView& cl, int n, double* w1out,
                                            double* w2out, int* iters) {
   const int lane = lane_id();
   GjkRegs g;
   g.npts = 1;  // GJK.c:340-347
   g.lam[0] = 1.0;
-  g.c2[0][0] = px[0]; g.c2[0][1] = py[0]; g.c2[0][2] = pz[0];
+  cl.get(0, g.c2[0][0], g.c2[0][1], g.c2[0][2]);
   g.use_default = 1;
   int first_iteration = 1;
   double oldsqrd = 0.0, sqrd = 0.0;
@@ -224,7 +239,9 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     double best = -1.7976931348623157e308;
     int besti = 0x7fffffff;
     for (int m = lane; m < n; m += 32) {
-      const double v = dot3(px[m], py[m], pz[m], r0, r1, r2);
+      double qx, qy, qz;
+      cl.get(m, qx, qy, qz);
+      const double v = dot3(qx, qy, qz, r0, r1, r2);
       if (v > best) { best = v; besti = m; }
     }
 #pragma unroll
@@ -241,7 +258,8 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     if (g_val < 0.0) g_val = 0;
     if (g_val < LQRO_GJK_EPS) { exhausted = false; break; }
     if ((first_iteration || sqrd < oldsqrd) && g.npts <= 3) {  // GJK.c:472-487
-      const double nx = px[minp], ny = py[minp], nz = pz[minp];
+      double nx, ny, nz;
+      cl.get(minp, nx, ny, nz);
 #pragma unroll
       for (int i = 1; i < 4; ++i)
         if (i == g.npts) { g.c2[i][0] = nx; g.c2[i][1] = ny; g.c2[i][2] = nz; g.lam[i] = 0.0; }

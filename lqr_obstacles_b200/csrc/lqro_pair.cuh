@@ -197,26 +197,34 @@ struct PairTables {
 // `sum((q-c)^2/r^2) < 1` (MAIN:703) is false for all P samples, and step k adds nothing to the cloud.  The
 // surviving steps are evaluated with the reference's arithmetic, so the cloud is identical, bit for bit
 // (tests: GPU step with and without pruning; CPU check of the rule against the oracle).
-__device__ __forceinline__ bool step_prunable(const LqroParams& p, const PairTables& t, const double* tr, int k, double vr0, double vr1,
-                                              double vr2) {
+// tr0..2: Translate_k as computed by the caller; tr_err: bound on |tr - (reference's rounded Translate_k)|_1
+// (0 when tr is the reference-order value itself).
+__device__ __forceinline__ bool step_prunable_v(const LqroParams& p, const PairTables& t, int k, double tr0, double tr1, double tr2,
+                                                double tr_err, double vr0, double vr1, double vr2) {
   const double* G = t.CG + 9 * k;
   const double* c = t.prn + LQRO_PRN * k;
   const double c0 = fma(G[0], vr0, fma(G[1], vr1, G[2] * vr2));
   const double c1 = fma(G[3], vr0, fma(G[4], vr1, G[5] * vr2));
   const double c2 = fma(G[6], vr0, fma(G[7], vr1, G[8] * vr2));
-  const double w0 = tr[3 * k] - c0, w1 = tr[3 * k + 1] - c1, w2 = tr[3 * k + 2] - c2;
-  const double g0 = fmax(0.0, fabs(w0) - p.box[0]), g1 = fmax(0.0, fabs(w1) - p.box[1]), g2 = fmax(0.0, fabs(w2) - p.box[2]);
-  const double U = fabs(w0) + fabs(w1) + fabs(w2) + p.box[0] + p.box[1] + p.box[2];  // >= |z| for every z in the box
+  const double w0 = tr0 - c0, w1 = tr1 - c1, w2 = tr2 - c2;
+  const double g0 = fmax(0.0, fabs(w0) - p.box[0] - tr_err), g1 = fmax(0.0, fabs(w1) - p.box[1] - tr_err),
+               g2 = fmax(0.0, fabs(w2) - p.box[2] - tr_err);
+  const double U = fabs(w0) + fabs(w1) + fabs(w2) + p.box[0] + p.box[1] + p.box[2] + 3.0 * tr_err;  // >= |z| for every z in the box
   const double c1n = fabs(c0) + fabs(c1) + fabs(c2);
   const double v1n = fabs(vr0) + fabs(vr1) + fabs(vr2);
   const double need = p.max_speed * (1.0 + 1.0e-6) + 1.0e-11 * (c[6] * (U + c1n + 1.0) + c[1] * v1n);
-  // (ball) in position space: |g| > sigma_max * need
-  const double gap = sqrt(fma(g0, g0, fma(g1, g1, g2 * g2)));
-  if (gap * (1.0 - 1.0e-12) > (c[0] / p.max_speed) * need) return true;
-  // (diagonal) in velocity space
+  // (ball) in position space: |g| > sigma_max * need   (compared as squares, both sides >= 0)
+  const double gap2 = fma(g0, g0, fma(g1, g1, g2 * g2));
+  const double rb = (c[0] / p.max_speed) * need;
+  if (gap2 * (1.0 - 1.0e-12) > rb * rb) return true;
+  // (diagonal) in velocity space: sqrt(sum (T_ii g_i)^2) > need + |offdiag T|_F U
   const double d0 = c[2] * g0, d1 = c[3] * g1, d2 = c[4] * g2;
-  const double lb = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))) * (1.0 - 1.0e-12) - c[5] * U;
-  return lb > need;
+  const double rhs = need + c[5] * U;
+  return fma(d0, d0, fma(d1, d1, d2 * d2)) * (1.0 - 1.0e-12) > rhs * rhs;
+}
+__device__ __forceinline__ bool step_prunable(const LqroParams& p, const PairTables& t, const double* tr, int k, double vr0, double vr1,
+                                              double vr2) {
+  return step_prunable_v(p, t, k, tr[3 * k], tr[3 * k + 1], tr[3 * k + 2], 0.0, vr0, vr1, vr2);
 }
 
 // Build the reachable cloud of one pair in shared memory (order preserved), return its size.
@@ -310,62 +318,182 @@ __device__ __forceinline__ void write_plane(float* pl, const double* vi, double 
   pl[5] = (float)n2;
 }
 
-// Persistent kernel: one warp per pair, pairs handed out by an atomic counter (their cost varies
-// from "no reachable point" to a 1000-point GJK).  Dynamic shared memory = tables + per-warp clouds.
-__global__ void __launch_bounds__(256) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
-                                               PairOutputs out, int* __restrict__ work_counter, HullQueue hq) {
+// ------------------------------------------------------------------------------------------------
+// The pair kernel.  Persistent CTAs (one per SM, up to 16 warps); a warp takes BATCHES of 32 consecutive
+// pair slots (one atomic per batch) and runs two stages:
+//
+//  stage 1, lane = pair (32 pairs in flight per warp, no shuffles, table reads are warp-uniform broadcasts):
+//     load x_i, x_j, form dx; for every horizon step evaluate Translate_k with FMAs (an approximation whose
+//     error is charged to the bound) and the exact pruning rule -> 64-bit mask of surviving steps.
+//     Pairs with no surviving step are finished here (status NONE), with coalesced stores.
+//  stage 2, warp = pair, for the lanes whose mask is non-zero: Translate_k of the surviving steps in the
+//     reference's operation order, candidate generation + reachable filter into the warp's cloud (first
+//     LQRO_PAIR_CLOUD_CAP points in shared memory, overflow in a per-warp global area), GJK, half-plane
+//     (outside case) or hull queue (inside case).
+#define LQRO_PAIR_CLOUD_CAP 256
+
+struct PairWarpV2 {
+  double *cx, *cy, *cz;  // [LQRO_PAIR_CLOUD_CAP]
+  double* tr;            // [3H]
+  double* dx;            // [16]
+  double* xi;            // [16]
+  int* klist;            // [H]
+};
+__host__ __device__ inline size_t pair2_warp_doubles(int H) { return (size_t)3 * LQRO_PAIR_CLOUD_CAP + 3 * H + 32 + (H + 1) / 2 + 1; }
+
+__global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+                                                  PairOutputs out, int* __restrict__ work_counter, HullQueue hq,
+                                                  double* __restrict__ ovf_base, size_t ovf_stride) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   PairTables t;
-  PairWarpSmem w;
   load_block_tables(smem, tb, p.H, p.P);
-  carve_pair_smem(smem, warp, p.H, p.P, t, w);
+  {
+    const int H = p.H, P = p.P;
+    t.NFt = smem; t.T = smem + 16 * 3 * H; t.sphx = t.T + 9 * H; t.sphy = t.sphx + P; t.sphz = t.sphy + P;
+    t.CG = t.sphz + P; t.prn = t.CG + 9 * H;
+  }
+  PairWarpV2 w;
+  {
+    double* wb = smem + pair_block_table_doubles(p.H, p.P) + (size_t)warp * pair2_warp_doubles(p.H);
+    w.cx = wb; w.cy = wb + LQRO_PAIR_CLOUD_CAP; w.cz = wb + 2 * LQRO_PAIR_CLOUD_CAP;
+    w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * p.H; w.xi = w.dx + 16;
+    w.klist = reinterpret_cast<int*>(w.xi + 16);
+  }
+  CloudView cl;
+  cl.sx = w.cx; cl.sy = w.cy; cl.sz = w.cz; cl.cap = LQRO_PAIR_CLOUD_CAP;
+  {
+    double* ov = ovf_base + ovf_stride * (size_t)(blockIdx.x * (blockDim.x >> 5) + warp);
+    const size_t no = (size_t)(p.HP > LQRO_PAIR_CLOUD_CAP ? p.HP - LQRO_PAIR_CLOUD_CAP : 0);
+    cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
+  }
   const int npairs = p.n_local * p.K;
+  const int n3 = 3 * p.H;
+  const unsigned long long allsteps = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
   while (true) {
-    int pair = 0;
-    if (lane == 0) pair = atomicAdd(work_counter, 1);
-    pair = __shfl_sync(LQRO_FULL, pair, 0);
-    if (pair >= npairs) break;
-    const int il = pair / p.K;
-    const int i = p.local_begin + il;
-    const int j = nbr[pair];
-    if (j < 0 || j == i || j >= p.N) {  // empty slot (the reference skips i == j, MAIN:1379)
-      if (lane == 0) { out.status[pair] = 0; out.nreach[pair] = 0; }
-      continue;
-    }
-    if (lane < 16) {
-      const double a = x[(size_t)i * 16 + lane], b = x[(size_t)j * 16 + lane];
-      w.xi[lane] = a;
-      w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
-    }
-    __syncwarp();
-    const int n = warp_reachable_cloud(p, t, w);
-    if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
-      if (lane == 0) { out.status[pair] = 0; out.nreach[pair] = n; }
-      __syncwarp();
-      continue;
-    }
-    const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
-    double gw1[3], gw2[3];
-    const double sq = gjk_warp(vr0, vr1, vr2, w.px, w.py, w.pz, n, gw1, gw2, nullptr);
-    if (lane == 0) {
-      const double distance = sqrt(sq);                    // MAIN:741
-      const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
-      out.nreach[pair] = n;
-      if (!inside) {
-        const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
-        const double n1 = (gw1[1] - gw2[1]) / distance;
-        const double n2 = (gw1[2] - gw2[2]) / distance;
-        write_plane(out.planes + 6 * (size_t)pair, w.xi + 3, distance, n0, n1, n2, false);
-        out.dist[pair] = distance;
-        out.status[pair] = 1;
-      } else {
-        out.status[pair] = 2;  // plane filled in by k_hull
-        const int slot = atomicAdd(hq.count, 1);
-        if (slot < hq.capacity) hq.items[slot] = pair;
+    int batch = 0;
+    if (lane == 0) batch = atomicAdd(work_counter, 1);
+    batch = __shfl_sync(LQRO_FULL, batch, 0);
+    const int base = batch * 32;
+    if (base >= npairs) break;
+    // ---------------- stage 1: lane = pair
+    const int pair = base + lane;
+    int i = 0, j = -1;
+    unsigned long long kmask = 0ull;
+    if (pair < npairs) {
+      i = p.local_begin + pair / p.K;
+      j = nbr[pair];
+      if (j >= 0 && j != i && j < p.N) {  // the reference skips i == j (MAIN:1379)
+        if (!p.prune) {
+          kmask = allsteps;
+        } else {
+          double dx[16];
+          const double2* xi2 = reinterpret_cast<const double2*>(x + (size_t)i * 16);
+          const double2* xj2 = reinterpret_cast<const double2*>(x + (size_t)j * 16);
+          double dx1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const double2 a = xi2[m], b = xj2[m];
+            dx[2 * m] = a.x - b.x; dx[2 * m + 1] = a.y - b.y;
+            dx1 += fabs(dx[2 * m]) + fabs(dx[2 * m + 1]);
+          }
+          const double vr0 = dx[3], vr1 = dx[4], vr2 = dx[5];
+          for (int k = 0; k < p.H; ++k) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            const double* nf = t.NFt + 3 * k;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+              t0 = fma(nf[m * n3], dx[m], t0);
+              t1 = fma(nf[m * n3 + 1], dx[m], t1);
+              t2 = fma(nf[m * n3 + 2], dx[m], t2);
+            }
+            // |fused sum - reference's rounded sum| <= 2 * 16 * 2^-53 * sum |NF||dx| <= 1e-14 * max|NF_k| * |dx|_1
+            const double tr_err = 1.0e-14 * t.prn[LQRO_PRN * k + 7] * dx1;
+            if (!step_prunable_v(p, t, k, t0, t1, t2, tr_err, vr0, vr1, vr2)) kmask |= 1ull << k;
+          }
+        }
       }
+      if (kmask == 0ull) { out.status[pair] = 0; out.nreach[pair] = 0; }
     }
-    __syncwarp();
+    // ---------------- stage 2: warp = pair
+    unsigned act = __ballot_sync(LQRO_FULL, kmask != 0ull);
+    while (act) {
+      const int src = __ffs(act) - 1;
+      act &= act - 1;
+      const int pr = base + src;
+      const int ii = __shfl_sync(LQRO_FULL, i, src);
+      const int jj = __shfl_sync(LQRO_FULL, j, src);
+      const unsigned long long km = __shfl_sync(LQRO_FULL, kmask, src);
+      if (lane < 16) {
+        const double a = x[(size_t)ii * 16 + lane], b = x[(size_t)jj * 16 + lane];
+        w.xi[lane] = a;
+        w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
+      }
+      const int nk = __popcll(km);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < p.H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
+      }
+      __syncwarp();
+      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231)
+      for (int e = lane; e < 3 * nk; e += 32) {
+        const int ki = e / 3, c = e - 3 * ki;
+        const int k = w.klist[ki];
+        const double* nf = t.NFt + 3 * k + c;
+        double s = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s += nf[m * n3] * w.dx[m];
+        w.tr[3 * k + c] = s;
+      }
+      __syncwarp();
+      const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
+      int count = 0;
+      const int total = nk * p.P;
+      int ki = 0, s = lane;
+      while (s >= p.P) { s -= p.P; ++ki; }
+      for (int b0 = 0; b0 < total; b0 += 32) {
+        const int m = b0 + lane;
+        bool pass = false;
+        double q0 = 0, q1 = 0, q2 = 0;
+        if (m < total) {
+          candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
+          pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
+        }
+        const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+        if (pass) cl.put(count + __popc(mask & ((1u << lane) - 1u)), q0, q1, q2);
+        count += __popc(mask);
+        s += 32;
+        while (s >= p.P) { s -= p.P; ++ki; }
+      }
+      __syncwarp();
+      const int n = count;
+      if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
+        if (lane == 0) { out.status[pr] = 0; out.nreach[pr] = n; }
+        __syncwarp();
+        continue;
+      }
+      double gw1[3], gw2[3];
+      const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
+      if (lane == 0) {
+        const double distance = sqrt(sq);                             // MAIN:741
+        const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
+        out.nreach[pr] = n;
+        if (!inside) {
+          const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
+          const double n1 = (gw1[1] - gw2[1]) / distance;
+          const double n2 = (gw1[2] - gw2[2]) / distance;
+          write_plane(out.planes + 6 * (size_t)pr, w.xi + 3, distance, n0, n1, n2, false);
+          out.dist[pr] = distance;
+          out.status[pr] = 1;
+        } else {
+          out.status[pr] = 2;  // plane filled in by k_hull
+          const int slot = atomicAdd(hq.count, 1);
+          if (slot < hq.capacity) hq.items[slot] = pr;
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -420,7 +548,9 @@ __global__ void __launch_bounds__(32) k_stage_gjk(const double* __restrict__ vre
   __syncwarp();
   int it = 0;
   double w1[3], w2[3];
-  const double sq = gjk_warp(vrel[0], vrel[1], vrel[2], px, py, pz, n, w1, w2, &it);
+  CloudView cl;
+  cl.sx = px; cl.sy = py; cl.sz = pz; cl.gx = cl.gy = cl.gz = nullptr; cl.cap = n;
+  const double sq = gjk_warp(vrel[0], vrel[1], vrel[2], cl, n, w1, w2, &it);
   if (lane == 0) {
     out[0] = sq; out[1] = w2[0]; out[2] = w2[1]; out[3] = w2[2];
     out[4] = w1[0]; out[5] = w1[1]; out[6] = w1[2];
