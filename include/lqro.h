@@ -178,6 +178,11 @@ int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops);
 /* Device time (ms) of the kernels of the last step: [0] pair kernel, [1] hull kernel, [2] LP kernel,
  * [3] whole step (kernels only, measured with CUDA events on the launching stream). */
 int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
+/* SM-cycle breakdown of the hull kernel of the last step, summed over hulls (development aid):
+ * [0] init+simplex [1] partitionall [2] furthest+horizon+cone [3] planes+match [4] list [5] walk [6] redo
+ * [7] append [8] delete [9] - [10] insertions [11] points re-partitioned [12] max cycles of one hull
+ * [13] max points [14] max facets */
+int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16);
 
 #ifdef __cplusplus
 }

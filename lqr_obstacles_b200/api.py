@@ -36,6 +36,7 @@ EXPORTS = [
     "lqro_get_counters", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
+    "lqro_debug_hull_cycles",
 ]
 
 
@@ -82,6 +83,7 @@ def load_library(path=None):
     lib.lqro_measure_fp64_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_measure_fp32_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
+    lib.lqro_debug_hull_cycles.argtypes = [c_void_p, c_void_p]
     if path == _build.SO:
         _lib = lib
     return lib
@@ -198,6 +200,11 @@ class Lqro:
         t = np.zeros(4, dtype=np.float32)
         self._ck(self.lib.lqro_last_step_ms(self.h, _p(t)))
         return dict(pairs=float(t[0]), hull=float(t[1]), lp=float(t[2]), total=float(t[3]))
+
+    def hull_cycles(self):
+        c = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.lqro_debug_hull_cycles(self.h, _p(c)))
+        return c
 
     # -- per-stage
     def createObstacle(self, xi, xj):

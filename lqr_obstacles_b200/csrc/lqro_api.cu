@@ -70,6 +70,7 @@ struct lqro_ctx {
   int* d_hull_items = nullptr;
   char* d_hull_ws = nullptr;
   double* d_pair_ovf = nullptr; size_t pair_ovf_stride = 0;
+  long long* d_prof = nullptr;
   size_t hull_ws_stride = 0;
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
@@ -141,7 +142,7 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_CG, ctx->d_prn, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
                   ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
-                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf};
+                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf, ctx->d_prof};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -202,6 +203,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMalloc(&ctx->d_planes_c, sizeof(float) * 6 * NP));
   CUC(cudaMalloc(&ctx->d_proj, sizeof(float) * 6 * NP));
   CUC(cudaMalloc(&ctx->d_ctr, sizeof(int) * 16));
+  CUC(cudaMalloc(&ctx->d_prof, sizeof(long long) * 16));
+  CUC(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 16));
   CUC(cudaMemset(ctx->d_ctr, 0, sizeof(int) * 16));
   CUC(cudaMemset(ctx->d_status, 0, sizeof(int) * NP));
   CUC(cudaMemset(ctx->d_nfacets, 0, sizeof(int) * NP));
@@ -369,13 +372,14 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   PairOutputs po{ctx->d_planes, ctx->d_status, ctx->d_nreach, ctx->d_dist, ctx->d_nfacets};
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
   CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
+  CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 16, st));
   CU(cudaEventRecord(ctx->ev[0], st));
   k_pairs<<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, ctx->d_ctr + 0, hq, ctx->d_pair_ovf,
                                                                            ctx->pair_ovf_stride);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   k_hull<<<ctx->hull_blocks, ctx->hull_wpb * 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws,
-                                                                      ctx->hull_ws_stride, ctx->cap_pts, ctx->d_ctr);
+                                                                      ctx->hull_ws_stride, ctx->cap_pts, ctx->d_ctr, ctx->d_prof);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,
@@ -457,6 +461,15 @@ extern "C" int lqro_get_counters(lqro_ctx* ctx, long long* out6) {
   out6[3] = c[3];
   out6[4] = c[1] > ctx->hull_cap ? c[1] - ctx->hull_cap : 0;
   out6[5] = ctx->launches;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16) {
+  if (!ctx || !out16) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out16, ctx->d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
   return LQRO_OK;
 }
 

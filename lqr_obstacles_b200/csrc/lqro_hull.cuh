@@ -170,6 +170,7 @@ struct HullCtl {
   int ninserted;
   int maxpoints[6];
   int simplex[4];
+  long long prof[12];  // cycles per phase (lane 0): 0 init, 1 partitionall, 2 next+horizon+cone, 3 planes+match, 4 list, 5 walk, 6 redo, 7 append, 8 delete, 9 output, 10 insertions, 11 points re-partitioned
 };
 
 __device__ __forceinline__ double hdist(const HFacet& f, double x, double y, double z) {  // qh_distplane
@@ -361,7 +362,9 @@ __device__ inline int hull_findbest_walk(const HullWs& w, const HullCtl& c, doub
 // w.order[0..c.nfacets_out) = facets in qhull list order.
 __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
   const int lane = lane_id();
+  long long tprof = clock64();
   if (lane == 0) {
+    for (int q = 0; q < 12; ++q) c.prof[q] = 0;
     c.degenerate = 0; c.fail = 0; c.nfree = 0; c.pool_used = 1; c.nverts = 0; c.ninserted = 0; c.nfacets_out = 0;
     c.facet_list = 0; c.facet_next = 0; c.newfacet_list = -1;
     w.F[0].prev = -1; w.F[0].next = -1; w.F[0].isnew = 0; w.F[0].visible = 0;
@@ -474,6 +477,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
   }
   __syncwarp();
   if (c.fail) return;
+  if (lane == 0) { const long long tn = clock64(); c.prof[0] += tn - tprof; tprof = tn; }
   // ---- qh_partitionall: first facet (list order) a point is outside of; distances in parallel
   {
     const double distoutside = hull_distoutside(c);
@@ -529,6 +533,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
     }
     __syncwarp();
   }
+  if (lane == 0) { const long long tn = clock64(); c.prof[1] += tn - tprof; tprof = tn; }
   // ---- qh_buildhull
   while (true) {
     if (lane == 0) {
@@ -603,6 +608,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       }
     }
     __syncwarp();
+    if (lane == 0) { const long long tn = clock64(); c.prof[2] += tn - tprof; tprof = tn; }
     if (c.nvis < 0 || c.fail) break;
     const int nnew = c.nnew;
     // qh_makenewplanes + qh_matchnewfacets (lane per cone facet)
@@ -626,6 +632,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
     }
     deg = __reduce_max_sync(LQRO_FULL, deg);
     __syncwarp();
+    if (lane == 0) { const long long tn = clock64(); c.prof[3] += tn - tprof; tprof = tn; }
     if (lane == 0) {
       if (deg == 1) c.degenerate = 1;
       if (deg == 2) c.fail = 3;
@@ -651,6 +658,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       c.trigger_pos = 0x7fffffff;
     }
     __syncwarp();
+    if (lane == 0) { const long long tn = clock64(); c.prof[4] += tn - tprof; tprof = tn; c.prof[10] += 1; c.prof[11] += c.nlist; }
     if (c.fail) break;
     const int nl = c.nlist;
     if (nl > 0 && nnew > 0) {
@@ -669,6 +677,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       }
       mytrig = (int)__reduce_min_sync(LQRO_FULL, (unsigned)mytrig);
       __syncwarp();
+      if (lane == 0) { const long long tn = clock64(); c.prof[5] += tn - tprof; tprof = tn; }
       // pass 3 (parallel): walks that ended below -DISTround.  Sharp cone: from the first such point on
       // (processing order) qhull switches to the exhaustive search (qh.findbestnew stays set for the
       // rest of this partition); otherwise each such walk finishes with its horizon test.
@@ -694,6 +703,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       }
       ldeg = __any_sync(LQRO_FULL, ldeg);
       __syncwarp();
+      if (lane == 0) { const long long tn = clock64(); c.prof[6] += tn - tprof; tprof = tn; }
       if (lane == 0) {
         if (ldeg) c.degenerate = 1;
         // pass 4: append in processing order (qh_partitionpoint)
@@ -709,6 +719,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       }
       __syncwarp();
     }
+    if (lane == 0) { const long long tn = clock64(); c.prof[7] += tn - tprof; tprof = tn; }
     if (lane == 0) {
       // qh_deletevisible + qh_resetlists
       for (int vi = 0; vi < c.nvis; ++vi) {
@@ -721,6 +732,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       c.newfacet_list = -1;
     }
     __syncwarp();
+    if (lane == 0) { const long long tn = clock64(); c.prof[8] += tn - tprof; tprof = tn; }
   }
   if (lane == 0 && !c.fail) {
     int nf = 0;
@@ -770,7 +782,7 @@ __host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
 // pair at a time; blocks take work items from an atomic counter and own one global workspace slot.
 __global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
-                                             size_t ws_stride, int cap_pts, int* __restrict__ counters) {
+                                             size_t ws_stride, int cap_pts, int* __restrict__ counters, long long* __restrict__ prof) {
   extern __shared__ double smem[];
   const int lane = lane_id();
   int nq = *hq.count;
@@ -829,6 +841,13 @@ __global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const 
     }
     double distance, normal[3]; int bestf;
     hull_nearest_facet(w, *ctl, w.ux, w.uy, w.uz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
+    if (lane == 0 && prof) {
+      long long tot = 0;
+      for (int q = 0; q < 12; ++q) { atomicAdd((unsigned long long*)prof + q, (unsigned long long)ctl->prof[q]); if (q < 10) tot += ctl->prof[q]; }
+      atomicMax(prof + 12, tot);
+      atomicMax(prof + 13, (long long)n);
+      atomicMax(prof + 14, (long long)ctl->nfacets_out);
+    }
     if (lane == 0) {
       write_plane(out.planes + 6 * (size_t)pair, pw.xi + 3, distance, normal[0], normal[1], normal[2], true);
       out.dist[pair] = distance;
