@@ -499,24 +499,27 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
     __syncwarp();
     if (lane == 0) {
       if (deg) c.degenerate = 1;
-      // build each facet's list: points in index order, every record placed at the end of its reign
-      for (int q = 0; q < 4; ++q) {
-        const int f = c.simplex[q];
-        int bestpoint = -1; double bestdist = 0;
-        HFacet& F = w.F[f];
-        int tail = -1;
+      // build the four lists in one pass: points in index order, every record placed at the end of its reign
+      {
+        int bestpoint[4] = {-1, -1, -1, -1}, tail[4] = {-1, -1, -1, -1};
+        double bestdist[4] = {0, 0, 0, 0};
+        const int f0 = c.simplex[0], f1 = c.simplex[1], f2 = c.simplex[2];
         for (int i = 0; i < n; ++i) {
-          if (w.pbest[i] != f) continue;
+          const int f = w.pbest[i];
+          if (f < 0) continue;
+          const int q = (f == f0) ? 0 : (f == f1) ? 1 : (f == f2) ? 2 : 3;
           const double d = w.pdist[i];
           int emit = -1;
-          if (bestpoint < 0) { bestpoint = i; bestdist = d; }
-          else if (d > bestdist) { emit = bestpoint; bestpoint = i; bestdist = d; }
+          if (bestpoint[q] < 0) { bestpoint[q] = i; bestdist[q] = d; }
+          else if (d > bestdist[q]) { emit = bestpoint[q]; bestpoint[q] = i; bestdist[q] = d; }
           else emit = i;
-          if (emit >= 0) { if (tail < 0) F.ohead = emit; else w.pnext[tail] = emit; tail = emit; }
+          if (emit >= 0) { if (tail[q] < 0) w.F[f].ohead = (hidx)emit; else w.pnext[tail[q]] = (hidx)emit; tail[q] = emit; }
         }
-        if (bestpoint >= 0) {
-          if (tail < 0) F.ohead = bestpoint; else w.pnext[tail] = bestpoint;
-          F.oprev = tail; F.olast = bestpoint; w.pnext[bestpoint] = -1; F.furthestdist = bestdist;
+        for (int q = 0; q < 4; ++q) {
+          if (bestpoint[q] < 0) continue;
+          HFacet& F = w.F[c.simplex[q]];
+          if (tail[q] < 0) F.ohead = (hidx)bestpoint[q]; else w.pnext[tail[q]] = (hidx)bestpoint[q];
+          F.oprev = (hidx)tail[q]; F.olast = (hidx)bestpoint[q]; w.pnext[bestpoint[q]] = -1; F.furthestdist = bestdist[q];
         }
       }
       // ---- qh_furthestnext: facet with the furthest outside point moves to the front
@@ -549,62 +552,128 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
         const int furthest = F0.olast;
         if (F0.oprev >= 0) { w.pnext[F0.oprev] = -1; F0.olast = F0.oprev; } else { F0.ohead = -1; F0.olast = -1; }
         ++c.ninserted;
-        const double ax = w.hx[furthest], ay = w.hy[furthest], az = w.hz[furthest];
-        c.apex[0] = ax; c.apex[1] = ay; c.apex[2] = az;
-        // qh_findhorizon: breadth-first over neighbours, visible facets move to the list end
-        hl_remove(w, c, facet); hl_append(w, c, facet);
+        c.apex[0] = w.hx[furthest]; c.apex[1] = w.hy[furthest]; c.apex[2] = w.hz[furthest];
         F0.visible = 1; F0.replace = -1;
-        const int vid = c.ninserted;  // unique per insertion (tags of live facets are <= earlier ids or cone indices reset below)
-        w.vis[c.nvis++] = facet;
-        F0.tag = -vid;
-        for (int vi = 0; vi < c.nvis; ++vi) {
-          const int vf = w.vis[vi];
-          for (int k = 0; k < 3; ++k) {
-            const int nb = w.F[vf].nb[k];
-            HFacet& NB = w.F[nb];
-            if (NB.tag == -vid) continue;
-            NB.tag = -vid;
-            const double d = hdist(NB, ax, ay, az);
-            if (d > c.MINvisible) {
-              hl_remove(w, c, nb); hl_append(w, c, nb);
-              NB.visible = 1; NB.replace = -1;
-              w.vis[c.nvis++] = nb;
-            } else if (d > -c.MAXcoplanar) c.degenerate = 1;  // coplanar horizon: qhull would merge
-          }
-        }
-        // qh_makenewfacets / qh_makenew_simplicial
-        c.newfacet_list = 0;
-        const int apex = c.nverts;
-        w.vpoint[c.nverts++] = furthest;
-        for (int vi = 0; vi < c.nvis && !c.fail; ++vi) {
-          const int vf = w.vis[vi];
-          int last_new = -1;
-          for (int k = 0; k < 3; ++k) {
-            const int nb = w.F[vf].nb[k];
-            if (w.F[nb].visible) continue;
-            int horizonskip = -1;
-            for (int q = 0; q < 3; ++q) if (w.F[nb].nb[q] == vf) { horizonskip = q; break; }
-            const int nf = hl_newfacet(w, c);
-            if (nf < 0) break;  // c.fail = 2 set by hl_newfacet
-            if (horizonskip < 0 || c.nnew >= LQRO_HULL_MAXNEW) { c.fail = 3; break; }
-            HFacet& HZ = w.F[nb];
-            HFacet& NF = w.F[nf];
-            NF.v[0] = apex;
-            int q2 = 1;
-            for (int q = 0; q < 3; ++q) if (q != horizonskip) NF.v[q2++] = HZ.v[q];
-            NF.toporient = HZ.toporient ? (horizonskip & 1) : ((horizonskip & 1) ^ 1);
-            NF.nb[0] = nb; NF.nb[1] = NF.nb[2] = -1;
-            NF.isnew = 1;
-            NF.tag = c.nnew;  // cone-local index
-            hl_append(w, c, nf);
-            HZ.nb[horizonskip] = nf;
-            w.newf[c.nnew++] = nf;
-            last_new = nf;
-          }
-          if (last_new >= 0) w.F[vf].replace = last_new;
-        }
+        F0.tag = (hidx)(-c.ninserted);
+        w.vis[0] = (hidx)facet;
+        c.nvis = 1;
+        w.vpoint[c.nverts] = (hidx)furthest;  // the apex gets the next vertex id
       } else {
         c.nvis = -1;  // done
+      }
+    }
+    __syncwarp();
+    if (c.nvis < 0) break;
+    {
+      // qh_findhorizon as a wave-parallel breadth-first search.  qhull scans the visible list in order and,
+      // per facet, its neighbours k = 0,1,2; a neighbour is tested once (first occurrence) and appended to
+      // the list if visible.  Processing the (facet, k) slots of one wave in index order, with duplicates
+      // inside a 32-slot chunk resolved to the lowest lane, yields the same list.  (qhull also moves visible
+      // facets to the end of its facet list; they are deleted before anyone looks, so they stay in place.)
+      const hidx vid = (hidx)(-c.ninserted);
+      const double ax = c.apex[0], ay = c.apex[1], az = c.apex[2];
+      int nvis = 1, wave = 0, deg = 0;
+      while (wave < nvis) {
+        const int wend = nvis;
+        for (int b0 = wave * 3; b0 < wend * 3; b0 += 32) {
+          const int idx = b0 + lane;
+          const bool valid = idx < wend * 3;
+          int nb = -1 - lane;
+          if (valid) nb = w.F[w.vis[idx / 3]].nb[idx % 3];
+          const unsigned peers = __match_any_sync(LQRO_FULL, nb);
+          bool test = valid && (lane == __ffs(peers) - 1);
+          if (test) test = w.F[nb].tag != vid;
+          bool isvis = false;
+          if (test) {
+            HFacet& NB = w.F[nb];
+            NB.tag = vid;
+            const double d = hdist(NB, ax, ay, az);
+            if (d > c.MINvisible) { isvis = true; NB.visible = 1; NB.replace = -1; }
+            else if (d > -c.MAXcoplanar) deg = 1;  // coplanar horizon: qhull would merge
+          }
+          const unsigned m = __ballot_sync(LQRO_FULL, isvis);
+          if (isvis) w.vis[nvis + __popc(m & ((1u << lane) - 1u))] = (hidx)nb;
+          nvis += __popc(m);
+          __syncwarp();
+        }
+        wave = wend;
+      }
+      deg = __any_sync(LQRO_FULL, deg);
+      // qh_makenewfacets / qh_makenew_simplicial: one cone facet per horizon ridge, in (visible facet, k) order
+      const int apex = c.nverts;
+      int nnew = 0, failcode = 0;
+      // pass A: count and rank the ridges
+      for (int b0 = 0; b0 < nvis * 3; b0 += 32) {
+        const int idx = b0 + lane;
+        bool ridge = false;
+        int vf = 0, nb = 0;
+        if (idx < nvis * 3) { vf = w.vis[idx / 3]; nb = w.F[vf].nb[idx % 3]; ridge = !w.F[nb].visible; }
+        const unsigned m = __ballot_sync(LQRO_FULL, ridge);
+        if (ridge) {
+          const int r = nnew + __popc(m & ((1u << lane) - 1u));
+          if (r < LQRO_HULL_MAXNEW) {
+            // facet id: free list first (popped from the back), then fresh pool entries
+            int f;
+            if (r < c.nfree) f = w.freel[c.nfree - 1 - r];
+            else f = c.pool_used + (r - c.nfree);
+            if (f >= w.cap_f) failcode = 2;
+            else {
+              w.newf[r] = (hidx)f;
+              HFacet& HZ = w.F[nb];
+              int horizonskip = -1;
+              for (int q = 0; q < 3; ++q) if (HZ.nb[q] == vf) { horizonskip = q; break; }
+              if (horizonskip < 0) failcode = 3;
+              else {
+                HFacet& NF = w.F[f];
+                NF.ohead = NF.olast = NF.oprev = -1; NF.furthestdist = 0; NF.replace = -1;
+                NF.visible = 0; NF.isnew = 1;
+                NF.v[0] = (hidx)apex;
+                int q2 = 1;
+                for (int q = 0; q < 3; ++q) if (q != horizonskip) NF.v[q2++] = HZ.v[q];
+                NF.toporient = HZ.toporient ? (horizonskip & 1) : ((horizonskip & 1) ^ 1);
+                NF.nb[0] = (hidx)nb; NF.nb[1] = NF.nb[2] = -1;
+                NF.tag = (hidx)r;  // cone-local index
+                HZ.nb[horizonskip] = (hidx)f;
+                // the visible facet remembers the LAST cone facet made from its ridges (f.replace)
+                bool last = true;
+                for (int k2 = (idx % 3) + 1; k2 < 3; ++k2) if (!w.F[w.F[vf].nb[k2]].visible) last = false;
+                if (last) w.F[vf].replace = (hidx)f;
+              }
+            }
+          } else failcode = 3;
+        }
+        nnew += __popc(m);
+      }
+      failcode = __reduce_max_sync(LQRO_FULL, failcode);
+      __syncwarp();
+      // pass B: append the cone facets to the facet list in rank order
+      if (!failcode) {
+        const int last_old = w.F[0].prev;
+        for (int r = lane; r < nnew; r += 32) {
+          const int f = w.newf[r];
+          w.F[f].prev = (hidx)(r == 0 ? last_old : w.newf[r - 1]);
+          w.F[f].next = (hidx)(r == nnew - 1 ? 0 : w.newf[r + 1]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (deg) c.degenerate = 1;
+        if (failcode) c.fail = failcode;
+        else {
+          c.nverts = apex + 1;
+          const int used_free = nnew < c.nfree ? nnew : c.nfree;
+          c.pool_used += nnew - used_free;
+          c.nfree -= used_free;
+          if (nnew > 0) {
+            const int f0 = w.newf[0], fl = w.newf[nnew - 1];
+            const int last_old = w.F[f0].prev;
+            if (last_old >= 0) w.F[last_old].next = (hidx)f0; else c.facet_list = f0;
+            w.F[0].prev = (hidx)fl;
+            if (c.facet_next == 0) c.facet_next = f0;
+            c.newfacet_list = f0;
+          } else c.newfacet_list = 0;
+        }
+        c.nvis = nvis; c.nnew = nnew;
       }
     }
     __syncwarp();
