@@ -94,7 +94,7 @@ __global__ void k_round6(const double* __restrict__ in, int n, double* __restric
 // in shared memory next to the tables (fast path); a hull that needs more facets than the shared pool
 // holds is re-run on the full-size pool in global memory (same code, other pointers).
 typedef short hidx;
-struct HFacet {           // 72 bytes
+struct HFacet {           // 80 bytes
   double n[3], off;
   double furthestdist;
   hidx v[3];              // vertex ids, decreasing
@@ -103,11 +103,12 @@ struct HFacet {           // 72 bytes
   hidx ohead, olast, oprev;  // outside list (furthest last)
   hidx tag;               // scratch: BFS visit id (negative) / cone-local index
   hidx replace;
+  hidx ocount;            // points in the outside list
   unsigned char toporient, visible, isnew, pad;
 };
 
 struct HullWs {
-  double *hx, *hy, *hz;   // hull input coordinates [cap_pts]            (global)
+  double *hx, *hy, *hz;   // hull input coordinates [cap_pts]            (with the hot structures)
   double *ux, *uy, *uz;   // un-rounded cloud [cap_pts]                  (global)
   double* pdist;          // [cap_pts]
   hidx *pnext, *pbest, *plist, *pstart, *vpoint;  // [cap_pts + 8]
@@ -124,12 +125,13 @@ __host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   b += hull_align16(sizeof(double) * (size_t)cap_pts);                  // pdist
   b += hull_align16(sizeof(hidx) * 5 * ((size_t)cap_pts + 8));          // pnext pbest plist pstart vpoint
   b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + LQRO_HULL_MAXNEW));  // order vis freel newf
+  b += hull_align16(3 * sizeof(double) * (size_t)cap_pts);              // hx hy hz (hull input coordinates)
   return b;
 }
 __host__ __device__ inline int hull_full_facets(int cap_pts) { return 2 * cap_pts + 64; }
 // one global slot: 6 coordinate arrays + a full-size copy of the hot structures (fallback path)
 __host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
-  size_t b = hull_align16(6 * sizeof(double) * (size_t)cap_pts) + hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
+  size_t b = hull_align16(3 * sizeof(double) * (size_t)cap_pts) + hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
   return (b + 255) & ~(size_t)255;
 }
 __device__ inline void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs& w) {
@@ -144,16 +146,18 @@ __device__ inline void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs
   base += hull_align16(sizeof(hidx) * 5 * ci);
   hidx* jp = reinterpret_cast<hidx*>(base);
   w.order = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f; w.newf = jp + 3 * (size_t)cap_f;
-}
-__device__ inline void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {
-  double* d = reinterpret_cast<double*>(gbase);
+  base += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + LQRO_HULL_MAXNEW));
+  double* d = reinterpret_cast<double*>(base);
   w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
-  w.ux = d + 3 * (size_t)cap_pts; w.uy = d + 4 * (size_t)cap_pts; w.uz = d + 5 * (size_t)cap_pts;
+}
+__device__ inline void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {  // the un-rounded cloud
+  double* d = reinterpret_cast<double*>(gbase);
+  w.ux = d; w.uy = d + cap_pts; w.uz = d + 2 * (size_t)cap_pts;
 }
 // everything in the global slot (fallback / stage kernel)
 __device__ inline void hull_ws_carve(char* gbase, int cap_pts, HullWs& w) {
   hull_carve_coords(gbase, cap_pts, w);
-  hull_carve_hot(gbase + hull_align16(6 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+  hull_carve_hot(gbase + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
 }
 
 // per-warp control block in shared memory (written by lane 0, read by all after __syncwarp)
@@ -204,13 +208,14 @@ __device__ inline int hl_newfacet(HullWs& w, HullCtl& c) {
   else if (c.pool_used < w.cap_f) f = c.pool_used++;
   else { c.fail = 2; return -1; }  // pool exhausted
   HFacet& F = w.F[f];
-  F.prev = F.next = -1; F.ohead = F.olast = F.oprev = -1; F.furthestdist = 0; F.tag = 0; F.replace = -1;
+  F.prev = F.next = -1; F.ohead = F.olast = F.oprev = -1; F.furthestdist = 0; F.tag = 0; F.replace = -1; F.ocount = 0;
   F.toporient = F.visible = F.isnew = 0;
   return f;
 }
 // outside-list append with qhull's "furthest stays last" rule (qh_partitionpoint)
 __device__ inline void hl_outside_add(HullWs& w, int f, int p, double d) {
   HFacet& F = w.F[f];
+  F.ocount++;
   if (F.olast < 0) { F.ohead = F.olast = p; F.oprev = -1; w.pnext[p] = -1; F.furthestdist = d; }
   else if (F.furthestdist < d) { w.pnext[F.olast] = p; F.oprev = F.olast; F.olast = p; w.pnext[p] = -1; F.furthestdist = d; }
   else {  // qh_setappend2ndlast
@@ -514,6 +519,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
           else if (d > bestdist[q]) { emit = bestpoint[q]; bestpoint[q] = i; bestdist[q] = d; }
           else emit = i;
           if (emit >= 0) { if (tail[q] < 0) w.F[f].ohead = (hidx)emit; else w.pnext[tail[q]] = (hidx)emit; tail[q] = emit; }
+          w.F[f].ocount++;
         }
         for (int q = 0; q < 4; ++q) {
           if (bestpoint[q] < 0) continue;
@@ -551,6 +557,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
         HFacet& F0 = w.F[facet];
         const int furthest = F0.olast;
         if (F0.oprev >= 0) { w.pnext[F0.oprev] = -1; F0.olast = F0.oprev; } else { F0.ohead = -1; F0.olast = -1; }
+        F0.ocount--;
         ++c.ninserted;
         c.apex[0] = w.hx[furthest]; c.apex[1] = w.hy[furthest]; c.apex[2] = w.hz[furthest];
         F0.visible = 1; F0.replace = -1;
@@ -625,7 +632,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
               if (horizonskip < 0) failcode = 3;
               else {
                 HFacet& NF = w.F[f];
-                NF.ohead = NF.olast = NF.oprev = -1; NF.furthestdist = 0; NF.replace = -1;
+                NF.ohead = NF.olast = NF.oprev = -1; NF.furthestdist = 0; NF.replace = -1; NF.ocount = 0;
                 NF.visible = 0; NF.isnew = 1;
                 NF.v[0] = (hidx)apex;
                 int q2 = 1;
@@ -715,16 +722,35 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
           if (q0 != (f.n[0] > 0) || q1 != (f.n[1] > 0) || q2 != (f.n[2] > 0)) c.sharp = 1;
         }
       }
-      // qh_partitionvisible, pass 1: the points to re-partition in qhull's processing order
-      int nl = 0;
-      for (int vi = 0; vi < c.nvis; ++vi) {
-        HFacet& VF = w.F[w.vis[vi]];
-        const int start = VF.replace >= 0 ? VF.replace : c.newfacet_list;
-        for (int p = VF.ohead; p >= 0; p = w.pnext[p]) { w.plist[nl] = p; w.pstart[nl] = start; ++nl; }
-        VF.ohead = VF.olast = VF.oprev = -1;
-      }
-      c.nlist = nl;
       c.trigger_pos = 0x7fffffff;
+    }
+    __syncwarp();
+    // qh_partitionvisible, pass 1: the points to re-partition in qhull's processing order (visible facets in
+    // list order, each one's outside list in order).  One lane per visible facet walks its own list; the
+    // offsets come from a warp scan of the list lengths.
+    {
+      int nl = 0;
+      const int nvis = c.nvis;
+      for (int v0 = 0; v0 < nvis; v0 += 32) {
+        const int vi = v0 + lane;
+        int cnt = 0, vf = 0;
+        if (vi < nvis) { vf = w.vis[vi]; cnt = w.F[vf].ocount; }
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(LQRO_FULL, incl, off);
+          if (lane >= off) incl += t;
+        }
+        int pos = nl + incl - cnt;
+        if (vi < nvis && cnt > 0) {
+          HFacet& VF = w.F[vf];
+          const hidx start = (hidx)(VF.replace >= 0 ? VF.replace : c.newfacet_list);
+          for (int p = VF.ohead; p >= 0; p = w.pnext[p]) { w.plist[pos] = (hidx)p; w.pstart[pos] = start; ++pos; }
+          VF.ohead = VF.olast = VF.oprev = -1; VF.ocount = 0;
+        }
+        nl += __shfl_sync(LQRO_FULL, incl, 31);
+      }
+      if (lane == 0) c.nlist = nl;
     }
     __syncwarp();
     if (lane == 0) { const long long tn = clock64(); c.prof[4] += tn - tprof; tprof = tn; c.prof[10] += 1; c.prof[11] += c.nlist; }
@@ -773,17 +799,54 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
       ldeg = __any_sync(LQRO_FULL, ldeg);
       __syncwarp();
       if (lane == 0) { const long long tn = clock64(); c.prof[6] += tn - tprof; tprof = tn; }
-      if (lane == 0) {
-        if (ldeg) c.degenerate = 1;
-        // pass 4: append in processing order (qh_partitionpoint)
-        for (int q = 0; q < nl; ++q) {
+      // pass 4: append in processing order (qh_partitionpoint).  Appends to different facets commute, so lane t
+      // owns cone facet t and keeps its list head / last / second-last / furthest distance in registers while
+      // all lanes sweep the points in order; the rare points that land on an old facet are appended afterwards.
+      {
+        int pdeg = 0, anyold = 0;
+        for (int q = lane; q < nl; q += 32) {  // target code: cone index, -1 dropped, -2 - facet for an old facet
           const int b = w.pbest[q];
-          const double d = w.pdist[q];
-          if (fabs(d) < 4 * c.MINoutside) c.degenerate = 1;
-          if (b < 0) continue;  // inside / coplanar: dropped
-          const bool wasempty = w.F[b].olast < 0;
-          hl_outside_add(w, b, w.plist[q], d);
-          if (wasempty && !w.F[b].isnew) { hl_remove(w, c, b); hl_append(w, c, b); }
+          if (fabs(w.pdist[q]) < 4 * c.MINoutside) pdeg = 1;
+          int code = -1;
+          if (b >= 0) { if (w.F[b].isnew) code = w.F[b].tag; else { code = -2 - b; anyold = 1; } }
+          w.pstart[q] = (hidx)code;
+        }
+        pdeg = __any_sync(LQRO_FULL, pdeg || ldeg);
+        anyold = __any_sync(LQRO_FULL, anyold);
+        __syncwarp();
+        for (int t0 = 0; t0 < nnew; t0 += 32) {
+          const int mine = t0 + lane;
+          int oh = -1, ol = -1, op = -1, cnt = 0;
+          double fd = 0.0;
+          for (int q = 0; q < nl; ++q) {
+            const int code = w.pstart[q];
+            if (code == mine) {
+              const int pt = w.plist[q];
+              const double d = w.pdist[q];
+              ++cnt;
+              if (ol < 0) { oh = ol = pt; op = -1; w.pnext[pt] = -1; fd = d; }
+              else if (fd < d) { w.pnext[ol] = (hidx)pt; op = ol; ol = pt; w.pnext[pt] = -1; fd = d; }
+              else { if (op >= 0) w.pnext[op] = (hidx)pt; else oh = pt; w.pnext[pt] = (hidx)ol; op = pt; }  // qh_setappend2ndlast
+            }
+          }
+          if (mine < nnew && cnt > 0) {
+            HFacet& NF = w.F[w.newf[mine]];
+            NF.ohead = (hidx)oh; NF.olast = (hidx)ol; NF.oprev = (hidx)op; NF.furthestdist = fd; NF.ocount = (hidx)cnt;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if (pdeg) c.degenerate = 1;
+          if (anyold) {
+            for (int q = 0; q < nl; ++q) {
+              const int code = w.pstart[q];
+              if (code >= -1) continue;
+              const int b = -2 - code;
+              const bool wasempty = w.F[b].olast < 0;
+              hl_outside_add(w, b, w.plist[q], w.pdist[q]);
+              if (wasempty) { hl_remove(w, c, b); hl_append(w, c, b); }  // qhull moves it behind qh.facet_next
+            }
+          }
         }
       }
       __syncwarp();
@@ -838,7 +901,7 @@ __device__ inline void hull_nearest_facet(const HullWs& w, const HullCtl& c, con
 
 // ---- kernels -------------------------------------------------------------------------------------
 // shared-memory facet pool of the fast path (facets alive at once; typical LQR-obstacle hulls need < 700)
-#define LQRO_HULL_SMEM_FACETS 768
+#define LQRO_HULL_SMEM_FACETS 512
 
 __host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
   size_t b = sizeof(double) * (pair_block_table_doubles(H, P) + 3 * (size_t)H + 32 + (H + 1) / 2 + 1);  // tables + tr, dx, xi, klist
@@ -891,16 +954,17 @@ __global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const 
     }
     __syncwarp();
     const int n = warp_reachable_cloud(p, pt, pw);
-    for (int m = lane; m < n; m += 32) {
-      if (p.hull_input == 0) { w.hx[m] = round6_dev(w.ux[m]); w.hy[m] = round6_dev(w.uy[m]); w.hz[m] = round6_dev(w.uz[m]); }
-      else { w.hx[m] = w.ux[m]; w.hy[m] = w.uy[m]; w.hz[m] = w.uz[m]; }
-    }
-    __syncwarp();
-    hull_carve_hot(hot, cap_pts, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures in shared memory
-    hull_build(w, *ctl, n);
-    if (ctl->fail == 2) {                                       // pool too small: full-size pool in the global slot
-      hull_carve_hot(gslot + hull_align16(6 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+    hull_carve_hot(hot, cap_pts, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures + coordinates in shared memory
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int m = lane; m < n; m += 32) {
+        if (p.hull_input == 0) { w.hx[m] = round6_dev(w.ux[m]); w.hy[m] = round6_dev(w.uy[m]); w.hz[m] = round6_dev(w.uz[m]); }
+        else { w.hx[m] = w.ux[m]; w.hy[m] = w.uy[m]; w.hz[m] = w.uz[m]; }
+      }
+      __syncwarp();
       hull_build(w, *ctl, n);
+      if (ctl->fail != 2 || pass == 1) break;
+      // pool too small: once more with the full-size pool in the global slot
+      hull_carve_hot(gslot + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
       if (lane == 0) atomicAdd(counters + 5, 1);
     }
     if (ctl->fail) {
