@@ -27,14 +27,14 @@
 #define LQRO_HULL_MAXNEW 256  // cone facets per insertion handled by the per-lane visited bit set
 
 // ---- strtod(printf("%g", x)): nearest double to the 6-significant-digit decimal rendering of x ------
-__device__ inline double pow10_exact(int k) {  // 10^k, exact for 0 <= k <= 22
+__device__ __forceinline__ double pow10_exact(int k) {  // 10^k, exact for 0 <= k <= 22
   const double t[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
                         1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
   return t[k];
 }
 // value of |x| * 10^s as an unevaluated sum hi + lo (exact when 10^|s| is exact and the quotient case
 // is avoided; for s < 0 the quotient is correctly rounded and lo carries the exact remainder sign)
-__device__ inline void scale10(double ax, int s, double& hi, double& lo) {
+__device__ __forceinline__ void scale10(double ax, int s, double& hi, double& lo) {
   if (s >= 0) {
     double p = (s <= 22) ? pow10_exact(s) : pow10_exact(22);
     hi = ax * p;
@@ -55,7 +55,7 @@ __device__ inline void scale10(double ax, int s, double& hi, double& lo) {
     lo = -fma(hi, p, -ax) / p;  // remainder (ax - hi*p) / p, sign-exact
   }
 }
-__device__ inline double round6_dev(double x) {
+__device__ __forceinline__ double round6_dev(double x) {
   if (x == 0.0 || !(fabs(x) < 1.7976931348623157e308)) return x;
   const double ax = fabs(x);
   int e2;
@@ -134,7 +134,7 @@ __host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
   size_t b = hull_align16(3 * sizeof(double) * (size_t)cap_pts) + hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
   return (b + 255) & ~(size_t)255;
 }
-__device__ inline void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs& w) {
+__device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs& w) {
   w.cap_pts = cap_pts; w.cap_f = cap_f;
   w.F = reinterpret_cast<HFacet*>(base);
   base += hull_align16(sizeof(HFacet) * (size_t)cap_f);
@@ -150,12 +150,12 @@ __device__ inline void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs
   double* d = reinterpret_cast<double*>(base);
   w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
 }
-__device__ inline void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {  // the un-rounded cloud
+__device__ __forceinline__ void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {  // the un-rounded cloud
   double* d = reinterpret_cast<double*>(gbase);
   w.ux = d; w.uy = d + cap_pts; w.uz = d + 2 * (size_t)cap_pts;
 }
 // everything in the global slot (fallback / stage kernel)
-__device__ inline void hull_ws_carve(char* gbase, int cap_pts, HullWs& w) {
+__device__ __forceinline__ void hull_ws_carve(char* gbase, int cap_pts, HullWs& w) {
   hull_carve_coords(gbase, cap_pts, w);
   hull_carve_hot(gbase + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
 }
@@ -186,7 +186,7 @@ __device__ __forceinline__ double hull_searchdist(const HullCtl& c) {
 }
 
 // list surgery (lane 0): qh_appendfacet / qh_removefacet
-__device__ inline void hl_append(HullWs& w, HullCtl& c, int f) {
+__device__ __forceinline__ void hl_append(HullWs& w, HullCtl& c, int f) {
   const int tail = 0;
   if (tail == c.newfacet_list) c.newfacet_list = f;
   if (tail == c.facet_next) c.facet_next = f;
@@ -195,14 +195,14 @@ __device__ inline void hl_append(HullWs& w, HullCtl& c, int f) {
   if (w.F[tail].prev >= 0) w.F[w.F[tail].prev].next = f; else c.facet_list = f;
   w.F[tail].prev = f;
 }
-__device__ inline void hl_remove(HullWs& w, HullCtl& c, int f) {
+__device__ __forceinline__ void hl_remove(HullWs& w, HullCtl& c, int f) {
   const int nx = w.F[f].next, pv = w.F[f].prev;
   if (f == c.newfacet_list) c.newfacet_list = nx;
   if (f == c.facet_next) c.facet_next = nx;
   if (pv >= 0) { w.F[pv].next = nx; w.F[nx].prev = pv; }
   else { c.facet_list = nx; w.F[nx].prev = -1; }
 }
-__device__ inline int hl_newfacet(HullWs& w, HullCtl& c) {
+__device__ __forceinline__ int hl_newfacet(HullWs& w, HullCtl& c) {
   int f;
   if (c.nfree > 0) f = w.freel[--c.nfree];
   else if (c.pool_used < w.cap_f) f = c.pool_used++;
@@ -213,7 +213,7 @@ __device__ inline int hl_newfacet(HullWs& w, HullCtl& c) {
   return f;
 }
 // outside-list append with qhull's "furthest stays last" rule (qh_partitionpoint)
-__device__ inline void hl_outside_add(HullWs& w, int f, int p, double d) {
+__device__ __forceinline__ void hl_outside_add(HullWs& w, int f, int p, double d) {
   HFacet& F = w.F[f];
   F.ocount++;
   if (F.olast < 0) { F.ohead = F.olast = p; F.oprev = -1; w.pnext[p] = -1; F.furthestdist = d; }
@@ -225,7 +225,7 @@ __device__ inline void hl_outside_add(HullWs& w, int f, int p, double d) {
 }
 
 // qh_setfacetplane -> qh_sethyperplane_det (3-d) + qh_normalize2
-__device__ inline void hull_setplane(HullWs& w, int fi) {
+__device__ __forceinline__ void hull_setplane(HullWs& w, int fi) {
   HFacet& f = w.F[fi];
   const int a = w.vpoint[f.v[0]], b = w.vpoint[f.v[1]], c = w.vpoint[f.v[2]];
   const double p0x = w.hx[a], p0y = w.hy[a], p0z = w.hz[a];
@@ -240,12 +240,12 @@ __device__ inline void hull_setplane(HullWs& w, int fi) {
   f.off = -(p0x * f.n[0] + p0y * f.n[1] + p0z * f.n[2]);
 }
 
-__device__ inline double hdet2(double a1, double a2, double b1, double b2) { return a1 * b2 - a2 * b1; }
-__device__ inline double hdet3(double a1, double a2, double a3, double b1, double b2, double b3, double c1, double c2, double c3) {
+__device__ __forceinline__ double hdet2(double a1, double a2, double b1, double b2) { return a1 * b2 - a2 * b1; }
+__device__ __forceinline__ double hdet3(double a1, double a2, double a3, double b1, double b2, double b3, double c1, double c2, double c3) {
   return a1 * hdet2(b2, b3, c2, c3) - b1 * hdet2(a2, a3, c2, c3) + c1 * hdet2(a2, a3, b2, b3);
 }
 // qh_detsimplex on the first k coordinates (k = current simplex size)
-__device__ inline double hull_detsimplex(const HullWs& w, const HullCtl& c, int apex, const int* simplex, int k, bool* nearzero) {
+__device__ __forceinline__ double hull_detsimplex(const HullWs& w, const HullCtl& c, int apex, const int* simplex, int k, bool* nearzero) {
   const double ax = w.hx[apex], ay = w.hy[apex], az = w.hz[apex];
   double r[3][3];
   for (int i = 0; i < k; ++i) {
@@ -260,7 +260,7 @@ __device__ inline double hull_detsimplex(const HullWs& w, const HullCtl& c, int 
 
 // qh_findbesthorizon restricted to what can change a non-degenerate outcome: hill-climb over the
 // neighbours (new or old) of the best facet while one is strictly better (band = SEARCHdist).
-__device__ inline int hull_findbesthorizon(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* bestdist,
+__device__ __forceinline__ int hull_findbesthorizon(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* bestdist,
                                            int* degenerate) {
   int seen[24];
   int nseen = 0, best = start;
@@ -298,7 +298,7 @@ __device__ inline int hull_findbesthorizon(const HullWs& w, const HullCtl& c, do
 }
 
 // qh_findbestnew: exhaustive over the cone facets (list order == newf[] order), cyclically from `start`
-__device__ inline int hull_findbestnew(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+__device__ __forceinline__ int hull_findbestnew(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
                                        bool* isoutside, int* degenerate) {
   double bestdist = -8.9884656743115785e307;
   int best = -1;
@@ -323,7 +323,7 @@ __device__ inline int hull_findbestnew(const HullWs& w, const HullCtl& c, double
 
 // qh_findbest(point, start, !bestoutside, isnewfacets): directed walk over the cone facets.
 // trigger: the walk ended below -DISTround (the caller applies qhull's sharp-cone rule).
-__device__ inline int hull_findbest_walk(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+__device__ __forceinline__ int hull_findbest_walk(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
                                          bool* isoutside, bool* trigger, int* degenerate) {
   unsigned long long vm[LQRO_HULL_MAXNEW / 64];
 #pragma unroll
@@ -365,7 +365,7 @@ __device__ inline int hull_findbest_walk(const HullWs& w, const HullCtl& c, doub
 
 // Build the hull of the n points in w.hx/hy/hz.  On return (all lanes): c.fail / c.degenerate set,
 // w.order[0..c.nfacets_out) = facets in qhull list order.
-__device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
+__device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
   const int lane = lane_id();
   long long tprof = clock64();
   if (lane == 0) {
@@ -876,7 +876,7 @@ __device__ inline void hull_build(HullWs& w, HullCtl& c, int n) {
 
 // Nearest facet to v_rel in qhull's facet order (MAIN:825-837, with normal = facet 0's when it wins):
 // distance_f = |n_f . (v_rel - p_f)|, p_f = first listed vertex of f from the UN-ROUNDED cloud (ux,uy,uz).
-__device__ inline void hull_nearest_facet(const HullWs& w, const HullCtl& c, const double* ux, const double* uy, const double* uz,
+__device__ __forceinline__ void hull_nearest_facet(const HullWs& w, const HullCtl& c, const double* ux, const double* uy, const double* uz,
                                           double vr0, double vr1, double vr2, double* distance, double* normal, int* best_facet) {
   const int lane = lane_id();
   double bd = 1.7976931348623157e308;
@@ -912,7 +912,7 @@ __host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
 // Inside-case pairs queued by k_pairs: regenerate the reachable cloud (same code, same bits), render
 // it to 6 digits, hull it, pick the nearest facet, write the plane.  One warp (= one block) per queued
 // pair at a time; blocks take work items from an atomic counter and own one global workspace slot.
-__global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
                                              size_t ws_stride, int cap_pts, int* __restrict__ counters, long long* __restrict__ prof) {
   extern __shared__ double smem[];
@@ -996,7 +996,7 @@ __global__ void __launch_bounds__(32) k_hull(LqroParams p, LqroTables tb, const 
 // mode bit 0: apply the 6-digit rendering first.  Outputs facets in qhull order (planes nf*4, verts nf*3
 // as point indices); when vrel != NULL also the nearest-facet result (escape[0] = distance,
 // [1..3] = normal) and best facet.
-__global__ void __launch_bounds__(32) k_stage_hull(const double* __restrict__ pts, int n, int mode, char* __restrict__ ws_base, int cap_pts,
+__global__ void __launch_bounds__(32, 1) k_stage_hull(const double* __restrict__ pts, int n, int mode, char* __restrict__ ws_base, int cap_pts,
                                                    double* __restrict__ planes, int* __restrict__ verts, int maxf, int* __restrict__ info /*nf, degenerate, fail, ninserted, best*/,
                                                    const double* __restrict__ vrel, double* __restrict__ escape) {
   __shared__ HullCtl ctl;
