@@ -357,6 +357,15 @@ extern "C" void ref_sim_set_vgoal(void* h, const double* v) {
 // Avoidance half of a time step: MAIN:1373-1407 with run-time n and H.
 //   planes_out : n*(n-1)*6 floats or 0;  status_out : n*(n-1) ints or 0 (0 none, 1 outside, 2 inside)
 //   nplanes_out: n ints or 0.  Slot (i, jj) with jj = j - (j>i).
+static int g_fix_facet0 = 0;       // harness option, see ref_sim_set_fix_facet0
+static long g_facet0_events = 0;
+// The reference leaves `normal` untouched when hull facet 0 is the nearest one (MAIN:825-836), so the plane
+// inherits the previous pair's normal.  With this option the HARNESS (not the reference code) overwrites the
+// normal with facet 0's after convexHull returns, which is what a pair-parallel implementation computes.
+// Either way the number of such events is counted.
+extern "C" void ref_sim_set_fix_facet0(int on) { g_fix_facet0 = on; }
+extern "C" long ref_sim_facet0_events(void) { return g_facet0_events; }
+
 extern "C" void ref_sim_avoid(void* h, int H, double maxSpeed, double* newV, float* planes_out, int* status_out,
                               int* nplanes_out, int* nreach_out) {
   RefSim* s = (RefSim*)h;
@@ -384,7 +393,27 @@ extern "C" void ref_sim_avoid(void* h, int H, double maxSpeed, double* newV, flo
       int st = 0;
       if (numObstacle > 4) {
         pointInHull(qi->reachablePoints, s->insideHull, qi->x, s->q[j]->x);
-        if (s->insideHull) { convexHull(qi->reachablePoints, qi->x, s->q[j]->x, s->distance, s->normalVector); st = 2; }
+        if (s->insideHull) {
+          convexHull(qi->reachablePoints, qi->x, s->q[j]->x, s->distance, s->normalVector); st = 2;
+          if (g_last_nfacets > 0) {  // was facet 0 the nearest?  (distance is then exactly facet 0's)
+            const int v0 = g_last_verts[0];
+            const double d0 = abs(g_last_planes[0] * ((qi->x[3] - s->q[j]->x[3]) - qi->reachablePoints[v0][0]) +
+                                  g_last_planes[1] * ((qi->x[4] - s->q[j]->x[4]) - qi->reachablePoints[v0][1]) +
+                                  g_last_planes[2] * ((qi->x[5] - s->q[j]->x[5]) - qi->reachablePoints[v0][2]));
+            bool nearest0 = true;
+            for (int f = 1; f < g_last_nfacets && nearest0; ++f) {
+              const int vf = g_last_verts[3 * f];
+              const double df = abs(g_last_planes[4 * f] * ((qi->x[3] - s->q[j]->x[3]) - qi->reachablePoints[vf][0]) +
+                                    g_last_planes[4 * f + 1] * ((qi->x[4] - s->q[j]->x[4]) - qi->reachablePoints[vf][1]) +
+                                    g_last_planes[4 * f + 2] * ((qi->x[5] - s->q[j]->x[5]) - qi->reachablePoints[vf][2]));
+              if (df < d0) nearest0 = false;
+            }
+            if (nearest0) {
+              ++g_facet0_events;
+              if (g_fix_facet0) { s->normalVector[0] = g_last_planes[0]; s->normalVector[1] = g_last_planes[1]; s->normalVector[2] = g_last_planes[2]; }
+            }
+          }
+        }
         else { run_gjk(qi->x, s->q[j]->x, qi->reachablePoints, s->distance, s->normalVector); st = 1; }
         s->distance *= 0.5;
         createHalfPlanes(qi->x, s->distance, s->normalVector, s->insideHull, s->orcaPlanes);

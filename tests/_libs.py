@@ -191,6 +191,8 @@ class Reference:
         lib.ref_control_matrices.argtypes = [c_void_p] * 10
         lib.ref_find_fg.argtypes = [c_void_p] * 6
         lib.ref_set_weights.argtypes = [c_double] * 3
+        lib.ref_sim_facet0_events.restype = ctypes.c_long
+        lib.ref_sim_set_fix_facet0.argtypes = [c_int]
         lib.ref_step_agents.restype = ctypes.c_long
         lib.ref_step_agents.argtypes = [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_void_p, c_void_p]
         self._tmp = workdir or tempfile.mkdtemp(prefix="lqro_ref_")
