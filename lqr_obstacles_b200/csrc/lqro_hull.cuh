@@ -55,7 +55,7 @@ __device__ __forceinline__ void scale10(double ax, int s, double& hi, double& lo
     lo = -fma(hi, p, -ax) / p;  // remainder (ax - hi*p) / p, sign-exact
   }
 }
-__device__ __forceinline__ double round6_dev(double x) {
+__device__ __noinline__ double round6_dev(double x) {
   if (x == 0.0 || !(fabs(x) < 1.7976931348623157e308)) return x;
   const double ax = fabs(x);
   int e2;
@@ -258,15 +258,24 @@ __device__ __forceinline__ double hull_detsimplex(const HullWs& w, const HullCtl
   return det;
 }
 
+// The point-location routines are kept out of line (the hull loop is latency bound on one warp: its code
+// must stay small enough for the instruction cache); they get what they need by value.
+struct HullSearch {
+  const HFacet* F;
+  const hidx* newf;
+  int nnew;
+  double MINoutside, DISTround, distoutside, searchdist;
+};
+
 // qh_findbesthorizon restricted to what can change a non-degenerate outcome: hill-climb over the
 // neighbours (new or old) of the best facet while one is strictly better (band = SEARCHdist).
-__device__ __forceinline__ int hull_findbesthorizon(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* bestdist,
+__device__ __noinline__ int hull_findbesthorizon(const HullSearch w, double x, double y, double z, int start, double* bestdist,
                                            int* degenerate) {
   int seen[24];
   int nseen = 0, best = start;
   int stack[24];
   int nstack = 0;
-  const double searchdist = hull_searchdist(c);
+  const double searchdist = w.searchdist;
   double minsearch = *bestdist - searchdist;
   seen[nseen++] = start;
   int facet = start;
@@ -298,12 +307,12 @@ __device__ __forceinline__ int hull_findbesthorizon(const HullWs& w, const HullC
 }
 
 // qh_findbestnew: exhaustive over the cone facets (list order == newf[] order), cyclically from `start`
-__device__ __forceinline__ int hull_findbestnew(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+__device__ __noinline__ int hull_findbestnew(const HullSearch w, double x, double y, double z, int start, double* dist,
                                        bool* isoutside, int* degenerate) {
   double bestdist = -8.9884656743115785e307;
   int best = -1;
-  const double distoutside = hull_distoutside(c);
-  const int m = c.nnew;
+  const double distoutside = w.distoutside;
+  const int m = w.nnew;
   const int s0 = w.F[start].isnew ? w.F[start].tag : 0;
   for (int q = 0; q < m; ++q) {
     int idx = s0 + q; if (idx >= m) idx -= m;
@@ -315,15 +324,15 @@ __device__ __forceinline__ int hull_findbestnew(const HullWs& w, const HullCtl& 
       bestdist = d;
     }
   }
-  best = hull_findbesthorizon(w, c, x, y, z, best >= 0 ? best : start, &bestdist, degenerate);
+  best = hull_findbesthorizon(w, x, y, z, best >= 0 ? best : start, &bestdist, degenerate);
   *dist = bestdist;
-  *isoutside = !(bestdist < c.MINoutside);
+  *isoutside = !(bestdist < w.MINoutside);
   return best;
 }
 
 // qh_findbest(point, start, !bestoutside, isnewfacets): directed walk over the cone facets.
 // trigger: the walk ended below -DISTround (the caller applies qhull's sharp-cone rule).
-__device__ __forceinline__ int hull_findbest_walk(const HullWs& w, const HullCtl& c, double x, double y, double z, int start, double* dist,
+__device__ __noinline__ int hull_findbest_walk(const HullSearch w, double x, double y, double z, int start, double* dist,
                                          bool* isoutside, bool* trigger, int* degenerate) {
   unsigned long long vm[LQRO_HULL_MAXNEW / 64];
 #pragma unroll
@@ -331,7 +340,7 @@ __device__ __forceinline__ int hull_findbest_walk(const HullWs& w, const HullCtl
   *trigger = false;
   *isoutside = true;
   double d = hdist(w.F[start], x, y, z);
-  if (d >= c.MINoutside) { *dist = d; return start; }
+  if (d >= w.MINoutside) { *dist = d; return start; }
   double bestdist = d;
   int best = start;
   { const int t = w.F[start].tag; vm[t >> 6] |= 1ull << (t & 63); }
@@ -348,7 +357,7 @@ __device__ __forceinline__ int hull_findbest_walk(const HullWs& w, const HullCtl
       vm[t >> 6] |= 1ull << (t & 63);
       d = hdist(NB, x, y, z);
       if (d > bestdist) {
-        if (d >= c.MINoutside) { *dist = d; return nb; }
+        if (d >= w.MINoutside) { *dist = d; return nb; }
         best = nb; bestdist = d; nextf = nb;
         break;
       }
@@ -356,10 +365,10 @@ __device__ __forceinline__ int hull_findbest_walk(const HullWs& w, const HullCtl
     facet = nextf;
   }
   *dist = bestdist;
-  if (bestdist < -c.DISTround) { *trigger = true; return best; }  // caller decides (sharp / not sharp)
-  best = hull_findbesthorizon(w, c, x, y, z, best, &bestdist, degenerate);
+  if (bestdist < -w.DISTround) { *trigger = true; return best; }  // caller decides (sharp / not sharp)
+  best = hull_findbesthorizon(w, x, y, z, best, &bestdist, degenerate);
   *dist = bestdist;
-  *isoutside = !(bestdist < c.MINoutside);
+  *isoutside = !(bestdist < w.MINoutside);
   return best;
 }
 
@@ -760,10 +769,13 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
       // pass 2 (parallel): directed walk of every point.  w.pnext[p] is free while p is off every
       // list: it carries the "walk ended below -DISTround" mark.
       int mytrig = 0x7fffffff, ldeg = 0;
+      HullSearch hs;
+      hs.F = w.F; hs.newf = w.newf; hs.nnew = nnew; hs.MINoutside = c.MINoutside; hs.DISTround = c.DISTround;
+      hs.distoutside = hull_distoutside(c); hs.searchdist = hull_searchdist(c);
       for (int q = lane; q < nl; q += 32) {
         const int p = w.plist[q];
         double d; bool outside, trig;
-        const int best = hull_findbest_walk(w, c, w.hx[p], w.hy[p], w.hz[p], w.pstart[q], &d, &outside, &trig, &ldeg);
+        const int best = hull_findbest_walk(hs, w.hx[p], w.hy[p], w.hz[p], w.pstart[q], &d, &outside, &trig, &ldeg);
         if (trig) outside = false;
         w.pbest[q] = outside ? best : -1 - best;  // negative: not (yet) outside
         w.pdist[q] = d;
@@ -786,10 +798,10 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
             if (q < mytrig) continue;
             int start = w.pstart[q];
             if (q == mytrig) start = -1 - w.pbest[q];
-            best = hull_findbestnew(w, c, x, y, z, start, &d, &outside, &ldeg);
+            best = hull_findbestnew(hs, x, y, z, start, &d, &outside, &ldeg);
           } else {
             if (!w.pnext[p]) continue;
-            best = hull_findbesthorizon(w, c, x, y, z, -1 - w.pbest[q], &d, &ldeg);
+            best = hull_findbesthorizon(hs, x, y, z, -1 - w.pbest[q], &d, &ldeg);
             outside = !(d < c.MINoutside);
           }
           w.pbest[q] = outside ? best : -1 - best;
