@@ -15,6 +15,7 @@
 #include "lqro_gjk.cuh"
 #include "lqro_pair.cuh"
 #include "lqro_hull.cuh"
+#include "lqro_step.cuh"
 #include "lqro_lp.cuh"
 #include "lqro_riccati.cuh"
 
@@ -74,7 +75,7 @@ struct lqro_ctx {
   size_t hull_ws_stride = 0;
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
-  int pair_warps = 0, pair_blocks = 0; size_t pair_smem = 0;
+  int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
   int hull_wpb = 2, hull_blocks = 0; size_t hull_smem = 0;
   // stage scratch (grown on demand)
   char* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -211,7 +212,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMemset(ctx->d_nreach, 0, sizeof(int) * NP));
   CUC(cudaMemset(ctx->d_dist, 0, sizeof(double) * NP));
   CUC(cudaMemset(ctx->d_planes, 0, sizeof(float) * 6 * NP));
-  ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)(NP < 0x7fffffff ? NP : 0x7fffffff);
+  ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)(NP < (1u << 20) ? NP : (1u << 20));
   CUC(cudaMalloc(&ctx->d_hull_items, sizeof(int) * (size_t)ctx->hull_cap));
   // sphere samples: createSpheres, MAIN:665-680 (one-off table; radii doubled for the Minkowski sum)
   {
@@ -237,11 +238,16 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     const size_t per = sizeof(double) * pair_warp_doubles(H, P);     // full-capacity warp scratch (stage kernels)
     const size_t per2 = sizeof(double) * pair2_warp_doubles(H);      // pair kernel: capped cloud + overflow in HBM
     if (tbl + per > ctx->smem_optin) { g_create_err = "H*P too large for shared memory"; return bail(LQRO_E_LIMIT); }
-    int wp = (int)((ctx->smem_optin - tbl) / per2);
-    if (wp > 16) wp = 16;
+    // one hull warp per CTA if its structures fit next to >= 8 pair warps (512 threads x 128 registers = the
+    // whole register file, so 15 + 1 warps at most)
+    const size_t hullw = hull_warp_smem_bytes(H, P) + 32;
+    ctx->fused_hull = (tbl + 8 * per2 + hullw <= ctx->smem_optin) ? 1 : 0;
+    int wp = (int)((ctx->smem_optin - tbl - (ctx->fused_hull ? hullw : 0)) / per2);
+    const int wmax = ctx->fused_hull ? 15 : 16;
+    if (wp > wmax) wp = wmax;
     if (wp < 1) { g_create_err = "H too large for shared memory"; return bail(LQRO_E_LIMIT); }
     ctx->pair_warps = wp;
-    ctx->pair_smem = tbl + per2 * wp;
+    ctx->pair_smem = tbl + per2 * wp + (ctx->fused_hull ? hullw : 0);
     ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM
     ctx->pair_ovf_stride = 3 * (size_t)(H * P > LQRO_PAIR_CLOUD_CAP ? H * P - LQRO_PAIR_CLOUD_CAP : 0) + 8;
     CUC(cudaMalloc(&ctx->d_pair_ovf, sizeof(double) * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * wp));
@@ -258,6 +264,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int slots = cfg->hull_slots > 0 ? cfg->hull_slots : ctx->sm_count * per_sm;
+    if (slots < ctx->sm_count) slots = ctx->sm_count;
     ctx->hull_slots = slots;
     ctx->hull_blocks = slots;
     ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
@@ -373,13 +380,15 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
   CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
   CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 16, st));
+  CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet
+  StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   CU(cudaEventRecord(ctx->ev[0], st));
-  k_pairs<<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, ctx->d_ctr + 0, hq, ctx->d_pair_ovf,
-                                                                           ctx->pair_ovf_stride);
+  k_pairs<<<ctx->pair_blocks, (ctx->pair_warps + ctx->fused_hull) * 32, ctx->pair_smem, st>>>(
+      p, ctx->tb, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf, ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
-  k_hull<<<ctx->hull_blocks, ctx->hull_wpb * 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws,
-                                                                      ctx->hull_ws_stride, ctx->cap_pts, ctx->d_ctr, ctx->d_prof);
+  k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws, ctx->hull_ws_stride,
+                                                      ctx->d_ctr, ctx->d_prof);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,

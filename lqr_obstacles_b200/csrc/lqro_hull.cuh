@@ -915,92 +915,119 @@ __device__ __forceinline__ void hull_nearest_facet(const HullWs& w, const HullCt
 // shared-memory facet pool of the fast path (facets alive at once; typical LQR-obstacle hulls need < 700)
 #define LQRO_HULL_SMEM_FACETS 512
 
+
+// One hull warp: its shared-memory scratch (Translate / dx / xi / step list, hot hull structures, control block)
+// and its global slot (un-rounded cloud + full-size fallback pool).
+struct HullWarp {
+  PairWarpSmem pw;
+  HullWs w;
+  HullCtl* ctl;
+  char* hot;
+  char* gslot;
+};
+// bytes of shared memory one hull warp needs after the block tables
+__host__ __device__ inline size_t hull_warp_smem_bytes(int H, int P) {
+  return hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1)) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) +
+         hull_align16(sizeof(HullCtl));
+}
 __host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
-  size_t b = sizeof(double) * (pair_block_table_doubles(H, P) + 3 * (size_t)H + 32 + (H + 1) / 2 + 1);  // tables + tr, dx, xi, klist
-  b = hull_align16(b) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) + hull_align16(sizeof(HullCtl));
-  return b;
+  return hull_align16(sizeof(double) * pair_block_table_doubles(H, P)) + hull_warp_smem_bytes(H, P);
+}
+__device__ __forceinline__ void hull_warp_setup(HullWarp& hw, char* sm, char* gslot, int H, int P) {
+  double* wb = reinterpret_cast<double*>(sm);
+  hw.pw.tr = wb; hw.pw.dx = wb + 3 * H; hw.pw.xi = hw.pw.dx + 16; hw.pw.klist = reinterpret_cast<int*>(hw.pw.xi + 16);
+  hw.hot = sm + hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1));
+  hw.ctl = reinterpret_cast<HullCtl*>(hw.hot + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS));
+  hw.gslot = gslot;
+  hull_carve_coords(gslot, H * P, hw.w);
+  hw.pw.px = hw.w.ux; hw.pw.py = hw.w.uy; hw.pw.pz = hw.w.uz;
 }
 
-// Inside-case pairs queued by k_pairs: regenerate the reachable cloud (same code, same bits), render
-// it to 6 digits, hull it, pick the nearest facet, write the plane.  One warp (= one block) per queued
-// pair at a time; blocks take work items from an atomic counter and own one global workspace slot.
+// One queued inside-case pair: regenerate the reachable cloud (same code, same bits as k_pairs), render it to
+// 6 digits, hull it, pick the nearest facet, write the plane.
+__device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTables& pt, HullWarp& hw, const double* __restrict__ x,
+                                             const int* __restrict__ nbr, const PairOutputs& out, int pair, int* counters,
+                                             long long* prof) {
+  const int lane = lane_id();
+  const int cap_pts = p.HP;
+  PairWarpSmem& pw = hw.pw;
+  HullWs& w = hw.w;
+  HullCtl* ctl = hw.ctl;
+  const int il = pair / p.K;
+  const int i = p.local_begin + il;
+  const int j = nbr[pair];
+  if (lane < 16) {
+    const double a = x[(size_t)i * 16 + lane], b = x[(size_t)j * 16 + lane];
+    pw.xi[lane] = a;
+    pw.dx[lane] = a - b;
+  }
+  __syncwarp();
+  const int n = warp_reachable_cloud(p, pt, pw);
+  hull_carve_hot(hw.hot, cap_pts, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures + coordinates in shared memory
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int m = lane; m < n; m += 32) {
+      if (p.hull_input == 0) { w.hx[m] = round6_dev(w.ux[m]); w.hy[m] = round6_dev(w.uy[m]); w.hz[m] = round6_dev(w.uz[m]); }
+      else { w.hx[m] = w.ux[m]; w.hy[m] = w.uy[m]; w.hz[m] = w.uz[m]; }
+    }
+    __syncwarp();
+    hull_build(w, *ctl, n);
+    if (ctl->fail != 2 || pass == 1) break;
+    // pool too small: once more with the full-size pool in the global slot
+    hull_carve_hot(hw.gslot + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+    if (lane == 0) atomicAdd(counters + 5, 1);
+  }
+  if (ctl->fail) {
+    if (lane == 0) { out.status[pair] = 0x100; out.nfacets[pair] = 0; atomicAdd(counters + 3, 1); }  // no plane
+    __syncwarp();
+    return;
+  }
+  double distance, normal[3]; int bestf;
+  hull_nearest_facet(w, *ctl, w.ux, w.uy, w.uz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
+  if (lane == 0 && prof) {
+    long long tot = 0;
+    for (int q = 0; q < 12; ++q) { atomicAdd((unsigned long long*)prof + q, (unsigned long long)ctl->prof[q]); if (q < 10) tot += ctl->prof[q]; }
+    atomicMax(prof + 12, tot);
+    atomicMax(prof + 13, (long long)n);
+    atomicMax(prof + 14, (long long)ctl->nfacets_out);
+  }
+  if (lane == 0) {
+    write_plane(out.planes + 6 * (size_t)pair, pw.xi + 3, distance, normal[0], normal[1], normal[2], true);
+    out.dist[pair] = distance;
+    out.nfacets[pair] = ctl->nfacets_out;
+    out.status[pair] = 2 | (ctl->degenerate ? 0x100 : 0);
+    if (ctl->degenerate) atomicAdd(counters + 3, 1);
+  }
+  __syncwarp();
+}
+
+// Stand-alone hull kernel: drains whatever the hull warps of k_pairs left in the queue (tickets continue on the
+// same counter).  One warp (= one block) per queued pair at a time.
 __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
-                                             size_t ws_stride, int cap_pts, int* __restrict__ counters, long long* __restrict__ prof) {
+                                             size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof) {
   extern __shared__ double smem[];
   const int lane = lane_id();
   int nq = *hq.count;
   if (nq > hq.capacity) nq = hq.capacity;
-  if ((int)blockIdx.x >= nq) return;  // nothing can be left for this block
+  if (*work_counter + (int)blockIdx.x >= nq) return;  // nothing can be left for this block
   PairTables pt;
-  PairWarpSmem pw;
   load_block_tables(smem, tb, p.H, p.P);
-  // small per-warp scratch right after the tables; the cloud itself goes to the global slot
   {
     const int H = p.H, P = p.P;
     pt.NFt = smem; pt.T = smem + 16 * 3 * H; pt.sphx = pt.T + 9 * H; pt.sphy = pt.sphx + P; pt.sphz = pt.sphy + P;
     pt.CG = pt.sphz + P; pt.prn = pt.CG + 9 * H;
-    double* wb = smem + pair_block_table_doubles(H, P);
-    pw.tr = wb; pw.dx = wb + 3 * H; pw.xi = pw.dx + 16; pw.klist = reinterpret_cast<int*>(pw.xi + 16);
   }
-  char* hot = reinterpret_cast<char*>(smem) +
-              hull_align16(sizeof(double) * (pair_block_table_doubles(p.H, p.P) + 3 * (size_t)p.H + 32 + (p.H + 1) / 2 + 1));
-  HullCtl* ctl = reinterpret_cast<HullCtl*>(hot + hull_hot_bytes(cap_pts, LQRO_HULL_SMEM_FACETS));
-  char* gslot = ws_base + ws_stride * (size_t)blockIdx.x;
-  HullWs w;
-  hull_carve_coords(gslot, cap_pts, w);
-  pw.px = w.ux; pw.py = w.uy; pw.pz = w.uz;
+  HullWarp hw;
+  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * pair_block_table_doubles(p.H, p.P)),
+                  ws_base + ws_stride * (size_t)blockIdx.x, p.H, p.P);
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(work_counter, 1);
     item = __shfl_sync(LQRO_FULL, item, 0);
     if (item >= nq) break;
     const int pair = hq.items[item];
-    const int il = pair / p.K;
-    const int i = p.local_begin + il;
-    const int j = nbr[pair];
-    if (lane < 16) {
-      const double a = x[(size_t)i * 16 + lane], b = x[(size_t)j * 16 + lane];
-      pw.xi[lane] = a;
-      pw.dx[lane] = a - b;
-    }
-    __syncwarp();
-    const int n = warp_reachable_cloud(p, pt, pw);
-    hull_carve_hot(hot, cap_pts, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures + coordinates in shared memory
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int m = lane; m < n; m += 32) {
-        if (p.hull_input == 0) { w.hx[m] = round6_dev(w.ux[m]); w.hy[m] = round6_dev(w.uy[m]); w.hz[m] = round6_dev(w.uz[m]); }
-        else { w.hx[m] = w.ux[m]; w.hy[m] = w.uy[m]; w.hz[m] = w.uz[m]; }
-      }
-      __syncwarp();
-      hull_build(w, *ctl, n);
-      if (ctl->fail != 2 || pass == 1) break;
-      // pool too small: once more with the full-size pool in the global slot
-      hull_carve_hot(gslot + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
-      if (lane == 0) atomicAdd(counters + 5, 1);
-    }
-    if (ctl->fail) {
-      if (lane == 0) { out.status[pair] = 0x100; out.nfacets[pair] = 0; atomicAdd(counters + 3, 1); }  // no plane
-      __syncwarp();
-      continue;
-    }
-    double distance, normal[3]; int bestf;
-    hull_nearest_facet(w, *ctl, w.ux, w.uy, w.uz, pw.dx[3], pw.dx[4], pw.dx[5], &distance, normal, &bestf);
-    if (lane == 0 && prof) {
-      long long tot = 0;
-      for (int q = 0; q < 12; ++q) { atomicAdd((unsigned long long*)prof + q, (unsigned long long)ctl->prof[q]); if (q < 10) tot += ctl->prof[q]; }
-      atomicMax(prof + 12, tot);
-      atomicMax(prof + 13, (long long)n);
-      atomicMax(prof + 14, (long long)ctl->nfacets_out);
-    }
-    if (lane == 0) {
-      write_plane(out.planes + 6 * (size_t)pair, pw.xi + 3, distance, normal[0], normal[1], normal[2], true);
-      out.dist[pair] = distance;
-      out.nfacets[pair] = ctl->nfacets_out;
-      out.status[pair] = 2 | (ctl->degenerate ? 0x100 : 0);
-      if (ctl->degenerate) atomicAdd(counters + 3, 1);
-    }
-    __syncwarp();
+    if (pair < 0) continue;
+    hull_do_pair(p, pt, hw, x, nbr, out, pair, counters, prof);
   }
 }
 

@@ -319,185 +319,6 @@ __device__ __forceinline__ void write_plane(float* pl, const double* vi, double 
 }
 
 // ------------------------------------------------------------------------------------------------
-// The pair kernel.  Persistent CTAs (one per SM, up to 16 warps); a warp takes BATCHES of 32 consecutive
-// pair slots (one atomic per batch) and runs two stages:
-//
-//  stage 1, lane = pair (32 pairs in flight per warp, no shuffles, table reads are warp-uniform broadcasts):
-//     load x_i, x_j, form dx; for every horizon step evaluate Translate_k with FMAs (an approximation whose
-//     error is charged to the bound) and the exact pruning rule -> 64-bit mask of surviving steps.
-//     Pairs with no surviving step are finished here (status NONE), with coalesced stores.
-//  stage 2, warp = pair, for the lanes whose mask is non-zero: Translate_k of the surviving steps in the
-//     reference's operation order, candidate generation + reachable filter into the warp's cloud (first
-//     LQRO_PAIR_CLOUD_CAP points in shared memory, overflow in a per-warp global area), GJK, half-plane
-//     (outside case) or hull queue (inside case).
-#define LQRO_PAIR_CLOUD_CAP 256
-
-struct PairWarpV2 {
-  double *cx, *cy, *cz;  // [LQRO_PAIR_CLOUD_CAP]
-  double* tr;            // [3H]
-  double* dx;            // [16]
-  double* xi;            // [16]
-  int* klist;            // [H]
-};
-__host__ __device__ inline size_t pair2_warp_doubles(int H) { return (size_t)3 * LQRO_PAIR_CLOUD_CAP + 3 * H + 32 + (H + 1) / 2 + 1; }
-
-__global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
-                                                  PairOutputs out, int* __restrict__ work_counter, HullQueue hq,
-                                                  double* __restrict__ ovf_base, size_t ovf_stride) {
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  PairTables t;
-  load_block_tables(smem, tb, p.H, p.P);
-  {
-    const int H = p.H, P = p.P;
-    t.NFt = smem; t.T = smem + 16 * 3 * H; t.sphx = t.T + 9 * H; t.sphy = t.sphx + P; t.sphz = t.sphy + P;
-    t.CG = t.sphz + P; t.prn = t.CG + 9 * H;
-  }
-  PairWarpV2 w;
-  {
-    double* wb = smem + pair_block_table_doubles(p.H, p.P) + (size_t)warp * pair2_warp_doubles(p.H);
-    w.cx = wb; w.cy = wb + LQRO_PAIR_CLOUD_CAP; w.cz = wb + 2 * LQRO_PAIR_CLOUD_CAP;
-    w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * p.H; w.xi = w.dx + 16;
-    w.klist = reinterpret_cast<int*>(w.xi + 16);
-  }
-  CloudView cl;
-  cl.sx = w.cx; cl.sy = w.cy; cl.sz = w.cz; cl.cap = LQRO_PAIR_CLOUD_CAP;
-  {
-    double* ov = ovf_base + ovf_stride * (size_t)(blockIdx.x * (blockDim.x >> 5) + warp);
-    const size_t no = (size_t)(p.HP > LQRO_PAIR_CLOUD_CAP ? p.HP - LQRO_PAIR_CLOUD_CAP : 0);
-    cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
-  }
-  const int npairs = p.n_local * p.K;
-  const int n3 = 3 * p.H;
-  const unsigned long long allsteps = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
-  while (true) {
-    int batch = 0;
-    if (lane == 0) batch = atomicAdd(work_counter, 1);
-    batch = __shfl_sync(LQRO_FULL, batch, 0);
-    const int base = batch * 32;
-    if (base >= npairs) break;
-    // ---------------- stage 1: lane = pair
-    const int pair = base + lane;
-    int i = 0, j = -1;
-    unsigned long long kmask = 0ull;
-    if (pair < npairs) {
-      i = p.local_begin + pair / p.K;
-      j = nbr[pair];
-      if (j >= 0 && j != i && j < p.N) {  // the reference skips i == j (MAIN:1379)
-        if (!p.prune) {
-          kmask = allsteps;
-        } else {
-          double dx[16];
-          const double2* xi2 = reinterpret_cast<const double2*>(x + (size_t)i * 16);
-          const double2* xj2 = reinterpret_cast<const double2*>(x + (size_t)j * 16);
-          double dx1 = 0.0;
-#pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const double2 a = xi2[m], b = xj2[m];
-            dx[2 * m] = a.x - b.x; dx[2 * m + 1] = a.y - b.y;
-            dx1 += fabs(dx[2 * m]) + fabs(dx[2 * m + 1]);
-          }
-          const double vr0 = dx[3], vr1 = dx[4], vr2 = dx[5];
-          for (int k = 0; k < p.H; ++k) {
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            const double* nf = t.NFt + 3 * k;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-              t0 = fma(nf[m * n3], dx[m], t0);
-              t1 = fma(nf[m * n3 + 1], dx[m], t1);
-              t2 = fma(nf[m * n3 + 2], dx[m], t2);
-            }
-            // |fused sum - reference's rounded sum| <= 2 * 16 * 2^-53 * sum |NF||dx| <= 1e-14 * max|NF_k| * |dx|_1
-            const double tr_err = 1.0e-14 * t.prn[LQRO_PRN * k + 7] * dx1;
-            if (!step_prunable_v(p, t, k, t0, t1, t2, tr_err, vr0, vr1, vr2)) kmask |= 1ull << k;
-          }
-        }
-      }
-      if (kmask == 0ull) { out.status[pair] = 0; out.nreach[pair] = 0; }
-    }
-    // ---------------- stage 2: warp = pair
-    unsigned act = __ballot_sync(LQRO_FULL, kmask != 0ull);
-    while (act) {
-      const int src = __ffs(act) - 1;
-      act &= act - 1;
-      const int pr = base + src;
-      const int ii = __shfl_sync(LQRO_FULL, i, src);
-      const int jj = __shfl_sync(LQRO_FULL, j, src);
-      const unsigned long long km = __shfl_sync(LQRO_FULL, kmask, src);
-      if (lane < 16) {
-        const double a = x[(size_t)ii * 16 + lane], b = x[(size_t)jj * 16 + lane];
-        w.xi[lane] = a;
-        w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
-      }
-      const int nk = __popcll(km);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int k = lane + 32 * h;
-        if (k < p.H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
-      }
-      __syncwarp();
-      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231)
-      for (int e = lane; e < 3 * nk; e += 32) {
-        const int ki = e / 3, c = e - 3 * ki;
-        const int k = w.klist[ki];
-        const double* nf = t.NFt + 3 * k + c;
-        double s = 0;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) s += nf[m * n3] * w.dx[m];
-        w.tr[3 * k + c] = s;
-      }
-      __syncwarp();
-      const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
-      int count = 0;
-      const int total = nk * p.P;
-      int ki = 0, s = lane;
-      while (s >= p.P) { s -= p.P; ++ki; }
-      for (int b0 = 0; b0 < total; b0 += 32) {
-        const int m = b0 + lane;
-        bool pass = false;
-        double q0 = 0, q1 = 0, q2 = 0;
-        if (m < total) {
-          candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
-          pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
-        }
-        const unsigned mask = __ballot_sync(LQRO_FULL, pass);
-        if (pass) cl.put(count + __popc(mask & ((1u << lane) - 1u)), q0, q1, q2);
-        count += __popc(mask);
-        s += 32;
-        while (s >= p.P) { s -= p.P; ++ki; }
-      }
-      __syncwarp();
-      const int n = count;
-      if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
-        if (lane == 0) { out.status[pr] = 0; out.nreach[pr] = n; }
-        __syncwarp();
-        continue;
-      }
-      double gw1[3], gw2[3];
-      const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
-      if (lane == 0) {
-        const double distance = sqrt(sq);                             // MAIN:741
-        const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
-        out.nreach[pr] = n;
-        if (!inside) {
-          const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
-          const double n1 = (gw1[1] - gw2[1]) / distance;
-          const double n2 = (gw1[2] - gw2[2]) / distance;
-          write_plane(out.planes + 6 * (size_t)pr, w.xi + 3, distance, n0, n1, n2, false);
-          out.dist[pr] = distance;
-          out.status[pr] = 1;
-        } else {
-          out.status[pr] = 2;  // plane filled in by k_hull
-          const int slot = atomicAdd(hq.count, 1);
-          if (slot < hq.capacity) hq.items[slot] = pr;
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Stage kernels behind the per-stage C entry points (one warp, one pair / one cloud).
 
 // mode 0: all H*P candidate points of the pair (xi, xj) -> q_out (AoS [HP][3])

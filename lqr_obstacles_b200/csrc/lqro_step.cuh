@@ -1,0 +1,274 @@
+// lqro_step.cuh -- the pair kernel of a step, with the hull work of the inside case overlapped.
+//
+// Persistent CTAs, one per SM.  Warp roles:
+//
+//  * PAIR warps take BATCHES of 32 pair slots (one atomic per batch) and run two stages:
+//      stage 1, lane = pair (32 pairs in flight, no shuffles, table reads are warp-uniform broadcasts): load
+//        x_i, x_j, form dx; per horizon step evaluate Translate_k with FMAs (approximation charged to the bound)
+//        and the exact pruning rule -> 64-bit mask of surviving steps.  Pairs with no surviving step finish here
+//        (status NONE, coalesced stores).
+//      stage 2, warp = pair, for the lanes with a non-zero mask: Translate_k of the surviving steps in the
+//        reference's operation order, candidate generation + reachable filter into the warp's cloud (first
+//        LQRO_PAIR_CLOUD_CAP points in shared memory, overflow in a per-warp HBM area), GJK, half-plane
+//        (outside case) or a ticket in the hull queue (inside case).
+//    Batches are handed out SLOT-MAJOR (all agents' slots 0..31 first): neighbour lists are sorted by distance,
+//    so the inside pairs -- the ones that need a hull -- surface early in the kernel.
+//
+//  * one HULL warp per CTA (when its structures fit next to the pair warps) consumes the hull queue while the
+//    pair warps are still producing: qhull's insertion order makes one hull a ~1.5 ms sequential job, which
+//    would otherwise sit on the critical path of the step after the pair kernel.  Whatever is still queued
+//    when the producers finish is drained by the wide stand-alone k_hull launched right after.
+//    Queue protocol: producers take a slot with atomicAdd(count), store the pair id, fence; consumers take
+//    tickets with atomicAdd(head) and poll items[ticket] (initialised to -1 every step) until it is filled or
+//    every producer warp has signed off.  Producers never wait for consumers.
+#pragma once
+#include "lqro_common.cuh"
+#include "lqro_gjk.cuh"
+#include "lqro_pair.cuh"
+#include "lqro_hull.cuh"
+
+#define LQRO_PAIR_CLOUD_CAP 256
+
+struct PairWarpV2 {
+  double *cx, *cy, *cz;  // [LQRO_PAIR_CLOUD_CAP]
+  double* tr;            // [3H]
+  double* dx;            // [16]
+  double* xi;            // [16]
+  int* klist;            // [H]
+};
+__host__ __device__ inline size_t pair2_warp_doubles(int H) { return (size_t)3 * LQRO_PAIR_CLOUD_CAP + 3 * H + 32 + (H + 1) / 2 + 1; }
+
+struct StepSync {
+  int* batch_counter;   // next batch of pairs
+  int* hull_head;       // next hull ticket
+  int* done_warps;      // pair warps that have finished
+  int* counters;        // misc counters (degenerate, fallback, ...)
+  long long* prof;
+};
+
+// slot-major enumeration: chunk c covers neighbour slots [32c, min(K, 32c+32)); within a chunk pairs are
+// agent-major.  idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end.
+__device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long idx, int& il, int& kk) {
+  int c0 = 0;
+  while (c0 < p.K) {
+    const int wdt = (p.K - c0 < 32) ? (p.K - c0) : 32;
+    const long long cnt = (long long)p.n_local * wdt;
+    const long long padded = (cnt + 31) & ~31ll;  // chunks start on a batch boundary
+    if (idx < padded) {
+      if (idx >= cnt) return false;
+      il = (int)(idx / wdt);
+      kk = c0 + (int)(idx - (long long)il * wdt);
+      return true;
+    }
+    idx -= padded;
+    c0 += 32;
+  }
+  return false;
+}
+__host__ __device__ inline long long slot_major_total(int n_local, int K) {
+  long long t = 0;
+  for (int c0 = 0; c0 < K; c0 += 32) {
+    const int wdt = (K - c0 < 32) ? (K - c0) : 32;
+    t += (((long long)n_local * wdt) + 31) & ~31ll;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+                                                  PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
+                                                  size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  PairTables t;
+  load_block_tables(smem, tb, p.H, p.P);
+  {
+    const int H = p.H, P = p.P;
+    t.NFt = smem; t.T = smem + 16 * 3 * H; t.sphx = t.T + 9 * H; t.sphy = t.sphx + P; t.sphz = t.sphy + P;
+    t.CG = t.sphz + P; t.prn = t.CG + 9 * H;
+  }
+  const int total_pair_warps = n_pair_warps * gridDim.x;
+
+  if (warp >= n_pair_warps) {
+    // ------------------------------------------------------------------ hull warp (consumer)
+    HullWarp hw;
+    char* sm = reinterpret_cast<char*>(smem) +
+               hull_align16(sizeof(double) * (pair_block_table_doubles(p.H, p.P) + (size_t)n_pair_warps * pair2_warp_doubles(p.H)));
+    hull_warp_setup(hw, sm, hull_ws + hull_ws_stride * (size_t)blockIdx.x, p.H, p.P);
+    while (true) {
+      int ticket = -1;
+      if (lane == 0) {
+        // stop taking tickets once every producer has signed off: the stand-alone k_hull drains the rest
+        if (*(volatile int*)sy.done_warps < total_pair_warps) ticket = atomicAdd(sy.hull_head, 1);
+      }
+      ticket = __shfl_sync(LQRO_FULL, ticket, 0);
+      if (ticket < 0 || ticket >= hq.capacity) break;
+      int pair = -1;
+      if (lane == 0) {
+        while (true) {
+          pair = *(volatile int*)(hq.items + ticket);
+          if (pair >= 0) break;
+          if (*(volatile int*)sy.done_warps >= total_pair_warps) {  // all items are published by now
+            pair = *(volatile int*)(hq.items + ticket);
+            break;
+          }
+          __nanosleep(400);
+        }
+      }
+      pair = __shfl_sync(LQRO_FULL, pair, 0);
+      if (pair < 0) {  // ticket beyond the final tail: hand it back so k_hull's scan stays contiguous
+        break;
+      }
+      hull_do_pair(p, t, hw, x, nbr, out, pair, sy.counters, sy.prof);
+      if (lane == 0) hq.items[ticket] = -2 - pair;  // done marker (k_hull skips negative entries)
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- pair warps (producers)
+  PairWarpV2 w;
+  {
+    double* wb = smem + pair_block_table_doubles(p.H, p.P) + (size_t)warp * pair2_warp_doubles(p.H);
+    w.cx = wb; w.cy = wb + LQRO_PAIR_CLOUD_CAP; w.cz = wb + 2 * LQRO_PAIR_CLOUD_CAP;
+    w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * p.H; w.xi = w.dx + 16;
+    w.klist = reinterpret_cast<int*>(w.xi + 16);
+  }
+  CloudView cl;
+  cl.sx = w.cx; cl.sy = w.cy; cl.sz = w.cz; cl.cap = LQRO_PAIR_CLOUD_CAP;
+  {
+    double* ov = ovf_base + ovf_stride * (size_t)(blockIdx.x * n_pair_warps + warp);
+    const size_t no = (size_t)(p.HP > LQRO_PAIR_CLOUD_CAP ? p.HP - LQRO_PAIR_CLOUD_CAP : 0);
+    cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
+  }
+  const long long total = slot_major_total(p.n_local, p.K);
+  const int n3 = 3 * p.H;
+  const unsigned long long allsteps = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
+  while (true) {
+    int batch = 0;
+    if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
+    batch = __shfl_sync(LQRO_FULL, batch, 0);
+    const long long base = (long long)batch * 32;
+    if (base >= total) break;
+    // ---------------- stage 1: lane = pair
+    int il = 0, kk = 0;
+    const bool have = slot_major_pair(p, base + lane, il, kk);
+    const int pair = have ? il * p.K + kk : -1;
+    int i = 0, j = -1;
+    unsigned long long kmask = 0ull;
+    if (have) {
+      i = p.local_begin + il;
+      j = nbr[pair];
+      if (j >= 0 && j != i && j < p.N) {  // the reference skips i == j (MAIN:1379)
+        if (!p.prune) {
+          kmask = allsteps;
+        } else {
+          double dx[16];
+          const double2* xi2 = reinterpret_cast<const double2*>(x + (size_t)i * 16);
+          const double2* xj2 = reinterpret_cast<const double2*>(x + (size_t)j * 16);
+          double dx1 = 0.0;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const double2 a = xi2[m], b = xj2[m];
+            dx[2 * m] = a.x - b.x; dx[2 * m + 1] = a.y - b.y;
+            dx1 += fabs(dx[2 * m]) + fabs(dx[2 * m + 1]);
+          }
+          const double vr0 = dx[3], vr1 = dx[4], vr2 = dx[5];
+          for (int k = 0; k < p.H; ++k) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            const double* nf = t.NFt + 3 * k;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+              t0 = fma(nf[m * n3], dx[m], t0);
+              t1 = fma(nf[m * n3 + 1], dx[m], t1);
+              t2 = fma(nf[m * n3 + 2], dx[m], t2);
+            }
+            // |fused sum - reference's rounded sum| <= 2 * 16 * 2^-53 * sum |NF||dx| <= 1e-14 * max|NF_k| * |dx|_1
+            const double tr_err = 1.0e-14 * t.prn[LQRO_PRN * k + 7] * dx1;
+            if (!step_prunable_v(p, t, k, t0, t1, t2, tr_err, vr0, vr1, vr2)) kmask |= 1ull << k;
+          }
+        }
+      }
+      if (kmask == 0ull) { out.status[pair] = 0; out.nreach[pair] = 0; }
+    }
+    // ---------------- stage 2: warp = pair
+    unsigned act = __ballot_sync(LQRO_FULL, kmask != 0ull);
+    while (act) {
+      const int src = __ffs(act) - 1;
+      act &= act - 1;
+      const int pr = __shfl_sync(LQRO_FULL, pair, src);
+      const int ii = __shfl_sync(LQRO_FULL, i, src);
+      const int jj = __shfl_sync(LQRO_FULL, j, src);
+      const unsigned long long km = __shfl_sync(LQRO_FULL, kmask, src);
+      if (lane < 16) {
+        const double a = x[(size_t)ii * 16 + lane], b = x[(size_t)jj * 16 + lane];
+        w.xi[lane] = a;
+        w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
+      }
+      const int nk = __popcll(km);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < p.H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
+      }
+      __syncwarp();
+      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231)
+      for (int e = lane; e < 3 * nk; e += 32) {
+        const int ki = e / 3, c = e - 3 * ki;
+        const int k = w.klist[ki];
+        const double* nf = t.NFt + 3 * k + c;
+        double s = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s += nf[m * n3] * w.dx[m];
+        w.tr[3 * k + c] = s;
+      }
+      __syncwarp();
+      const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
+      int count = 0;
+      const int tot = nk * p.P;
+      int ki = 0, s = lane;
+      while (s >= p.P) { s -= p.P; ++ki; }
+      for (int b0 = 0; b0 < tot; b0 += 32) {
+        const int m = b0 + lane;
+        bool pass = false;
+        double q0 = 0, q1 = 0, q2 = 0;
+        if (m < tot) {
+          candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
+          pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
+        }
+        const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+        if (pass) cl.put(count + __popc(mask & ((1u << lane) - 1u)), q0, q1, q2);
+        count += __popc(mask);
+        s += 32;
+        while (s >= p.P) { s -= p.P; ++ki; }
+      }
+      __syncwarp();
+      const int n = count;
+      if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
+        if (lane == 0) { out.status[pr] = 0; out.nreach[pr] = n; }
+        __syncwarp();
+        continue;
+      }
+      double gw1[3], gw2[3];
+      const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
+      if (lane == 0) {
+        const double distance = sqrt(sq);                             // MAIN:741
+        const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
+        out.nreach[pr] = n;
+        if (!inside) {
+          const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
+          const double n1 = (gw1[1] - gw2[1]) / distance;
+          const double n2 = (gw1[2] - gw2[2]) / distance;
+          write_plane(out.planes + 6 * (size_t)pr, w.xi + 3, distance, n0, n1, n2, false);
+          out.dist[pr] = distance;
+          out.status[pr] = 1;
+        } else {
+          out.status[pr] = 2;  // plane filled in by a hull warp / k_hull
+          __threadfence();
+          const int slot = atomicAdd(hq.count, 1);
+          if (slot < hq.capacity) { *(volatile int*)(hq.items + slot) = pr; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) { __threadfence(); atomicAdd(sy.done_warps, 1); }
+}
