@@ -70,6 +70,8 @@ typedef struct lqro_config {
 } lqro_config;
 
 #define LQRO_FLAG_NO_PRUNE 1   /* evaluate every horizon step of every pair (ablation / parity of the exact pruning) */
+#define LQRO_FLAG_FUSED_HULL 2 /* one hull warp per pair-kernel CTA consumes the inside-case queue concurrently
+                                  (experimental: measured slower than the stand-alone hull kernel) */
 
 /* Fills the reference's compile-time constants (MAIN:30-36, 1102, 1367). */
 void lqro_default_config(lqro_config* cfg);

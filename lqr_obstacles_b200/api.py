@@ -12,6 +12,7 @@ c_int, c_double, c_float, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_flo
 HULL_TEXT6, HULL_FP64 = 0, 1
 PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE = 0, 1, 2, 0x100
 FLAG_NO_PRUNE = 1
+FLAG_FUSED_HULL = 2
 
 
 class LqroError(RuntimeError):

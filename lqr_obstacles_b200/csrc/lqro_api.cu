@@ -241,7 +241,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     // one hull warp per CTA if its structures fit next to >= 8 pair warps (512 threads x 128 registers = the
     // whole register file, so 15 + 1 warps at most)
     const size_t hullw = hull_warp_smem_bytes(H, P) + 32;
-    ctx->fused_hull = (tbl + 8 * per2 + hullw <= ctx->smem_optin) ? 1 : 0;
+    ctx->fused_hull = ((cfg->flags & LQRO_FLAG_FUSED_HULL) && tbl + 8 * per2 + hullw <= ctx->smem_optin) ? 1 : 0;
     int wp = (int)((ctx->smem_optin - tbl - (ctx->fused_hull ? hullw : 0)) / per2);
     const int wmax = ctx->fused_hull ? 15 : 16;
     if (wp > wmax) wp = wmax;

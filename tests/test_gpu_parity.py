@@ -266,6 +266,10 @@ def test_swarm_step_vs_oracle(golden, oracle, product_lib):
     c = ctx.counters()
     assert c["inside"] == (ost3 == 2).sum() and c["launches"] == 3 and c["hull_overflow"] == 0
     ctx.close()
+    # experimental fused variant (hull warps inside the pair kernel): same bits
+    ctx_f = make_ctx(golden, n_agents=512, max_neighbors=32, horizon=20, flags=2)
+    _step_vs_oracle(ctx_f, oracle, x3, vpref, swarm.knn(x3[:, :3], 32), 20)
+    ctx_f.close()
 
 
 def test_full_size_properties(golden, oracle, product_lib):
