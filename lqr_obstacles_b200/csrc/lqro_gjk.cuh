@@ -181,6 +181,21 @@ __device__ __forceinline__ void gjk_simplex_step(GjkRegs& g, double v0, double v
   if (!g.use_default) gjk_backup_distance<SIZE>(g);
 }
 
+template <int N>
+__device__ __forceinline__ void gjk_witness(GjkRegs& g, double v0, double v1, double v2) {
+  const double vv[3] = {v0, v1, v2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a += vv[d] * g.lam[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) b += g.c2[i][d] * g.lam[i];
+    g.w1[d] = a;
+    g.w2[d] = b;
+  }
+}
+
 // The cloud of one pair: the first `cap` points in shared memory (SoA), the rest in a per-warp overflow
 // area in global memory (rare: dense scenes).  For a plain global cloud set cap = n.
 struct CloudView {
@@ -217,19 +232,12 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     else if (g.npts == 2) gjk_simplex_step<2>(g, v0, v1, v2);
     else if (g.npts == 3) gjk_simplex_step<3>(g, v0, v1, v2);
     else gjk_simplex_step<4>(g, v0, v1, v2);
-    // compute_point (GJK.c:851-862), accumulated from 0
-    {
-      const double vv[3] = {v0, v1, v2};
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        double a = 0, b = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < g.npts) a += vv[d] * g.lam[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < g.npts) b += g.c2[i][d] * g.lam[i];
-        g.w1[d] = a;
-        g.w2[d] = b;
-      }
+    // compute_point (GJK.c:851-862), accumulated from 0; one fully unrolled body per simplex size
+    switch (g.npts) {
+      case 1: gjk_witness<1>(g, v0, v1, v2); break;
+      case 2: gjk_witness<2>(g, v0, v1, v2); break;
+      case 3: gjk_witness<3>(g, v0, v1, v2); break;
+      default: gjk_witness<4>(g, v0, v1, v2); break;
     }
     const double d0 = g.w2[0] - g.w1[0], d1 = g.w2[1] - g.w1[1], d2 = g.w2[2] - g.w1[2];
     sqrd = dot3(d0, d1, d2, d0, d1, d2);
@@ -238,11 +246,20 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     // support of the cloud in direction r (support_simple, GJK.c:770-794)
     double best = -1.7976931348623157e308;
     int besti = 0x7fffffff;
-    for (int m = lane; m < n; m += 32) {
-      double qx, qy, qz;
-      cl.get(m, qx, qy, qz);
-      const double v = dot3(qx, qy, qz, r0, r1, r2);
-      if (v > best) { best = v; besti = m; }
+    {
+      const int ns = n < cl.cap ? n : cl.cap;  // shared part, then (rarely) the overflow part, ascending index
+      for (int m = lane; m < ns; m += 32) {
+        const double v = dot3(cl.sx[m], cl.sy[m], cl.sz[m], r0, r1, r2);
+        if (v > best) { best = v; besti = m; }
+      }
+      if (n > cl.cap) {
+        int m = lane;
+        while (m < cl.cap) m += 32;
+        for (; m < n; m += 32) {
+          const double v = dot3(cl.gx[m - cl.cap], cl.gy[m - cl.cap], cl.gz[m - cl.cap], r0, r1, r2);
+          if (v > best) { best = v; besti = m; }
+        }
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -260,9 +277,11 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     if ((first_iteration || sqrd < oldsqrd) && g.npts <= 3) {  // GJK.c:472-487
       double nx, ny, nz;
       cl.get(minp, nx, ny, nz);
-#pragma unroll
-      for (int i = 1; i < 4; ++i)
-        if (i == g.npts) { g.c2[i][0] = nx; g.c2[i][1] = ny; g.c2[i][2] = nz; g.lam[i] = 0.0; }
+      switch (g.npts) {
+        case 1: g.c2[1][0] = nx; g.c2[1][1] = ny; g.c2[1][2] = nz; g.lam[1] = 0.0; break;
+        case 2: g.c2[2][0] = nx; g.c2[2][1] = ny; g.c2[2][2] = nz; g.lam[2] = 0.0; break;
+        default: g.c2[3][0] = nx; g.c2[3][1] = ny; g.c2[3][2] = nz; g.lam[3] = 0.0; break;
+      }
       g.npts++;
       g.use_default = 1;
       oldsqrd = sqrd;

@@ -141,7 +141,7 @@ __host__ __device__ inline size_t pair_warp_doubles(int H, int P) {
 }
 
 // exact reachable test, MAIN:703: pow(a,2)/pow(r,2) + pow(b,2)/pow(r,2) + pow(c,2)/pow(r,2) < 1.0
-__device__ __forceinline__ bool reach_exact(double a, double b, double c, double r2) {
+__device__ __noinline__ bool reach_exact(double a, double b, double c, double r2) {  // out of line: the fast test below almost always decides
   return (a * a) / r2 + (b * b) / r2 + (c * c) / r2 < 1.0;
 }
 // Same decision without the three divisions unless the sum is within 1e-9 of the threshold: the

@@ -74,6 +74,7 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K) {
   return t;
 }
 
+template <bool FUSED_HULL>
 __global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
                                                   size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride) {
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, c
   }
   const int total_pair_warps = n_pair_warps * gridDim.x;
 
-  if (warp >= n_pair_warps) {
+  if (FUSED_HULL && warp >= n_pair_warps) {
     // ------------------------------------------------------------------ hull warp (consumer)
     HullWarp hw;
     char* sm = reinterpret_cast<char*>(smem) +
@@ -235,10 +236,14 @@ __global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, c
           pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
         }
         const unsigned mask = __ballot_sync(LQRO_FULL, pass);
-        if (pass) cl.put(count + __popc(mask & ((1u << lane) - 1u)), q0, q1, q2);
+        if (pass) {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          if (count + 32 <= LQRO_PAIR_CLOUD_CAP) { w.cx[pos] = q0; w.cy[pos] = q1; w.cz[pos] = q2; }  // warp-uniform fast path
+          else cl.put(pos, q0, q1, q2);
+        }
         count += __popc(mask);
         s += 32;
-        while (s >= p.P) { s -= p.P; ++ki; }
+        if (s >= p.P) { s -= p.P; ++ki; while (s >= p.P) { s -= p.P; ++ki; } }
       }
       __syncwarp();
       const int n = count;
