@@ -376,8 +376,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="swarm65536", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-agents", type=int, default=2048, help="agents in the cpu_baseline sample")
-    ap.add_argument("--ref-agents", type=int, default=1024, help="agents per step of --impl reference")
+    ap.add_argument("--cpu-agents", type=int, default=32768, help="agents in the cpu_baseline sample (~10-30 s of CPU work)")
+    ap.add_argument("--ref-agents", type=int, default=8192, help="agents per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

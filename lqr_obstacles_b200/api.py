@@ -46,7 +46,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.SO
+    path = path or os.environ.get("LQRO_LIB") or _build.SO
     if not os.path.exists(path):
         raise LqroError("liblqro.so is missing (%s): build it with `python -m lqr_obstacles_b200.build`; "
                         "there is no CPU fallback" % path)

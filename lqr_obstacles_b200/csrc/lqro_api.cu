@@ -243,7 +243,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     const size_t hullw = hull_warp_smem_bytes(H, P) + 32;
     ctx->fused_hull = ((cfg->flags & LQRO_FLAG_FUSED_HULL) && tbl + 8 * per2 + hullw <= ctx->smem_optin) ? 1 : 0;
     int wp = (int)((ctx->smem_optin - tbl - (ctx->fused_hull ? hullw : 0)) / per2);
-    const int wmax = ctx->fused_hull ? 15 : 16;
+    const int wmax = ctx->fused_hull ? LQRO_PAIR_MAX_WARPS - 1 : LQRO_PAIR_MAX_WARPS;
     if (wp > wmax) wp = wmax;
     if (wp < 1) { g_create_err = "H too large for shared memory"; return bail(LQRO_E_LIMIT); }
     ctx->pair_warps = wp;

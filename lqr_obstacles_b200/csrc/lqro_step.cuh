@@ -28,6 +28,9 @@
 #include "lqro_hull.cuh"
 
 #define LQRO_PAIR_CLOUD_CAP 256
+#ifndef LQRO_PAIR_MAX_WARPS
+#define LQRO_PAIR_MAX_WARPS 16  // x 32 threads x 128 registers = the whole register file of an SM
+#endif
 
 struct PairWarpV2 {
   double *cx, *cy, *cz;  // [LQRO_PAIR_CLOUD_CAP]
@@ -75,7 +78,7 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K) {
 }
 
 template <bool FUSED_HULL>
-__global__ void __launch_bounds__(512, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
                                                   size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride) {
   extern __shared__ double smem[];
