@@ -248,6 +248,7 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
     int besti = 0x7fffffff;
     {
       const int ns = n < cl.cap ? n : cl.cap;  // shared part, then (rarely) the overflow part, ascending index
+#pragma unroll 2
       for (int m = lane; m < ns; m += 32) {
         const double v = dot3(cl.sx[m], cl.sy[m], cl.sz[m], r0, r1, r2);
         if (v > best) { best = v; besti = m; }
