@@ -227,43 +227,26 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       __syncwarp();
       const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
       int count = 0;
-      // candidates of the surviving steps, k-major then sample order (MAIN:1383-1389, 686-687); per step the
-      // warp takes two chunks of 32 samples at once (Transform_k / Translate_k read once, two independent chains)
-      for (int ki = 0; ki < nk; ++ki) {
-        const int k = w.klist[ki];
-        const double* Tk = t.T + 9 * k;
-        const double T0 = Tk[0], T1 = Tk[1], T2 = Tk[2], T3 = Tk[3], T4 = Tk[4], T5 = Tk[5], T6 = Tk[6], T7 = Tk[7], T8 = Tk[8];
-        const double tr0 = w.tr[3 * k], tr1 = w.tr[3 * k + 1], tr2 = w.tr[3 * k + 2];
-        for (int s0 = 0; s0 < p.P; s0 += 64) {
-          const int sa = s0 + lane, sb = s0 + 32 + lane;
-          bool pa = false, pb = false;
-          double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
-          if (sa < p.P) {
-            const double v0 = t.sphx[sa] + tr0, v1 = t.sphy[sa] + tr1, v2 = t.sphz[sa] + tr2;
-            a0 = T0 * v0 + T1 * v1 + T2 * v2;
-            a1 = T3 * v0 + T4 * v1 + T5 * v2;
-            a2 = T6 * v0 + T7 * v1 + T8 * v2;
-            pa = reach_test(a0 - vr0, a1 - vr1, a2 - vr2, p.r2, p.inv_r2);
-          }
-          if (sb < p.P) {
-            const double v0 = t.sphx[sb] + tr0, v1 = t.sphy[sb] + tr1, v2 = t.sphz[sb] + tr2;
-            b0 = T0 * v0 + T1 * v1 + T2 * v2;
-            b1 = T3 * v0 + T4 * v1 + T5 * v2;
-            b2 = T6 * v0 + T7 * v1 + T8 * v2;
-            pb = reach_test(b0 - vr0, b1 - vr1, b2 - vr2, p.r2, p.inv_r2);
-          }
-          const unsigned ma = __ballot_sync(LQRO_FULL, pa), mb = __ballot_sync(LQRO_FULL, pb);
-          const unsigned lt = (1u << lane) - 1u;
-          const int ca = __popc(ma), cb = __popc(mb);
-          if (count + ca + cb <= LQRO_PAIR_CLOUD_CAP) {  // warp-uniform fast path: everything lands in shared memory
-            if (pa) { const int pos = count + __popc(ma & lt); w.cx[pos] = a0; w.cy[pos] = a1; w.cz[pos] = a2; }
-            if (pb) { const int pos = count + ca + __popc(mb & lt); w.cx[pos] = b0; w.cy[pos] = b1; w.cz[pos] = b2; }
-          } else {
-            if (pa) cl.put(count + __popc(ma & lt), a0, a1, a2);
-            if (pb) cl.put(count + ca + __popc(mb & lt), b0, b1, b2);
-          }
-          count += ca + cb;
+      const int tot = nk * p.P;
+      int ki = 0, s = lane;
+      while (s >= p.P) { s -= p.P; ++ki; }
+      for (int b0 = 0; b0 < tot; b0 += 32) {
+        const int m = b0 + lane;
+        bool pass = false;
+        double q0 = 0, q1 = 0, q2 = 0;
+        if (m < tot) {
+          candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
+          pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
         }
+        const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+        if (pass) {
+          const int pos = count + __popc(mask & ((1u << lane) - 1u));
+          if (count + 32 <= LQRO_PAIR_CLOUD_CAP) { w.cx[pos] = q0; w.cy[pos] = q1; w.cz[pos] = q2; }  // warp-uniform fast path
+          else cl.put(pos, q0, q1, q2);
+        }
+        count += __popc(mask);
+        s += 32;
+        if (s >= p.P) { s -= p.P; ++ki; while (s >= p.P) { s -= p.P; ++ki; } }
       }
       __syncwarp();
       const int n = count;
