@@ -138,8 +138,10 @@ int lqro_get_counters(lqro_ctx* ctx, long long* out6);
 int lqro_candidates(lqro_ctx* ctx, const double* xi, const double* xj, double* q);
 /* findReachableObstacle (MAIN:691-706): ascending indices of reachable points; returns count in *n_out. */
 int lqro_reachable(lqro_ctx* ctx, const double* q, int n, const double* xi, const double* xj, int* idx, int* n_out);
-/* run_gjk (MAIN:712-746): squared distance, witness on the cloud, G-test count. */
-int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_hull, int* iterations);
+/* run_gjk (MAIN:712-746): squared distance, the two witness points (on {v_rel} -- a rounded convex combination
+ * of v_rel with itself, GJK.c:851-862 -- and on the cloud), G-test count.  Optional outputs may be NULL. */
+int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_vrel, double* wpt_hull,
+             int* iterations);
 /* qconvex n + Fv (MAIN:762-806) for one cloud given as-is (no rounding applied here): facets in qhull
  * order, planes nf*4, verts nf*3 (first vertex = apex).  *nf_io: in capacity, out count. */
 int lqro_convex_hull(lqro_ctx* ctx, const double* pts, int n, double* planes, int* verts, int* nf_io, int* degenerate);

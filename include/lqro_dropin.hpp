@@ -18,6 +18,7 @@
 //   * lqro::Swarm -- the whole `for i / for j` block of MAIN:1373-1407 for all agents in ONE device
 //     step (lqro_step): this is what replaces the hot loop.
 #pragma once
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -25,6 +26,14 @@
 #include "lqro.h"
 
 namespace lqro {
+
+// The reference's Matrix::operator[] const returns by value (MAT:58-61), so matrices are copied out element-wise.
+template <class M>
+inline std::vector<double> flat(const M& m, int n) {
+  std::vector<double> v(n);
+  for (int i = 0; i < n; ++i) v[i] = m[i];
+  return v;
+}
 
 inline void check(int rc, lqro_ctx* ctx, const char* what) {
   if (rc != LQRO_OK) {
@@ -66,7 +75,7 @@ inline lqro_ctx* ensure_ctx() {
 template <class M16x16, class M16x4, class M4x16, class M4x3>
 inline void setDynamics(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E) {
   lqro_ctx* ctx = ensure_ctx();
-  check(lqro_set_dynamics(ctx, &A[0], &B[0], &L[0], &E[0]), ctx, "lqro_set_dynamics");
+  check(lqro_set_dynamics(ctx, flat(A, 256).data(), flat(B, 64).data(), flat(L, 64).data(), flat(E, 12).data()), ctx, "lqro_set_dynamics");
 }
 
 // ---- MAIN:490-544 controlMatrices, Riccati part (A, B already linearised/discretised by the caller:
@@ -75,7 +84,12 @@ template <class M16x16, class M16x4, class M4x16, class M4x3, class M3x16, class
 inline void controlMatricesRiccati(const M16x16& A, const M16x4& B, double qv, double qp, double r, M4x16& L, M4x3& E, M3x16& Lh,
                                    M3x3& Eh) {
   lqro_ctx* ctx = ensure_ctx();
-  check(lqro_solve_gains(ctx, 1, &A[0], &B[0], qv, qp, r, 300, &L[0], &E[0], &Lh[0], &Eh[0]), ctx, "lqro_solve_gains");
+  double l[64], e[12], lh[48], eh[9];
+  check(lqro_solve_gains(ctx, 1, flat(A, 256).data(), flat(B, 64).data(), qv, qp, r, 300, l, e, lh, eh), ctx, "lqro_solve_gains");
+  for (int i = 0; i < 64; ++i) L[i] = l[i];
+  for (int i = 0; i < 12; ++i) E[i] = e[i];
+  for (int i = 0; i < 48; ++i) Lh[i] = lh[i];
+  for (int i = 0; i < 9; ++i) Eh[i] = eh[i];
 }
 
 // ---- MAIN:665-680 createSpheres(std::vector<Matrix<3,1>>& points): appends NUM_POINTS samples
@@ -115,7 +129,7 @@ inline void createObstacleAll(std::vector<V3d>& ellipsoids, const State& xInit1,
 #endif
   const int n = cfg.horizon * cfg.n_samples;
   std::vector<double> q(3 * (size_t)n);
-  check(lqro_candidates(ctx, &xInit1[0], &xInit2[0], q.data()), ctx, "lqro_candidates");
+  check(lqro_candidates(ctx, flat(xInit1, 16).data(), flat(xInit2, 16).data(), q.data()), ctx, "lqro_candidates");
   for (int i = 0; i < n; ++i) {
     V3d p;
     p[0] = q[3 * i]; p[1] = q[3 * i + 1]; p[2] = q[3 * i + 2];
@@ -133,7 +147,7 @@ inline void findReachableObstacle(const std::vector<V3d>& ellipsoids, std::vecto
   for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) q[3 * i + k] = ellipsoids[i][k];
   std::vector<int> idx(n > 0 ? n : 1);
   int cnt = 0;
-  check(lqro_reachable(ctx, q.data(), n, &x0[0], &x1[0], idx.data(), &cnt), ctx, "lqro_reachable");
+  check(lqro_reachable(ctx, q.data(), n, flat(x0, 16).data(), flat(x1, 16).data(), idx.data(), &cnt), ctx, "lqro_reachable");
   for (int i = 0; i < cnt; ++i) reachablePoints.push_back(ellipsoids[idx[i]]);
 }
 
@@ -145,11 +159,10 @@ inline void run_gjk(const State& x0, const State& x1, const std::vector<V3d>& re
   std::vector<double> q(3 * (size_t)n);
   for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) q[3 * i + k] = reachablePoints[i][k];
   const double vrel[3] = {x0[3] - x1[3], x0[4] - x1[4], x0[5] - x1[5]};
-  double sq = 0, w[3];
-  check(lqro_gjk(ctx, vrel, q.data(), n, &sq, w, nullptr), ctx, "lqro_gjk");
-  distance = std::sqrt(sq);
-  // witness on {v_rel} is v_rel itself
-  normal[0] = (vrel[0] - w[0]) / distance; normal[1] = (vrel[1] - w[1]) / distance; normal[2] = (vrel[2] - w[2]) / distance;
+  double sq = 0, w[3], wv[3];
+  check(lqro_gjk(ctx, vrel, q.data(), n, &sq, wv, w, nullptr), ctx, "lqro_gjk");
+  distance = std::sqrt(sq);                                   // MAIN:741
+  normal[0] = (wv[0] - w[0]) / distance; normal[1] = (wv[1] - w[1]) / distance; normal[2] = (wv[2] - w[2]) / distance;  // MAIN:743-745
 }
 
 // ---- MAIN:749-758 pointInHull
@@ -235,7 +248,7 @@ class Swarm {
 
   template <class M16x16, class M16x4, class M4x16, class M4x3>
   void setDynamics(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E) {
-    check(lqro_set_dynamics(ctx_, &A[0], &B[0], &L[0], &E[0]), ctx_, "lqro_set_dynamics");
+    check(lqro_set_dynamics(ctx_, flat(A, 256).data(), flat(B, 64).data(), flat(L, 64).data(), flat(E, 12).data()), ctx_, "lqro_set_dynamics");
   }
   void setNeighbors(const std::vector<int>& nbr) { nbr_ = nbr; }
 

@@ -70,7 +70,7 @@ def load_library(path=None):
     lib.lqro_get_counters.argtypes = [c_void_p, c_void_p]
     lib.lqro_candidates.argtypes = [c_void_p] * 4
     lib.lqro_reachable.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
-    lib.lqro_gjk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    lib.lqro_gjk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lqro_convex_hull.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lqro_hull_escape.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lqro_new_velocity.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -225,9 +225,10 @@ class Lqro:
     def run_gjk(self, vrel, pts):
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         sq, it = c_double(), c_int()
-        w = np.zeros(3)
+        w, w1 = np.zeros(3), np.zeros(3)
         self._ck(self.lib.lqro_gjk(self.h, _p(np.ascontiguousarray(vrel, dtype=np.float64)), _p(pts), len(pts), ctypes.byref(sq),
-                                   _p(w), ctypes.byref(it)))
+                                   _p(w1), _p(w), ctypes.byref(it)))
+        self.last_gjk_witness_vrel = w1
         return sq.value, w, it.value
 
     def convex_hull(self, pts):

@@ -536,7 +536,8 @@ extern "C" int lqro_reachable(lqro_ctx* ctx, const double* q, int n, const doubl
   return LQRO_OK;
 }
 
-extern "C" int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_hull, int* iterations) {
+extern "C" int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, int n, double* sqdist, double* wpt_vrel, double* wpt_hull,
+                        int* iterations) {
   if (!ctx || !vrel || !pts || n < 1 || !sqdist) return fail(ctx, LQRO_E_ARG, "bad argument");
   CU(cudaSetDevice(ctx->cfg.device));
   int rc = ensure_scratch(ctx, sizeof(double) * (16 + 6 * (size_t)n) + 16);
@@ -553,6 +554,7 @@ extern "C" int lqro_gjk(lqro_ctx* ctx, const double* vrel, const double* pts, in
   CU(cudaStreamSynchronize(ctx->stream));
   *sqdist = out[0];
   if (wpt_hull) { wpt_hull[0] = out[1]; wpt_hull[1] = out[2]; wpt_hull[2] = out[3]; }
+  if (wpt_vrel) { wpt_vrel[0] = out[4]; wpt_vrel[1] = out[5]; wpt_vrel[2] = out[6]; }
   if (iterations) *iterations = it;
   return LQRO_OK;
 }

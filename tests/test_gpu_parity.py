@@ -70,6 +70,7 @@ def test_stage_candidates_reachable_gjk(ctx30, ctx20, oracle, golden):
             sq, w2, it = ctx.run_gjk(vrel, q[idx])
             d2, ow1, ow2, st = oracle.gjk(vrel, q[idx])
             assert sq == d2 and np.array_equal(w2, ow2) and it == st[0] == golden["pair_gjk"][c][0]
+            assert np.array_equal(ctx.last_gjk_witness_vrel, ow1)
 
 
 def test_gjk_random_clouds(ctx30, oracle):
