@@ -94,7 +94,7 @@ __global__ void k_round6(const double* __restrict__ in, int n, double* __restric
 // in shared memory next to the tables (fast path); a hull that needs more facets than the shared pool
 // holds is re-run on the full-size pool in global memory (same code, other pointers).
 typedef short hidx;
-struct HFacet {           // 80 bytes
+struct HFacet {           // 88 bytes
   double n[3], off;
   double furthestdist;
   hidx v[3];              // vertex ids, decreasing
@@ -104,7 +104,7 @@ struct HFacet {           // 80 bytes
   hidx tag;               // scratch: BFS visit id (negative) / cone-local index
   hidx replace;
   hidx ocount;            // points in the outside list
-  unsigned char toporient, visible, isnew, pad;
+  hidx toporient, visible, isnew, pad;   // shorts, not chars: a char store would alias every other access
 };
 
 struct HullWs {
@@ -114,6 +114,8 @@ struct HullWs {
   hidx *pnext, *pbest, *plist, *pstart, *vpoint;  // [cap_pts + 8]
   HFacet* F;              // [cap_f]; F[0] is the list sentinel
   hidx *order, *newf, *vis, *freel;  // [cap_f], newf [LQRO_HULL_MAXNEW]
+  int* vown;              // [cap_pts + 8] ridge matching: cone facet that last touched vertex id v (-1 = none)
+  int* claim;             // [cap_f] horizon search: first (facet,k) slot that reached a facet in this insertion
   int cap_pts, cap_f;
 };
 
@@ -126,6 +128,7 @@ __host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   b += hull_align16(sizeof(hidx) * 5 * ((size_t)cap_pts + 8));          // pnext pbest plist pstart vpoint
   b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + LQRO_HULL_MAXNEW));  // order vis freel newf
   b += hull_align16(3 * sizeof(double) * (size_t)cap_pts);              // hx hy hz (hull input coordinates)
+  b += hull_align16(sizeof(int) * ((size_t)cap_pts + 8 + (size_t)cap_f));   // vown, claim
   return b;
 }
 __host__ __device__ inline int hull_full_facets(int cap_pts) { return 2 * cap_pts + 64; }
@@ -149,6 +152,9 @@ __device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_
   base += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + LQRO_HULL_MAXNEW));
   double* d = reinterpret_cast<double*>(base);
   w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
+  base += hull_align16(3 * sizeof(double) * (size_t)cap_pts);
+  w.vown = reinterpret_cast<int*>(base);
+  w.claim = w.vown + cap_pts + 8;
 }
 __device__ __forceinline__ void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {  // the un-rounded cloud
   double* d = reinterpret_cast<double*>(gbase);
@@ -386,6 +392,8 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
   }
   __syncwarp();
   if (c.fail) return;
+  for (int q = lane; q < n + 8; q += 32) w.vown[q] = -1;
+  for (int q = lane; q < w.cap_f; q += 32) w.claim[q] = 0x7fffffff;
   // ---- qh_maxmin: first index attaining the max / min of each coordinate
   double mxv[3], mnv[3];
   int mxi[3], mni[3];
@@ -594,11 +602,18 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
         for (int b0 = wave * 3; b0 < wend * 3; b0 += 32) {
           const int idx = b0 + lane;
           const bool valid = idx < wend * 3;
-          int nb = -1 - lane;
-          if (valid) nb = w.F[w.vis[idx / 3]].nb[idx % 3];
-          const unsigned peers = __match_any_sync(LQRO_FULL, nb);
-          bool test = valid && (lane == __ffs(peers) - 1);
-          if (test) test = w.F[nb].tag != vid;
+          int nb = 0;
+          bool test = false;
+          // a facet is tested once, by the first (facet, k) slot that reaches it: claim words only ever
+          // decrease (key = insertions left << 8 | slot-in-chunk), so no reset is needed between insertions
+          const int key = ((0x7fff00 - (c.ninserted << 8))) | lane;
+          if (valid) {
+            nb = w.F[w.vis[idx / 3]].nb[idx % 3];
+            if (w.F[nb].tag != vid) atomicMin(&w.claim[nb], key);
+          }
+          __syncwarp();
+          if (valid && w.F[nb].tag != vid) test = (w.claim[nb] == key);
+          __syncwarp();
           bool isvis = false;
           if (test) {
             HFacet& NB = w.F[nb];
@@ -700,20 +715,44 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
     for (int q = lane; q < nnew; q += 32) hull_setplane(w, w.newf[q]);
     __syncwarp();
     int deg = 0;
-    for (int q = lane; q < nnew; q += 32) {
-      HFacet& fa = w.F[w.newf[q]];
-      if (!(hdist(fa, c.interior[0], c.interior[1], c.interior[2]) < 0)) deg = 1;
-      for (int s = 1; s <= 2; ++s) {
-        const int wv = fa.v[3 - s];  // the neighbour opposite v[s] shares the ridge {apex, v[3-s]}
-        int found = -1;
-        for (int b = 0; b < nnew; ++b) {
-          if (b == q) continue;
-          const HFacet& fb = w.F[w.newf[b]];
-          if (fb.v[1] == wv || fb.v[2] == wv) { found = w.newf[b]; break; }
+    // qh_matchnewfacets: the cone facets {apex, a, b} meet along the ridges {apex, w}; every ridge vertex w lies
+    // on exactly two of them.  The second facet to reach vown[w] links both (the neighbour opposite v[1] shares
+    // {apex, v[2]} and vice versa).  sharp test of qh_sharpnewfacets folded in (orthant of the normals).
+    {
+      int q0s = 0;
+      if (nnew > 0) { const HFacet& f0 = w.F[w.newf[0]]; q0s = (f0.n[0] > 0 ? 1 : 0) | (f0.n[1] > 0 ? 2 : 0) | (f0.n[2] > 0 ? 4 : 0); }
+      int sharp = 0;
+      for (int q0 = 0; q0 < nnew; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < nnew) {
+          const int f = w.newf[q];
+          HFacet& fa = w.F[f];
+          if (!(hdist(fa, c.interior[0], c.interior[1], c.interior[2]) < 0)) deg = 1;
+          const int sg = (fa.n[0] > 0 ? 1 : 0) | (fa.n[1] > 0 ? 2 : 0) | (fa.n[2] > 0 ? 4 : 0);
+          if (sg != q0s) sharp = 1;
+#pragma unroll
+          for (int s = 1; s <= 2; ++s) {
+            const int wv = fa.v[s];
+            const int prev = atomicExch(&w.vown[wv], f);
+            if (prev >= 0) {
+              fa.nb[3 - s] = (hidx)prev;                       // opposite the OTHER ridge vertex
+              HFacet& fp = w.F[prev];
+              if (fp.v[1] == wv) fp.nb[2] = (hidx)f; else fp.nb[1] = (hidx)f;
+            }
+          }
         }
-        if (found < 0) deg = 2;
-        fa.nb[s] = found;
       }
+      __syncwarp();
+      for (int q0 = 0; q0 < nnew; q0 += 32) {   // reset the scratch, check every ridge found its partner
+        const int q = q0 + lane;
+        if (q < nnew) {
+          HFacet& fa = w.F[w.newf[q]];
+          w.vown[fa.v[1]] = -1; w.vown[fa.v[2]] = -1;
+          if (fa.nb[1] < 0 || fa.nb[2] < 0) deg = 2;
+        }
+      }
+      sharp = __any_sync(LQRO_FULL, sharp);
+      if (lane == 0) c.sharp = sharp;
     }
     deg = __reduce_max_sync(LQRO_FULL, deg);
     __syncwarp();
@@ -721,16 +760,6 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
     if (lane == 0) {
       if (deg == 1) c.degenerate = 1;
       if (deg == 2) c.fail = 3;
-      // qh_sharpnewfacets
-      c.sharp = 0;
-      if (nnew > 0) {
-        const HFacet& f0 = w.F[w.newf[0]];
-        const bool q0 = f0.n[0] > 0, q1 = f0.n[1] > 0, q2 = f0.n[2] > 0;
-        for (int q = 1; q < nnew && !c.sharp; ++q) {
-          const HFacet& f = w.F[w.newf[q]];
-          if (q0 != (f.n[0] > 0) || q1 != (f.n[1] > 0) || q2 != (f.n[2] > 0)) c.sharp = 1;
-        }
-      }
       c.trigger_pos = 0x7fffffff;
     }
     __syncwarp();
@@ -866,14 +895,19 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
     if (lane == 0) { const long long tn = clock64(); c.prof[7] += tn - tprof; tprof = tn; }
     if (lane == 0) {
       // qh_deletevisible + qh_resetlists
-      for (int vi = 0; vi < c.nvis; ++vi) {
-        const int vf = w.vis[vi];
-        hl_remove(w, c, vf);
-        w.F[vf].visible = 0; w.F[vf].isnew = 0; w.F[vf].tag = 0;
-        w.freel[c.nfree++] = vf;
-      }
-      for (int q = 0; q < c.nnew; ++q) { w.F[w.newf[q]].isnew = 0; w.F[w.newf[q]].tag = 0; }
+      for (int vi = 0; vi < c.nvis; ++vi) hl_remove(w, c, w.vis[vi]);
       c.newfacet_list = -1;
+    }
+    {
+      const int nv = c.nvis, nf0 = c.nfree;
+      for (int vi = lane; vi < nv; vi += 32) {
+        const int vf = w.vis[vi];
+        w.F[vf].visible = 0; w.F[vf].isnew = 0; w.F[vf].tag = 0;
+        w.freel[nf0 + vi] = (hidx)vf;
+      }
+      for (int q = lane; q < nnew; q += 32) { w.F[w.newf[q]].isnew = 0; w.F[w.newf[q]].tag = 0; }
+      __syncwarp();
+      if (lane == 0) c.nfree = nf0 + nv;
     }
     __syncwarp();
     if (lane == 0) { const long long tn = clock64(); c.prof[8] += tn - tprof; tprof = tn; }
