@@ -264,37 +264,27 @@ __device__ __forceinline__ double hull_detsimplex(const HullWs& w, const HullCtl
   return det;
 }
 
-// The point-location routines are kept out of line (the hull loop is latency bound on one warp: its code
-// must stay small enough for the instruction cache); they get what they need by value.
-struct HullSearch {
-  const HFacet* F;
-  const hidx* newf;
-  int nnew;
-  double MINoutside, DISTround, distoutside, searchdist;
-};
-
-// qh_findbesthorizon restricted to what can change a non-degenerate outcome: hill-climb over the
-// neighbours (new or old) of the best facet while one is strictly better (band = SEARCHdist).
-__device__ __noinline__ int hull_findbesthorizon(const HullSearch w, double x, double y, double z, int start, double* bestdist,
-                                           int* degenerate) {
+// qh_findbesthorizon restricted to what can change a non-degenerate outcome: flood over the neighbours (new or
+// old) of the best facet that are within SEARCHdist of it, keeping the best.  General (rare) case, out of line.
+__device__ __noinline__ int hull_horizon_flood(const HFacet* F, double searchdist, double x, double y, double z, int start,
+                                               double* bestdist, int* degenerate) {
   int seen[24];
   int nseen = 0, best = start;
   int stack[24];
   int nstack = 0;
-  const double searchdist = w.searchdist;
   double minsearch = *bestdist - searchdist;
   seen[nseen++] = start;
   int facet = start;
   while (true) {
-    const HFacet& F = w.F[facet];
+    const HFacet& Fc = F[facet];
     int nextfacet = -1;
     for (int k = 0; k < 3; ++k) {
-      const int nb = F.nb[k];
+      const int nb = Fc.nb[k];
       bool was = false;
       for (int q = 0; q < nseen; ++q) if (seen[q] == nb) was = true;
       if (was) continue;
       if (nseen < 24) seen[nseen++] = nb; else { *degenerate = 1; return best; }
-      const double d = hdist(w.F[nb], x, y, z);
+      const double d = hdist(F[nb], x, y, z);
       if (d > *bestdist) {
         best = nb;
         if (d > *bestdist + searchdist) nstack = 0;
@@ -311,71 +301,15 @@ __device__ __noinline__ int hull_findbesthorizon(const HullSearch w, double x, d
   }
   return best;
 }
-
-// qh_findbestnew: exhaustive over the cone facets (list order == newf[] order), cyclically from `start`
-__device__ __noinline__ int hull_findbestnew(const HullSearch w, double x, double y, double z, int start, double* dist,
-                                       bool* isoutside, int* degenerate) {
-  double bestdist = -8.9884656743115785e307;
-  int best = -1;
-  const double distoutside = w.distoutside;
-  const int m = w.nnew;
-  const int s0 = w.F[start].isnew ? w.F[start].tag : 0;
-  for (int q = 0; q < m; ++q) {
-    int idx = s0 + q; if (idx >= m) idx -= m;
-    const int f = w.newf[idx];
-    const double d = hdist(w.F[f], x, y, z);
-    if (d > bestdist) {
-      best = f;
-      if (d >= distoutside) { *dist = d; *isoutside = true; return best; }
-      bestdist = d;
-    }
-  }
-  best = hull_findbesthorizon(w, x, y, z, best >= 0 ? best : start, &bestdist, degenerate);
-  *dist = bestdist;
-  *isoutside = !(bestdist < w.MINoutside);
-  return best;
-}
-
-// qh_findbest(point, start, !bestoutside, isnewfacets): directed walk over the cone facets.
-// trigger: the walk ended below -DISTround (the caller applies qhull's sharp-cone rule).
-__device__ __noinline__ int hull_findbest_walk(const HullSearch w, double x, double y, double z, int start, double* dist,
-                                         bool* isoutside, bool* trigger, int* degenerate) {
-  unsigned long long vm[LQRO_HULL_MAXNEW / 64];
-#pragma unroll
-  for (int q = 0; q < LQRO_HULL_MAXNEW / 64; ++q) vm[q] = 0ull;
-  *trigger = false;
-  *isoutside = true;
-  double d = hdist(w.F[start], x, y, z);
-  if (d >= w.MINoutside) { *dist = d; return start; }
-  double bestdist = d;
-  int best = start;
-  { const int t = w.F[start].tag; vm[t >> 6] |= 1ull << (t & 63); }
-  int facet = start;
-  while (facet >= 0) {
-    const HFacet& F = w.F[facet];
-    int nextf = -1;
-    for (int k = 0; k < 3; ++k) {
-      const int nb = F.nb[k];
-      const HFacet& NB = w.F[nb];
-      if (!NB.isnew) continue;
-      const int t = NB.tag;
-      if (vm[t >> 6] & (1ull << (t & 63))) continue;
-      vm[t >> 6] |= 1ull << (t & 63);
-      d = hdist(NB, x, y, z);
-      if (d > bestdist) {
-        if (d >= w.MINoutside) { *dist = d; return nb; }
-        best = nb; bestdist = d; nextf = nb;
-        break;
-      }
-    }
-    facet = nextf;
-  }
-  *dist = bestdist;
-  if (bestdist < -w.DISTround) { *trigger = true; return best; }  // caller decides (sharp / not sharp)
-  best = hull_findbesthorizon(w, x, y, z, best, &bestdist, degenerate);
-  *dist = bestdist;
-  *isoutside = !(bestdist < w.MINoutside);
-  return best;
+// Common case first: if none of the three neighbours of `start` comes within SEARCHdist of the current best,
+// the flood visits nothing else and the answer is `start`.
+__device__ __forceinline__ int hull_findbesthorizon(const HFacet* F, double searchdist, double x, double y, double z, int start,
+                                                    double* bestdist, int* degenerate) {
+  const HFacet& Fs = F[start];
+  const double minsearch = *bestdist - searchdist;
+  const double d0 = hdist(F[Fs.nb[0]], x, y, z), d1 = hdist(F[Fs.nb[1]], x, y, z), d2 = hdist(F[Fs.nb[2]], x, y, z);
+  if (d0 < minsearch && d1 < minsearch && d2 < minsearch) return start;
+  return hull_horizon_flood(F, searchdist, x, y, z, start, bestdist, degenerate);
 }
 
 // Build the hull of the n points in w.hx/hy/hz.  On return (all lanes): c.fail / c.degenerate set,
@@ -795,47 +729,95 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
     if (c.fail) break;
     const int nl = c.nlist;
     if (nl > 0 && nnew > 0) {
-      // pass 2 (parallel): directed walk of every point.  w.pnext[p] is free while p is off every
-      // list: it carries the "walk ended below -DISTround" mark.
+      // pass 2 (parallel): qh_findbest(point, start, !bestoutside, isnewfacets) = directed walk over the cone
+      // facets from the start facet.  Outcome per point, kept in pbest/pdist and a state in pnext (free while the
+      // point is off every list): 0 = outside facet found, 1 = walk ended in [-DISTround, MINoutside): owes the
+      // horizon test, 2 = walk ended below -DISTround (qhull then looks at the cone: sharp -> exhaustive search).
       int mytrig = 0x7fffffff, ldeg = 0;
-      HullSearch hs;
-      hs.F = w.F; hs.newf = w.newf; hs.nnew = nnew; hs.MINoutside = c.MINoutside; hs.DISTround = c.DISTround;
-      hs.distoutside = hull_distoutside(c); hs.searchdist = hull_searchdist(c);
+      const double MINout = c.MINoutside, DISTr = c.DISTround, distoutside = hull_distoutside(c), searchdist = hull_searchdist(c);
       for (int q = lane; q < nl; q += 32) {
         const int p = w.plist[q];
-        double d; bool outside, trig;
-        const int best = hull_findbest_walk(hs, w.hx[p], w.hy[p], w.hz[p], w.pstart[q], &d, &outside, &trig, &ldeg);
-        if (trig) outside = false;
-        w.pbest[q] = outside ? best : -1 - best;  // negative: not (yet) outside
-        w.pdist[q] = d;
-        w.pnext[p] = trig ? 1 : 0;
-        if (trig && q < mytrig) mytrig = q;
+        const double x = w.hx[p], y = w.hy[p], z = w.hz[p];
+        int start = w.pstart[q];
+        unsigned long long vm0 = 0ull, vm1 = 0ull, vm2 = 0ull, vm3 = 0ull;  // visited cone facets (<= 256)
+        double bestdist = hdist(w.F[start], x, y, z);
+        int best = start, state = 0;
+        if (!(bestdist >= MINout)) {
+          { const int t = w.F[start].tag; const unsigned long long bit = 1ull << (t & 63);
+            if (t < 64) vm0 |= bit; else if (t < 128) vm1 |= bit; else if (t < 192) vm2 |= bit; else vm3 |= bit; }
+          int facet = start;
+          state = 1;
+          while (facet >= 0) {
+            const HFacet& Fc = w.F[facet];
+            int nextf = -1;
+            for (int k = 0; k < 3; ++k) {
+              const int nb = Fc.nb[k];
+              const HFacet& NB = w.F[nb];
+              if (!NB.isnew) continue;
+              const int t = NB.tag;
+              const unsigned long long bit = 1ull << (t & 63);
+              const unsigned long long cur = (t < 64) ? vm0 : (t < 128) ? vm1 : (t < 192) ? vm2 : vm3;
+              if (cur & bit) continue;
+              if (t < 64) vm0 |= bit; else if (t < 128) vm1 |= bit; else if (t < 192) vm2 |= bit; else vm3 |= bit;
+              const double d = hdist(NB, x, y, z);
+              if (d > bestdist) {
+                best = nb; bestdist = d;
+                if (d >= MINout) { state = 0; nextf = -1; } else nextf = nb;
+                break;
+              }
+            }
+            facet = nextf;
+          }
+          if (state == 1 && bestdist < -DISTr) state = 2;
+        }
+        w.pbest[q] = (hidx)best;
+        w.pdist[q] = bestdist;
+        w.pnext[p] = (hidx)state;
+        if (state == 2 && q < mytrig) mytrig = q;
       }
       mytrig = (int)__reduce_min_sync(LQRO_FULL, (unsigned)mytrig);
       __syncwarp();
       if (lane == 0) { const long long tn = clock64(); c.prof[5] += tn - tprof; tprof = tn; }
-      // pass 3 (parallel): walks that ended below -DISTround.  Sharp cone: from the first such point on
-      // (processing order) qhull switches to the exhaustive search (qh.findbestnew stays set for the
-      // rest of this partition); otherwise each such walk finishes with its horizon test.
-      if (mytrig != 0x7fffffff) {
-        for (int q = lane; q < nl; q += 32) {
+      // pass 3a: sharp cone -> from the first state-2 point on (processing order) qhull searches exhaustively
+      // (qh_findbestnew: cone facets in list order, cyclically from the start facet; first one at or above
+      // DISToutside wins, else the best) and stays in that mode for the rest of this partition.
+      const bool sharp = c.sharp != 0;
+      if (mytrig != 0x7fffffff && sharp) {
+        for (int q = mytrig + lane; q < nl; q += 32) {
           const int p = w.plist[q];
           const double x = w.hx[p], y = w.hy[p], z = w.hz[p];
-          double d = w.pdist[q]; bool outside;
-          int best;
-          if (c.sharp) {
-            if (q < mytrig) continue;
-            int start = w.pstart[q];
-            if (q == mytrig) start = -1 - w.pbest[q];
-            best = hull_findbestnew(hs, x, y, z, start, &d, &outside, &ldeg);
-          } else {
-            if (!w.pnext[p]) continue;
-            best = hull_findbesthorizon(hs, x, y, z, -1 - w.pbest[q], &d, &ldeg);
-            outside = !(d < c.MINoutside);
+          const int start = (q == mytrig) ? (int)w.pbest[q] : (int)w.pstart[q];
+          const int s0 = w.F[start].isnew ? (int)w.F[start].tag : 0;
+          double bestdist = -8.9884656743115785e307;
+          int best = start, state = 1;
+          int idx = s0;
+          for (int it = 0; it < nnew; ++it) {
+            const int f = w.newf[idx];
+            const double d = hdist(w.F[f], x, y, z);
+            if (d > bestdist) {
+              best = f; bestdist = d;
+              if (d >= distoutside) { state = 0; break; }
+            }
+            if (++idx == nnew) idx = 0;
           }
-          w.pbest[q] = outside ? best : -1 - best;
-          w.pdist[q] = d;
+          w.pbest[q] = (hidx)best;
+          w.pdist[q] = bestdist;
+          w.pnext[p] = (hidx)state;
         }
+        __syncwarp();
+      }
+      // pass 3b: horizon test (qh_findbesthorizon) for every point that is not outside yet
+      for (int q = lane; q < nl; q += 32) {
+        const int p = w.plist[q];
+        int state = w.pnext[p];
+        int best = w.pbest[q];
+        if (state != 0) {
+          double bestdist = w.pdist[q];
+          best = hull_findbesthorizon(w.F, searchdist, w.hx[p], w.hy[p], w.hz[p], best, &bestdist, &ldeg);
+          w.pdist[q] = bestdist;
+          if (bestdist < MINout) best = -1 - best;  // not outside: inside / coplanar, dropped
+        }
+        w.pbest[q] = (hidx)best;
       }
       ldeg = __any_sync(LQRO_FULL, ldeg);
       __syncwarp();
