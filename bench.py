@@ -326,9 +326,26 @@ def run_ours(args):
         pairs_per_launch = NL * K
         pair_s = pair_ms * 1e-3
         achieved_tf = pairs_per_launch * f_alg(H, P) / pair_s / 1e12
+        # DRAM traffic and executed-FP64 counts of k_pairs come from the committed ncu capture of this workload
+        # (profiles/rNN_k_pairs_<workload>_ncu.json, written by tools/ from the .ncu-rep); never measured under ncu here
+        ncu = None
+        import glob
+        caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pairs_%s_ncu.json" % args.workload)))
+        if caps and world == 1:
+            try:
+                ncu = json.load(open(caps[-1]))
+                ncu["file"] = os.path.relpath(caps[-1], ROOT)
+            except Exception:
+                ncu = None
         roofline = {
             "bound": "fp64", "kernel": "k_pairs", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": achieved_tf / fp64_peak, "traffic": None,
+            "frac": achieved_tf / fp64_peak,
+            "traffic": (ncu["traffic_bytes"] if ncu and ncu.get("pairs_per_launch") == pairs_per_launch else None),
+            "algorithmic_bytes_per_launch": pairs_per_launch * b_alg(K),
+            "executed": ({"source": ncu["file"], "fp64_flop_per_launch": ncu["executed_fp64_flop"],
+                          "fp64_pipe_pct": ncu["fp64_pipe_pct"], "issue_active_pct": ncu["issue_active_pct"],
+                          "note": "exact pruning skips horizon steps, so executed flop < algorithmic flop (F_alg counts every step)"}
+                         if ncu else None),
             "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_ms,
             "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak); "
                            "MEASURED_PEAKS.json has no FP64 figure",

@@ -204,8 +204,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMalloc(&ctx->d_planes_c, sizeof(float) * 6 * NP));
   CUC(cudaMalloc(&ctx->d_proj, sizeof(float) * 6 * NP));
   CUC(cudaMalloc(&ctx->d_ctr, sizeof(int) * 16));
-  CUC(cudaMalloc(&ctx->d_prof, sizeof(long long) * 16));
-  CUC(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 16));
+  CUC(cudaMalloc(&ctx->d_prof, sizeof(long long) * 32));
+  CUC(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 32));
   CUC(cudaMemset(ctx->d_ctr, 0, sizeof(int) * 16));
   CUC(cudaMemset(ctx->d_status, 0, sizeof(int) * NP));
   CUC(cudaMemset(ctx->d_nfacets, 0, sizeof(int) * NP));
@@ -380,7 +380,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   PairOutputs po{ctx->d_planes, ctx->d_status, ctx->d_nreach, ctx->d_dist, ctx->d_nfacets};
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
   CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
-  CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 16, st));
+  CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 32, st));
   CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet
   StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   CU(cudaEventRecord(ctx->ev[0], st));
@@ -483,7 +483,11 @@ extern "C" int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16) {
   if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
   CU(cudaSetDevice(ctx->cfg.device));
   CU(cudaStreamSynchronize(ctx->stream));
+#ifdef LQRO_PAIR_PROF  // profiling build: the pair kernel's phase cycles instead
+  CU(cudaMemcpy(out16, ctx->d_prof + 16, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+#else
   CU(cudaMemcpy(out16, ctx->d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+#endif
   return LQRO_OK;
 }
 

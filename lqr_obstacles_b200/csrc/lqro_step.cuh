@@ -77,6 +77,18 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K) {
   return t;
 }
 
+#ifdef LQRO_PAIR_PROF  // per-phase cycle counts of the pair warps (lane 0), profiling builds only
+#define PAIR_PROF_DECL long long pprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ptick = clock64();
+#define PAIR_PROF(q) { const long long tn_ = clock64(); pprof[q] += tn_ - ptick; ptick = tn_; }
+#define PAIR_PROF_COUNT(q, v) { pprof[q] += (v); }
+#define PAIR_PROF_FLUSH if (lane == 0) { for (int q_ = 0; q_ < 8; ++q_) atomicAdd((unsigned long long*)sy.prof + 16 + q_, (unsigned long long)pprof[q_]); }
+#else
+#define PAIR_PROF_DECL
+#define PAIR_PROF(q)
+#define PAIR_PROF_COUNT(q, v)
+#define PAIR_PROF_FLUSH
+#endif
+
 template <bool FUSED_HULL>
 __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
@@ -146,6 +158,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
   const long long total = slot_major_total(p.n_local, p.K);
   const int n3 = 3 * p.H;
   const unsigned long long allsteps = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
+  PAIR_PROF_DECL
   while (true) {
     int batch = 0;
     if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
@@ -195,6 +208,8 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     }
     // ---------------- stage 2: warp = pair
     unsigned act = __ballot_sync(LQRO_FULL, kmask != 0ull);
+    PAIR_PROF(0)
+    PAIR_PROF_COUNT(6, __popc(act))
     while (act) {
       const int src = __ffs(act) - 1;
       act &= act - 1;
@@ -225,6 +240,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         w.tr[3 * k + c] = s;
       }
       __syncwarp();
+      PAIR_PROF(1)
       const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
       int count = 0;
       const int tot = nk * p.P;
@@ -249,7 +265,9 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         if (s >= p.P) { s -= p.P; ++ki; while (s >= p.P) { s -= p.P; ++ki; } }
       }
       __syncwarp();
+      PAIR_PROF(2)
       const int n = count;
+      PAIR_PROF_COUNT(7, n)
       if (n <= 4) {  // "GJK errors with less than 4", MAIN:1393
         if (lane == 0) { out.status[pr] = 0; out.nreach[pr] = n; }
         __syncwarp();
@@ -257,6 +275,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       }
       double gw1[3], gw2[3];
       const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
+      PAIR_PROF(3)
       if (lane == 0) {
         const double distance = sqrt(sq);                             // MAIN:741
         const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
@@ -276,7 +295,9 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         }
       }
       __syncwarp();
+      PAIR_PROF(4)
     }
   }
+  PAIR_PROF_FLUSH
   if (lane == 0) { __threadfence(); atomicAdd(sy.done_warps, 1); }
 }
