@@ -262,11 +262,19 @@ __device__ __forceinline__ double gjk_warp(const double v0, const double v1, con
         }
       }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ov = __shfl_xor_sync(LQRO_FULL, best, off);
-      const int oi = __shfl_xor_sync(LQRO_FULL, besti, off);
-      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    // warp arg-max, lowest index on ties (support_simple keeps the first maximum, GJK.c:779-790): the doubles
+    // are mapped to order-preserving 64-bit keys (-0 folded into +0 first) and reduced with three REDUX
+    // operations (high word, low word among the high-word winners, lowest index among the winners).
+    {
+      const long long bits = __double_as_longlong(best + 0.0);
+      const unsigned long long key = (unsigned long long)bits ^ ((unsigned long long)(bits >> 63) | 0x8000000000000000ull);
+      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      const unsigned mhi = __reduce_max_sync(LQRO_FULL, hi);
+      const unsigned mlo = __reduce_max_sync(LQRO_FULL, hi == mhi ? lo : 0u);
+      const bool win = hi == mhi && lo == mlo;
+      besti = (int)__reduce_min_sync(LQRO_FULL, win ? (unsigned)besti : 0x7fffffffu);
+      const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+      best = __longlong_as_double((long long)((mkey >> 63) ? (mkey ^ 0x8000000000000000ull) : ~mkey));
     }
     const double minus_minv = best;
     const int minp = besti;

@@ -27,7 +27,9 @@
 #include "lqro_pair.cuh"
 #include "lqro_hull.cuh"
 
+#ifndef LQRO_PAIR_CLOUD_CAP
 #define LQRO_PAIR_CLOUD_CAP 256
+#endif
 #ifndef LQRO_PAIR_MAX_WARPS
 #define LQRO_PAIR_MAX_WARPS 16  // x 32 threads x 128 registers = the whole register file of an SM
 #endif
@@ -276,18 +278,24 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       double gw1[3], gw2[3];
       const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
       PAIR_PROF(3)
-      if (lane == 0) {
+      {
         const double distance = sqrt(sq);                             // MAIN:741
         const bool inside = distance < 0.0001 && distance > -0.0001;  // MAIN:752-757
-        out.nreach[pr] = n;
         if (!inside) {
-          const double n0 = (gw1[0] - gw2[0]) / distance;  // MAIN:743-745
-          const double n1 = (gw1[1] - gw2[1]) / distance;
-          const double n2 = (gw1[2] - gw2[2]) / distance;
-          write_plane(out.planes + 6 * (size_t)pr, w.xi + 3, distance, n0, n1, n2, false);
-          out.dist[pr] = distance;
-          out.status[pr] = 1;
-        } else {
+          // lanes 0..2 each finish one component: normal (MAIN:743-745), then createHalfPlanes (MAIN:1085-1098)
+          // after `distance *= 0.5` (MAIN:1401), narrowed to float as Vector3(double,double,double) does
+          if (lane < 3) {
+            const double a = lane == 0 ? gw1[0] : lane == 1 ? gw1[1] : gw1[2];
+            const double b = lane == 0 ? gw2[0] : lane == 1 ? gw2[1] : gw2[2];
+            const double nc = (a - b) / distance;
+            const double md = -1.0 * (distance * 0.5);
+            float* pl = out.planes + 6 * (size_t)pr;
+            pl[lane] = (float)(w.xi[3 + lane] + md * nc);
+            pl[3 + lane] = (float)nc;
+          }
+          if (lane == 3) { out.nreach[pr] = n; out.dist[pr] = distance; out.status[pr] = 1; }
+        } else if (lane == 0) {
+          out.nreach[pr] = n;
           out.status[pr] = 2;  // plane filled in by a hull warp / k_hull
           __threadfence();
           const int slot = atomicAdd(hq.count, 1);

@@ -1,0 +1,10 @@
+import sys, os, numpy as np
+sys.path.insert(0,'/root/repo')
+from lqr_obstacles_b200 import Lqro, swarm
+g=np.load('/root/repo/tests/golden/ref_vectors.npz')
+x,vp=swarm.lattice_swarm((64,32,32)); nb=swarm.knn(x[:,:3],64)
+ctx=Lqro(n_agents=65536,max_neighbors=64,horizon=20); ctx.set_dynamics(g['dyn_A'],g['dyn_B'],g['dyn_L'],g['dyn_E'])
+ms=[]
+for r in range(6):
+    nv=ctx.step(x,vp,nb); ms.append(ctx.last_step_ms()['pairs'])
+print(os.environ.get('LQRO_LIB'), 'pairs ms', min(ms), np.median(ms), 'checksum', float(nv.sum()), ctx.counters()['planes'])
