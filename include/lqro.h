@@ -70,6 +70,9 @@ typedef struct lqro_config {
 } lqro_config;
 
 #define LQRO_FLAG_NO_PRUNE 1   /* evaluate every horizon step of every pair (ablation / parity of the exact pruning) */
+#define LQRO_FLAG_DEVICE_KNN 4 /* lqro_step / lqro_step_sharded called with nbr == NULL rebuild the neighbour table on the
+                                  device from the current positions every step (lqro_knn_device) instead of reusing the
+                                  table uploaded last */
 #define LQRO_FLAG_FUSED_HULL 2 /* one hull warp per pair-kernel CTA consumes the inside-case queue concurrently
                                   (experimental: measured slower than the stand-alone hull kernel) */
 
@@ -154,6 +157,16 @@ int lqro_new_velocity(lqro_ctx* ctx, int batch, int max_planes, const float* pla
                       const double* goal, double* newV);
 /* RVO-form Agent::update (AGENT:176-180), FP32: vel = newVel; pos += vel*dt.  Host pointers, n*3 each. */
 int lqro_agent_update(lqro_ctx* ctx, int n, float* pos, float* vel, const float* newVel, float dt);
+/* Neighbour search (the list RVO's Agent::insertAgentNeighbor builds, AGENT:153-174; the KdTree that feeds it is
+ * not in the reference): for every owned agent the max_neighbors other agents with the smallest squared
+ * distance (dx*dx + dy*dy) + dz*dz, ascending, equal distances to the lower index, -1 = none.  Uniform grid on
+ * the device.  x n_agents*16 (positions = entries 0..2; NULL = the state already resident), nbr n_local*K out.
+ * The table also stays resident as the context's neighbour table. */
+int lqro_knn(lqro_ctx* ctx, const double* x, int* nbr);
+/* Same with device pointers, asynchronous (d_x NULL = resident state, d_nbr NULL = the resident table). */
+int lqro_knn_device(lqro_ctx* ctx, const double* d_x, int* d_nbr, void* stream);
+/* Copies the resident neighbour table (n_local*K) to the host. */
+int lqro_get_neighbors(lqro_ctx* ctx, int* nbr);
 /* printf("%g")/strtod round trip of MAIN:765-767 applied to n doubles on the device. */
 int lqro_round6(lqro_ctx* ctx, const double* in, int n, double* out);
 

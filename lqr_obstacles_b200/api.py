@@ -13,6 +13,7 @@ HULL_TEXT6, HULL_FP64 = 0, 1
 PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE = 0, 1, 2, 0x100
 FLAG_NO_PRUNE = 1
 FLAG_FUSED_HULL = 2
+FLAG_DEVICE_KNN = 4
 
 
 class LqroError(RuntimeError):
@@ -37,7 +38,7 @@ EXPORTS = [
     "lqro_get_counters", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
-    "lqro_debug_hull_cycles",
+    "lqro_debug_hull_cycles", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
 ]
 
 
@@ -262,6 +263,21 @@ class Lqro:
         newVel = np.ascontiguousarray(newVel, dtype=np.float32)
         self._ck(self.lib.lqro_agent_update(self.h, len(pos), _p(pos), _p(vel), _p(newVel), dt))
         return pos, vel
+
+    def knn(self, x=None):
+        """K nearest other agents of every owned agent on the device (AGENT:153-174 ordering); the table stays
+        resident as the context's neighbour table.  x None = the state already on the device."""
+        nbr = np.zeros((self.NL, self.K), dtype=np.int32)
+        self._ck(self.lib.lqro_knn(self.h, _p(x), _p(nbr)))
+        return nbr
+
+    def knn_device(self, d_x=None, d_nbr=None, stream=None):
+        self._ck(self.lib.lqro_knn_device(self.h, _p(d_x), _p(d_nbr), stream))
+
+    def neighbors(self):
+        nbr = np.zeros((self.NL, self.K), dtype=np.int32)
+        self._ck(self.lib.lqro_get_neighbors(self.h, _p(nbr)))
+        return nbr
 
     def round6(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)

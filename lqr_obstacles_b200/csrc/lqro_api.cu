@@ -13,9 +13,11 @@
 #include "../../include/lqro.h"
 #include "lqro_common.cuh"
 #include "lqro_gjk.cuh"
+#include "lqro_knn.cuh"
 #include "lqro_pair.cuh"
 #include "lqro_hull.cuh"
 #include "lqro_step.cuh"
+#include "lqro_knn.cuh"
 #include "lqro_lp.cuh"
 #include "lqro_riccati.cuh"
 
@@ -72,6 +74,12 @@ struct lqro_ctx {
   char* d_hull_ws = nullptr;
   double* d_pair_ovf = nullptr; size_t pair_ovf_stride = 0;
   long long* d_prof = nullptr;
+  // device neighbour search (lqro_knn.cuh), allocated on first use
+  unsigned long long* d_knn_bb = nullptr;
+  KnnGrid* d_knn_grid = nullptr;
+  int *d_knn_cell = nullptr, *d_knn_count = nullptr, *d_knn_start = nullptr, *d_knn_sid = nullptr;
+  double* d_knn_spos = nullptr;
+  int device_knn = 0;
   size_t hull_ws_stride = 0;
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
@@ -143,7 +151,8 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_CG, ctx->d_prn, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
                   ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
-                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf, ctx->d_prof};
+                  ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf, ctx->d_prof,
+                  ctx->d_knn_bb, ctx->d_knn_grid, ctx->d_knn_cell, ctx->d_knn_count, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -173,6 +182,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
   p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
+  ctx->device_knn = (cfg->flags & LQRO_FLAG_DEVICE_KNN) ? 1 : 0;
   p.box[0] = p.box[1] = p.box[2] = 0.0;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) { delete ctx; return fail(nullptr, LQRO_E_CUDA, "cudaGetDeviceProperties failed"); }
@@ -374,6 +384,66 @@ extern "C" int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* sph
   return LQRO_OK;
 }
 
+// ---- neighbour search on the device (AGENT:153-174 ordering) ----------------------------
+static int launch_knn(lqro_ctx* ctx, const double* d_x, int* d_nbr_out, cudaStream_t st) {
+  const LqroParams& p = ctx->prm;
+  if (p.K > 128) return fail(ctx, LQRO_E_LIMIT, "device neighbour search supports K <= 128");
+  if (!ctx->d_knn_bb) {
+    CU(cudaMalloc(&ctx->d_knn_bb, sizeof(unsigned long long) * 6));
+    CU(cudaMalloc(&ctx->d_knn_grid, sizeof(KnnGrid)));
+    CU(cudaMalloc(&ctx->d_knn_cell, sizeof(int) * (size_t)p.N));
+    CU(cudaMalloc(&ctx->d_knn_count, sizeof(int) * LQRO_KNN_MAX_CELLS));
+    CU(cudaMalloc(&ctx->d_knn_start, sizeof(int) * (LQRO_KNN_MAX_CELLS + 1)));
+    CU(cudaMalloc(&ctx->d_knn_sid, sizeof(int) * (size_t)p.N));
+    CU(cudaMalloc(&ctx->d_knn_spos, sizeof(double) * 3 * (size_t)p.N));
+  }
+  CU(cudaMemsetAsync(ctx->d_knn_bb, 0xff, sizeof(unsigned long long) * 3, st));
+  CU(cudaMemsetAsync(ctx->d_knn_bb + 3, 0, sizeof(unsigned long long) * 3, st));
+  CU(cudaMemsetAsync(ctx->d_knn_count, 0, sizeof(int) * LQRO_KNN_MAX_CELLS, st));
+  const int nb = std::min((p.N + 255) / 256, 2 * ctx->sm_count);
+  k_knn_bbox<<<nb, 256, 0, st>>>(d_x, p.N, ctx->d_knn_bb);
+  k_knn_setup<<<1, 32, 0, st>>>(ctx->d_knn_bb, p.N, p.K, ctx->d_knn_grid);
+  k_knn_count<<<nb, 256, 0, st>>>(d_x, p.N, ctx->d_knn_grid, ctx->d_knn_cell, ctx->d_knn_count);
+  k_knn_scan<<<1, 1024, 0, st>>>(ctx->d_knn_grid, ctx->d_knn_count, ctx->d_knn_start);
+  k_knn_scatter<<<nb, 256, 0, st>>>(d_x, p.N, ctx->d_knn_cell, ctx->d_knn_start, ctx->d_knn_count, ctx->d_knn_sid, ctx->d_knn_spos);
+  const int E = p.K <= 32 ? 1 : p.K <= 64 ? 2 : 4;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (32 * E + LQRO_KNN_STAGE) * (sizeof(double) + sizeof(int));
+  const int qb = std::min((p.n_local + wpb - 1) / wpb, 16 * ctx->sm_count);
+  if (E == 1) k_knn_query<1><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
+  else if (E == 2) k_knn_query<2><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
+  else k_knn_query<4><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
+  CU(cudaGetLastError());
+  return LQRO_OK;
+}
+
+extern "C" int lqro_knn_device(lqro_ctx* ctx, const double* d_x, int* d_nbr, void* stream) {
+  if (!ctx) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  return launch_knn(ctx, d_x ? d_x : ctx->d_x, d_nbr ? d_nbr : ctx->d_nbr, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int lqro_knn(lqro_ctx* ctx, const double* x, int* nbr) {
+  if (!ctx || !nbr) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const LqroParams& p = ctx->prm;
+  cudaStream_t st = ctx->stream;
+  if (x) CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
+  int rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(nbr, ctx->d_nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_get_neighbors(lqro_ctx* ctx, int* nbr) {
+  if (!ctx || !nbr) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(nbr, ctx->d_nbr, sizeof(int) * (size_t)ctx->prm.n_local * ctx->prm.K, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
 // ---- the step ----------------------------------------------------------------------------------------
 static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV, cudaStream_t st) {
   const LqroParams& p = ctx->prm;
@@ -421,7 +491,9 @@ extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, co
   CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
   if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
-  int rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
+  int rc = LQRO_OK;
+  if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
+  rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -719,6 +791,7 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
   int rc = lqro_allgather_state(ctx);
   if (rc) return rc;
+  if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));

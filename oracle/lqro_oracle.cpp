@@ -7,8 +7,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <limits>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -667,4 +670,41 @@ extern "C" void lqro_o_step(int N, int K, int H, int P, const double* NF, const 
 
 extern "C" void lqro_o_agent_update(int N, float* pos, float* vel, const float* newVel, float dt) {
   for (int i = 0; i < 3 * N; ++i) { vel[i] = newVel[i]; pos[i] += vel[i] * dt; }
+}
+
+// AGENT:153-174, restated: sorted insertion with a shrinking range
+static void knn_rows(int N, const double* x, int begin, int end, int row0, int K, int* nbr) {
+  std::vector<std::pair<double, int>> nb;
+  for (int i = begin; i < end; ++i) {
+    nb.clear();
+    double rangeSq = std::numeric_limits<double>::infinity();
+    const double* pi = x + (size_t)i * 16;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;                                     // AGENT:155
+      const double* pj = x + (size_t)j * 16;
+      const double d0 = pi[0] - pj[0], d1 = pi[1] - pj[1], d2 = pi[2] - pj[2];
+      const double distSq = d0 * d0 + d1 * d1 + d2 * d2;        // absSq, V3:309-312
+      if (distSq < rangeSq) {                                   // AGENT:158
+        if ((int)nb.size() < K) nb.push_back(std::make_pair(distSq, j));
+        size_t q = nb.size() - 1;
+        while (q != 0 && distSq < nb[q - 1].first) { nb[q] = nb[q - 1]; --q; }
+        nb[q] = std::make_pair(distSq, j);
+        if ((int)nb.size() == K) rangeSq = nb.back().first;     // AGENT:169-171
+      }
+    }
+    int* out = nbr + (size_t)(i - row0) * K;
+    for (int q = 0; q < K; ++q) out[q] = q < (int)nb.size() ? nb[q].second : -1;
+  }
+}
+
+extern "C" void lqro_o_knn(int N, const double* x, int begin, int n_local, int K, int nthreads, int* nbr) {
+  if (K <= 0) return;
+  if (nthreads <= 1) { knn_rows(N, x, begin, begin + n_local, begin, K, nbr); return; }
+  std::vector<std::thread> th;
+  const int per = (n_local + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    const int b = begin + t * per, e = std::min(begin + n_local, b + per);
+    if (b < e) th.emplace_back(knn_rows, N, x, b, e, begin, K, nbr);
+  }
+  for (auto& t : th) t.join();
 }

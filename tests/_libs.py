@@ -160,6 +160,14 @@ class Oracle:
                              lp_radius, fix_facet0, nthreads, P(newV), P(planes), P(status), P(nplanes))
         return newV, planes, status, nplanes
 
+    def knn(self, x, K, begin=0, n_local=None, nthreads=1):
+        """AGENT:153-174 neighbour lists by brute force (lqro_o_knn)"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n_local = len(x) - begin if n_local is None else n_local
+        nbr = np.zeros((n_local, K), dtype=np.int32)
+        self.lib.lqro_o_knn(len(x), P(x), begin, n_local, K, nthreads, P(nbr))
+        return nbr
+
 
 class Reference:
     """Wrapper over oracle/_ref/liblqro_ref.so: the reference's own code (see oracle/ref_harness.cpp).
