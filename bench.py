@@ -307,6 +307,29 @@ def run_ours(args):
     barrier()
     checksum = float(hout.sum())
 
+    # ---- the same call with the neighbour table rebuilt on the device every step (LQRO_FLAG_DEVICE_KNN, nbr = NULL):
+    # informative; the headline e2e keeps the host-provided lists, like the reference arm
+    knn_arm = None
+    if world == 1:
+        from lqr_obstacles_b200.api import FLAG_DEVICE_KNN
+        ctx2 = Lqro(device=local_rank, n_agents=N, max_neighbors=K, horizon=H, n_samples=P, flags=FLAG_DEVICE_KNN)
+        ctx2.set_dynamics(A, B, L, E)
+        ctx2.set_stream(stream.cuda_stream)
+        hout2 = torch.zeros(NL, 3, dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            ctx2.step_sharded(hx.data_ptr(), hv.data_ptr(), None, hout2.data_ptr())
+        stream.synchronize()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            ctx2.step_sharded(hx.data_ptr(), hv.data_ptr(), None, hout2.data_ptr())
+        stream.synchronize()
+        k_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        knn_arm = {"value": N * K / (k_ms * 1e-3), "unit": UNIT, "ms_per_step": k_ms,
+                   "h2d_bytes_per_step": int(x_loc.nbytes + vp_loc.nbytes), "gpu_launches_per_step": 9,
+                   "neighbour_table_identical": bool(np.array_equal(ctx2.neighbors(), nbr_loc)),
+                   "checksum": float(hout2.sum()), "api": "lqro_step_sharded(nbr=NULL) with LQRO_FLAG_DEVICE_KNN"}
+        ctx2.close()
+
     t_dev = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, kern_ms[0]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -374,7 +397,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (x_loc.nbytes + vp_loc.nbytes + nbr_loc.nbytes)),
                     "d2h_bytes_per_step": int(world * NL * 24), "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps,
-                    "api": "lqro_step_sharded (host pinned buffers)", "checksum": checksum},
+                    "api": "lqro_step_sharded (host pinned buffers)", "checksum": checksum, "device_knn": knn_arm},
             "gpu_launches": 3 * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -37,5 +37,22 @@ def build(force=False, verbose=False):
     return SO
 
 
+QCONVEX_SRC = os.path.join(os.path.dirname(HERE), "tools", "qconvex", "qconvex_gpu.cpp")
+QCONVEX_EXE = os.path.join(os.path.dirname(HERE), "tools", "qconvex", "qconvex")
+
+
+def build_qconvex(force=False):
+    """tools/qconvex/qconvex: the `qconvex` executable the unmodified reference spawns (MAIN:769-770), backed by
+    the GPU hull through the C ABI.  Host-only C++ (g++), linked against liblqro.so with an rpath."""
+    so = build()
+    if not force and os.path.exists(QCONVEX_EXE) and os.path.getmtime(QCONVEX_EXE) > max(os.path.getmtime(QCONVEX_SRC), os.path.getmtime(so)):
+        return QCONVEX_EXE
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-o", QCONVEX_EXE, QCONVEX_SRC, "-L" + HERE, "-llqro",
+                           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../lqr_obstacles_b200"])
+    return QCONVEX_EXE
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))
+    print(build_qconvex(force=True))

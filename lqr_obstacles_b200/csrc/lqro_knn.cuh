@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) k_knn_query(const double* __restrict__ x,
     KnnTop<E> top;
 #pragma unroll
     for (int j = 0; j < E; ++j) { top.d[j] = INF; top.i[j] = 0x7fffffff; }
-    int nst = 0;
+    int nst = 0, seen = 0;  // seen: agents in the cells searched so far (self included)
     // K-th best so far (entry K-1 of the sorted top), warp-uniform
     double kd = INF;
     int ki = 0x7fffffff;
@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(128) k_knn_query(const double* __restrict__ x,
             if (face || r == 0) { c0 = max(xa, 0); c1 = min(xb, g.dim[0] - 1); }
             else { c0 = c1 = part == 0 ? xa : xb; if (c0 < 0 || c0 >= g.dim[0]) continue; }
             const int s0 = start[rowbase + c0], s1 = start[rowbase + c1 + 1];
+            seen += s1 - s0;
             for (int b0 = s0; b0 < s1; b0 += 32) {
               const int q = b0 + lane;
               bool keep = false;
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(128) k_knn_query(const double* __restrict__ x,
         }
       }
       // shell r done: merge what is staged, then test whether unsearched cells can still matter
+      if (seen <= K && r < rmax) continue;  // fewer than K others so far: the test below cannot succeed
       while (nst > 0) knn_flush<E>(top, st, nst, lane);
       {
         const int ke = K - 1;

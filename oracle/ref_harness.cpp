@@ -71,8 +71,14 @@ extern "C" int ref_last_hull(int* nfacets, int* npoints, double* planes, int* ve
 extern "C" void ref_counters(int* hull_calls, int* system_calls) { *hull_calls = g_hull_calls; *system_calls = g_system_calls; }
 
 // Parses:  qconvex <n|Fv> TO "<out>" < "<in>"   and performs it with the hull callback.
+// passthrough: hand the command line to the real shell (a `qconvex` on PATH does the work, e.g.
+// tools/qconvex/qconvex = the GPU hull behind qhull's file formats) instead of the in-process stand-in
+static int g_system_passthrough = 0;
+extern "C" void ref_set_system_passthrough(int on) { g_system_passthrough = on; }
+#undef system
 extern "C" int lqr_ref_system(const char* cmd) {
   ++g_system_calls;
+  if (g_system_passthrough) { ++g_hull_calls; return ::system(cmd); }
   char opt[16], outp[256], inp[256];
   if (sscanf(cmd, "qconvex %15s TO \"%255[^\"]\" < \"%255[^\"]\"", opt, outp, inp) != 3) return -1;
   FILE* fi = fopen(inp, "r");
