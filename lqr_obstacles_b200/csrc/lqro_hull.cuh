@@ -841,15 +841,28 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
           const int mine = t0 + lane;
           int oh = -1, ol = -1, op = -1, cnt = 0;
           double fd = 0.0;
-          for (int q = 0; q < nl; ++q) {
-            const int code = w.pstart[q];
-            if (code == mine) {
-              const int pt = w.plist[q];
-              const double d = w.pdist[q];
-              ++cnt;
-              if (ol < 0) { oh = ol = pt; op = -1; w.pnext[pt] = -1; fd = d; }
-              else if (fd < d) { w.pnext[ol] = (hidx)pt; op = ol; ol = pt; w.pnext[pt] = -1; fd = d; }
-              else { if (op >= 0) w.pnext[op] = (hidx)pt; else oh = pt; w.pnext[pt] = (hidx)ol; op = pt; }  // qh_setappend2ndlast
+          for (int c0 = 0; c0 < nl; c0 += 32) {
+            // lane q holds point c0+q of the processing order; every owner collects the lanes that target its
+            // facet (ascending lane = processing order) and replays exactly those appends
+            const int q = c0 + lane;
+            int code_l = -9, pt_l = 0;
+            double d_l = 0.0;
+            if (q < nl) { code_l = w.pstart[q]; pt_l = w.plist[q]; d_l = w.pdist[q]; }
+            const int cn = nl - c0 < 32 ? nl - c0 : 32;
+            unsigned m = 0u;
+            for (int j = 0; j < cn; ++j) m |= (unsigned)(__shfl_sync(LQRO_FULL, code_l, j) == mine) << j;
+            const int steps = (int)__reduce_max_sync(LQRO_FULL, (unsigned)__popc(m));
+            for (int it = 0; it < steps; ++it) {
+              const int src = m ? __ffs(m) - 1 : 0;
+              const int pt = __shfl_sync(LQRO_FULL, pt_l, src);
+              const double d = __shfl_sync(LQRO_FULL, d_l, src);
+              if (m) {
+                m &= m - 1;
+                ++cnt;
+                if (ol < 0) { oh = ol = pt; op = -1; w.pnext[pt] = -1; fd = d; }
+                else if (fd < d) { w.pnext[ol] = (hidx)pt; op = ol; ol = pt; w.pnext[pt] = -1; fd = d; }
+                else { if (op >= 0) w.pnext[op] = (hidx)pt; else oh = pt; w.pnext[pt] = (hidx)ol; op = pt; }  // qh_setappend2ndlast
+              }
             }
           }
           if (mine < nnew && cnt > 0) {
@@ -858,6 +871,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
           }
         }
         __syncwarp();
+        if (lane == 0) { const long long tn = clock64(); c.prof[7] += tn - tprof; tprof = tn; }
         if (lane == 0) {
           if (pdeg) c.degenerate = 1;
           if (anyold) {
@@ -874,7 +888,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n) {
       }
       __syncwarp();
     }
-    if (lane == 0) { const long long tn = clock64(); c.prof[7] += tn - tprof; tprof = tn; }
+    if (lane == 0) { const long long tn = clock64(); c.prof[9] += tn - tprof; tprof = tn; }
     if (lane == 0) {
       // qh_deletevisible + qh_resetlists
       for (int vi = 0; vi < c.nvis; ++vi) hl_remove(w, c, w.vis[vi]);

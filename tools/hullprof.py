@@ -8,7 +8,7 @@ for r in range(3):
     ctx.step(x,vp,nb)
 print(ctx.last_step_ms(), ctx.counters())
 c=ctx.hull_cycles()
-names=['init','partall','next+horizon+cone','planes+match','list','walk','redo','append','delete','-','insertions','repartitioned','maxcycles','maxpts','maxfacets']
+names=['init','partall','next+horizon+cone','planes+match','list','walk','redo','append','delete','append-old','insertions','repartitioned','maxcycles','maxpts','maxfacets']
 tot=c[:10].sum()
 for n,v in zip(names,c): print('%-20s %12d %5.1f%%'%(n,v,100*v/tot if tot else 0))
 res=ctx.pair_results(); st=res['status']&0xff
