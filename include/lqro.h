@@ -44,6 +44,8 @@ extern "C" {
 #define LQRO_PAIR_OUTSIDE  1   /* relative velocity outside the obstacle: GJK plane (MAIN:1399) */
 #define LQRO_PAIR_INSIDE   2   /* inside: nearest-hull-facet plane (MAIN:1396) */
 #define LQRO_PAIR_DEGENERATE 0x100 /* OR-ed in: the hull met a round-off-band decision / internal limit */
+#define LQRO_PAIR_DROPPED  0x200   /* inside pair that did not fit the hull work queue (max_hull_pairs): carries NO plane
+                                      (low byte 0), counted in lqro_get_counters()[4]; enlarge max_hull_pairs */
 
 typedef struct lqro_ctx lqro_ctx;
 

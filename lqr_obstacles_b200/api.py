@@ -10,7 +10,7 @@ from . import build as _build
 c_int, c_double, c_float, c_void_p = ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_void_p
 
 HULL_TEXT6, HULL_FP64 = 0, 1
-PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE = 0, 1, 2, 0x100
+PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE, PAIR_DROPPED = 0, 1, 2, 0x100, 0x200
 FLAG_NO_PRUNE = 1
 FLAG_FUSED_HULL = 2
 FLAG_DEVICE_KNN = 4

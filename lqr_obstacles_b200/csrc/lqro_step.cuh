@@ -296,9 +296,9 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
           if (lane == 3) { out.nreach[pr] = n; out.dist[pr] = distance; out.status[pr] = 1; }
         } else if (lane == 0) {
           out.nreach[pr] = n;
-          out.status[pr] = 2;  // plane filled in by a hull warp / k_hull
-          __threadfence();
           const int slot = atomicAdd(hq.count, 1);
+          out.status[pr] = slot < hq.capacity ? 2 : 0x200;  // 2: plane filled in by a hull warp / k_hull; 0x200: queue full, no plane
+          __threadfence();
           if (slot < hq.capacity) { *(volatile int*)(hq.items + slot) = pr; }
         }
       }
