@@ -131,13 +131,18 @@ def _ref_chunk(agents):
     A, B, L, E, NF, T, sph, x, vpref, nbr, H = _WL
     rows = np.ascontiguousarray(nbr[agents])
     if kind == "reference":
+        import ctypes
+        R.lib.ref_stage_seconds(None, None, 1)
         npairs, newV, _ = R.step_agents(A, B, L, E, x, vpref, rows, agents, H, 30.0)
-        return int(npairs), newV
+        st = np.zeros(4)
+        nh = ctypes.c_long()
+        R.lib.ref_stage_seconds(st.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nh), 1)
+        return int(npairs), newV, st, int(nh.value)
     xs = x  # the port takes the same global state; restrict the neighbour table to the shard
     full = np.full((len(x), rows.shape[1]), -1, dtype=np.int32)
     full[agents] = rows
     newV = R.step(NF, T, sph, xs, vpref, full, nthreads=1)[0][agents]
-    return int((rows >= 0).sum()), newV
+    return int((rows >= 0).sum()), newV, np.zeros(4), 0
 
 
 class CpuBaseline:
@@ -171,6 +176,14 @@ class CpuBaseline:
         res = self.pool.map(_ref_chunk, tasks)
         dt = time.perf_counter() - t0
         pairs = sum(r[0] for r in res)
+        # CPU seconds (summed over processes) in the reference's own categories, SURVEY 8(d)
+        st = np.sum([r[2] for r in res], axis=0)
+        self.stages = {"unit": "cpu-us per pair (summed over processes / pairs)",
+                       "obstacle_creation": 1e6 * st[0] / max(pairs, 1), "half_plane_creation": 1e6 * st[1] / max(pairs, 1),
+                       "new_velocity": 1e6 * st[2] / max(pairs, 1), "hull_branch_share_of_half_plane": st[3] / max(st[1], 1e-30),
+                       "hulls": int(sum(r[3] for r in res)),
+                       "hull_ms_each": 1e3 * st[3] / max(1, sum(r[3] for r in res)),
+                       "note": "hull = in-process qhull-order quickhull + the reference's text round trip, no process spawn"}
         return pairs, dt, len(agents)
 
     def close(self):
@@ -201,7 +214,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %d agents, K=%d, H=%d, P=%d" % (args.workload, N, wl[3]["K"], wl[3]["H"], wl[3]["P"]),
                    "sample": "%d randomly chosen agents per step (all their K pairs + LP)" % sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "stages": getattr(cpu, "stages", None),
                          "sample": "%d agents x K pairs per step, %d steps, process-sharded" % (sample, args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -384,7 +397,7 @@ def run_ours(args):
             cpu.run(cpu.cores)  # warm the pool
             p, d, na = cpu.run(args.cpu_agents)
             cpu.close()
-            cpu_baseline = {"value": p / d, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+            cpu_baseline = {"value": p / d, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "stages": getattr(cpu, "stages", None),
                             "sample": "%d randomly chosen agents (x K=%d pairs + LP) of the same swarm, process-sharded, %.1f s" % (na, K, d)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

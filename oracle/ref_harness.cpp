@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cstdio>
 #include <unistd.h>
+#include <time.h>
 #include "hull_cpu.h"
 
 // ---------------------------------------------------------------- MSVC CRT rand() emulation
@@ -462,6 +463,19 @@ extern "C" void ref_sim_update(void* handle) {
 // of MAIN:1376-1406 per listed agent, all in the reference's own functions.  x: n_all*16 estimates,
 // vpref: n_all*3, nbr_rows: n_sel*K neighbour ids of the selected agents (<0 = empty), newV: n_sel*3.
 // Returns the number of (i,j) pairs evaluated.  This is what the CPU baseline times.
+// wall-clock seconds spent in the reference's own three categories ("obstacle creation" = findFG + createObstacle +
+// findReachableObstacle, "half-plane creation" = pointInHull + run_gjk/convexHull + createHalfPlanes, "new velocity" =
+// calculateNewV; the category names of the reference's timing printouts) plus the hull branch alone, accumulated by
+// ref_step_agents since the last ref_stage_seconds(reset = 1)
+static double g_stage_s[4] = {0, 0, 0, 0};
+static long g_stage_hulls = 0;
+static inline double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+extern "C" void ref_stage_seconds(double* out4, long* hulls, int reset) {
+  if (out4) for (int q = 0; q < 4; ++q) out4[q] = g_stage_s[q];
+  if (hulls) *hulls = g_stage_hulls;
+  if (reset) { for (int q = 0; q < 4; ++q) g_stage_s[q] = 0; g_stage_hulls = 0; }
+}
+
 extern "C" long ref_step_agents(const double* A, const double* B, const double* L, const double* E, const double* x,
                                 const double* vpref, const int* nbr_rows, const int* agents, int n_sel, int K, int H,
                                 double maxSpeed, double* newV, int* nplanes_out) {
@@ -487,23 +501,33 @@ extern "C" long ref_step_agents(const double* A, const double* B, const double* 
       if (j < 0 || j == i) continue;
       ++npairs;
       State x1; to_mat(x + 16 * (size_t)j, x1);
+      const double t0 = now_s();
       Ft = identity<X_DIM>(); Gt = zeros<X_DIM, V_DIM>();
       for (int k = 0; k < H; ++k) {
         findFG(mA, mB, mL, mE, Ft, Gt);
         createObstacle(ell, points, Transform, Translate, t, Ft, Gt, C, x0, x1, 1);
       }
       findReachableObstacle(ell, reach, x0, x1, maxSpeed);
+      const double t1 = now_s();
+      g_stage_s[0] += t1 - t0;
       if ((int)reach.size() > 4) {
         pointInHull(reach, insideHull, x0, x1);
-        if (insideHull) convexHull(reach, x0, x1, distance, normalVector);
-        else run_gjk(x0, x1, reach, distance, normalVector);
+        if (insideHull) {
+          const double th = now_s();
+          convexHull(reach, x0, x1, distance, normalVector);
+          g_stage_s[3] += now_s() - th;
+          ++g_stage_hulls;
+        } else run_gjk(x0, x1, reach, distance, normalVector);
         distance *= 0.5;
         createHalfPlanes(x0, distance, normalVector, insideHull, orcaPlanes);
+        g_stage_s[1] += now_s() - t1;
       }
     }
     if (nplanes_out) nplanes_out[a] = (int)orcaPlanes.size();
     Matrix<3, 1> g, v; to_mat(vpref + 3 * (size_t)i, g);
+    const double t2 = now_s();
     calculateNewV(orcaPlanes, g, v);
+    g_stage_s[2] += now_s() - t2;
     from_mat(v, newV + 3 * (size_t)a);
   }
   return npairs;
