@@ -15,6 +15,9 @@
 #pragma once
 #include "lqro_common.cuh"
 
+#ifndef LQRO_GJK_LANES
+#define LQRO_GJK_LANES 1       // 1: lane-parallel Johnson sub-algorithm (default); 0: register-resident scalar version
+#endif
 #define LQRO_GJK_EPS 1.0e-8    // GJK.h:208
 #define LQRO_GJK_TINY 1.0e-20  // GJK.h:214
 
@@ -211,6 +214,264 @@ struct CloudView {
     else { gx[m - cap] = x; gy[m - cap] = y; gz[m - cap] = z; }
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// LANE-PARALLEL Johnson sub-algorithm (the default).  A simplex of <= 4 points has 15 non-empty subsets and
+// sum |s| = 32 (subset, element) pairs: exactly one per lane.  Lane (s, j) owns delta_values[s][j]; the
+// recursion over subset size (GJK.c:527-581) proceeds level by level with shuffles from the lanes that own the
+// predecessors' deltas, the dot products live in shared memory (16 doubles per warp, next to the 4 simplex
+// points), the sign tests of GJK.c:593-657 become one ballot plus mask arithmetic, and "first viable subset in
+// numeric order" is an OR-reduction.  Every delta is produced by the same operations in the same order as in the
+// scalar routine, so results are bit-identical to it; what changes is that no lane carries the 15-subset
+// tables in registers (the register-resident version needs ~160 registers at simplex size 4 and spills under
+// the 128-register budget of the 16-warp pair kernel).
+//   lane = e*8 + idx, idx = s with bit e squeezed out  <=>  (s, e) with bit e of s set.
+__device__ __forceinline__ int gjk_lane_of(int s, int e) { return e * 8 + ((s & ((1 << e) - 1)) | ((s >> (e + 1)) << e)); }
+#define LQRO_GJK_WARP_DOUBLES 28  // sc2[4][3] + sprod[4][4]
+
+struct GjkLane {
+  double* sc2;    // [4][3] cloud-side coordinates of the simplex points (the other side is always v_rel)
+  double* sprod;  // [4][4] dot products (GJK.c:540-548)
+  double lam[4];  // uniform
+  double del;     // delta_values[my_s][my_j]
+  double dsum;    // delta[my_s], kept by the lane of the subset's lowest element; persists across iterations like
+                  // the reference's static tables (the backup procedure may read values of an earlier iteration)
+  double de[4];   // deltas of my own subset, by element (gathered after the recursion)
+  int my_s, my_j;
+  int npts, use_default;
+};
+
+// GJK.c:527-581 for a simplex of `size` points
+__device__ __forceinline__ void gjkl_subterms(GjkLane& g, int size, int lane, double v0, double v1, double v2) {
+  if (lane < 16) {
+    const int a = lane >> 2, b = lane & 3;
+    if (a < size && b < size) {
+      const int i = a < b ? a : b, j = a < b ? b : a;
+      const double ci0 = v0 - g.sc2[3 * i], ci1 = v1 - g.sc2[3 * i + 1], ci2 = v2 - g.sc2[3 * i + 2];
+      const double cj0 = v0 - g.sc2[3 * j], cj1 = v1 - g.sc2[3 * j + 1], cj2 = v2 - g.sc2[3 * j + 2];
+      g.sprod[lane] = dot3(ci0, ci1, ci2, cj0, cj1, cj2);
+    }
+  }
+  __syncwarp();
+  const int s = g.my_s, j = g.my_j;
+  const int cs = __popc(s);
+  const bool act = (s >> size) == 0;
+  double del = 1.0;
+  if (act && cs == 2) {
+    const int k = __ffs(s & ~(1 << j)) - 1;
+    del = g.sprod[k * 4 + k] - g.sprod[k * 4 + j];
+  }
+  const int jsub = s & ~(1 << j);
+  const int e0 = jsub ? __ffs(jsub) - 1 : 0;
+  for (int c = 3; c <= size; ++c) {
+    const bool mine = act && cs == c;
+    double sum = 0;
+    int rem = jsub;
+    for (int t = 0; t < c - 1; ++t) {
+      const int i = mine ? __ffs(rem) - 1 : 0;
+      const int src = mine ? gjk_lane_of(jsub, i) : lane;
+      const double dv = __shfl_sync(LQRO_FULL, del, src);
+      if (mine) { sum += dv * (g.sprod[i * 4 + e0] - g.sprod[i * 4 + j]); rem &= rem - 1; }
+    }
+    if (mine) del = sum;
+  }
+  g.del = del;
+  // every lane collects the deltas of its own subset, by element
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const bool in = (s >> e) & 1;
+    const double dv = __shfl_sync(LQRO_FULL, del, in ? gjk_lane_of(s, e) : lane);
+    g.de[e] = dv;
+  }
+}
+
+// GJK.c:708-736: the simplex becomes subset `sel` (elements move down in order), lambdas = delta_values / delta
+__device__ __forceinline__ void gjkl_reset(GjkLane& g, int sel, int lane) {
+  const double ds = __shfl_sync(LQRO_FULL, g.dsum, gjk_lane_of(sel, __ffs(sel) - 1));
+  int rem = sel;
+  const int cs = __popc(sel);
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int oldpos = jj < cs ? __ffs(rem) - 1 : 0;
+    const double dv = __shfl_sync(LQRO_FULL, g.del, jj < cs ? gjk_lane_of(sel, oldpos) : lane);
+    if (jj < cs) {
+      rem &= rem - 1;
+      if (lane < 3 && oldpos != jj) g.sc2[3 * jj + lane] = g.sc2[3 * oldpos + lane];  // sources lie at or above jj: in-place is safe
+      g.lam[jj] = dv / ds;
+    }
+  }
+  g.npts = cs;
+  __syncwarp();
+}
+
+// GJK.c:593-657.  Returns 1 when a viable subset was found (and the simplex reset to it).
+__device__ __forceinline__ int gjkl_default_distance(GjkLane& g, int size, int lane) {
+  const int s = g.my_s;
+  const bool act = (s >> size) == 0;
+  const unsigned P = __ballot_sync(LQRO_FULL, act && g.del > 0);
+  bool ok = true;
+  double ds = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (((s >> e) & 1) && ok) { if (g.de[e] > 0) ds += g.de[e]; else ok = false; }
+#pragma unroll
+  for (int ne = 0; ne < 4; ++ne)
+    if (ne < size && !((s >> ne) & 1) && ((P >> gjk_lane_of(s | (1 << ne), ne)) & 1u)) ok = false;
+  const bool valid = act && ok && ds >= LQRO_GJK_TINY;
+  const unsigned V = __reduce_or_sync(LQRO_FULL, valid ? 1u << s : 0u);
+  const int sel = V ? __ffs(V) - 1 : 0;
+  // the scalar loop assigns delta[s] for every subset it reaches: all of them, or up to the selected one
+  if (act && g.my_j == __ffs(s) - 1 && (sel == 0 || s <= sel)) g.dsum = ds;
+  if (sel) { gjkl_reset(g, sel, lane); return 1; }
+  return 0;
+}
+
+// GJK.c:663-706
+__device__ __forceinline__ void gjkl_backup_distance(GjkLane& g, int size, int lane) {
+  const int s = g.my_s;
+  const bool act = (s >> size) == 0;
+  const int low = __ffs(s) - 1;
+  const double mydsum = __shfl_sync(LQRO_FULL, g.dsum, gjk_lane_of(s, low));
+  bool viable = act && mydsum > 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (((s >> e) & 1) && g.de[e] <= 0) viable = false;
+  double acc = 0;
+#pragma unroll
+  for (int ej = 0; ej < 4; ++ej)
+#pragma unroll
+    for (int ek = 0; ek < 4; ++ek)
+      if (act && ((s >> ej) & 1) && ((s >> ek) & 1)) acc += (g.de[ej] * g.de[ek]) * g.sprod[ej * 4 + ek];
+  const double den = mydsum * mydsum;
+  int bests = 0;
+  double bnum = 0, bden = 0;
+  for (int t = 1; t < (1 << size); ++t) {  // the reference's order-dependent scan, uniform on all lanes
+    const int src = gjk_lane_of(t, __ffs(t) - 1);
+    const int tv = __shfl_sync(LQRO_FULL, (int)viable, src);
+    const double ta = __shfl_sync(LQRO_FULL, acc, src);
+    const double td = __shfl_sync(LQRO_FULL, den, src);
+    if (tv && (bests < 1 || ta * bden < bnum * td)) { bests = t; bnum = ta; bden = td; }
+  }
+  if (bests) gjkl_reset(g, bests, lane);
+}
+
+__device__ __forceinline__ void gjkl_simplex_step(GjkLane& g, int lane, double v0, double v1, double v2) {
+  const int size = g.npts;
+  gjkl_subterms(g, size, lane, v0, v1, v2);
+  if (g.use_default) g.use_default = gjkl_default_distance(g, size, lane);
+  if (!g.use_default) gjkl_backup_distance(g, size, lane);
+}
+
+// Warp-cooperative GJK with the lane-parallel sub-algorithm.  scratch: LQRO_GJK_WARP_DOUBLES doubles of shared
+// memory private to the warp.  Same contract as gjk_warp below.
+__device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v1, const double v2, const CloudView& cl, int n, double* scratch,
+                                                 double* w1out, double* w2out, int* iters) {
+  const int lane = lane_id();
+  GjkLane g;
+  g.sc2 = scratch;
+  g.sprod = scratch + 12;
+  {
+    const int e = lane >> 3, idx = lane & 7;
+    g.my_j = e;
+    g.my_s = (idx & ((1 << e) - 1)) | (1 << e) | ((idx >> e) << (e + 1));
+  }
+  g.npts = 1;  // GJK.c:340-347
+  g.lam[0] = 1.0; g.lam[1] = g.lam[2] = g.lam[3] = 0.0;
+  g.del = 1.0; g.dsum = 0.0;
+  g.de[0] = g.de[1] = g.de[2] = g.de[3] = 0.0;
+  {
+    double x, y, z;
+    cl.get(0, x, y, z);
+    __syncwarp();
+    if (lane == 0) { g.sc2[0] = x; g.sc2[1] = y; g.sc2[2] = z; }
+    __syncwarp();
+  }
+  g.use_default = 1;
+  int first_iteration = 1;
+  double oldsqrd = 0.0, sqrd = 0.0;
+  int max_iterations = n;  // NumVertices(obj1) * NumVertices(obj2), GJK.c:367
+  int ntests = 0;
+  bool exhausted = true;
+  double w1[3] = {0, 0, 0}, w2[3] = {0, 0, 0};
+  while (max_iterations-- > 0) {
+    if (g.npts == 1) g.lam[0] = 1.0;
+    else gjkl_simplex_step(g, lane, v0, v1, v2);
+    // compute_point (GJK.c:851-862), accumulated from 0
+    {
+      const double vv[3] = {v0, v1, v2};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double a = 0, b = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < g.npts) a += vv[d] * g.lam[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (i < g.npts) b += g.sc2[3 * i + d] * g.lam[i];
+        w1[d] = a;
+        w2[d] = b;
+      }
+    }
+    const double d0 = w2[0] - w1[0], d1 = w2[1] - w1[1], d2 = w2[2] - w1[2];
+    sqrd = dot3(d0, d1, d2, d0, d1, d2);
+    if (sqrd < LQRO_GJK_EPS) { exhausted = false; break; }  // GJK.c:419-422
+    const double r0 = -d0, r1 = -d1, r2 = -d2;  // reverse_displacementv
+    // support of the cloud in direction r (support_simple, GJK.c:770-794)
+    double best = -1.7976931348623157e308;
+    int besti = 0x7fffffff;
+    {
+      const int ns = n < cl.cap ? n : cl.cap;  // shared part, then (rarely) the overflow part, ascending index
+#pragma unroll 2
+      for (int m = lane; m < ns; m += 32) {
+        const double v = dot3(cl.sx[m], cl.sy[m], cl.sz[m], r0, r1, r2);
+        if (v > best) { best = v; besti = m; }
+      }
+      if (n > cl.cap) {
+        int m = lane;
+        while (m < cl.cap) m += 32;
+        for (; m < n; m += 32) {
+          const double v = dot3(cl.gx[m - cl.cap], cl.gy[m - cl.cap], cl.gz[m - cl.cap], r0, r1, r2);
+          if (v > best) { best = v; besti = m; }
+        }
+      }
+    }
+    {  // warp arg-max, lowest index on ties: see gjk_warp
+      const long long bits = __double_as_longlong(best + 0.0);
+      const unsigned long long key = (unsigned long long)bits ^ ((unsigned long long)(bits >> 63) | 0x8000000000000000ull);
+      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      const unsigned mhi = __reduce_max_sync(LQRO_FULL, hi);
+      const unsigned mlo = __reduce_max_sync(LQRO_FULL, hi == mhi ? lo : 0u);
+      const bool win = hi == mhi && lo == mlo;
+      besti = (int)__reduce_min_sync(LQRO_FULL, win ? (unsigned)besti : 0x7fffffffu);
+      const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+      best = __longlong_as_double((long long)((mkey >> 63) ? (mkey ^ 0x8000000000000000ull) : ~mkey));
+    }
+    const double minus_minv = best;
+    const int minp = besti;
+    const double maxv = dot3(v0, v1, v2, d0, d1, d2);  // support of the single point
+    ++ntests;
+    double g_val = sqrd + maxv + minus_minv;  // GJK.c:450
+    if (g_val < 0.0) g_val = 0;
+    if (g_val < LQRO_GJK_EPS) { exhausted = false; break; }
+    if ((first_iteration || sqrd < oldsqrd) && g.npts <= 3) {  // GJK.c:472-487
+      double nx, ny, nz;
+      cl.get(minp, nx, ny, nz);
+      if (lane == 0) { g.sc2[3 * g.npts] = nx; g.sc2[3 * g.npts + 1] = ny; g.sc2[3 * g.npts + 2] = nz; }
+      if (g.npts == 1) g.lam[1] = 0.0; else if (g.npts == 2) g.lam[2] = 0.0; else g.lam[3] = 0.0;
+      g.npts++;
+      __syncwarp();
+      g.use_default = 1;
+      oldsqrd = sqrd;
+      first_iteration = 0;
+      continue;
+    }
+    if (g.use_default) g.use_default = 0;  // GJK.c:490-496
+    else { exhausted = false; break; }
+  }
+  if (iters) *iters = ntests;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { w1out[d] = w1[d]; w2out[d] = w2[d]; }
+  if (exhausted) return 0.0;  // GJK.c:499
+  return sqrd;
+}
 
 // Warp-cooperative GJK on a cloud of n points.  Returns d^2 (uniform across the warp); witnesses in w1
 // (on {v_rel}) / w2 (on conv(cloud)); *iters = number of G-tests.

@@ -371,7 +371,12 @@ __global__ void __launch_bounds__(32) k_stage_gjk(const double* __restrict__ vre
   double w1[3], w2[3];
   CloudView cl;
   cl.sx = px; cl.sy = py; cl.sz = pz; cl.gx = cl.gy = cl.gz = nullptr; cl.cap = n;
+#if LQRO_GJK_LANES
+  __shared__ double gjk_scratch[LQRO_GJK_WARP_DOUBLES];
+  const double sq = gjk_warp_lanes(vrel[0], vrel[1], vrel[2], cl, n, gjk_scratch, w1, w2, &it);
+#else
   const double sq = gjk_warp(vrel[0], vrel[1], vrel[2], cl, n, w1, w2, &it);
+#endif
   if (lane == 0) {
     out[0] = sq; out[1] = w2[0]; out[2] = w2[1]; out[3] = w2[2];
     out[4] = w1[0]; out[5] = w1[1]; out[6] = w1[2];

@@ -40,8 +40,11 @@ struct PairWarpV2 {
   double* dx;            // [16]
   double* xi;            // [16]
   int* klist;            // [H]
+  double* gjk;           // [LQRO_GJK_WARP_DOUBLES] simplex points + dot products of the lane-parallel sub-algorithm
 };
-__host__ __device__ inline size_t pair2_warp_doubles(int H) { return (size_t)3 * LQRO_PAIR_CLOUD_CAP + 3 * H + 32 + (H + 1) / 2 + 1; }
+__host__ __device__ inline size_t pair2_warp_doubles(int H) {
+  return (size_t)3 * LQRO_PAIR_CLOUD_CAP + 3 * H + 32 + (H + 1) / 2 + 1 + LQRO_GJK_WARP_DOUBLES;
+}
 
 struct StepSync {
   int* batch_counter;   // next batch of pairs
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     w.cx = wb; w.cy = wb + LQRO_PAIR_CLOUD_CAP; w.cz = wb + 2 * LQRO_PAIR_CLOUD_CAP;
     w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * p.H; w.xi = w.dx + 16;
     w.klist = reinterpret_cast<int*>(w.xi + 16);
+    w.gjk = w.xi + 16 + (p.H + 1) / 2 + 1;
   }
   CloudView cl;
   cl.sx = w.cx; cl.sy = w.cy; cl.sz = w.cz; cl.cap = LQRO_PAIR_CLOUD_CAP;
@@ -276,7 +280,11 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         continue;
       }
       double gw1[3], gw2[3];
+#if LQRO_GJK_LANES
+      const double sq = gjk_warp_lanes(vr0, vr1, vr2, cl, n, w.gjk, gw1, gw2, nullptr);
+#else
       const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
+#endif
       PAIR_PROF(3)
       {
         const double distance = sqrt(sq);                             // MAIN:741
