@@ -355,6 +355,21 @@ __device__ __forceinline__ void gjkl_backup_distance(GjkLane& g, int size, int l
   if (bests) gjkl_reset(g, bests, lane);
 }
 
+template <int N>
+__device__ __forceinline__ void gjkl_witness(const GjkLane& g, double v0, double v1, double v2, double* w1, double* w2) {
+  const double vv[3] = {v0, v1, v2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a += vv[d] * g.lam[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) b += g.sc2[3 * i + d] * g.lam[i];
+    w1[d] = a;
+    w2[d] = b;
+  }
+}
+
 __device__ __forceinline__ void gjkl_simplex_step(GjkLane& g, int lane, double v0, double v1, double v2) {
   const int size = g.npts;
   gjkl_subterms(g, size, lane, v0, v1, v2);
@@ -396,19 +411,12 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
   while (max_iterations-- > 0) {
     if (g.npts == 1) g.lam[0] = 1.0;
     else gjkl_simplex_step(g, lane, v0, v1, v2);
-    // compute_point (GJK.c:851-862), accumulated from 0
-    {
-      const double vv[3] = {v0, v1, v2};
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        double a = 0, b = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < g.npts) a += vv[d] * g.lam[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (i < g.npts) b += g.sc2[3 * i + d] * g.lam[i];
-        w1[d] = a;
-        w2[d] = b;
-      }
+    // compute_point (GJK.c:851-862), accumulated from 0; one unrolled body per simplex size (uniform branch)
+    switch (g.npts) {
+      case 1: gjkl_witness<1>(g, v0, v1, v2, w1, w2); break;
+      case 2: gjkl_witness<2>(g, v0, v1, v2, w1, w2); break;
+      case 3: gjkl_witness<3>(g, v0, v1, v2, w1, w2); break;
+      default: gjkl_witness<4>(g, v0, v1, v2, w1, w2); break;
     }
     const double d0 = w2[0] - w1[0], d1 = w2[1] - w1[1], d2 = w2[2] - w1[2];
     sqrd = dot3(d0, d1, d2, d0, d1, d2);
