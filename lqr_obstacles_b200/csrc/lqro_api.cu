@@ -263,8 +263,10 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     CUC(cudaMalloc(&ctx->d_pair_ovf, sizeof(double) * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * wp));
     // function attributes are per function, not per context: always allow the device maximum so that
     // contexts with different H*P can coexist
-    CUC(cudaFuncSetAttribute(k_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-    CUC(cudaFuncSetAttribute(k_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 20, 50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 30, 50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     ctx->hull_wpb = 1;
     ctx->cap_pts = H * P;
@@ -454,12 +456,13 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet
   StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   CU(cudaEventRecord(ctx->ev[0], st));
-  if (ctx->fused_hull)
-    k_pairs<true><<<ctx->pair_blocks, (ctx->pair_warps + 1) * 32, ctx->pair_smem, st>>>(
-        p, ctx->tb, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf, ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride);
-  else
-    k_pairs<false><<<ctx->pair_blocks, ctx->pair_warps * 32, ctx->pair_smem, st>>>(
-        p, ctx->tb, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf, ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride);
+#define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS)                                                                                   \
+  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf, \
+                                                                            ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride)
+  if (ctx->fused_hull) LQRO_LAUNCH_PAIRS(true, 0, 0, ctx->pair_warps + 1);
+  else if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, ctx->pair_warps);  // the synthetic-swarm configuration
+  else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps);  // the reference's own constants (MAIN:30-34)
+  else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws, ctx->hull_ws_stride,

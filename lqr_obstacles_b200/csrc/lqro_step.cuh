@@ -94,16 +94,18 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K) {
 #define PAIR_PROF_FLUSH
 #endif
 
-template <bool FUSED_HULL>
+// HT, PT > 0: horizon / sample counts known at compile time (table offsets and loop bounds fold into immediates);
+// 0: taken from the parameters.
+template <bool FUSED_HULL, int HT, int PT>
 __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
                                                   size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int H = HT > 0 ? HT : p.H, P = PT > 0 ? PT : p.P;
   PairTables t;
-  load_block_tables(smem, tb, p.H, p.P);
+  load_block_tables(smem, tb, H, P);
   {
-    const int H = p.H, P = p.P;
     t.NFt = smem; t.T = smem + 16 * 3 * H; t.sphx = t.T + 9 * H; t.sphy = t.sphx + P; t.sphz = t.sphy + P;
     t.CG = t.sphz + P; t.prn = t.CG + 9 * H;
   }
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     // ------------------------------------------------------------------ hull warp (consumer)
     HullWarp hw;
     char* sm = reinterpret_cast<char*>(smem) +
-               hull_align16(sizeof(double) * (pair_block_table_doubles(p.H, p.P) + (size_t)n_pair_warps * pair2_warp_doubles(p.H)));
-    hull_warp_setup(hw, sm, hull_ws + hull_ws_stride * (size_t)blockIdx.x, p.H, p.P);
+               hull_align16(sizeof(double) * (pair_block_table_doubles(H, P) + (size_t)n_pair_warps * pair2_warp_doubles(H)));
+    hull_warp_setup(hw, sm, hull_ws + hull_ws_stride * (size_t)blockIdx.x, H, P);
     while (true) {
       int ticket = -1;
       if (lane == 0) {
@@ -148,22 +150,22 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
   // -------------------------------------------------------------------- pair warps (producers)
   PairWarpV2 w;
   {
-    double* wb = smem + pair_block_table_doubles(p.H, p.P) + (size_t)warp * pair2_warp_doubles(p.H);
+    double* wb = smem + pair_block_table_doubles(H, P) + (size_t)warp * pair2_warp_doubles(H);
     w.cx = wb; w.cy = wb + LQRO_PAIR_CLOUD_CAP; w.cz = wb + 2 * LQRO_PAIR_CLOUD_CAP;
-    w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * p.H; w.xi = w.dx + 16;
+    w.tr = wb + 3 * LQRO_PAIR_CLOUD_CAP; w.dx = w.tr + 3 * H; w.xi = w.dx + 16;
     w.klist = reinterpret_cast<int*>(w.xi + 16);
-    w.gjk = w.xi + 16 + (p.H + 1) / 2 + 1;
+    w.gjk = w.xi + 16 + (H + 1) / 2 + 1;
   }
   CloudView cl;
   cl.sx = w.cx; cl.sy = w.cy; cl.sz = w.cz; cl.cap = LQRO_PAIR_CLOUD_CAP;
   {
     double* ov = ovf_base + ovf_stride * (size_t)(blockIdx.x * n_pair_warps + warp);
-    const size_t no = (size_t)(p.HP > LQRO_PAIR_CLOUD_CAP ? p.HP - LQRO_PAIR_CLOUD_CAP : 0);
+    const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
   const long long total = slot_major_total(p.n_local, p.K);
-  const int n3 = 3 * p.H;
-  const unsigned long long allsteps = (p.H >= 64) ? ~0ull : ((1ull << p.H) - 1ull);
+  const int n3 = 3 * H;
+  const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
   while (true) {
     int batch = 0;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
             dx1 += fabs(dx[2 * m]) + fabs(dx[2 * m + 1]);
           }
           const double vr0 = dx[3], vr1 = dx[4], vr2 = dx[5];
-          for (int k = 0; k < p.H; ++k) {
+          for (int k = 0; k < H; ++k) {
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
             const double* nf = t.NFt + 3 * k;
 #pragma unroll
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int k = lane + 32 * h;
-        if (k < p.H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
+        if (k < H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
       }
       __syncwarp();
       // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231)
@@ -249,9 +251,9 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       PAIR_PROF(1)
       const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
       int count = 0;
-      const int tot = nk * p.P;
+      const int tot = nk * P;
       int ki = 0, s = lane;
-      while (s >= p.P) { s -= p.P; ++ki; }
+      while (s >= P) { s -= P; ++ki; }
       for (int b0 = 0; b0 < tot; b0 += 32) {
         const int m = b0 + lane;
         bool pass = false;
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         }
         count += __popc(mask);
         s += 32;
-        { const bool wrap = s >= p.P; s -= wrap ? p.P : 0; ki += wrap ? 1 : 0; }
-        if (p.P < 32) while (s >= p.P) { s -= p.P; ++ki; }
+        { const bool wrap = s >= P; s -= wrap ? P : 0; ki += wrap ? 1 : 0; }
+        if (P < 32) while (s >= P) { s -= P; ++ki; }
       }
       __syncwarp();
       PAIR_PROF(2)
