@@ -238,6 +238,7 @@ struct GjkLane {
                   // the reference's static tables (the backup procedure may read values of an earlier iteration)
   double de[4];   // deltas of my own subset, by element (gathered after the recursion)
   int my_s, my_j;
+  unsigned sup[3];  // sup[size-2]: lanes (s + k, k), k < size not in my_s -- a positive delta there rules my subset out (GJK.c:624-631)
   int npts, use_default;
 };
 
@@ -314,9 +315,7 @@ __device__ __forceinline__ int gjkl_default_distance(GjkLane& g, int size, int l
 #pragma unroll
   for (int e = 0; e < 4; ++e)
     if (((s >> e) & 1) && ok) { if (g.de[e] > 0) ds += g.de[e]; else ok = false; }
-#pragma unroll
-  for (int ne = 0; ne < 4; ++ne)
-    if (ne < size && !((s >> ne) & 1) && ((P >> gjk_lane_of(s | (1 << ne), ne)) & 1u)) ok = false;
+  if (P & (size == 2 ? g.sup[0] : size == 3 ? g.sup[1] : g.sup[2])) ok = false;
   const bool valid = act && ok && ds >= LQRO_GJK_TINY;
   const unsigned V = __reduce_or_sync(LQRO_FULL, valid ? 1u << s : 0u);
   const int sel = V ? __ffs(V) - 1 : 0;
@@ -389,6 +388,14 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
     const int e = lane >> 3, idx = lane & 7;
     g.my_j = e;
     g.my_s = (idx & ((1 << e) - 1)) | (1 << e) | ((idx >> e) << (e + 1));
+#pragma unroll
+    for (int size = 2; size <= 4; ++size) {
+      unsigned m = 0u;
+#pragma unroll
+      for (int ne = 0; ne < 4; ++ne)
+        if (ne < size && !((g.my_s >> ne) & 1)) m |= 1u << gjk_lane_of(g.my_s | (1 << ne), ne);
+      g.sup[size - 2] = m;
+    }
   }
   g.npts = 1;  // GJK.c:340-347
   g.lam[0] = 1.0; g.lam[1] = g.lam[2] = g.lam[3] = 0.0;
