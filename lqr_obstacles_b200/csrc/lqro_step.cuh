@@ -256,12 +256,10 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       while (s >= P) { s -= P; ++ki; }
       for (int b0 = 0; b0 < tot; b0 += 32) {
         const int m = b0 + lane;
-        bool pass = false;
-        double q0 = 0, q1 = 0, q2 = 0;
-        if (m < tot) {
-          candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki], s, q0, q1, q2);
-          pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2);
-        }
+        // lanes past the end of the last chunk redo a valid candidate and are masked out: no divergent body
+        double q0, q1, q2;
+        candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki < nk ? ki : nk - 1], s, q0, q1, q2);
+        const bool pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2) && m < tot;
         const unsigned mask = __ballot_sync(LQRO_FULL, pass);
         if (pass) {
           const int pos = count + __popc(mask & ((1u << lane) - 1u));
