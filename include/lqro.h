@@ -100,6 +100,14 @@ int lqro_solve_gains(lqro_ctx* ctx, int n_batch, const double* A, const double* 
  * k = 1..H with F_k = (A+BL)^k, G_k = sum_{m<k} (A+BL)^m B E.  Must precede any step. Host pointers. */
 int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E);
 
+/* Heterogeneous dynamics (dynamics classes, e.g. mass / inertia / latency variants): the same for class `cls` in
+ * [0, 16); class 0 is what lqro_set_dynamics sets.  The obstacle of a pair (i, j) is built from the matrices of agent
+ * i (findFG(A, B, qlist[i]->L, qlist[i]->E, ...), MAIN:1384), i.e. from the tables of i's class. */
+int lqro_set_dynamics_class(lqro_ctx* ctx, int cls, const double* A, const double* B, const double* L, const double* E);
+/* Class of every agent: n_agents ints (host), every class named must have its dynamics set.  NULL: all class 0.
+ * The step then runs the pair kernel once per class over the owned agents of that class. */
+int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls);
+
 /* Copies the tables back (parity checks): NF H*3*16, T H*3*3, sphere samples P*3 (createSpheres,
  * MAIN:665-680).  Any pointer may be NULL. */
 int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* spheres);

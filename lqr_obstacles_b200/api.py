@@ -39,6 +39,7 @@ EXPORTS = [
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
     "lqro_debug_hull_cycles", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
+    "lqro_set_dynamics_class", "lqro_set_agent_classes",
 ]
 
 
@@ -263,6 +264,20 @@ class Lqro:
         newVel = np.ascontiguousarray(newVel, dtype=np.float32)
         self._ck(self.lib.lqro_agent_update(self.h, len(pos), _p(pos), _p(vel), _p(newVel), dt))
         return pos, vel
+
+    def set_dynamics_class(self, cls, A, B, L, E):
+        """dynamics class `cls` (0..15); class 0 == set_dynamics"""
+        A, B, L, E = (np.ascontiguousarray(m, dtype=np.float64) for m in (A, B, L, E))
+        self._ck(self.lib.lqro_set_dynamics_class(self.h, int(cls), _p(A), _p(B), _p(L), _p(E)))
+
+    def set_agent_classes(self, cls):
+        """class id of every agent (n_agents ints), or None for a single class"""
+        if cls is None:
+            self._ck(self.lib.lqro_set_agent_classes(self.h, None))
+            return
+        cls = np.ascontiguousarray(cls, dtype=np.int32)
+        assert cls.shape == (self.N,)
+        self._ck(self.lib.lqro_set_agent_classes(self.h, _p(cls)))
 
     def knn(self, x=None):
         """K nearest other agents of every owned agent on the device (AGENT:153-174 ordering); the table stays

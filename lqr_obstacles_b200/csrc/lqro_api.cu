@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/lqro.h"
+#define LQRO_MAX_CLASSES 16
 #include "lqro_common.cuh"
 #include "lqro_gjk.cuh"
 #include "lqro_knn.cuh"
@@ -65,6 +66,14 @@ struct lqro_ctx {
   // tables / dynamics
   double *d_dyn = nullptr;   // A(256) B(64) L(64) E(12)
   double *d_NFt = nullptr, *d_NF = nullptr, *d_T = nullptr, *d_sph = nullptr, *d_CG = nullptr, *d_prn = nullptr;
+  // heterogeneous dynamics: tables of the extra classes 1..15 (class 0 = the buffers above), the class
+  // of every agent, the owned agents ordered by class, one batch counter per class
+  struct ClassTab { double *NFt = nullptr, *NF = nullptr, *T = nullptr, *CG = nullptr, *prn = nullptr; bool set = false; };
+  ClassTab cls[LQRO_MAX_CLASSES];
+  LqroTables* d_tbs = nullptr;           // [LQRO_MAX_CLASSES] for the hull kernel
+  int *d_agent_class = nullptr, *d_order = nullptr, *d_cls_ctr = nullptr;
+  int cls_begin[LQRO_MAX_CLASSES] = {0}, cls_count[LQRO_MAX_CLASSES] = {0};
+  bool hetero = false;
   // step buffers
   double *d_x = nullptr, *d_vpref = nullptr, *d_newV = nullptr, *d_dist = nullptr;
   int *d_nbr = nullptr, *d_status = nullptr, *d_nreach = nullptr, *d_nfacets = nullptr, *d_nplanes = nullptr;
@@ -91,6 +100,7 @@ struct lqro_ctx {
   // multi-GPU
   lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
   long long launches = 0;
+  int launches_extra = 0;
   std::string err;
 };
 
@@ -154,6 +164,11 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
                   ctx->d_hull_items, ctx->d_hull_ws, ctx->d_scratch, ctx->d_stage_ws, ctx->d_pair_ovf, ctx->d_prof,
                   ctx->d_knn_bb, ctx->d_knn_grid, ctx->d_knn_cell, ctx->d_knn_count, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int c = 1; c < LQRO_MAX_CLASSES; ++c) {
+    void* q[] = {ctx->cls[c].NFt, ctx->cls[c].NF, ctx->cls[c].T, ctx->cls[c].CG, ctx->cls[c].prn};
+    for (void* p : q) if (p) cudaFree(p);
+  }
+  { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr}; for (void* p : q) if (p) cudaFree(p); }
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -242,6 +257,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
       for (int k = 0; k < 3; ++k) if (fabs(sph[3 * i + k]) > p.box[k]) p.box[k] = fabs(sph[3 * i + k]);
   }
   ctx->tb.NFt = ctx->d_NFt; ctx->tb.T = ctx->d_T; ctx->tb.sph = ctx->d_sph; ctx->tb.CG = ctx->d_CG; ctx->tb.prn = ctx->d_prn;
+  ctx->cls[0].NFt = ctx->d_NFt; ctx->cls[0].NF = ctx->d_NF; ctx->cls[0].T = ctx->d_T; ctx->cls[0].CG = ctx->d_CG; ctx->cls[0].prn = ctx->d_prn;
   // launch geometry of the pair kernel: as many warps per block as the opt-in shared memory holds
   {
     const size_t tbl = sizeof(double) * pair_block_table_doubles(H, P);
@@ -313,15 +329,24 @@ extern "C" int lqro_solve_gains(lqro_ctx* ctx, int nb, const double* A, const do
   return LQRO_OK;
 }
 
-extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E) {
-  if (!ctx || !A || !B || !L || !E) return fail(ctx, LQRO_E_ARG, "bad argument");
+static int set_dynamics_impl(lqro_ctx* ctx, int cls, const double* A, const double* B, const double* L, const double* E) {
+  if (!ctx || !A || !B || !L || !E || cls < 0 || cls >= LQRO_MAX_CLASSES) return fail(ctx, LQRO_E_ARG, "bad argument");
   CU(cudaSetDevice(ctx->cfg.device));
+  lqro_ctx::ClassTab& ct = ctx->cls[cls];
+  if (!ct.NFt) {
+    const int H = ctx->prm.H;
+    CU(cudaMalloc(&ct.NFt, sizeof(double) * 48 * H));
+    CU(cudaMalloc(&ct.NF, sizeof(double) * 48 * H));
+    CU(cudaMalloc(&ct.T, sizeof(double) * 9 * H));
+    CU(cudaMalloc(&ct.CG, sizeof(double) * 9 * H));
+    CU(cudaMalloc(&ct.prn, sizeof(double) * LQRO_PRN * H));
+  }
   double* d = ctx->d_dyn;
   CU(cudaMemcpyAsync(d, A, sizeof(double) * 256, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d + 256, B, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d + 320, L, sizeof(double) * 64, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d + 384, E, sizeof(double) * 12, cudaMemcpyHostToDevice, ctx->stream));
-  k_horizon_tables<<<1, 256, 0, ctx->stream>>>(d, d + 256, d + 320, d + 384, ctx->prm.H, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_CG);
+  k_horizon_tables<<<1, 256, 0, ctx->stream>>>(d, d + 256, d + 320, d + 384, ctx->prm.H, ct.NFt, ct.NF, ct.T, ct.CG);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   // pruning constants per horizon step (see step_prunable in lqro_pair.cuh): an UPPER bound of
@@ -330,10 +355,10 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
   {
     const int H = ctx->prm.H;
     std::vector<double> cg(9 * (size_t)H), T(9 * (size_t)H), prn(LQRO_PRN * (size_t)H, 0.0);
-    CU(cudaMemcpy(cg.data(), ctx->d_CG, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(T.data(), ctx->d_T, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cg.data(), ct.CG, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(T.data(), ct.T, sizeof(double) * 9 * H, cudaMemcpyDeviceToHost));
     std::vector<double> nf(48 * (size_t)H), nfmax(H, 0.0);
-    CU(cudaMemcpy(nf.data(), ctx->d_NF, sizeof(double) * 48 * H, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nf.data(), ct.NF, sizeof(double) * 48 * H, cudaMemcpyDeviceToHost));
     for (int k = 0; k < H; ++k) for (int e = 0; e < 48; ++e) nfmax[k] = fmax(nfmax[k], fabs(nf[48 * (size_t)k + e]));
     for (int k = 0; k < H; ++k) {
       const double* g = cg.data() + 9 * k;
@@ -369,9 +394,54 @@ extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B
       c[6] = sqrt(tf) * (1.0 + 1e-9);
       c[7] = nfmax[k];
     }
-    CU(cudaMemcpy(ctx->d_prn, prn.data(), sizeof(double) * LQRO_PRN * H, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ct.prn, prn.data(), sizeof(double) * LQRO_PRN * H, cudaMemcpyHostToDevice));
   }
-  ctx->have_dynamics = true;
+  ct.set = true;
+  if (cls == 0) ctx->have_dynamics = true;
+  {
+    LqroTables tbs[LQRO_MAX_CLASSES];
+    for (int c = 0; c < LQRO_MAX_CLASSES; ++c) {
+      const lqro_ctx::ClassTab& q = ctx->cls[c].set ? ctx->cls[c] : ctx->cls[0];
+      tbs[c].NFt = q.NFt; tbs[c].T = q.T; tbs[c].sph = ctx->d_sph; tbs[c].CG = q.CG; tbs[c].prn = q.prn;
+    }
+    if (!ctx->d_tbs) CU(cudaMalloc(&ctx->d_tbs, sizeof(tbs)));
+    CU(cudaMemcpy(ctx->d_tbs, tbs, sizeof(tbs), cudaMemcpyHostToDevice));
+  }
+  return LQRO_OK;
+}
+
+extern "C" int lqro_set_dynamics(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E) {
+  return set_dynamics_impl(ctx, 0, A, B, L, E);
+}
+
+extern "C" int lqro_set_dynamics_class(lqro_ctx* ctx, int cls, const double* A, const double* B, const double* L, const double* E) {
+  return set_dynamics_impl(ctx, cls, A, B, L, E);
+}
+
+// class of every agent (n_agents ints in [0, 16), every class used must have its dynamics set); NULL = all class 0
+extern "C" int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls) {
+  if (!ctx) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const LqroParams& p = ctx->prm;
+  if (!cls) { ctx->hetero = false; return LQRO_OK; }
+  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) ctx->cls_count[c] = 0;
+  for (int i = 0; i < p.N; ++i) {
+    if (cls[i] < 0 || cls[i] >= LQRO_MAX_CLASSES || !ctx->cls[cls[i]].set) return fail(ctx, LQRO_E_ARG, "agent class without dynamics");
+  }
+  for (int il = 0; il < p.n_local; ++il) ctx->cls_count[cls[p.local_begin + il]]++;
+  int run = 0;
+  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) { ctx->cls_begin[c] = run; run += ctx->cls_count[c]; }
+  std::vector<int> order(p.n_local), fill(LQRO_MAX_CLASSES, 0);
+  for (int il = 0; il < p.n_local; ++il) { const int c = cls[p.local_begin + il]; order[ctx->cls_begin[c] + fill[c]++] = il; }
+  if (!ctx->d_agent_class) {
+    CU(cudaMalloc(&ctx->d_agent_class, sizeof(int) * (size_t)p.N));
+    CU(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)p.n_local));
+    CU(cudaMalloc(&ctx->d_cls_ctr, sizeof(int) * LQRO_MAX_CLASSES));
+  }
+  CU(cudaMemcpy(ctx->d_agent_class, cls, sizeof(int) * (size_t)p.N, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->d_order, order.data(), sizeof(int) * (size_t)p.n_local, cudaMemcpyHostToDevice));
+  ctx->hetero = true;
   return LQRO_OK;
 }
 
@@ -456,24 +526,45 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet
   StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   CU(cudaEventRecord(ctx->ev[0], st));
-#define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS)                                                                                   \
-  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf, \
-                                                                            ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride)
-  if (ctx->fused_hull) LQRO_LAUNCH_PAIRS(true, 0, 0, ctx->pair_warps + 1);
-  else if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, ctx->pair_warps);  // the synthetic-swarm configuration
-  else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps);  // the reference's own constants (MAIN:30-34)
-  else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps);
+#define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
+  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, st>>>(PP, TB, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf,   \
+                                                                            ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
+#define LQRO_LAUNCH_PAIRS_ANY(PP, TB, ORD)                                                                                     \
+  do {                                                                                                                         \
+    if (ctx->fused_hull && !(ORD)) LQRO_LAUNCH_PAIRS(true, 0, 0, ctx->pair_warps + 1, PP, TB, ORD);                             \
+    else if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, ctx->pair_warps, PP, TB, ORD); /* synthetic swarms */     \
+    else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
+    else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
+  } while (0)
+  if (!ctx->hetero) {
+    LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+  } else {
+    // one launch per dynamics class over the owned agents of that class (the tables of one class fill the CTA's shared memory)
+    CU(cudaMemsetAsync(ctx->d_cls_ctr, 0, sizeof(int) * LQRO_MAX_CLASSES, st));
+    for (int c = 0; c < LQRO_MAX_CLASSES; ++c) {
+      if (!ctx->cls_count[c]) continue;
+      LqroParams pc = p;
+      pc.n_local = ctx->cls_count[c];
+      LqroTables tbc = ctx->tb;
+      tbc.NFt = ctx->cls[c].NFt; tbc.T = ctx->cls[c].T; tbc.CG = ctx->cls[c].CG; tbc.prn = ctx->cls[c].prn;
+      sy.batch_counter = ctx->d_cls_ctr + c;
+      const int* ord = ctx->d_order + ctx->cls_begin[c];
+      LQRO_LAUNCH_PAIRS_ANY(pc, tbc, ord);
+      ++ctx->launches_extra;
+    }
+  }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws, ctx->hull_ws_stride,
-                                                      ctx->d_ctr, ctx->d_prof);
+                                                      ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,
                                                           ctx->d_planes_c, ctx->d_proj, d_newV, ctx->d_nplanes);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
-  ctx->launches = 3;
+  ctx->launches = ctx->hetero ? 2 + ctx->launches_extra : 3;
+  ctx->launches_extra = 0;
   ctx->stepped = true;
   return LQRO_OK;
 }

@@ -1034,7 +1034,8 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
 // same counter).  One warp (= one block) per queued pair at a time.
 __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
-                                             size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof) {
+                                             size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
+                                             const int* __restrict__ agent_class /* NULL: one class */, const LqroTables* __restrict__ class_tables) {
   extern __shared__ double smem[];
   const int lane = lane_id();
   int nq = *hq.count;
@@ -1050,6 +1051,7 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
   HullWarp hw;
   hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * pair_block_table_doubles(p.H, p.P)),
                   ws_base + ws_stride * (size_t)blockIdx.x, p.H, p.P);
+  int loaded = agent_class ? -1 : 0;
   while (true) {
     int item = 0;
     if (lane == 0) item = atomicAdd(work_counter, 1);
@@ -1057,6 +1059,10 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
     if (item >= nq) break;
     const int pair = hq.items[item];
     if (pair < 0) continue;
+    if (agent_class) {  // heterogeneous dynamics: the obstacle of pair (i, j) uses agent i's class (MAIN:1384)
+      const int c = agent_class[p.local_begin + pair / p.K];
+      if (c != loaded) { __syncwarp(); load_block_tables(smem, class_tables[c], p.H, p.P); loaded = c; }
+    }
     hull_do_pair(p, pt, hw, x, nbr, out, pair, counters, prof);
   }
 }

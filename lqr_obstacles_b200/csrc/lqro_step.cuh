@@ -99,7 +99,8 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K) {
 template <bool FUSED_HULL, int HT, int PT>
 __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
-                                                  size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride) {
+                                                  size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride,
+                                                  const int* __restrict__ order /* NULL, or the owned agents of one dynamics class: p.n_local of them */) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int H = HT > 0 ? HT : p.H, P = PT > 0 ? PT : p.P;
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     // ---------------- stage 1: lane = pair
     int il = 0, kk = 0;
     const bool have = slot_major_pair(p, base + lane, il, kk);
+    if (have && order) il = order[il];
     const int pair = have ? il * p.K + kk : -1;
     int i = 0, j = -1;
     unsigned long long kmask = 0ull;
