@@ -12,6 +12,7 @@
 
 #include "../../include/lqro.h"
 #define LQRO_MAX_CLASSES 16
+#define LQRO_NBR_CHUNKS 4  // measured at 65,536 agents x K=64: none 7.85 ms end to end, 4 -> 7.74, 8 -> 7.84
 #include "lqro_common.cuh"
 #include "lqro_gjk.cuh"
 #include "lqro_knn.cuh"
@@ -74,6 +75,13 @@ struct lqro_ctx {
   int *d_agent_class = nullptr, *d_order = nullptr, *d_cls_ctr = nullptr;
   int cls_begin[LQRO_MAX_CLASSES] = {0}, cls_count[LQRO_MAX_CLASSES] = {0};
   bool hetero = false;
+  // host-buffer steps of large swarms: the neighbour table is uploaded in LQRO_NBR_CHUNKS agent blocks on a copy stream while
+  // the pair kernel of the previous block runs (one launch per block, each on its own stream, so block c+1 moves onto an SM
+  // as soon as block c's CTA leaves it)
+  const int* h_nbr_chunked = nullptr;
+  cudaStream_t copy_stream = nullptr, chunk_stream[LQRO_NBR_CHUNKS] = {nullptr};
+  cudaEvent_t ev_ready = nullptr, ev_up[LQRO_NBR_CHUNKS] = {nullptr}, ev_done[LQRO_NBR_CHUNKS] = {nullptr};
+  int *d_identity = nullptr, *d_chunk_ctr = nullptr;
   // step buffers
   double *d_x = nullptr, *d_vpref = nullptr, *d_newV = nullptr, *d_dist = nullptr;
   int *d_nbr = nullptr, *d_status = nullptr, *d_nreach = nullptr, *d_nfacets = nullptr, *d_nplanes = nullptr;
@@ -168,7 +176,14 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
     void* q[] = {ctx->cls[c].NFt, ctx->cls[c].NF, ctx->cls[c].T, ctx->cls[c].CG, ctx->cls[c].prn};
     for (void* p : q) if (p) cudaFree(p);
   }
-  { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr}; for (void* p : q) if (p) cudaFree(p); }
+  { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr, ctx->d_identity, ctx->d_chunk_ctr}; for (void* p : q) if (p) cudaFree(p); }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
+    if (ctx->chunk_stream[c]) cudaStreamDestroy(ctx->chunk_stream[c]);
+    if (ctx->ev_up[c]) cudaEventDestroy(ctx->ev_up[c]);
+    if (ctx->ev_done[c]) cudaEventDestroy(ctx->ev_done[c]);
+  }
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -527,7 +542,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
-  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, st>>>(PP, TB, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf,   \
+  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf,  \
                                                                             ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
 #define LQRO_LAUNCH_PAIRS_ANY(PP, TB, ORD)                                                                                     \
   do {                                                                                                                         \
@@ -536,7 +551,50 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
     else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
   } while (0)
-  if (!ctx->hetero) {
+  cudaStream_t pst = st;  // stream of the pair-kernel launches
+  if (ctx->h_nbr_chunked) {
+    const int* h_nbr = ctx->h_nbr_chunked;
+    ctx->h_nbr_chunked = nullptr;
+    if (!ctx->copy_stream) {
+      CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+      for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
+        CU(cudaStreamCreateWithFlags(&ctx->chunk_stream[c], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_up[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_done[c], cudaEventDisableTiming));
+      }
+      std::vector<int> id(p.n_local);
+      for (int i = 0; i < p.n_local; ++i) id[i] = i;
+      CU(cudaMalloc(&ctx->d_identity, sizeof(int) * (size_t)p.n_local));
+      CU(cudaMemcpy(ctx->d_identity, id.data(), sizeof(int) * (size_t)p.n_local, cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&ctx->d_chunk_ctr, sizeof(int) * LQRO_NBR_CHUNKS));
+    }
+    CU(cudaMemsetAsync(ctx->d_chunk_ctr, 0, sizeof(int) * LQRO_NBR_CHUNKS, st));
+    CU(cudaEventRecord(ctx->ev_ready, st));  // state gathered, counters cleared, previous step finished
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));  // d_nbr may still be read by the previous step
+    const int per = (p.n_local + LQRO_NBR_CHUNKS - 1) / LQRO_NBR_CHUNKS;
+    for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
+      const int off = c * per, cnt = std::min(per, p.n_local - off);
+      if (cnt <= 0) break;
+      CU(cudaMemcpyAsync(ctx->d_nbr + (size_t)off * p.K, h_nbr + (size_t)off * p.K, sizeof(int) * (size_t)cnt * p.K, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->ev_up[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
+      const int off = c * per, cnt = std::min(per, p.n_local - off);
+      if (cnt <= 0) break;
+      pst = ctx->chunk_stream[c];
+      CU(cudaStreamWaitEvent(pst, ctx->ev_up[c], 0));
+      LqroParams pc = p;
+      pc.n_local = cnt;
+      sy.batch_counter = ctx->d_chunk_ctr + c;
+      const int* ord = ctx->d_identity + off;
+      LQRO_LAUNCH_PAIRS_ANY(pc, ctx->tb, ord);
+      CU(cudaEventRecord(ctx->ev_done[c], pst));
+      CU(cudaStreamWaitEvent(st, ctx->ev_done[c], 0));
+      ++ctx->launches_extra;
+    }
+    pst = st;
+  } else if (!ctx->hetero) {
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
   } else {
     // one launch per dynamics class over the owned agents of that class (the tables of one class fill the CTA's shared memory)
@@ -563,7 +621,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
                                                           ctx->d_planes_c, ctx->d_proj, d_newV, ctx->d_nplanes);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
-  ctx->launches = ctx->hetero ? 2 + ctx->launches_extra : 3;
+  ctx->launches = ctx->launches_extra ? 2 + ctx->launches_extra : 3;
   ctx->launches_extra = 0;
   ctx->stepped = true;
   return LQRO_OK;
@@ -584,7 +642,10 @@ extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, co
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  // large swarms: the neighbour table goes up in blocks, overlapped with the pair kernel (see launch_step)
+  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
+  if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  ctx->h_nbr_chunked = chunked ? nbr : nullptr;
   int rc = LQRO_OK;
   if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
@@ -882,7 +943,9 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(ctx->d_x + 16 * (size_t)p.local_begin, x_local, sizeof(double) * 16 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  if (nbr) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
+  if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  ctx->h_nbr_chunked = chunked ? nbr : nullptr;
   int rc = lqro_allgather_state(ctx);
   if (rc) return rc;
   if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;

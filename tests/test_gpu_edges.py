@@ -120,3 +120,24 @@ def test_maximum_reachable_cloud(golden, oracle, product_lib):
     st = ost & 0xFF
     assert np.array_equal(res["planes"][st != 0], opl[st != 0])
     ctx.close()
+
+
+def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
+    """host-buffer steps of >= 2^20 pairs upload the neighbour table in blocks overlapped with the pair kernel (one
+    launch per block): same planes, statuses and velocities as the single-launch path fed with a resident table"""
+    x, vp = swarm.lattice_swarm((32, 32, 16))
+    N, K = len(x), 64
+    nbr = swarm.knn(x[:, :3], K)
+    a = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
+    v1 = a.step(x, vp, nbr).copy()          # chunked (N*K = 2^20)
+    r1 = a.pair_results()
+    assert a.counters()["launches"] > 3
+    v2 = a.step(x, vp, None).copy()         # table already resident: one pair-kernel launch
+    r2 = a.pair_results()
+    assert a.counters()["launches"] == 3
+    assert np.array_equal(v1, v2) and np.array_equal(r1["status"], r2["status"]) and np.array_equal(r1["nreach"], r2["nreach"])
+    has = (r1["status"] & 0xFF) != 0
+    assert np.array_equal(r1["planes"][has], r2["planes"][has])
+    v3 = a.step(x, vp, nbr)                 # and again chunked, after a plain step
+    assert np.array_equal(v3, v1)
+    a.close()
