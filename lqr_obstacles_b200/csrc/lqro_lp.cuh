@@ -150,11 +150,43 @@ __global__ void __launch_bounds__(128) k_new_velocity(int batch, int stride, con
   float* pc = planes_c + (size_t)a * stride * 6;
   int n = 0;
   if (status) {
-    for (int s = 0; s < stride; ++s) {
-      if ((status[(size_t)a * stride + s] & 0xff) != 0) {
+    // compaction in slot order.  The statuses of a window of 64 slots are read first (independent, vectorised loads)
+    // into a bit mask, then the planes of the set bits are copied four at a time, so that the thread waits for a
+    // handful of memory round trips instead of one per slot.
+    const int* stp = status + (size_t)a * stride;
+    for (int w0 = 0; w0 < stride; w0 += 64) {
+      const int wn = stride - w0 < 64 ? stride - w0 : 64;
+      unsigned long long valid = 0ull;
+      if ((stride & 3) == 0) {
+        for (int s = 0; s < wn; s += 4) {
+          const int4 q = *reinterpret_cast<const int4*>(stp + w0 + s);
+          valid |= (unsigned long long)(((q.x & 0xff) != 0) | (((q.y & 0xff) != 0) << 1) | (((q.z & 0xff) != 0) << 2) | (((q.w & 0xff) != 0) << 3)) << s;
+        }
+      } else {
+        for (int s = 0; s < wn; ++s) valid |= (unsigned long long)((stp[w0 + s] & 0xff) != 0) << s;
+      }
+      while (valid) {
+        int sl[4];
+        float2 v[4][3];
+        int m = 0;
 #pragma unroll
-        for (int d = 0; d < 6; ++d) pc[6 * n + d] = src[6 * s + d];
-        ++n;
+        for (int q = 0; q < 4; ++q) {
+          sl[q] = valid ? __ffsll((long long)valid) - 1 : -1;
+          if (valid) { valid &= valid - 1; ++m; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (sl[q] >= 0) {
+            const float2* sp = reinterpret_cast<const float2*>(src + 6 * (size_t)(w0 + sl[q]));
+            v[q][0] = sp[0]; v[q][1] = sp[1]; v[q][2] = sp[2];
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (sl[q] >= 0) {
+            float2* dp = reinterpret_cast<float2*>(pc + 6 * (size_t)(n + q));
+            dp[0] = v[q][0]; dp[1] = v[q][1]; dp[2] = v[q][2];
+          }
+        n += m;
       }
     }
   } else {
