@@ -5,7 +5,7 @@ g=np.load('/root/repo/tests/golden/ref_vectors.npz')
 x,vp=swarm.lattice_swarm((64,32,32)); nb=swarm.knn(x[:,:3],64)
 ctx=Lqro(n_agents=65536,max_neighbors=64,horizon=20); ctx.set_dynamics(g['dyn_A'],g['dyn_B'],g['dyn_L'],g['dyn_E'])
 for r in range(3):
-    ctx.step(x,vp,nb)
+    ctx.step(x,vp,nb if r==0 else None)
 print(ctx.last_step_ms(), ctx.counters())
 c=ctx.hull_cycles()
 names=['init','partall','next+horizon+cone','planes+match','list','walk','redo','append','delete','append-old','insertions','repartitioned','maxcycles','maxpts','maxfacets']
