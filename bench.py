@@ -287,6 +287,8 @@ def run_ours(args):
     barrier()
     with torch.cuda.stream(stream):
         for s in range(args.steps):
+            if world > 1:
+                dist.barrier()  # line the ranks up before every timed step: host-side skew is not step time
             flush.zero_()  # L2 flush, outside the per-step events
             ev[s][0].record(stream)
             one_step()
