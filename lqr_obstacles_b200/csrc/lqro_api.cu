@@ -495,7 +495,7 @@ static int launch_knn(lqro_ctx* ctx, const double* d_x, int* d_nbr_out, cudaStre
   k_knn_scatter<<<nb, 256, 0, st>>>(d_x, p.N, ctx->d_knn_cell, ctx->d_knn_start, ctx->d_knn_count, ctx->d_knn_sid, ctx->d_knn_spos);
   const int E = p.K <= 32 ? 1 : p.K <= 64 ? 2 : 4;
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * (32 * E + LQRO_KNN_STAGE) * (sizeof(double) + sizeof(int));
+  const size_t smem = (size_t)wpb * knn_warp_smem_bytes(E);
   const int qb = std::min((p.n_local + wpb - 1) / wpb, 16 * ctx->sm_count);
   if (E == 1) k_knn_query<1><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
   else if (E == 2) k_knn_query<2><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);

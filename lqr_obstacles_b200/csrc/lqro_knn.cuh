@@ -22,6 +22,12 @@
 
 #define LQRO_KNN_MAX_CELLS (1 << 18)
 #define LQRO_KNN_STAGE 32  // extra staging entries beyond one merge batch
+#define LQRO_KNN_FAST_CAP 128  // staging entries of the histogram-seeded fast path
+// shared memory per warp: staging keys (double + int) and the 32-bin histogram
+__host__ __device__ inline size_t knn_warp_smem_bytes(int E) {
+  const int cap = 32 * E + LQRO_KNN_STAGE > LQRO_KNN_FAST_CAP ? 32 * E + LQRO_KNN_STAGE : LQRO_KNN_FAST_CAP;
+  return (size_t)cap * (sizeof(double) + sizeof(int)) + 32 * sizeof(int);
+}
 
 struct KnnGrid {
   double org[3];
@@ -264,16 +270,112 @@ __global__ void __launch_bounds__(128) k_knn_query(const double* __restrict__ x,
   extern __shared__ double knn_smem[];
   const KnnGrid g = *gp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  constexpr int CAP = 32 * E + LQRO_KNN_STAGE;
+  constexpr int CAP = 32 * E + LQRO_KNN_STAGE > LQRO_KNN_FAST_CAP ? 32 * E + LQRO_KNN_STAGE : LQRO_KNN_FAST_CAP;
   KnnStage st;
   st.d = knn_smem + (size_t)warp * CAP;
   st.i = reinterpret_cast<int*>(knn_smem + (size_t)wpb * CAP) + (size_t)warp * CAP;
+  int* hist = reinterpret_cast<int*>(knn_smem + (size_t)wpb * CAP) + (size_t)wpb * CAP + (size_t)warp * 32;
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
   for (int il = blockIdx.x * wpb + warp; il < n_local; il += gridDim.x * wpb) {
     const int i = local_begin + il;
     const double px = x[(size_t)i * LQRO_XD], py = x[(size_t)i * LQRO_XD + 1], pz = x[(size_t)i * LQRO_XD + 2];
     int cx, cy, cz;
     knn_cell_of(g, px, py, pz, cx, cy, cz);
+    // ---- fast path: exact threshold from a histogram of the 3x3x3 block, one collection pass, rank selection.
+    // Pass 1 bins the squared distances of the block's agents (32 bins up to (1.5 h)^2) and takes the first bin
+    // edge T below which at least K other agents lie; if T is inside the distance to the nearest unsearched face,
+    // the K nearest are exactly the K smallest of {dsq < T} -- typically K + a few -- which pass 2 stages in shared
+    // memory; every staged key then counts the keys below it and lands at that position (sorted output, no merge).
+    // Anything unusual (too few agents nearby, too many below T, block not covering T) falls through to the general
+    // shell search below.
+    {
+      const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, g.dim[1] - 1);
+      const int c0 = max(cx - 1, 0), c1 = min(cx + 1, g.dim[0] - 1);
+      const double rm2 = 2.25 * g.h * g.h, inv_w = 32.0 / rm2;
+      hist[lane] = 0;
+      __syncwarp();
+      for (int zz = z0; zz <= z1; ++zz)
+        for (int yy = y0; yy <= y1; ++yy) {
+          const int rowbase = (zz * g.dim[1] + yy) * g.dim[0];
+          const int s0 = start[rowbase + c0], s1 = start[rowbase + c1 + 1];
+          for (int q = s0 + lane; q < s1; q += 32) {
+            const double dx = spos[(size_t)q * 3] - px, dy = spos[(size_t)q * 3 + 1] - py, dz = spos[(size_t)q * 3 + 2] - pz;
+            const double dsq = dx * dx + dy * dy + dz * dz;
+            if (sid[q] != i) { const double b = dsq * inv_w; atomicAdd(&hist[b < 31.0 ? (int)b : 31], 1); }
+          }
+        }
+      __syncwarp();
+      int cum = hist[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(LQRO_FULL, cum, off);
+        if (lane >= off) cum += t;
+      }
+      const unsigned reach = __ballot_sync(LQRO_FULL, cum >= K) & 0x7fffffffu;  // bin 31 is the catch-all
+      bool done = false;
+      if (reach) {
+        const int B = __ffs(reach) - 1;
+        // dsq * inv_w < B + 1 up to one rounding  =>  dsq < T
+        const double T = (double)(B + 1) * (rm2 / 32.0) * (1.0 + 1.0e-12);
+        double cov = INF;  // distance to the nearest face of the block with cells behind it
+        if (cx - 1 > 0) cov = fmin(cov, px - (g.org[0] + (double)(cx - 1) * g.h));
+        if (cx + 1 < g.dim[0] - 1) cov = fmin(cov, (g.org[0] + (double)(cx + 2) * g.h) - px);
+        if (cy - 1 > 0) cov = fmin(cov, py - (g.org[1] + (double)(cy - 1) * g.h));
+        if (cy + 1 < g.dim[1] - 1) cov = fmin(cov, (g.org[1] + (double)(cy + 2) * g.h) - py);
+        if (cz - 1 > 0) cov = fmin(cov, pz - (g.org[2] + (double)(cz - 1) * g.h));
+        if (cz + 1 < g.dim[2] - 1) cov = fmin(cov, (g.org[2] + (double)(cz + 2) * g.h) - pz);
+        const double safe = cov * (1.0 - 1.0e-9) - 1.0e-9 * g.h;
+        if (cov == INF || (safe > 0 && T < safe * safe)) {
+          int c = 0;
+          bool fits = true;
+          for (int zz = z0; zz <= z1 && fits; ++zz)
+            for (int yy = y0; yy <= y1 && fits; ++yy) {
+              const int rowbase = (zz * g.dim[1] + yy) * g.dim[0];
+              const int s0 = start[rowbase + c0], s1 = start[rowbase + c1 + 1];
+              for (int b0 = s0; b0 < s1; b0 += 32) {
+                const int q = b0 + lane;
+                bool keep = false;
+                double dsq = 0;
+                int j = 0;
+                if (q < s1) {
+                  j = sid[q];
+                  const double dx = spos[(size_t)q * 3] - px, dy = spos[(size_t)q * 3 + 1] - py, dz = spos[(size_t)q * 3 + 2] - pz;
+                  dsq = dx * dx + dy * dy + dz * dz;
+                  keep = j != i && dsq < T;
+                }
+                const unsigned m = __ballot_sync(LQRO_FULL, keep);
+                if (c + __popc(m) > LQRO_KNN_FAST_CAP) { fits = false; break; }
+                if (keep) { const int pos = c + __popc(m & ((1u << lane) - 1u)); st.d[pos] = dsq; st.i[pos] = j; }
+                c += __popc(m);
+              }
+            }
+          __syncwarp();
+          if (fits && c >= K) {
+            // rank selection: entry e = lane + 32 t; its rank = number of staged keys below it
+            double md[LQRO_KNN_FAST_CAP / 32];
+            int mi[LQRO_KNN_FAST_CAP / 32], rk[LQRO_KNN_FAST_CAP / 32];
+#pragma unroll
+            for (int t = 0; t < LQRO_KNN_FAST_CAP / 32; ++t) {
+              const int e = lane + 32 * t;
+              md[t] = e < c ? st.d[e] : INF; mi[t] = e < c ? st.i[e] : 0x7fffffff; rk[t] = 0;
+            }
+            for (int u = 0; u < c; ++u) {
+              const double od = st.d[u];
+              const int oi = st.i[u];
+#pragma unroll
+              for (int t = 0; t < LQRO_KNN_FAST_CAP / 32; ++t) rk[t] += knn_less(od, oi, md[t], mi[t]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int t = 0; t < LQRO_KNN_FAST_CAP / 32; ++t)
+              if (lane + 32 * t < c && rk[t] < K) nbr_out[(size_t)il * K + rk[t]] = mi[t];
+            done = true;
+          }
+          __syncwarp();
+        }
+      }
+      if (done) continue;
+    }
+    // ---- general path: shells of cells of growing radius
     KnnTop<E> top;
 #pragma unroll
     for (int j = 0; j < E; ++j) { top.d[j] = INF; top.i[j] = 0x7fffffff; }
