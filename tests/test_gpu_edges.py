@@ -141,3 +141,25 @@ def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
     v3 = a.step(x, vp, nbr)                 # and again chunked, after a plain step
     assert np.array_equal(v3, v1)
     a.close()
+
+
+@pytest.mark.parametrize("H,P", [(12, 32), (25, 40), (7, 64), (20, 50), (30, 50)])
+def test_other_horizons_and_sample_counts(golden, oracle, product_lib, H, P):
+    """(H, P) = (20, 50) and (30, 50) run kernels specialised at compile time, everything else the generic ones:
+    each against the oracle with the same H and P, hull branch included"""
+    x, vp = _tight_swarm()
+    N, K = len(x), 10
+    nbr = swarm.knn(x[:, :3], K)
+    ctx = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=H, n_samples=P)
+    v = ctx.step(x, vp, nbr)
+    res = ctx.pair_results()
+    NF, T, sph = ctx.tables()
+    oNF, oT, _ = oracle.horizon(golden["dyn_A"], golden["dyn_B"], golden["dyn_L"], golden["dyn_E"], H)
+    assert np.array_equal(T, oT) and np.array_equal(sph, oracle.spheres(P))
+    ov, opl, ost, _ = oracle.step(NF, T, sph, x, vp, nbr, nthreads=4)
+    st = res["status"] & 0xFF
+    assert np.array_equal(st, ost & 0xFF)
+    assert np.array_equal(res["planes"][st != 0], opl[st != 0])
+    assert np.array_equal(v, ov)
+    assert (st == 2).sum() >= 1 or H < 20   # short horizons see no inside pair in this swarm
+    ctx.close()
