@@ -7,11 +7,12 @@
 // the geometry: same subset order, same delta recursion, same operation order, no FMA.
 //
 // Mapping: one warp per pair.  The support scan over the cloud (the only O(n) part) is spread over
-// the 32 lanes and reduced with shuffles to (max value, lowest index) -- the reference's strict '>'
-// scan (GJK.c:786) keeps the lowest index on ties.  The simplex sub-algorithm (Johnson's deltas over
-// <= 15 subsets) is scalar work; every lane runs it redundantly on REGISTER-resident state: the subset
-// loops are templates on the simplex size and fully unrolled, so the delta / dot-product tables of
-// GJK.c:163-164 never touch memory and no lane waits for another.
+// the 32 lanes and reduced to (max value, lowest index) -- the reference's strict '>' scan (GJK.c:786)
+// keeps the lowest index on ties -- with three REDUX operations on order-preserving keys.  The simplex
+// sub-algorithm (Johnson's deltas over <= 15 subsets) runs LANE-PARALLEL by default (gjk_warp_lanes: one
+// (subset, element) pair per lane, see below).  The older scalar version (gjk_warp: every lane runs it
+// redundantly on register-resident state, subset loops templated on the simplex size and fully unrolled)
+// is kept behind LQRO_GJK_LANES=0 as the ablation it was measured against; both are bit-identical.
 #pragma once
 #include "lqro_common.cuh"
 
