@@ -75,3 +75,17 @@ def test_reference_scenarios(reference, golden, product_lib, n, steps):
     print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d" % (n, steps, err, ir, ig, ev))
     assert ir == ig
     assert err <= 1e-6
+
+
+@pytest.mark.parametrize("n,radius,steps", [(32, 12.0, 60), (64, 24.0, 25)])
+def test_large_reference_scenarios(reference, golden, product_lib, n, radius, steps):
+    """BASELINE configs 32 and 64 quads (the repo holds no initial conditions for them: circle-antipodal sets of radius
+    12 / 24 m); K = N-1 as in the reference, its own H = 30"""
+    from lqr_obstacles_b200.swarm import circle_antipodal
+
+    S, G = circle_antipodal(n, radius)
+    tr, tg, ir, ig, ev = run_pair(reference, golden, S, G, steps)
+    err = np.abs(tr[:, :, :3] - tg[:, :, :3]).max()
+    print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d" % (n, steps, err, ir, ig, ev))
+    assert ir == ig
+    assert err <= 1e-6
