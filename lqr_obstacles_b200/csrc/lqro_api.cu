@@ -617,8 +617,14 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
                                                       ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
-  k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,
-                                                          ctx->d_planes_c, ctx->d_proj, d_newV, ctx->d_nplanes);
+  if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
+    // few agents: one warp per agent (the reference's own scenarios are dense: O(K^2) with the inner loops spread over the lanes)
+    k_new_velocity_warp<<<(p.n_local + 3) / 4, 128, (size_t)4 * 12 * p.K * sizeof(float), st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, d_vpref,
+                                                                                                 p.lp_radius, d_newV, ctx->d_nplanes);
+  } else {
+    k_new_velocity<<<(p.n_local + 127) / 128, 128, 0, st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, nullptr, d_vpref, p.lp_radius,
+                                                            ctx->d_planes_c, ctx->d_proj, d_newV, ctx->d_nplanes);
+  }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
   ctx->launches = ctx->launches_extra ? 2 + ctx->launches_extra : 3;
