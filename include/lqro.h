@@ -180,6 +180,49 @@ int lqro_get_neighbors(lqro_ctx* ctx, int* nbr);
 /* printf("%g")/strtod round trip of MAIN:765-767 applied to n doubles on the device. */
 int lqro_round6(lqro_ctx* ctx, const double* in, int n, double* out);
 
+/* ---- simulator-form agent update: the second loop of the reference's time step ------------ */
+
+/* What the reference keeps in globals (MAIN:40-76; values set in setup() MAIN:176-198 and _tmain MAIN:1126-1140) and in
+ * every Quadrotor (gains, MAIN:95-99).  Row-major FP64. */
+typedef struct lqro_sim_model {
+  double dt, gravity, mass, moment_const, thrust_latency, length, jstep;
+  double inertia[9], inv_inertia[9];
+  double u_goal[4];                              /* uGoal = nominalInput x 4 (MAIN:1126-1127) */
+  double L[64], E[12], l[4], Lh[48], Eh[9];      /* controlMatrices outputs (MAIN:490-544) */
+  double M[256], N[36];                          /* motion / observation noise covariances (MAIN:1139-1140) */
+} lqro_sim_model;
+/* Fills the reference's constants (setup(), MAIN:176-198; M = N = 1e-9 I); gains are zeroed: copy L, E, l, Lh, Eh in
+ * (from lqro_solve_gains or the caller's controlMatrices). */
+void lqro_sim_default_model(lqro_sim_model* m);
+int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m);
+
+/* Replaces, for n agents at once, the loop body MAIN:1409-1416:
+ *     vGoal = newV; u = findU(); propagateU(u); kalmanFilter1(x, Rot, u, M, P);
+ *     z = sampleGaussian(h(xTrue, RotTrue), N); kalmanFilter2(x, Rot, z, N, P); vGoal = findVGoal();
+ * (riccatiControllerSteady MAIN:547-576, propagate MAIN:442-455, kalmanFilter1/2 MAIN:457-487,
+ * riccatiControllerSteadyPosition MAIN:579-608), one warp per agent.  HOST pointers, updated in place:
+ *   x n*16 estimate, Rot n*9, P n*256 covariance, xTrue n*16, RotTrue n*9 (Quadrotor::x, Rot, P, xTrue, RotTrue)
+ *   newV n*3 (calculateNewV's output), pGoal n*3 (Quadrotor::pGoal)
+ *   normals n*22: the standard normals the reference's sampleGaussian calls draw for agent i, in its order -- 16 for
+ *           propagate's process noise (MAIN:450), then 6 for the observation (MAIN:1413); see lqro_msvc_normals
+ *   vGoal n*3 out (next preferred velocity), u n*4 out (control input; may be NULL) */
+int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue,
+                    const double* newV, const double* pGoal, const double* normals, double* vGoal, double* u);
+/* Same with DEVICE pointers, asynchronous on the context's stream (or `stream`).  d_x may be the context's own state
+ * buffer (lqro_device_state), d_newV the d_newV of lqro_step_device and d_vGoal its d_vpref for the next step, so that a
+ * whole time step stays on the device. */
+int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue,
+                           const double* d_newV, const double* d_pGoal, const double* d_normals, double* d_vGoal, double* d_u,
+                           void* stream);
+/* Host helper, no device work: `count` draws of the reference's normal() (MAIN:325-336) from the MSVC CRT rand() stream
+ * it was written against (RAND_MAX 32767, seed*214013+2531011; random() MAIN:320-322).  *seed_io: generator state in,
+ * state out (srand(1) at program start => 1).  The stream is sequential across agents, which is why the noise is an
+ * input of lqro_sim_update rather than generated on the device. */
+int lqro_msvc_normals(unsigned int* seed_io, int count, double* out);
+/* Device time (ms) of the last lqro_sim_update / lqro_sim_update_device kernel (CUDA events on the launching stream;
+ * synchronises). */
+int lqro_sim_last_ms(lqro_ctx* ctx, float* ms);
+
 /* ---- multi-GPU: agents partitioned, one all-gather of the state per step --------------------- */
 
 /* 128-byte NCCL unique id (rank 0 creates it, the caller ships it to the other ranks). */

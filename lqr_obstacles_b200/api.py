@@ -40,7 +40,51 @@ EXPORTS = [
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
     "lqro_debug_hull_cycles", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
+    "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
+    "lqro_sim_last_ms",
 ]
+
+
+class SimModel(ctypes.Structure):
+    """lqro_sim_model: the reference's world / quadrotor globals (MAIN:40-76, 176-198), gains and noise covariances."""
+    _fields_ = [
+        ("dt", c_double), ("gravity", c_double), ("mass", c_double), ("moment_const", c_double), ("thrust_latency", c_double),
+        ("length", c_double), ("jstep", c_double), ("inertia", c_double * 9), ("inv_inertia", c_double * 9),
+        ("u_goal", c_double * 4), ("L", c_double * 64), ("E", c_double * 12), ("l", c_double * 4), ("Lh", c_double * 48),
+        ("Eh", c_double * 9), ("M", c_double * 256), ("N", c_double * 36),
+    ]
+
+    def as_array(self):
+        return np.frombuffer(bytes(self), dtype=np.float64).copy()
+
+    @classmethod
+    def from_array(cls, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.size * 8 == ctypes.sizeof(cls)
+        return cls.from_buffer_copy(a.tobytes())
+
+
+def sim_default_model(L=None, E=None, Lh=None, Eh=None, l=None):
+    """setup() constants (MAIN:176-198), M = N = 1e-9 I, plus the given gains."""
+    lib = load_library()
+    m = SimModel()
+    lib.lqro_sim_default_model(ctypes.byref(m))
+    for name, val in (("L", L), ("E", E), ("Lh", Lh), ("Eh", Eh), ("l", l)):
+        if val is not None:
+            v = np.ascontiguousarray(val, dtype=np.float64).ravel()
+            getattr(m, name)[:] = list(v)
+    return m
+
+
+def msvc_normals(seed, count):
+    """`count` draws of the reference's normal() (MAIN:325-336) from MSVC rand() state `seed`; returns (normals, new seed)."""
+    lib = load_library()
+    s = ctypes.c_uint(seed)
+    out = np.zeros(count)
+    rc = lib.lqro_msvc_normals(ctypes.byref(s), count, _p(out))
+    if rc != 0:
+        raise LqroError("lqro_msvc_normals failed (%d)" % rc)
+    return out, s.value
 
 
 def load_library(path=None):
@@ -87,6 +131,13 @@ def load_library(path=None):
     lib.lqro_measure_fp32_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_hull_cycles.argtypes = [c_void_p, c_void_p]
+    lib.lqro_sim_default_model.argtypes = [ctypes.POINTER(SimModel)]
+    lib.lqro_sim_default_model.restype = None
+    lib.lqro_sim_set_model.argtypes = [c_void_p, ctypes.POINTER(SimModel)]
+    lib.lqro_sim_update.argtypes = [c_void_p, c_int] + [c_void_p] * 10
+    lib.lqro_sim_update_device.argtypes = [c_void_p, c_int] + [c_void_p] * 11
+    lib.lqro_msvc_normals.argtypes = [ctypes.POINTER(ctypes.c_uint), c_int, c_void_p]
+    lib.lqro_sim_last_ms.argtypes = [c_void_p, ctypes.POINTER(c_float)]
     if path == _build.SO:
         _lib = lib
     return lib
@@ -192,6 +243,32 @@ class Lqro:
         nfac = np.zeros((self.NL, self.K), dtype=np.int32)
         self._ck(self.lib.lqro_get_pair_results(self.h, _p(planes), _p(status), _p(nreach), _p(dist), _p(nfac)))
         return dict(planes=planes, status=status, nreach=nreach, dist=dist, nfacets=nfac)
+
+    # -- simulator-form agent update (MAIN:1408-1417)
+    def sim_set_model(self, model):
+        self._ck(self.lib.lqro_sim_set_model(self.h, ctypes.byref(model)))
+
+    def sim_update(self, x, Rot, P, xTrue, RotTrue, newV, pGoal, normals):
+        """In place on x (n,16), Rot (n,9), P (n,256), xTrue (n,16), RotTrue (n,9); returns (vGoal (n,3), u (n,4))."""
+        n = len(x)
+        for a in (x, Rot, P, xTrue, RotTrue):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        newV, pGoal, normals = f(newV), f(pGoal), f(normals)
+        assert normals.size == 22 * n
+        vGoal, u = np.zeros((n, 3)), np.zeros((n, 4))
+        self._ck(self.lib.lqro_sim_update(self.h, n, _p(x), _p(Rot), _p(P), _p(xTrue), _p(RotTrue), _p(newV), _p(pGoal), _p(normals),
+                                          _p(vGoal), _p(u)))
+        return vGoal, u
+
+    def sim_update_device(self, n, d_x, d_Rot, d_P, d_xTrue, d_RotTrue, d_newV, d_pGoal, d_normals, d_vGoal, d_u=None, stream=None):
+        self._ck(self.lib.lqro_sim_update_device(self.h, n, _p(d_x), _p(d_Rot), _p(d_P), _p(d_xTrue), _p(d_RotTrue), _p(d_newV),
+                                                 _p(d_pGoal), _p(d_normals), _p(d_vGoal), _p(d_u), stream))
+
+    def sim_last_ms(self):
+        ms = c_float()
+        self._ck(self.lib.lqro_sim_last_ms(self.h, ctypes.byref(ms)))
+        return ms.value
 
     def counters(self):
         c = np.zeros(6, dtype=np.int64)

@@ -22,6 +22,7 @@
 #include "lqro_knn.cuh"
 #include "lqro_lp.cuh"
 #include "lqro_riccati.cuh"
+#include "lqro_sim.cuh"
 
 // ---- minimal NCCL surface, resolved at run time (no link-time dependency; the process may already
 //      hold a libnccl, e.g. the one bundled with PyTorch) ------------------------------------------
@@ -107,6 +108,10 @@ struct lqro_ctx {
   char* d_stage_ws = nullptr; int stage_ws_pts = 0;
   // multi-GPU
   lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
+  // simulator-form agent update (lqro_sim.cuh)
+  LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false;
+  char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
+  cudaEvent_t ev_sim[2] = {nullptr, nullptr};
   long long launches = 0;
   int launches_extra = 0;
   std::string err;
@@ -176,6 +181,8 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
     void* q[] = {ctx->cls[c].NFt, ctx->cls[c].NF, ctx->cls[c].T, ctx->cls[c].CG, ctx->cls[c].prn};
     for (void* p : q) if (p) cudaFree(p);
   }
+  { void* q[] = {ctx->d_sim_model, ctx->d_sim_buf}; for (void* p : q) if (p) cudaFree(p); }
+  for (cudaEvent_t e : ctx->ev_sim) if (e) cudaEventDestroy(e);
   { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr, ctx->d_identity, ctx->d_chunk_ctr}; for (void* p : q) if (p) cudaFree(p); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
@@ -708,6 +715,143 @@ extern "C" int lqro_get_counters(lqro_ctx* ctx, long long* out6) {
   out6[3] = c[3];
   out6[4] = c[1] > ctx->hull_cap ? c[1] - ctx->hull_cap : 0;
   out6[5] = ctx->launches;
+  return LQRO_OK;
+}
+
+// ---- simulator-form agent update (lqro_sim.cuh) -----------------------------------------------
+static_assert(sizeof(lqro_sim_model) == sizeof(LqroSimModel), "lqro_sim_model and LqroSimModel must have one layout");
+
+extern "C" void lqro_sim_default_model(lqro_sim_model* m) {  // setup(), MAIN:176-198; M, N MAIN:1139-1140
+  memset(m, 0, sizeof *m);
+  m->dt = 1.0 / 30.0;
+  m->gravity = 9.80665;
+  m->mass = 0.500;
+  m->moment_const = 1.5e-9 / 6.11e-8;
+  m->thrust_latency = 40.0;
+  m->length = 0.3429 / 2;
+  m->jstep = 0.0009765625;
+  // inertia = 0.1*identity<3>(); invInertia = !inertia (full-pivot Gauss of a diagonal matrix: 1/0.1 on the diagonal)
+  for (int i = 0; i < 3; ++i) { m->inertia[4 * i] = 1.0 * 0.1; m->inv_inertia[4 * i] = 1.0 / (1.0 * 0.1); }
+  const double nominal = m->gravity * m->mass / 4;
+  for (int i = 0; i < 4; ++i) m->u_goal[i] = nominal;
+  for (int i = 0; i < 16; ++i) m->M[17 * i] = 1.0 * 0.000000001;
+  for (int i = 0; i < 6; ++i) m->N[7 * i] = 1.0 * 0.000000001;
+}
+
+extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
+  if (!ctx || !m) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->d_sim_model) CU(cudaMalloc(&ctx->d_sim_model, sizeof(LqroSimModel)));
+  CU(cudaMemcpyAsync(ctx->d_sim_model, m, sizeof(LqroSimModel), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_sim_model = true;
+  return LQRO_OK;
+}
+
+static const int kSimWarps = 4;
+static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
+                             const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
+  const size_t smem = sizeof(LqroSimModel) + (size_t)kSimWarps * sizeof(LqroSimWs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_sim_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (!ctx->ev_sim[0]) { CU(cudaEventCreate(&ctx->ev_sim[0])); CU(cudaEventCreate(&ctx->ev_sim[1])); }
+  int blocks = (n + kSimWarps - 1) / kSimWarps;
+  const int cap = ctx->sm_count * 2;  // two resident CTAs per SM (2 x 99.6 KB of shared memory); grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  CU(cudaEventRecord(ctx->ev_sim[0], st));
+  k_sim_update<<<blocks, kSimWarps * 32, smem, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, newV, pGoal, normals, vGoal, u);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_sim[1], st));
+  ctx->launches_extra++;
+  return LQRO_OK;
+}
+
+extern "C" int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue,
+                                      const double* d_newV, const double* d_pGoal, const double* d_normals, double* d_vGoal, double* d_u,
+                                      void* stream) {
+  if (!ctx || n < 0 || !d_x || !d_Rot || !d_P || !d_xTrue || !d_RotTrue || !d_newV || !d_pGoal || !d_normals || !d_vGoal)
+    return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_sim_model) return fail(ctx, LQRO_E_STATE, "lqro_sim_set_model first");
+  if (n == 0) return LQRO_OK;
+  CU(cudaSetDevice(ctx->cfg.device));
+  return launch_sim_update(ctx, n, d_x, d_Rot, d_P, d_xTrue, d_RotTrue, d_newV, d_pGoal, d_normals, d_vGoal, d_u,
+                           stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
+                               const double* pGoal, const double* normals, double* vGoal, double* u) {
+  if (!ctx || n < 0 || !x || !Rot || !P || !xTrue || !RotTrue || !newV || !pGoal || !normals || !vGoal) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_sim_model) return fail(ctx, LQRO_E_STATE, "lqro_sim_set_model first");
+  if (n == 0) return LQRO_OK;
+  CU(cudaSetDevice(ctx->cfg.device));
+  // one device block: x 16 | Rot 9 | P 256 | xTrue 16 | RotTrue 9 | newV 3 | pGoal 3 | normals 22 | vGoal 3 | u 4  (doubles per agent)
+  const size_t per = 16 + 9 + 256 + 16 + 9 + 3 + 3 + 22 + 3 + 4;
+  const size_t need = sizeof(double) * per * (size_t)n;
+  if (ctx->sim_buf_bytes < need) {
+    if (ctx->d_sim_buf) cudaFree(ctx->d_sim_buf);
+    ctx->d_sim_buf = nullptr; ctx->sim_buf_bytes = 0;
+    CU(cudaMalloc(&ctx->d_sim_buf, need));
+    ctx->sim_buf_bytes = need;
+  }
+  double* b = (double*)ctx->d_sim_buf;
+  const size_t N = (size_t)n;
+  double *dx = b, *dR = dx + 16 * N, *dP = dR + 9 * N, *dxT = dP + 256 * N, *dRT = dxT + 16 * N, *dnV = dRT + 9 * N, *dpG = dnV + 3 * N,
+         *dnr = dpG + 3 * N, *dvG = dnr + 22 * N, *du = dvG + 3 * N;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(dx, x, 8 * 16 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dR, Rot, 8 * 9 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dP, P, 8 * 256 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dxT, xTrue, 8 * 16 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dRT, RotTrue, 8 * 9 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dnV, newV, 8 * 3 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dpG, pGoal, 8 * 3 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dnr, normals, 8 * 22 * N, cudaMemcpyHostToDevice, st));
+  int rc = launch_sim_update(ctx, n, dx, dR, dP, dxT, dRT, dnV, dpG, dnr, dvG, du, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(x, dx, 8 * 16 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(Rot, dR, 8 * 9 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(P, dP, 8 * 256 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(xTrue, dxT, 8 * 16 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(RotTrue, dRT, 8 * 9 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(vGoal, dvG, 8 * 3 * N, cudaMemcpyDeviceToHost, st));
+  if (u) CU(cudaMemcpyAsync(u, du, 8 * 4 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_sim_last_ms(lqro_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return LQRO_E_ARG;
+  if (!ctx->ev_sim[0]) return fail(ctx, LQRO_E_STATE, "no simulator update yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaEventSynchronize(ctx->ev_sim[1]));
+  CU(cudaEventElapsedTime(ms, ctx->ev_sim[0], ctx->ev_sim[1]));
+  return LQRO_OK;
+}
+
+// Host only: the reference's normal() (MAIN:325-336) over the MSVC CRT generator it was written for.
+extern "C" int lqro_msvc_normals(unsigned int* seed_io, int count, double* out) {
+  if (!seed_io || count < 0 || (count && !out)) return LQRO_E_ARG;
+  unsigned int seed = *seed_io;
+  auto rnd = [&seed]() -> int { seed = seed * 214013u + 2531011u; return (int)((seed >> 16) & 0x7fff); };
+  const int RM = 32767;
+  auto uniform = [&]() -> double {  // random(), MAIN:320-322: integer arithmetic, then one division
+    const int a = rnd();
+    const int b = rnd();
+    return (double)(a * (RM + 1) + b) / (RM * (RM + 2));
+  };
+  for (int i = 0; i < count; ++i) {
+    double u = 0, v = 0, s = 0;
+    while (s == 0 || s > 1) {
+      u = 2 * uniform() - 1;
+      v = 2 * uniform() - 1;
+      s = u * u + v * v;
+    }
+    out[i] = u * sqrt(-2 * log(s) / s);
+  }
+  *seed_io = seed;
   return LQRO_OK;
 }
 

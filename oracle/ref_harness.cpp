@@ -542,3 +542,53 @@ extern "C" int ref_run_tmain(void) {
   g_inited = true;   // setup() ran and the weights are the _tmain ones
   return rc;
 }
+
+// ---------------------------------------------------------------- simulator-form update parity
+extern "C" unsigned int ref_get_seed(void) { return g_msvc_seed; }
+// `count` draws of the reference's own normal() (MAIN:325-336) from the current stream position
+extern "C" void ref_normals(int count, double* out) { for (int i = 0; i < count; ++i) out[i] = normal(); }
+// full per-agent state in / out (any pointer may be 0)
+extern "C" void ref_sim_set_state(void* h, const double* x, const double* xTrue, const double* Rot, const double* RotTrue,
+                                  const double* P) {
+  RefSim* s = (RefSim*)h;
+  for (int i = 0; i < s->n; ++i) {
+    if (x) to_mat(x + 16 * i, s->q[i]->x);
+    if (xTrue) to_mat(xTrue + 16 * i, s->q[i]->xTrue);
+    if (Rot) to_mat(Rot + 9 * i, s->q[i]->Rot);
+    if (RotTrue) to_mat(RotTrue + 9 * i, s->q[i]->RotTrue);
+    if (P) to_mat(P + 256 * i, s->q[i]->P);
+  }
+}
+extern "C" void ref_sim_get_goals(void* h, double* pGoal, double* newV) {
+  RefSim* s = (RefSim*)h;
+  for (int i = 0; i < s->n; ++i) {
+    if (pGoal) from_mat(s->q[i]->pGoal, pGoal + 3 * i);
+    if (newV) from_mat(s->q[i]->newV, newV + 3 * i);
+  }
+}
+// The reference's globals and quad 0's gains in the layout of lqro_sim_model (include/lqro.h): 458 doubles
+extern "C" int ref_sim_model(void* h, double* out) {
+  RefSim* s = (RefSim*)h;
+  double* p = out;
+  *p++ = dt; *p++ = gravity; *p++ = mass; *p++ = momentConst; *p++ = thrust_latency; *p++ = length_; *p++ = jStep;
+  from_mat(inertia, p); p += 9;
+  from_mat(invInertia, p); p += 9;
+  from_mat(s->q[0]->uGoal, p); p += 4;
+  from_mat(s->q[0]->L, p); p += 64;
+  from_mat(s->q[0]->E, p); p += 12;
+  from_mat(s->q[0]->l, p); p += 4;
+  from_mat(s->q[0]->Lh, p); p += 48;
+  from_mat(s->q[0]->Eh, p); p += 9;
+  from_mat(M, p); p += 256;
+  from_mat(N, p); p += 36;
+  return (int)(p - out);
+}
+// Stage-level entry points on explicit arguments (unit parity of the pieces of the update)
+extern "C" void ref_exp16(const double* q, double* out) { Matrix<16, 16> m; to_mat(q, m); from_mat(exp(m), out); }
+extern "C" void ref_exp3(const double* q, double* out) { Matrix<3, 3> m; to_mat(q, m); from_mat(exp(m), out); }
+extern "C" void ref_jacobi16(const double* q, double* V, double* D) {
+  Matrix<16, 16> m, v, d; to_mat(q, m); jacobi(m, v, d); from_mat(v, V); from_mat(d, D);
+}
+extern "C" void ref_f(const double* x, const double* Rot, const double* u, double* xdot) {
+  State xs; Rotation R; Input us; to_mat(x, xs); to_mat(Rot, R); to_mat(u, us); from_mat(f(xs, R, us), xdot);
+}

@@ -203,6 +203,15 @@ class Reference:
         lib.ref_sim_set_fix_facet0.argtypes = [c_int]
         lib.ref_step_agents.restype = ctypes.c_long
         lib.ref_step_agents.argtypes = [c_void_p] * 8 + [c_int, c_int, c_int, c_double, c_void_p, c_void_p]
+        lib.ref_get_seed.restype = ctypes.c_uint
+        lib.ref_normals.argtypes = [c_int, c_void_p]
+        lib.ref_sim_set_state.argtypes = [c_void_p] * 6
+        lib.ref_sim_get_goals.argtypes = [c_void_p] * 3
+        lib.ref_sim_model.argtypes = [c_void_p, c_void_p]
+        for name in ("ref_exp16", "ref_exp3"):
+            getattr(lib, name).argtypes = [c_void_p, c_void_p]
+        lib.ref_jacobi16.argtypes = [c_void_p] * 3
+        lib.ref_f.argtypes = [c_void_p] * 4
         self._tmp = workdir or tempfile.mkdtemp(prefix="lqro_ref_")
         lib.ref_chdir(self._tmp.encode())
         lib.ref_init()
@@ -358,6 +367,66 @@ class RefSim:
     def update(self):
         self.lib.ref_sim_update(self.h)
 
+    # -- simulator-form update parity
+    def full_state(self):
+        """dict of x, xTrue (n,16), vGoal (n,3), Rot, RotTrue (n,9), P (n,256), pGoal, newV (n,3)"""
+        n = self.n
+        d = dict(x=np.zeros((n, 16)), xTrue=np.zeros((n, 16)), vGoal=np.zeros((n, 3)), Rot=np.zeros((n, 9)),
+                 RotTrue=np.zeros((n, 9)), P=np.zeros((n, 256)), pGoal=np.zeros((n, 3)), newV=np.zeros((n, 3)))
+        self.lib.ref_sim_get(self.h, P(d["x"]), P(d["xTrue"]), P(d["vGoal"]), P(d["Rot"]), P(d["RotTrue"]), P(d["P"]))
+        self.lib.ref_sim_get_goals(self.h, P(d["pGoal"]), P(d["newV"]))
+        return d
+
+    def set_state(self, x=None, xTrue=None, Rot=None, RotTrue=None, Pcov=None):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+        x, xTrue, Rot, RotTrue, Pcov = f(x), f(xTrue), f(Rot), f(RotTrue), f(Pcov)
+        self.lib.ref_sim_set_state(self.h, P(x), P(xTrue), P(Rot), P(RotTrue), P(Pcov))
+
+    def model(self):
+        """the reference's globals + quad 0's gains as the 458 doubles of lqro_sim_model"""
+        out = np.zeros(458)
+        k = self.lib.ref_sim_model(self.h, P(out))
+        assert k == 458
+        return out
+
+    def seed(self):
+        return self.lib.ref_get_seed()
+
 
 def have_reference():
     return os.path.exists(REF_SO) or os.path.isdir(REFERENCE_TREE)
+
+
+SIMHOST_SRC = os.path.join(ROOT, "tests", "sim_host", "sim_host.cpp")
+SIMHOST_SO = os.path.join(ROOT, "tests", "sim_host", "libsimhost.so")
+SIM_KERNEL_SRC = os.path.join(ROOT, "lqr_obstacles_b200", "csrc", "lqro_sim.cuh")
+
+
+class SimHost:
+    """The kernel source csrc/lqro_sim.cuh compiled as plain C++ (one sequential lane): checks the LOGIC of the
+    simulator-form update kernel where no GPU exists.  Test infrastructure; the product never links it."""
+
+    def __init__(self):
+        if (not os.path.exists(SIMHOST_SO)
+                or os.path.getmtime(SIMHOST_SO) < max(os.path.getmtime(SIMHOST_SRC), os.path.getmtime(SIM_KERNEL_SRC))):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-std=c++14", "-shared",
+                                   "-o", SIMHOST_SO, SIMHOST_SRC])
+        self.lib = lib = ctypes.CDLL(SIMHOST_SO)
+        lib.simhost_update.argtypes = [c_int] + [c_void_p] * 11
+        lib.simhost_exp16.argtypes = [c_void_p] * 2
+        lib.simhost_exp3.argtypes = [c_void_p] * 2
+        lib.simhost_jacobi16.argtypes = [c_void_p] * 3
+        lib.simhost_f.argtypes = [c_void_p] * 5
+
+    def update(self, model, st, newV, normals):
+        """st: dict as RefSim.full_state(); returns the updated copy (+ vGoal, u)"""
+        o = {k: np.array(st[k], dtype=np.float64, copy=True) for k in ("x", "Rot", "P", "xTrue", "RotTrue")}
+        n = len(o["x"])
+        o["vGoal"], o["u"] = np.zeros((n, 3)), np.zeros((n, 4))
+        model = np.ascontiguousarray(model, dtype=np.float64)
+        newV = np.ascontiguousarray(newV, dtype=np.float64)
+        pGoal = np.ascontiguousarray(st["pGoal"], dtype=np.float64)
+        normals = np.ascontiguousarray(normals, dtype=np.float64)
+        self.lib.simhost_update(n, P(model), P(o["x"]), P(o["Rot"]), P(o["P"]), P(o["xTrue"]), P(o["RotTrue"]), P(newV), P(pGoal),
+                                P(normals), P(o["vGoal"]), P(o["u"]))
+        return o

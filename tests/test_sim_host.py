@@ -1,0 +1,141 @@
+"""Simulator-form agent update (MAIN:1408-1417) -- CPU-side checks.
+
+The kernel source csrc/lqro_sim.cuh also compiles as plain C++ (tests/sim_host); that build must agree BIT FOR BIT with
+the compiled reference (all arithmetic in the reference's order, the same libm), which pins the kernel's logic without a
+GPU.  The GPU parity proper is tests/test_gpu_sim.py (1e-9: CUDA's tan/asin/atan2/log/hypot differ from glibc's in the
+last bit).  Also here: lqro_msvc_normals against the reference's normal(), the default model against the reference's
+globals, the golden fixture against the reference."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from _libs import P, RefSim, SimHost
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ("x", "Rot", "P", "xTrue", "RotTrue", "vGoal")
+
+
+@pytest.fixture(scope="module")
+def sim_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "sim_update.npz"))
+
+
+@pytest.fixture(scope="module")
+def simhost():
+    return SimHost()
+
+
+def _before(g, t):
+    return {k: g["s%d_before_%s" % (t, k)] for k in ("x", "Rot", "P", "xTrue", "RotTrue", "pGoal")}
+
+
+def test_host_build_of_the_kernel_reproduces_the_golden_updates_bit_for_bit(sim_golden, simhost):
+    g = sim_golden
+    for t in g["record_steps"]:
+        o = simhost.update(g["model"], _before(g, t), g["s%d_newV" % t], g["s%d_normals" % t])
+        for k in KEYS:
+            assert np.array_equal(o[k], g["s%d_after_%s" % (t, k)]), (int(t), k)
+
+
+def test_stage_pieces_match_the_reference_bit_for_bit(reference, simhost):
+    rng = np.random.default_rng(7)
+    lib, sh = reference.lib, simhost.lib
+    for it in range(40):
+        q = rng.normal(size=(16, 16)) * rng.choice([0.0, 0.01, 0.1, 1, 5])
+        a, b = np.zeros((16, 16)), np.zeros((16, 16))
+        lib.ref_exp16(P(q), P(a)); sh.simhost_exp16(P(q), P(b))
+        assert np.array_equal(a, b)
+        q3 = rng.normal(size=(3, 3)) * rng.choice([0.0, 1e-3, 1, 5])
+        a3, b3 = np.zeros((3, 3)), np.zeros((3, 3))
+        lib.ref_exp3(P(q3), P(a3)); sh.simhost_exp3(P(q3), P(b3))
+        assert np.array_equal(a3, b3)
+        m = rng.normal(size=(16, 16))
+        m = m @ m.T * 1e-10
+        if it % 4 == 0:
+            m = np.diag(np.diag(m))  # already diagonal: no rotation at all
+        V1, D1, V2, D2 = (np.zeros((16, 16)) for _ in range(4))
+        lib.ref_jacobi16(P(m), P(V1), P(D1)); sh.simhost_jacobi16(P(m), P(V2), P(D2))
+        assert np.array_equal(V1, V2) and np.array_equal(np.diag(D1), np.diag(D2))
+
+
+def test_model_f_matches_the_reference(reference, simhost, sim_golden):
+    rng = np.random.default_rng(11)
+    md = np.ascontiguousarray(sim_golden["model"])
+    for it in range(50):
+        x = rng.normal(size=16)
+        if it % 3 == 0:
+            x[6:9] = 0.0  # the state the simulator actually evaluates f at (rotation error folded into R)
+        x[12:] = 1.2 + 0.1 * rng.normal(size=4)
+        Rm = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        u = 1.2 + 0.1 * rng.normal(size=4)
+        a, b = np.zeros(16), np.zeros(16)
+        reference.lib.ref_f(P(x), P(np.ascontiguousarray(Rm)), P(u), P(a))
+        simhost.lib.simhost_f(P(md), P(x), P(np.ascontiguousarray(Rm)), P(u), P(b))
+        assert np.array_equal(a, b)
+
+
+def test_closed_loop_against_the_reference_40_steps(reference, simhost, product_lib):
+    """reference avoidance + (host build of the kernel) update == reference avoidance + reference update, bit for bit,
+    with the noise drawn by lqro_msvc_normals from the same stream position"""
+    from lqr_obstacles_b200.api import msvc_normals
+    from golden.make_golden import hexagon
+
+    starts, goals = hexagon()
+    sim = RefSim(reference, starts, goals, seed=1)
+    md = sim.model()
+    n = sim.n
+    for step in range(40):
+        newV = sim.avoid(H=30)[0]
+        st = sim.full_state()
+        normals, seed_after = msvc_normals(sim.seed(), 22 * n)
+        sim.update()
+        assert sim.seed() == seed_after
+        ref_after = sim.full_state()
+        o = simhost.update(md, st, newV, normals)
+        for k in KEYS:
+            assert np.array_equal(o[k], ref_after[k]), (step, k)
+    sim.close()
+
+
+def test_msvc_normals_are_the_reference_normals(reference, product_lib):
+    from lqr_obstacles_b200.api import msvc_normals
+
+    reference.lib.ref_srand(12345)
+    a = np.zeros(500)
+    reference.lib.ref_normals(500, P(a))
+    b, seed = msvc_normals(12345, 500)
+    assert np.array_equal(a, b)
+    assert seed == reference.lib.ref_get_seed()
+
+
+def test_default_model_is_the_reference_globals(sim_golden, product_lib):
+    from lqr_obstacles_b200.api import sim_default_model
+
+    g = sim_golden["model"]
+    m = sim_default_model().as_array()
+    gains = slice(7 + 18 + 4, 7 + 18 + 4 + 64 + 12 + 4 + 48 + 9)
+    assert np.array_equal(m[:29], g[:29])          # dt .. u_goal
+    assert np.array_equal(m[gains.stop:], g[gains.stop:])  # M, N
+    assert not m[gains].any()
+
+
+def test_golden_fixture_is_what_the_reference_computes(reference, sim_golden):
+    """regenerates the first recorded steps from oracle/_ref and compares with the committed fixture"""
+    from golden.make_golden import hexagon
+
+    g = sim_golden
+    starts, goals = hexagon()
+    sim = RefSim(reference, starts, goals, seed=1)
+    assert np.array_equal(sim.model(), g["model"])
+    for t in range(6):
+        sim.avoid(H=30)
+        assert sim.seed() == int(g["seeds"][t])
+        sim.update()
+        st = sim.full_state()
+        assert np.array_equal(st["xTrue"], g["traj_xTrue"][t])
+        if t in (0, 1, 5):
+            for k in KEYS:
+                assert np.array_equal(st[k], g["s%d_after_%s" % (t, k)])
+    sim.close()
