@@ -751,7 +751,7 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
 static const int kSimWarps = 4;
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
-  const size_t smem = sizeof(LqroSimModel) + (size_t)kSimWarps * sizeof(LqroSimWs);
+  const size_t smem = (size_t)kSimWarps * sizeof(LqroSimWs);
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_sim_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -759,7 +759,7 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   }
   if (!ctx->ev_sim[0]) { CU(cudaEventCreate(&ctx->ev_sim[0])); CU(cudaEventCreate(&ctx->ev_sim[1])); }
   int blocks = (n + kSimWarps - 1) / kSimWarps;
-  const int cap = ctx->sm_count * 2;  // two resident CTAs per SM (2 x 99.6 KB of shared memory); grid-stride beyond that
+  const int cap = ctx->sm_count * 3;  // three resident CTAs per SM (3 x 69.6 KB of shared memory); grid-stride beyond that
   if (blocks > cap) blocks = cap;
   CU(cudaEventRecord(ctx->ev_sim[0], st));
   k_sim_update<<<blocks, kSimWarps * 32, smem, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, newV, pGoal, normals, vGoal, u);
@@ -828,6 +828,15 @@ extern "C" int lqro_sim_last_ms(lqro_ctx* ctx, float* ms) {
   CU(cudaSetDevice(ctx->cfg.device));
   CU(cudaEventSynchronize(ctx->ev_sim[1]));
   CU(cudaEventElapsedTime(ms, ctx->ev_sim[0], ctx->ev_sim[1]));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_debug_sim_cycles(lqro_ctx* ctx, long long* out16, int reset) {
+  if (!ctx || !out16) return LQRO_E_ARG;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyFromSymbol(out16, g_sim_prof, sizeof(long long) * 16));
+  if (reset) { long long z[16] = {0}; CU(cudaMemcpyToSymbol(g_sim_prof, z, sizeof z)); }
   return LQRO_OK;
 }
 

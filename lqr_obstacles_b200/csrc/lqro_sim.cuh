@@ -41,6 +41,23 @@
 #define SIMM inline
 #endif
 
+// Per-phase SM-cycle counters of the update kernel (lane 0 of every warp), profiling builds only (-DLQRO_SIM_PROF,
+// tools/simprof.py): [0] findU [1] Jacobian (f) [2] exp: powers + Pade polynomials [3] exp: solve [4] exp: squarings
+// [5] noise covariance + Simpson step [6] Jacobi 16x16 + sample [7] propagate tail [8] kalmanFilter1 tail
+// [9] observation sample [10] kalmanFilter2 [11] findVGoal [12] load / store [15] agents
+#if defined(__CUDACC__)
+__device__ long long g_sim_prof[16];
+#endif
+#if defined(__CUDACC__) && defined(LQRO_SIM_PROF)
+#define SIM_TIC() long long sim_t0__ = clock64()
+#define SIM_RETIC() sim_t0__ = clock64()
+#define SIM_TOC(n) do { const long long t1__ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)&g_sim_prof[n], (unsigned long long)(t1__ - sim_t0__)); sim_t0__ = t1__; } while (0)
+#else
+#define SIM_TIC() do { } while (0)
+#define SIM_RETIC() do { } while (0)
+#define SIM_TOC(n) do { } while (0)
+#endif
+
 // What the reference keeps in globals (MAIN:40-76, setup() MAIN:176-198) and in each Quadrotor (MAIN:95-99).
 struct LqroSimModel {
   double dt, gravity, mass, moment_const, thrust_latency, length, jstep;
@@ -62,26 +79,20 @@ struct SimWarp {
   SIMM static int lane() { return (int)(threadIdx.x & 31); }
   SIMM static int stride() { return 32; }
   SIMM static void sync() { __syncwarp(); }
-  // larger value wins, equal values go to the smaller index: the reference's scans use strict > in
-  // increasing index order, i.e. the first maximum
+  // larger value wins, equal values go to the smaller index: the reference's scans use strict > in increasing
+  // index order, i.e. the first maximum.  v >= 0 (an absolute value), so its bit pattern orders like an integer:
+  // three REDUX operations (high word, low word among the leaders, index among the ties).
   SIMM static void argmax(double& v, int& idx) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-    }
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    idx = (int)__reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)idx : 0xffffffffu);
+    v = __hiloint2double((int)mh, (int)ml);
   }
 };
-SIMF double sim_hypot(double x, double y) {  // hypot(x, y) with an FMA-evaluated residual correction (MAT:715,717 call the CRT's)
-  x = fabs(x); y = fabs(y);
-  if (x < y) { const double t = x; x = y; y = t; }
-  if (x == 0.0 || isinf(x)) return x;
-  const double h = sqrt(fma(x, x, y * y));
-  const double h2 = h * h, x2 = x * x;
-  const double r = fma(-y, y, h2 - x2) + fma(h, h, -h2) - fma(x, x, -x2);
-  return h - r / (2.0 * h);
-}
+// hypot(x, y) as MAT:715,717 call it (|x| unbounded, y = 1): one fused x*x + y*y and an IEEE square root, i.e. within
+// one ulp of the CRT's result.  Only the Jacobi rotation angles depend on it (no decision does).
+SIMF double sim_hypot(double x, double y) { return sqrt(fma(x, x, y * y)); }
 #else
 typedef SimSeq SimWarp;
 SIMF double sim_hypot(double x, double y) { return ::hypot(x, y); }
@@ -152,6 +163,88 @@ SIMF void sim_solve(double* m, double* inv, int* rp, int* cp, double* fac) {
   P::sync();
 }
 
+#if defined(__CUDACC__)
+// The same elimination for one warp: lane = (h, c) = (lane >> 4, lane & 15) works on column position c of m and column
+// c of inv, for every second row.  No index divisions; a step first gathers its row offsets, factors and operands
+// (independent loads), then computes and stores.
+template <int N>
+SIMF void sim_solve_warp(double* m, double* inv, int* rp, int* cp, double* fac) {
+  constexpr int TM = (N + 1) / 2;
+  const int lane = (int)(threadIdx.x & 31), h = lane >> 4, c = lane & 15;
+  const bool act = c < N;
+  if (lane < N) { rp[lane] = lane; cp[lane] = lane; }
+  __syncwarp();
+  for (int k = 0; k < N; ++k) {
+    double best = 0.0; int key = 0x7fffffff;  // key = (row position << 4) | column position: row-major order of the scan
+    if (act && c >= k) {
+      const int col = cp[c];
+      for (int i0 = k + h; i0 < N; i0 += 8) {
+        double a[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; a[t] = i < N ? fabs(m[rp[i] * N + col]) : 0.0; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { if (a[t] > best) { best = a[t]; key = ((i0 + 2 * t) << 4) | c; } }
+      }
+    }
+    SimWarp::argmax(best, key);
+    if (!(best > 0.0)) key = (k << 4) | k;
+    __syncwarp();
+    if (lane == 0) {
+      const int mr = key >> 4, mc = key & 15;
+      int s = rp[k]; rp[k] = rp[mr]; rp[mr] = s;
+      s = cp[k]; cp[k] = cp[mc]; cp[mc] = s;
+    }
+    __syncwarp();
+    const int rk = rp[k] * N, ck = cp[k], mcol = act ? cp[c] : 0;
+    if (lane > k && lane < N) fac[lane] = m[rp[lane] * N + ck] / m[rk + ck];
+    const double pm = m[rk + mcol], pi = act ? inv[rk + c] : 0.0;
+    __syncwarp();
+    if (act) {
+      for (int i0 = k + 1 + h; i0 < N; i0 += 8) {  // rows in chunks of four: gather, compute, store
+        int rr[4]; double ff[4], mv[4], iv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; const bool ok = i < N; rr[t] = ok ? rp[i] * N : -1; ff[t] = ok ? fac[i] : 0.0; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { if (rr[t] >= 0) { mv[t] = m[rr[t] + mcol]; iv[t] = inv[rr[t] + c]; } }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (rr[t] >= 0) {
+            if (c > k) m[rr[t] + mcol] = mv[t] - ff[t] * pm;
+            inv[rr[t] + c] = iv[t] - ff[t] * pi;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    const int rk = rp[k] * N, ck = cp[k];
+    const double pv = act ? inv[rk + c] / m[rk + ck] : 0.0;  // both half-warps form the same quotient
+    __syncwarp();
+    if (act) {
+      if (h == 0) inv[rk + c] = pv;
+      for (int i0 = h; i0 < k; i0 += 8) {
+        int rr[4]; double mf[4], iv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; rr[t] = i < k ? rp[i] * N : -1; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { if (rr[t] >= 0) { mf[t] = m[rr[t] + ck]; iv[t] = inv[rr[t] + c]; } }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { if (rr[t] >= 0) inv[rr[t] + c] = iv[t] - mf[t] * pv; }
+      }
+    }
+    __syncwarp();
+  }
+  if (act) {
+#pragma unroll
+    for (int t = 0; t < TM; ++t) { const int i = h + 2 * t; if (i < N) m[cp[i] * N + c] = inv[rp[i] * N + c]; }
+  }
+  __syncwarp();
+}
+template <> SIMF void sim_solve<SimWarp, 16>(double* m, double* inv, int* rp, int* cp, double* fac) { sim_solve_warp<16>(m, inv, rp, cp, fac); }
+template <> SIMF void sim_solve<SimWarp, 6>(double* m, double* inv, int* rp, int* cp, double* fac) { sim_solve_warp<6>(m, inv, rp, cp, fac); }
+#endif
+
 #define SIM_JB0 1729728e1
 #define SIM_JB1 864864e1
 #define SIM_JB2 199584e1
@@ -163,12 +256,12 @@ SIMF void sim_solve(double* m, double* inv, int* rp, int* cp, double* fac) {
 #define SIM_NORMLIM 9.504178996162932e-1
 #define SIM_LOG2E 1.4426950408889634074
 
-// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  ws: 6*N*N doubles, ints 2N,
-// small N doubles.  out may not alias q or ws.
+// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  q is scaled IN PLACE (destroyed);
+// ws: 4*N*N doubles, perm: 2N ints, small: N doubles.  out may not alias q or ws.
 template <class P, int N>
-SIMF void sim_exp(double* out, const double* q, double* ws, int* perm, double* small) {
-  double* A = ws; double* A2 = ws + N * N; double* A4 = ws + 2 * N * N; double* A6 = ws + 3 * N * N;
-  double* T = ws + 4 * N * N; double* U = ws + 5 * N * N;
+SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) {
+  double* A = q; double* A2 = ws; double* A4 = ws + N * N; double* A6 = ws + 2 * N * N; double* T = ws + 3 * N * N;
+  SIM_TIC();
   SIM_FOR(P, j, N) {  // 1-norm: column sums top to bottom (MAT:275-288)
     double s = 0.0;
     for (int i = 0; i < N; ++i) s += fabs(q[i * N + j]);
@@ -179,34 +272,33 @@ SIMF void sim_exp(double* out, const double* q, double* ws, int* perm, double* s
   for (int j = 0; j < N; ++j) if (small[j] > norm1) norm1 = small[j];
   const double sd = ceil(log(norm1 / SIM_NORMLIM) * SIM_LOG2E);
   const int s = (int)(sd > 0.0 ? sd : 0.0);
-  const double scale = ldexp(1.0, s);  // pow(2.0, s), exact
-  SIM_FOR(P, e, N * N) A[e] = q[e] / scale;
+  const double rscale = ldexp(1.0, -s);  // A /= 2^s (MAT:779): multiplying by 2^-s gives the same bits (both exact up to underflow)
+  SIM_FOR(P, e, N * N) A[e] = A[e] * rscale;
   P::sync();
   sim_mm<P, false>(A2, A, A, N, N, N);
   sim_mm<P, false>(A4, A2, A2, N, N, N);
   sim_mm<P, false>(A6, A2, A4, N, N, N);
-  SIM_FOR(P, e, N * N) {
+  SIM_FOR(P, e, N * N) {  // the two Pade polynomials: U's factor into T, V over A6
     const double id = (e / N == e % N) ? 1.0 : 0.0;
-    T[e] = A6[e] * SIM_JB7 + A4[e] * SIM_JB5 + A2[e] * SIM_JB3 + id * SIM_JB1;
+    const double a6 = A6[e], a4 = A4[e], a2 = A2[e];
+    T[e] = a6 * SIM_JB7 + a4 * SIM_JB5 + a2 * SIM_JB3 + id * SIM_JB1;
+    A6[e] = a6 * SIM_JB6 + a4 * SIM_JB4 + a2 * SIM_JB2 + id * SIM_JB0;
   }
   P::sync();
-  sim_mm<P, false>(U, A, T, N, N, N);
-  SIM_FOR(P, e, N * N) {  // V, then (V - U) into A2 and (V + U) into A4 (A2, A4 are dead once V is formed)
-    const double id = (e / N == e % N) ? 1.0 : 0.0;
-    const double v = A6[e] * SIM_JB6 + A4[e] * SIM_JB4 + A2[e] * SIM_JB2 + id * SIM_JB0;
-    T[e] = v;
-  }
+  sim_mm<P, false>(A2, A, T, N, N, N);  // U (A2 is dead)
+  SIM_FOR(P, e, N * N) { const double v = A6[e], u = A2[e]; A4[e] = v - u; T[e] = v + u; }
   P::sync();
-  SIM_FOR(P, e, N * N) { A2[e] = T[e] - U[e]; A4[e] = T[e] + U[e]; }
-  P::sync();
-  sim_solve<P, N>(A2, A4, perm, perm + N, small);  // R7 = (V - U) % (V + U), result in A2
-  double* cur = A2; double* nxt = A6;
+  if (N == 16) SIM_TOC(2);
+  sim_solve<P, N>(A4, T, perm, perm + N, small);  // R7 = (V - U) % (V + U), result in A4
+  if (N == 16) SIM_TOC(3);
+  double* cur = A4; double* nxt = A2;
   for (int i = 0; i < s; ++i) {
     sim_mm<P, false>(nxt, cur, cur, N, N, N);
     double* t = cur; cur = nxt; nxt = t;
   }
   SIM_FOR(P, e, N * N) out[e] = cur[e];
   P::sync();
+  if (N == 16) SIM_TOC(4);
 }
 
 // Cyclic-by-row Jacobi eigen-decomposition (MAT:674-757): D <- eigenvalues on the diagonal (upper triangle
@@ -288,10 +380,12 @@ SIMF void sim_skew(double* S, const double* v) {  // stdafx.h:77-84
   S[6] = -v[1]; S[7] = v[0]; S[8] = 0.0;
 }
 SIMF void sim_mv3(double* y, const double* Mx, const double* v) {
-  for (int i = 0; i < 3; ++i) { double t = 0.0; for (int k = 0; k < 3; ++k) t += Mx[i * 3 + k] * v[k]; y[i] = t; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { double t = 0.0; t += Mx[i * 3] * v[0]; t += Mx[i * 3 + 1] * v[1]; t += Mx[i * 3 + 2] * v[2]; y[i] = t; }
 }
 SIMF void sim_mtv3(double* y, const double* Mx, const double* v) {  // (~M) * v
-  for (int i = 0; i < 3; ++i) { double t = 0.0; for (int k = 0; k < 3; ++k) t += Mx[k * 3 + i] * v[k]; y[i] = t; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { double t = 0.0; t += Mx[i] * v[0]; t += Mx[3 + i] * v[1]; t += Mx[6 + i] * v[2]; y[i] = t; }
 }
 SIMF double sim_hypot3(const double* v) {  // stdafx.h:86-97
   const double X = fabs(v[0]), Y = fabs(v[1]), Z = fabs(v[2]);
@@ -299,16 +393,124 @@ SIMF double sim_hypot3(const double* v) {  // stdafx.h:86-97
   else if (Y > Z) return Y * sqrt(1.0 + (X / Y) * (X / Y) + (Z / Y) * (Z / Y));
   else return Z * sqrt(1.0 + (X / Z) * (X / Z) + (Y / Z) * (Y / Z));
 }
+// 3x3 product, fully unrolled (every index a compile-time constant: the operands stay in registers)
+SIMF void sim_mm3(double* C, const double* A, const double* B) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t += A[i * 3 + k] * B[k * 3 + j];
+      C[i * 3 + j] = t;
+    }
+  }
+}
+// P X = Q for 3x3 operands in registers: the full-pivot elimination of MAT:370-440 with the pivot brought to (k, k) by
+// physically exchanging rows / columns (the reference permutes indices instead; the arithmetic on each logical element
+// and the row-major order of the pivot scan over POSITIONS are the same).  m: in P, destroyed; inv: in Q, destroyed;
+// X: out.
+SIMF void sim_solve3(double* X, double* m, double* inv) {
+  int cp0 = 0, cp1 = 1, cp2 = 2;  // logical column at each column position
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double best = 0.0; int mr = k, mc = k;
+#pragma unroll
+    for (int i = k; i < 3; ++i) {
+#pragma unroll
+      for (int j = k; j < 3; ++j) {
+        const double a = fabs(m[i * 3 + j]);
+        if (a > best) { best = a; mr = i; mc = j; }
+      }
+    }
+#pragma unroll
+    for (int r = k + 1; r < 3; ++r) {
+      if (mr == r) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          double t = m[k * 3 + j]; m[k * 3 + j] = m[r * 3 + j]; m[r * 3 + j] = t;
+          t = inv[k * 3 + j]; inv[k * 3 + j] = inv[r * 3 + j]; inv[r * 3 + j] = t;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) {
+      if (mc == c) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double t = m[i * 3 + k]; m[i * 3 + k] = m[i * 3 + c]; m[i * 3 + c] = t; }
+        if (k == 0) { const int t = cp0; if (c == 1) { cp0 = cp1; cp1 = t; } else { cp0 = cp2; cp2 = t; } }
+        else { const int t = cp1; cp1 = cp2; cp2 = t; }
+      }
+    }
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i) {
+      const double factor = m[i * 3 + k] / m[k * 3 + k];
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) m[i * 3 + j] -= factor * m[k * 3 + j];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) inv[i * 3 + j] -= factor * inv[k * 3 + j];
+    }
+  }
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    const double quotient = m[k * 3 + k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) inv[k * 3 + j] /= quotient;
+#pragma unroll
+    for (int i = 0; i < k; ++i) {
+      const double factor = m[i * 3 + k];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) inv[i * 3 + j] -= factor * inv[k * 3 + j];
+    }
+  }
+  // X(cp[i], :) = row i
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) X[r * 3 + j] = (cp0 == r) ? inv[j] : ((cp1 == r) ? inv[3 + j] : inv[6 + j]);
+  }
+}
+// exp of a 3x3 matrix (MAT:773-790) with everything in registers
 SIMF void sim_exp3(double* out, const double* q) {
-  double ws[54]; int perm[6]; double small[3];
-  sim_exp<SimSeq, 3>(out, q, ws, perm, small);
+  double norm1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) c += fabs(q[i * 3 + j]);
+    if (c > norm1) norm1 = c;
+  }
+  const double sd = ceil(log(norm1 / SIM_NORMLIM) * SIM_LOG2E);
+  const int s = (int)(sd > 0.0 ? sd : 0.0);
+  const double rscale = ldexp(1.0, -s);  // A /= 2^s: the product with 2^-s has the same bits
+  double A[9], A2[9], A4[9], A6[9], T[9], U[9], V[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) A[e] = q[e] * rscale;
+  sim_mm3(A2, A, A);
+  sim_mm3(A4, A2, A2);
+  sim_mm3(A6, A2, A4);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    const double id = (e % 4 == 0) ? 1.0 : 0.0;
+    T[e] = A6[e] * SIM_JB7 + A4[e] * SIM_JB5 + A2[e] * SIM_JB3 + id * SIM_JB1;
+    V[e] = A6[e] * SIM_JB6 + A4[e] * SIM_JB4 + A2[e] * SIM_JB2 + id * SIM_JB0;
+  }
+  sim_mm3(U, A, T);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { A2[e] = V[e] - U[e]; A4[e] = V[e] + U[e]; }
+  sim_solve3(out, A2, A4);
+  for (int i = 0; i < s; ++i) {
+    sim_mm3(T, out, out);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) out[e] = T[e];
+  }
 }
 // R <- R * exp(skew(r))   (the "reset rotation-error" step, MAIN:453, 472, 485)
 SIMF void sim_fold_rotation(double* R, const double* r) {
   double S[9], Ex[9], Rn[9];
   sim_skew(S, r);
   sim_exp3(Ex, S);
-  sim_mm<SimSeq, false>(Rn, R, Ex, 3, 3, 3);
+  sim_mm3(Rn, R, Ex);
   for (int i = 0; i < 9; ++i) R[i] = Rn[i];
 }
 
@@ -320,7 +522,7 @@ SIMF void sim_f(double* xdot, const double* x, const double* R, const double* u,
     double S[9], Ex[9], RE[9];
     sim_skew(S, r);
     sim_exp3(Ex, S);
-    sim_mm<SimSeq, false>(RE, R, Ex, 3, 3, 3);
+    sim_mm3(RE, R, Ex);
     const double a = (F[0] + F[1] + F[2] + F[3]) / md.mass;
     const double ez[3] = {0.0, 0.0, 1.0};
     for (int i = 0; i < 3; ++i) {
@@ -352,7 +554,7 @@ SIMF void sim_f(double* xdot, const double* x, const double* R, const double* u,
     const double ex[3] = {1.0, 0.0, 0.0}, ey[3] = {0.0, 1.0, 0.0}, ez[3] = {0.0, 0.0, 1.0};
     double S[9], SJ[9], g[3], rhs[3];
     sim_skew(S, w);
-    sim_mm<SimSeq, false>(SJ, S, md.inertia, 3, 3, 3);
+    sim_mm3(SJ, S, md.inertia);
     sim_mv3(g, SJ, w);
     for (int i = 0; i < 3; ++i) rhs[i] = ex[i] * a + ey[i] * b + ez[i] * c - g[i];
     sim_mv3(xdot + 9, md.inv_inertia, rhs);
@@ -372,7 +574,7 @@ SIMF void sim_local_frame(double* RLocal, double* xTilde, const double* x, const
   double Ex[9];
   sim_skew(S, axis);
   sim_exp3(Ex, S);
-  sim_mm<SimSeq, false>(RLocal, Ex, R0, 3, 3, 3);
+  sim_mm3(RLocal, Ex, R0);
   sim_mtv3(xTilde, RLocal, x);
   sim_mtv3(xTilde + 3, RLocal, x + 3);
   {  // errFromRot(~RLocal*R0)  (stdafx.h:35-49)
@@ -416,7 +618,7 @@ SIMF void sim_find_vgoal(double* vG, const double* x, const double* R0, const do
 
 // ---- per-agent (per-warp) workspace -------------------------------------------------------------------
 struct LqroSimWs {
-  double F[256], Ae[256], A2e[256], MM[256], P[256], W[6 * 256];
+  double F[256], Ae[256], MM[256], P[256], W[4 * 256];  // F doubles as exp(dt/2 F) once the Jacobian is spent
   double x[16], xT[16], R[9], RT[9], u[4], z[6], hz[6], nrm[22], xdot[16], v1[16], v2[16], samp[16], small[16];
   int perm[32];
 };
@@ -431,6 +633,7 @@ struct LqroSimObs {
 // xs, Rs: the state / rotation linearised about (shared memory of the warp).
 template <class P>
 SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroSimModel& md) {
+  SIM_TIC();
   SIM_FOR(P, c, 17) {  // columns 0..15 of the central-difference Jacobian (MAIN:392-401), "column" 16 = f itself
     double xr[16], R[9], u[4], fr[16], fl[16];
     for (int i = 0; i < 9; ++i) R[i] = Rs[i];
@@ -440,37 +643,43 @@ SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroS
       if (c < 16) {
         for (int i = 0; i < 16; ++i) if (i == c) { if (side == 0) xr[i] += md.jstep; else xr[i] -= md.jstep; }
       }
-      sim_f(side == 0 ? fr : fl, xr, R, u, md);
+      double ft[16];
+      sim_f(ft, xr, R, u, md);
+      for (int i = 0; i < 16; ++i) { if (side == 0) fr[i] = ft[i]; else fl[i] = ft[i]; }
       if (c == 16) break;
     }
     if (c < 16) { for (int i = 0; i < 16; ++i) w.F[i * 16 + c] = (fr[i] - fl[i]) / (2 * md.jstep); }
     else { for (int i = 0; i < 16; ++i) w.xdot[i] = fr[i]; }
   }
   P::sync();
-  double* T1 = w.W; double* T2 = w.W + 256;  // sim_exp uses all of W: scaled copies go to MM / P-free buffers instead
+  SIM_TOC(1);
+  double* T1 = w.W; double* T2 = w.W + 256;
+  double* const A2e = w.F;  // exp(dt/2 F) replaces the Jacobian once dt/2 F has been formed
   SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * md.dt;
   P::sync();
   sim_exp<P, 16>(w.Ae, w.MM, w.W, w.perm, w.small);
   SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * (md.dt * 0.5);
   P::sync();
-  sim_exp<P, 16>(w.A2e, w.MM, w.W, w.perm, w.small);
+  sim_exp<P, 16>(A2e, w.MM, w.W, w.perm, w.small);
   // MM = (dt/6) * (M + 4*A2*M*~A2 + A*M*~A)
+  SIM_RETIC();
   double* T3 = w.W + 512; double* T4 = w.W + 768;
-  SIM_FOR(P, e, 256) T1[e] = w.A2e[e] * 4;
+  SIM_FOR(P, e, 256) T1[e] = A2e[e] * 4;
   P::sync();
   sim_mm<P, false>(T2, T1, md.M, 16, 16, 16);
-  sim_mm<P, true>(T3, T2, w.A2e, 16, 16, 16);
+  sim_mm<P, true>(T3, T2, A2e, 16, 16, 16);
   sim_mm<P, false>(T2, w.Ae, md.M, 16, 16, 16);
   sim_mm<P, true>(T4, T2, w.Ae, 16, 16, 16);
   SIM_FOR(P, e, 256) w.MM[e] = (md.M[e] + T3[e] + T4[e]) * (md.dt / 6);
   // v1 = (dt/6)*(xDot + 4*(A2*xDot) + A*xDot)
   SIM_FOR(P, i, 16) {
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < 16; ++k) a += w.A2e[i * 16 + k] * w.xdot[k];
+    for (int k = 0; k < 16; ++k) a += A2e[i * 16 + k] * w.xdot[k];
     for (int k = 0; k < 16; ++k) b += w.Ae[i * 16 + k] * w.xdot[k];
     w.v1[i] = (w.xdot[i] + a * 4 + b) * (md.dt / 6);
   }
   P::sync();
+  SIM_TOC(5);
 }
 
 // One agent, MAIN:1409-1416.  On entry the workspace holds x, R (estimate), xT, RT (true state), P, nrm (22 standard
@@ -478,6 +687,7 @@ SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroS
 // On exit x, R, xT, RT, P are updated, w.u holds the control input, vG the next goal velocity.
 template <class P>
 SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal, double* vG, const LqroSimModel& md) {
+  SIM_TIC();
   {  // Input u = findU()  (vGoal = newV, MAIN:1409-1410)
     double x[16], R[9], u[4];
     for (int i = 0; i < 16; ++i) x[i] = w.x[i];
@@ -487,14 +697,17 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     if (P::lane() == 0) for (int i = 0; i < 4; ++i) w.u[i] = u[i];
     P::sync();
   }
+  SIM_TOC(0);
   // propagate(xTrue, RotTrue, u, M)  (MAIN:442-455)
   sim_flow<P>(w, w.xT, w.RT, md);
+  SIM_RETIC();
   {
     double* T1 = w.W; double* V = w.W + 256;
     SIM_FOR(P, e, 256) T1[e] = w.MM[e];
     SIM_FOR(P, i, 16) w.v2[i] = 0.0;
     P::sync();
     sim_sample_gaussian<P, 16>(w.samp, w.v2, T1, V, w.nrm);
+    SIM_TOC(6);
     double r[3], R[9];
     for (int i = 0; i < 3; ++i) r[i] = w.xT[6 + i] + w.v1[6 + i] + w.samp[6 + i];
     for (int i = 0; i < 9; ++i) R[i] = w.RT[i];
@@ -504,8 +717,10 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     SIM_FOR(P, i, 9) w.RT[i] = R[i];
     P::sync();
   }
+  SIM_TOC(7);
   // kalmanFilter1(x, Rot, u, M, P)  (MAIN:457-474)
   sim_flow<P>(w, w.x, w.R, md);
+  SIM_RETIC();
   {
     double* T1 = w.W; double* T2 = w.W + 256;
     sim_mm<P, false>(T1, w.Ae, w.P, 16, 16, 16);
@@ -520,6 +735,7 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     SIM_FOR(P, i, 9) w.R[i] = R[i];
     P::sync();
   }
+  SIM_TOC(8);
   const LqroSimObs o(w.W);
   // Observation z = sampleGaussian(h(xTrue, RotTrue), N)  (MAIN:1413; h MAIN:369-390: rate gyros, then position)
   {
@@ -528,6 +744,7 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     P::sync();
     sim_sample_gaussian<P, 6>(w.z, w.hz, o.S6, o.V6, w.nrm + 16);
   }
+  SIM_TOC(9);
   // kalmanFilter2(x, Rot, z, N, P)  (MAIN:476-487)
   {
     SIM_FOR(P, e, 96) {  // H = Jacobian_hx: central differences of h (MAIN:414-423)
@@ -563,31 +780,28 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     SIM_FOR(P, i, 9) w.R[i] = R[i];
     P::sync();
   }
+  SIM_TOC(10);
   {  // vGoal = findVGoal()  (MAIN:1416)
     double x[16], R[9];
     for (int i = 0; i < 16; ++i) x[i] = w.x[i];
     for (int i = 0; i < 9; ++i) R[i] = w.R[i];
     sim_find_vgoal(vG, x, R, pGoal, md);
   }
+  SIM_TOC(11);
 }
 
 #if defined(__CUDACC__)
-// grid-stride over agents, one warp each; dynamic shared memory = sizeof(LqroSimModel) + warps * sizeof(LqroSimWs)
-__global__ void __launch_bounds__(128) k_sim_update(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
+// grid-stride over agents, one warp each; dynamic shared memory = warps * sizeof(LqroSimWs) (17.4 KB per warp: three
+// 4-warp CTAs per SM)
+__global__ void __launch_bounds__(128, 3) k_sim_update(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
                                                     double* __restrict__ Rot, double* __restrict__ Pcov, double* __restrict__ xTrue,
                                                     double* __restrict__ RotTrue, const double* __restrict__ newV,
                                                     const double* __restrict__ pGoal, const double* __restrict__ normals,
                                                     double* __restrict__ vGoal, double* __restrict__ uOut) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
-  LqroSimModel& md = *reinterpret_cast<LqroSimModel*>(sim_smem);
-  {
-    const double* src = reinterpret_cast<const double*>(model);
-    double* dst = reinterpret_cast<double*>(sim_smem);
-    for (int e = threadIdx.x; e < (int)(sizeof(LqroSimModel) / 8); e += blockDim.x) dst[e] = src[e];
-  }
-  __syncthreads();
+  const LqroSimModel& md = *model;  // 3.6 KB of constants and gains, read through L1 (uniform or row-contiguous accesses)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  LqroSimWs& w = *reinterpret_cast<LqroSimWs*>(sim_smem + sizeof(LqroSimModel) + (size_t)warp * sizeof(LqroSimWs));
+  LqroSimWs& w = *reinterpret_cast<LqroSimWs*>(sim_smem + (size_t)warp * sizeof(LqroSimWs));
   for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
     for (int e = lane; e < 256; e += 32) w.P[e] = Pcov[(size_t)a * 256 + e];
     if (lane < 16) { w.x[lane] = x[(size_t)a * 16 + lane]; w.xT[lane] = xTrue[(size_t)a * 16 + lane]; }
@@ -600,7 +814,7 @@ __global__ void __launch_bounds__(128) k_sim_update(int n, const LqroSimModel* _
     for (int e = lane; e < 256; e += 32) Pcov[(size_t)a * 256 + e] = w.P[e];
     if (lane < 16) { x[(size_t)a * 16 + lane] = w.x[lane]; xTrue[(size_t)a * 16 + lane] = w.xT[lane]; }
     if (lane < 9) { Rot[(size_t)a * 9 + lane] = w.R[lane]; RotTrue[(size_t)a * 9 + lane] = w.RT[lane]; }
-    if (lane < 3) vGoal[(size_t)a * 3 + lane] = vG[lane];
+    if (lane == 0) { vGoal[(size_t)a * 3] = vG[0]; vGoal[(size_t)a * 3 + 1] = vG[1]; vGoal[(size_t)a * 3 + 2] = vG[2]; }
     if (uOut && lane < 4) uOut[(size_t)a * 4 + lane] = w.u[lane];
     __syncwarp();
   }

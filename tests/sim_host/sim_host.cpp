@@ -25,8 +25,9 @@ extern "C" void simhost_update(int n, const LqroSimModel* md, double* x, double*
   }
 }
 extern "C" void simhost_exp16(const double* q, double* out) {
-  static double ws[6 * 256]; int perm[32]; double small[16];
-  sim_exp<SimSeq, 16>(out, q, ws, perm, small);
+  static double ws[4 * 256], a[256]; int perm[32]; double small[16];
+  for (int e = 0; e < 256; ++e) a[e] = q[e];  // sim_exp scales its argument in place
+  sim_exp<SimSeq, 16>(out, a, ws, perm, small);
 }
 extern "C" void simhost_exp3(const double* q, double* out) { sim_exp3(out, q); }
 extern "C" void simhost_jacobi16(const double* q, double* V, double* D) {
