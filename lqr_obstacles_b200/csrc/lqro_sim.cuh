@@ -101,9 +101,38 @@ SIMF double sim_hypot(double x, double y) { return ::hypot(x, y); }
 #define SIM_FOR(P, e, n) for (int e = P::lane(); e < (n); e += P::stride())
 
 // ---- small dense algebra in the reference's operation order ---------------------------------------
+#if defined(__CUDACC__)
+// 16x16x16 for one warp: lane = (h, j) owns column j of C for every second row, k outermost: one B operand and four
+// 16-byte A loads feed eight independent left-to-right sums (each output still adds its products in k order).
+template <bool TB>
+SIMF void sim_mm16_warp(double* C, const double* A, const double* B) {
+  const int lane = (int)(threadIdx.x & 31), h = lane >> 4, j = lane & 15;
+  double acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const double b0 = TB ? B[j * 16 + k] : B[k * 16 + j];
+    const double b1 = TB ? B[j * 16 + k + 1] : B[(k + 1) * 16 + j];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const double2 a = *reinterpret_cast<const double2*>(A + (h + 2 * t) * 16 + k);
+      acc[t] += a.x * b0;
+      acc[t] += a.y * b1;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) C[(h + 2 * t) * 16 + j] = acc[t];
+  __syncwarp();
+}
+#endif
+
 // C (n x p) = A (n x m) * B (m x p); TB: B is given transposed (stored p x m).  MAT:219-231.
 template <class P, bool TB>
 SIMF void sim_mm(double* C, const double* A, const double* B, int n, int m, int p) {
+#if defined(__CUDACC__)
+  if (P::stride() == 32 && n == 16 && m == 16 && p == 16) { sim_mm16_warp<TB>(C, A, B); return; }  // resolved at compile time after inlining
+#endif
   SIM_FOR(P, e, n * p) {
     const int i = e / p, j = e - i * p;
     double t = 0.0;
@@ -634,23 +663,23 @@ struct LqroSimObs {
 template <class P>
 SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroSimModel& md) {
   SIM_TIC();
-  SIM_FOR(P, c, 17) {  // columns 0..15 of the central-difference Jacobian (MAIN:392-401), "column" 16 = f itself
-    double xr[16], R[9], u[4], fr[16], fl[16];
+  // Central-difference Jacobian (MAIN:392-401): the 32 evaluations f(x +- jStep e_c) run one per lane, results staged in W.
+  // sim_f never reads the position x[0..2] (MAIN:341 extracts p and does not use it), so f(x + jStep e_0) is f(x) bit for
+  // bit: the unperturbed xDot (MAIN:444) is column 0's evaluation.
+  double* fb = w.W;  // [32][17]: padded rows, conflict-free for lane-per-row stores
+  SIM_FOR(P, t, 32) {
+    const int c = t & 15, side = t >> 4;
+    double xr[16], R[9], u[4], ft[16];
     for (int i = 0; i < 9; ++i) R[i] = Rs[i];
     for (int i = 0; i < 4; ++i) u[i] = w.u[i];
-    for (int side = 0; side < 2; ++side) {
-      for (int i = 0; i < 16; ++i) xr[i] = xs[i];
-      if (c < 16) {
-        for (int i = 0; i < 16; ++i) if (i == c) { if (side == 0) xr[i] += md.jstep; else xr[i] -= md.jstep; }
-      }
-      double ft[16];
-      sim_f(ft, xr, R, u, md);
-      for (int i = 0; i < 16; ++i) { if (side == 0) fr[i] = ft[i]; else fl[i] = ft[i]; }
-      if (c == 16) break;
-    }
-    if (c < 16) { for (int i = 0; i < 16; ++i) w.F[i * 16 + c] = (fr[i] - fl[i]) / (2 * md.jstep); }
-    else { for (int i = 0; i < 16; ++i) w.xdot[i] = fr[i]; }
+    for (int i = 0; i < 16; ++i) xr[i] = xs[i];
+    for (int i = 0; i < 16; ++i) if (i == c) { if (side == 0) xr[i] += md.jstep; else xr[i] -= md.jstep; }
+    sim_f(ft, xr, R, u, md);
+    for (int i = 0; i < 16; ++i) fb[t * 17 + i] = ft[i];
   }
+  P::sync();
+  SIM_FOR(P, e, 256) { const int i = e >> 4, c = e & 15; w.F[e] = (fb[c * 17 + i] - fb[(16 + c) * 17 + i]) / (2 * md.jstep); }
+  SIM_FOR(P, i, 16) w.xdot[i] = fb[i];
   P::sync();
   SIM_TOC(1);
   double* T1 = w.W; double* T2 = w.W + 256;
