@@ -223,6 +223,60 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def sim_update_arm(ctx, x, L, E, stream, args):
+    """k_sim_update over every agent of the swarm: estimates = the swarm's states, identity attitudes, P = 1e-9 I, synthetic
+    standard normals (numpy; the kernel's cost does not depend on their values), gains from the golden vectors.  Timed
+    with CUDA events around each launch (lqro_sim_last_ms); beside it the reference's own update loop on one host core
+    (oracle/_ref, 32 quads) when it is available."""
+    import torch
+    from lqr_obstacles_b200.api import sim_default_model
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+    n = len(x)
+    ctx.sim_set_model(sim_default_model(L=L, E=E, Lh=g["dyn_Lh"], Eh=g["dyn_Eh"]))
+    rng = np.random.default_rng(1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    eye3, p0 = np.eye(3).ravel(), (1e-9 * np.eye(16)).ravel()
+    dx, dxt = dev(x), dev(x)
+    dR, dRT = dev(np.tile(eye3, (n, 1))), dev(np.tile(eye3, (n, 1)))
+    dP = dev(np.tile(p0, (n, 1)))
+    dnv = dev(x[:, 3:6] + 0.1 * rng.normal(size=(n, 3)))
+    dpg = dev(-x[:, 0:3])
+    dnr = dev(rng.normal(size=(n, 22)))
+    dvg, du = torch.zeros(n, 3, dtype=torch.float64, device="cuda"), torch.zeros(n, 4, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ms = []
+    for it in range(2 + max(1, min(args.steps, 5))):
+        ctx.sim_update_device(n, dx.data_ptr(), dR.data_ptr(), dP.data_ptr(), dxt.data_ptr(), dRT.data_ptr(), dnv.data_ptr(),
+                              dpg.data_ptr(), dnr.data_ptr(), dvg.data_ptr(), du.data_ptr())
+        ms.append(ctx.sim_last_ms())
+    ms = ms[2:]
+    k_ms = float(np.mean(ms))
+    arm = {"kernel": "k_sim_update", "agents": n, "ms_per_launch": k_ms, "agents_per_s": n / (k_ms * 1e-3),
+           "finite": bool(torch.isfinite(dx).all().item() and torch.isfinite(dP).all().item()),
+           "api": "lqro_sim_update_device (state resident; standard normals supplied by the host, see lqro_msvc_normals)"}
+    if not args.no_cpu:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from _libs import Reference, RefSim
+            ref = Reference()
+            m = 32
+            ang = np.arange(m) * 2 * np.pi / m
+            starts = np.stack([12 * np.cos(ang), 12 * np.sin(ang), np.zeros(m)], 1)
+            sim = RefSim(ref, starts, -starts, seed=1)
+            sim.set_newv(np.zeros((m, 3)))
+            sim.update()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                sim.update()
+            d = time.perf_counter() - t0
+            sim.close()
+            arm["cpu_reference"] = {"agents_per_s": 3 * m / d, "cores": 1, "kind": "reference",
+                                    "sample": "the reference's own update loop (oracle/_ref ref_sim_update), 32 quads x 3 steps, %.2f s" % d}
+        except Exception as e:  # oracle/_ref not present on this box
+            arm["cpu_reference"] = {"unavailable": str(e)[:120]}
+    return arm
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -346,6 +400,12 @@ def run_ours(args):
                    "checksum": float(hout2.sum()), "api": "lqro_step_sharded(nbr=NULL) with LQRO_FLAG_DEVICE_KNN"}
         ctx2.close()
 
+    # ---- the second half of the reference's time step (MAIN:1408-1417: LQR feedback, propagate, Kalman filter) for the same
+    # swarm on the device (lqro_sim_update_device): informative, not part of `value`
+    sim_arm = None
+    if world == 1:
+        sim_arm = sim_update_arm(ctx, x, L, E, stream, args)
+
     t_dev = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, kern_ms[0]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -419,6 +479,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "counters": counters,
+            "sim_update": sim_arm,
         }
         print(json.dumps(line))
     ctx.close()

@@ -16,7 +16,8 @@
 //   * per-function shims below: same names, same argument lists (createObstacle ... calculateNewV,
 //     controlMatrices' Riccati part) -- each call is one small device round trip: correct, slow;
 //   * lqro::Swarm -- the whole `for i / for j` block of MAIN:1373-1407 for all agents in ONE device
-//     step (lqro_step): this is what replaces the hot loop.
+//     step (lqro_step): this is what replaces the hot loop; Swarm::update replaces the second loop of the
+//     time step (MAIN:1408-1417: LQR feedback, propagate, Kalman filter) with one lqro_sim_update call.
 #pragma once
 #include <cmath>
 #include <cstdio>
@@ -262,6 +263,46 @@ class Swarm {
     check(lqro_step(ctx_, x_.data(), vpref_.data(), nbr_.data(), newv_.data()), ctx_, "lqro_step");
     for (int i = 0; i < n_; ++i) for (int k = 0; k < 3; ++k) qlist[i]->newV[k] = newv_[3 * (size_t)i + k];
   }
+  // ---- the second loop of the time step, MAIN:1408-1417, in one device call (lqro_sim_update) ----------------
+  // Fill simModel() from the reference's globals once after setup()/controlMatrices, e.g.
+  //     lqro_sim_model& m = swarm.simModel();       // pre-filled with setup()'s constants (MAIN:176-198)
+  //     lqro::copy(m.L, qlist[0]->L, 64); lqro::copy(m.E, qlist[0]->E, 12); lqro::copy(m.l, qlist[0]->l, 4);
+  //     lqro::copy(m.Lh, qlist[0]->Lh, 48); lqro::copy(m.Eh, qlist[0]->Eh, 9); lqro::copy(m.M, M, 256); lqro::copy(m.N, N, 36);
+  //     swarm.commitSimModel();
+  // then, each time step, instead of the loop MAIN:1408-1417:
+  //     swarm.update(qlist, normal);                // `normal` = the reference's own normal(), MAIN:325-336
+  lqro_sim_model& simModel() {
+    if (!model_init_) { lqro_sim_default_model(&model_); model_init_ = true; }
+    return model_;
+  }
+  void commitSimModel() { check(lqro_sim_set_model(ctx_, &simModel()), ctx_, "lqro_sim_set_model"); }
+
+  // QuadPtrVec: std::vector<Quadrotor*> with members x, xTrue (State), Rot, RotTrue (Rotation), P (Matrix<16,16>), newV, pGoal,
+  // vGoal (Matrix<3,1>) -- the reference's Quadrotor (MAIN:79-99).  `normal` is called 22 times per quad in the reference's
+  // order (16 for propagate's process noise MAIN:450, then 6 for the observation MAIN:1413), so the CRT rand() stream is
+  // consumed exactly as by the loop it replaces.  Per quad: vGoal = newV; u = findU(); propagateU(u); kalmanFilter1;
+  // z = sampleGaussian(h(xTrue, RotTrue), N); kalmanFilter2; vGoal = findVGoal().  (visualize() stays with the caller.)
+  template <class QuadPtrVec, class NormalFn>
+  void update(QuadPtrVec& qlist, NormalFn normal) {
+    const size_t n = (size_t)n_;
+    sx_.resize(16 * n); sxt_.resize(16 * n); sr_.resize(9 * n); srt_.resize(9 * n); sp_.resize(256 * n);
+    snv_.resize(3 * n); spg_.resize(3 * n); snr_.resize(22 * n); svg_.resize(3 * n);
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 16; ++k) { sx_[16 * i + k] = qlist[i]->x[k]; sxt_[16 * i + k] = qlist[i]->xTrue[k]; }
+      for (int k = 0; k < 9; ++k) { sr_[9 * i + k] = qlist[i]->Rot[k]; srt_[9 * i + k] = qlist[i]->RotTrue[k]; }
+      for (int k = 0; k < 256; ++k) sp_[256 * i + k] = qlist[i]->P[k];
+      for (int k = 0; k < 3; ++k) { snv_[3 * i + k] = qlist[i]->newV[k]; spg_[3 * i + k] = qlist[i]->pGoal[k]; }
+      for (int k = 0; k < 22; ++k) snr_[22 * i + k] = normal();
+    }
+    check(lqro_sim_update(ctx_, n_, sx_.data(), sr_.data(), sp_.data(), sxt_.data(), srt_.data(), snv_.data(), spg_.data(), snr_.data(),
+                          svg_.data(), nullptr), ctx_, "lqro_sim_update");
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 16; ++k) { qlist[i]->x[k] = sx_[16 * i + k]; qlist[i]->xTrue[k] = sxt_[16 * i + k]; }
+      for (int k = 0; k < 9; ++k) { qlist[i]->Rot[k] = sr_[9 * i + k]; qlist[i]->RotTrue[k] = srt_[9 * i + k]; }
+      for (int k = 0; k < 256; ++k) qlist[i]->P[k] = sp_[256 * i + k];
+      for (int k = 0; k < 3; ++k) qlist[i]->vGoal[k] = svg_[3 * i + k];
+    }
+  }
   lqro_ctx* context() { return ctx_; }
 
  private:
@@ -269,6 +310,13 @@ class Swarm {
   lqro_ctx* ctx_ = nullptr;
   std::vector<double> x_, vpref_, newv_;
   std::vector<int> nbr_;
+  lqro_sim_model model_;
+  bool model_init_ = false;
+  std::vector<double> sx_, sxt_, sr_, srt_, sp_, snv_, spg_, snr_, svg_;
 };
+
+// element-wise copy out of a reference Matrix (operator[] const returns by value, MAT:58-61)
+template <class M>
+inline void copy(double* dst, const M& m, int n) { for (int i = 0; i < n; ++i) dst[i] = m[i]; }
 
 }  // namespace lqro

@@ -41,7 +41,8 @@ struct Plane { Vector3 point; Vector3 normal; };  // MAIN:844-855
 #include "lqro_dropin.hpp"
 
 typedef Matrix<16> State;
-struct Quadrotor { State x; Matrix<3, 1> vGoal, newV; };
+struct Quadrotor { State x, xTrue; Matrix<3, 3> Rot, RotTrue; Matrix<16, 16> P; Matrix<3, 1> vGoal, newV, pGoal; };
+static double demo_normal() { return 0.0; }  // stands in for the reference's normal() (MAIN:325-336)
 
 static bool read_doubles(double* d, int n) { for (int i = 0; i < n; ++i) if (scanf("%lf", d + i) != 1) return false; return true; }
 
@@ -56,6 +57,13 @@ int main(int argc, char** argv) {
   lqro::Swarm swarm(n, n - 1);
   swarm.setDynamics(A, B, L, E);
   lqro::setDynamics(A, B, L, E);  // per-function shims use their own small context
+  if (argc > 1) {  // instantiates the simulator-form update shims (MAIN:1408-1417); exercised by tests/test_gpu_sim.py via the C ABI
+    lqro_sim_model& m = swarm.simModel();
+    lqro::copy(m.L, L, 64); lqro::copy(m.E, E, 12);
+    swarm.commitSimModel();
+    swarm.update(qlist, demo_normal);
+    return 0;
+  }
   while (true) {
     bool ok = true;
     for (int i = 0; i < n && ok; ++i) ok = read_doubles(&qlist[i]->x[0], 16) && read_doubles(&qlist[i]->vGoal[0], 3);
