@@ -224,7 +224,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def sim_update_arm(ctx, x, L, E, stream, args):
-    """k_sim_update over every agent of the swarm: estimates = the swarm's states, identity attitudes, P = 1e-9 I, synthetic
+    """The simulator-form update (k_sim_flow, k_sim_noise, k_sim_filter) over every agent of the swarm: estimates = the swarm's states, identity attitudes, P = 1e-9 I, synthetic
     standard normals (numpy; the kernel's cost does not depend on their values), gains from the golden vectors.  Timed
     with CUDA events around each launch (lqro_sim_last_ms); beside it the reference's own update loop on one host core
     (oracle/_ref, 32 quads) when it is available."""
@@ -248,10 +248,11 @@ def sim_update_arm(ctx, x, L, E, stream, args):
     for it in range(2 + max(1, min(args.steps, 5))):
         ctx.sim_update_device(n, dx.data_ptr(), dR.data_ptr(), dP.data_ptr(), dxt.data_ptr(), dRT.data_ptr(), dnv.data_ptr(),
                               dpg.data_ptr(), dnr.data_ptr(), dvg.data_ptr(), du.data_ptr())
-        ms.append(ctx.sim_last_ms())
-    ms = ms[2:]
-    k_ms = float(np.mean(ms))
-    arm = {"kernel": "k_sim_update", "agents": n, "ms_per_launch": k_ms, "agents_per_s": n / (k_ms * 1e-3),
+        ms.append(ctx.sim_last_ms(parts=True))
+    ms = np.array(ms[2:])
+    k_ms = float(ms[:, 0].mean())
+    arm = {"kernels": {"k_sim_flow": float(ms[:, 1].mean()), "k_sim_noise": float(ms[:, 2].mean()), "k_sim_filter": float(ms[:, 3].mean())},
+           "agents": n, "ms_per_update": k_ms, "agents_per_s": n / (k_ms * 1e-3),
            "finite": bool(torch.isfinite(dx).all().item() and torch.isfinite(dP).all().item()),
            "api": "lqro_sim_update_device (state resident; standard normals supplied by the host, see lqro_msvc_normals)"}
     if not args.no_cpu:
@@ -266,12 +267,12 @@ def sim_update_arm(ctx, x, L, E, stream, args):
             sim.set_newv(np.zeros((m, 3)))
             sim.update()
             t0 = time.perf_counter()
-            for _ in range(3):
+            for _ in range(20):
                 sim.update()
             d = time.perf_counter() - t0
             sim.close()
-            arm["cpu_reference"] = {"agents_per_s": 3 * m / d, "cores": 1, "kind": "reference",
-                                    "sample": "the reference's own update loop (oracle/_ref ref_sim_update), 32 quads x 3 steps, %.2f s" % d}
+            arm["cpu_reference"] = {"agents_per_s": 20 * m / d, "cores": 1, "kind": "reference",
+                                    "sample": "the reference's own update loop (oracle/_ref ref_sim_update), 32 quads x 20 steps, %.2f s" % d}
         except Exception as e:  # oracle/_ref not present on this box
             arm["cpu_reference"] = {"unavailable": str(e)[:120]}
     return arm

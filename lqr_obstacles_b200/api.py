@@ -137,7 +137,7 @@ def load_library(path=None):
     lib.lqro_sim_update.argtypes = [c_void_p, c_int] + [c_void_p] * 10
     lib.lqro_sim_update_device.argtypes = [c_void_p, c_int] + [c_void_p] * 11
     lib.lqro_msvc_normals.argtypes = [ctypes.POINTER(ctypes.c_uint), c_int, c_void_p]
-    lib.lqro_sim_last_ms.argtypes = [c_void_p, ctypes.POINTER(c_float)]
+    lib.lqro_sim_last_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_sim_cycles.argtypes = [c_void_p, c_void_p, c_int]
     if path == _build.SO:
         _lib = lib
@@ -271,10 +271,11 @@ class Lqro:
         self._ck(self.lib.lqro_debug_sim_cycles(self.h, _p(c), int(reset)))
         return c
 
-    def sim_last_ms(self):
-        ms = c_float()
-        self._ck(self.lib.lqro_sim_last_ms(self.h, ctypes.byref(ms)))
-        return ms.value
+    def sim_last_ms(self, parts=False):
+        """device ms of the last simulator-form update; parts=True: (total, k_sim_flow, k_sim_noise, k_sim_filter)"""
+        ms = np.zeros(4, dtype=np.float32)
+        self._ck(self.lib.lqro_sim_last_ms(self.h, _p(ms)))
+        return tuple(float(v) for v in ms) if parts else float(ms[0])
 
     def counters(self):
         c = np.zeros(6, dtype=np.int64)

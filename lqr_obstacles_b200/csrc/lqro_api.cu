@@ -111,7 +111,8 @@ struct lqro_ctx {
   // simulator-form agent update (lqro_sim.cuh)
   LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false;
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
-  cudaEvent_t ev_sim[2] = {nullptr, nullptr};
+  cudaEvent_t ev_sim[4] = {nullptr, nullptr, nullptr, nullptr};
+  char* d_sim_scratch = nullptr; size_t sim_scratch_bytes = 0;
   long long launches = 0;
   int launches_extra = 0;
   std::string err;
@@ -181,7 +182,7 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
     void* q[] = {ctx->cls[c].NFt, ctx->cls[c].NF, ctx->cls[c].T, ctx->cls[c].CG, ctx->cls[c].prn};
     for (void* p : q) if (p) cudaFree(p);
   }
-  { void* q[] = {ctx->d_sim_model, ctx->d_sim_buf}; for (void* p : q) if (p) cudaFree(p); }
+  { void* q[] = {ctx->d_sim_model, ctx->d_sim_buf, ctx->d_sim_scratch}; for (void* p : q) if (p) cudaFree(p); }
   for (cudaEvent_t e : ctx->ev_sim) if (e) cudaEventDestroy(e);
   { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr, ctx->d_identity, ctx->d_chunk_ctr}; for (void* p : q) if (p) cudaFree(p); }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -748,24 +749,41 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
   return LQRO_OK;
 }
 
-static const int kSimWarps = 4;
+// Three launches per update (lqro_sim.cuh): flows + kalmanFilter1 (17.3 KB of shared memory per warp, 12 warps per SM), the
+// process-noise sample (4.5 KB, 32 warps per SM), propagate's tail + observation + kalmanFilter2 + findVGoal (11.3 KB, 20).
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
-  const size_t smem = (size_t)kSimWarps * sizeof(LqroSimWs);
+  const int wa = 4, wb = 8, wc = 4;
+  const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * sizeof(LqroSimWsB), smem_c = (size_t)wc * sizeof(LqroSimWsC);
   static bool attr_set = false;
   if (!attr_set) {
-    CU(cudaFuncSetAttribute(k_sim_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k_sim_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    CU(cudaFuncSetAttribute(k_sim_noise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    CU(cudaFuncSetAttribute(k_sim_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     attr_set = true;
   }
-  if (!ctx->ev_sim[0]) { CU(cudaEventCreate(&ctx->ev_sim[0])); CU(cudaEventCreate(&ctx->ev_sim[1])); }
-  int blocks = (n + kSimWarps - 1) / kSimWarps;
-  const int cap = ctx->sm_count * 3;  // three resident CTAs per SM (3 x 69.6 KB of shared memory); grid-stride beyond that
-  if (blocks > cap) blocks = cap;
+  for (cudaEvent_t& e : ctx->ev_sim) if (!e) CU(cudaEventCreate(&e));
+  const size_t need = sizeof(double) * (256 + 16 + 16) * (size_t)n;  // MMp | v1p | samp
+  if (ctx->sim_scratch_bytes < need) {
+    CU(cudaStreamSynchronize(st));
+    if (ctx->d_sim_scratch) cudaFree(ctx->d_sim_scratch);
+    ctx->d_sim_scratch = nullptr; ctx->sim_scratch_bytes = 0;
+    CU(cudaMalloc(&ctx->d_sim_scratch, need));
+    ctx->sim_scratch_bytes = need;
+  }
+  double* MMp = (double*)ctx->d_sim_scratch; double* v1p = MMp + 256 * (size_t)n; double* samp = v1p + 16 * (size_t)n;
+  auto grid = [&](int warps, int ctas_per_sm) { int b = (n + warps - 1) / warps; const int cap = ctx->sm_count * ctas_per_sm; return b > cap ? cap : b; };
   CU(cudaEventRecord(ctx->ev_sim[0], st));
-  k_sim_update<<<blocks, kSimWarps * 32, smem, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, newV, pGoal, normals, vGoal, u);
+  k_sim_flow<<<grid(wa, 3), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, newV, MMp, v1p, u);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
-  ctx->launches_extra++;
+  k_sim_noise<<<grid(wb, 4), wb * 32, smem_b, st>>>(n, MMp, normals, samp);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_sim[2], st));
+  k_sim_filter<<<grid(wc, 5), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, v1p, samp, vGoal);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_sim[3], st));
+  ctx->launches_extra += 3;
   return LQRO_OK;
 }
 
@@ -822,12 +840,13 @@ extern "C" int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, dou
   return LQRO_OK;
 }
 
-extern "C" int lqro_sim_last_ms(lqro_ctx* ctx, float* ms) {
-  if (!ctx || !ms) return LQRO_E_ARG;
+extern "C" int lqro_sim_last_ms(lqro_ctx* ctx, float* out4) {
+  if (!ctx || !out4) return LQRO_E_ARG;
   if (!ctx->ev_sim[0]) return fail(ctx, LQRO_E_STATE, "no simulator update yet");
   CU(cudaSetDevice(ctx->cfg.device));
-  CU(cudaEventSynchronize(ctx->ev_sim[1]));
-  CU(cudaEventElapsedTime(ms, ctx->ev_sim[0], ctx->ev_sim[1]));
+  CU(cudaEventSynchronize(ctx->ev_sim[3]));
+  CU(cudaEventElapsedTime(out4 + 0, ctx->ev_sim[0], ctx->ev_sim[3]));
+  for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(out4 + 1 + i, ctx->ev_sim[i], ctx->ev_sim[i + 1]));
   return LQRO_OK;
 }
 

@@ -645,10 +645,21 @@ SIMF void sim_find_vgoal(double* vG, const double* x, const double* R0, const do
   sim_mv3(vG, RLocal, s);
 }
 
-// ---- per-agent (per-warp) workspace -------------------------------------------------------------------
-struct LqroSimWs {
+// ---- per-agent (per-warp) workspaces of the three phases --------------------------------------------------
+// A: control input + both linearised flows (propagate's and kalmanFilter1's) + kalmanFilter1's covariance update
+struct LqroSimWsA {
   double F[256], Ae[256], MM[256], P[256], W[4 * 256];  // F doubles as exp(dt/2 F) once the Jacobian is spent
-  double x[16], xT[16], R[9], RT[9], u[4], z[6], hz[6], nrm[22], xdot[16], v1[16], v2[16], samp[16], small[16];
+  double x[16], xT[16], R[9], RT[9], u[4], xdot[16], v1[16], small[16];
+  int perm[32];
+};
+// B: the process-noise sample (Jacobi eigen-decomposition of propagate's MM)
+struct LqroSimWsB {
+  double D[256], V[256], nrm[16], samp[16], zero[16];
+};
+// C: propagate's state update, the observation, kalmanFilter2, the next goal velocity
+struct LqroSimWsC {
+  double P[256], W[4 * 256];
+  double x[16], xT[16], R[9], RT[9], z[6], hz[6], nrm[6], v1[16], v2[16], small[16];
   int perm[32];
 };
 // 6-dimensional operands of the observation / kalmanFilter2 overlay the part of W the 16x16 products there leave free
@@ -661,7 +672,7 @@ struct LqroSimObs {
 // A2 = exp(dt/2 F), MM = (dt/6)(M + 4 A2 M ~A2 + A M ~A), v1 = (dt/6)(xDot + 4 (A2 xDot) + A xDot).
 // xs, Rs: the state / rotation linearised about (shared memory of the warp).
 template <class P>
-SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroSimModel& md) {
+SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const LqroSimModel& md) {
   SIM_TIC();
   // Central-difference Jacobian (MAIN:392-401): the 32 evaluations f(x +- jStep e_c) run one per lane, results staged in W.
   // sim_f never reads the position x[0..2] (MAIN:341 extracts p and does not use it), so f(x + jStep e_0) is f(x) bit for
@@ -711,11 +722,15 @@ SIMN void sim_flow(LqroSimWs& w, const double* xs, const double* Rs, const LqroS
   SIM_TOC(5);
 }
 
-// One agent, MAIN:1409-1416.  On entry the workspace holds x, R (estimate), xT, RT (true state), P, nrm (22 standard
-// normals: 16 for propagate's process noise, 6 for the observation); newV/pGoal: 3 doubles each.
-// On exit x, R, xT, RT, P are updated, w.u holds the control input, vG the next goal velocity.
+// One agent, MAIN:1409-1416, in three phases (three kernels on the device, so that each runs at the occupancy its own
+// shared-memory footprint allows; the host build calls them back to back).
+//
+// Phase A.  In: w.x, w.R (estimate), w.xT, w.RT (true state), w.P, newV.  u = findU(); the linearised flow about the
+// TRUE state (propagate's F, A, A2, MM and Simpson increment, MAIN:443-450) -> MMp[256], v1p[16]; the flow about the
+// ESTIMATE and kalmanFilter1's update of x, R, P (MAIN:457-474).  kalmanFilter1 does not read anything propagate
+// writes, so running it before propagate's noise sample changes no value.
 template <class P>
-SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal, double* vG, const LqroSimModel& md) {
+SIMF void sim_phase_a(LqroSimWsA& w, const double* newV, double* MMp, double* v1p, const LqroSimModel& md) {
   SIM_TIC();
   {  // Input u = findU()  (vGoal = newV, MAIN:1409-1410)
     double x[16], R[9], u[4];
@@ -727,28 +742,11 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     P::sync();
   }
   SIM_TOC(0);
-  // propagate(xTrue, RotTrue, u, M)  (MAIN:442-455)
-  sim_flow<P>(w, w.xT, w.RT, md);
-  SIM_RETIC();
-  {
-    double* T1 = w.W; double* V = w.W + 256;
-    SIM_FOR(P, e, 256) T1[e] = w.MM[e];
-    SIM_FOR(P, i, 16) w.v2[i] = 0.0;
-    P::sync();
-    sim_sample_gaussian<P, 16>(w.samp, w.v2, T1, V, w.nrm);
-    SIM_TOC(6);
-    double r[3], R[9];
-    for (int i = 0; i < 3; ++i) r[i] = w.xT[6 + i] + w.v1[6 + i] + w.samp[6 + i];
-    for (int i = 0; i < 9; ++i) R[i] = w.RT[i];
-    sim_fold_rotation(R, r);
-    P::sync();
-    SIM_FOR(P, i, 16) w.xT[i] = (i >= 6 && i < 9) ? 0.0 : w.xT[i] + w.v1[i] + w.samp[i];
-    SIM_FOR(P, i, 9) w.RT[i] = R[i];
-    P::sync();
-  }
-  SIM_TOC(7);
-  // kalmanFilter1(x, Rot, u, M, P)  (MAIN:457-474)
-  sim_flow<P>(w, w.x, w.R, md);
+  sim_flow<P>(w, w.xT, w.RT, md);  // propagate(xTrue, RotTrue, u, M), MAIN:442-450 up to the noise sample
+  SIM_FOR(P, e, 256) MMp[e] = w.MM[e];
+  SIM_FOR(P, i, 16) v1p[i] = w.v1[i];
+  P::sync();
+  sim_flow<P>(w, w.x, w.R, md);    // kalmanFilter1(x, Rot, u, M, P), MAIN:457-474
   SIM_RETIC();
   {
     double* T1 = w.W; double* T2 = w.W + 256;
@@ -765,13 +763,43 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
     P::sync();
   }
   SIM_TOC(8);
+}
+
+// Phase B.  In: w.D = propagate's MM, w.nrm = the 16 process-noise normals.  Out: w.samp = sampleGaussian(0, MM)
+// (MAIN:450, SIM2:19-31).
+template <class P>
+SIMF void sim_phase_b(LqroSimWsB& w) {
+  SIM_TIC();
+  SIM_FOR(P, i, 16) w.zero[i] = 0.0;
+  P::sync();
+  sim_sample_gaussian<P, 16>(w.samp, w.zero, w.D, w.V, w.nrm);
+  SIM_TOC(6);
+}
+
+// Phase C.  In: w.x, w.R, w.P (after kalmanFilter1), w.xT, w.RT (before propagate), v1p / samp (phases A / B), w.nrm =
+// the 6 observation normals, pGoal.  Finishes propagate (MAIN:450-454), draws the observation (MAIN:1413), runs
+// kalmanFilter2 (MAIN:476-487) and findVGoal (MAIN:1416).
+template <class P>
+SIMF void sim_phase_c(LqroSimWsC& w, const double* v1p, const double* samp, const double* pGoal, double* vG, const LqroSimModel& md) {
+  SIM_TIC();
+  {
+    double r[3], R[9];
+    for (int i = 0; i < 3; ++i) r[i] = w.xT[6 + i] + v1p[6 + i] + samp[6 + i];
+    for (int i = 0; i < 9; ++i) R[i] = w.RT[i];
+    sim_fold_rotation(R, r);
+    P::sync();
+    SIM_FOR(P, i, 16) w.xT[i] = (i >= 6 && i < 9) ? 0.0 : w.xT[i] + v1p[i] + samp[i];
+    SIM_FOR(P, i, 9) w.RT[i] = R[i];
+    P::sync();
+  }
+  SIM_TOC(7);
   const LqroSimObs o(w.W);
   // Observation z = sampleGaussian(h(xTrue, RotTrue), N)  (MAIN:1413; h MAIN:369-390: rate gyros, then position)
   {
     SIM_FOR(P, i, 6) w.hz[i] = i < 3 ? w.xT[9 + i] : w.xT[i - 3];
     SIM_FOR(P, e, 36) o.S6[e] = md.N[e];
     P::sync();
-    sim_sample_gaussian<P, 6>(w.z, w.hz, o.S6, o.V6, w.nrm + 16);
+    sim_sample_gaussian<P, 6>(w.z, w.hz, o.S6, o.V6, w.nrm);
   }
   SIM_TOC(9);
   // kalmanFilter2(x, Rot, z, N, P)  (MAIN:476-487)
@@ -820,31 +848,70 @@ SIMF void sim_update_agent(LqroSimWs& w, const double* newV, const double* pGoal
 }
 
 #if defined(__CUDACC__)
-// grid-stride over agents, one warp each; dynamic shared memory = warps * sizeof(LqroSimWs) (17.4 KB per warp: three
-// 4-warp CTAs per SM)
-__global__ void __launch_bounds__(128, 3) k_sim_update(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
-                                                    double* __restrict__ Rot, double* __restrict__ Pcov, double* __restrict__ xTrue,
-                                                    double* __restrict__ RotTrue, const double* __restrict__ newV,
-                                                    const double* __restrict__ pGoal, const double* __restrict__ normals,
-                                                    double* __restrict__ vGoal, double* __restrict__ uOut) {
+// Three kernels, each grid-stride over agents with one warp per agent.  Scratch in HBM between them (per agent):
+// MMp[256] + v1p[16] (A -> B, C) and samp[16] (B -> C).
+__global__ void __launch_bounds__(128, 3) k_sim_flow(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
+                                                     double* __restrict__ Rot, double* __restrict__ Pcov, const double* __restrict__ xTrue,
+                                                     const double* __restrict__ RotTrue, const double* __restrict__ newV,
+                                                     double* __restrict__ MMp, double* __restrict__ v1p, double* __restrict__ uOut) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const LqroSimModel& md = *model;  // 3.6 KB of constants and gains, read through L1 (uniform or row-contiguous accesses)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  LqroSimWs& w = *reinterpret_cast<LqroSimWs*>(sim_smem + (size_t)warp * sizeof(LqroSimWs));
+  LqroSimWsA& w = *reinterpret_cast<LqroSimWsA*>(sim_smem + (size_t)warp * sizeof(LqroSimWsA));
   for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
     for (int e = lane; e < 256; e += 32) w.P[e] = Pcov[(size_t)a * 256 + e];
     if (lane < 16) { w.x[lane] = x[(size_t)a * 16 + lane]; w.xT[lane] = xTrue[(size_t)a * 16 + lane]; }
     if (lane < 9) { w.R[lane] = Rot[(size_t)a * 9 + lane]; w.RT[lane] = RotTrue[(size_t)a * 9 + lane]; }
-    if (lane < 22) w.nrm[lane] = normals[(size_t)a * 22 + lane];
     __syncwarp();
-    double nv[3], pg[3], vG[3];
-    for (int i = 0; i < 3; ++i) { nv[i] = newV[(size_t)a * 3 + i]; pg[i] = pGoal[(size_t)a * 3 + i]; }
-    sim_update_agent<SimWarp>(w, nv, pg, vG, md);
+    double nv[3];
+    for (int i = 0; i < 3; ++i) nv[i] = newV[(size_t)a * 3 + i];
+    sim_phase_a<SimWarp>(w, nv, MMp + (size_t)a * 256, v1p + (size_t)a * 16, md);
+    for (int e = lane; e < 256; e += 32) Pcov[(size_t)a * 256 + e] = w.P[e];
+    if (lane < 16) x[(size_t)a * 16 + lane] = w.x[lane];
+    if (lane < 9) Rot[(size_t)a * 9 + lane] = w.R[lane];
+    if (uOut && lane < 4) uOut[(size_t)a * 4 + lane] = w.u[lane];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) k_sim_noise(int n, const double* __restrict__ MMp, const double* __restrict__ normals,
+                                                      double* __restrict__ samp) {
+  extern __shared__ __align__(16) unsigned char sim_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  LqroSimWsB& w = *reinterpret_cast<LqroSimWsB*>(sim_smem + (size_t)warp * sizeof(LqroSimWsB));
+  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
+    for (int e = lane; e < 256; e += 32) w.D[e] = MMp[(size_t)a * 256 + e];
+    if (lane < 16) w.nrm[lane] = normals[(size_t)a * 22 + lane];
+    __syncwarp();
+    sim_phase_b<SimWarp>(w);
+    if (lane < 16) samp[(size_t)a * 16 + lane] = w.samp[lane];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128, 5) k_sim_filter(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
+                                                       double* __restrict__ Rot, double* __restrict__ Pcov, double* __restrict__ xTrue,
+                                                       double* __restrict__ RotTrue, const double* __restrict__ pGoal,
+                                                       const double* __restrict__ normals, const double* __restrict__ v1p,
+                                                       const double* __restrict__ samp, double* __restrict__ vGoal) {
+  extern __shared__ __align__(16) unsigned char sim_smem[];
+  const LqroSimModel& md = *model;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  LqroSimWsC& w = *reinterpret_cast<LqroSimWsC*>(sim_smem + (size_t)warp * sizeof(LqroSimWsC));
+  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
+    for (int e = lane; e < 256; e += 32) w.P[e] = Pcov[(size_t)a * 256 + e];
+    if (lane < 16) { w.x[lane] = x[(size_t)a * 16 + lane]; w.xT[lane] = xTrue[(size_t)a * 16 + lane]; }
+    if (lane < 9) { w.R[lane] = Rot[(size_t)a * 9 + lane]; w.RT[lane] = RotTrue[(size_t)a * 9 + lane]; }
+    if (lane < 6) w.nrm[lane] = normals[(size_t)a * 22 + 16 + lane];
+    __syncwarp();
+    double pg[3], vG[3], v1[16], sm[16];
+    for (int i = 0; i < 3; ++i) pg[i] = pGoal[(size_t)a * 3 + i];
+    for (int i = 0; i < 16; ++i) { v1[i] = v1p[(size_t)a * 16 + i]; sm[i] = samp[(size_t)a * 16 + i]; }
+    sim_phase_c<SimWarp>(w, v1, sm, pg, vG, md);
     for (int e = lane; e < 256; e += 32) Pcov[(size_t)a * 256 + e] = w.P[e];
     if (lane < 16) { x[(size_t)a * 16 + lane] = w.x[lane]; xTrue[(size_t)a * 16 + lane] = w.xT[lane]; }
     if (lane < 9) { Rot[(size_t)a * 9 + lane] = w.R[lane]; RotTrue[(size_t)a * 9 + lane] = w.RT[lane]; }
     if (lane == 0) { vGoal[(size_t)a * 3] = vG[0]; vGoal[(size_t)a * 3 + 1] = vG[1]; vGoal[(size_t)a * 3 + 2] = vG[2]; }
-    if (uOut && lane < 4) uOut[(size_t)a * 4 + lane] = w.u[lane];
     __syncwarp();
   }
 }

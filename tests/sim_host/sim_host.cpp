@@ -9,19 +9,29 @@ extern "C" int simhost_model_doubles(void) { return (int)(sizeof(LqroSimModel) /
 
 extern "C" void simhost_update(int n, const LqroSimModel* md, double* x, double* Rot, double* P, double* xTrue, double* RotTrue,
                                const double* newV, const double* pGoal, const double* normals, double* vGoal, double* u) {
-  static LqroSimWs w;
+  static LqroSimWsA wa; static LqroSimWsB wb; static LqroSimWsC wc;
   for (int a = 0; a < n; ++a) {
-    for (int e = 0; e < 256; ++e) w.P[e] = P[256 * a + e];
-    for (int e = 0; e < 16; ++e) { w.x[e] = x[16 * a + e]; w.xT[e] = xTrue[16 * a + e]; }
-    for (int e = 0; e < 9; ++e) { w.R[e] = Rot[9 * a + e]; w.RT[e] = RotTrue[9 * a + e]; }
-    for (int e = 0; e < 22; ++e) w.nrm[e] = normals[22 * a + e];
-    double vG[3];
-    sim_update_agent<SimWarp>(w, newV + 3 * a, pGoal + 3 * a, vG, *md);
-    for (int e = 0; e < 256; ++e) P[256 * a + e] = w.P[e];
-    for (int e = 0; e < 16; ++e) { x[16 * a + e] = w.x[e]; xTrue[16 * a + e] = w.xT[e]; }
-    for (int e = 0; e < 9; ++e) { Rot[9 * a + e] = w.R[e]; RotTrue[9 * a + e] = w.RT[e]; }
+    double MMp[256], v1p[16], vG[3];
+    // phase A (k_sim_flow)
+    for (int e = 0; e < 256; ++e) wa.P[e] = P[256 * a + e];
+    for (int e = 0; e < 16; ++e) { wa.x[e] = x[16 * a + e]; wa.xT[e] = xTrue[16 * a + e]; }
+    for (int e = 0; e < 9; ++e) { wa.R[e] = Rot[9 * a + e]; wa.RT[e] = RotTrue[9 * a + e]; }
+    sim_phase_a<SimWarp>(wa, newV + 3 * a, MMp, v1p, *md);
+    // phase B (k_sim_noise)
+    for (int e = 0; e < 256; ++e) wb.D[e] = MMp[e];
+    for (int e = 0; e < 16; ++e) wb.nrm[e] = normals[22 * a + e];
+    sim_phase_b<SimWarp>(wb);
+    // phase C (k_sim_filter)
+    for (int e = 0; e < 256; ++e) wc.P[e] = wa.P[e];
+    for (int e = 0; e < 16; ++e) { wc.x[e] = wa.x[e]; wc.xT[e] = xTrue[16 * a + e]; }
+    for (int e = 0; e < 9; ++e) { wc.R[e] = wa.R[e]; wc.RT[e] = RotTrue[9 * a + e]; }
+    for (int e = 0; e < 6; ++e) wc.nrm[e] = normals[22 * a + 16 + e];
+    sim_phase_c<SimWarp>(wc, v1p, wb.samp, pGoal + 3 * a, vG, *md);
+    for (int e = 0; e < 256; ++e) P[256 * a + e] = wc.P[e];
+    for (int e = 0; e < 16; ++e) { x[16 * a + e] = wc.x[e]; xTrue[16 * a + e] = wc.xT[e]; }
+    for (int e = 0; e < 9; ++e) { Rot[9 * a + e] = wc.R[e]; RotTrue[9 * a + e] = wc.RT[e]; }
     for (int e = 0; e < 3; ++e) vGoal[3 * a + e] = vG[e];
-    if (u) for (int e = 0; e < 4; ++e) u[4 * a + e] = w.u[e];
+    if (u) for (int e = 0; e < 4; ++e) u[4 * a + e] = wa.u[e];
   }
 }
 extern "C" void simhost_exp16(const double* q, double* out) {

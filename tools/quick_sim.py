@@ -1,4 +1,5 @@
-"""Kernel time of the simulator-form update (k_sim_update) for N agents (copies of the 6 golden quads at step 90)."""
+"""Kernel times of the simulator-form update (k_sim_flow / k_sim_noise / k_sim_filter) for N agents (copies of the 6 golden
+quads at step 90)."""
 import os
 import sys
 
@@ -19,5 +20,5 @@ ms = []
 for it in range(4):
     st = [tile(g["s90_before_" + k]) for k in ("x", "Rot", "P", "xTrue", "RotTrue")]
     c.sim_update(*st, tile(g["s90_newV"]), tile(g["s90_before_pGoal"]), tile(g["s90_normals"]))
-    ms.append(c.sim_last_ms())
-print("k_sim_update N=%d ms per launch:" % N, ["%.3f" % m for m in ms], "agents/s %.3e" % (N / (min(ms) * 1e-3)))
+    ms.append(c.sim_last_ms(parts=True))
+print("sim update N=%d ms (total, flow, noise, filter):" % N, [tuple(round(v, 3) for v in m) for m in ms], "agents/s %.3e" % (N / (min(m[0] for m in ms) * 1e-3)))

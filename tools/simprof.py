@@ -28,5 +28,5 @@ cyc = c.sim_cycles()
 names = ['findU', 'Jacobian (f)', 'exp: powers+Pade', 'exp: solve', 'exp: squarings', 'noise cov + Simpson', 'Jacobi16 + sample',
          'propagate tail', 'KF1 tail', 'observation sample', 'KF2', 'findVGoal']
 tot = cyc[:12].sum()
-print('N', N, 'kernel ms', c.sim_last_ms(), 'cycles per agent', tot / N)
+print('N', N, 'kernel ms (total, flow, noise, filter)', c.sim_last_ms(parts=True), 'cycles per agent', tot / N)
 for n, v in zip(names, cyc): print('%-22s %12.0f cyc/agent %5.1f%%' % (n, v / N, 100 * v / tot))
