@@ -200,7 +200,7 @@ int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m);
  *     vGoal = newV; u = findU(); propagateU(u); kalmanFilter1(x, Rot, u, M, P);
  *     z = sampleGaussian(h(xTrue, RotTrue), N); kalmanFilter2(x, Rot, z, N, P); vGoal = findVGoal();
  * (riccatiControllerSteady MAIN:547-576, propagate MAIN:442-455, kalmanFilter1/2 MAIN:457-487,
- * riccatiControllerSteadyPosition MAIN:579-608), one warp per agent in each of three kernels.  HOST pointers, updated in place:
+ * riccatiControllerSteadyPosition MAIN:579-608), one warp per agent (per flow) in each of the update's kernels.  HOST pointers, updated in place:
  *   x n*16 estimate, Rot n*9, P n*256 covariance, xTrue n*16, RotTrue n*9 (Quadrotor::x, Rot, P, xTrue, RotTrue)
  *   newV n*3 (calculateNewV's output), pGoal n*3 (Quadrotor::pGoal)
  *   normals n*22: the standard normals the reference's sampleGaussian calls draw for agent i, in its order -- 16 for
@@ -220,8 +220,9 @@ int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, dou
  * input of lqro_sim_update rather than generated on the device. */
 int lqro_msvc_normals(unsigned int* seed_io, int count, double* out);
 /* Device time (ms) of the last lqro_sim_update / lqro_sim_update_device (CUDA events on the launching stream;
- * synchronises): [0] the three kernels together, [1] k_sim_flow (control input, both linearised flows, kalmanFilter1),
- * [2] k_sim_noise (process-noise sample), [3] k_sim_filter (propagate's tail, observation, kalmanFilter2, findVGoal). */
+ * synchronises): [0] all kernels together, [1] k_sim_control + k_sim_flow (control input, the two linearised flows of every
+ * agent), [2] k_sim_noise (process-noise sample), [3] k_sim_filter (state / covariance updates of kalmanFilter1 and propagate,
+ * observation, kalmanFilter2, findVGoal). */
 int lqro_sim_last_ms(lqro_ctx* ctx, float* out4);
 
 /* ---- multi-GPU: agents partitioned, one all-gather of the state per step --------------------- */

@@ -749,11 +749,12 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
   return LQRO_OK;
 }
 
-// Three launches per update (lqro_sim.cuh): flows + kalmanFilter1 (17.3 KB of shared memory per warp, 12 warps per SM), the
-// process-noise sample (4.5 KB, 32 warps per SM), propagate's tail + observation + kalmanFilter2 + findVGoal (11.3 KB, 20).
+// Four launches per update (lqro_sim.cuh): the control input (thread per agent), the two linearised flows of every agent as
+// independent warp tasks (15.3 KB of shared memory per warp, 15 warps per SM), the process-noise sample (4.5 KB, 32 warps per
+// SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
-  const int wa = 4, wb = 8, wc = 4;
+  const int wa = 5, wb = 8, wc = 4;
   const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * sizeof(LqroSimWsB), smem_c = (size_t)wc * sizeof(LqroSimWsC);
   static bool attr_set = false;
   if (!attr_set) {
@@ -763,7 +764,8 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
     attr_set = true;
   }
   for (cudaEvent_t& e : ctx->ev_sim) if (!e) CU(cudaEventCreate(&e));
-  const size_t need = sizeof(double) * (256 + 16 + 16) * (size_t)n;  // MMp | v1p | samp
+  const size_t per = 4 + 2 * 256 + 2 * 16 + 256 + 16;  // u | MM x2 | v1 x2 | Ae | samp   (doubles per agent)
+  const size_t need = sizeof(double) * per * (size_t)n;
   if (ctx->sim_scratch_bytes < need) {
     CU(cudaStreamSynchronize(st));
     if (ctx->d_sim_scratch) cudaFree(ctx->d_sim_scratch);
@@ -771,19 +773,24 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
     CU(cudaMalloc(&ctx->d_sim_scratch, need));
     ctx->sim_scratch_bytes = need;
   }
-  double* MMp = (double*)ctx->d_sim_scratch; double* v1p = MMp + 256 * (size_t)n; double* samp = v1p + 16 * (size_t)n;
-  auto grid = [&](int warps, int ctas_per_sm) { int b = (n + warps - 1) / warps; const int cap = ctx->sm_count * ctas_per_sm; return b > cap ? cap : b; };
+  const size_t N = (size_t)n;
+  LqroSimScratch sc;
+  sc.MM = (double*)ctx->d_sim_scratch; sc.Ae = sc.MM + 512 * N; sc.v1 = sc.Ae + 256 * N; sc.samp = sc.v1 + 32 * N; sc.u = sc.samp + 16 * N;
+  auto grid = [&](long long items, int warps, int ctas_per_sm) {
+    long long b = (items + warps - 1) / warps; const long long cap = (long long)ctx->sm_count * ctas_per_sm; return (int)(b > cap ? cap : b); };
   CU(cudaEventRecord(ctx->ev_sim[0], st));
-  k_sim_flow<<<grid(wa, 3), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, newV, MMp, v1p, u);
+  k_sim_control<<<(n + 127) / 128, 128, 0, st>>>(n, ctx->d_sim_model, x, Rot, newV, sc.u, u);
+  CU(cudaGetLastError());
+  k_sim_flow<<<grid(2LL * n, wa, 3), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
-  k_sim_noise<<<grid(wb, 4), wb * 32, smem_b, st>>>(n, MMp, normals, samp);
+  k_sim_noise<<<grid(n, wb, 4), wb * 32, smem_b, st>>>(n, normals, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[2], st));
-  k_sim_filter<<<grid(wc, 5), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, v1p, samp, vGoal);
+  k_sim_filter<<<grid(n, wc, 5), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, sc, vGoal);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[3], st));
-  ctx->launches_extra += 3;
+  ctx->launches_extra += 4;
   return LQRO_OK;
 }
 

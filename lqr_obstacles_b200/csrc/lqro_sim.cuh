@@ -646,18 +646,18 @@ SIMF void sim_find_vgoal(double* vG, const double* x, const double* R0, const do
 }
 
 // ---- per-agent (per-warp) workspaces of the three phases --------------------------------------------------
-// A: control input + both linearised flows (propagate's and kalmanFilter1's) + kalmanFilter1's covariance update
-struct LqroSimWsA {
-  double F[256], Ae[256], MM[256], P[256], W[4 * 256];  // F doubles as exp(dt/2 F) once the Jacobian is spent
-  double x[16], xT[16], R[9], RT[9], u[4], xdot[16], v1[16], small[16];
+// A: one linearised flow (propagate's about the true state, or kalmanFilter1's about the estimate)
+struct alignas(16) LqroSimWsA {
+  double F[256], Ae[256], MM[256], W[4 * 256];  // F doubles as exp(dt/2 F) once the Jacobian is spent
+  double xs[16], Rs[9], u[4], xdot[16], v1[16], small[16];
   int perm[32];
 };
 // B: the process-noise sample (Jacobi eigen-decomposition of propagate's MM)
-struct LqroSimWsB {
+struct alignas(16) LqroSimWsB {
   double D[256], V[256], nrm[16], samp[16], zero[16];
 };
-// C: propagate's state update, the observation, kalmanFilter2, the next goal velocity
-struct LqroSimWsC {
+// C: kalmanFilter1's and propagate's state updates, the observation, kalmanFilter2, the next goal velocity
+struct alignas(16) LqroSimWsC {
   double P[256], W[4 * 256];
   double x[16], xT[16], R[9], RT[9], z[6], hz[6], nrm[6], v1[16], v2[16], small[16];
   int perm[32];
@@ -722,47 +722,24 @@ SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const Lqro
   SIM_TOC(5);
 }
 
-// One agent, MAIN:1409-1416, in three phases (three kernels on the device, so that each runs at the occupancy its own
-// shared-memory footprint allows; the host build calls them back to back).
+// One agent, MAIN:1409-1416, in phases (four kernels on the device, so that each runs at the occupancy its own
+// shared-memory footprint allows; the host build calls them back to back):
+//   control  u = findU()                                                        thread per agent
+//   flow     the linearised flow about the TRUE state (propagate, MAIN:443-450) and about the ESTIMATE
+//            (kalmanFilter1, MAIN:458-468): two independent tasks per agent       warp per task
+//   noise    sampleGaussian(0, MM) of propagate (MAIN:450)                       warp per agent
+//   filter   the state / covariance updates of kalmanFilter1 and propagate, the observation, kalmanFilter2, findVGoal
+// kalmanFilter1 reads nothing propagate writes (and vice versa), so their order does not change any value.
 //
-// Phase A.  In: w.x, w.R (estimate), w.xT, w.RT (true state), w.P, newV.  u = findU(); the linearised flow about the
-// TRUE state (propagate's F, A, A2, MM and Simpson increment, MAIN:443-450) -> MMp[256], v1p[16]; the flow about the
-// ESTIMATE and kalmanFilter1's update of x, R, P (MAIN:457-474).  kalmanFilter1 does not read anything propagate
-// writes, so running it before propagate's noise sample changes no value.
+// Flow phase.  In: w.xs, w.Rs (the state / rotation linearised about), w.u.  Out: MM[256], v1[16] (noise covariance and
+// Simpson increment) and, if Ae_out != 0, A = exp(dt F)[256].
 template <class P>
-SIMF void sim_phase_a(LqroSimWsA& w, const double* newV, double* MMp, double* v1p, const LqroSimModel& md) {
-  SIM_TIC();
-  {  // Input u = findU()  (vGoal = newV, MAIN:1409-1410)
-    double x[16], R[9], u[4];
-    for (int i = 0; i < 16; ++i) x[i] = w.x[i];
-    for (int i = 0; i < 9; ++i) R[i] = w.R[i];
-    sim_find_u(u, x, R, newV, md);
-    P::sync();
-    if (P::lane() == 0) for (int i = 0; i < 4; ++i) w.u[i] = u[i];
-    P::sync();
-  }
-  SIM_TOC(0);
-  sim_flow<P>(w, w.xT, w.RT, md);  // propagate(xTrue, RotTrue, u, M), MAIN:442-450 up to the noise sample
-  SIM_FOR(P, e, 256) MMp[e] = w.MM[e];
-  SIM_FOR(P, i, 16) v1p[i] = w.v1[i];
+SIMF void sim_phase_flow(LqroSimWsA& w, double* MM_out, double* v1_out, double* Ae_out, const LqroSimModel& md) {
+  sim_flow<P>(w, w.xs, w.Rs, md);
+  SIM_FOR(P, e, 256) MM_out[e] = w.MM[e];
+  SIM_FOR(P, i, 16) v1_out[i] = w.v1[i];
+  if (Ae_out) { SIM_FOR(P, e, 256) Ae_out[e] = w.Ae[e]; }
   P::sync();
-  sim_flow<P>(w, w.x, w.R, md);    // kalmanFilter1(x, Rot, u, M, P), MAIN:457-474
-  SIM_RETIC();
-  {
-    double* T1 = w.W; double* T2 = w.W + 256;
-    sim_mm<P, false>(T1, w.Ae, w.P, 16, 16, 16);
-    sim_mm<P, true>(T2, T1, w.Ae, 16, 16, 16);
-    SIM_FOR(P, e, 256) w.P[e] = T2[e] + w.MM[e];
-    double r[3], R[9];
-    for (int i = 0; i < 3; ++i) r[i] = w.x[6 + i] + w.v1[6 + i];
-    for (int i = 0; i < 9; ++i) R[i] = w.R[i];
-    sim_fold_rotation(R, r);
-    P::sync();
-    SIM_FOR(P, i, 16) w.x[i] = (i >= 6 && i < 9) ? 0.0 : w.x[i] + w.v1[i];
-    SIM_FOR(P, i, 9) w.R[i] = R[i];
-    P::sync();
-  }
-  SIM_TOC(8);
 }
 
 // Phase B.  In: w.D = propagate's MM, w.nrm = the 16 process-noise normals.  Out: w.samp = sampleGaussian(0, MM)
@@ -776,12 +753,29 @@ SIMF void sim_phase_b(LqroSimWsB& w) {
   SIM_TOC(6);
 }
 
-// Phase C.  In: w.x, w.R, w.P (after kalmanFilter1), w.xT, w.RT (before propagate), v1p / samp (phases A / B), w.nrm =
-// the 6 observation normals, pGoal.  Finishes propagate (MAIN:450-454), draws the observation (MAIN:1413), runs
-// kalmanFilter2 (MAIN:476-487) and findVGoal (MAIN:1416).
+// Filter phase.  In: w.x, w.R, w.P (estimate), w.xT, w.RT (true state), the flow results of both tasks (Ae_k, MM_k, v1k:
+// kalmanFilter1's; v1p: propagate's), samp (noise phase), w.nrm = the 6 observation normals, pGoal.  Finishes
+// kalmanFilter1 (MAIN:465-473) and propagate (MAIN:450-454), draws the observation (MAIN:1413), runs kalmanFilter2
+// (MAIN:476-487) and findVGoal (MAIN:1416).
 template <class P>
-SIMF void sim_phase_c(LqroSimWsC& w, const double* v1p, const double* samp, const double* pGoal, double* vG, const LqroSimModel& md) {
+SIMF void sim_phase_filter(LqroSimWsC& w, const double* Ae_k, const double* MM_k, const double* v1k, const double* v1p,
+                           const double* samp, const double* pGoal, double* vG, const LqroSimModel& md) {
   SIM_TIC();
+  {  // kalmanFilter1: P = A*P*~A + MM; x += increment; fold the rotation error
+    double* T1 = w.W; double* T2 = w.W + 256;
+    sim_mm<P, false>(T1, Ae_k, w.P, 16, 16, 16);
+    sim_mm<P, true>(T2, T1, Ae_k, 16, 16, 16);
+    SIM_FOR(P, e, 256) w.P[e] = T2[e] + MM_k[e];
+    double r[3], R[9];
+    for (int i = 0; i < 3; ++i) r[i] = w.x[6 + i] + v1k[6 + i];
+    for (int i = 0; i < 9; ++i) R[i] = w.R[i];
+    sim_fold_rotation(R, r);
+    P::sync();
+    SIM_FOR(P, i, 16) w.x[i] = (i >= 6 && i < 9) ? 0.0 : w.x[i] + v1k[i];
+    SIM_FOR(P, i, 9) w.R[i] = R[i];
+    P::sync();
+  }
+  SIM_TOC(8);
   {
     double r[3], R[9];
     for (int i = 0; i < 3; ++i) r[i] = w.xT[6 + i] + v1p[6 + i] + samp[6 + i];
@@ -848,43 +842,52 @@ SIMF void sim_phase_c(LqroSimWsC& w, const double* v1p, const double* samp, cons
 }
 
 #if defined(__CUDACC__)
-// Three kernels, each grid-stride over agents with one warp per agent.  Scratch in HBM between them (per agent):
-// MMp[256] + v1p[16] (A -> B, C) and samp[16] (B -> C).
-__global__ void __launch_bounds__(128, 3) k_sim_flow(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
-                                                     double* __restrict__ Rot, double* __restrict__ Pcov, const double* __restrict__ xTrue,
-                                                     const double* __restrict__ RotTrue, const double* __restrict__ newV,
-                                                     double* __restrict__ MMp, double* __restrict__ v1p, double* __restrict__ uOut) {
+// Scratch in HBM between the kernels (per agent): u[4]; per flow task MM[256] + v1[16]; kalmanFilter1's A[256]; samp[16].
+struct LqroSimScratch {
+  double *u, *MM, *v1, *Ae, *samp;  // u [n][4], MM [2n][256], v1 [2n][16], Ae [n][256], samp [n][16]; task = 2*agent + {0: true state, 1: estimate}
+};
+
+__global__ void __launch_bounds__(128) k_sim_control(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+                                                     const double* __restrict__ Rot, const double* __restrict__ newV,
+                                                     double* __restrict__ u, double* __restrict__ uOut) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  double xs[16], R[9], nv[3], uu[4];
+  for (int i = 0; i < 16; ++i) xs[i] = x[(size_t)a * 16 + i];
+  for (int i = 0; i < 9; ++i) R[i] = Rot[(size_t)a * 9 + i];
+  for (int i = 0; i < 3; ++i) nv[i] = newV[(size_t)a * 3 + i];
+  sim_find_u(uu, xs, R, nv, *model);
+  for (int i = 0; i < 4; ++i) { u[(size_t)a * 4 + i] = uu[i]; if (uOut) uOut[(size_t)a * 4 + i] = uu[i]; }
+}
+
+__global__ void __launch_bounds__(160, 3) k_sim_flow(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+                                                     const double* __restrict__ Rot, const double* __restrict__ xTrue,
+                                                     const double* __restrict__ RotTrue, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const LqroSimModel& md = *model;  // 3.6 KB of constants and gains, read through L1 (uniform or row-contiguous accesses)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   LqroSimWsA& w = *reinterpret_cast<LqroSimWsA*>(sim_smem + (size_t)warp * sizeof(LqroSimWsA));
-  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
-    for (int e = lane; e < 256; e += 32) w.P[e] = Pcov[(size_t)a * 256 + e];
-    if (lane < 16) { w.x[lane] = x[(size_t)a * 16 + lane]; w.xT[lane] = xTrue[(size_t)a * 16 + lane]; }
-    if (lane < 9) { w.R[lane] = Rot[(size_t)a * 9 + lane]; w.RT[lane] = RotTrue[(size_t)a * 9 + lane]; }
+  for (int t = blockIdx.x * wpb + warp; t < 2 * n; t += gridDim.x * wpb) {
+    const int a = t >> 1, est = t & 1;
+    const double* xs = est ? x : xTrue; const double* Rs = est ? Rot : RotTrue;
+    if (lane < 16) w.xs[lane] = xs[(size_t)a * 16 + lane];
+    if (lane < 9) w.Rs[lane] = Rs[(size_t)a * 9 + lane];
+    if (lane < 4) w.u[lane] = sc.u[(size_t)a * 4 + lane];
     __syncwarp();
-    double nv[3];
-    for (int i = 0; i < 3; ++i) nv[i] = newV[(size_t)a * 3 + i];
-    sim_phase_a<SimWarp>(w, nv, MMp + (size_t)a * 256, v1p + (size_t)a * 16, md);
-    for (int e = lane; e < 256; e += 32) Pcov[(size_t)a * 256 + e] = w.P[e];
-    if (lane < 16) x[(size_t)a * 16 + lane] = w.x[lane];
-    if (lane < 9) Rot[(size_t)a * 9 + lane] = w.R[lane];
-    if (uOut && lane < 4) uOut[(size_t)a * 4 + lane] = w.u[lane];
-    __syncwarp();
+    sim_phase_flow<SimWarp>(w, sc.MM + (size_t)t * 256, sc.v1 + (size_t)t * 16, est ? sc.Ae + (size_t)a * 256 : nullptr, md);
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_sim_noise(int n, const double* __restrict__ MMp, const double* __restrict__ normals,
-                                                      double* __restrict__ samp) {
+__global__ void __launch_bounds__(256, 4) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   LqroSimWsB& w = *reinterpret_cast<LqroSimWsB*>(sim_smem + (size_t)warp * sizeof(LqroSimWsB));
   for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
-    for (int e = lane; e < 256; e += 32) w.D[e] = MMp[(size_t)a * 256 + e];
+    for (int e = lane; e < 256; e += 32) w.D[e] = sc.MM[(size_t)(2 * a) * 256 + e];
     if (lane < 16) w.nrm[lane] = normals[(size_t)a * 22 + lane];
     __syncwarp();
     sim_phase_b<SimWarp>(w);
-    if (lane < 16) samp[(size_t)a * 16 + lane] = w.samp[lane];
+    if (lane < 16) sc.samp[(size_t)a * 16 + lane] = w.samp[lane];
     __syncwarp();
   }
 }
@@ -892,8 +895,7 @@ __global__ void __launch_bounds__(256, 4) k_sim_noise(int n, const double* __res
 __global__ void __launch_bounds__(128, 5) k_sim_filter(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
                                                        double* __restrict__ Rot, double* __restrict__ Pcov, double* __restrict__ xTrue,
                                                        double* __restrict__ RotTrue, const double* __restrict__ pGoal,
-                                                       const double* __restrict__ normals, const double* __restrict__ v1p,
-                                                       const double* __restrict__ samp, double* __restrict__ vGoal) {
+                                                       const double* __restrict__ normals, LqroSimScratch sc, double* __restrict__ vGoal) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const LqroSimModel& md = *model;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -904,10 +906,10 @@ __global__ void __launch_bounds__(128, 5) k_sim_filter(int n, const LqroSimModel
     if (lane < 9) { w.R[lane] = Rot[(size_t)a * 9 + lane]; w.RT[lane] = RotTrue[(size_t)a * 9 + lane]; }
     if (lane < 6) w.nrm[lane] = normals[(size_t)a * 22 + 16 + lane];
     __syncwarp();
-    double pg[3], vG[3], v1[16], sm[16];
+    double pg[3], vG[3];
     for (int i = 0; i < 3; ++i) pg[i] = pGoal[(size_t)a * 3 + i];
-    for (int i = 0; i < 16; ++i) { v1[i] = v1p[(size_t)a * 16 + i]; sm[i] = samp[(size_t)a * 16 + i]; }
-    sim_phase_c<SimWarp>(w, v1, sm, pg, vG, md);
+    sim_phase_filter<SimWarp>(w, sc.Ae + (size_t)a * 256, sc.MM + (size_t)(2 * a + 1) * 256, sc.v1 + (size_t)(2 * a + 1) * 16,
+                              sc.v1 + (size_t)(2 * a) * 16, sc.samp + (size_t)a * 16, pg, vG, md);
     for (int e = lane; e < 256; e += 32) Pcov[(size_t)a * 256 + e] = w.P[e];
     if (lane < 16) { x[(size_t)a * 16 + lane] = w.x[lane]; xTrue[(size_t)a * 16 + lane] = w.xT[lane]; }
     if (lane < 9) { Rot[(size_t)a * 9 + lane] = w.R[lane]; RotTrue[(size_t)a * 9 + lane] = w.RT[lane]; }

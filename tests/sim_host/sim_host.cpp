@@ -11,27 +11,31 @@ extern "C" void simhost_update(int n, const LqroSimModel* md, double* x, double*
                                const double* newV, const double* pGoal, const double* normals, double* vGoal, double* u) {
   static LqroSimWsA wa; static LqroSimWsB wb; static LqroSimWsC wc;
   for (int a = 0; a < n; ++a) {
-    double MMp[256], v1p[16], vG[3];
-    // phase A (k_sim_flow)
-    for (int e = 0; e < 256; ++e) wa.P[e] = P[256 * a + e];
-    for (int e = 0; e < 16; ++e) { wa.x[e] = x[16 * a + e]; wa.xT[e] = xTrue[16 * a + e]; }
-    for (int e = 0; e < 9; ++e) { wa.R[e] = Rot[9 * a + e]; wa.RT[e] = RotTrue[9 * a + e]; }
-    sim_phase_a<SimWarp>(wa, newV + 3 * a, MMp, v1p, *md);
-    // phase B (k_sim_noise)
-    for (int e = 0; e < 256; ++e) wb.D[e] = MMp[e];
+    double MM[2][256], v1[2][16], Ae[256], uu[4], vG[3];
+    // control (k_sim_control)
+    sim_find_u(uu, x + 16 * a, Rot + 9 * a, newV + 3 * a, *md);
+    // flow, task 0 = true state, task 1 = estimate (k_sim_flow)
+    for (int est = 0; est < 2; ++est) {
+      for (int e = 0; e < 16; ++e) wa.xs[e] = est ? x[16 * a + e] : xTrue[16 * a + e];
+      for (int e = 0; e < 9; ++e) wa.Rs[e] = est ? Rot[9 * a + e] : RotTrue[9 * a + e];
+      for (int e = 0; e < 4; ++e) wa.u[e] = uu[e];
+      sim_phase_flow<SimWarp>(wa, MM[est], v1[est], est ? Ae : nullptr, *md);
+    }
+    // noise (k_sim_noise)
+    for (int e = 0; e < 256; ++e) wb.D[e] = MM[0][e];
     for (int e = 0; e < 16; ++e) wb.nrm[e] = normals[22 * a + e];
     sim_phase_b<SimWarp>(wb);
-    // phase C (k_sim_filter)
-    for (int e = 0; e < 256; ++e) wc.P[e] = wa.P[e];
-    for (int e = 0; e < 16; ++e) { wc.x[e] = wa.x[e]; wc.xT[e] = xTrue[16 * a + e]; }
-    for (int e = 0; e < 9; ++e) { wc.R[e] = wa.R[e]; wc.RT[e] = RotTrue[9 * a + e]; }
+    // filter (k_sim_filter)
+    for (int e = 0; e < 256; ++e) wc.P[e] = P[256 * a + e];
+    for (int e = 0; e < 16; ++e) { wc.x[e] = x[16 * a + e]; wc.xT[e] = xTrue[16 * a + e]; }
+    for (int e = 0; e < 9; ++e) { wc.R[e] = Rot[9 * a + e]; wc.RT[e] = RotTrue[9 * a + e]; }
     for (int e = 0; e < 6; ++e) wc.nrm[e] = normals[22 * a + 16 + e];
-    sim_phase_c<SimWarp>(wc, v1p, wb.samp, pGoal + 3 * a, vG, *md);
+    sim_phase_filter<SimWarp>(wc, Ae, MM[1], v1[1], v1[0], wb.samp, pGoal + 3 * a, vG, *md);
     for (int e = 0; e < 256; ++e) P[256 * a + e] = wc.P[e];
     for (int e = 0; e < 16; ++e) { x[16 * a + e] = wc.x[e]; xTrue[16 * a + e] = wc.xT[e]; }
     for (int e = 0; e < 9; ++e) { Rot[9 * a + e] = wc.R[e]; RotTrue[9 * a + e] = wc.RT[e]; }
     for (int e = 0; e < 3; ++e) vGoal[3 * a + e] = vG[e];
-    if (u) for (int e = 0; e < 4; ++e) u[4 * a + e] = wa.u[e];
+    if (u) for (int e = 0; e < 4; ++e) u[4 * a + e] = uu[e];
   }
 }
 extern "C" void simhost_exp16(const double* q, double* out) {
