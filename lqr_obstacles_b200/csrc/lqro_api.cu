@@ -750,12 +750,12 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
 }
 
 // Four launches per update (lqro_sim.cuh): the control input (thread per agent), the two linearised flows of every agent as
-// independent warp tasks (15.3 KB of shared memory per warp, 15 warps per SM), the process-noise sample (4.5 KB, 32 warps per
-// SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
+// independent warp tasks (15.3 KB of shared memory per warp, 15 warps per SM), the process-noise sample (four agents per warp, 17 KB per warp,
+// 12-16 warps per SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
-  const int wa = 5, wb = 8, wc = 4;
-  const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * sizeof(LqroSimWsB), smem_c = (size_t)wc * sizeof(LqroSimWsC);
+  const int wa = 5, wb = 4, wc = 4;
+  const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * 4 * SIM_NOISE_GROUP_DOUBLES * sizeof(double), smem_c = (size_t)wc * sizeof(LqroSimWsC);
   static bool attr_set = false;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_sim_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
@@ -784,7 +784,7 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   k_sim_flow<<<grid(2LL * n, wa, 3), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
-  k_sim_noise<<<grid(n, wb, 4), wb * 32, smem_b, st>>>(n, normals, sc);
+  k_sim_noise<<<grid((n + 3) / 4, wb, 3), wb * 32, smem_b, st>>>(n, normals, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[2], st));
   k_sim_filter<<<grid(n, wc, 5), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, sc, vGoal);

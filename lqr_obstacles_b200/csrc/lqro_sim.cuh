@@ -330,6 +330,9 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
   if (N == 16) SIM_TOC(4);
 }
 
+#ifdef SIM_COUNT_JACOBI
+static long sim_jacobi_counts[4];  // host-side instrumentation: iterations / rotations of the 16x16 and 6x6 problems
+#endif
 // Cyclic-by-row Jacobi eigen-decomposition (MAT:674-757): D <- eigenvalues on the diagonal (upper triangle
 // worked on), V <- eigenvectors.  D holds the matrix on entry.
 template <class P, int N>
@@ -347,6 +350,9 @@ SIMF void sim_jacobi(double* D, double* V) {
     P::argmax(maximum, bi);
     const int p = bi < pivotRow ? bi : pivotRow, q = bi < pivotRow ? pivotRow : bi;
     pivotRow = (pivotRow + 1) % N;
+#ifdef SIM_COUNT_JACOBI
+    sim_jacobi_counts[N == 16 ? 0 : 2] += 1; if (maximum > DBL_EPSILON) sim_jacobi_counts[N == 16 ? 1 : 3] += 1;
+#endif
     if (maximum <= DBL_EPSILON) {
       if (++zeroCount == N) break;
       continue;
@@ -878,16 +884,102 @@ __global__ void __launch_bounds__(160, 3) k_sim_flow(int n, const LqroSimModel* 
   }
 }
 
-__global__ void __launch_bounds__(256, 4) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
+// The noise phase for FOUR agents per warp (8 lanes each).  The Jacobi iteration (MAT:674-757) is a chain of scalar FP64
+// divisions and square roots that every lane of a warp would execute redundantly for ONE agent; with four agents side
+// by side the same instructions serve four.  The four groups run the loop in lockstep (a group that has converged idles
+// on dummy operands), every group performs exactly the operation sequence of sim_jacobi / sim_sample_gaussian.
+// Shared memory per group: D[256] | Vt[256] (eigenvectors TRANSPOSED: a rotation touches two contiguous rows) | nrm[16].
+#define SIM_NOISE_GROUP_DOUBLES (256 + 256 + 16 + 4)  // +4: group bases fall on different banks
+__global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
+  constexpr int N = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  LqroSimWsB& w = *reinterpret_cast<LqroSimWsB*>(sim_smem + (size_t)warp * sizeof(LqroSimWsB));
-  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
-    for (int e = lane; e < 256; e += 32) w.D[e] = sc.MM[(size_t)(2 * a) * 256 + e];
-    if (lane < 16) w.nrm[lane] = normals[(size_t)a * 22 + lane];
+  const int g = lane >> 3, sl = lane & 7;
+  const unsigned gmask = 0xffu << (8 * g);
+  double* D = reinterpret_cast<double*>(sim_smem) + (size_t)(warp * 4 + g) * SIM_NOISE_GROUP_DOUBLES;
+  double* Vt = D + 256; double* nrm = Vt + 256;
+  for (int a0 = (blockIdx.x * wpb + warp) * 4; a0 < n; a0 += gridDim.x * wpb * 4) {
+    const int a = a0 + g;
+    bool done = a >= n;
+    if (!done) {
+      for (int e = sl; e < 256; e += 8) { D[e] = sc.MM[(size_t)(2 * a) * 256 + e]; Vt[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; }
+      for (int e = sl; e < 16; e += 8) nrm[e] = normals[(size_t)a * 22 + e];
+    }
     __syncwarp();
-    sim_phase_b<SimWarp>(w);
-    if (lane < 16) sc.samp[(size_t)a * 16 + lane] = w.samp[lane];
+    int pivotRow = 0, zeroCount = 0;
+    while (!__all_sync(0xffffffffu, done)) {
+      double maximum = 0.0; int bi = 0x7fffffff;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int k = sl + 8 * t;
+        if (k != pivotRow) {
+          const double av = fabs(k < pivotRow ? D[k * N + pivotRow] : D[pivotRow * N + k]);
+          if (av > maximum) { maximum = av; bi = k; }
+        }
+      }
+      {  // first maximum of the group: REDUX over the group's eight lanes
+        const unsigned hi = (unsigned)__double2hiint(maximum), lo = (unsigned)__double2loint(maximum);
+        const unsigned mh = __reduce_max_sync(gmask, hi);
+        const unsigned ml = __reduce_max_sync(gmask, hi == mh ? lo : 0u);
+        bi = (int)__reduce_min_sync(gmask, (hi == mh && lo == ml) ? (unsigned)bi : 0xffffffffu);
+        maximum = __hiloint2double((int)mh, (int)ml);
+      }
+      const bool rot = !done && maximum > DBL_EPSILON;
+      const int p = rot ? (bi < pivotRow ? bi : pivotRow) : 0, q = rot ? (bi < pivotRow ? pivotRow : bi) : 1;
+      if (!done) {
+        pivotRow = (pivotRow + 1) % N;
+        if (rot) zeroCount = 0;
+        else if (++zeroCount == N) done = true;
+      }
+      const double Dpq = rot ? D[p * N + q] : 1.0;
+      const double theta = 0.5 * ((rot ? D[q * N + q] : 0.0) - (rot ? D[p * N + p] : 0.0)) / Dpq;
+      double t = 1 / (fabs(theta) + sim_hypot(theta, 1));
+      if (theta < 0) t = -t;
+      const double c = 1 / sim_hypot(t, 1);
+      const double s = c * t;
+      const double tau = s / (1 + c);
+      __syncwarp();
+      if (rot) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = sl + 8 * u;
+          if (r < N) {
+            if (r < p) {
+              const double Drp = D[r * N + p], Drq = D[r * N + q];
+              D[r * N + p] -= s * (Drq + tau * Drp);
+              D[r * N + q] += s * (Drp - tau * Drq);
+            } else if (r > p && r < q) {
+              const double Drp = D[p * N + r], Drq = D[r * N + q];
+              D[p * N + r] -= s * (Drq + tau * Drp);
+              D[r * N + q] += s * (Drp - tau * Drq);
+            } else if (r > q) {
+              const double Drp = D[p * N + r], Drq = D[q * N + r];
+              D[p * N + r] -= s * (Drq + tau * Drp);
+              D[q * N + r] += s * (Drp - tau * Drq);
+            } else if (r == p) {
+              D[p * N + p] -= t * Dpq;
+              D[q * N + q] += t * Dpq;
+              D[p * N + q] = 0;
+            }
+          } else {
+            const int rr = r - N;
+            const double Vrp = Vt[p * N + rr], Vrq = Vt[q * N + rr];
+            Vt[p * N + rr] -= s * (Vrq + tau * Vrp);
+            Vt[q * N + rr] += s * (Vrp - tau * Vrq);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (a < n) {  // sample = SVec * sqrt(SVal) * normals + 0  (SIM2:19-31)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = sl + 8 * u;
+        double acc = 0.0;
+        for (int j = 0; j < N; ++j) acc += (Vt[j * N + i] * sqrt(D[j * N + j])) * nrm[j];
+        sc.samp[(size_t)a * 16 + i] = acc + 0.0;
+      }
+    }
     __syncwarp();
   }
 }
