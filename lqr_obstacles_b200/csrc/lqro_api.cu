@@ -109,7 +109,7 @@ struct lqro_ctx {
   // multi-GPU
   lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
   // simulator-form agent update (lqro_sim.cuh)
-  LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false;
+  LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false, sim_attr_set = false;
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
   cudaEvent_t ev_sim[4] = {nullptr, nullptr, nullptr, nullptr};
   char* d_sim_scratch = nullptr; size_t sim_scratch_bytes = 0;
@@ -756,12 +756,11 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
   const int wa = 5, wb = 4, wc = 4;
   const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * 4 * SIM_NOISE_GROUP_DOUBLES * sizeof(double), smem_c = (size_t)wc * sizeof(LqroSimWsC);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!ctx->sim_attr_set) {  // per device, hence per context
     CU(cudaFuncSetAttribute(k_sim_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
     CU(cudaFuncSetAttribute(k_sim_noise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     CU(cudaFuncSetAttribute(k_sim_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-    attr_set = true;
+    ctx->sim_attr_set = true;
   }
   for (cudaEvent_t& e : ctx->ev_sim) if (!e) CU(cudaEventCreate(&e));
   const size_t per = 4 + 2 * 256 + 2 * 16 + 256 + 16;  // u | MM x2 | v1 x2 | Ae | samp   (doubles per agent)

@@ -7,12 +7,20 @@
 // noise, sampleGaussian SIM2:19-31 through the cyclic Jacobi eigen-decomposition MAT:674-757), kalmanFilter1/2
 // (MAIN:457-487, 6x6 inverse by full-pivot Gauss MAT:603-671) and riccatiControllerSteadyPosition (MAIN:579-608).
 //
-// Mapping: ONE WARP PER AGENT.  Every 16x16 operand (Jacobian, both exponentials, their Pade workspace, the two
-// covariances) lives in the warp's 23 KB of shared memory; a lane owns 8 elements of each 16x16 product (every
-// element a left-to-right sum, as Matrix::operator* MAT:219-231 forms it); the 34 evaluations of f behind one
-// Jacobian run one (column, side) pair per lane with the 3x3 exponential in registers; pivot searches (full-pivot
-// Gauss, Jacobi row pivot) are warp arg-max reductions that keep the reference's first-maximum rule; the rotation
-// of one Jacobi step is spread over the 16 lanes of the two rows/columns it touches.  Too small for tensor cores.
+// Mapping: FOUR KERNELS, each sized by the shared memory its phase needs (the phases are latency-bound chains of small FP64
+// operations -- full-pivot Gauss, Jacobi rotations, 16-term sums -- so resident warps per SM decide the throughput):
+//   k_sim_control  thread per agent   u = findU()
+//   k_sim_flow     warp per TASK      the linearised flow about the true state (propagate) and about the estimate
+//                                     (kalmanFilter1) are independent: 2 tasks per agent.  One flow = 32 evaluations of f
+//                                     (one per lane, 3x3 exponential in registers), two 16x16 Pade exponentials, the noise
+//                                     covariance MM and the Simpson increment; 7 16x16 buffers = 15 KB per warp, 15 warps/SM
+//   k_sim_noise    8 lanes per agent  Jacobi eigen-decomposition of propagate's MM + the sample: its scalar division /
+//                                     square-root chain is executed once per warp for four agents in lockstep
+//   k_sim_filter   warp per agent     covariance / state updates of kalmanFilter1 and propagate, the observation sample,
+//                                     kalmanFilter2 (6x6 full-pivot inverse), findVGoal; 11 KB per warp, 20 warps/SM
+// A lane owns 8 elements of each 16x16 product (every element a left-to-right sum, as Matrix::operator* MAT:219-231
+// forms it); pivot searches (full-pivot Gauss, Jacobi row pivot) are REDUX arg-max reductions that keep the reference's
+// first-maximum rule.  Too small for tensor cores.
 //
 // ARITHMETIC.  Same contract as the rest of the library (-fmad=false, IEEE / and sqrt, reference operation order),
 // so everything except the libm calls (tan, asin, atan2, log, hypot: CUDA's differ from glibc's in the last bit) is
@@ -22,7 +30,8 @@
 // kernel applies the covariance square root.
 //
 // DUAL COMPILATION.  This file also compiles as plain C++ (no __CUDACC__): the warp policy collapses to a single
-// sequential lane.  Only tests/sim_host uses that build, to check the kernel's logic against the compiled reference
+// sequential lane (the warp-specialised routines -- sim_solve_warp, sim_mm16_warp, k_sim_noise's packed Jacobi -- have
+// generic twins that the host build uses).  Only tests/sim_host uses that build, to check the kernel's logic against the compiled reference
 // where no GPU exists; liblqro.so never contains it.
 #pragma once
 #include <math.h>
@@ -889,7 +898,8 @@ __global__ void __launch_bounds__(160, 3) k_sim_flow(int n, const LqroSimModel* 
 // by side the same instructions serve four.  The four groups run the loop in lockstep (a group that has converged idles
 // on dummy operands), every group performs exactly the operation sequence of sim_jacobi / sim_sample_gaussian.
 // Shared memory per group: D[256] | Vt[256] (eigenvectors TRANSPOSED: a rotation touches two contiguous rows) | nrm[16].
-#define SIM_NOISE_GROUP_DOUBLES (256 + 256 + 16 + 4)  // +4: group bases fall on different banks
+#define SIM_NOISE_LD 17  // row stride of D: its column accesses (the pivot search, the rotation) fall on distinct banks
+#define SIM_NOISE_GROUP_DOUBLES (16 * SIM_NOISE_LD + 256 + 16 + 4)  // +4: group bases fall on different banks
 __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   constexpr int N = 16;
@@ -897,12 +907,13 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
   const int g = lane >> 3, sl = lane & 7;
   const unsigned gmask = 0xffu << (8 * g);
   double* D = reinterpret_cast<double*>(sim_smem) + (size_t)(warp * 4 + g) * SIM_NOISE_GROUP_DOUBLES;
-  double* Vt = D + 256; double* nrm = Vt + 256;
+  constexpr int LD = SIM_NOISE_LD;
+  double* Vt = D + 16 * LD; double* nrm = Vt + 256;
   for (int a0 = (blockIdx.x * wpb + warp) * 4; a0 < n; a0 += gridDim.x * wpb * 4) {
     const int a = a0 + g;
     bool done = a >= n;
     if (!done) {
-      for (int e = sl; e < 256; e += 8) { D[e] = sc.MM[(size_t)(2 * a) * 256 + e]; Vt[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; }
+      for (int e = sl; e < 256; e += 8) { D[(e >> 4) * LD + (e & 15)] = sc.MM[(size_t)(2 * a) * 256 + e]; Vt[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; }
       for (int e = sl; e < 16; e += 8) nrm[e] = normals[(size_t)a * 22 + e];
     }
     __syncwarp();
@@ -913,16 +924,15 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
       for (int t = 0; t < 2; ++t) {
         const int k = sl + 8 * t;
         if (k != pivotRow) {
-          const double av = fabs(k < pivotRow ? D[k * N + pivotRow] : D[pivotRow * N + k]);
+          const double av = fabs(k < pivotRow ? D[k * LD + pivotRow] : D[pivotRow * LD + k]);
           if (av > maximum) { maximum = av; bi = k; }
         }
       }
-      {  // first maximum of the group: REDUX over the group's eight lanes
-        const unsigned hi = (unsigned)__double2hiint(maximum), lo = (unsigned)__double2loint(maximum);
-        const unsigned mh = __reduce_max_sync(gmask, hi);
-        const unsigned ml = __reduce_max_sync(gmask, hi == mh ? lo : 0u);
-        bi = (int)__reduce_min_sync(gmask, (hi == mh && lo == ml) ? (unsigned)bi : 0xffffffffu);
-        maximum = __hiloint2double((int)mh, (int)ml);
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {  // first maximum of the group's eight lanes: larger value, then smaller index
+        const double ov = __shfl_xor_sync(0xffffffffu, maximum, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > maximum || (ov == maximum && oi < bi)) { maximum = ov; bi = oi; }
       }
       const bool rot = !done && maximum > DBL_EPSILON;
       const int p = rot ? (bi < pivotRow ? bi : pivotRow) : 0, q = rot ? (bi < pivotRow ? pivotRow : bi) : 1;
@@ -931,8 +941,8 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
         if (rot) zeroCount = 0;
         else if (++zeroCount == N) done = true;
       }
-      const double Dpq = rot ? D[p * N + q] : 1.0;
-      const double theta = 0.5 * ((rot ? D[q * N + q] : 0.0) - (rot ? D[p * N + p] : 0.0)) / Dpq;
+      const double Dpq = rot ? D[p * LD + q] : 1.0;
+      const double theta = 0.5 * ((rot ? D[q * LD + q] : 0.0) - (rot ? D[p * LD + p] : 0.0)) / Dpq;
       double t = 1 / (fabs(theta) + sim_hypot(theta, 1));
       if (theta < 0) t = -t;
       const double c = 1 / sim_hypot(t, 1);
@@ -945,21 +955,21 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
           const int r = sl + 8 * u;
           if (r < N) {
             if (r < p) {
-              const double Drp = D[r * N + p], Drq = D[r * N + q];
-              D[r * N + p] -= s * (Drq + tau * Drp);
-              D[r * N + q] += s * (Drp - tau * Drq);
+              const double Drp = D[r * LD + p], Drq = D[r * LD + q];
+              D[r * LD + p] -= s * (Drq + tau * Drp);
+              D[r * LD + q] += s * (Drp - tau * Drq);
             } else if (r > p && r < q) {
-              const double Drp = D[p * N + r], Drq = D[r * N + q];
-              D[p * N + r] -= s * (Drq + tau * Drp);
-              D[r * N + q] += s * (Drp - tau * Drq);
+              const double Drp = D[p * LD + r], Drq = D[r * LD + q];
+              D[p * LD + r] -= s * (Drq + tau * Drp);
+              D[r * LD + q] += s * (Drp - tau * Drq);
             } else if (r > q) {
-              const double Drp = D[p * N + r], Drq = D[q * N + r];
-              D[p * N + r] -= s * (Drq + tau * Drp);
-              D[q * N + r] += s * (Drp - tau * Drq);
+              const double Drp = D[p * LD + r], Drq = D[q * LD + r];
+              D[p * LD + r] -= s * (Drq + tau * Drp);
+              D[q * LD + r] += s * (Drp - tau * Drq);
             } else if (r == p) {
-              D[p * N + p] -= t * Dpq;
-              D[q * N + q] += t * Dpq;
-              D[p * N + q] = 0;
+              D[p * LD + p] -= t * Dpq;
+              D[q * LD + q] += t * Dpq;
+              D[p * LD + q] = 0;
             }
           } else {
             const int rr = r - N;
@@ -976,7 +986,7 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
       for (int u = 0; u < 2; ++u) {
         const int i = sl + 8 * u;
         double acc = 0.0;
-        for (int j = 0; j < N; ++j) acc += (Vt[j * N + i] * sqrt(D[j * N + j])) * nrm[j];
+        for (int j = 0; j < N; ++j) acc += (Vt[j * N + i] * sqrt(D[j * LD + j])) * nrm[j];
         sc.samp[(size_t)a * 16 + i] = acc + 0.0;
       }
     }
