@@ -206,48 +206,54 @@ SIMF void sim_solve(double* m, double* inv, int* rp, int* cp, double* fac) {
 // c of inv, for every second row.  No index divisions; a step first gathers its row offsets, factors and operands
 // (independent loads), then computes and stores.
 template <int N>
-SIMF void sim_solve_warp(double* m, double* inv, int* rp, int* cp, double* fac) {
-  constexpr int TM = (N + 1) / 2;
+SIMF void sim_solve_warp(double* m, double* inv, int* /*rp*/, int* /*cp*/, double* fac) {
+  // The row / column permutations live in registers, one nibble per position (every lane keeps the same copy), so a
+  // pivot exchange costs no shared-memory round trip; the pivot search of step k+1 is folded into the update of step k
+  // (its candidates are exactly the elements that update has just produced).
   const int lane = (int)(threadIdx.x & 31), h = lane >> 4, c = lane & 15;
   const bool act = c < N;
-  if (lane < N) { rp[lane] = lane; cp[lane] = lane; }
-  __syncwarp();
-  for (int k = 0; k < N; ++k) {
-    double best = 0.0; int key = 0x7fffffff;  // key = (row position << 4) | column position: row-major order of the scan
-    if (act && c >= k) {
-      const int col = cp[c];
-      for (int i0 = k + h; i0 < N; i0 += 8) {
-        double a[4];
+  unsigned long long rpk = 0xfedcba9876543210ull, cpk = 0xfedcba9876543210ull;
+#define SIM_NIB(pk, i) ((int)((pk) >> (4 * (i))) & 15)
+  double best = 0.0; int key = 0x7fffffff;  // key = (row position << 4) | column position: row-major order of the scan
+  if (act) {
+    for (int i0 = h; i0 < N; i0 += 8) {
+      double a[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; a[t] = i < N ? fabs(m[rp[i] * N + col]) : 0.0; }
+      for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; a[t] = i < N ? fabs(m[i * N + c]) : 0.0; }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { if (a[t] > best) { best = a[t]; key = ((i0 + 2 * t) << 4) | c; } }
-      }
+      for (int t = 0; t < 4; ++t) { if (a[t] > best) { best = a[t]; key = ((i0 + 2 * t) << 4) | c; } }
     }
+  }
+  for (int k = 0; k < N; ++k) {
     SimWarp::argmax(best, key);
     if (!(best > 0.0)) key = (k << 4) | k;
-    __syncwarp();
-    if (lane == 0) {
+    {
       const int mr = key >> 4, mc = key & 15;
-      int s = rp[k]; rp[k] = rp[mr]; rp[mr] = s;
-      s = cp[k]; cp[k] = cp[mc]; cp[mc] = s;
+      const unsigned long long rk_ = SIM_NIB(rpk, k), rm_ = SIM_NIB(rpk, mr), ck_ = SIM_NIB(cpk, k), cm_ = SIM_NIB(cpk, mc);
+      rpk = (rpk & ~(0xfull << (4 * k)) & ~(0xfull << (4 * mr))) | (rm_ << (4 * k)) | (mr != k ? rk_ << (4 * mr) : 0ull);
+      cpk = (cpk & ~(0xfull << (4 * k)) & ~(0xfull << (4 * mc))) | (cm_ << (4 * k)) | (mc != k ? ck_ << (4 * mc) : 0ull);
     }
-    __syncwarp();
-    const int rk = rp[k] * N, ck = cp[k], mcol = act ? cp[c] : 0;
-    if (lane > k && lane < N) fac[lane] = m[rp[lane] * N + ck] / m[rk + ck];
+    const int rk = SIM_NIB(rpk, k) * N, ck = SIM_NIB(cpk, k), mcol = act ? SIM_NIB(cpk, c) : 0;
+    if (lane > k && lane < N) fac[lane] = m[SIM_NIB(rpk, lane) * N + ck] / m[rk + ck];
     const double pm = m[rk + mcol], pi = act ? inv[rk + c] : 0.0;
     __syncwarp();
+    best = 0.0; key = 0x7fffffff;
     if (act) {
       for (int i0 = k + 1 + h; i0 < N; i0 += 8) {  // rows in chunks of four: gather, compute, store
         int rr[4]; double ff[4], mv[4], iv[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; const bool ok = i < N; rr[t] = ok ? rp[i] * N : -1; ff[t] = ok ? fac[i] : 0.0; }
+        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; const bool ok = i < N; rr[t] = ok ? SIM_NIB(rpk, i) * N : -1; ff[t] = ok ? fac[i] : 0.0; }
 #pragma unroll
         for (int t = 0; t < 4; ++t) { if (rr[t] >= 0) { mv[t] = m[rr[t] + mcol]; iv[t] = inv[rr[t] + c]; } }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (rr[t] >= 0) {
-            if (c > k) m[rr[t] + mcol] = mv[t] - ff[t] * pm;
+            if (c > k) {
+              const double nv = mv[t] - ff[t] * pm;
+              m[rr[t] + mcol] = nv;
+              const double av = fabs(nv);
+              if (av > best) { best = av; key = ((i0 + 2 * t) << 4) | c; }  // candidate of the next step's pivot scan
+            }
             inv[rr[t] + c] = iv[t] - ff[t] * pi;
           }
         }
@@ -256,7 +262,7 @@ SIMF void sim_solve_warp(double* m, double* inv, int* rp, int* cp, double* fac) 
     __syncwarp();
   }
   for (int k = N - 1; k >= 0; --k) {
-    const int rk = rp[k] * N, ck = cp[k];
+    const int rk = SIM_NIB(rpk, k) * N, ck = SIM_NIB(cpk, k);
     const double pv = act ? inv[rk + c] / m[rk + ck] : 0.0;  // both half-warps form the same quotient
     __syncwarp();
     if (act) {
@@ -264,7 +270,7 @@ SIMF void sim_solve_warp(double* m, double* inv, int* rp, int* cp, double* fac) 
       for (int i0 = h; i0 < k; i0 += 8) {
         int rr[4]; double mf[4], iv[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; rr[t] = i < k ? rp[i] * N : -1; }
+        for (int t = 0; t < 4; ++t) { const int i = i0 + 2 * t; rr[t] = i < k ? SIM_NIB(rpk, i) * N : -1; }
 #pragma unroll
         for (int t = 0; t < 4; ++t) { if (rr[t] >= 0) { mf[t] = m[rr[t] + ck]; iv[t] = inv[rr[t] + c]; } }
 #pragma unroll
@@ -274,10 +280,10 @@ SIMF void sim_solve_warp(double* m, double* inv, int* rp, int* cp, double* fac) 
     __syncwarp();
   }
   if (act) {
-#pragma unroll
-    for (int t = 0; t < TM; ++t) { const int i = h + 2 * t; if (i < N) m[cp[i] * N + c] = inv[rp[i] * N + c]; }
+    for (int i = h; i < N; i += 2) m[SIM_NIB(cpk, i) * N + c] = inv[SIM_NIB(rpk, i) * N + c];
   }
   __syncwarp();
+#undef SIM_NIB
 }
 template <> SIMF void sim_solve<SimWarp, 16>(double* m, double* inv, int* rp, int* cp, double* fac) { sim_solve_warp<16>(m, inv, rp, cp, fac); }
 template <> SIMF void sim_solve<SimWarp, 6>(double* m, double* inv, int* rp, int* cp, double* fac) { sim_solve_warp<6>(m, inv, rp, cp, fac); }
