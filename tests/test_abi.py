@@ -71,6 +71,14 @@ def test_bad_arguments_return_codes(product_lib):
     assert product_lib.lqro_create(ctypes.byref(c), ctypes.byref(h)) == -1  # LQRO_E_ARG
     assert product_lib.lqro_create(None, ctypes.byref(h)) == -1
     assert product_lib.lqro_destroy(None) == 0
+    # simulator-form update: no context / no buffers => LQRO_E_ARG, never a crash
+    assert product_lib.lqro_sim_update(None, 1, *([None] * 10)) == -1
+    assert product_lib.lqro_sim_update_device(None, 1, *([None] * 11)) == -1
+    assert product_lib.lqro_sim_set_model(None, None) == -1
+    seed = ctypes.c_uint(1)
+    assert product_lib.lqro_msvc_normals(ctypes.byref(seed), -1, None) == -1
+    assert product_lib.lqro_msvc_normals(None, 1, None) == -1
+    assert product_lib.lqro_msvc_normals(ctypes.byref(seed), 0, None) == 0 and seed.value == 1
 
 
 def test_swarm_generator_is_deterministic():

@@ -69,6 +69,34 @@ def test_many_agents_grid_stride_and_determinism(ctx, sim_golden):
     assert ctx.sim_last_ms() > 0.0
 
 
+def test_against_the_host_build_of_the_kernel_source_on_random_states(ctx, sim_golden):
+    """no reference needed: the same source compiled as plain C++ (tests/sim_host, bit-identical to the reference where the
+    reference is available, tests/test_sim_host.py) on random states, incl. the control input u and odd agent counts
+    (7 = one full and one partial group of the 4-agents-per-warp noise kernel; 1)"""
+    from _libs import SimHost
+
+    sh = SimHost()
+    g = sim_golden
+    rng = np.random.default_rng(5)
+    for n in (7, 1):
+        x = rng.normal(size=(n, 16)) * 0.5
+        x[:, 6:9] = 0.0
+        x[:, 12:] = 1.226 + 0.05 * rng.normal(size=(n, 4))
+        xT = x + rng.normal(size=(n, 16)) * 1e-4
+        xT[:, 6:9] = 0.0
+        Rs = np.array([np.linalg.qr(np.eye(3) + 0.1 * rng.normal(size=(3, 3)))[0].ravel() for _ in range(n)])
+        Rs *= np.sign(Rs[:, [0]])
+        A = rng.normal(size=(n, 16, 16)) * 1e-5
+        Pc = (A @ A.transpose(0, 2, 1) + 1e-9 * np.eye(16)).reshape(n, 256)
+        st = dict(x=x, Rot=Rs, P=Pc, xTrue=xT, RotTrue=Rs.copy(), pGoal=rng.normal(size=(n, 3)) * 5)
+        newV, normals = rng.normal(size=(n, 3)), rng.normal(size=(n, 22))
+        want = sh.update(g["model"], st, newV, normals)
+        got = {k: st[k].copy() for k in KEYS}
+        got["vGoal"], got["u"] = ctx.sim_update(got["x"], got["Rot"], got["P"], got["xTrue"], got["RotTrue"], newV, st["pGoal"], normals)
+        for k in KEYS + ("vGoal", "u"):
+            _close(got[k], want[k], "n=%d %s" % (n, k))
+
+
 def test_requires_a_model():
     from lqr_obstacles_b200 import Lqro, LqroError
 
