@@ -255,6 +255,19 @@ def sim_update_arm(ctx, x, L, E, stream, args):
            "agents": n, "ms_per_update": k_ms, "agents_per_s": n / (k_ms * 1e-3),
            "finite": bool(torch.isfinite(dx).all().item() and torch.isfinite(dP).all().item()),
            "api": "lqro_sim_update_device (state resident; standard normals supplied by the host, see lqro_msvc_normals)"}
+    # whole time step resident on the device (lqro_timestep_device: avoidance step on the context's state + the update;
+    # the neighbour table is the resident one): a closed loop of a few steps, CUDA events on the launching stream
+    ts = []
+    for it in range(2 + max(1, min(args.steps, 5))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.timestep_device(dR.data_ptr(), dP.data_ptr(), dxt.data_ptr(), dRT.data_ptr(), dpg.data_ptr(), dnr.data_ptr(), dvg.data_ptr())
+        e1.record(stream)
+        stream.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    arm["timestep"] = {"ms_per_step": float(np.mean(ts[2:])), "api": "lqro_timestep_device (MAIN:1373-1417 for every agent: k_pairs, k_hull, "
+                       "k_new_velocity, k_sim_control, k_sim_flow, k_sim_noise, k_sim_filter; state resident)",
+                       "gpu_launches_per_step": 7, "finite": bool(torch.isfinite(dvg).all().item())}
     if not args.no_cpu:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -214,6 +214,15 @@ int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, dou
 int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue,
                            const double* d_newV, const double* d_pGoal, const double* d_normals, double* d_vGoal, double* d_u,
                            void* stream);
+/* One WHOLE time step of the reference's loop (MAIN:1373-1417) for the owned agents with everything resident on the device,
+ * launches only: [ncclAllGather of the estimates when a communicator exists] -> [neighbour table rebuilt from the current
+ * positions with LQRO_FLAG_DEVICE_KNN, else the resident table] -> the avoidance step (as lqro_step_device on the context's
+ * state buffer, lqro_device_state) -> the simulator-form update of the owned agents' block of that buffer.
+ *   d_Rot, d_P, d_xTrue, d_RotTrue, d_pGoal, d_normals: as lqro_sim_update_device, n_local agents
+ *   d_vgoal n_local*3  in: Quadrotor::vGoal (the preferred velocities of this step), out: the next step's
+ * Per step only the 22*n_local standard normals have to come from the host. */
+int lqro_timestep_device(lqro_ctx* ctx, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue, const double* d_pGoal,
+                         const double* d_normals, double* d_vgoal, void* stream);
 /* Host helper, no device work: `count` draws of the reference's normal() (MAIN:325-336) from the MSVC CRT rand() stream
  * it was written against (RAND_MAX 32767, seed*214013+2531011; random() MAIN:320-322).  *seed_io: generator state in,
  * state out (srand(1) at program start => 1).  The stream is sequential across agents, which is why the noise is an

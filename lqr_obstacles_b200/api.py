@@ -41,7 +41,7 @@ EXPORTS = [
     "lqro_debug_hull_cycles", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
-    "lqro_sim_last_ms", "lqro_debug_sim_cycles",
+    "lqro_sim_last_ms", "lqro_debug_sim_cycles", "lqro_timestep_device",
 ]
 
 
@@ -139,6 +139,7 @@ def load_library(path=None):
     lib.lqro_msvc_normals.argtypes = [ctypes.POINTER(ctypes.c_uint), c_int, c_void_p]
     lib.lqro_sim_last_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_sim_cycles.argtypes = [c_void_p, c_void_p, c_int]
+    lib.lqro_timestep_device.argtypes = [c_void_p] * 9
     if path == _build.SO:
         _lib = lib
     return lib
@@ -265,6 +266,11 @@ class Lqro:
     def sim_update_device(self, n, d_x, d_Rot, d_P, d_xTrue, d_RotTrue, d_newV, d_pGoal, d_normals, d_vGoal, d_u=None, stream=None):
         self._ck(self.lib.lqro_sim_update_device(self.h, n, _p(d_x), _p(d_Rot), _p(d_P), _p(d_xTrue), _p(d_RotTrue), _p(d_newV),
                                                  _p(d_pGoal), _p(d_normals), _p(d_vGoal), _p(d_u), stream))
+
+    def timestep_device(self, d_Rot, d_P, d_xTrue, d_RotTrue, d_pGoal, d_normals, d_vgoal, stream=None):
+        """one whole time step (MAIN:1373-1417) on device-resident state; the estimates are the context's state buffer"""
+        self._ck(self.lib.lqro_timestep_device(self.h, _p(d_Rot), _p(d_P), _p(d_xTrue), _p(d_RotTrue), _p(d_pGoal), _p(d_normals),
+                                               _p(d_vgoal), stream))
 
     def sim_cycles(self, reset=True):
         c = np.zeros(16, dtype=np.int64)

@@ -1151,6 +1151,28 @@ extern "C" int lqro_allgather_state(lqro_ctx* ctx) {
   return LQRO_OK;
 }
 
+// One whole time step of the reference's loop (MAIN:1373-1417) with everything resident: [all-gather of the estimates] ->
+// [neighbour table] -> avoidance step -> simulator-form update of the owned agents.  Launches only; no host synchronisation.
+extern "C" int lqro_timestep_device(lqro_ctx* ctx, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue, const double* d_pGoal,
+                                    const double* d_normals, double* d_vgoal, void* stream) {
+  if (!ctx || !d_Rot || !d_P || !d_xTrue || !d_RotTrue || !d_pGoal || !d_normals || !d_vgoal) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  if (!ctx->have_sim_model) return fail(ctx, LQRO_E_STATE, "lqro_sim_set_model first");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const LqroParams& p = ctx->prm;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc = LQRO_OK;
+  if (ctx->comm) {
+    if (st != ctx->stream) return fail(ctx, LQRO_E_ARG, "with a communicator the time step runs on the context's stream (lqro_set_stream)");
+    if ((rc = lqro_allgather_state(ctx))) return rc;
+  }
+  ctx->h_nbr_chunked = nullptr;
+  if (ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
+  if ((rc = launch_step(ctx, ctx->d_x, d_vgoal, ctx->d_nbr, ctx->d_newV, st))) return rc;
+  return launch_sim_update(ctx, p.n_local, ctx->d_x + 16 * (size_t)p.local_begin, d_Rot, d_P, d_xTrue, d_RotTrue, ctx->d_newV, d_pGoal, d_normals,
+                           d_vgoal, nullptr, st);
+}
+
 // ---- measurement helpers ------------------------------------------------------------------------------
 template <typename T, typename Kern>
 static int measure_peak(lqro_ctx* ctx, Kern kern, double* tflops) {

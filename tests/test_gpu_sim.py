@@ -137,6 +137,56 @@ def test_closed_loop_on_the_device_follows_the_reference_trajectory(sim_golden, 
     assert worst <= 1e-6
 
 
+def test_resident_time_steps_equal_the_host_buffer_loop(sim_golden, golden):
+    """lqro_timestep_device (avoidance + update, state resident, launches only) over 60 steps of the canonical scenario:
+    same bits as the loop of lqro_step + lqro_sim_update with host buffers, and within 1e-6 m of the reference trajectory"""
+    import torch
+    from lqr_obstacles_b200 import Lqro
+    from lqr_obstacles_b200.api import SimModel, msvc_normals
+
+    g = sim_golden
+    n, steps = 6, 60
+    nbr = np.array([[j for j in range(n) if j != i] for i in range(n)], dtype=np.int32)
+
+    def make():
+        c = Lqro(n_agents=n, max_neighbors=n - 1, horizon=30)
+        c.set_dynamics(golden["dyn_A"], golden["dyn_B"], golden["dyn_L"], golden["dyn_E"])
+        c.sim_set_model(SimModel.from_array(g["model"]))
+        return c
+
+    # host-buffer loop
+    c = make()
+    st = {k: g["init_" + k].copy() for k in KEYS}
+    vpref, seed, host_traj = g["init_vGoal"].copy(), int(g["seeds"][0]), []
+    for t in range(steps):
+        newV = c.step(st["x"], vpref, nbr)
+        normals, seed = msvc_normals(seed, 22 * n)
+        vpref, _ = c.sim_update(st["x"], st["Rot"], st["P"], st["xTrue"], st["RotTrue"], newV, g["init_pGoal"], normals)
+        host_traj.append((st["x"].copy(), st["xTrue"].copy(), vpref.copy()))
+    c.close()
+    # resident loop: one call per step, only the normals go up
+    c = make()
+    c.step(g["init_x"].copy(), g["init_vGoal"].copy(), nbr)  # makes the neighbour table (and the state) resident
+    c.upload_local_state(np.ascontiguousarray(g["init_x"]))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    d = {k: dev(g["init_" + k]) for k in ("Rot", "P", "xTrue", "RotTrue", "pGoal", "vGoal")}
+    dx = torch.empty(0)
+    seed = int(g["seeds"][0])
+    torch.cuda.synchronize()
+    for t in range(steps):
+        normals, seed = msvc_normals(seed, 22 * n)
+        dn = dev(normals)
+        torch.cuda.synchronize()
+        c.timestep_device(d["Rot"].data_ptr(), d["P"].data_ptr(), d["xTrue"].data_ptr(), d["RotTrue"].data_ptr(), d["pGoal"].data_ptr(),
+                          dn.data_ptr(), d["vGoal"].data_ptr())
+        c.synchronize()
+        hx, hxt, hv = host_traj[t]
+        assert np.array_equal(d["xTrue"].cpu().numpy(), hxt), t
+        assert np.array_equal(d["vGoal"].cpu().numpy(), hv), t
+        assert np.abs(hxt[:, :6] - g["traj_xTrue"][t][:, :6]).max() <= 1e-6
+    c.close()
+
+
 def test_update_against_the_compiled_reference_on_perturbed_states(ctx, reference, sim_golden):
     """states off the canonical trajectory: random attitude errors, velocities and covariances pushed through the
     reference's own update (oracle/_ref) and through the kernel with the same normals"""
