@@ -74,3 +74,69 @@ def test_two_gpus_match_one(tmp_path, product_lib):
 
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert np.load(os.path.join(str(tmp_path), "ok.npy")).all()
+
+
+def _timestep_worker(rank, world, port, outdir):
+    """whole resident time steps (lqro_timestep_device) of the canonical 6-quad scenario with the quads split 3 + 3 over two
+    GPUs: the estimates are all-gathered inside the call; every rank keeps only its own Rot, P, xTrue, RotTrue."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch
+    import torch.distributed as dist
+
+    from lqr_obstacles_b200 import Lqro
+    from lqr_obstacles_b200.api import SimModel, msvc_normals
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    g = np.load(os.path.join(HERE, "golden", "ref_vectors.npz"))
+    s = np.load(os.path.join(HERE, "golden", "sim_update.npz"))
+    n, steps = 6, 40
+    nl = n // world
+    lo = rank * nl
+    nbr = np.array([[j for j in range(n) if j != i] for i in range(n)], dtype=np.int32)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(Lqro.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    ctx = Lqro(device=rank, n_agents=n, local_begin=lo, n_local=nl, max_neighbors=n - 1, horizon=30)
+    ctx.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
+    ctx.sim_set_model(SimModel.from_array(s["model"]))
+    ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    sl = slice(lo, lo + nl)
+    # one sharded step makes the neighbour table resident; then the state is put back to the initial one
+    ctx.step_sharded(np.ascontiguousarray(s["init_x"][sl]), np.ascontiguousarray(s["init_vGoal"][sl]), np.ascontiguousarray(nbr[sl]))
+    ctx.upload_local_state(np.ascontiguousarray(s["init_x"][sl]))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    d = {k: dev(s["init_" + k][sl]) for k in ("Rot", "P", "xTrue", "RotTrue", "pGoal", "vGoal")}
+    seed = int(s["seeds"][0])
+    worst = 0.0
+    for t in range(steps):
+        normals, seed = msvc_normals(seed, 22 * n)  # the reference's stream is sequential over ALL quads: every rank draws all, uses its block
+        dn = dev(normals.reshape(n, 22)[sl])
+        torch.cuda.synchronize()
+        ctx.timestep_device(d["Rot"].data_ptr(), d["P"].data_ptr(), d["xTrue"].data_ptr(), d["RotTrue"].data_ptr(), d["pGoal"].data_ptr(),
+                            dn.data_ptr(), d["vGoal"].data_ptr())
+        ctx.synchronize()
+        worst = max(worst, float(np.abs(d["xTrue"].cpu().numpy()[:, :6] - s["traj_xTrue"][t][sl, :6]).max()))
+    w = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        np.save(os.path.join(outdir, "worst.npy"), np.array([float(w.item())]))
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_resident_time_steps_follow_the_reference(tmp_path, product_lib):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_timestep_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    worst = float(np.load(os.path.join(str(tmp_path), "worst.npy"))[0])
+    print("2 GPUs, 40 resident time steps: max |xTrue - reference| = %.3e m" % worst)
+    assert worst <= 1e-6
