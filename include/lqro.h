@@ -214,6 +214,13 @@ int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, dou
 int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue,
                            const double* d_newV, const double* d_pGoal, const double* d_normals, double* d_vGoal, double* d_u,
                            void* stream);
+/* Replaces linearizeDiscretize (MAIN:425-440; Jacobian_fx / Jacobian_fu MAIN:392-412, exp MAT:773-790), batched over
+ * n_batch operating points of the model set by lqro_sim_set_model (its gains are not used): A = exp(dt F) 16x16,
+ * B = Int*G 16x4, c = Int*f 16, Int = (dt/6)(I + 4 exp(dt/2 F) + A).  Followed by lqro_solve_gains this is the whole of
+ * controlMatrices (MAIN:490-544) on the device: x = [0 .. 0, uGoal], Rot = I, u = uGoal there.  Host pointers:
+ * x n*16, Rot n*9, u n*4 in; A n*256, B n*64, c n*16 out. */
+int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const double* x, const double* Rot, const double* u, double* A, double* B,
+                              double* c);
 /* One WHOLE time step of the reference's loop (MAIN:1373-1417) for the owned agents with everything resident on the device,
  * launches only: [ncclAllGather of the estimates when a communicator exists] -> [neighbour table rebuilt from the current
  * positions with LQRO_FLAG_DEVICE_KNN, else the resident table] -> the avoidance step (as lqro_step_device on the context's

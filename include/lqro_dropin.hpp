@@ -14,7 +14,7 @@
 //
 // Two levels:
 //   * per-function shims below: same names, same argument lists (createObstacle ... calculateNewV,
-//     controlMatrices' Riccati part) -- each call is one small device round trip: correct, slow;
+//     controlMatrices) -- each call is one small device round trip: correct, slow;
 //   * lqro::Swarm -- the whole `for i / for j` block of MAIN:1373-1407 for all agents in ONE device
 //     step (lqro_step): this is what replaces the hot loop; Swarm::update replaces the second loop of the
 //     time step (MAIN:1408-1417: LQR feedback, propagate, Kalman filter) with one lqro_sim_update call.
@@ -89,6 +89,34 @@ inline void controlMatricesRiccati(const M16x16& A, const M16x4& B, double qv, d
   check(lqro_solve_gains(ctx, 1, flat(A, 256).data(), flat(B, 64).data(), qv, qp, r, 300, l, e, lh, eh), ctx, "lqro_solve_gains");
   for (int i = 0; i < 64; ++i) L[i] = l[i];
   for (int i = 0; i < 12; ++i) E[i] = e[i];
+  for (int i = 0; i < 48; ++i) Lh[i] = lh[i];
+  for (int i = 0; i < 9; ++i) Eh[i] = eh[i];
+}
+
+// ---- MAIN:490-544 controlMatrices with the reference's own argument list (SIM2:43): linearizeDiscretize about the
+// hover point (xHat = [0 .. 0, uGoal], RHat = I, MAIN:497-509) and both Riccati recursions on the device.
+// `xstar` is unused, as in the reference.  Weights Qv = qv*I, Qp = qp*I, R = r*I are the reference's globals
+// (MAIN:1130-1137: 100, 0.1, 5); the physical constants are setup()'s (lqro_sim_default_model) unless `model` is given.
+template <class Input, class M16, class M16x16, class M16x4, class M4x16, class M4x3, class M4, class M3x16, class M3x3>
+inline void controlMatrices(const Input& uGoal, const M16& /*xstar*/, M16x16& A, M16x4& B, M16& c, M4x16& L, M4x3& E, M4& l, M3x16& Lh,
+                            M3x3& Eh, double qv = 100.0, double qp = 0.1, double r = 5.0, const lqro_sim_model* model = nullptr) {
+  lqro_ctx* ctx = ensure_ctx();
+  lqro_sim_model m;
+  if (model) m = *model; else lqro_sim_default_model(&m);
+  check(lqro_sim_set_model(ctx, &m), ctx, "lqro_sim_set_model");
+  double x[16] = {0}, Rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, u[4], a[256], b[64], cc[16], ll[64], e[12], lh[48], eh[9];
+  for (int i = 0; i < 4; ++i) { u[i] = uGoal[i]; x[12 + i] = uGoal[i]; }
+  check(lqro_linearize_discretize(ctx, 1, x, Rot, u, a, b, cc), ctx, "lqro_linearize_discretize");
+  check(lqro_solve_gains(ctx, 1, a, b, qv, qp, r, 300, ll, e, lh, eh), ctx, "lqro_solve_gains");
+  for (int i = 0; i < 256; ++i) A[i] = a[i];
+  for (int i = 0; i < 64; ++i) { B[i] = b[i]; L[i] = ll[i]; }
+  for (int i = 0; i < 16; ++i) c[i] = cc[i];
+  for (int i = 0; i < 12; ++i) E[i] = e[i];
+  // l = -(R + B'SB)^-1 (B'S c + B'a), a = pinv(..)(Qx xstar - A'S c + ..) (MAIN:519-524): with Qx = 0 and c = 0 -- the hover
+  // point is an equilibrium, f = 0 -- both vanish, l = 0 (the reference's value).  Any other point is refused.
+  for (int i = 0; i < 16; ++i)
+    if (cc[i] != 0.0) { std::fprintf(stderr, "lqro::controlMatrices: c != 0 (not an equilibrium): l is not available\n"); std::exit(-1); }
+  for (int i = 0; i < 4; ++i) l[i] = 0.0;
   for (int i = 0; i < 48; ++i) Lh[i] = lh[i];
   for (int i = 0; i < 9; ++i) Eh[i] = eh[i];
 }

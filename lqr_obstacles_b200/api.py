@@ -42,6 +42,7 @@ EXPORTS = [
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
     "lqro_sim_last_ms", "lqro_debug_sim_cycles", "lqro_timestep_device",
+    "lqro_linearize_discretize",
 ]
 
 
@@ -140,6 +141,7 @@ def load_library(path=None):
     lib.lqro_sim_last_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_sim_cycles.argtypes = [c_void_p, c_void_p, c_int]
     lib.lqro_timestep_device.argtypes = [c_void_p] * 9
+    lib.lqro_linearize_discretize.argtypes = [c_void_p, c_int] + [c_void_p] * 6
     if path == _build.SO:
         _lib = lib
     return lib
@@ -266,6 +268,15 @@ class Lqro:
     def sim_update_device(self, n, d_x, d_Rot, d_P, d_xTrue, d_RotTrue, d_newV, d_pGoal, d_normals, d_vGoal, d_u=None, stream=None):
         self._ck(self.lib.lqro_sim_update_device(self.h, n, _p(d_x), _p(d_Rot), _p(d_P), _p(d_xTrue), _p(d_RotTrue), _p(d_newV),
                                                  _p(d_pGoal), _p(d_normals), _p(d_vGoal), _p(d_u), stream))
+
+    def linearize_discretize(self, x, Rot, u):
+        """linearizeDiscretize (MAIN:425-440) about each (x, Rot, u): returns A (n,16,16), B (n,16,4), c (n,16)"""
+        f = lambda a, k: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, k)
+        x, Rot, u = f(x, 16), f(Rot, 9), f(u, 4)
+        n = len(x)
+        A, B, c = np.zeros((n, 16, 16)), np.zeros((n, 16, 4)), np.zeros((n, 16))
+        self._ck(self.lib.lqro_linearize_discretize(self.h, n, _p(x), _p(Rot), _p(u), _p(A), _p(B), _p(c)))
+        return A, B, c
 
     def timestep_device(self, d_Rot, d_P, d_xTrue, d_RotTrue, d_pGoal, d_normals, d_vgoal, stream=None):
         """one whole time step (MAIN:1373-1417) on device-resident state; the estimates are the context's state buffer"""

@@ -1151,6 +1151,35 @@ extern "C" int lqro_allgather_state(lqro_ctx* ctx) {
   return LQRO_OK;
 }
 
+extern "C" int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const double* x, const double* Rot, const double* u, double* A, double* B,
+                                         double* c) {
+  if (!ctx || n_batch < 0 || !x || !Rot || !u || !A || !B || !c) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_sim_model) return fail(ctx, LQRO_E_STATE, "lqro_sim_set_model first");
+  if (n_batch == 0) return LQRO_OK;
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t nb = (size_t)n_batch, per = 16 + 9 + 4 + 256 + 64 + 16;
+  int rc = ensure_scratch(ctx, sizeof(double) * per * nb);
+  if (rc) return rc;
+  double *dx = (double*)ctx->d_scratch, *dR = dx + 16 * nb, *du = dR + 9 * nb, *dA = du + 4 * nb, *dB = dA + 256 * nb, *dc = dB + 64 * nb;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(dx, x, 8 * 16 * nb, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dR, Rot, 8 * 9 * nb, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(du, u, 8 * 4 * nb, cudaMemcpyHostToDevice, st));
+  const int wa = 5;
+  const size_t smem = (size_t)wa * sizeof(LqroSimWsA);
+  CU(cudaFuncSetAttribute(k_sim_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int blocks = (n_batch + wa - 1) / wa;
+  if (blocks > ctx->sm_count * 3) blocks = ctx->sm_count * 3;
+  k_sim_linearize<<<blocks, wa * 32, smem, st>>>(n_batch, ctx->d_sim_model, dx, dR, du, dA, dB, dc);
+  CU(cudaGetLastError());
+  ctx->launches_extra++;
+  CU(cudaMemcpyAsync(A, dA, 8 * 256 * nb, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(B, dB, 8 * 64 * nb, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(c, dc, 8 * 16 * nb, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
 // One whole time step of the reference's loop (MAIN:1373-1417) with everything resident: [all-gather of the estimates] ->
 // [neighbour table] -> avoidance step -> simulator-form update of the owned agents.  Launches only; no host synchronisation.
 extern "C" int lqro_timestep_device(lqro_ctx* ctx, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue, const double* d_pGoal,

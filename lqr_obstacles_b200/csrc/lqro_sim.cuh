@@ -763,6 +763,34 @@ SIMF void sim_phase_flow(LqroSimWsA& w, double* MM_out, double* v1_out, double* 
   P::sync();
 }
 
+// linearizeDiscretize (MAIN:425-440) about (w.xs, w.Rs, w.u): A = exp(dt F), B = Int*G, c = Int*xDot with
+// Int = (dt/6)(I + 4 exp(dt/2 F) + A) and G = Jacobian_fu (central differences in the four inputs, MAIN:403-412).
+// The flow phase already forms F, xDot, A and exp(dt/2 F); with lqro_solve_gains this is controlMatrices (MAIN:490-544).
+template <class P>
+SIMF void sim_phase_linearize(LqroSimWsA& w, double* A_out, double* B_out, double* c_out, const LqroSimModel& md) {
+  sim_flow<P>(w, w.xs, w.Rs, md);
+  const double* A2e = w.F;
+  double* fb = w.W; double* G = w.W + 256; double* Int = w.W + 512;  // fb [8][17], G 16x4, Int 16x16
+  SIM_FOR(P, t, 8) {
+    const int c = t & 3, side = t >> 2;
+    double xr[16], R[9], u[4], ft[16];
+    for (int i = 0; i < 16; ++i) xr[i] = w.xs[i];
+    for (int i = 0; i < 9; ++i) R[i] = w.Rs[i];
+    for (int i = 0; i < 4; ++i) u[i] = w.u[i];
+    for (int i = 0; i < 4; ++i) if (i == c) { if (side == 0) u[i] += md.jstep; else u[i] -= md.jstep; }
+    sim_f(ft, xr, R, u, md);
+    for (int i = 0; i < 16; ++i) fb[t * 17 + i] = ft[i];
+  }
+  P::sync();
+  SIM_FOR(P, e, 64) { const int i = e >> 2, c = e & 3; G[e] = (fb[c * 17 + i] - fb[(4 + c) * 17 + i]) / (2 * md.jstep); }
+  SIM_FOR(P, e, 256) { const double id = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; Int[e] = (id + A2e[e] * 4.0 + w.Ae[e]) * (md.dt / 6.0); }
+  P::sync();
+  sim_mm<P, false>(B_out, Int, G, 16, 16, 4);
+  SIM_FOR(P, i, 16) { double t = 0.0; for (int k = 0; k < 16; ++k) t += Int[i * 16 + k] * w.xdot[k]; c_out[i] = t; }
+  SIM_FOR(P, e, 256) A_out[e] = w.Ae[e];
+  P::sync();
+}
+
 // Phase B.  In: w.D = propagate's MM, w.nrm = the 16 process-noise normals.  Out: w.samp = sampleGaussian(0, MM)
 // (MAIN:450, SIM2:19-31).
 template <class P>
@@ -879,6 +907,23 @@ __global__ void __launch_bounds__(128) k_sim_control(int n, const LqroSimModel* 
   for (int i = 0; i < 3; ++i) nv[i] = newV[(size_t)a * 3 + i];
   sim_find_u(uu, xs, R, nv, *model);
   for (int i = 0; i < 4; ++i) { u[(size_t)a * 4 + i] = uu[i]; if (uOut) uOut[(size_t)a * 4 + i] = uu[i]; }
+}
+
+// linearizeDiscretize for a batch of operating points (warp per problem)
+__global__ void __launch_bounds__(160, 3) k_sim_linearize(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+                                                          const double* __restrict__ Rot, const double* __restrict__ u,
+                                                          double* __restrict__ A, double* __restrict__ B, double* __restrict__ c) {
+  extern __shared__ __align__(16) unsigned char sim_smem[];
+  const LqroSimModel& md = *model;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  LqroSimWsA& w = *reinterpret_cast<LqroSimWsA*>(sim_smem + (size_t)warp * sizeof(LqroSimWsA));
+  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
+    if (lane < 16) w.xs[lane] = x[(size_t)a * 16 + lane];
+    if (lane < 9) w.Rs[lane] = Rot[(size_t)a * 9 + lane];
+    if (lane < 4) w.u[lane] = u[(size_t)a * 4 + lane];
+    __syncwarp();
+    sim_phase_linearize<SimWarp>(w, A + (size_t)a * 256, B + (size_t)a * 64, c + (size_t)a * 16, md);
+  }
 }
 
 __global__ void __launch_bounds__(160, 3) k_sim_flow(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,

@@ -212,6 +212,7 @@ class Reference:
             getattr(lib, name).argtypes = [c_void_p, c_void_p]
         lib.ref_jacobi16.argtypes = [c_void_p] * 3
         lib.ref_f.argtypes = [c_void_p] * 4
+        lib.ref_linearize_discretize.argtypes = [c_void_p] * 6
         self._tmp = workdir or tempfile.mkdtemp(prefix="lqro_ref_")
         lib.ref_chdir(self._tmp.encode())
         lib.ref_init()
@@ -417,6 +418,7 @@ class SimHost:
         lib.simhost_exp3.argtypes = [c_void_p] * 2
         lib.simhost_jacobi16.argtypes = [c_void_p] * 3
         lib.simhost_f.argtypes = [c_void_p] * 5
+        lib.simhost_linearize.argtypes = [c_void_p] * 7
 
     def update(self, model, st, newV, normals):
         """st: dict as RefSim.full_state(); returns the updated copy (+ vGoal, u)"""

@@ -62,6 +62,9 @@ int main(int argc, char** argv) {
     lqro::copy(m.L, L, 64); lqro::copy(m.E, E, 12);
     swarm.commitSimModel();
     swarm.update(qlist, demo_normal);
+    Matrix<4> uGoal, lvec; Matrix<16> xstar, cvec; Matrix<3, 16> Lh; Matrix<3, 3> Eh;
+    for (int i = 0; i < 4; ++i) uGoal[i] = 9.80665 * 0.5 / 4;
+    lqro::controlMatrices(uGoal, xstar, A, B, cvec, L, E, lvec, Lh, Eh);  // SIM2:43 argument list
     return 0;
   }
   while (true) {

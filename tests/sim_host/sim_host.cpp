@@ -51,3 +51,10 @@ extern "C" void simhost_jacobi16(const double* q, double* V, double* D) {
 extern "C" void simhost_f(const LqroSimModel* md, const double* x, const double* Rot, const double* u, double* xdot) {
   sim_f(xdot, x, Rot, u, *md);
 }
+extern "C" void simhost_linearize(const LqroSimModel* md, const double* x, const double* Rot, const double* u, double* A, double* B, double* c) {
+  static LqroSimWsA w;
+  for (int e = 0; e < 16; ++e) w.xs[e] = x[e];
+  for (int e = 0; e < 9; ++e) w.Rs[e] = Rot[e];
+  for (int e = 0; e < 4; ++e) w.u[e] = u[e];
+  sim_phase_linearize<SimWarp>(w, A, B, c, *md);
+}

@@ -97,6 +97,37 @@ def test_against_the_host_build_of_the_kernel_source_on_random_states(ctx, sim_g
             _close(got[k], want[k], "n=%d %s" % (n, k))
 
 
+def test_control_matrices_entirely_on_the_device(ctx, sim_golden, golden):
+    """controlMatrices (MAIN:490-544) = lqro_linearize_discretize at the hover point + lqro_solve_gains: A, B, c and the four
+    gains against the reference's (golden vectors), 1e-9; plus random operating points against the host build of the kernel"""
+    from _libs import P, SimHost
+
+    u0 = float(sim_golden["model"][25])  # u_goal[0] = nominalInput
+    x = np.concatenate([np.zeros(12), np.full(4, u0)])
+    A, B, c = ctx.linearize_discretize(x, np.eye(3), np.full(4, u0))
+    _close(A[0], golden["dyn_A"], "A")
+    _close(B[0], golden["dyn_B"], "B")
+    assert np.abs(c[0] - golden["dyn_c"].ravel()).max() <= 1e-12
+    L, E, Lh, Eh = ctx.solve_gains(A, B)
+    for got, k in ((L, "dyn_L"), (E, "dyn_E"), (Lh, "dyn_Lh"), (Eh, "dyn_Eh")):
+        _close(got[0], golden[k], k)
+    sh = SimHost()
+    rng = np.random.default_rng(9)
+    n = 37
+    xs = rng.normal(size=(n, 16)) * 0.3
+    xs[:, 12:] = u0 + 0.05 * rng.normal(size=(n, 4))
+    Rs = np.array([np.linalg.qr(np.eye(3) + 0.1 * rng.normal(size=(3, 3)))[0].ravel() for _ in range(n)])
+    us = u0 + 0.05 * rng.normal(size=(n, 4))
+    A, B, c = ctx.linearize_discretize(xs, Rs, us)
+    md = np.ascontiguousarray(sim_golden["model"])
+    for i in range(n):
+        A2, B2, c2 = np.zeros((16, 16)), np.zeros((16, 4)), np.zeros(16)
+        sh.lib.simhost_linearize(P(md), P(np.ascontiguousarray(xs[i])), P(np.ascontiguousarray(Rs[i])), P(np.ascontiguousarray(us[i])), P(A2), P(B2), P(c2))
+        _close(A[i], A2, "A[%d]" % i)
+        _close(B[i], B2, "B[%d]" % i)
+        _close(c[i], c2, "c[%d]" % i)
+
+
 def test_requires_a_model():
     from lqr_obstacles_b200 import Lqro, LqroError
 

@@ -99,6 +99,28 @@ def test_closed_loop_against_the_reference_40_steps(reference, simhost, product_
     sim.close()
 
 
+def _operating_points(rng, u0, n):
+    pts = [(np.concatenate([np.zeros(12), np.full(4, u0)]), np.eye(3).ravel().copy(), np.full(4, u0))]  # controlMatrices' hover point
+    for _ in range(n - 1):
+        u = u0 + 0.05 * rng.normal(size=4)
+        x = rng.normal(size=16) * 0.3
+        x[12:] = u0 + 0.05 * rng.normal(size=4)
+        R = np.linalg.qr(np.eye(3) + 0.1 * rng.normal(size=(3, 3)))[0].ravel().copy()
+        pts.append((x, R, u))
+    return pts
+
+
+def test_linearize_discretize_matches_the_reference_and_the_golden_dynamics(reference, simhost, sim_golden, golden):
+    md = np.ascontiguousarray(sim_golden["model"])
+    for it, (x, R, u) in enumerate(_operating_points(np.random.default_rng(2), reference.nominal_input(), 8)):
+        A1, B1, c1, A2, B2, c2 = (np.zeros(s) for s in [(16, 16), (16, 4), 16] * 2)
+        reference.lib.ref_linearize_discretize(P(x), P(R), P(u), P(A1), P(B1), P(c1))
+        simhost.lib.simhost_linearize(P(md), P(x), P(R), P(u), P(A2), P(B2), P(c2))
+        assert np.array_equal(A1, A2) and np.array_equal(B1, B2) and np.array_equal(c1, c2), it
+        if it == 0:  # = the A, B, c controlMatrices produced for the golden vectors
+            assert np.array_equal(A2, golden["dyn_A"]) and np.array_equal(B2, golden["dyn_B"]) and np.array_equal(c2, golden["dyn_c"].ravel())
+
+
 def test_msvc_normals_are_the_reference_normals(reference, product_lib):
     from lqr_obstacles_b200.api import msvc_normals
 
