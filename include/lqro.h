@@ -214,6 +214,12 @@ int lqro_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, dou
 int lqro_sim_update_device(lqro_ctx* ctx, int n, double* d_x, double* d_Rot, double* d_P, double* d_xTrue, double* d_RotTrue,
                            const double* d_newV, const double* d_pGoal, const double* d_normals, double* d_vGoal, double* d_u,
                            void* stream);
+/* Replaces the noise part of Quadrotor::setupQuadrotors (MAIN:126-129) and the first findVGoal (MAIN:1355) for n agents:
+ * xTrue = sampleGaussian(x, P); RotTrue = Rot*exp([xTrue_r]); xTrue_r = 0; vGoal = findVGoal().  Host pointers:
+ * x n*16, Rot n*9, P n*256, pGoal n*3, normals16 n*16 (the 16 draws of normal() per agent, in agent order) in;
+ * xTrue n*16, RotTrue n*9, vGoal n*3 out. */
+int lqro_sim_init(lqro_ctx* ctx, int n, const double* x, const double* Rot, const double* P, const double* pGoal,
+                  const double* normals16, double* xTrue, double* RotTrue, double* vGoal);
 /* Replaces linearizeDiscretize (MAIN:425-440; Jacobian_fx / Jacobian_fu MAIN:392-412, exp MAT:773-790), batched over
  * n_batch operating points of the model set by lqro_sim_set_model (its gains are not used): A = exp(dt F) 16x16,
  * B = Int*G 16x4, c = Int*f 16, Int = (dt/6)(I + 4 exp(dt/2 F) + A).  Followed by lqro_solve_gains this is the whole of

@@ -42,7 +42,7 @@ EXPORTS = [
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
     "lqro_sim_last_ms", "lqro_debug_sim_cycles", "lqro_timestep_device",
-    "lqro_linearize_discretize",
+    "lqro_linearize_discretize", "lqro_sim_init",
 ]
 
 
@@ -142,6 +142,7 @@ def load_library(path=None):
     lib.lqro_debug_sim_cycles.argtypes = [c_void_p, c_void_p, c_int]
     lib.lqro_timestep_device.argtypes = [c_void_p] * 9
     lib.lqro_linearize_discretize.argtypes = [c_void_p, c_int] + [c_void_p] * 6
+    lib.lqro_sim_init.argtypes = [c_void_p, c_int] + [c_void_p] * 8
     if path == _build.SO:
         _lib = lib
     return lib
@@ -268,6 +269,15 @@ class Lqro:
     def sim_update_device(self, n, d_x, d_Rot, d_P, d_xTrue, d_RotTrue, d_newV, d_pGoal, d_normals, d_vGoal, d_u=None, stream=None):
         self._ck(self.lib.lqro_sim_update_device(self.h, n, _p(d_x), _p(d_Rot), _p(d_P), _p(d_xTrue), _p(d_RotTrue), _p(d_newV),
                                                  _p(d_pGoal), _p(d_normals), _p(d_vGoal), _p(d_u), stream))
+
+    def sim_init(self, x, Rot, P, pGoal, normals16):
+        """setupQuadrotors' noise part + first findVGoal (MAIN:126-129, 1355): returns xTrue (n,16), RotTrue (n,9), vGoal (n,3)"""
+        f = lambda a, k: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, k)
+        x, Rot, P, pGoal, normals16 = f(x, 16), f(Rot, 9), f(P, 256), f(pGoal, 3), f(normals16, 16)
+        n = len(x)
+        xT, RT, vG = np.zeros((n, 16)), np.zeros((n, 9)), np.zeros((n, 3))
+        self._ck(self.lib.lqro_sim_init(self.h, n, _p(x), _p(Rot), _p(P), _p(pGoal), _p(normals16), _p(xT), _p(RT), _p(vG)))
+        return xT, RT, vG
 
     def linearize_discretize(self, x, Rot, u):
         """linearizeDiscretize (MAIN:425-440) about each (x, Rot, u): returns A (n,16,16), B (n,16,4), c (n,16)"""

@@ -52,7 +52,22 @@ def build_qconvex(force=False):
     return QCONVEX_EXE
 
 
+HEADLESS_SRC = os.path.join(os.path.dirname(HERE), "tools", "headless", "lqro_headless.cpp")
+HEADLESS_EXE = os.path.join(os.path.dirname(HERE), "tools", "headless", "lqro_headless")
+
+
+def build_headless(force=False):
+    """tools/headless/lqro_headless: the reference's simulator main loop headless on Linux over the C ABI (host-only C++)."""
+    so = build()
+    if not force and os.path.exists(HEADLESS_EXE) and os.path.getmtime(HEADLESS_EXE) > max(os.path.getmtime(HEADLESS_SRC), os.path.getmtime(so)):
+        return HEADLESS_EXE
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(os.path.dirname(HERE), "include"), "-o", HEADLESS_EXE,
+                           HEADLESS_SRC, "-L" + HERE, "-llqro", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../../lqr_obstacles_b200"])
+    return HEADLESS_EXE
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
     print(build_qconvex(force=True))
+    print(build_headless(force=True))

@@ -1151,6 +1151,36 @@ extern "C" int lqro_allgather_state(lqro_ctx* ctx) {
   return LQRO_OK;
 }
 
+extern "C" int lqro_sim_init(lqro_ctx* ctx, int n, const double* x, const double* Rot, const double* P, const double* pGoal,
+                             const double* normals16, double* xTrue, double* RotTrue, double* vGoal) {
+  if (!ctx || n < 0 || !x || !Rot || !P || !pGoal || !normals16 || !xTrue || !RotTrue || !vGoal) return fail(ctx, LQRO_E_ARG, "bad argument");
+  if (!ctx->have_sim_model) return fail(ctx, LQRO_E_STATE, "lqro_sim_set_model first");
+  if (n == 0) return LQRO_OK;
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t N = (size_t)n, per = 16 + 9 + 256 + 3 + 16 + 16 + 9 + 3;
+  int rc = ensure_scratch(ctx, sizeof(double) * per * N);
+  if (rc) return rc;
+  double *dx = (double*)ctx->d_scratch, *dR = dx + 16 * N, *dP = dR + 9 * N, *dpg = dP + 256 * N, *dn = dpg + 3 * N, *dxT = dn + 16 * N,
+         *dRT = dxT + 16 * N, *dvG = dRT + 9 * N;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(dx, x, 8 * 16 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dR, Rot, 8 * 9 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dP, P, 8 * 256 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dpg, pGoal, 8 * 3 * N, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dn, normals16, 8 * 16 * N, cudaMemcpyHostToDevice, st));
+  const int wpb = 4;
+  int blocks = (n + wpb - 1) / wpb;
+  if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  k_sim_init<<<blocks, wpb * 32, wpb * sizeof(LqroSimWsB), st>>>(n, ctx->d_sim_model, dx, dR, dP, dpg, dn, dxT, dRT, dvG);
+  CU(cudaGetLastError());
+  ctx->launches_extra++;
+  CU(cudaMemcpyAsync(xTrue, dxT, 8 * 16 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(RotTrue, dRT, 8 * 9 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(vGoal, dvG, 8 * 3 * N, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
 extern "C" int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const double* x, const double* Rot, const double* u, double* A, double* B,
                                          double* c) {
   if (!ctx || n_batch < 0 || !x || !Rot || !u || !A || !B || !c) return fail(ctx, LQRO_E_ARG, "bad argument");

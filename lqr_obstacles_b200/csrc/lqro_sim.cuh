@@ -763,6 +763,21 @@ SIMF void sim_phase_flow(LqroSimWsA& w, double* MM_out, double* v1_out, double* 
   P::sync();
 }
 
+// Quadrotor::setupQuadrotors' noise part (MAIN:126-129) and the first findVGoal (MAIN:1355): xTrue = sampleGaussian(x, P);
+// RotTrue = Rot*exp([xTrue_r]); xTrue_r = 0; vGoal = findVGoal().  In: w.D = P, w.nrm = 16 normals, w.zero = x (the mean).
+template <class P>
+SIMF void sim_phase_init(LqroSimWsB& w, const double* x, const double* Rot, const double* pGoal, double* xT, double* RT, double* vG,
+                         const LqroSimModel& md) {
+  sim_sample_gaussian<P, 16>(w.samp, w.zero, w.D, w.V, w.nrm);
+  double r[3], R[9];
+  for (int i = 0; i < 3; ++i) r[i] = w.samp[6 + i];
+  for (int i = 0; i < 9; ++i) R[i] = Rot[i];
+  sim_fold_rotation(R, r);
+  for (int i = 0; i < 16; ++i) xT[i] = (i >= 6 && i < 9) ? 0.0 : w.samp[i];
+  for (int i = 0; i < 9; ++i) RT[i] = R[i];
+  sim_find_vgoal(vG, x, Rot, pGoal, md);
+}
+
 // linearizeDiscretize (MAIN:425-440) about (w.xs, w.Rs, w.u): A = exp(dt F), B = Int*G, c = Int*xDot with
 // Int = (dt/6)(I + 4 exp(dt/2 F) + A) and G = Jacobian_fu (central differences in the four inputs, MAIN:403-412).
 // The flow phase already forms F, xDot, A and exp(dt/2 F); with lqro_solve_gains this is controlMatrices (MAIN:490-544).
@@ -907,6 +922,33 @@ __global__ void __launch_bounds__(128) k_sim_control(int n, const LqroSimModel* 
   for (int i = 0; i < 3; ++i) nv[i] = newV[(size_t)a * 3 + i];
   sim_find_u(uu, xs, R, nv, *model);
   for (int i = 0; i < 4; ++i) { u[(size_t)a * 4 + i] = uu[i]; if (uOut) uOut[(size_t)a * 4 + i] = uu[i]; }
+}
+
+// initial true states and goal velocities (warp per agent; runs once)
+__global__ void __launch_bounds__(128) k_sim_init(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+                                                  const double* __restrict__ Rot, const double* __restrict__ Pcov,
+                                                  const double* __restrict__ pGoal, const double* __restrict__ normals16,
+                                                  double* __restrict__ xTrue, double* __restrict__ RotTrue, double* __restrict__ vGoal) {
+  extern __shared__ __align__(16) unsigned char sim_smem[];
+  const LqroSimModel& md = *model;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  LqroSimWsB& w = *reinterpret_cast<LqroSimWsB*>(sim_smem + (size_t)warp * sizeof(LqroSimWsB));
+  for (int a = blockIdx.x * wpb + warp; a < n; a += gridDim.x * wpb) {
+    for (int e = lane; e < 256; e += 32) w.D[e] = Pcov[(size_t)a * 256 + e];
+    if (lane < 16) { w.nrm[lane] = normals16[(size_t)a * 16 + lane]; w.zero[lane] = x[(size_t)a * 16 + lane]; }
+    __syncwarp();
+    double xs[16], R[9], pg[3], xT[16], RT[9], vG[3];
+    for (int i = 0; i < 16; ++i) xs[i] = x[(size_t)a * 16 + i];
+    for (int i = 0; i < 9; ++i) R[i] = Rot[(size_t)a * 9 + i];
+    for (int i = 0; i < 3; ++i) pg[i] = pGoal[(size_t)a * 3 + i];
+    sim_phase_init<SimWarp>(w, xs, R, pg, xT, RT, vG, md);
+    if (lane == 0) {
+      for (int i = 0; i < 16; ++i) xTrue[(size_t)a * 16 + i] = xT[i];
+      for (int i = 0; i < 9; ++i) RotTrue[(size_t)a * 9 + i] = RT[i];
+      for (int i = 0; i < 3; ++i) vGoal[(size_t)a * 3 + i] = vG[i];
+    }
+    __syncwarp();
+  }
 }
 
 // linearizeDiscretize for a batch of operating points (warp per problem)

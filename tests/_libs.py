@@ -419,6 +419,7 @@ class SimHost:
         lib.simhost_jacobi16.argtypes = [c_void_p] * 3
         lib.simhost_f.argtypes = [c_void_p] * 5
         lib.simhost_linearize.argtypes = [c_void_p] * 7
+        lib.simhost_init.argtypes = [c_int] + [c_void_p] * 9
 
     def update(self, model, st, newV, normals):
         """st: dict as RefSim.full_state(); returns the updated copy (+ vGoal, u)"""

@@ -58,3 +58,12 @@ extern "C" void simhost_linearize(const LqroSimModel* md, const double* x, const
   for (int e = 0; e < 4; ++e) w.u[e] = u[e];
   sim_phase_linearize<SimWarp>(w, A, B, c, *md);
 }
+extern "C" void simhost_init(int n, const LqroSimModel* md, const double* x, const double* Rot, const double* P, const double* pGoal,
+                             const double* normals16, double* xTrue, double* RotTrue, double* vGoal) {
+  static LqroSimWsB w;
+  for (int a = 0; a < n; ++a) {
+    for (int e = 0; e < 256; ++e) w.D[e] = P[256 * a + e];
+    for (int e = 0; e < 16; ++e) { w.nrm[e] = normals16[16 * a + e]; w.zero[e] = x[16 * a + e]; }
+    sim_phase_init<SimWarp>(w, x + 16 * a, Rot + 9 * a, pGoal + 3 * a, xTrue + 16 * a, RotTrue + 9 * a, vGoal + 3 * a, *md);
+  }
+}

@@ -128,6 +128,43 @@ def test_control_matrices_entirely_on_the_device(ctx, sim_golden, golden):
         _close(c[i], c2, "c[%d]" % i)
 
 
+def test_initial_states_on_the_device(ctx, sim_golden):
+    from lqr_obstacles_b200.api import msvc_normals
+
+    g = sim_golden
+    nrm, _ = msvc_normals(1, 16 * 6)
+    xT, RT, vG = ctx.sim_init(g["init_x"], g["init_Rot"], g["init_P"], g["init_pGoal"], nrm)
+    _close(xT, g["init_xTrue"], "xTrue")
+    _close(RT, g["init_RotTrue"], "RotTrue")
+    _close(vG, g["init_vGoal"], "vGoal")
+
+
+def test_headless_simulator_reproduces_the_reference_run(sim_golden, product_lib, tmp_path):
+    """tools/headless/lqro_headless: the reference's _tmain headless over the C ABI (setup incl. controlMatrices on the device,
+    210 steps of the canonical scenario).  Its gains come from the device Riccati solve (1e-14 from the reference's), so
+    the trajectory is held to 1e-5 m of the reference's own run; the rand() stream must end where the reference's ends."""
+    import json
+    import subprocess
+
+    from lqr_obstacles_b200 import build
+
+    exe = build.build_headless()
+    out = str(tmp_path / "traj.bin")
+    r = subprocess.run([exe, "--scenario", "hexagon6", "--steps", "210", "--out", out, "--quiet"], capture_output=True, text=True, check=True)
+    m = json.loads(r.stdout.strip().splitlines()[-1])
+    raw = open(out, "rb").read()
+    assert raw[:8] == b"LQROTRJ1"
+    n, steps, sd, _ = np.frombuffer(raw[8:24], dtype=np.int32)
+    assert (n, steps, sd) == (6, 210, 16)
+    tr = np.frombuffer(raw[24:], dtype=np.float64).reshape(steps, 2, n, 16)
+    g = sim_golden
+    err = np.abs(tr[:, 0, :, :6] - g["traj_xTrue"][:, :, :6]).max()
+    err_est = np.abs(tr[:, 1, :, :6] - g["traj_x"][:, :, :6]).max()
+    print("headless run: max |xTrue - reference| %.3e m, estimates %.3e, %s" % (err, err_est, m))
+    assert err <= 1e-5 and err_est <= 1e-5
+    assert m["inside_pairs"] > 0 and m["max_distance_to_goal_m"] < 1.0
+
+
 def test_requires_a_model():
     from lqr_obstacles_b200 import Lqro, LqroError
 

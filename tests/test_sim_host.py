@@ -121,6 +121,21 @@ def test_linearize_discretize_matches_the_reference_and_the_golden_dynamics(refe
             assert np.array_equal(A2, golden["dyn_A"]) and np.array_equal(B2, golden["dyn_B"]) and np.array_equal(c2, golden["dyn_c"].ravel())
 
 
+def test_initial_true_states_match_the_reference_setup(simhost, sim_golden, product_lib):
+    """setupQuadrotors' sampleGaussian + rotation fold and the first findVGoal (MAIN:126-129, 1355) from rand() state 1"""
+    from lqr_obstacles_b200.api import msvc_normals
+
+    g = sim_golden
+    n = len(g["init_x"])
+    nrm, seed = msvc_normals(1, 16 * n)
+    assert seed == int(g["seeds"][0])  # the stream position the reference reaches after setup
+    xT, RT, vG = np.zeros((n, 16)), np.zeros((n, 9)), np.zeros((n, 3))
+    c = np.ascontiguousarray
+    simhost.lib.simhost_init(n, P(c(g["model"])), P(c(g["init_x"])), P(c(g["init_Rot"])), P(c(g["init_P"])), P(c(g["init_pGoal"])), P(nrm),
+                             P(xT), P(RT), P(vG))
+    assert np.array_equal(xT, g["init_xTrue"]) and np.array_equal(RT, g["init_RotTrue"]) and np.array_equal(vG, g["init_vGoal"])
+
+
 def test_msvc_normals_are_the_reference_normals(reference, product_lib):
     from lqr_obstacles_b200.api import msvc_normals
 
