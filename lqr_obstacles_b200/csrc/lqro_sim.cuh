@@ -998,7 +998,6 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
   constexpr int N = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int g = lane >> 3, sl = lane & 7;
-  const unsigned gmask = 0xffu << (8 * g);
   double* D = reinterpret_cast<double*>(sim_smem) + (size_t)(warp * 4 + g) * SIM_NOISE_GROUP_DOUBLES;
   constexpr int LD = SIM_NOISE_LD;
   double* Vt = D + 16 * LD; double* nrm = Vt + 256;
