@@ -300,13 +300,10 @@ template <> SIMF void sim_solve<SimWarp, 6>(double* m, double* inv, int* rp, int
 #define SIM_NORMLIM 9.504178996162932e-1
 #define SIM_LOG2E 1.4426950408889634074
 
-// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  q is scaled IN PLACE (destroyed);
-// ws: 4*N*N doubles, perm: 2N ints, small: N doubles.  out may not alias q or ws.
+// 1-norm of q (column sums top to bottom, MAT:275-288) and the scaling exponent of exp (MAT:776)
 template <class P, int N>
-SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) {
-  double* A = q; double* A2 = ws; double* A4 = ws + N * N; double* A6 = ws + 2 * N * N; double* T = ws + 3 * N * N;
-  SIM_TIC();
-  SIM_FOR(P, j, N) {  // 1-norm: column sums top to bottom (MAT:275-288)
+SIMF double sim_norm1(const double* q, double* small) {
+  SIM_FOR(P, j, N) {
     double s = 0.0;
     for (int i = 0; i < N; ++i) s += fabs(q[i * N + j]);
     small[j] = s;
@@ -314,8 +311,19 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
   P::sync();
   double norm1 = 0.0;
   for (int j = 0; j < N; ++j) if (small[j] > norm1) norm1 = small[j];
+  P::sync();  // small[] is reused by the solve
+  return norm1;
+}
+SIMF int sim_exp_scaling(double norm1) {
   const double sd = ceil(log(norm1 / SIM_NORMLIM) * SIM_LOG2E);
-  const int s = (int)(sd > 0.0 ? sd : 0.0);
+  return (int)(sd > 0.0 ? sd : 0.0);
+}
+// The part of exp(q) before the squarings (MAT:779-786): q is scaled IN PLACE by 2^-s (destroyed), R7 = (V - U) % (V + U)
+// is left in ws[N*N .. 2N*N) ("A4"); ws[0 .. N*N) ("A2") is free afterwards.  ws: 4*N*N doubles, perm: 2N ints, small: N.
+template <class P, int N>
+SIMF void sim_exp_pade(double* q, int s, double* ws, int* perm, double* small) {
+  double* A = q; double* A2 = ws; double* A4 = ws + N * N; double* A6 = ws + 2 * N * N; double* T = ws + 3 * N * N;
+  SIM_TIC();
   const double rscale = ldexp(1.0, -s);  // A /= 2^s (MAT:779): multiplying by 2^-s gives the same bits (both exact up to underflow)
   SIM_FOR(P, e, N * N) A[e] = A[e] * rscale;
   P::sync();
@@ -335,7 +343,15 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
   if (N == 16) SIM_TOC(2);
   sim_solve<P, N>(A4, T, perm, perm + N, small);  // R7 = (V - U) % (V + U), result in A4
   if (N == 16) SIM_TOC(3);
-  double* cur = A4; double* nxt = A2;
+}
+// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  q is scaled IN PLACE (destroyed);
+// ws: 4*N*N doubles, perm: 2N ints, small: N doubles.  out may not alias q or ws.
+template <class P, int N>
+SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) {
+  const int s = sim_exp_scaling(sim_norm1<P, N>(q, small));
+  sim_exp_pade<P, N>(q, s, ws, perm, small);
+  SIM_TIC();
+  double* cur = ws + N * N; double* nxt = ws;
   for (int i = 0; i < s; ++i) {
     sim_mm<P, false>(nxt, cur, cur, N, N, N);
     double* t = cur; cur = nxt; nxt = t;
@@ -343,6 +359,30 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
   SIM_FOR(P, e, N * N) out[e] = cur[e];
   P::sync();
   if (N == 16) SIM_TOC(4);
+}
+// full = exp(q) and half = exp(q/2) together -- propagate and kalmanFilter1 ask for exp(dt*F) and exp((dt*0.5)*F)
+// (MAIN:446-447, 461-462), and (dt*0.5)*F is dt*F halved bit for bit (halving is exact).  exp scales its argument by 2^-s
+// with s = max(0, ceil(log2(|q|_1 / 0.95))) (MAT:776-779); |q/2|_1 = |q|_1 / 2 exactly, so s(q/2) = s(q) - 1 whenever
+// s(q) >= 1 (checked with the reference's own formula on both norms): both exponentials then start from THE SAME scaled
+// matrix, hence the same A^2, A^4, A^6, U, V and R7, and differ only in the number of squarings -- half = R7^(2^(s-1)),
+// full = half*half, each the very product the reference forms.  Exact work avoidance: one Pade approximant and one
+// full-pivot solve instead of two.  Returns false, with q untouched, when the exponents do not line up (s(q) = 0).
+template <class P, int N>
+SIMF bool sim_exp_with_half(double* full, double* half, double* q, double* ws, int* perm, double* small) {
+  const double norm1 = sim_norm1<P, N>(q, small);
+  const int s = sim_exp_scaling(norm1), sh = sim_exp_scaling(norm1 * 0.5);
+  if (s < 1 || sh != s - 1) return false;
+  sim_exp_pade<P, N>(q, s, ws, perm, small);
+  SIM_TIC();
+  double* cur = ws + N * N; double* nxt = ws;
+  for (int i = 0; i < sh; ++i) {
+    sim_mm<P, false>(nxt, cur, cur, N, N, N);
+    double* t = cur; cur = nxt; nxt = t;
+  }
+  SIM_FOR(P, e, N * N) half[e] = cur[e];
+  sim_mm<P, false>(full, cur, cur, N, N, N);
+  if (N == 16) SIM_TOC(4);
+  return true;
 }
 
 #ifdef SIM_COUNT_JACOBI
@@ -718,10 +758,12 @@ SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const Lqro
   double* const A2e = w.F;  // exp(dt/2 F) replaces the Jacobian once dt/2 F has been formed
   SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * md.dt;
   P::sync();
-  sim_exp<P, 16>(w.Ae, w.MM, w.W, w.perm, w.small);
-  SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * (md.dt * 0.5);
-  P::sync();
-  sim_exp<P, 16>(A2e, w.MM, w.W, w.perm, w.small);
+  if (!sim_exp_with_half<P, 16>(w.Ae, A2e, w.MM, w.W, w.perm, w.small)) {  // general path: two separate exponentials
+    sim_exp<P, 16>(w.Ae, w.MM, w.W, w.perm, w.small);
+    SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * (md.dt * 0.5);
+    P::sync();
+    sim_exp<P, 16>(A2e, w.MM, w.W, w.perm, w.small);
+  }
   // MM = (dt/6) * (M + 4*A2*M*~A2 + A*M*~A)
   SIM_RETIC();
   double* T3 = w.W + 512; double* T4 = w.W + 768;

@@ -420,6 +420,7 @@ class SimHost:
         lib.simhost_f.argtypes = [c_void_p] * 5
         lib.simhost_linearize.argtypes = [c_void_p] * 7
         lib.simhost_init.argtypes = [c_int] + [c_void_p] * 9
+        lib.simhost_exp_with_half.argtypes = [c_void_p] * 3
 
     def update(self, model, st, newV, normals):
         """st: dict as RefSim.full_state(); returns the updated copy (+ vGoal, u)"""

@@ -67,3 +67,14 @@ extern "C" void simhost_init(int n, const LqroSimModel* md, const double* x, con
     sim_phase_init<SimWarp>(w, x + 16 * a, Rot + 9 * a, pGoal + 3 * a, xTrue + 16 * a, RotTrue + 9 * a, vGoal + 3 * a, *md);
   }
 }
+// exp(q) and exp(q*0.5) through the shared-Pade routine; returns 1 when the shared path was taken, else 0 (then the
+// outputs come from two separate sim_exp calls, as sim_flow falls back)
+extern "C" int simhost_exp_with_half(const double* q, double* full, double* half) {
+  static double ws[4 * 256], a[256]; int perm[32]; double small[16];
+  for (int e = 0; e < 256; ++e) a[e] = q[e];
+  if (sim_exp_with_half<SimSeq, 16>(full, half, a, ws, perm, small)) return 1;
+  sim_exp<SimSeq, 16>(full, a, ws, perm, small);
+  for (int e = 0; e < 256; ++e) a[e] = q[e] * 0.5;
+  sim_exp<SimSeq, 16>(half, a, ws, perm, small);
+  return 0;
+}

@@ -60,6 +60,24 @@ def test_stage_pieces_match_the_reference_bit_for_bit(reference, simhost):
         assert np.array_equal(V1, V2) and np.array_equal(np.diag(D1), np.diag(D2))
 
 
+def test_shared_pade_for_exp_and_exp_of_half_is_exact(reference, simhost):
+    """exp(q) and exp(q/2) from ONE Pade approximant + solve (csrc/lqro_sim.cuh: sim_exp_with_half) equal the reference's two
+    separate exp calls bit for bit, on the shared path and on the fallback (s(q) = 0), incl. norms on the ceil boundary"""
+    rng = np.random.default_rng(4)
+    taken = [0, 0]
+    for it in range(200):
+        q = rng.normal(size=(16, 16)) * rng.choice([0.001, 0.02, 0.05, 0.06, 0.1, 0.3, 1, 3, 10])
+        if it % 7 == 0:
+            q = q / np.abs(q).sum(0).max() * 0.9504178996162932 * rng.choice([1, 2, 4])
+        q = np.ascontiguousarray(q)
+        f1, h1, f2, h2 = (np.zeros((16, 16)) for _ in range(4))
+        reference.lib.ref_exp16(P(q), P(f1))
+        reference.lib.ref_exp16(P(np.ascontiguousarray(q * 0.5)), P(h1))
+        taken[simhost.lib.simhost_exp_with_half(P(q), P(f2), P(h2))] += 1
+        assert np.array_equal(f1, f2) and np.array_equal(h1, h2), it
+    assert taken[0] > 10 and taken[1] > 10
+
+
 def test_model_f_matches_the_reference(reference, simhost, sim_golden):
     rng = np.random.default_rng(11)
     md = np.ascontiguousarray(sim_golden["model"])
