@@ -12,7 +12,8 @@
 //   k_sim_control  thread per agent   u = findU()
 //   k_sim_flow     warp per TASK      the linearised flow about the true state (propagate) and about the estimate
 //                                     (kalmanFilter1) are independent: 2 tasks per agent.  One flow = 32 evaluations of f
-//                                     (one per lane, 3x3 exponential in registers), two 16x16 Pade exponentials, the noise
+//                                     (one per lane, 3x3 exponential in registers), exp(dt F) and exp(dt/2 F) from ONE 16x16
+//                                     Pade approximant + solve (sim_exp_with_half: exact work avoidance), the noise
 //                                     covariance MM and the Simpson increment; 7 16x16 buffers = 15 KB per warp, 15 warps/SM
 //   k_sim_noise    8 lanes per agent  Jacobi eigen-decomposition of propagate's MM + the sample: its scalar division /
 //                                     square-root chain is executed once per warp for four agents in lockstep
