@@ -750,11 +750,11 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
 }
 
 // Four launches per update (lqro_sim.cuh): the control input (thread per agent), the two linearised flows of every agent as
-// independent warp tasks (15.3 KB of shared memory per warp, 15 warps per SM), the process-noise sample (four agents per warp, 17 KB per warp,
+// independent warp tasks (11 KB of shared memory per warp, 20 warps per SM), the process-noise sample (four agents per warp, 17 KB per warp,
 // 12-16 warps per SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
-  const int wa = 5, wb = 4, wc = 4;
+  const int wa = SIM_FLOW_WARPS, wb = 4, wc = 4;
   const size_t smem_a = (size_t)wa * sizeof(LqroSimWsA), smem_b = (size_t)wb * 4 * SIM_NOISE_GROUP_DOUBLES * sizeof(double), smem_c = (size_t)wc * sizeof(LqroSimWsC);
   if (!ctx->sim_attr_set) {  // per device, hence per context
     CU(cudaFuncSetAttribute(k_sim_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
@@ -780,7 +780,7 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   CU(cudaEventRecord(ctx->ev_sim[0], st));
   k_sim_control<<<(n + 127) / 128, 128, 0, st>>>(n, ctx->d_sim_model, x, Rot, newV, sc.u, u);
   CU(cudaGetLastError());
-  k_sim_flow<<<grid(2LL * n, wa, 3), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
+  k_sim_flow<<<grid(2LL * n, wa, SIM_FLOW_CTAS), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
   k_sim_noise<<<grid((n + 3) / 4, wb, 3), wb * 32, smem_b, st>>>(n, normals, sc);
@@ -1195,11 +1195,11 @@ extern "C" int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const doubl
   CU(cudaMemcpyAsync(dx, x, 8 * 16 * nb, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(dR, Rot, 8 * 9 * nb, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(du, u, 8 * 4 * nb, cudaMemcpyHostToDevice, st));
-  const int wa = 5;
+  const int wa = SIM_FLOW_WARPS;
   const size_t smem = (size_t)wa * sizeof(LqroSimWsA);
   CU(cudaFuncSetAttribute(k_sim_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = (n_batch + wa - 1) / wa;
-  if (blocks > ctx->sm_count * 3) blocks = ctx->sm_count * 3;
+  if (blocks > ctx->sm_count * SIM_FLOW_CTAS) blocks = ctx->sm_count * SIM_FLOW_CTAS;
   k_sim_linearize<<<blocks, wa * 32, smem, st>>>(n_batch, ctx->d_sim_model, dx, dR, du, dA, dB, dc);
   CU(cudaGetLastError());
   ctx->launches_extra++;

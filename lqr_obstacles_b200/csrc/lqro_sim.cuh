@@ -14,7 +14,7 @@
 //                                     (kalmanFilter1) are independent: 2 tasks per agent.  One flow = 32 evaluations of f
 //                                     (one per lane, 3x3 exponential in registers), exp(dt F) and exp(dt/2 F) from ONE 16x16
 //                                     Pade approximant + solve (sim_exp_with_half: exact work avoidance), the noise
-//                                     covariance MM and the Simpson increment; 7 16x16 buffers = 15 KB per warp, 15 warps/SM
+//                                     covariance MM and the Simpson increment; 5 16x16 buffers = 11 KB per warp, 20 warps/SM
 //   k_sim_noise    8 lanes per agent  Jacobi eigen-decomposition of propagate's MM + the sample: its scalar division /
 //                                     square-root chain is executed once per warp for four agents in lockstep
 //   k_sim_filter   warp per agent     covariance / state updates of kalmanFilter1 and propagate, the observation sample,
@@ -345,10 +345,11 @@ SIMF void sim_exp_pade(double* q, int s, double* ws, int* perm, double* small) {
   sim_solve<P, N>(A4, T, perm, perm + N, small);  // R7 = (V - U) % (V + U), result in A4
   if (N == 16) SIM_TOC(3);
 }
-// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  q is scaled IN PLACE (destroyed);
-// ws: 4*N*N doubles, perm: 2N ints, small: N doubles.  out may not alias q or ws.
+// out = exp(q) by scaling, the (7,7) Pade approximant and squaring (MAT:773-790).  q is scaled IN PLACE by 2^-s (s is
+// returned); ws: 4*N*N doubles, perm: 2N ints, small: N doubles.  out may not alias q or the first two buffers of ws (the
+// last two, A6 and T, are dead when out is written).
 template <class P, int N>
-SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) {
+SIMF int sim_exp(double* out, double* q, double* ws, int* perm, double* small) {
   const int s = sim_exp_scaling(sim_norm1<P, N>(q, small));
   sim_exp_pade<P, N>(q, s, ws, perm, small);
   SIM_TIC();
@@ -360,6 +361,7 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
   SIM_FOR(P, e, N * N) out[e] = cur[e];
   P::sync();
   if (N == 16) SIM_TOC(4);
+  return s;
 }
 // full = exp(q) and half = exp(q/2) together -- propagate and kalmanFilter1 ask for exp(dt*F) and exp((dt*0.5)*F)
 // (MAIN:446-447, 461-462), and (dt*0.5)*F is dt*F halved bit for bit (halving is exact).  exp scales its argument by 2^-s
@@ -368,6 +370,7 @@ SIMF void sim_exp(double* out, double* q, double* ws, int* perm, double* small) 
 // matrix, hence the same A^2, A^4, A^6, U, V and R7, and differ only in the number of squarings -- half = R7^(2^(s-1)),
 // full = half*half, each the very product the reference forms.  Exact work avoidance: one Pade approximant and one
 // full-pivot solve instead of two.  Returns false, with q untouched, when the exponents do not line up (s(q) = 0).
+// full / half may be the last two buffers of ws (dead by then), not q or the first two.
 template <class P, int N>
 SIMF bool sim_exp_with_half(double* full, double* half, double* q, double* ws, int* perm, double* small) {
   const double norm1 = sim_norm1<P, N>(q, small);
@@ -708,11 +711,15 @@ SIMF void sim_find_vgoal(double* vG, const double* x, const double* R0, const do
 }
 
 // ---- per-agent (per-warp) workspaces of the three phases --------------------------------------------------
-// A: one linearised flow (propagate's about the true state, or kalmanFilter1's about the estimate)
+// A: one linearised flow (propagate's about the true state, or kalmanFilter1's about the estimate): FIVE 16x16 buffers whose
+// roles rotate through the phase (see sim_flow), 11 KB per warp
 struct alignas(16) LqroSimWsA {
-  double F[256], Ae[256], MM[256], W[4 * 256];  // F doubles as exp(dt/2 F) once the Jacobian is spent
+  double buf[5 * 256];
   double xs[16], Rs[9], u[4], xdot[16], v1[16], small[16];
   int perm[32];
+  SIMM double* A2e() { return buf + 3 * 256; }  // after sim_flow: exp(dt/2 F)
+  SIMM double* Ae() { return buf + 4 * 256; }   //                 exp(dt F)
+  SIMM double* MM() { return buf + 1 * 256; }   //                 the noise covariance
 };
 // B: the process-noise sample (Jacobi eigen-decomposition of propagate's MM)
 struct alignas(16) LqroSimWsB {
@@ -730,16 +737,27 @@ struct LqroSimObs {
   SIMM explicit LqroSimObs(double* W) : H(W + 512), PHt(W + 608), HP(W + 704), S6(W + 800), S6b(W + 836), K(W + 872), V6(W + 968) {}
 };
 
+#if defined(__CUDACC__)
+#define SIM_FORCE_GENERAL_EXP 0
+#else
+static int sim_force_general_exp = 0;  // CPU build only: lets the tests run sim_flow's general path on inputs that never take it
+#define SIM_FORCE_GENERAL_EXP sim_force_general_exp
+#endif
 // Common half of propagate and kalmanFilter1 (MAIN:443-450, 458-468): F = Jacobian_fx, xDot = f, A = exp(dt F),
 // A2 = exp(dt/2 F), MM = (dt/6)(M + 4 A2 M ~A2 + A M ~A), v1 = (dt/6)(xDot + 4 (A2 xDot) + A xDot).
-// xs, Rs: the state / rotation linearised about (shared memory of the warp).
+// xs, Rs: the state / rotation linearised about (shared memory of the warp).  `park`: 256 doubles outside the workspace
+// (the task's output slot in HBM), used only by the general path of the exponentials.
+// Buffer roles (B0..B4 = w.buf):  Jacobian: f staging in B1..B3, F -> B0;  q = dt F in place in B0;  exponentials: A = B0,
+// A2 A4 A6 T = B1..B4, exp(dt/2 F) -> B3, exp(dt F) -> B4;  noise covariance: temporaries B0, B1, B2, MM -> B1.
 template <class P>
-SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const LqroSimModel& md) {
+SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, double* park, const LqroSimModel& md) {
   SIM_TIC();
-  // Central-difference Jacobian (MAIN:392-401): the 32 evaluations f(x +- jStep e_c) run one per lane, results staged in W.
+  double* const B0 = w.buf; double* const B1 = w.buf + 256; double* const B2 = w.buf + 512;
+  double* const A2e = w.A2e(); double* const Ae = w.Ae();
+  // Central-difference Jacobian (MAIN:392-401): the 32 evaluations f(x +- jStep e_c) run one per lane, results staged.
   // sim_f never reads the position x[0..2] (MAIN:341 extracts p and does not use it), so f(x + jStep e_0) is f(x) bit for
   // bit: the unperturbed xDot (MAIN:444) is column 0's evaluation.
-  double* fb = w.W;  // [32][17]: padded rows, conflict-free for lane-per-row stores
+  double* fb = B1;  // [32][17]: padded rows, conflict-free for lane-per-row stores
   SIM_FOR(P, t, 32) {
     const int c = t & 15, side = t >> 4;
     double xr[16], R[9], u[4], ft[16];
@@ -751,35 +769,38 @@ SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const Lqro
     for (int i = 0; i < 16; ++i) fb[t * 17 + i] = ft[i];
   }
   P::sync();
-  SIM_FOR(P, e, 256) { const int i = e >> 4, c = e & 15; w.F[e] = (fb[c * 17 + i] - fb[(16 + c) * 17 + i]) / (2 * md.jstep); }
+  SIM_FOR(P, e, 256) {  // q = dt*F directly (MAIN:446: exp(dt*F)); F itself is not needed again
+    const int i = e >> 4, c = e & 15;
+    B0[e] = ((fb[c * 17 + i] - fb[(16 + c) * 17 + i]) / (2 * md.jstep)) * md.dt;
+  }
   SIM_FOR(P, i, 16) w.xdot[i] = fb[i];
   P::sync();
   SIM_TOC(1);
-  double* T1 = w.W; double* T2 = w.W + 256;
-  double* const A2e = w.F;  // exp(dt/2 F) replaces the Jacobian once dt/2 F has been formed
-  SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * md.dt;
-  P::sync();
-  if (!sim_exp_with_half<P, 16>(w.Ae, A2e, w.MM, w.W, w.perm, w.small)) {  // general path: two separate exponentials
-    sim_exp<P, 16>(w.Ae, w.MM, w.W, w.perm, w.small);
-    SIM_FOR(P, e, 256) w.MM[e] = w.F[e] * (md.dt * 0.5);
+  if (SIM_FORCE_GENERAL_EXP || !sim_exp_with_half<P, 16>(Ae, A2e, B0, B1, w.perm, w.small)) {
+    // general path: two separate exponentials.  exp(q) is parked outside the workspace while exp(q/2) is formed; q/2 is
+    // recovered from the scaled copy exp left in B0 (q 2^-s, exact): q/2 = (q 2^-s) 2^(s-1)
+    const int s1 = sim_exp<P, 16>(park, B0, B1, w.perm, w.small);
+    const double back = ldexp(1.0, s1 - 1);
+    SIM_FOR(P, e, 256) B0[e] = B0[e] * back;
     P::sync();
-    sim_exp<P, 16>(A2e, w.MM, w.W, w.perm, w.small);
+    sim_exp<P, 16>(A2e, B0, B1, w.perm, w.small);
+    SIM_FOR(P, e, 256) Ae[e] = park[e];
+    P::sync();
   }
   // MM = (dt/6) * (M + 4*A2*M*~A2 + A*M*~A)
   SIM_RETIC();
-  double* T3 = w.W + 512; double* T4 = w.W + 768;
-  SIM_FOR(P, e, 256) T1[e] = A2e[e] * 4;
+  SIM_FOR(P, e, 256) B0[e] = A2e[e] * 4;
   P::sync();
-  sim_mm<P, false>(T2, T1, md.M, 16, 16, 16);
-  sim_mm<P, true>(T3, T2, A2e, 16, 16, 16);
-  sim_mm<P, false>(T2, w.Ae, md.M, 16, 16, 16);
-  sim_mm<P, true>(T4, T2, w.Ae, 16, 16, 16);
-  SIM_FOR(P, e, 256) w.MM[e] = (md.M[e] + T3[e] + T4[e]) * (md.dt / 6);
+  sim_mm<P, false>(B1, B0, md.M, 16, 16, 16);
+  sim_mm<P, true>(B2, B1, A2e, 16, 16, 16);   // 4*A2*M*~A2
+  sim_mm<P, false>(B1, Ae, md.M, 16, 16, 16);
+  sim_mm<P, true>(B0, B1, Ae, 16, 16, 16);    // A*M*~A
+  SIM_FOR(P, e, 256) B1[e] = (md.M[e] + B2[e] + B0[e]) * (md.dt / 6);
   // v1 = (dt/6)*(xDot + 4*(A2*xDot) + A*xDot)
   SIM_FOR(P, i, 16) {
     double a = 0.0, b = 0.0;
     for (int k = 0; k < 16; ++k) a += A2e[i * 16 + k] * w.xdot[k];
-    for (int k = 0; k < 16; ++k) b += w.Ae[i * 16 + k] * w.xdot[k];
+    for (int k = 0; k < 16; ++k) b += Ae[i * 16 + k] * w.xdot[k];
     w.v1[i] = (w.xdot[i] + a * 4 + b) * (md.dt / 6);
   }
   P::sync();
@@ -799,10 +820,10 @@ SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, const Lqro
 // Simpson increment) and, if Ae_out != 0, A = exp(dt F)[256].
 template <class P>
 SIMF void sim_phase_flow(LqroSimWsA& w, double* MM_out, double* v1_out, double* Ae_out, const LqroSimModel& md) {
-  sim_flow<P>(w, w.xs, w.Rs, md);
-  SIM_FOR(P, e, 256) MM_out[e] = w.MM[e];
+  sim_flow<P>(w, w.xs, w.Rs, MM_out, md);
+  SIM_FOR(P, e, 256) MM_out[e] = w.MM()[e];
   SIM_FOR(P, i, 16) v1_out[i] = w.v1[i];
-  if (Ae_out) { SIM_FOR(P, e, 256) Ae_out[e] = w.Ae[e]; }
+  if (Ae_out) { SIM_FOR(P, e, 256) Ae_out[e] = w.Ae()[e]; }
   P::sync();
 }
 
@@ -826,9 +847,9 @@ SIMF void sim_phase_init(LqroSimWsB& w, const double* x, const double* Rot, cons
 // The flow phase already forms F, xDot, A and exp(dt/2 F); with lqro_solve_gains this is controlMatrices (MAIN:490-544).
 template <class P>
 SIMF void sim_phase_linearize(LqroSimWsA& w, double* A_out, double* B_out, double* c_out, const LqroSimModel& md) {
-  sim_flow<P>(w, w.xs, w.Rs, md);
-  const double* A2e = w.F;
-  double* fb = w.W; double* G = w.W + 256; double* Int = w.W + 512;  // fb [8][17], G 16x4, Int 16x16
+  sim_flow<P>(w, w.xs, w.Rs, A_out, md);
+  const double* A2e = w.A2e(); const double* Ae = w.Ae();
+  double* fb = w.buf; double* G = w.buf + 160; double* Int = w.buf + 512;  // fb [8][17], G 16x4 (B0), Int 16x16 (B2)
   SIM_FOR(P, t, 8) {
     const int c = t & 3, side = t >> 2;
     double xr[16], R[9], u[4], ft[16];
@@ -841,11 +862,11 @@ SIMF void sim_phase_linearize(LqroSimWsA& w, double* A_out, double* B_out, doubl
   }
   P::sync();
   SIM_FOR(P, e, 64) { const int i = e >> 2, c = e & 3; G[e] = (fb[c * 17 + i] - fb[(4 + c) * 17 + i]) / (2 * md.jstep); }
-  SIM_FOR(P, e, 256) { const double id = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; Int[e] = (id + A2e[e] * 4.0 + w.Ae[e]) * (md.dt / 6.0); }
+  SIM_FOR(P, e, 256) { const double id = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; Int[e] = (id + A2e[e] * 4.0 + Ae[e]) * (md.dt / 6.0); }
   P::sync();
   sim_mm<P, false>(B_out, Int, G, 16, 16, 4);
   SIM_FOR(P, i, 16) { double t = 0.0; for (int k = 0; k < 16; ++k) t += Int[i * 16 + k] * w.xdot[k]; c_out[i] = t; }
-  SIM_FOR(P, e, 256) A_out[e] = w.Ae[e];
+  SIM_FOR(P, e, 256) A_out[e] = Ae[e];
   P::sync();
 }
 
@@ -994,8 +1015,14 @@ __global__ void __launch_bounds__(128) k_sim_init(int n, const LqroSimModel* __r
   }
 }
 
+// launch geometry of the flow kernels: warps per CTA x CTAs per SM (11 KB of shared memory per warp; the register cap that
+// follows is 65536 / (32 x warps x CTAs)): measured at 65,536 agents 5 x 3 (128 registers) 6.0 ms, 5 x 4 (96) 6.55 ms
+#ifndef SIM_FLOW_WARPS
+#define SIM_FLOW_WARPS 4
+#define SIM_FLOW_CTAS 4
+#endif
 // linearizeDiscretize for a batch of operating points (warp per problem)
-__global__ void __launch_bounds__(160, 3) k_sim_linearize(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+__global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_linearize(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
                                                           const double* __restrict__ Rot, const double* __restrict__ u,
                                                           double* __restrict__ A, double* __restrict__ B, double* __restrict__ c) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
@@ -1011,7 +1038,7 @@ __global__ void __launch_bounds__(160, 3) k_sim_linearize(int n, const LqroSimMo
   }
 }
 
-__global__ void __launch_bounds__(160, 3) k_sim_flow(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
+__global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_flow(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
                                                      const double* __restrict__ Rot, const double* __restrict__ xTrue,
                                                      const double* __restrict__ RotTrue, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];

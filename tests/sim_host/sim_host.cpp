@@ -78,3 +78,4 @@ extern "C" int simhost_exp_with_half(const double* q, double* full, double* half
   sim_exp<SimSeq, 16>(half, a, ws, perm, small);
   return 0;
 }
+extern "C" void simhost_force_general_exp(int on) { sim_force_general_exp = on; }

@@ -39,6 +39,20 @@ def test_host_build_of_the_kernel_reproduces_the_golden_updates_bit_for_bit(sim_
             assert np.array_equal(o[k], g["s%d_after_%s" % (t, k)]), (int(t), k)
 
 
+def test_general_path_of_the_flow_also_reproduces_the_golden_updates(sim_golden, simhost):
+    """sim_flow with the shared Pade approximant switched off (two separate exponentials, exp(dt F) parked outside the
+    workspace, dt/2 F recovered from the scaled copy): the path inputs with |dt F|_1 < 0.95 would take"""
+    g = sim_golden
+    simhost.lib.simhost_force_general_exp(1)
+    try:
+        for t in (0, 90):
+            o = simhost.update(g["model"], _before(g, t), g["s%d_newV" % t], g["s%d_normals" % t])
+            for k in KEYS:
+                assert np.array_equal(o[k], g["s%d_after_%s" % (t, k)]), (int(t), k)
+    finally:
+        simhost.lib.simhost_force_general_exp(0)
+
+
 def test_stage_pieces_match_the_reference_bit_for_bit(reference, simhost):
     rng = np.random.default_rng(7)
     lib, sh = reference.lib, simhost.lib
