@@ -750,8 +750,8 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
 }
 
 // Four launches per update (lqro_sim.cuh): the control input (thread per agent), the two linearised flows of every agent as
-// independent warp tasks (11 KB of shared memory per warp, 20 warps per SM), the process-noise sample (four agents per warp, 17 KB per warp,
-// 12-16 warps per SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
+// independent warp tasks (11 KB of shared memory per warp, 20 warps per SM), the process-noise sample (four agents per warp, 13 KB per warp,
+// 16 warps per SM), the state / covariance updates + observation + kalmanFilter2 + findVGoal (11.3 KB, 20 warps per SM).
 static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, double* P, double* xTrue, double* RotTrue, const double* newV,
                              const double* pGoal, const double* normals, double* vGoal, double* u, cudaStream_t st) {
   const int wa = SIM_FLOW_WARPS, wb = 4, wc = 4;
@@ -783,10 +783,10 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   k_sim_flow<<<grid(2LL * n, wa, SIM_FLOW_CTAS), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
-  k_sim_noise<<<grid((n + 3) / 4, wb, 3), wb * 32, smem_b, st>>>(n, normals, sc);
+  k_sim_noise<<<grid((n + 3) / 4, wb, 4), wb * 32, smem_b, st>>>(n, normals, sc);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[2], st));
-  k_sim_filter<<<grid(n, wc, 5), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, sc, vGoal);
+  k_sim_filter<<<grid(n, wc, SIM_FILTER_CTAS), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, sc, vGoal);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[3], st));
   ctx->launches_extra += 4;

@@ -1061,21 +1061,26 @@ __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_flow
 // by side the same instructions serve four.  The four groups run the loop in lockstep (a group that has converged idles
 // on dummy operands), every group performs exactly the operation sequence of sim_jacobi / sim_sample_gaussian.
 // Shared memory per group: D[256] | Vt[256] (eigenvectors TRANSPOSED: a rotation touches two contiguous rows) | nrm[16].
-#define SIM_NOISE_LD 17  // row stride of D: its column accesses (the pivot search, the rotation) fall on distinct banks
-#define SIM_NOISE_GROUP_DOUBLES (16 * SIM_NOISE_LD + 256 + 16 + 4)  // +4: group bases fall on different banks
-__global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
+// D is symmetric and the iteration only ever touches its upper triangle (MAT:686-740): packed storage, 136 doubles,
+// element (r, c), r <= c, at r(31 - r)/2 + c -- rows of decreasing length, so column accesses spread over the banks
+#define SIM_TRI(r, c) ((((r) * (31 - (r))) >> 1) + (c))
+#define SIM_NOISE_GROUP_DOUBLES (136 + 256 + 16 + 4)  // +4: group bases fall on different banks
+__global__ void __launch_bounds__(128, 4) k_sim_noise(int n, const double* __restrict__ normals, LqroSimScratch sc) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   constexpr int N = 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int g = lane >> 3, sl = lane & 7;
   double* D = reinterpret_cast<double*>(sim_smem) + (size_t)(warp * 4 + g) * SIM_NOISE_GROUP_DOUBLES;
-  constexpr int LD = SIM_NOISE_LD;
-  double* Vt = D + 16 * LD; double* nrm = Vt + 256;
+  double* Vt = D + 136; double* nrm = Vt + 256;
   for (int a0 = (blockIdx.x * wpb + warp) * 4; a0 < n; a0 += gridDim.x * wpb * 4) {
     const int a = a0 + g;
     bool done = a >= n;
     if (!done) {
-      for (int e = sl; e < 256; e += 8) { D[(e >> 4) * LD + (e & 15)] = sc.MM[(size_t)(2 * a) * 256 + e]; Vt[e] = ((e >> 4) == (e & 15)) ? 1.0 : 0.0; }
+      for (int e = sl; e < 256; e += 8) {
+        const int r = e >> 4, c = e & 15;
+        if (r <= c) D[SIM_TRI(r, c)] = sc.MM[(size_t)(2 * a) * 256 + e];
+        Vt[e] = (r == c) ? 1.0 : 0.0;
+      }
       for (int e = sl; e < 16; e += 8) nrm[e] = normals[(size_t)a * 22 + e];
     }
     __syncwarp();
@@ -1086,7 +1091,7 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
       for (int t = 0; t < 2; ++t) {
         const int k = sl + 8 * t;
         if (k != pivotRow) {
-          const double av = fabs(k < pivotRow ? D[k * LD + pivotRow] : D[pivotRow * LD + k]);
+          const double av = fabs(k < pivotRow ? D[SIM_TRI(k, pivotRow)] : D[SIM_TRI(pivotRow, k)]);
           if (av > maximum) { maximum = av; bi = k; }
         }
       }
@@ -1103,8 +1108,8 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
         if (rot) zeroCount = 0;
         else if (++zeroCount == N) done = true;
       }
-      const double Dpq = rot ? D[p * LD + q] : 1.0;
-      const double theta = 0.5 * ((rot ? D[q * LD + q] : 0.0) - (rot ? D[p * LD + p] : 0.0)) / Dpq;
+      const double Dpq = rot ? D[SIM_TRI(p, q)] : 1.0;
+      const double theta = 0.5 * ((rot ? D[SIM_TRI(q, q)] : 0.0) - (rot ? D[SIM_TRI(p, p)] : 0.0)) / Dpq;
       double t = 1 / (fabs(theta) + sim_hypot(theta, 1));
       if (theta < 0) t = -t;
       const double c = 1 / sim_hypot(t, 1);
@@ -1117,21 +1122,21 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
           const int r = sl + 8 * u;
           if (r < N) {
             if (r < p) {
-              const double Drp = D[r * LD + p], Drq = D[r * LD + q];
-              D[r * LD + p] -= s * (Drq + tau * Drp);
-              D[r * LD + q] += s * (Drp - tau * Drq);
+              const double Drp = D[SIM_TRI(r, p)], Drq = D[SIM_TRI(r, q)];
+              D[SIM_TRI(r, p)] -= s * (Drq + tau * Drp);
+              D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
             } else if (r > p && r < q) {
-              const double Drp = D[p * LD + r], Drq = D[r * LD + q];
-              D[p * LD + r] -= s * (Drq + tau * Drp);
-              D[r * LD + q] += s * (Drp - tau * Drq);
+              const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(r, q)];
+              D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
+              D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
             } else if (r > q) {
-              const double Drp = D[p * LD + r], Drq = D[q * LD + r];
-              D[p * LD + r] -= s * (Drq + tau * Drp);
-              D[q * LD + r] += s * (Drp - tau * Drq);
+              const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(q, r)];
+              D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
+              D[SIM_TRI(q, r)] += s * (Drp - tau * Drq);
             } else if (r == p) {
-              D[p * LD + p] -= t * Dpq;
-              D[q * LD + q] += t * Dpq;
-              D[p * LD + q] = 0;
+              D[SIM_TRI(p, p)] -= t * Dpq;
+              D[SIM_TRI(q, q)] += t * Dpq;
+              D[SIM_TRI(p, q)] = 0;
             }
           } else {
             const int rr = r - N;
@@ -1148,7 +1153,7 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
       for (int u = 0; u < 2; ++u) {
         const int i = sl + 8 * u;
         double acc = 0.0;
-        for (int j = 0; j < N; ++j) acc += (Vt[j * N + i] * sqrt(D[j * LD + j])) * nrm[j];
+        for (int j = 0; j < N; ++j) acc += (Vt[j * N + i] * sqrt(D[SIM_TRI(j, j)])) * nrm[j];
         sc.samp[(size_t)a * 16 + i] = acc + 0.0;
       }
     }
@@ -1156,7 +1161,10 @@ __global__ void __launch_bounds__(128, 3) k_sim_noise(int n, const double* __res
   }
 }
 
-__global__ void __launch_bounds__(128, 5) k_sim_filter(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
+#ifndef SIM_FILTER_CTAS
+#define SIM_FILTER_CTAS 5  // x 4 warps, 11.3 KB of shared memory per warp
+#endif
+__global__ void __launch_bounds__(128, SIM_FILTER_CTAS) k_sim_filter(int n, const LqroSimModel* __restrict__ model, double* __restrict__ x,
                                                        double* __restrict__ Rot, double* __restrict__ Pcov, double* __restrict__ xTrue,
                                                        double* __restrict__ RotTrue, const double* __restrict__ pGoal,
                                                        const double* __restrict__ normals, LqroSimScratch sc, double* __restrict__ vGoal) {
