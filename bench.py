@@ -13,6 +13,10 @@ ours      : value = pairs / device time with everything resident in HBM (CUDA ev
             stream, L2 flushed between timed steps, max over ranks); e2e = the same through the C-ABI call
             lqro_step_sharded() with pinned HOST buffers (H2D of state/vpref/neighbours and D2H of the new
             velocities inside the timed region).
+            N = 1 also reports, outside `value` / `e2e`: `sim_update` -- the second half of the reference's time step
+            (LQR feedback, propagate, Kalman filter: lqro_sim_update_device) for the same agents, per-kernel ms, the
+            reference's own update loop on one host core beside it, and `sim_update.timestep`: whole time steps on
+            resident state (lqro_timestep_device) in closed loop.
 reference : the reference's own CPU implementation (oracle/_ref, built from /root/reference; else the
             oracle port) on the host cores, sharded by process, on a bounded sample of the same workload.
 """
