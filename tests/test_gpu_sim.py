@@ -255,6 +255,53 @@ def test_resident_time_steps_equal_the_host_buffer_loop(sim_golden, golden):
     c.close()
 
 
+def test_resident_time_steps_with_device_neighbour_search(sim_golden, golden):
+    """lqro_timestep_device with LQRO_FLAG_DEVICE_KNN on a 216-agent lattice swarm, K = 12: neighbour table rebuilt on the
+    device from the current positions every step; only the normals go up.  Same bits as the host loop that builds the
+    lists with the kd-tree restatement (swarm.knn), steps with lqro_step and updates with lqro_sim_update."""
+    import torch
+    from lqr_obstacles_b200 import Lqro, swarm
+    from lqr_obstacles_b200.api import FLAG_DEVICE_KNN, SimModel
+
+    g = sim_golden
+    x0, vpref0 = swarm.lattice_swarm((6, 6, 6))
+    x0[:, :3] *= 0.6
+    n, K, steps = len(x0), 12, 5
+    rng = np.random.default_rng(8)
+    normals = rng.normal(size=(steps, n, 22))
+    pGoal = -x0[:, :3].copy()
+    eye, p0 = np.tile(np.eye(3).ravel(), (n, 1)), np.tile((1e-9 * np.eye(16)).ravel(), (n, 1))
+
+    def make(flags):
+        c = Lqro(n_agents=n, max_neighbors=K, horizon=20, flags=flags)
+        c.set_dynamics(golden["dyn_A"], golden["dyn_B"], golden["dyn_L"], golden["dyn_E"])
+        c.sim_set_model(SimModel.from_array(g["model"]))
+        return c
+
+    c = make(0)
+    st = dict(x=x0.copy(), Rot=eye.copy(), P=p0.copy(), xTrue=x0.copy(), RotTrue=eye.copy())
+    vpref = vpref0.copy()
+    for t in range(steps):
+        newV = c.step(st["x"], vpref, swarm.knn(st["x"][:, :3], K))
+        vpref, _ = c.sim_update(st["x"], st["Rot"], st["P"], st["xTrue"], st["RotTrue"], newV, pGoal, normals[t])
+    c.close()
+    c = make(FLAG_DEVICE_KNN)
+    c.upload_local_state(np.ascontiguousarray(x0))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    d = dict(Rot=dev(eye), P=dev(p0), xTrue=dev(x0), RotTrue=dev(eye), pGoal=dev(pGoal), vGoal=dev(vpref0))
+    torch.cuda.synchronize()
+    for t in range(steps):
+        dn = dev(normals[t])
+        torch.cuda.synchronize()
+        c.timestep_device(d["Rot"].data_ptr(), d["P"].data_ptr(), d["xTrue"].data_ptr(), d["RotTrue"].data_ptr(), d["pGoal"].data_ptr(),
+                          dn.data_ptr(), d["vGoal"].data_ptr())
+        c.synchronize()
+    assert np.array_equal(d["xTrue"].cpu().numpy(), st["xTrue"])
+    assert np.array_equal(d["P"].cpu().numpy(), st["P"])
+    assert np.array_equal(d["vGoal"].cpu().numpy(), vpref)
+    c.close()
+
+
 def test_update_against_the_compiled_reference_on_perturbed_states(ctx, reference, sim_golden):
     """states off the canonical trajectory: random attitude errors, velocities and covariances pushed through the
     reference's own update (oracle/_ref) and through the kernel with the same normals"""
