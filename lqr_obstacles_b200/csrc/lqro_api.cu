@@ -109,7 +109,7 @@ struct lqro_ctx {
   // multi-GPU
   lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
   // simulator-form agent update (lqro_sim.cuh)
-  LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false, sim_attr_set = false;
+  LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false, sim_attr_set = false; int sim_m_diag = 0;
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
   cudaEvent_t ev_sim[4] = {nullptr, nullptr, nullptr, nullptr};
   char* d_sim_scratch = nullptr; size_t sim_scratch_bytes = 0;
@@ -745,6 +745,8 @@ extern "C" int lqro_sim_set_model(lqro_ctx* ctx, const lqro_sim_model* m) {
   if (!ctx->d_sim_model) CU(cudaMalloc(&ctx->d_sim_model, sizeof(LqroSimModel)));
   CU(cudaMemcpyAsync(ctx->d_sim_model, m, sizeof(LqroSimModel), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->sim_m_diag = 1;  // diagonal motion-noise covariance: two of the four products of the noise covariance collapse (lqro_sim.cuh)
+  for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) if (i != j && m->M[i * 16 + j] != 0.0) ctx->sim_m_diag = 0;
   ctx->have_sim_model = true;
   return LQRO_OK;
 }
@@ -780,7 +782,7 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   CU(cudaEventRecord(ctx->ev_sim[0], st));
   k_sim_control<<<(n + 127) / 128, 128, 0, st>>>(n, ctx->d_sim_model, x, Rot, newV, sc.u, u);
   CU(cudaGetLastError());
-  k_sim_flow<<<grid(2LL * n, wa, SIM_FLOW_CTAS), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc);
+  k_sim_flow<<<grid(2LL * n, wa, SIM_FLOW_CTAS), wa * 32, smem_a, st>>>(n, ctx->d_sim_model, x, Rot, xTrue, RotTrue, sc, ctx->sim_m_diag);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[1], st));
   k_sim_noise<<<grid((n + 3) / 4, wb, 4), wb * 32, smem_b, st>>>(n, normals, sc);
@@ -1200,7 +1202,7 @@ extern "C" int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const doubl
   CU(cudaFuncSetAttribute(k_sim_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int blocks = (n_batch + wa - 1) / wa;
   if (blocks > ctx->sm_count * SIM_FLOW_CTAS) blocks = ctx->sm_count * SIM_FLOW_CTAS;
-  k_sim_linearize<<<blocks, wa * 32, smem, st>>>(n_batch, ctx->d_sim_model, dx, dR, du, dA, dB, dc);
+  k_sim_linearize<<<blocks, wa * 32, smem, st>>>(n_batch, ctx->d_sim_model, dx, dR, du, dA, dB, dc, ctx->sim_m_diag);
   CU(cudaGetLastError());
   ctx->launches_extra++;
   CU(cudaMemcpyAsync(A, dA, 8 * 256 * nb, cudaMemcpyDeviceToHost, st));

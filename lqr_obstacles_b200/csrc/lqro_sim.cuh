@@ -716,7 +716,7 @@ SIMF void sim_find_vgoal(double* vG, const double* x, const double* R0, const do
 struct alignas(16) LqroSimWsA {
   double buf[5 * 256];
   double xs[16], Rs[9], u[4], xdot[16], v1[16], small[16];
-  int perm[32];
+  int perm[32], m_diag, pad_;  // m_diag: the motion-noise covariance M is diagonal (set by the caller; see sim_flow)
   SIMM double* A2e() { return buf + 3 * 256; }  // after sim_flow: exp(dt/2 F)
   SIMM double* Ae() { return buf + 4 * 256; }   //                 exp(dt F)
   SIMM double* MM() { return buf + 1 * 256; }   //                 the noise covariance
@@ -791,9 +791,13 @@ SIMN void sim_flow(LqroSimWsA& w, const double* xs, const double* Rs, double* pa
   SIM_RETIC();
   SIM_FOR(P, e, 256) B0[e] = A2e[e] * 4;
   P::sync();
-  sim_mm<P, false>(B1, B0, md.M, 16, 16, 16);
+  // X*M for a DIAGONAL M (the reference's M = 1e-9 I, MAIN:1139): the 16-term sum 0 + X(i,0) M(0,j) + ... has one non-zero
+  // term, so it equals 0.0 + X(i,j) M(j,j) bit for bit (the leading +0 reproduces the sum's +0 when the product is -0)
+  if (w.m_diag) { SIM_FOR(P, e, 256) B1[e] = 0.0 + B0[e] * md.M[(e & 15) * 17]; P::sync(); }
+  else sim_mm<P, false>(B1, B0, md.M, 16, 16, 16);
   sim_mm<P, true>(B2, B1, A2e, 16, 16, 16);   // 4*A2*M*~A2
-  sim_mm<P, false>(B1, Ae, md.M, 16, 16, 16);
+  if (w.m_diag) { SIM_FOR(P, e, 256) B1[e] = 0.0 + Ae[e] * md.M[(e & 15) * 17]; P::sync(); }
+  else sim_mm<P, false>(B1, Ae, md.M, 16, 16, 16);
   sim_mm<P, true>(B0, B1, Ae, 16, 16, 16);    // A*M*~A
   SIM_FOR(P, e, 256) B1[e] = (md.M[e] + B2[e] + B0[e]) * (md.dt / 6);
   // v1 = (dt/6)*(xDot + 4*(A2*xDot) + A*xDot)
@@ -1024,7 +1028,7 @@ __global__ void __launch_bounds__(128) k_sim_init(int n, const LqroSimModel* __r
 // linearizeDiscretize for a batch of operating points (warp per problem)
 __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_linearize(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
                                                           const double* __restrict__ Rot, const double* __restrict__ u,
-                                                          double* __restrict__ A, double* __restrict__ B, double* __restrict__ c) {
+                                                          double* __restrict__ A, double* __restrict__ B, double* __restrict__ c, int m_diag) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const LqroSimModel& md = *model;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -1033,6 +1037,7 @@ __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_line
     if (lane < 16) w.xs[lane] = x[(size_t)a * 16 + lane];
     if (lane < 9) w.Rs[lane] = Rot[(size_t)a * 9 + lane];
     if (lane < 4) w.u[lane] = u[(size_t)a * 4 + lane];
+    if (lane == 0) w.m_diag = m_diag;
     __syncwarp();
     sim_phase_linearize<SimWarp>(w, A + (size_t)a * 256, B + (size_t)a * 64, c + (size_t)a * 16, md);
   }
@@ -1040,7 +1045,7 @@ __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_line
 
 __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_flow(int n, const LqroSimModel* __restrict__ model, const double* __restrict__ x,
                                                      const double* __restrict__ Rot, const double* __restrict__ xTrue,
-                                                     const double* __restrict__ RotTrue, LqroSimScratch sc) {
+                                                     const double* __restrict__ RotTrue, LqroSimScratch sc, int m_diag) {
   extern __shared__ __align__(16) unsigned char sim_smem[];
   const LqroSimModel& md = *model;  // 3.6 KB of constants and gains, read through L1 (uniform or row-contiguous accesses)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -1051,6 +1056,7 @@ __global__ void __launch_bounds__(SIM_FLOW_WARPS * 32, SIM_FLOW_CTAS) k_sim_flow
     if (lane < 16) w.xs[lane] = xs[(size_t)a * 16 + lane];
     if (lane < 9) w.Rs[lane] = Rs[(size_t)a * 9 + lane];
     if (lane < 4) w.u[lane] = sc.u[(size_t)a * 4 + lane];
+    if (lane == 0) w.m_diag = m_diag;
     __syncwarp();
     sim_phase_flow<SimWarp>(w, sc.MM + (size_t)t * 256, sc.v1 + (size_t)t * 16, est ? sc.Ae + (size_t)a * 256 : nullptr, md);
   }

@@ -5,6 +5,13 @@
 // there is no CPU fallback.
 #include "../../lqr_obstacles_b200/csrc/lqro_sim.cuh"
 
+static int g_use_m_diag = 1;  // tests switch the diagonal-M shortcut of sim_flow off to compare both forms
+extern "C" void simhost_use_m_diag(int on) { g_use_m_diag = on; }
+static int m_is_diag(const LqroSimModel* md) {
+  if (!g_use_m_diag) return 0;
+  for (int i = 0; i < 16; ++i) for (int j = 0; j < 16; ++j) if (i != j && md->M[i * 16 + j] != 0.0) return 0;
+  return 1;
+}
 extern "C" int simhost_model_doubles(void) { return (int)(sizeof(LqroSimModel) / sizeof(double)); }
 
 extern "C" void simhost_update(int n, const LqroSimModel* md, double* x, double* Rot, double* P, double* xTrue, double* RotTrue,
@@ -19,6 +26,7 @@ extern "C" void simhost_update(int n, const LqroSimModel* md, double* x, double*
       for (int e = 0; e < 16; ++e) wa.xs[e] = est ? x[16 * a + e] : xTrue[16 * a + e];
       for (int e = 0; e < 9; ++e) wa.Rs[e] = est ? Rot[9 * a + e] : RotTrue[9 * a + e];
       for (int e = 0; e < 4; ++e) wa.u[e] = uu[e];
+      wa.m_diag = m_is_diag(md);
       sim_phase_flow<SimWarp>(wa, MM[est], v1[est], est ? Ae : nullptr, *md);
     }
     // noise (k_sim_noise)
@@ -56,6 +64,7 @@ extern "C" void simhost_linearize(const LqroSimModel* md, const double* x, const
   for (int e = 0; e < 16; ++e) w.xs[e] = x[e];
   for (int e = 0; e < 9; ++e) w.Rs[e] = Rot[e];
   for (int e = 0; e < 4; ++e) w.u[e] = u[e];
+  w.m_diag = m_is_diag(md);
   sim_phase_linearize<SimWarp>(w, A, B, c, *md);
 }
 extern "C" void simhost_init(int n, const LqroSimModel* md, const double* x, const double* Rot, const double* P, const double* pGoal,

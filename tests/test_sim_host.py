@@ -53,6 +53,24 @@ def test_general_path_of_the_flow_also_reproduces_the_golden_updates(sim_golden,
         simhost.lib.simhost_force_general_exp(0)
 
 
+def test_diagonal_noise_covariance_shortcut_changes_no_bit(sim_golden, simhost):
+    """X*M for the diagonal M = 1e-9 I as one product per element (sim_flow) vs the full 16-term sums: same bits, and both
+    equal the reference's update (the default run of the other tests uses the shortcut)"""
+    g = sim_golden
+    simhost.lib.simhost_use_m_diag(0)
+    try:
+        for t in (1, 90, 209):
+            o = simhost.update(g["model"], _before(g, t), g["s%d_newV" % t], g["s%d_normals" % t])
+            for k in KEYS:
+                assert np.array_equal(o[k], g["s%d_after_%s" % (t, k)]), (int(t), k)
+                assert np.array_equal(np.signbit(o[k]), np.signbit(g["s%d_after_%s" % (t, k)])), (int(t), k)  # zeros keep their sign too
+    finally:
+        simhost.lib.simhost_use_m_diag(1)
+    o = simhost.update(g["model"], _before(g, 90), g["s90_newV"], g["s90_normals"])
+    for k in KEYS:
+        assert np.array_equal(np.signbit(o[k]), np.signbit(g["s90_after_%s" % k])), k
+
+
 def test_stage_pieces_match_the_reference_bit_for_bit(reference, simhost):
     rng = np.random.default_rng(7)
     lib, sh = reference.lib, simhost.lib
