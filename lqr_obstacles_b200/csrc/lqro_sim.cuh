@@ -894,9 +894,11 @@ SIMF void sim_phase_filter(LqroSimWsC& w, const double* Ae_k, const double* MM_k
                            const double* samp, const double* pGoal, double* vG, const LqroSimModel& md) {
   SIM_TIC();
   {  // kalmanFilter1: P = A*P*~A + MM; x += increment; fold the rotation error
-    double* T1 = w.W; double* T2 = w.W + 256;
-    sim_mm<P, false>(T1, Ae_k, w.P, 16, 16, 16);
-    sim_mm<P, true>(T2, T1, Ae_k, 16, 16, 16);
+    double* T1 = w.W; double* T2 = w.W + 256; double* As = w.W + 512;
+    SIM_FOR(P, e, 256) As[e] = Ae_k[e];  // stage A (HBM scratch of the flow kernel) once: both products read it 16 times over
+    P::sync();
+    sim_mm<P, false>(T1, As, w.P, 16, 16, 16);
+    sim_mm<P, true>(T2, T1, As, 16, 16, 16);
     SIM_FOR(P, e, 256) w.P[e] = T2[e] + MM_k[e];
     double r[3], R[9];
     for (int i = 0; i < 3; ++i) r[i] = w.x[6 + i] + v1k[6 + i];
