@@ -1116,45 +1116,47 @@ __global__ void __launch_bounds__(128, 4) k_sim_noise(int n, const double* __res
         if (rot) zeroCount = 0;
         else if (++zeroCount == N) done = true;
       }
-      const double Dpq = rot ? D[SIM_TRI(p, q)] : 1.0;
-      const double theta = 0.5 * ((rot ? D[SIM_TRI(q, q)] : 0.0) - (rot ? D[SIM_TRI(p, p)] : 0.0)) / Dpq;
-      double t = 1 / (fabs(theta) + sim_hypot(theta, 1));
-      if (theta < 0) t = -t;
-      const double c = 1 / sim_hypot(t, 1);
-      const double s = c * t;
-      const double tau = s / (1 + c);
-      __syncwarp();
-      if (rot) {
+      if (__any_sync(0xffffffffu, rot)) {  // warp-uniform: an iteration in which no group rotates costs only its pivot scan
+        const double Dpq = rot ? D[SIM_TRI(p, q)] : 1.0;
+        const double theta = 0.5 * ((rot ? D[SIM_TRI(q, q)] : 0.0) - (rot ? D[SIM_TRI(p, p)] : 0.0)) / Dpq;
+        double t = 1 / (fabs(theta) + sim_hypot(theta, 1));
+        if (theta < 0) t = -t;
+        const double c = 1 / sim_hypot(t, 1);
+        const double s = c * t;
+        const double tau = s / (1 + c);
+        __syncwarp();
+        if (rot) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = sl + 8 * u;
-          if (r < N) {
-            if (r < p) {
-              const double Drp = D[SIM_TRI(r, p)], Drq = D[SIM_TRI(r, q)];
-              D[SIM_TRI(r, p)] -= s * (Drq + tau * Drp);
-              D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
-            } else if (r > p && r < q) {
-              const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(r, q)];
-              D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
-              D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
-            } else if (r > q) {
-              const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(q, r)];
-              D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
-              D[SIM_TRI(q, r)] += s * (Drp - tau * Drq);
-            } else if (r == p) {
-              D[SIM_TRI(p, p)] -= t * Dpq;
-              D[SIM_TRI(q, q)] += t * Dpq;
-              D[SIM_TRI(p, q)] = 0;
+          for (int u = 0; u < 4; ++u) {
+            const int r = sl + 8 * u;
+            if (r < N) {
+              if (r < p) {
+                const double Drp = D[SIM_TRI(r, p)], Drq = D[SIM_TRI(r, q)];
+                D[SIM_TRI(r, p)] -= s * (Drq + tau * Drp);
+                D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
+              } else if (r > p && r < q) {
+                const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(r, q)];
+                D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
+                D[SIM_TRI(r, q)] += s * (Drp - tau * Drq);
+              } else if (r > q) {
+                const double Drp = D[SIM_TRI(p, r)], Drq = D[SIM_TRI(q, r)];
+                D[SIM_TRI(p, r)] -= s * (Drq + tau * Drp);
+                D[SIM_TRI(q, r)] += s * (Drp - tau * Drq);
+              } else if (r == p) {
+                D[SIM_TRI(p, p)] -= t * Dpq;
+                D[SIM_TRI(q, q)] += t * Dpq;
+                D[SIM_TRI(p, q)] = 0;
+              }
+            } else {
+              const int rr = r - N;
+              const double Vrp = Vt[p * N + rr], Vrq = Vt[q * N + rr];
+              Vt[p * N + rr] -= s * (Vrq + tau * Vrp);
+              Vt[q * N + rr] += s * (Vrp - tau * Vrq);
             }
-          } else {
-            const int rr = r - N;
-            const double Vrp = Vt[p * N + rr], Vrq = Vt[q * N + rr];
-            Vt[p * N + rr] -= s * (Vrq + tau * Vrp);
-            Vt[q * N + rr] += s * (Vrp - tau * Vrq);
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (a < n) {  // sample = SVec * sqrt(SVal) * normals + 0  (SIM2:19-31)
 #pragma unroll
