@@ -39,3 +39,15 @@ def allgather_state(x_local, group=None):
 def gather_results(v_local, group=None):
     """all ranks' new velocities in agent order (used by tests / drivers that want the full vector)"""
     return allgather_state(v_local, group)
+
+
+def local_normals(seed, n_agents, world, rank, per_agent=22):
+    """Standard normals of one simulator-form update for this rank's agents.  The reference draws its noise from ONE sequential
+    rand() stream over all quadrotors (MAIN:1408-1417), so every rank draws the whole step's per_agent*n_agents values
+    (host work: microseconds per agent) and keeps its block; all ranks end on the same generator state.
+    -> (normals (n_local, per_agent), new_seed)"""
+    from .api import msvc_normals
+
+    lo, nl = shard_bounds(n_agents, world, rank)
+    allv, new_seed = msvc_normals(seed, per_agent * n_agents)
+    return np.ascontiguousarray(allv.reshape(n_agents, per_agent)[lo:lo + nl]), new_seed

@@ -81,6 +81,21 @@ def test_bad_arguments_return_codes(product_lib):
     assert product_lib.lqro_msvc_normals(ctypes.byref(seed), 0, None) == 0 and seed.value == 1
 
 
+def test_headless_simulator_refuses_to_run_without_a_gpu(product_lib):
+    """tools/headless/lqro_headless is product code: with no CUDA device it must fail loudly, not fall back"""
+    import subprocess
+
+    import torch
+    from lqr_obstacles_b200 import build
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = build.build_headless()
+    r = subprocess.run([exe, "--steps", "1", "--quiet"], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
 def test_swarm_generator_is_deterministic():
     from lqr_obstacles_b200 import swarm
 

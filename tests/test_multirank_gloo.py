@@ -61,6 +61,49 @@ def test_two_rank_sharding_matches_single(tmp_path):
     assert np.load(os.path.join(str(tmp_path), "ok.npy"))[0]
 
 
+def _sim_worker(rank, world, port, outdir):
+    """simulator-form update sharded over two ranks (the CPU build of the update kernels' source does the per-agent work
+    here): each rank updates its own quads with its block of the step's normals; the assembled result equals the
+    one-process update bit for bit and both ranks end on the same rand() state"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from _libs import SimHost
+    from lqr_obstacles_b200 import dist as ldist
+    from lqr_obstacles_b200.api import msvc_normals
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = np.load(os.path.join(HERE, "golden", "sim_update.npz"))
+    sh = SimHost()
+    n, t = 6, 90
+    lo, nl = ldist.shard_bounds(n, world, rank)
+    seed0 = int(g["seeds"][t])
+    nrm, seed1 = ldist.local_normals(seed0, n, world, rank)
+    assert np.array_equal(nrm, g["s%d_normals" % t][lo:lo + nl])
+    st = {k: np.ascontiguousarray(g["s%d_before_%s" % (t, k)][lo:lo + nl]) for k in ("x", "Rot", "P", "xTrue", "RotTrue", "pGoal")}
+    o = sh.update(g["model"], st, np.ascontiguousarray(g["s%d_newV" % t][lo:lo + nl]), nrm)
+    x_all = ldist.allgather_state(o["x"])          # the exchange the next avoidance step starts with
+    xt_all = ldist.gather_results(o["xTrue"])
+    ok = [np.array_equal(x_all, g["s%d_after_x" % t]), np.array_equal(xt_all, g["s%d_after_xTrue" % t]),
+          seed1 == msvc_normals(seed0, 22 * n)[1]]
+    if t + 1 < len(g["seeds"]):
+        ok.append(seed1 == int(g["seeds"][t + 1]))
+    np.save(os.path.join(outdir, "ok%d.npy" % rank), np.array(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_simulator_update_matches_the_reference(tmp_path):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_sim_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(os.path.join(str(tmp_path), "ok%d.npy" % r)).all()
+
+
 def test_shard_bounds():
     sys.path.insert(0, os.path.dirname(HERE))
     from lqr_obstacles_b200.dist import shard_bounds
