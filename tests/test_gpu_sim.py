@@ -152,14 +152,13 @@ def test_headless_simulator_reproduces_the_reference_run(sim_golden, product_lib
     out = str(tmp_path / "traj.bin")
     r = subprocess.run([exe, "--scenario", "hexagon6", "--steps", "210", "--out", out, "--quiet"], capture_output=True, text=True, check=True)
     m = json.loads(r.stdout.strip().splitlines()[-1])
-    raw = open(out, "rb").read()
-    assert raw[:8] == b"LQROTRJ1"
-    n, steps, sd, _ = np.frombuffer(raw[8:24], dtype=np.int32)
-    assert (n, steps, sd) == (6, 210, 16)
-    tr = np.frombuffer(raw[24:], dtype=np.float64).reshape(steps, 2, n, 16)
+    from lqr_obstacles_b200.formats import read_trajectory
+
+    x_true, x_est = read_trajectory(out)
+    assert x_true.shape == (210, 6, 16)
     g = sim_golden
-    err = np.abs(tr[:, 0, :, :6] - g["traj_xTrue"][:, :, :6]).max()
-    err_est = np.abs(tr[:, 1, :, :6] - g["traj_x"][:, :, :6]).max()
+    err = np.abs(x_true[:, :, :6] - g["traj_xTrue"][:, :, :6]).max()
+    err_est = np.abs(x_est[:, :, :6] - g["traj_x"][:, :, :6]).max()
     print("headless run: max |xTrue - reference| %.3e m, estimates %.3e, %s" % (err, err_est, m))
     assert err <= 1e-5 and err_est <= 1e-5
     assert m["inside_pairs"] > 0 and m["max_distance_to_goal_m"] < 1.0
