@@ -434,3 +434,53 @@ class SimHost:
         self.lib.simhost_update(n, P(model), P(o["x"]), P(o["Rot"]), P(o["P"]), P(o["xTrue"]), P(o["RotTrue"]), P(newV), P(pGoal),
                                 P(normals), P(o["vGoal"]), P(o["u"]))
         return o
+
+
+HULLHOST_DIR = os.path.join(ROOT, "tests", "hull_host")
+HULLHOST_SO = os.path.join(HULLHOST_DIR, "libhullhost.so")
+HULLHOST_SRCS = [os.path.join(HULLHOST_DIR, "hull_host.cpp"), os.path.join(HULLHOST_DIR, "warp_emul.h"),
+                 os.path.join(ROOT, "lqr_obstacles_b200", "csrc", "lqro_hull_core.cuh")]
+
+
+class HullHost:
+    """The kernel source csrc/lqro_hull_core.cuh compiled as plain C++ on a 32-thread lockstep emulation of the warp
+    primitives (tests/hull_host/warp_emul.h): checks the LOGIC of the CUDA hull where no GPU exists.  Test
+    infrastructure; the product never links it."""
+
+    def __init__(self, general=False):
+        """general=True: the build that forces the general branches (owner-word ridge matching, wide visited set) on every
+        cone of more than 2 / 3 facets, so that small clouds exercise them"""
+        so = HULLHOST_SO.replace(".so", "_general.so") if general else HULLHOST_SO
+        extra = ["-DLQRO_HULL_PAIRMATCH_MAX=2", "-DLQRO_HULL_NARROW_WALK_MAX=3"] if general else []
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in HULLHOST_SRCS):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-pthread"]
+                                  + extra + ["-o", so, HULLHOST_SRCS[0]])
+        self.lib = lib = ctypes.CDLL(so)
+        lib.hullhost_build.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+        lib.hullhost_coverage.argtypes = [c_void_p, c_int]
+        lib.hullhost_round6.restype = c_double
+        lib.hullhost_round6.argtypes = [c_double]
+
+    def hull(self, pts, mode=0, cap_f=0, vrel=None, ring=0):
+        """ring > 0: size of the pending ring (a power of two below the default, to force its compaction)
+        -> planes (nf,4), verts (nf,3), info dict, escape (distance, normal[3]) or None"""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        n = len(pts)
+        maxf = 2 * n + 64
+        planes, verts = np.zeros((maxf, 4)), np.zeros((maxf, 3), dtype=np.int32)
+        info, esc = np.zeros(5, dtype=np.int32), np.zeros(4)
+        v = None if vrel is None else np.ascontiguousarray(vrel, dtype=np.float64)
+        self.lib.hullhost_build(P(pts), n, mode, cap_f, ring, P(planes), P(verts), maxf, P(info), P(v), P(esc))
+        nf = int(info[0])
+        d = dict(nfacets=nf, degenerate=int(info[1]), fail=int(info[2]), ninserted=int(info[3]), best_facet=int(info[4]))
+        return planes[:nf], verts[:nf], d, (None if vrel is None else (esc[0], esc[1:4].copy()))
+
+    def coverage(self, reset=False):
+        out = np.zeros(8, dtype=np.int64)
+        self.lib.hullhost_coverage(P(out), 1 if reset else 0)
+        return dict(zip(("cone_gt16", "cone_gt64", "exhaustive", "old_facet_moved", "ring_compaction", "horizon_flood",
+                         "multi_chunk_partition", "multi_chunk_wave"), out.tolist()))
+
+    def round6(self, a):
+        a = np.asarray(a, dtype=np.float64)
+        return np.array([self.lib.hullhost_round6(float(v)) for v in a.ravel()]).reshape(a.shape)
