@@ -143,6 +143,11 @@ def load_library(path=None):
     lib.lqro_timestep_device.argtypes = [c_void_p] * 9
     lib.lqro_linearize_discretize.argtypes = [c_void_p, c_int] + [c_void_p] * 6
     lib.lqro_sim_init.argtypes = [c_void_p, c_int] + [c_void_p] * 8
+    lib.lqro_knn.argtypes = [c_void_p] * 3
+    lib.lqro_knn_device.argtypes = [c_void_p] * 4   # the stream is a 64-bit handle: never let ctypes marshal it as a C int
+    lib.lqro_get_neighbors.argtypes = [c_void_p] * 2
+    lib.lqro_set_dynamics_class.argtypes = [c_void_p, c_int] + [c_void_p] * 4
+    lib.lqro_set_agent_classes.argtypes = [c_void_p] * 2
     if path == _build.SO:
         _lib = lib
     return lib
@@ -398,7 +403,7 @@ class Lqro:
         return nbr
 
     def knn_device(self, d_x=None, d_nbr=None, stream=None):
-        self._ck(self.lib.lqro_knn_device(self.h, _p(d_x), _p(d_nbr), stream))
+        self._ck(self.lib.lqro_knn_device(self.h, _p(d_x), _p(d_nbr), c_void_p(stream) if stream else None))
 
     def neighbors(self):
         nbr = np.zeros((self.NL, self.K), dtype=np.int32)

@@ -64,7 +64,7 @@ struct lqro_ctx {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool have_dynamics = false, stepped = false;
+  bool have_dynamics = false, stepped = false, have_nbr = false;  // have_nbr: a neighbour table is resident in d_nbr
   // tables / dynamics
   double *d_dyn = nullptr;   // A(256) B(64) L(64) E(12)
   double *d_NFt = nullptr, *d_NF = nullptr, *d_T = nullptr, *d_sph = nullptr, *d_CG = nullptr, *d_prn = nullptr;
@@ -113,8 +113,8 @@ struct lqro_ctx {
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
   cudaEvent_t ev_sim[4] = {nullptr, nullptr, nullptr, nullptr};
   char* d_sim_scratch = nullptr; size_t sim_scratch_bytes = 0;
-  long long launches = 0;
-  int launches_extra = 0;
+  long long launches = 0;      // kernel launches of the last avoidance step (launch_step)
+  long long sim_launches = 0;  // kernel launches of the simulator-form entry points, cumulative
   std::string err;
 };
 
@@ -260,7 +260,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMemset(ctx->d_nreach, 0, sizeof(int) * NP));
   CUC(cudaMemset(ctx->d_dist, 0, sizeof(double) * NP));
   CUC(cudaMemset(ctx->d_planes, 0, sizeof(float) * 6 * NP));
-  ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)(NP < (1u << 20) ? NP : (1u << 20));
+  ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)NP;  // lqro.h: 0 => every pair may queue
   CUC(cudaMalloc(&ctx->d_hull_items, sizeof(int) * (size_t)ctx->hull_cap));
   // sphere samples: createSpheres, MAIN:665-680 (one-off table; radii doubled for the Minkowski sum)
   {
@@ -299,7 +299,9 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     ctx->pair_smem = tbl + per2 * wp + (ctx->fused_hull ? hullw : 0);
     ctx->pair_blocks = ctx->sm_count;  // persistent: one CTA per SM
     ctx->pair_ovf_stride = 3 * (size_t)(H * P > LQRO_PAIR_CLOUD_CAP ? H * P - LQRO_PAIR_CLOUD_CAP : 0) + 8;
-    CUC(cudaMalloc(&ctx->d_pair_ovf, sizeof(double) * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * wp));
+    // one overflow area per pair warp AND per concurrent launch: the chunked neighbour upload (launch_step) runs LQRO_NBR_CHUNKS
+    // pair kernels on independent streams, CTA b of chunk c and CTA b of chunk c + 1 can be resident at the same time
+    CUC(cudaMalloc(&ctx->d_pair_ovf, sizeof(double) * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * wp * LQRO_NBR_CHUNKS));
     // function attributes are per function, not per context: always allow the device maximum so that
     // contexts with different H*P can coexist
     CUC(cudaFuncSetAttribute(k_pairs<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
@@ -448,15 +450,16 @@ extern "C" int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls) {
   CU(cudaStreamSynchronize(ctx->stream));
   const LqroParams& p = ctx->prm;
   if (!cls) { ctx->hetero = false; return LQRO_OK; }
-  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) ctx->cls_count[c] = 0;
+  // validate into locals, commit only on success (a failed call leaves the previous assignment in force)
+  int count[LQRO_MAX_CLASSES] = {0}, begin[LQRO_MAX_CLASSES] = {0};
   for (int i = 0; i < p.N; ++i) {
     if (cls[i] < 0 || cls[i] >= LQRO_MAX_CLASSES || !ctx->cls[cls[i]].set) return fail(ctx, LQRO_E_ARG, "agent class without dynamics");
   }
-  for (int il = 0; il < p.n_local; ++il) ctx->cls_count[cls[p.local_begin + il]]++;
+  for (int il = 0; il < p.n_local; ++il) count[cls[p.local_begin + il]]++;
   int run = 0;
-  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) { ctx->cls_begin[c] = run; run += ctx->cls_count[c]; }
+  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) { begin[c] = run; run += count[c]; }
   std::vector<int> order(p.n_local), fill(LQRO_MAX_CLASSES, 0);
-  for (int il = 0; il < p.n_local; ++il) { const int c = cls[p.local_begin + il]; order[ctx->cls_begin[c] + fill[c]++] = il; }
+  for (int il = 0; il < p.n_local; ++il) { const int c = cls[p.local_begin + il]; order[begin[c] + fill[c]++] = il; }
   if (!ctx->d_agent_class) {
     CU(cudaMalloc(&ctx->d_agent_class, sizeof(int) * (size_t)p.N));
     CU(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)p.n_local));
@@ -464,6 +467,7 @@ extern "C" int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls) {
   }
   CU(cudaMemcpy(ctx->d_agent_class, cls, sizeof(int) * (size_t)p.N, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(ctx->d_order, order.data(), sizeof(int) * (size_t)p.n_local, cudaMemcpyHostToDevice));
+  for (int c = 0; c < LQRO_MAX_CLASSES; ++c) { ctx->cls_count[c] = count[c]; ctx->cls_begin[c] = begin[c]; }
   ctx->hetero = true;
   return LQRO_OK;
 }
@@ -509,6 +513,7 @@ static int launch_knn(lqro_ctx* ctx, const double* d_x, int* d_nbr_out, cudaStre
   else if (E == 2) k_knn_query<2><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
   else k_knn_query<4><<<qb, wpb * 32, smem, st>>>(d_x, p.local_begin, p.n_local, p.K, ctx->d_knn_grid, ctx->d_knn_start, ctx->d_knn_sid, ctx->d_knn_spos, d_nbr_out);
   CU(cudaGetLastError());
+  if (d_nbr_out == ctx->d_nbr) ctx->have_nbr = true;
   return LQRO_OK;
 }
 
@@ -546,11 +551,12 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
   CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
   CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 32, st));
-  CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet
+  if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
   StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  int pair_launches = 0;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
-  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ctx->d_pair_ovf,  \
+  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,         \
                                                                             ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
 #define LQRO_LAUNCH_PAIRS_ANY(PP, TB, ORD)                                                                                     \
   do {                                                                                                                         \
@@ -560,6 +566,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
   } while (0)
   cudaStream_t pst = st;  // stream of the pair-kernel launches
+  double* ovf_base = ctx->d_pair_ovf;  // overflow clouds of the launch (one region per concurrent launch)
   if (ctx->h_nbr_chunked) {
     const int* h_nbr = ctx->h_nbr_chunked;
     ctx->h_nbr_chunked = nullptr;
@@ -596,14 +603,17 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       pc.n_local = cnt;
       sy.batch_counter = ctx->d_chunk_ctr + c;
       const int* ord = ctx->d_identity + off;
+      ovf_base = ctx->d_pair_ovf + (size_t)c * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * ctx->pair_warps;
       LQRO_LAUNCH_PAIRS_ANY(pc, ctx->tb, ord);
       CU(cudaEventRecord(ctx->ev_done[c], pst));
       CU(cudaStreamWaitEvent(st, ctx->ev_done[c], 0));
-      ++ctx->launches_extra;
+      ++pair_launches;
     }
     pst = st;
+    ovf_base = ctx->d_pair_ovf;
   } else if (!ctx->hetero) {
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+    ++pair_launches;
   } else {
     // one launch per dynamics class over the owned agents of that class (the tables of one class fill the CTA's shared memory)
     CU(cudaMemsetAsync(ctx->d_cls_ctr, 0, sizeof(int) * LQRO_MAX_CLASSES, st));
@@ -616,7 +626,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       sy.batch_counter = ctx->d_cls_ctr + c;
       const int* ord = ctx->d_order + ctx->cls_begin[c];
       LQRO_LAUNCH_PAIRS_ANY(pc, tbc, ord);
-      ++ctx->launches_extra;
+      ++pair_launches;
     }
   }
   CU(cudaGetLastError());
@@ -635,8 +645,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
-  ctx->launches = ctx->launches_extra ? 2 + ctx->launches_extra : 3;
-  ctx->launches_extra = 0;
+  ctx->launches = 2 + pair_launches;  // pair kernel(s) + hull + LP
   ctx->stepped = true;
   return LQRO_OK;
 }
@@ -644,6 +653,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
 extern "C" int lqro_step_device(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV, void* stream) {
   if (!ctx || !d_vpref || !d_newV) return fail(ctx, LQRO_E_ARG, "bad argument");
   if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  if (!d_nbr && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: pass d_nbr, or step once with a host table / lqro_knn_device first");
   CU(cudaSetDevice(ctx->cfg.device));
   return launch_step(ctx, d_x ? d_x : ctx->d_x, d_vpref, d_nbr ? d_nbr : ctx->d_nbr, d_newV, stream ? (cudaStream_t)stream : ctx->stream);
 }
@@ -651,6 +661,8 @@ extern "C" int lqro_step_device(lqro_ctx* ctx, const double* d_x, const double* 
 extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, const int* nbr, double* newV) {
   if (!ctx || !x || !vpref || !newV) return fail(ctx, LQRO_E_ARG, "bad argument");
   if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  if (!nbr && !ctx->device_knn && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: the first step needs nbr (or LQRO_FLAG_DEVICE_KNN)");
+  if (nbr) ctx->have_nbr = true;
   CU(cudaSetDevice(ctx->cfg.device));
   const LqroParams& p = ctx->prm;
   cudaStream_t st = ctx->stream;
@@ -665,7 +677,10 @@ extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, co
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
+  int queued = 0;
+  CU(cudaMemcpyAsync(&queued, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (queued > ctx->hull_cap) return fail(ctx, LQRO_E_LIMIT, "hull queue overflow: inside pairs beyond max_hull_pairs got no half-plane (status 0x200)");
   return LQRO_OK;
 }
 
@@ -791,7 +806,7 @@ static int launch_sim_update(lqro_ctx* ctx, int n, double* x, double* Rot, doubl
   k_sim_filter<<<grid(n, wc, SIM_FILTER_CTAS), wc * 32, smem_c, st>>>(n, ctx->d_sim_model, x, Rot, P, xTrue, RotTrue, pGoal, normals, sc, vGoal);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_sim[3], st));
-  ctx->launches_extra += 4;
+  ctx->sim_launches += 4;
   return LQRO_OK;
 }
 
@@ -1124,6 +1139,8 @@ extern "C" int lqro_allgather_state(lqro_ctx* ctx);
 extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const double* vpref, const int* nbr, double* newV) {
   if (!ctx || !x_local || !vpref || !newV) return fail(ctx, LQRO_E_ARG, "bad argument");
   if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
+  if (!nbr && !ctx->device_knn && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: the first step needs nbr (or LQRO_FLAG_DEVICE_KNN)");
+  if (nbr) ctx->have_nbr = true;
   CU(cudaSetDevice(ctx->cfg.device));
   const LqroParams& p = ctx->prm;
   cudaStream_t st = ctx->stream;
@@ -1138,7 +1155,10 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
+  int queued = 0;
+  CU(cudaMemcpyAsync(&queued, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (queued > ctx->hull_cap) return fail(ctx, LQRO_E_LIMIT, "hull queue overflow: inside pairs beyond max_hull_pairs got no half-plane (status 0x200)");
   return LQRO_OK;
 }
 
@@ -1175,7 +1195,7 @@ extern "C" int lqro_sim_init(lqro_ctx* ctx, int n, const double* x, const double
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   k_sim_init<<<blocks, wpb * 32, wpb * sizeof(LqroSimWsB), st>>>(n, ctx->d_sim_model, dx, dR, dP, dpg, dn, dxT, dRT, dvG);
   CU(cudaGetLastError());
-  ctx->launches_extra++;
+  ctx->sim_launches++;
   CU(cudaMemcpyAsync(xTrue, dxT, 8 * 16 * N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(RotTrue, dRT, 8 * 9 * N, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(vGoal, dvG, 8 * 3 * N, cudaMemcpyDeviceToHost, st));
@@ -1204,7 +1224,7 @@ extern "C" int lqro_linearize_discretize(lqro_ctx* ctx, int n_batch, const doubl
   if (blocks > ctx->sm_count * SIM_FLOW_CTAS) blocks = ctx->sm_count * SIM_FLOW_CTAS;
   k_sim_linearize<<<blocks, wa * 32, smem, st>>>(n_batch, ctx->d_sim_model, dx, dR, du, dA, dB, dc, ctx->sim_m_diag);
   CU(cudaGetLastError());
-  ctx->launches_extra++;
+  ctx->sim_launches++;
   CU(cudaMemcpyAsync(A, dA, 8 * 256 * nb, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(B, dB, 8 * 64 * nb, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(c, dc, 8 * 16 * nb, cudaMemcpyDeviceToHost, st));
@@ -1228,6 +1248,7 @@ extern "C" int lqro_timestep_device(lqro_ctx* ctx, double* d_Rot, double* d_P, d
     if ((rc = lqro_allgather_state(ctx))) return rc;
   }
   ctx->h_nbr_chunked = nullptr;
+  if (!ctx->device_knn && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: step once with a host table, lqro_knn_device, or LQRO_FLAG_DEVICE_KNN");
   if (ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   if ((rc = launch_step(ctx, ctx->d_x, d_vgoal, ctx->d_nbr, ctx->d_newV, st))) return rc;
   return launch_sim_update(ctx, p.n_local, ctx->d_x + 16 * (size_t)p.local_begin, d_Rot, d_P, d_xTrue, d_RotTrue, ctx->d_newV, d_pGoal, d_normals,

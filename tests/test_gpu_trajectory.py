@@ -65,7 +65,7 @@ def test_six_quads_1000_steps(reference, golden, product_lib):
     assert np.abs(tr[-1, :, :3] - G).max() < 0.5  # and the quads did reach their goals
 
 
-@pytest.mark.parametrize("n,steps", [(4, 400), (8, 400), (16, 300)])
+@pytest.mark.parametrize("n,steps", [(4, 1000), (8, 1000), (16, 1000)])  # BASELINE config 2: 1,000-step equivalence
 def test_reference_scenarios(reference, golden, product_lib, n, steps):
     from lqr_obstacles_b200.swarm import quad24
 

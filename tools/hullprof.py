@@ -1,17 +1,29 @@
-import sys, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+"""Per-phase cycle profile of the hull kernel on the bench swarm (profiling build -DLQRO_HULL_PROF into
+lqr_obstacles_b200/liblqro_hullprof.so; the product build carries no clock reads).  usage: python tools/hullprof.py [--build]"""
+import os, subprocess, sys
+import numpy as np
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, 'tests'))
+prof_so = os.path.join(root, 'lqr_obstacles_b200', 'liblqro_hullprof.so')
+if '--build' in sys.argv or not os.path.exists(prof_so):
+    subprocess.check_call(['nvcc', '-ccbin', '/usr/bin/g++', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
+                           '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-DLQRO_HULL_PROF', '-o', prof_so,
+                           os.path.join(root, 'lqr_obstacles_b200', 'csrc', 'lqro_api.cu')])
+    if '--build' in sys.argv: sys.exit(0)
+os.environ['LQRO_LIB'] = prof_so
 from lqr_obstacles_b200 import Lqro, swarm
-g=np.load('/root/repo/tests/golden/ref_vectors.npz')
-x,vp=swarm.lattice_swarm((64,32,32)); nb=swarm.knn(x[:,:3],64)
-ctx=Lqro(n_agents=65536,max_neighbors=64,horizon=20); ctx.set_dynamics(g['dyn_A'],g['dyn_B'],g['dyn_L'],g['dyn_E'])
+g = np.load(os.path.join(root, 'tests', 'golden', 'ref_vectors.npz'))
+x, vp = swarm.lattice_swarm((64, 32, 32)); nb = swarm.knn(x[:, :3], 64)
+ctx = Lqro(n_agents=65536, max_neighbors=64, horizon=20); ctx.set_dynamics(g['dyn_A'], g['dyn_B'], g['dyn_L'], g['dyn_E'])
 for r in range(3):
-    ctx.step(x,vp,nb if r==0 else None)
-print(ctx.last_step_ms(), ctx.counters())
-c=ctx.hull_cycles()
-names=['init','partall','next+horizon+cone','planes+match','list','walk','redo','append','delete','append-old','insertions','repartitioned','maxcycles','maxpts','maxfacets']
-tot=c[:10].sum()
-for n,v in zip(names,c): print('%-20s %12d %5.1f%%'%(n,v,100*v/tot if tot else 0))
-res=ctx.pair_results(); st=res['status']&0xff
-nr=res['nreach'][st==2]; nf=res['nfacets'][st==2]
-print('inside hull sizes: n mean %.0f max %d; facets mean %.0f max %d'%(nr.mean(),nr.max(),nf.mean(),nf.max()))
-print('cycles per insertion', tot/max(1,c[10]), 'per repartitioned point', (c[4]+c[5]+c[6]+c[7])/max(1,c[11]))
+    ctx.step(x, vp, nb if r == 0 else None)
+print('kernel ms (pairs, hull, lp, total)', ctx.last_step_ms(), 'counters', ctx.counters())
+c = ctx.hull_cycles()
+names = ['init', 'partitionall', 'next+horizon', 'cone', 'planes+match', 'gather', 'walk', 'exhaustive+horizon test', 'append', 'ring+delete',
+         'insertions', 'repartitioned', 'maxcycles', 'maxpts', 'maxfacets']
+tot = c[:10].sum()
+for n, v in zip(names, c): print('%-24s %12d %5.1f%%' % (n, v, 100 * v / tot if tot else 0))
+res = ctx.pair_results(); st = res['status'] & 0xff
+nr = res['nreach'][st == 2]; nf = res['nfacets'][st == 2]
+print('inside hull sizes: n mean %.0f max %d; facets mean %.0f max %d' % (nr.mean(), nr.max(), nf.mean(), nf.max()))
+print('cycles per insertion', tot / max(1, c[10]), 'points re-partitioned per insertion', c[11] / max(1, c[10]))
