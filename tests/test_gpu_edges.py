@@ -53,8 +53,8 @@ def test_k1_and_two_agents(golden, oracle, product_lib):
 
 
 def test_hull_queue_overflow_is_flagged(golden, product_lib):
-    """max_hull_pairs smaller than the number of inside pairs: the extra pairs carry LQRO_PAIR_DROPPED and no plane,
-    the counter reports them, the others are unchanged"""
+    """max_hull_pairs smaller than the number of inside pairs: lqro_step returns LQRO_E_LIMIT, the extra pairs carry
+    LQRO_PAIR_DROPPED and no plane, the counter reports them, the others are unchanged"""
     x, vp = _tight_swarm()
     N, K = len(x), 16
     nbr = swarm.knn(x[:, :3], K)
@@ -64,7 +64,9 @@ def test_hull_queue_overflow_is_flagged(golden, product_lib):
     full.close()
     assert c0["inside"] >= 3 and c0["hull_overflow"] == 0
     small = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20, max_hull_pairs=2)
-    small.step(x, vp, nbr)
+    with pytest.raises(LqroError, match="hull queue overflow"):   # the host-synchronous step reports it (LQRO_E_LIMIT) ...
+        small.step(x, vp, nbr)
+    # ... after finishing the step: results and counters are those of the step with the dropped pairs
     r1, c1 = small.pair_results(), small.counters()
     small.close()
     assert c1["hull_overflow"] == c0["inside"] - 2
