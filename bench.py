@@ -51,9 +51,29 @@ def b_alg(K):
     return 160.0 + 176.0 / K
 
 
-def load_dynamics():
+def reference_dynamics():
+    """A, B, L, E as the reference's own controlMatrices computed them (golden vectors generated from oracle/_ref): the
+    dynamics of the --impl reference arm, and the yardstick the device-computed gains are compared with."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
     return g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"]
+
+
+def device_dynamics(ctx):
+    """controlMatrices (MAIN:490-544) on the device: lqro_linearize_discretize at the hover point + lqro_solve_gains.
+    Returns A, B, L, E, Lh, Eh and the largest relative deviation of L, E from the reference's."""
+    from lqr_obstacles_b200.api import sim_default_model
+
+    m = sim_default_model()
+    ctx.sim_set_model(m)
+    u0 = float(m.u_goal[0])
+    xs = np.zeros(16)
+    xs[12:] = u0
+    A, B, c = ctx.linearize_discretize(xs, np.eye(3), np.full(4, u0))
+    L, E, Lh, Eh = ctx.solve_gains(A, B)
+    rA, rB, rL, rE = reference_dynamics()
+    dev = max(float(np.abs(L[0] - rL).max() / np.abs(rL).max()), float(np.abs(E[0] - rE).max() / np.abs(rE).max()),
+              float(np.abs(A[0] - rA).max() / np.abs(rA).max()), float(np.abs(B[0] - rB).max() / np.abs(rB).max()))
+    return A[0], B[0], L[0], E[0], Lh[0], Eh[0], dev
 
 
 def make_workload(name):
@@ -141,19 +161,20 @@ def _ref_chunk(agents):
         st = np.zeros(4)
         nh = ctypes.c_long()
         R.lib.ref_stage_seconds(st.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nh), 1)
-        return int(npairs), newV, st, int(nh.value)
+        cb_s = R.lib.ref_hull_callback_seconds(1) if hasattr(R.lib, "ref_hull_callback_seconds") else float("nan")
+        return int(npairs), newV, st, int(nh.value), cb_s
     xs = x  # the port takes the same global state; restrict the neighbour table to the shard
     full = np.full((len(x), rows.shape[1]), -1, dtype=np.int32)
     full[agents] = rows
     newV = R.step(NF, T, sph, xs, vpref, full, nthreads=1)[0][agents]
-    return int((rows >= 0).sum()), newV, np.zeros(4), 0
+    return int((rows >= 0).sum()), newV, np.zeros(4), 0, float("nan")
 
 
 class CpuBaseline:
     """The reference CPU path on the host cores.  Sharded by PROCESS (the reference's GJK scratch and world
     constants are file-static/global); every process loads its own copy of the library."""
 
-    def __init__(self, workload, nproc=None):
+    def __init__(self, workload, nproc=None, dynamics=None):
         import multiprocessing as mp
 
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -162,7 +183,7 @@ class CpuBaseline:
         build_oracle()
         self.kind = "reference" if os.path.exists(REF_SO) else "port"
         self.x, self.vpref, self.nbr, self.w = workload
-        self.A, self.B, self.L, self.E = load_dynamics()
+        self.A, self.B, self.L, self.E = dynamics if dynamics is not None else reference_dynamics()
         O = Oracle()
         self.NF, self.T, _ = O.horizon(self.A, self.B, self.L, self.E, self.w["H"])
         self.sph = O.spheres(self.w["P"])
@@ -182,16 +203,58 @@ class CpuBaseline:
         pairs = sum(r[0] for r in res)
         # CPU seconds (summed over processes) in the reference's own categories, SURVEY 8(d)
         st = np.sum([r[2] for r in res], axis=0)
+        hulls = int(sum(r[3] for r in res))
+        cb_s = float(np.sum([r[4] for r in res]))
         self.stages = {"unit": "cpu-us per pair (summed over processes / pairs)",
                        "obstacle_creation": 1e6 * st[0] / max(pairs, 1), "half_plane_creation": 1e6 * st[1] / max(pairs, 1),
                        "new_velocity": 1e6 * st[2] / max(pairs, 1), "hull_branch_share_of_half_plane": st[3] / max(st[1], 1e-30),
-                       "hulls": int(sum(r[3] for r in res)),
-                       "hull_ms_each": 1e3 * st[3] / max(1, sum(r[3] for r in res)),
-                       "note": "hull = in-process qhull-order quickhull + the reference's text round trip, no process spawn"}
+                       "hulls": hulls,
+                       "hull_ms_each": 1e3 * st[3] / max(1, hulls),
+                       # the reference asks qconvex four times per hull (MAIN:769-770, 814-815); every call parses
+                       # pointList.txt, computes the hull and writes its answer, and convexHullFiles writes / parses the files
+                       "hull_geometry_ms_each": 1e3 * cb_s / max(1, hulls),
+                       "text_roundtrip_ms_each": 1e3 * (st[3] - cb_s) / max(1, hulls),
+                       "note": "hull = in-process qhull-order quickhull behind the reference's own text round trip (4 qconvex requests "
+                               "per hull), no process spawn; text_roundtrip = convexHull time minus the geometry"}
         return pairs, dt, len(agents)
 
     def close(self):
         self.pool.terminate()
+
+
+def measure_spawn_ms(n_hulls=2):
+    """The reference's real hull path: convexHull spawning `qconvex` four times per hull (MAIN:769-770, 814-815), with a
+    scipy/qhull-backed executable on PATH (oracle/qconvex_scipy; qhull 2012.1 ships only as a Windows binary).
+    Returns ms per hull, or None where oracle/_ref is absent."""
+    import shutil
+    import tempfile
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _libs import REF_SO, Reference
+
+    if not os.path.exists(REF_SO):
+        return None
+    d = tempfile.mkdtemp(prefix="lqro_qconvex_")
+    os.symlink(os.path.join(ROOT, "oracle", "qconvex_scipy"), os.path.join(d, "qconvex"))
+    old = os.environ.get("PATH", "")
+    os.environ["PATH"] = d + os.pathsep + os.path.dirname(sys.executable) + os.pathsep + old
+    try:
+        ref = Reference()
+        rng = np.random.default_rng(7)
+        ref.lib.ref_set_system_passthrough(1)
+        t = []
+        for h in range(n_hulls + 1):
+            pts = rng.normal(size=(550, 3)) * [3.0, 2.0, 1.0]   # the size of an inside cloud of the bench swarm
+            t0 = time.perf_counter()
+            ref.convex_hull(rng.normal(size=3) * 0.2, pts)
+            t.append(time.perf_counter() - t0)
+        ref.lib.ref_set_system_passthrough(0)
+        return 1e3 * float(np.mean(t[1:]))   # the first hull's two stale-input requests fail early (no pointList.txt yet)
+    except Exception:
+        return None
+    finally:
+        os.environ["PATH"] = old
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def run_reference(args):
@@ -227,16 +290,15 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def sim_update_arm(ctx, x, L, E, stream, args):
+def sim_update_arm(ctx, x, L, E, Lh, Eh, stream, args):
     """The simulator-form update (k_sim_flow, k_sim_noise, k_sim_filter) over every agent of the swarm: estimates = the swarm's states, identity attitudes, P = 1e-9 I, synthetic
     standard normals (numpy; the kernel's cost does not depend on their values), gains from the golden vectors.  Timed
     with CUDA events around each launch (lqro_sim_last_ms); beside it the reference's own update loop on one host core
     (oracle/_ref, 32 quads) when it is available."""
     import torch
     from lqr_obstacles_b200.api import sim_default_model
-    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
     n = len(x)
-    ctx.sim_set_model(sim_default_model(L=L, E=E, Lh=g["dyn_Lh"], Eh=g["dyn_Eh"]))
+    ctx.sim_set_model(sim_default_model(L=L, E=E, Lh=Lh, Eh=Eh))
     rng = np.random.default_rng(1)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
     eye3, p0 = np.eye(3).ravel(), (1e-9 * np.eye(16)).ravel()
@@ -295,6 +357,91 @@ def sim_update_arm(ctx, x, L, E, stream, args):
     return arm
 
 
+def u64_sum(a):
+    """order-independent exact checksum: wrap-around sum of the raw 64-bit patterns (identical for any partition of the agents)"""
+    return int(np.ascontiguousarray(a).view(np.uint64).sum(dtype=np.uint64))
+
+
+def status_hash(status, first_pair):
+    """wrap-around sum over pairs of (status & 0xff) * odd multiplier of the GLOBAL pair index"""
+    st = (np.ascontiguousarray(status).ravel() & 0xFF).astype(np.uint64)
+    idx = np.arange(first_pair, first_pair + st.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int((st * (idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def oracle_sample_check(ctx, x, vpref, nbr, agents_global, lo, newV_local, res):
+    """UNTIMED checker: the listed agents' whole rows (status, half-planes, new velocity) against the CPU oracle, bit for bit.
+    The oracle is test infrastructure; it is never the thing measured."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _libs import Oracle
+
+    O = Oracle()
+    NF, T, sph = ctx.tables()
+    rows = nbr[agents_global]
+    others = np.unique(rows[rows >= 0])
+    ids = np.concatenate([agents_global, others])
+    remap = {int(g): len(agents_global) + t for t, g in enumerate(others)}
+    for t, g in enumerate(agents_global):
+        remap[int(g)] = t
+    rr = np.array([[remap[int(j)] if j >= 0 else -1 for j in r] for r in rows], dtype=np.int32)
+    full = np.full((len(ids), nbr.shape[1]), -1, dtype=np.int32)
+    full[:len(agents_global)] = rr
+    vs = np.zeros((len(ids), 3))
+    vs[:len(agents_global)] = vpref[agents_global]
+    oV, opl, ost, _ = O.step(NF, T, sph, np.ascontiguousarray(x[ids]), vs, full, nthreads=min(8, len(os.sched_getaffinity(0))))
+    n = len(agents_global)
+    loc = agents_global - lo
+    st = res["status"][loc] & 0xFF
+    has = (ost[:n] & 0xFF) != 0
+    ok = (np.array_equal(st, ost[:n] & 0xFF) and np.array_equal(res["planes"][loc][has], opl[:n][has])
+          and np.array_equal(newV_local[loc], oV[:n]))
+    return bool(ok), int(has.sum()), int(((ost[:n] & 0xFF) == 2).sum())
+
+
+def riccati_arm(ctx, n_batch=4096):
+    """Batched Riccati solve (north_star subsystem 1; controlMatrices MAIN:512-543): n_batch HETEROGENEOUS problems -- A, B from
+    lqro_linearize_discretize about perturbed operating points -- through lqro_solve_gains; kernel time from CUDA events around
+    the launch (lqro_riccati_last_ms), wall time of the host-buffer call beside it, gains of a few problems against the oracle."""
+    from lqr_obstacles_b200.api import sim_default_model
+
+    m = sim_default_model()
+    u0 = float(m.u_goal[0])
+    rng = np.random.default_rng(4096)
+    xs = rng.normal(size=(n_batch, 16)) * 0.05
+    xs[:, 12:] = u0 * (1.0 + 0.05 * rng.normal(size=(n_batch, 4)))
+    Rs = np.tile(np.eye(3).ravel(), (n_batch, 1))
+    us = u0 * (1.0 + 0.05 * rng.normal(size=(n_batch, 4)))
+    A, B, _ = ctx.linearize_discretize(xs, Rs, us)
+    ctx.solve_gains(A[:64], B[:64])  # warm
+    t0 = time.perf_counter()
+    L, E, Lh, Eh = ctx.solve_gains(A, B)
+    wall = (time.perf_counter() - t0) * 1e3
+    k_ms = ctx.riccati_last_ms()
+    one0 = time.perf_counter()
+    ctx.solve_gains(A[:1], B[:1])
+    one_wall = (time.perf_counter() - one0) * 1e3
+    one_ms = ctx.riccati_last_ms()
+    err = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _libs import Oracle
+
+        O = Oracle()
+        err = 0.0
+        for i in rng.choice(n_batch, 6, replace=False):
+            oL, oE, oLh, oEh = O.riccati(A[i], B[i])
+            for got, want in ((L[i], oL), (E[i], oE), (Lh[i], oLh), (Eh[i], oEh)):
+                err = max(err, float(np.abs(got - want).max() / np.abs(want).max()))
+    except Exception:
+        pass
+    return {"problems": n_batch, "kernel_ms": k_ms, "problems_per_s": n_batch / (k_ms * 1e-3), "wall_ms_host_buffers": wall,
+            "batch_of_one": {"kernel_ms": one_ms, "wall_ms": one_wall, "problems_per_s": 1.0 / (one_ms * 1e-3)},
+            "iterations": 300, "finite": bool(np.isfinite(L).all() and np.isfinite(Lh).all()),
+            "max_rel_err_vs_oracle_6_problems": err, "tolerance": 1e-9,
+            "api": "lqro_linearize_discretize + lqro_solve_gains (k_riccati, warp per problem); heterogeneous operating points"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -315,8 +462,9 @@ def run_ours(args):
     assert N % world == 0
     NL = N // world
     lo = rank * NL
-    A, B, L, E = load_dynamics()
     ctx = Lqro(device=local_rank, n_agents=N, local_begin=lo, n_local=NL, max_neighbors=K, horizon=H, n_samples=P)
+    # the dynamics come from the repo's own controlMatrices on the device (not from the golden file)
+    A, B, L, E, Lh, Eh, gains_dev = device_dynamics(ctx)
     ctx.set_dynamics(A, B, L, E)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -338,8 +486,12 @@ def run_ours(args):
     ctx.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def one_step():
+    def one_step(ev_ag=None):
+        if ev_ag:
+            ev_ag[0].record(stream)
         ctx.allgather_state()  # no-op on one GPU
+        if ev_ag:
+            ev_ag[1].record(stream)
         ctx.step_device(None, d_vpref.data_ptr(), d_nbr.data_ptr(), d_newV.data_ptr(), stream.cuda_stream)
 
     def barrier():
@@ -354,7 +506,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mk = lambda: torch.cuda.Event(enable_timing=True)
+    ev = [(mk(), mk()) for _ in range(args.steps)]
+    ev_ag = [(mk(), mk()) for _ in range(args.steps)]
     kern_ms = np.zeros(4)
     barrier()
     with torch.cuda.stream(stream):
@@ -363,16 +517,19 @@ def run_ours(args):
                 dist.barrier()  # line the ranks up before every timed step: host-side skew is not step time
             flush.zero_()  # L2 flush, outside the per-step events
             ev[s][0].record(stream)
-            one_step()
+            one_step(ev_ag[s])
             ev[s][1].record(stream)
             stream.synchronize()
             t = ctx.last_step_ms()
             kern_ms += np.array([t["pairs"], t["hull"], t["lp"], t["total"]])
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    ag_ms = sum(a.elapsed_time(b) for a, b in ev_ag) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     kern_ms /= args.steps
     counters = ctx.counters()
+    res_dev = ctx.pair_results()
+    newV_dev = d_newV.cpu().numpy()
 
     # ---- end-to-end arm: host buffers (pinned), copies inside the timed region
     hx = torch.from_numpy(x_loc).pin_memory()
@@ -392,8 +549,30 @@ def run_ours(args):
     e2e_ms = e2e_ev0.elapsed_time(e2e_ev1)
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    checksum = float(hout.sum())
-    e2e_launches = ctx.counters()["launches"]  # pair kernel per uploaded neighbour block + hull + LP
+    e2e_launches = ctx.counters()["launches"]
+
+    # ---- checksums that do not depend on the number of ranks (wrap-around 64-bit sums, all-reduced) and an UNTIMED
+    # oracle sample of this rank's agents
+    hout_np = hout.numpy()
+    same_arms = bool(np.array_equal(hout_np, newV_dev))
+    sums = torch.tensor([np.int64(np.uint64(u64_sum(hout_np)).astype(np.int64)),
+                         np.int64(np.uint64(status_hash(res_dev["status"], lo * K)).astype(np.int64))], dtype=torch.int64, device="cuda")
+    fsum = torch.tensor([float(hout_np.sum()), float(counters["inside"]), float(counters["planes"]), float(counters["degenerate"]),
+                         float(counters["hull_overflow"])], dtype=torch.float64, device="cuda")
+    rng = np.random.default_rng(1000 + rank)
+    sample = np.sort(lo + rng.choice(NL, size=min(args.parity_agents, NL), replace=False))
+    inside_owner = np.unique(np.argwhere((res_dev["status"] & 0xFF) == 2)[:, 0])[:8] + lo   # a few agents that own a hull plane
+    sample = np.unique(np.concatenate([sample, inside_owner])).astype(np.int64)
+    p_ok, p_planes, p_inside = oracle_sample_check(ctx, x, vpref, nbr, sample, lo, newV_dev, res_dev)
+    pstat = torch.tensor([1 if (p_ok and same_arms) else 0, len(sample), p_planes, p_inside], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fsum, op=dist.ReduceOp.SUM)
+        pmin = pstat[:1].clone()
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(pstat, op=dist.ReduceOp.SUM)
+        pstat[0] = pmin[0]
+    sums, fsum, pstat = sums.cpu().numpy(), fsum.cpu().numpy(), pstat.cpu().numpy()
 
     # ---- the same call with the neighbour table rebuilt on the device every step (LQRO_FLAG_DEVICE_KNN, nbr = NULL):
     # informative; the headline e2e keeps the host-provided lists, like the reference arm
@@ -415,19 +594,20 @@ def run_ours(args):
         knn_arm = {"value": N * K / (k_ms * 1e-3), "unit": UNIT, "ms_per_step": k_ms,
                    "h2d_bytes_per_step": int(x_loc.nbytes + vp_loc.nbytes), "gpu_launches_per_step": 9,
                    "neighbour_table_identical": bool(np.array_equal(ctx2.neighbors(), nbr_loc)),
-                   "checksum": float(hout2.sum()), "api": "lqro_step_sharded(nbr=NULL) with LQRO_FLAG_DEVICE_KNN"}
+                   "newV_identical": bool(np.array_equal(hout2.numpy(), hout_np)), "api": "lqro_step_sharded(nbr=NULL) with LQRO_FLAG_DEVICE_KNN"}
         ctx2.close()
 
     # ---- the second half of the reference's time step (MAIN:1408-1417: LQR feedback, propagate, Kalman filter) for the same
-    # swarm on the device (lqro_sim_update_device): informative, not part of `value`
-    sim_arm = None
+    # swarm on the device (lqro_sim_update_device) and the batched Riccati solve: informative, not part of `value`
+    sim_arm = ric_arm = None
     if world == 1:
-        sim_arm = sim_update_arm(ctx, x, L, E, stream, args)
+        sim_arm = sim_update_arm(ctx, x, L, E, Lh, Eh, stream, args)
+        ric_arm = riccati_arm(ctx)
 
-    t_dev = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, kern_ms[0]], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([dev_ms, e2e_ms, e2e_wall_ms, kern_ms[0], kern_ms[1], kern_ms[2], ag_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, e2e_wall_ms, pair_ms = [float(v) for v in t_dev.cpu()]
+    dev_ms, e2e_ms, e2e_wall_ms, pair_ms, hull_ms, lp_ms, ag_ms = [float(v) for v in t_dev.cpu()]
     total_pairs = N * K
     value = total_pairs * args.steps / (dev_ms * 1e-3)
     e2e_value = total_pairs * args.steps / (max(e2e_ms, e2e_wall_ms) * 1e-3)
@@ -443,42 +623,49 @@ def run_ours(args):
         pairs_per_launch = NL * K
         pair_s = pair_ms * 1e-3
         achieved_tf = pairs_per_launch * f_alg(H, P) / pair_s / 1e12
-        # DRAM traffic and executed-FP64 counts of k_pairs come from the committed ncu capture of this workload
-        # (profiles/rNN_k_pairs_<workload>_ncu.json, written by tools/ from the .ncu-rep); never measured under ncu here
+        # DRAM traffic and executed-FP64 counts of k_pairs come from the committed ncu captures of this workload at this rank
+        # count (profiles/rNN_k_pairs_<workload>[_nG]_ncu.json, written by tools/ from the .ncu-rep); never measured under ncu here
         ncu = None
         import glob
-        caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pairs_%s_ncu.json" % args.workload)))
-        if caps and world == 1:
+        caps = [c for c in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_pairs_%s*_ncu.json" % args.workload)))]
+        for cfile in reversed(caps):
             try:
-                ncu = json.load(open(caps[-1]))
-                ncu["file"] = os.path.relpath(caps[-1], ROOT)
+                cand = json.load(open(cfile))
             except Exception:
-                ncu = None
+                continue
+            if cand.get("pairs_per_launch") == pairs_per_launch:
+                ncu = cand
+                ncu["file"] = os.path.relpath(cfile, ROOT)
+                break
         roofline = {
             "bound": "fp64", "kernel": "k_pairs", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": achieved_tf / fp64_peak,
-            "traffic": (ncu["traffic_bytes"] if ncu and ncu.get("pairs_per_launch") == pairs_per_launch else None),
+            "traffic": (ncu["traffic_bytes"] if ncu else None),
+            "traffic_note": (None if ncu else "no committed ncu capture of k_pairs at %d pairs per launch (captures are taken at 1 GPU)" % pairs_per_launch),
             "algorithmic_bytes_per_launch": pairs_per_launch * b_alg(K),
             "executed": ({"source": ncu["file"], "fp64_flop_per_launch": ncu["executed_fp64_flop"],
                           "fp64_pipe_pct": ncu["fp64_pipe_pct"], "issue_active_pct": ncu["issue_active_pct"],
                           "note": "exact pruning skips horizon steps, so executed flop < algorithmic flop (F_alg counts every step)"}
                          if ncu else None),
             "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_ms,
-            "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak); "
-                           "MEASURED_PEAKS.json has no FP64 figure",
+            "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak; ncu capture of that kernel: "
+                           "profiles/r2_k_peak_fp64_ncu.txt); MEASURED_PEAKS.json has no FP64 figure",
             "hbm": {"achieved": pairs_per_launch * b_alg(K) / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": pairs_per_launch * b_alg(K) / pair_s / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
             "fp32_peak_tflops": fp32_peak,
-            "step_kernels_ms": {"k_pairs": kern_ms[0], "k_hull": kern_ms[1], "k_new_velocity": kern_ms[2], "sum": kern_ms[3]},
         }
         cpu_baseline = None
         if world == 1 and not args.no_cpu:
-            cpu = CpuBaseline((x, vpref, nbr, w))
+            cpu = CpuBaseline((x, vpref, nbr, w), dynamics=(A, B, L, E))
             cpu.run(cpu.cores)  # warm the pool
             p, d, na = cpu.run(args.cpu_agents)
             cpu.close()
             cpu_baseline = {"value": p / d, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "stages": getattr(cpu, "stages", None),
+                            "text_roundtrip_ms": (cpu.stages or {}).get("text_roundtrip_ms_each"),
+                            "spawn_ms": measure_spawn_ms(),
+                            "spawn_note": "ms per hull when convexHull really spawns `qconvex` four times (MAIN:769-770, 814-815; "
+                                          "scipy/qhull-backed executable, oracle/qconvex_scipy); not part of `value`",
                             "sample": "%d randomly chosen agents (x K=%d pairs + LP) of the same swarm, process-sharded, %.1f s" % (na, K, d)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -487,16 +674,29 @@ def run_ours(args):
             "config": {"workload": "%s: %d agents, K=%d, H=%d, P=%d, jittered 4 m lattice, seed 20261018" % (args.workload, N, K, H, P),
                        "parallelism": "agents sharded x%d, ncclAllGather of the 128-B state per step" % world,
                        "l2": "256 MiB buffer written between timed steps (outside the per-step events)",
-                       "pairs_per_step": total_pairs},
+                       "pairs_per_step": total_pairs,
+                       "dynamics": "controlMatrices on the device (lqro_linearize_discretize + lqro_solve_gains); max relative "
+                                   "deviation of A, B, L, E from the reference's: %.2e" % gains_dev},
             "clocks": clocks,
+            "stages_ms": {"allgather": ag_ms, "pairs": pair_ms, "hull": hull_ms, "lp": lp_ms,
+                          "note": "CUDA events on the launching stream, mean over the timed steps, max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (x_loc.nbytes + vp_loc.nbytes + nbr_loc.nbytes)),
                     "d2h_bytes_per_step": int(world * NL * 24), "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps,
-                    "api": "lqro_step_sharded (host pinned buffers; neighbour table uploaded in blocks overlapped with the pair kernel)",
-                    "gpu_launches_per_step": e2e_launches, "checksum": checksum, "device_knn": knn_arm},
-            "gpu_launches": 3 * args.steps,
+                    "api": "lqro_step_sharded (host pinned buffers: state, preferred velocities and neighbour table up, new velocities down, every step)",
+                    "gpu_launches_per_step": e2e_launches, "device_knn": knn_arm},
+            "checksum": {"newV_u64": "%016x" % (int(sums[0]) & 0xFFFFFFFFFFFFFFFF), "status_u64": "%016x" % (int(sums[1]) & 0xFFFFFFFFFFFFFFFF),
+                         "newV_float_sum": float(fsum[0]), "inside_pairs": int(fsum[1]), "planes": int(fsum[2]),
+                         "degenerate": int(fsum[3]), "hull_overflow": int(fsum[4]),
+                         "note": "wrap-around 64-bit sums over every rank's new velocities / pair statuses: identical for 1, 2, 4, 8 GPUs"},
+            "parity_sample_ok": bool(pstat[0] == 1),
+            "parity_sample": {"agents": int(pstat[1]), "planes_compared": int(pstat[2]), "inside_pairs_compared": int(pstat[3]),
+                              "what": "untimed: whole rows (status, half-planes, newV) of random agents of every rank + agents owning a "
+                                      "hull plane vs the CPU oracle, bit for bit; device-resident and host-buffer arms equal"},
+            "gpu_launches": counters["launches"] * args.steps,  # per step: k_pairs x 2 slices, k_hull early + wide, k_new_velocity (the all-gather kernel is NCCL's)
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "counters": counters,
+            "riccati": ric_arm,
             "sim_update": sim_arm,
         }
         print(json.dumps(line))
@@ -515,6 +715,7 @@ def main():
     ap.add_argument("--cpu-agents", type=int, default=32768, help="agents in the cpu_baseline sample (~10-30 s of CPU work)")
     ap.add_argument("--ref-agents", type=int, default=8192, help="agents per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--parity-agents", type=int, default=96, help="agents per rank in the untimed oracle sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -78,6 +78,11 @@ typedef struct lqro_config {
 #define LQRO_FLAG_FUSED_HULL 2 /* one hull warp per pair-kernel CTA consumes the inside-case queue concurrently
                                   (experimental: measured slower than the stand-alone hull kernel) */
 
+#define LQRO_FLAG_NO_OVERLAP 8 /* steps of large swarms (>= 2^17 pairs) run the pair kernel in two slices and hull the queue of the
+                                  first one next to the second; this flag (or LQRO_HULL_OVERLAP_SMS=0 in the environment) keeps one
+                                  pair launch followed by the hulls.  Host-buffer steps then upload the neighbour table in blocks
+                                  overlapped with per-block pair launches. */
+
 /* Fills the reference's compile-time constants (MAIN:30-36, 1102, 1367). */
 void lqro_default_config(lqro_config* cfg);
 
@@ -94,6 +99,8 @@ const char* lqro_version(void);
  * by `iters` fixed-point iterations on the device (warp per problem).  Host pointers. */
 int lqro_solve_gains(lqro_ctx* ctx, int n_batch, const double* A, const double* B, double qv, double qp, double r,
                      int iters, double* L, double* E, double* Lh, double* Eh);
+/* Device time (CUDA events around the launch) of the Riccati kernel of the last lqro_solve_gains, in milliseconds. */
+int lqro_riccati_last_ms(lqro_ctx* ctx, float* ms);
 
 /* Replaces findFG (MAIN:653-662) x H and the pair-independent half of createObstacle (MAIN:684-685):
  * builds on the device, in the reference's operation order, NF_k = -(C F_k) and T_k = (C G_k)^-1 for

@@ -14,6 +14,7 @@ PAIR_NONE, PAIR_OUTSIDE, PAIR_INSIDE, PAIR_DEGENERATE, PAIR_DROPPED = 0, 1, 2, 0
 FLAG_NO_PRUNE = 1
 FLAG_FUSED_HULL = 2
 FLAG_DEVICE_KNN = 4
+FLAG_NO_OVERLAP = 8
 
 
 class LqroError(RuntimeError):
@@ -38,7 +39,7 @@ EXPORTS = [
     "lqro_get_counters", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
-    "lqro_debug_hull_cycles", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
+    "lqro_debug_hull_cycles", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
     "lqro_sim_last_ms", "lqro_debug_sim_cycles", "lqro_timestep_device",
@@ -143,6 +144,7 @@ def load_library(path=None):
     lib.lqro_timestep_device.argtypes = [c_void_p] * 9
     lib.lqro_linearize_discretize.argtypes = [c_void_p, c_int] + [c_void_p] * 6
     lib.lqro_sim_init.argtypes = [c_void_p, c_int] + [c_void_p] * 8
+    lib.lqro_riccati_last_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_knn.argtypes = [c_void_p] * 3
     lib.lqro_knn_device.argtypes = [c_void_p] * 4   # the stream is a 64-bit handle: never let ctypes marshal it as a C int
     lib.lqro_get_neighbors.argtypes = [c_void_p] * 2
@@ -211,6 +213,11 @@ class Lqro:
         L, E, Lh, Eh = np.zeros((nb, 4, 16)), np.zeros((nb, 4, 3)), np.zeros((nb, 3, 16)), np.zeros((nb, 3, 3))
         self._ck(self.lib.lqro_solve_gains(self.h, nb, _p(A), _p(B), qv, qp, r, iters, _p(L), _p(E), _p(Lh), _p(Eh)))
         return L, E, Lh, Eh
+
+    def riccati_last_ms(self):
+        t = np.zeros(1, dtype=np.float32)
+        self._ck(self.lib.lqro_riccati_last_ms(self.h, _p(t)))
+        return float(t[0])
 
     def set_dynamics(self, A, B, L, E):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)

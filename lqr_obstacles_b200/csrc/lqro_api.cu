@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -103,6 +104,8 @@ struct lqro_ctx {
   // launch geometry
   int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
   int hull_wpb = 2, hull_blocks = 0; size_t hull_smem = 0;
+  // two-slice step of large swarms: SMs left to the early hull launch, its stream and the events that order it
+  int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr;
   // stage scratch (grown on demand)
   char* d_scratch = nullptr; size_t scratch_bytes = 0;
   char* d_stage_ws = nullptr; int stage_ws_pts = 0;
@@ -112,6 +115,7 @@ struct lqro_ctx {
   LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false, sim_attr_set = false; int sim_m_diag = 0;
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
   cudaEvent_t ev_sim[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ric[2] = {nullptr, nullptr};  // around the last k_riccati launch
   char* d_sim_scratch = nullptr; size_t sim_scratch_bytes = 0;
   long long launches = 0;      // kernel launches of the last avoidance step (launch_step)
   long long sim_launches = 0;  // kernel launches of the simulator-form entry points, cumulative
@@ -184,7 +188,11 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   }
   { void* q[] = {ctx->d_sim_model, ctx->d_sim_buf, ctx->d_sim_scratch}; for (void* p : q) if (p) cudaFree(p); }
   for (cudaEvent_t e : ctx->ev_sim) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_ric) if (e) cudaEventDestroy(e);
   { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr, ctx->d_identity, ctx->d_chunk_ctr}; for (void* p : q) if (p) cudaFree(p); }
+  if (ctx->hull_stream) cudaStreamDestroy(ctx->hull_stream);
+  if (ctx->ev_slice) cudaEventDestroy(ctx->ev_slice);
+  if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
@@ -321,6 +329,12 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     if (slots < ctx->sm_count) slots = ctx->sm_count;
     ctx->hull_slots = slots;
     ctx->hull_blocks = slots;
+    // SMs the second slice of the pair kernel leaves to the early hull launch (two hull blocks per SM); LQRO_HULL_OVERLAP_SMS=0
+    // or LQRO_FLAG_NO_OVERLAP: one pair launch, hulls afterwards
+    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 12;
+    if (const char* e = getenv("LQRO_HULL_OVERLAP_SMS")) ctx->overlap_sms = atoi(e);
+    if (ctx->overlap_sms < 0) ctx->overlap_sms = 0;
+    if (ctx->overlap_sms > ctx->sm_count / 2) ctx->overlap_sms = ctx->sm_count / 2;
     ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
     CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * (size_t)slots));
   }
@@ -344,13 +358,25 @@ extern "C" int lqro_solve_gains(lqro_ctx* ctx, int nb, const double* A, const do
   CU(cudaMemcpyAsync(dB, B, sizeof(double) * 64 * nb, cudaMemcpyHostToDevice, ctx->stream));
   const int wpb = 4;
   const size_t smem = (size_t)wpb * ((sizeof(RiccatiWs) + 7) / 8) * 8;
+  for (cudaEvent_t& e : ctx->ev_ric) if (!e) CU(cudaEventCreate(&e));
+  CU(cudaEventRecord(ctx->ev_ric[0], ctx->stream));
   k_riccati<<<(nb + wpb - 1) / wpb, wpb * 32, smem, ctx->stream>>>(nb, dA, dB, qv, qp, r, iters, dL, dE, dLh, dEh);
   CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_ric[1], ctx->stream));
   CU(cudaMemcpyAsync(L, dL, sizeof(double) * 64 * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(E, dE, sizeof(double) * 12 * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(Lh, dLh, sizeof(double) * 48 * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(Eh, dEh, sizeof(double) * 9 * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_riccati_last_ms(lqro_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return LQRO_E_ARG;
+  if (!ctx->ev_ric[0]) return fail(ctx, LQRO_E_STATE, "no lqro_solve_gains yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaEventSynchronize(ctx->ev_ric[1]));
+  CU(cudaEventElapsedTime(ms, ctx->ev_ric[0], ctx->ev_ric[1]));
   return LQRO_OK;
 }
 
@@ -549,15 +575,17 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   const LqroParams& p = ctx->prm;
   PairOutputs po{ctx->d_planes, ctx->d_status, ctx->d_nreach, ctx->d_dist, ctx->d_nfacets};
   HullQueue hq{ctx->d_hull_items, ctx->d_ctr + 1, ctx->hull_cap};
-  CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 8, st));
+  CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(int) * 16, st));
   CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 32, st));
   if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
-  StepSync sy{ctx->d_ctr + 0, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
-  int pair_launches = 0;
+  // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
+  //        [6] batch counter of the second slice [7] queue length when the first slice had finished
+  StepSync sy{ctx->d_ctr + 0, 0, -1, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_early = 0;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
-  k_pairs<F, HT, PT><<<ctx->pair_blocks, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,         \
-                                                                            ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
+  k_pairs<F, HT, PT><<<pair_grid, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,                \
+                                                                     ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
 #define LQRO_LAUNCH_PAIRS_ANY(PP, TB, ORD)                                                                                     \
   do {                                                                                                                         \
     if (ctx->fused_hull && !(ORD)) LQRO_LAUNCH_PAIRS(true, 0, 0, ctx->pair_warps + 1, PP, TB, ORD);                             \
@@ -565,6 +593,9 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
     else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
   } while (0)
+#define LQRO_LAUNCH_HULL(GRID, STREAM, LIMIT)                                                                                   \
+  k_hull<<<GRID, 32, ctx->hull_smem, STREAM>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, LIMIT, ctx->d_hull_ws, ctx->hull_ws_stride, \
+                                               ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs)
   cudaStream_t pst = st;  // stream of the pair-kernel launches
   double* ovf_base = ctx->d_pair_ovf;  // overflow clouds of the launch (one region per concurrent launch)
   if (ctx->h_nbr_chunked) {
@@ -611,6 +642,31 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     }
     pst = st;
     ovf_base = ctx->d_pair_ovf;
+  } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && p.K > LQRO_FIRST_SLOTS && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
+    // LARGE SWARM, TWO SLICES.  Slice 1 = the LQRO_FIRST_SLOTS nearest neighbour slots of every agent (where the inside pairs are).
+    // When it has finished, the queue length is recorded and an EARLY hull launch on its own stream works on those entries on
+    // the overlap_sms SMs that slice 2 (all the other slots, the bulk of the pairs) leaves free; one hull is a ~1 ms sequential
+    // job (qhull's insertion order), which this takes off the critical path of the step.  No kernel waits for another one:
+    // the early launch only takes tickets below the recorded length, the wide launch after slice 2 takes whatever is left.
+    if (!ctx->hull_stream) {
+      CU(cudaStreamCreateWithFlags(&ctx->hull_stream, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&ctx->ev_slice, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ev_early, cudaEventDisableTiming));
+    }
+    const int first = (int)(slot_major_first(p.n_local, p.K) / 32);
+    sy.batch_begin = 0; sy.batch_end = first;
+    LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+    CU(cudaMemcpyAsync(ctx->d_ctr + 7, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CU(cudaEventRecord(ctx->ev_slice, st));
+    CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_slice, 0));
+    LQRO_LAUNCH_HULL(2 * ctx->overlap_sms, ctx->hull_stream, ctx->d_ctr + 7);
+    CU(cudaEventRecord(ctx->ev_early, ctx->hull_stream));
+    sy.batch_counter = ctx->d_ctr + 6; sy.batch_begin = first; sy.batch_end = -1;
+    pair_grid = ctx->pair_blocks - ctx->overlap_sms;
+    LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+    pair_grid = ctx->pair_blocks;
+    pair_launches += 2;
+    hull_early = 1;
   } else if (!ctx->hetero) {
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     ++pair_launches;
@@ -631,8 +687,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
-  k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, ctx->d_hull_ws, ctx->hull_ws_stride,
-                                                      ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
+  if (hull_early) CU(cudaStreamWaitEvent(st, ctx->ev_early, 0));
+  LQRO_LAUNCH_HULL(ctx->hull_blocks, st, (const int*)nullptr);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
@@ -645,7 +701,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
-  ctx->launches = 2 + pair_launches;  // pair kernel(s) + hull + LP
+  ctx->launches = 2 + pair_launches + hull_early;  // pair kernel(s) + hull launch(es) + LP
   ctx->stepped = true;
   return LQRO_OK;
 }
@@ -669,7 +725,7 @@ extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, co
   CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
   // large swarms: the neighbour table goes up in blocks, overlapped with the pair kernel (see launch_step)
-  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
+  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && ctx->overlap_sms == 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
   if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
   ctx->h_nbr_chunked = chunked ? nbr : nullptr;
   int rc = LQRO_OK;
@@ -1146,7 +1202,7 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(ctx->d_x + 16 * (size_t)p.local_begin, x_local, sizeof(double) * 16 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
+  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && ctx->overlap_sms == 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
   if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
   ctx->h_nbr_chunked = chunked ? nbr : nullptr;
   int rc = lqro_allgather_state(ctx);

@@ -117,17 +117,19 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
   hull_finish_pair(w, ctl, pw, out, pair, n, counters, prof);
 }
 
-// Stand-alone hull kernel: drains whatever the hull warps of k_pairs left in the queue (tickets continue on the
-// same counter).  One warp (= one block) per queued pair at a time.
+// Hull kernel: one warp (= one block) per queued inside pair at a time, tickets from a shared counter.  Launched twice per
+// step of a large swarm: EARLY, on its own stream and on a few SMs, next to the second slice of the pair kernel -- it may take
+// the tickets below *limit only, the queue length recorded when the first slice had finished (every entry below it is complete;
+// nothing here waits for a producer) -- and WIDE after the pair kernel, for whatever is left (limit == NULL: the final length).
 __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
-                                             PairOutputs out, HullQueue hq, int* __restrict__ work_counter, char* __restrict__ ws_base,
-                                             size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
+                                             PairOutputs out, HullQueue hq, int* __restrict__ work_counter, const int* __restrict__ limit,
+                                             char* __restrict__ ws_base, size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
                                              const int* __restrict__ agent_class /* NULL: one class */, const LqroTables* __restrict__ class_tables) {
   extern __shared__ double smem[];
   const int lane = lane_id();
-  int nq = *hq.count;
+  int nq = limit ? *limit : *hq.count;
   if (nq > hq.capacity) nq = hq.capacity;
-  if (*work_counter + (int)blockIdx.x >= nq) return;  // nothing can be left for this block
+  if (*(volatile int*)work_counter + (int)blockIdx.x >= nq) return;  // nothing can be left for this block
   PairTables pt;
   load_block_tables(smem, tb, p.H, p.P);
   {
@@ -141,7 +143,10 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
   int loaded = agent_class ? -1 : 0;
   while (true) {
     int item = 0;
-    if (lane == 0) item = atomicAdd(work_counter, 1);
+    if (lane == 0) {
+      item = atomicAdd(work_counter, 1);
+      if (item >= nq) atomicSub(work_counter, 1);  // hand the ticket back: a later launch continues from the true head
+    }
     item = __shfl_sync(LQRO_FULL, item, 0);
     if (item >= nq) break;
     const int pair = hq.items[item];

@@ -19,7 +19,8 @@
 // re-partition (90 % of the insertions: <= 5 / 7 / 33): there is no 128-wide work to spread over a CTA, the cost of
 // an insertion is the LENGTH OF ITS DEPENDENT CHAIN.  So everything that defines the order is kept warp-uniform in
 // registers (pool / free-list / vertex / sequence counters, the pending-facet ring), duplicates in the horizon search
-// and the ridge matching are resolved with match.any instead of shared-memory atomics, the facet list is not a
+// and the ridge matching are resolved with ballots and short shuffle sweeps instead of shared-memory atomics (match.any
+// measured ~350 cycles per use on sm_100a and was replaced), the facet list is not a
 // linked list any more (a creation sequence number per facet gives qhull's list order; a ring of pending facet ids
 // gives qh_nextfurthest in one parallel probe), appends replay qh_partitionpoint's "furthest stays last" rule per
 // target facet with the bucket leader's state in registers, and visible / new marks are insertion stamps that never
@@ -592,7 +593,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
       // qh_findhorizon as a wave-parallel breadth-first search.  qhull scans the visible list in order and, per
       // facet, its neighbours k = 0,1,2; a neighbour is tested once (first occurrence) and appended to the list if
       // visible.  Processing the (facet, k) slots of one wave in index order, with duplicates inside a 32-slot
-      // chunk resolved to the lowest lane (match.any), yields the same list.
+      // chunk resolved to the lowest lane, yields the same list.
       int wave = 0;
       while (wave < nvis) {
         const int wend = nvis;
@@ -606,16 +607,27 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
             const int cand = w.tp[vf].nb[idx % 3];
             if ((w.tp[cand].vst >> 1) != ins) { fresh = true; nb = cand; }
           }
-          const unsigned peers = __match_any_sync(LQRO_FULL, nb);
+          // every fresh slot tests its candidate (a facet reached by several slots of the chunk is tested by each of them: same
+          // result, same stamp); only a VISIBLE facet must enter the list once, through its lowest slot
           bool isvis = false;
-          if (fresh && (__ffs(peers) - 1) == lane) {
+          if (fresh) {
             const double d = hdist(w.pl[nb], ax, ay, az);
             if (d > MINvisible) isvis = true;
             else if (d > -MAXcoplanar) degen = 1;  // coplanar horizon: qhull would merge
+          }
+          unsigned m = __ballot_sync(LQRO_FULL, isvis);  // every lane has read the stamps before any lane writes one
+          if (fresh) {
             w.tp[nb].vst = isvis ? vvis : vtest;
             if (isvis) w.aux[nb] = -1;
           }
-          const unsigned m = __ballot_sync(LQRO_FULL, isvis);
+          if (m & (m - 1)) {  // two or more visible candidates: drop the later slots of a repeated facet
+            for (unsigned rest = m; rest; rest &= rest - 1) {
+              const int j = __ffs(rest) - 1;
+              const int v = __shfl_sync(LQRO_FULL, nb, j);
+              if (lane > j && v == nb) isvis = false;
+            }
+            m = __ballot_sync(LQRO_FULL, isvis);
+          }
           if (isvis) w.vis[nvis + __popc(m & lt)] = (hidx)nb;
           nvis += __popc(m);
           __syncwarp();
@@ -705,11 +717,15 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         if (__any_sync(LQRO_FULL, q < nnew && sg != q0s)) sharp = true;
         if (nnew <= LQRO_HULL_PAIRMATCH_MAX) {
           // two lanes per cone facet: lane 2r + (s - 1) holds ridge vertex v[s] of facet r; the other lane with the
-          // same vertex is the facet across that ridge = the neighbour opposite the OTHER ridge vertex
+          // same vertex (found by a shuffle sweep over the 2 nnew lanes) is the facet across that ridge = the neighbour opposite the OTHER ridge vertex
           const int r = lane >> 1, s = 1 + (lane & 1);
           const int v1r = __shfl_sync(LQRO_FULL, v1, r), v2r = __shfl_sync(LQRO_FULL, v2, r), fr = __shfl_sync(LQRO_FULL, f, r);
           const int wv = (r < nnew) ? (s == 1 ? v1r : v2r) : (-1 - lane);
-          const unsigned other = __match_any_sync(LQRO_FULL, wv) & ~(1u << lane);
+          unsigned other = 0u;
+          for (int j = 0; j < 2 * nnew; ++j) {
+            const int v = __shfl_sync(LQRO_FULL, wv, j);
+            if (j != lane && v == wv) other |= 1u << j;
+          }
           const int pf = __shfl_sync(LQRO_FULL, fr, other ? __ffs(other) - 1 : lane);
           if (r < nnew) {
             if (__popc(other) != 1) mdeg = 2;
@@ -829,7 +845,12 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         // append: appends to different facets commute, so the first lane of every target facet (bucket leader)
         // replays its bucket in lane (= processing) order with the list state in registers
         const bool has = valid && best >= 0;
-        const unsigned peers = __match_any_sync(LQRO_FULL, has ? best : -1 - lane);
+        unsigned peers = 0u;
+        {
+          const int key = has ? best : -1 - lane;
+          const int cn = nl - c0 < 32 ? nl - c0 : 32;
+          for (int j = 0; j < cn; ++j) peers |= (unsigned)(__shfl_sync(LQRO_FULL, key, j) == key) << j;
+        }
         const bool leader = has && (__ffs(peers) - 1) == lane;
         HOut S; S.fdist = 0; S.ohead = S.olast = S.oprev = -1; S.ocount = 0;
         bool moved = false;

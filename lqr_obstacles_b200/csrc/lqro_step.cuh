@@ -47,19 +47,30 @@ __host__ __device__ inline size_t pair2_warp_doubles(int H) {
 }
 
 struct StepSync {
-  int* batch_counter;   // next batch of pairs
+  int* batch_counter;   // next batch of pairs of this launch (relative to batch_begin)
+  int batch_begin, batch_end;  // batches [begin, end) of the slot-major enumeration belong to this launch (end < 0: to the last one)
   int* hull_head;       // next hull ticket
   int* done_warps;      // pair warps that have finished
   int* counters;        // misc counters (degenerate, fallback, ...)
   long long* prof;
 };
 
-// slot-major enumeration: chunk c covers neighbour slots [32c, min(K, 32c+32)); within a chunk pairs are
-// agent-major.  idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end.
+// slot-major enumeration: the first chunk covers the LQRO_FIRST_SLOTS nearest neighbour slots of every agent, the following
+// ones 32 slots each; within a chunk pairs are agent-major.  Neighbour lists are sorted by distance, so the inside pairs -- the
+// ones that need a hull -- sit in the first chunk: the step launches it as its own slice of the pair kernel and starts hulling
+// its queue while the rest of the pairs are still being processed (launch_step).
+// idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end (chunks start on a batch boundary).
+#ifndef LQRO_FIRST_SLOTS
+#define LQRO_FIRST_SLOTS 8
+#endif
+__host__ __device__ inline int slot_chunk_width(int K, int c0) {
+  const int w = (c0 == 0) ? LQRO_FIRST_SLOTS : 32;
+  return (K - c0 < w) ? (K - c0) : w;
+}
 __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long idx, int& il, int& kk) {
   int c0 = 0;
   while (c0 < p.K) {
-    const int wdt = (p.K - c0 < 32) ? (p.K - c0) : 32;
+    const int wdt = slot_chunk_width(p.K, c0);
     const long long cnt = (long long)p.n_local * wdt;
     const long long padded = (cnt + 31) & ~31ll;  // chunks start on a batch boundary
     if (idx < padded) {
@@ -69,17 +80,18 @@ __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long i
       return true;
     }
     idx -= padded;
-    c0 += 32;
+    c0 += wdt;
   }
   return false;
 }
 __host__ __device__ inline long long slot_major_total(int n_local, int K) {
   long long t = 0;
-  for (int c0 = 0; c0 < K; c0 += 32) {
-    const int wdt = (K - c0 < 32) ? (K - c0) : 32;
-    t += (((long long)n_local * wdt) + 31) & ~31ll;
-  }
+  for (int c0 = 0; c0 < K; c0 += slot_chunk_width(K, c0)) t += (((long long)n_local * slot_chunk_width(K, c0)) + 31) & ~31ll;
   return t;
+}
+// pairs (padded to batches) of the first chunk
+__host__ __device__ inline long long slot_major_first(int n_local, int K) {
+  return (((long long)n_local * slot_chunk_width(K, 0)) + 31) & ~31ll;
 }
 
 #ifdef LQRO_PAIR_PROF  // per-phase cycle counts of the pair warps (lane 0), profiling builds only
@@ -164,14 +176,15 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
-  const long long total = slot_major_total(p.n_local, p.K);
+  const long long total_all = slot_major_total(p.n_local, p.K);
+  const long long total = (sy.batch_end >= 0 && (long long)sy.batch_end * 32 < total_all) ? (long long)sy.batch_end * 32 : total_all;
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
   while (true) {
     int batch = 0;
     if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
-    batch = __shfl_sync(LQRO_FULL, batch, 0);
+    batch = __shfl_sync(LQRO_FULL, batch, 0) + sy.batch_begin;
     const long long base = (long long)batch * 32;
     if (base >= total) break;
     // ---------------- stage 1: lane = pair

@@ -44,6 +44,8 @@ static std::vector<int> g_last_verts;
 static int g_last_nfacets = -1;
 static int g_last_npoints = 0;
 static int g_hull_calls = 0, g_system_calls = 0;
+static double g_hull_cb_s = 0;  // seconds inside the hull callback (the geometry alone, without the text round trip)
+static inline double hull_now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static int default_hull_cb(int n, const double* pts, int max_facets, double* planes, int* verts) {
   lqro_hull_result r;
@@ -69,6 +71,9 @@ extern "C" int ref_last_hull(int* nfacets, int* npoints, double* planes, int* ve
   }
   return 0;
 }
+// seconds spent in the hull callback since the last reset: convexHull time (ref_stage_seconds()[3]) minus this is the cost of
+// the text round trip of MAIN:762-806 (write pointList.txt, parse it, write and parse Planes.txt / facetVertices.txt), x4 per hull
+extern "C" double ref_hull_callback_seconds(int reset) { const double v = g_hull_cb_s; if (reset) g_hull_cb_s = 0; return v; }
 extern "C" void ref_counters(int* hull_calls, int* system_calls) { *hull_calls = g_hull_calls; *system_calls = g_system_calls; }
 
 // Parses:  qconvex <n|Fv> TO "<out>" < "<in>"   and performs it with the hull callback.
@@ -95,7 +100,9 @@ extern "C" int lqr_ref_system(const char* cmd) {
   std::vector<double> planes(4 * (size_t)maxf);
   std::vector<int> verts(3 * (size_t)maxf);
   lqr_hull_cb cb = g_hull_cb ? g_hull_cb : default_hull_cb;
+  const double tcb = hull_now_s();
   int nf = cb(n, pts.data(), maxf, planes.data(), verts.data());
+  g_hull_cb_s += hull_now_s() - tcb;
   ++g_hull_calls;
   if (nf < 0) return 2;
   g_last_nfacets = nf; g_last_npoints = n;

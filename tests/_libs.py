@@ -213,6 +213,9 @@ class Reference:
         lib.ref_jacobi16.argtypes = [c_void_p] * 3
         lib.ref_f.argtypes = [c_void_p] * 4
         lib.ref_linearize_discretize.argtypes = [c_void_p] * 6
+        if hasattr(lib, "ref_hull_callback_seconds"):
+            lib.ref_hull_callback_seconds.restype = c_double
+            lib.ref_hull_callback_seconds.argtypes = [c_int]
         self._tmp = workdir or tempfile.mkdtemp(prefix="lqro_ref_")
         lib.ref_chdir(self._tmp.encode())
         lib.ref_init()

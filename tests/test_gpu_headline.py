@@ -69,27 +69,38 @@ def test_swarm65536_sample_and_every_hull_against_the_oracle(golden, oracle, pro
     ctx.close()
 
 
-def test_chunked_neighbour_upload_with_overflowing_clouds(golden, product_lib):
-    """>= 2^20 pairs from host buffers: the neighbour table goes up in agent blocks and each block's pair kernel runs on its
-    own stream.  A tight swarm makes reachable clouds larger than the 256-point shared part, so the per-warp overflow
-    areas in HBM are live in every concurrent launch; the result must equal the single-launch step (device-resident table)."""
+def test_every_launch_shape_with_overflowing_clouds(golden, product_lib):
+    """Three ways a step of >= 2^20 pairs is launched must give the same bits on a TIGHT swarm -- reachable clouds larger than
+    the 256-point shared part, so the per-warp overflow areas in HBM are live, and thousands of hulls:
+    (a) default: pair kernel in two slices, early hull launch on its own stream next to the second slice, wide hull launch;
+    (b) LQRO_FLAG_NO_OVERLAP with a host table: the table goes up in agent blocks, one pair launch per block on concurrent streams;
+    (c) LQRO_FLAG_NO_OVERLAP with the resident table: one pair launch, hulls afterwards."""
+    from lqr_obstacles_b200.api import FLAG_NO_OVERLAP
+
     x, vpref = swarm.lattice_swarm((32, 32, 16))
     x[:, :3] *= 0.45
     K = 64
     nbr = swarm.knn(x[:, :3], K)
     N = len(x)
     assert N * K >= 1 << 20
-    ctx = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
-    v_chunked = ctx.step(x, vpref, nbr).copy()          # host table -> chunked upload
+    ctx = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20, flags=FLAG_NO_OVERLAP)
+    v_chunked = ctx.step(x, vpref, nbr).copy()          # (b)
     r_chunked = ctx.pair_results()
     assert ctx.counters()["launches"] > 3
     assert (r_chunked["nreach"] > 256).sum() > 1000     # the overflow areas were in use
-    v_plain = ctx.step(x, vpref, None).copy()           # resident table -> one launch
+    v_plain = ctx.step(x, vpref, None).copy()           # (c)
     r_plain = ctx.pair_results()
     assert ctx.counters()["launches"] == 3
-    assert np.array_equal(v_chunked, v_plain)
-    for k in ("status", "nreach", "nfacets"):
-        assert np.array_equal(r_chunked[k], r_plain[k]), k
-    has = (r_plain["status"] & 0xFF) != 0
-    assert np.array_equal(r_chunked["planes"][has], r_plain["planes"][has])
     ctx.close()
+    ctx = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
+    v_two = ctx.step(x, vpref, nbr).copy()              # (a)
+    r_two = ctx.pair_results()
+    cnt = ctx.counters()
+    assert cnt["launches"] == 5 and cnt["inside"] > 500
+    ctx.close()
+    has = (r_plain["status"] & 0xFF) != 0
+    for v, r in ((v_chunked, r_chunked), (v_two, r_two)):
+        assert np.array_equal(v, v_plain)
+        for k in ("status", "nreach", "nfacets"):
+            assert np.array_equal(r[k], r_plain[k]), k
+        assert np.array_equal(r["planes"][has], r_plain["planes"][has])
