@@ -87,18 +87,21 @@ def make_workload(name):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  nvidia-smi needs a few
+    hundred ms to come up and a timed region of a few steps lasts tens of ms, so it is started before the warm-up and polls every
+    20 ms; begin()/end() bracket the timed region and only the samples inside it (plus the one right before it, taken
+    under the warm-up load) are used."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.t0, self.t1 = gpu_index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -106,20 +109,31 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03]   # a sample printed <= 30 ms after the region was taken inside it
+        before = [r for ts, r in self.rows if ts < t0]
+        rows = inside + before[-1:]                                     # plus the last one of the warm-up (same load)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -129,7 +143,8 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside),
+                "timed_region_ms": (None if self.t1 is None or self.t0 is None else 1e3 * (self.t1 - self.t0))}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -457,6 +472,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # long before the timed region: nvidia-smi takes a few hundred ms to come up
     x, vpref, nbr, w = make_workload(args.workload)
     N, K, H, P = len(x), w["K"], w["H"], w["P"]
     assert N % world == 0
@@ -503,14 +521,13 @@ def run_ours(args):
         for _ in range(args.warmup):
             one_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     mk = lambda: torch.cuda.Event(enable_timing=True)
     ev = [(mk(), mk()) for _ in range(args.steps)]
     ev_ag = [(mk(), mk()) for _ in range(args.steps)]
     kern_ms = np.zeros(4)
+    detail_ms = np.zeros(3)
     barrier()
+    sampler.begin()
     with torch.cuda.stream(stream):
         for s in range(args.steps):
             if world > 1:
@@ -522,11 +539,16 @@ def run_ours(args):
             stream.synchronize()
             t = ctx.last_step_ms()
             kern_ms += np.array([t["pairs"], t["hull"], t["lp"], t["total"]])
+            dt = ctx.last_step_detail_ms()
+            detail_ms += np.array([dt["slice1"], dt["slice2"], dt["early_hull"]])
+            overlap_sms = dt["overlap_sms"]
     barrier()
+    sampler.end()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     ag_ms = sum(a.elapsed_time(b) for a, b in ev_ag) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     kern_ms /= args.steps
+    detail_ms /= args.steps
     counters = ctx.counters()
     res_dev = ctx.pair_results()
     newV_dev = d_newV.cpu().numpy()
@@ -620,9 +642,21 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        pairs_per_launch = NL * K
-        pair_s = pair_ms * 1e-3
+        # the dominant launch: with the two-slice step it is the second slice of k_pairs (all slots but the nearest 8 of every
+        # agent) on the SMs the early hull launch does not use -- its pairs, its duration, the FP64 peak of ITS SMs
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        if overlap_sms > 0 and detail_ms[1] > 0:
+            first_slots = min(8, K)
+            pairs_per_launch = NL * (K - first_slots)
+            pair_s = float(detail_ms[1]) * 1e-3
+            sm_frac = (sm_count - overlap_sms) / sm_count
+        else:
+            pairs_per_launch = NL * K
+            pair_s = pair_ms * 1e-3
+            sm_frac = 1.0
         achieved_tf = pairs_per_launch * f_alg(H, P) / pair_s / 1e12
+        fp64_peak_full = fp64_peak
+        fp64_peak = fp64_peak * sm_frac
         # DRAM traffic and executed-FP64 counts of k_pairs come from the committed ncu captures of this workload at this rank
         # count (profiles/rNN_k_pairs_<workload>[_nG]_ncu.json, written by tools/ from the .ncu-rep); never measured under ncu here
         ncu = None
@@ -647,7 +681,12 @@ def run_ours(args):
                           "fp64_pipe_pct": ncu["fp64_pipe_pct"], "issue_active_pct": ncu["issue_active_pct"],
                           "note": "exact pruning skips horizon steps, so executed flop < algorithmic flop (F_alg counts every step)"}
                          if ncu else None),
-            "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_ms,
+            "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_s * 1e3,
+            "launch": ("second slice of k_pairs (slots 8..K-1 of every owned agent) on %d of %d SMs; peak = measured whole-chip FP64 "
+                       "peak %.2f TFLOP/s x %d/%d" % (sm_count - overlap_sms, sm_count, fp64_peak_full, sm_count - overlap_sms, sm_count)
+                       if sm_frac < 1.0 else "k_pairs, one launch over every pair of the rank"),
+            "slices_ms": {"first": float(detail_ms[0]), "second": float(detail_ms[1]), "early_hull_launch": float(detail_ms[2]),
+                          "sms_left_to_the_early_hull_launch": int(overlap_sms)},
             "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak; ncu capture of that kernel: "
                            "profiles/r2_k_peak_fp64_ncu.txt); MEASURED_PEAKS.json has no FP64 figure",
             "hbm": {"achieved": pairs_per_launch * b_alg(K) / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

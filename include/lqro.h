@@ -115,6 +115,8 @@ int lqro_set_dynamics_class(lqro_ctx* ctx, int cls, const double* A, const doubl
  * The step then runs the pair kernel once per class over the owned agents of that class. */
 int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls);
 
+/* createSpheres (MAIN:665-680): the P samples of the doubled ellipsoid (P*3 doubles), available right after lqro_create. */
+int lqro_get_spheres(lqro_ctx* ctx, double* sph);
 /* Copies the tables back (parity checks): NF H*3*16, T H*3*3, sphere samples P*3 (createSpheres,
  * MAIN:665-680).  Any pointer may be NULL. */
 int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* spheres);
@@ -154,6 +156,15 @@ int lqro_get_counters(lqro_ctx* ctx, long long* out6);
 
 /* ---- per-stage entry points (unit parity; host pointers) -------------------------------------- */
 
+/* findFG (MAIN:653-662), one call with the reference's own meaning: F <- (A + B L) F, G <- (A + B L) G + B E, in place
+ * (A 16x16, B 16x4, L 4x16, E 4x3, F 16x16, G 16x3, row major), every element in the reference's operation order: the
+ * result has the reference's bits.  The step itself never calls this per pair: F_k, G_k are pair independent and tabulated
+ * once by lqro_set_dynamics. */
+int lqro_find_fg(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E, double* F, double* G);
+/* createObstacle (MAIN:683-688), one call for one horizon step with the caller's F, G and position map P (3x16):
+ * Transform = !(P G) (3x3), Translate = -P F (x1 - x2) (3), q[s] = Transform (points[s] + Translate), s < n_points. */
+int lqro_create_obstacle(lqro_ctx* ctx, int n_points, const double* points, const double* F, const double* G, const double* P,
+                         const double* x1, const double* x2, double* Transform, double* Translate, double* q);
 /* createObstacle x H for one pair (MAIN:683-688): q = H*P*3 candidate points, k-major. */
 int lqro_candidates(lqro_ctx* ctx, const double* xi, const double* xj, double* q);
 /* findReachableObstacle (MAIN:691-706): ascending indices of reachable points; returns count in *n_out. */
@@ -279,6 +290,9 @@ int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops);
 /* Device time (ms) of the kernels of the last step: [0] pair kernel, [1] hull kernel, [2] LP kernel,
  * [3] whole step (kernels only, measured with CUDA events on the launching stream). */
 int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
+/* Two-slice steps (large swarms): [0] first slice of the pair kernel (nearest slots, every SM), [1] second slice (on all but
+ * [3] SMs), [2] the early hull launch next to it (its own stream), [3] SMs left to that launch; one-launch steps: [1] only. */
+int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out4);
 /* SM-cycle breakdown of the hull kernel of the last step, summed over hulls (development aid):
  * [0] init+simplex [1] partitionall [2] furthest+horizon+cone [3] planes+match [4] list [5] walk [6] redo
  * [7] append [8] delete [9] - [10] insertions [11] points re-partitioned [12] max cycles of one hull

@@ -49,6 +49,8 @@ inline lqro_ctx*& shim_ctx() {
   static lqro_ctx* ctx = nullptr;
   return ctx;
 }
+inline int& shim_hp() { static int hp = 0; return hp; }        // H*P of the shim context
+inline int& shim_samples() { static int p = 0; return p; }   // P of the shim context
 inline lqro_ctx* ensure_ctx() {
   lqro_ctx*& ctx = shim_ctx();
   if (!ctx) {
@@ -67,12 +69,25 @@ inline lqro_ctx* ensure_ctx() {
     cfg.n_agents = 2;
     cfg.max_neighbors = 1;
     check(lqro_create(&cfg, &ctx), nullptr, "lqro_create");
+    shim_hp() = cfg.horizon * cfg.n_samples;
+    shim_samples() = cfg.n_samples;
   }
   return ctx;
 }
 
-// ---- MAIN:653-662 findFG is folded into lqro_set_dynamics (F_k, G_k for all k at once).
-// Call once after controlMatrices: replaces the H findFG calls the reference makes PER PAIR.
+// ---- MAIN:653-662 findFG(A, B, L, E, F, G): the reference's own argument list and meaning, one device call per call.
+// F <- (A + B L) F, G <- (A + B L) G + B E, in place, in the reference's operation order (same bits).
+template <class M16x16, class M16x4, class M4x16, class M4x3, class M16x3>
+inline void findFG(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E, M16x16& F, M16x3& G) {
+  lqro_ctx* ctx = ensure_ctx();
+  std::vector<double> f = flat(F, 256), g = flat(G, 48);
+  check(lqro_find_fg(ctx, flat(A, 256).data(), flat(B, 64).data(), flat(L, 64).data(), flat(E, 12).data(), f.data(), g.data()), ctx, "lqro_find_fg");
+  for (int i = 0; i < 256; ++i) F[i] = f[i];
+  for (int i = 0; i < 48; ++i) G[i] = g[i];
+}
+
+// The H findFG calls the reference makes PER PAIR (MAIN:1383-1384) compute pair-independent tables: setDynamics builds all of
+// them once on the device (lqro_set_dynamics); lqro::Swarm::step and createObstacleAll use them.
 template <class M16x16, class M16x4, class M4x16, class M4x3>
 inline void setDynamics(const M16x16& A, const M16x4& B, const M4x16& L, const M4x3& E) {
   lqro_ctx* ctx = ensure_ctx();
@@ -121,42 +136,49 @@ inline void controlMatrices(const Input& uGoal, const M16& /*xstar*/, M16x16& A,
   for (int i = 0; i < 9; ++i) Eh[i] = eh[i];
 }
 
-// ---- MAIN:665-680 createSpheres(std::vector<Matrix<3,1>>& points): appends NUM_POINTS samples
+// ---- MAIN:665-680 createSpheres(std::vector<Matrix<3,1>>& points): appends NUM_POINTS samples of the doubled ellipsoid
 template <class V3d>
 inline void createSpheres(std::vector<V3d>& points) {
   lqro_ctx* ctx = ensure_ctx();
-  if (false) check(0, ctx, "");
-  std::vector<double> sph;
-  // the tables need dynamics; spheres alone are available right after create through get_tables' third output
-  lqro_config cfg;
-  lqro_default_config(&cfg);
-#ifdef NUM_POINTS
-  cfg.n_samples = NUM_POINTS;
-#endif
-  sph.resize(3 * (size_t)cfg.n_samples);
-  int rc = lqro_get_tables(ctx, nullptr, nullptr, sph.data());
-  check(rc, ctx, "lqro_get_tables (call setDynamics first)");
-  for (int i = 0; i < cfg.n_samples; ++i) {
+  const int P = shim_samples();
+  std::vector<double> sph(3 * (size_t)P);
+  check(lqro_get_spheres(ctx, sph.data()), ctx, "lqro_get_spheres");
+  for (int i = 0; i < P; ++i) {
     V3d p;
     p[0] = sph[3 * i]; p[1] = sph[3 * i + 1]; p[2] = sph[3 * i + 2];
     points.push_back(p);
   }
 }
 
-// ---- MAIN:683-688 createObstacle for ALL horizon steps of one pair: appends H*P points (k-major), i.e.
-// what the reference's `for k` loop around createObstacle (MAIN:1383-1389) leaves in `ellipsoids`.
+// ---- MAIN:683-688 createObstacle(ellipsoids, points, Transform, Translate, t, F, G, P, xInit1, xInit2, radius): the reference's
+// own argument list (`t` and `radius` are unused there too).  Transform = !(P*G), Translate = -P*F*(xInit1-xInit2), appends
+// Transform*(points[i] + Translate) for every sample.
+template <class V3d, class M3x3, class M16x16, class M16x3, class M3x16, class State>
+inline void createObstacle(std::vector<V3d>& ellipsoids, const std::vector<V3d>& points, M3x3& Transform, V3d& Translate, const size_t& /*t*/,
+                           const M16x16& F, const M16x3& G, const M3x16& P, const State& xInit1, const State& xInit2, const int& /*radius*/) {
+  lqro_ctx* ctx = ensure_ctx();
+  const int n = (int)points.size();
+  std::vector<double> p(3 * (size_t)(n > 0 ? n : 1)), q(3 * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) p[3 * i + k] = points[i][k];
+  double T[9], tr[3];
+  check(lqro_create_obstacle(ctx, n, p.data(), flat(F, 256).data(), flat(G, 48).data(), flat(P, 48).data(), flat(xInit1, 16).data(),
+                             flat(xInit2, 16).data(), T, tr, q.data()), ctx, "lqro_create_obstacle");
+  for (int i = 0; i < 9; ++i) Transform[i] = T[i];
+  for (int i = 0; i < 3; ++i) Translate[i] = tr[i];
+  for (int i = 0; i < n; ++i) {
+    V3d v;
+    v[0] = q[3 * i]; v[1] = q[3 * i + 1]; v[2] = q[3 * i + 2];
+    ellipsoids.push_back(v);
+  }
+}
+
+// createObstacle for ALL horizon steps of one pair from the tables of setDynamics: appends H*P points (k-major), i.e. what the
+// reference's `for k` loop around findFG + createObstacle (MAIN:1383-1389) leaves in `ellipsoids`, in one device call.
+// H and P are the context's (the configuration the shim context was created with), not re-read from macros here.
 template <class V3d, class State>
 inline void createObstacleAll(std::vector<V3d>& ellipsoids, const State& xInit1, const State& xInit2) {
   lqro_ctx* ctx = ensure_ctx();
-  lqro_config cfg;
-  lqro_default_config(&cfg);
-#ifdef OBSTACLE_STEPS
-  cfg.horizon = OBSTACLE_STEPS;
-#endif
-#ifdef NUM_POINTS
-  cfg.n_samples = NUM_POINTS;
-#endif
-  const int n = cfg.horizon * cfg.n_samples;
+  const int n = shim_hp();
   std::vector<double> q(3 * (size_t)n);
   check(lqro_candidates(ctx, flat(xInit1, 16).data(), flat(xInit2, 16).data(), q.data()), ctx, "lqro_candidates");
   for (int i = 0; i < n; ++i) {
@@ -342,6 +364,41 @@ class Swarm {
   bool model_init_ = false;
   std::vector<double> sx_, sxt_, sr_, srt_, sp_, snv_, spg_, snr_, svg_;
 };
+
+// ---- RVO::Agent (AGENT:84-180, RVO2-3D: the file the LP in MAIN was taken from; not in the reference's build).  The two
+// members north_star names, with the reference's signatures: update() (AGENT:176-180: velocity_ = newVelocity_;
+// position_ += velocity_ * timeStep) on the device through lqro_agent_update, and computeNewVelocity() (AGENT:84-151) for the
+// part that is on the hot path here -- the linear programs over orcaPlanes_ (AGENT:147-150 = calculateNewV, MAIN:1101-1112);
+// in this code base the planes come from the LQR-obstacles (createHalfPlanes), not from RVO's velocity obstacles.
+namespace RVO {
+template <class Vec3, class PlaneT>
+class Agent {
+ public:
+  Vec3 position_, velocity_, newVelocity_, prefVelocity_;
+  std::vector<PlaneT> orcaPlanes_;
+  float maxSpeed_ = 100.0f;     // MAIN:1102
+  float timeStep_ = 1.0f / 30;  // sim_->timeStep_
+  void computeNewVelocity() {
+    lqro_ctx* ctx = ensure_ctx();
+    const int n = (int)orcaPlanes_.size();
+    std::vector<float> pl(6 * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) { pl[6 * i + k] = orcaPlanes_[i].point[k]; pl[6 * i + 3 + k] = orcaPlanes_[i].normal[k]; }
+    const double g[3] = {prefVelocity_[0], prefVelocity_[1], prefVelocity_[2]};
+    double v[3];
+    check(lqro_new_velocity(ctx, 1, n > 0 ? n : 1, pl.data(), &n, g, v), ctx, "lqro_new_velocity");
+    newVelocity_ = Vec3(v[0], v[1], v[2]);
+  }
+  void update() {
+    lqro_ctx* ctx = ensure_ctx();
+    float p[3] = {position_[0], position_[1], position_[2]}, v[3] = {velocity_[0], velocity_[1], velocity_[2]};
+    const float nv[3] = {newVelocity_[0], newVelocity_[1], newVelocity_[2]};
+    check(lqro_agent_update(ctx, 1, p, v, nv, timeStep_), ctx, "lqro_agent_update");
+    position_ = Vec3(p[0], p[1], p[2]);
+    velocity_ = Vec3(v[0], v[1], v[2]);
+  }
+};
+}  // namespace RVO
 
 // element-wise copy out of a reference Matrix (operator[] const returns by value, MAT:58-61)
 template <class M>

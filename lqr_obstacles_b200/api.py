@@ -34,11 +34,11 @@ _lib = None
 
 EXPORTS = [
     "lqro_default_config", "lqro_create", "lqro_destroy", "lqro_last_error", "lqro_version", "lqro_solve_gains",
-    "lqro_set_dynamics", "lqro_get_tables", "lqro_step", "lqro_step_device", "lqro_synchronize", "lqro_set_stream",
+    "lqro_set_dynamics", "lqro_get_tables", "lqro_get_spheres", "lqro_step", "lqro_step_device", "lqro_synchronize", "lqro_set_stream",
     "lqro_step_sharded", "lqro_get_pair_results",
-    "lqro_get_counters", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
+    "lqro_get_counters", "lqro_find_fg", "lqro_create_obstacle", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
-    "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms",
+    "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms", "lqro_last_step_detail_ms",
     "lqro_debug_hull_cycles", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
@@ -109,6 +109,7 @@ def load_library(path=None):
     lib.lqro_solve_gains.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_double, c_double, c_double, c_int] + [c_void_p] * 4
     lib.lqro_set_dynamics.argtypes = [c_void_p] * 5
     lib.lqro_get_tables.argtypes = [c_void_p] * 4
+    lib.lqro_get_spheres.argtypes = [c_void_p] * 2
     lib.lqro_step.argtypes = [c_void_p] * 5
     lib.lqro_step_device.argtypes = [c_void_p] * 6
     lib.lqro_synchronize.argtypes = [c_void_p]
@@ -117,6 +118,8 @@ def load_library(path=None):
     lib.lqro_get_pair_results.argtypes = [c_void_p] * 6
     lib.lqro_get_counters.argtypes = [c_void_p, c_void_p]
     lib.lqro_candidates.argtypes = [c_void_p] * 4
+    lib.lqro_find_fg.argtypes = [c_void_p] * 7
+    lib.lqro_create_obstacle.argtypes = [c_void_p, c_int] + [c_void_p] * 9
     lib.lqro_reachable.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lqro_gjk.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.lqro_convex_hull.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -132,6 +135,7 @@ def load_library(path=None):
     lib.lqro_measure_fp64_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_measure_fp32_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
+    lib.lqro_last_step_detail_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_hull_cycles.argtypes = [c_void_p, c_void_p]
     lib.lqro_sim_default_model.argtypes = [ctypes.POINTER(SimModel)]
     lib.lqro_sim_default_model.restype = None
@@ -327,12 +331,32 @@ class Lqro:
         self._ck(self.lib.lqro_last_step_ms(self.h, _p(t)))
         return dict(pairs=float(t[0]), hull=float(t[1]), lp=float(t[2]), total=float(t[3]))
 
+    def last_step_detail_ms(self):
+        t = np.zeros(4, dtype=np.float32)
+        self._ck(self.lib.lqro_last_step_detail_ms(self.h, _p(t)))
+        return dict(slice1=float(t[0]), slice2=float(t[1]), early_hull=float(t[2]), overlap_sms=int(t[3]))
+
     def hull_cycles(self):
         c = np.zeros(16, dtype=np.int64)
         self._ck(self.lib.lqro_debug_hull_cycles(self.h, _p(c)))
         return c
 
     # -- per-stage
+    def findFG(self, A, B, L, E, F, G):
+        """findFG (MAIN:653-662), one call: returns the updated (F, G)"""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        F, G = f(F).copy(), f(G).copy()
+        self._ck(self.lib.lqro_find_fg(self.h, _p(f(A)), _p(f(B)), _p(f(L)), _p(f(E)), _p(F), _p(G)))
+        return F, G
+
+    def createObstacleStep(self, points, F, G, P, x1, x2):
+        """createObstacle (MAIN:683-688), one call: returns (q, Transform, Translate)"""
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        points = f(points)
+        q, T, tr = np.zeros_like(points), np.zeros((3, 3)), np.zeros(3)
+        self._ck(self.lib.lqro_create_obstacle(self.h, len(points), _p(points), _p(f(F)), _p(f(G)), _p(f(P)), _p(f(x1)), _p(f(x2)), _p(T), _p(tr), _p(q)))
+        return q, T, tr
+
     def createObstacle(self, xi, xj):
         q = np.zeros((self.H * self.P, 3))
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)

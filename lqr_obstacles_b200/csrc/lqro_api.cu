@@ -105,7 +105,7 @@ struct lqro_ctx {
   int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
   int hull_wpb = 2, hull_blocks = 0; size_t hull_smem = 0;
   // two-slice step of large swarms: SMs left to the early hull launch, its stream and the events that order it
-  int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr;
+  int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr, ev_early0 = nullptr; bool last_two_slices = false;
   // stage scratch (grown on demand)
   char* d_scratch = nullptr; size_t scratch_bytes = 0;
   char* d_stage_ws = nullptr; int stage_ws_pts = 0;
@@ -193,6 +193,7 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (ctx->hull_stream) cudaStreamDestroy(ctx->hull_stream);
   if (ctx->ev_slice) cudaEventDestroy(ctx->ev_slice);
   if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
+  if (ctx->ev_early0) cudaEventDestroy(ctx->ev_early0);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
@@ -331,7 +332,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     ctx->hull_blocks = slots;
     // SMs the second slice of the pair kernel leaves to the early hull launch (two hull blocks per SM); LQRO_HULL_OVERLAP_SMS=0
     // or LQRO_FLAG_NO_OVERLAP: one pair launch, hulls afterwards
-    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 12;
+    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 16;  // measured at 65,536 x 64: 12 -> 7.96 ms, 16 -> 6.58, 20 -> 6.65 (0: 6.89); at 8,192 x 64: 1.74 -> 1.36
     if (const char* e = getenv("LQRO_HULL_OVERLAP_SMS")) ctx->overlap_sms = atoi(e);
     if (ctx->overlap_sms < 0) ctx->overlap_sms = 0;
     if (ctx->overlap_sms > ctx->sm_count / 2) ctx->overlap_sms = ctx->sm_count / 2;
@@ -498,6 +499,13 @@ extern "C" int lqro_set_agent_classes(lqro_ctx* ctx, const int* cls) {
   return LQRO_OK;
 }
 
+extern "C" int lqro_get_spheres(lqro_ctx* ctx, double* sph) {
+  if (!ctx || !sph) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaMemcpy(sph, ctx->d_sph, sizeof(double) * 3 * ctx->prm.P, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
 extern "C" int lqro_get_tables(lqro_ctx* ctx, double* NF, double* T, double* sph) {
   if (!ctx) return LQRO_E_ARG;
   if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
@@ -593,8 +601,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
     else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
   } while (0)
-#define LQRO_LAUNCH_HULL(GRID, STREAM, LIMIT)                                                                                   \
-  k_hull<<<GRID, 32, ctx->hull_smem, STREAM>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, LIMIT, ctx->d_hull_ws, ctx->hull_ws_stride, \
+#define LQRO_LAUNCH_HULL(GRID, STREAM, LIMIT, DONE, DONE_TOTAL)                                                                  \
+  k_hull<<<GRID, 32, ctx->hull_smem, STREAM>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, LIMIT, DONE, DONE_TOTAL, ctx->d_hull_ws, ctx->hull_ws_stride, \
                                                ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs)
   cudaStream_t pst = st;  // stream of the pair-kernel launches
   double* ovf_base = ctx->d_pair_ovf;  // overflow clouds of the launch (one region per concurrent launch)
@@ -650,8 +658,9 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     // the early launch only takes tickets below the recorded length, the wide launch after slice 2 takes whatever is left.
     if (!ctx->hull_stream) {
       CU(cudaStreamCreateWithFlags(&ctx->hull_stream, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&ctx->ev_slice, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ctx->ev_early, cudaEventDisableTiming));
+      CU(cudaEventCreate(&ctx->ev_slice));
+      CU(cudaEventCreate(&ctx->ev_early));
+      CU(cudaEventCreate(&ctx->ev_early0));
     }
     const int first = (int)(slot_major_first(p.n_local, p.K) / 32);
     sy.batch_begin = 0; sy.batch_end = first;
@@ -659,7 +668,9 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     CU(cudaMemcpyAsync(ctx->d_ctr + 7, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev_slice, st));
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_slice, 0));
-    LQRO_LAUNCH_HULL(2 * ctx->overlap_sms, ctx->hull_stream, ctx->d_ctr + 7);
+    CU(cudaEventRecord(ctx->ev_early0, ctx->hull_stream));
+    LQRO_LAUNCH_HULL(2 * ctx->overlap_sms, ctx->hull_stream, ctx->d_ctr + 7, ctx->d_ctr + 4,
+                     ctx->pair_warps * (2 * ctx->pair_blocks - ctx->overlap_sms));  // pair warps of both slices
     CU(cudaEventRecord(ctx->ev_early, ctx->hull_stream));
     sy.batch_counter = ctx->d_ctr + 6; sy.batch_begin = first; sy.batch_end = -1;
     pair_grid = ctx->pair_blocks - ctx->overlap_sms;
@@ -688,7 +699,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   if (hull_early) CU(cudaStreamWaitEvent(st, ctx->ev_early, 0));
-  LQRO_LAUNCH_HULL(ctx->hull_blocks, st, (const int*)nullptr);
+  LQRO_LAUNCH_HULL(ctx->hull_blocks, st, (const int*)nullptr, (const int*)nullptr, 0);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
@@ -701,6 +712,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
+  ctx->last_two_slices = hull_early != 0;
   ctx->launches = 2 + pair_launches + hull_early;  // pair kernel(s) + hull launch(es) + LP
   ctx->stepped = true;
   return LQRO_OK;
@@ -975,6 +987,19 @@ extern "C" int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16) {
   return LQRO_OK;
 }
 
+extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out4) {
+  if (!ctx || !out4) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaEventSynchronize(ctx->ev[3]));
+  out4[0] = out4[1] = out4[2] = 0.f; out4[3] = (float)ctx->overlap_sms;
+  if (!ctx->last_two_slices) { CU(cudaEventElapsedTime(out4 + 1, ctx->ev[0], ctx->ev[1])); out4[3] = 0.f; return LQRO_OK; }
+  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_slice));
+  CU(cudaEventElapsedTime(out4 + 1, ctx->ev_slice, ctx->ev[1]));
+  CU(cudaEventElapsedTime(out4 + 2, ctx->ev_early0, ctx->ev_early));
+  return LQRO_OK;
+}
+
 extern "C" int lqro_last_step_ms(lqro_ctx* ctx, float* out4) {
   if (!ctx || !out4) return LQRO_E_ARG;
   if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
@@ -1003,6 +1028,53 @@ extern "C" int lqro_candidates(lqro_ctx* ctx, const double* xi, const double* xj
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(q, dq, sizeof(double) * 3 * HP, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_find_fg(lqro_ctx* ctx, const double* A, const double* B, const double* L, const double* E, double* F, double* G) {
+  if (!ctx || !A || !B || !L || !E || !F || !G) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_scratch(ctx, sizeof(double) * (256 + 64 + 64 + 12 + 256 + 48));
+  if (rc) return rc;
+  double* d = (double*)ctx->d_scratch;
+  double *dA = d, *dB = d + 256, *dL = dB + 64, *dE = dL + 64, *dF = dE + 12, *dG = dF + 256;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(dA, A, sizeof(double) * 256, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dB, B, sizeof(double) * 64, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dL, L, sizeof(double) * 64, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dE, E, sizeof(double) * 12, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dF, F, sizeof(double) * 256, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dG, G, sizeof(double) * 48, cudaMemcpyHostToDevice, st));
+  k_stage_findfg<<<1, 256, 0, st>>>(dA, dB, dL, dE, dF, dG);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(F, dF, sizeof(double) * 256, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(G, dG, sizeof(double) * 48, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return LQRO_OK;
+}
+
+extern "C" int lqro_create_obstacle(lqro_ctx* ctx, int n_points, const double* points, const double* F, const double* G, const double* P,
+                                    const double* x1, const double* x2, double* Transform, double* Translate, double* q) {
+  if (!ctx || n_points < 1 || !points || !F || !G || !P || !x1 || !x2 || !Transform || !Translate || !q) return fail(ctx, LQRO_E_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  const size_t n3 = 3 * (size_t)n_points;
+  int rc = ensure_scratch(ctx, sizeof(double) * (2 * n3 + 256 + 48 + 48 + 32 + 12));
+  if (rc) return rc;
+  double* d = (double*)ctx->d_scratch;
+  double *dp = d, *dq = dp + n3, *dF = dq + n3, *dG = dF + 256, *dP = dG + 48, *dx1 = dP + 48, *dx2 = dx1 + 16, *dT = dx2 + 16, *dTr = dT + 9;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(dp, points, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dF, F, sizeof(double) * 256, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dG, G, sizeof(double) * 48, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dP, P, sizeof(double) * 48, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dx1, x1, sizeof(double) * 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dx2, x2, sizeof(double) * 16, cudaMemcpyHostToDevice, st));
+  k_stage_create_obstacle<<<1, 32, 0, st>>>(n_points, dp, dF, dG, dP, dx1, dx2, dT, dTr, dq);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(q, dq, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(Transform, dT, sizeof(double) * 9, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(Translate, dTr, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return LQRO_OK;
 }
 

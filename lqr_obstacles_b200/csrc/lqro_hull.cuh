@@ -120,9 +120,12 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
 // Hull kernel: one warp (= one block) per queued inside pair at a time, tickets from a shared counter.  Launched twice per
 // step of a large swarm: EARLY, on its own stream and on a few SMs, next to the second slice of the pair kernel -- it may take
 // the tickets below *limit only, the queue length recorded when the first slice had finished (every entry below it is complete;
-// nothing here waits for a producer) -- and WIDE after the pair kernel, for whatever is left (limit == NULL: the final length).
+// nothing here waits for a producer; once every pair warp of the step has signed off -- producers_done == producers_total --
+// it stops taking tickets, so that the wide launch takes over at full width instead of a few blocks working through a long queue)
+// -- and WIDE after the pair kernel, for whatever is left (limit == NULL: the final length).
 __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, const int* __restrict__ limit,
+                                             const int* __restrict__ producers_done, int producers_total,
                                              char* __restrict__ ws_base, size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
                                              const int* __restrict__ agent_class /* NULL: one class */, const LqroTables* __restrict__ class_tables) {
   extern __shared__ double smem[];
@@ -144,8 +147,11 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
   while (true) {
     int item = 0;
     if (lane == 0) {
-      item = atomicAdd(work_counter, 1);
-      if (item >= nq) atomicSub(work_counter, 1);  // hand the ticket back: a later launch continues from the true head
+      if (producers_done && *(volatile const int*)producers_done >= producers_total) item = nq;  // pair kernel finished: leave the rest to the wide launch
+      else {
+        item = atomicAdd(work_counter, 1);
+        if (item >= nq) atomicSub(work_counter, 1);  // hand the ticket back: a later launch continues from the true head
+      }
     }
     item = __shfl_sync(LQRO_FULL, item, 0);
     if (item >= nq) break;

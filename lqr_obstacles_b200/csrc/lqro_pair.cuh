@@ -321,6 +321,77 @@ __device__ __forceinline__ void write_plane(float* pl, const double* vi, double 
 // ------------------------------------------------------------------------------------------------
 // Stage kernels behind the per-stage C entry points (one warp, one pair / one cloud).
 
+// findFG (MAIN:653-662), ONE call: Atilde = A + (B*L), Btilde = B*E, F <- Atilde*F, G <- Atilde*G + Btilde, in place, every
+// element the left-to-right sum Matrix::operator* forms (MAT:218-231).  256 threads, thread = element of the 16x16 product.
+__global__ void __launch_bounds__(256) k_stage_findfg(const double* __restrict__ A, const double* __restrict__ B, const double* __restrict__ L,
+                                                      const double* __restrict__ E, double* __restrict__ F, double* __restrict__ G) {
+  __shared__ double sAt[256], sF[256], sG[48];
+  const int t = threadIdx.x, i = t >> 4, j = t & 15;
+  {
+    double bl = 0;
+    for (int k = 0; k < 4; ++k) bl += B[i * 4 + k] * L[k * 16 + j];
+    sAt[t] = A[t] + bl;
+    sF[t] = F[t];
+  }
+  if (t < 48) sG[t] = G[t];
+  __syncthreads();
+  double f = 0;
+  for (int m = 0; m < 16; ++m) f += sAt[i * 16 + m] * sF[m * 16 + j];
+  F[t] = f;
+  if (t < 48) {
+    const int gi = t / 3, gj = t % 3;
+    double be = 0, g = 0;
+    for (int k = 0; k < 4; ++k) be += B[gi * 4 + k] * E[k * 3 + gj];
+    for (int m = 0; m < 16; ++m) g += sAt[gi * 16 + m] * sG[m * 3 + gj];
+    G[t] = g + be;
+  }
+}
+
+// createObstacle (MAIN:683-688), ONE call with the caller's F, G and map P (3x16): Transform = !(P*G), Translate =
+// -P*F*(xInit1-xInit2) (evaluated as ((-P)*F)*(xInit1-xInit2)), q_s = Transform*(points[s] + Translate).  One warp.
+__global__ void __launch_bounds__(32) k_stage_create_obstacle(int n, const double* __restrict__ pts, const double* __restrict__ F,
+                                                              const double* __restrict__ G, const double* __restrict__ P,
+                                                              const double* __restrict__ x1, const double* __restrict__ x2,
+                                                              double* __restrict__ Transform, double* __restrict__ Translate,
+                                                              double* __restrict__ q) {
+  __shared__ double sMPF[48], sT[9], sTr[3], sDx[16];
+  const int lane = lane_id();
+  if (lane < 16) sDx[lane] = x1[lane] - x2[lane];
+  for (int e = lane; e < 48; e += 32) {   // (-P)*F, 3x16
+    const int c = e >> 4, m = e & 15;
+    double t = 0;
+    for (int k = 0; k < 16; ++k) t += (-P[c * 16 + k]) * F[k * 16 + m];
+    sMPF[e] = t;
+  }
+  if (lane == 0) {
+    double pg[9];
+    for (int e = 0; e < 9; ++e) {         // P*G, 3x3
+      const int c = e / 3, r = e % 3;
+      double t = 0;
+      for (int k = 0; k < 16; ++k) t += P[c * 16 + k] * G[k * 3 + r];
+      pg[e] = t;
+    }
+    inverse3_ref(pg, sT);
+    for (int e = 0; e < 9; ++e) Transform[e] = sT[e];
+  }
+  __syncwarp();
+  if (lane < 3) {
+    double t = 0;
+    for (int m = 0; m < 16; ++m) t += sMPF[lane * 16 + m] * sDx[m];
+    sTr[lane] = t;
+    Translate[lane] = t;
+  }
+  __syncwarp();
+  for (int s = lane; s < n; s += 32) {
+    const double v0 = pts[3 * s] + sTr[0], v1 = pts[3 * s + 1] + sTr[1], v2 = pts[3 * s + 2] + sTr[2];
+    for (int r = 0; r < 3; ++r) {
+      double t = 0;
+      t += sT[3 * r] * v0; t += sT[3 * r + 1] * v1; t += sT[3 * r + 2] * v2;
+      q[3 * s + r] = t;
+    }
+  }
+}
+
 // mode 0: all H*P candidate points of the pair (xi, xj) -> q_out (AoS [HP][3])
 __global__ void __launch_bounds__(32) k_stage_candidates(LqroParams p, LqroTables tb, const double* __restrict__ xi,
                                                          const double* __restrict__ xj, double* __restrict__ q_out) {
