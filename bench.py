@@ -541,7 +541,7 @@ def run_ours(args):
             kern_ms += np.array([t["pairs"], t["hull"], t["lp"], t["total"]])
             dt = ctx.last_step_detail_ms()
             detail_ms += np.array([dt["slice1"], dt["slice2"], dt["early_hull"]])
-            overlap_sms = dt["overlap_sms"]
+            overlap_sms, first_slots = dt["overlap_sms"], dt["first_slots"]
     barrier()
     sampler.end()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -646,8 +646,7 @@ def run_ours(args):
         # agent) on the SMs the early hull launch does not use -- its pairs, its duration, the FP64 peak of ITS SMs
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         if overlap_sms > 0 and detail_ms[1] > 0:
-            first_slots = min(8, K)
-            pairs_per_launch = NL * (K - first_slots)
+            pairs_per_launch = NL * (K - min(first_slots, K))
             pair_s = float(detail_ms[1]) * 1e-3
             sm_frac = (sm_count - overlap_sms) / sm_count
         else:
@@ -682,11 +681,11 @@ def run_ours(args):
                           "note": "exact pruning skips horizon steps, so executed flop < algorithmic flop (F_alg counts every step)"}
                          if ncu else None),
             "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_s * 1e3,
-            "launch": ("second slice of k_pairs (slots 8..K-1 of every owned agent) on %d of %d SMs; peak = measured whole-chip FP64 "
-                       "peak %.2f TFLOP/s x %d/%d" % (sm_count - overlap_sms, sm_count, fp64_peak_full, sm_count - overlap_sms, sm_count)
+            "launch": ("second slice of k_pairs (slots %d..K-1 of every owned agent) on %d of %d SMs; peak = measured whole-chip FP64 "
+                       "peak %.2f TFLOP/s x %d/%d" % (first_slots, sm_count - overlap_sms, sm_count, fp64_peak_full, sm_count - overlap_sms, sm_count)
                        if sm_frac < 1.0 else "k_pairs, one launch over every pair of the rank"),
             "slices_ms": {"first": float(detail_ms[0]), "second": float(detail_ms[1]), "early_hull_launch": float(detail_ms[2]),
-                          "sms_left_to_the_early_hull_launch": int(overlap_sms)},
+                          "sms_left_to_the_early_hull_launch": int(overlap_sms), "first_slice_slots": int(first_slots)},
             "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak; ncu capture of that kernel: "
                            "profiles/r2_k_peak_fp64_ncu.txt); MEASURED_PEAKS.json has no FP64 figure",
             "hbm": {"achieved": pairs_per_launch * b_alg(K) / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

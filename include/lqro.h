@@ -291,8 +291,9 @@ int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops);
  * [3] whole step (kernels only, measured with CUDA events on the launching stream). */
 int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
 /* Two-slice steps (large swarms): [0] first slice of the pair kernel (nearest slots, every SM), [1] second slice (on all but
- * [3] SMs), [2] the early hull launch next to it (its own stream), [3] SMs left to that launch; one-launch steps: [1] only. */
-int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out4);
+ * [3] SMs), [2] the early hull launch next to it (its own stream), [3] SMs left to that launch, [4] neighbour slots per agent in the
+ * first slice; one-launch steps: [1] only ([3] = 0). */
+int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5);
 /* SM-cycle breakdown of the hull kernel of the last step, summed over hulls (development aid):
  * [0] init+simplex [1] partitionall [2] furthest+horizon+cone [3] planes+match [4] list [5] walk [6] redo
  * [7] append [8] delete [9] - [10] insertions [11] points re-partitioned [12] max cycles of one hull

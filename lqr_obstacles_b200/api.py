@@ -332,9 +332,9 @@ class Lqro:
         return dict(pairs=float(t[0]), hull=float(t[1]), lp=float(t[2]), total=float(t[3]))
 
     def last_step_detail_ms(self):
-        t = np.zeros(4, dtype=np.float32)
+        t = np.zeros(5, dtype=np.float32)
         self._ck(self.lib.lqro_last_step_detail_ms(self.h, _p(t)))
-        return dict(slice1=float(t[0]), slice2=float(t[1]), early_hull=float(t[2]), overlap_sms=int(t[3]))
+        return dict(slice1=float(t[0]), slice2=float(t[1]), early_hull=float(t[2]), overlap_sms=int(t[3]), first_slots=int(t[4]))
 
     def hull_cycles(self):
         c = np.zeros(16, dtype=np.int64)

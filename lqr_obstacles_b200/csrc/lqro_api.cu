@@ -229,6 +229,12 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
   p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
+  // nearest slots that form the first slice of the pair kernel (where the inside pairs are: 173 / 41 / 10 / 1 / 0 ... of the 225
+  // inside pairs of the bench swarm sit in slots 0 / 1 / 2 / 3 / 4+)
+  p.first_slots = 4;
+  if (const char* e = getenv("LQRO_FIRST_SLOTS")) p.first_slots = atoi(e);
+  if (p.first_slots < 1) p.first_slots = 1;
+  if (p.first_slots > 32) p.first_slots = 32;
   ctx->device_knn = (cfg->flags & LQRO_FLAG_DEVICE_KNN) ? 1 : 0;
   p.box[0] = p.box[1] = p.box[2] = 0.0;
   cudaDeviceProp prop;
@@ -650,8 +656,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     }
     pst = st;
     ovf_base = ctx->d_pair_ovf;
-  } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && p.K > LQRO_FIRST_SLOTS && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
-    // LARGE SWARM, TWO SLICES.  Slice 1 = the LQRO_FIRST_SLOTS nearest neighbour slots of every agent (where the inside pairs are).
+  } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && p.K > p.first_slots && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
+    // LARGE SWARM, TWO SLICES.  Slice 1 = the p.first_slots nearest neighbour slots of every agent (where the inside pairs are).
     // When it has finished, the queue length is recorded and an EARLY hull launch on its own stream works on those entries on
     // the overlap_sms SMs that slice 2 (all the other slots, the bulk of the pairs) leaves free; one hull is a ~1 ms sequential
     // job (qhull's insertion order), which this takes off the critical path of the step.  No kernel waits for another one:
@@ -662,7 +668,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       CU(cudaEventCreate(&ctx->ev_early));
       CU(cudaEventCreate(&ctx->ev_early0));
     }
-    const int first = (int)(slot_major_first(p.n_local, p.K) / 32);
+    const int first = (int)(slot_major_first(p.n_local, p.K, p.first_slots) / 32);
     sy.batch_begin = 0; sy.batch_end = first;
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     CU(cudaMemcpyAsync(ctx->d_ctr + 7, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -987,12 +993,13 @@ extern "C" int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16) {
   return LQRO_OK;
 }
 
-extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out4) {
-  if (!ctx || !out4) return LQRO_E_ARG;
+extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5) {
+  float* out4 = out5;
+  if (!ctx || !out5) return LQRO_E_ARG;
   if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
   CU(cudaSetDevice(ctx->cfg.device));
   CU(cudaEventSynchronize(ctx->ev[3]));
-  out4[0] = out4[1] = out4[2] = 0.f; out4[3] = (float)ctx->overlap_sms;
+  out4[0] = out4[1] = out4[2] = 0.f; out4[3] = (float)ctx->overlap_sms; out5[4] = (float)ctx->prm.first_slots;
   if (!ctx->last_two_slices) { CU(cudaEventElapsedTime(out4 + 1, ctx->ev[0], ctx->ev[1])); out4[3] = 0.f; return LQRO_OK; }
   CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_slice));
   CU(cudaEventElapsedTime(out4 + 1, ctx->ev_slice, ctx->ev[1]));

@@ -30,6 +30,7 @@ struct LqroParams {
   float lp_radius;
   int hull_input;
   int fix_facet0;
+  int first_slots;  // neighbour slots per agent in the first chunk of the slot-major pair enumeration (lqro_step.cuh)
   int prune;        // 1: skip horizon steps whose whole ellipsoid is provably unreachable (exact, see lqro_pair.cuh)
   double box[3];    // max_s |p_s| per coordinate: bounding box of the ellipsoid samples
 };

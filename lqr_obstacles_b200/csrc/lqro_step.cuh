@@ -55,22 +55,19 @@ struct StepSync {
   long long* prof;
 };
 
-// slot-major enumeration: the first chunk covers the LQRO_FIRST_SLOTS nearest neighbour slots of every agent, the following
+// slot-major enumeration: the first chunk covers the p.first_slots nearest neighbour slots of every agent, the following
 // ones 32 slots each; within a chunk pairs are agent-major.  Neighbour lists are sorted by distance, so the inside pairs -- the
 // ones that need a hull -- sit in the first chunk: the step launches it as its own slice of the pair kernel and starts hulling
 // its queue while the rest of the pairs are still being processed (launch_step).
 // idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end (chunks start on a batch boundary).
-#ifndef LQRO_FIRST_SLOTS
-#define LQRO_FIRST_SLOTS 8
-#endif
-__host__ __device__ inline int slot_chunk_width(int K, int c0) {
-  const int w = (c0 == 0) ? LQRO_FIRST_SLOTS : 32;
+__host__ __device__ inline int slot_chunk_width(int K, int c0, int first) {
+  const int w = (c0 == 0) ? first : 32;
   return (K - c0 < w) ? (K - c0) : w;
 }
 __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long idx, int& il, int& kk) {
   int c0 = 0;
   while (c0 < p.K) {
-    const int wdt = slot_chunk_width(p.K, c0);
+    const int wdt = slot_chunk_width(p.K, c0, p.first_slots);
     const long long cnt = (long long)p.n_local * wdt;
     const long long padded = (cnt + 31) & ~31ll;  // chunks start on a batch boundary
     if (idx < padded) {
@@ -84,14 +81,14 @@ __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long i
   }
   return false;
 }
-__host__ __device__ inline long long slot_major_total(int n_local, int K) {
+__host__ __device__ inline long long slot_major_total(int n_local, int K, int first) {
   long long t = 0;
-  for (int c0 = 0; c0 < K; c0 += slot_chunk_width(K, c0)) t += (((long long)n_local * slot_chunk_width(K, c0)) + 31) & ~31ll;
+  for (int c0 = 0; c0 < K; c0 += slot_chunk_width(K, c0, first)) t += (((long long)n_local * slot_chunk_width(K, c0, first)) + 31) & ~31ll;
   return t;
 }
 // pairs (padded to batches) of the first chunk
-__host__ __device__ inline long long slot_major_first(int n_local, int K) {
-  return (((long long)n_local * slot_chunk_width(K, 0)) + 31) & ~31ll;
+__host__ __device__ inline long long slot_major_first(int n_local, int K, int first) {
+  return (((long long)n_local * slot_chunk_width(K, 0, first)) + 31) & ~31ll;
 }
 
 #ifdef LQRO_PAIR_PROF  // per-phase cycle counts of the pair warps (lane 0), profiling builds only
@@ -176,7 +173,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
-  const long long total_all = slot_major_total(p.n_local, p.K);
+  const long long total_all = slot_major_total(p.n_local, p.K, p.first_slots);
   const long long total = (sy.batch_end >= 0 && (long long)sy.batch_end * 32 < total_all) ? (long long)sy.batch_end * 32 : total_all;
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);

@@ -14,5 +14,5 @@ for r in range(8):
     nv = ctx.step(x, vp, nb if r == 0 else None)
     if r >= 2: ms.append(ctx.last_step_ms())
 med = {k: float(np.median([m[k] for m in ms])) for k in ms[0]}
-print('overlap_sms', os.environ.get('LQRO_HULL_OVERLAP_SMS'), 'agents', len(x), 'K', K, 'median ms', {k: round(v, 4) for k, v in med.items()},
+print("overlap_sms", os.environ.get("LQRO_HULL_OVERLAP_SMS"), "first_slots", os.environ.get("LQRO_FIRST_SLOTS"), ctx.last_step_detail_ms(), 'agents', len(x), 'K', K, 'median ms', {k: round(v, 4) for k, v in med.items()},
       'checksum', float(nv.sum()), ctx.counters())

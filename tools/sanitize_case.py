@@ -19,3 +19,20 @@ print("classes ok", ctx.counters(), float(v.sum()))
 pl, vt, deg = ctx.convex_hull(g["qh_points"])
 print("hull ok", len(pl), deg)
 ctx.close()
+# a step large enough for the two-slice path (pair kernel in two slices, early hull launch on its own stream, wide hull launch)
+x, vp = swarm.lattice_swarm((16, 16, 8)); x[:, :3] *= 0.6
+nbr = swarm.knn(x[:, :3], 64)
+ctx = Lqro(n_agents=len(x), max_neighbors=64, horizon=20)
+ctx.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
+v = ctx.step(x, vp, nbr)
+print("two-slice step ok", ctx.counters(), float(v.sum()))
+# simulator-form update of the canonical 6 quads (golden state) and the batched Riccati solve
+from lqr_obstacles_b200.api import SimModel
+s = np.load(os.path.join(R, "tests/golden/sim_update.npz"))
+ctx.sim_set_model(SimModel.from_array(s["model"]))
+st = {k: s["s90_before_" + k].copy() for k in ("x", "Rot", "P", "xTrue", "RotTrue")}
+vG, _ = ctx.sim_update(st["x"], st["Rot"], st["P"], st["xTrue"], st["RotTrue"], s["s90_newV"], s["s90_before_pGoal"], s["s90_normals"])
+print("sim update ok", float(vG.sum()))
+L, E, Lh, Eh = ctx.solve_gains(np.tile(g["dyn_A"], (8, 1, 1)), np.tile(g["dyn_B"], (8, 1, 1)), iters=20)
+print("riccati ok", float(L.sum()))
+ctx.close()

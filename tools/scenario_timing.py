@@ -3,7 +3,7 @@
 stage, device next to the reference's own CPU code (oracle/_ref; one core, as the reference is single-threaded).
 The scenario is advanced by the reference simulator (LQR feedback, propagation, EKF) with the device step supplying
 newV (bit-identical trajectory, tests/test_gpu_trajectory.py); every `stride`-th step is also timed on the CPU through
-ref_step_agents.  Writes profiles/r1_scenarios_32_64.json and prints a markdown table."""
+ref_step_agents.  Writes profiles/r2_scenarios_32_64.json and prints a markdown table."""
 import ctypes, json, os, sys, time
 import numpy as np
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -53,7 +53,7 @@ for n, radius, steps, stride in ((32, 12.0, 60, 10), (64, 24.0, 60, 15)):
                 "reference_cpu_ms (1 core, in-process hull, no spawn)": {"obstacle_creation": m(c["obstacle"]), "half_plane_creation_without_hull": m(c["halfplane"]),
                                      "hull": m(c["hull"]), "new_velocity": m(c["newv"]), "step": m(c["total"]), "hulls_per_step": m(c["hulls"]),
                                      "steps_timed": len(c["total"])}})
-json.dump(out, open(os.path.join(R, "profiles", "r1_scenarios_32_64.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(R, "profiles", "r2_scenarios_32_64.json"), "w"), indent=1)
 print("| quads | pairs/step | inside pairs/step | k_pairs ms | k_hull ms | k_new_velocity ms | device step (kernels) ms | lqro_step wall ms | CPU obstacle ms | CPU half-plane ms | CPU hull ms | CPU new-V ms | CPU step ms |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for o in out:
