@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -103,7 +104,7 @@ struct lqro_ctx {
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
   int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
-  int hull_wpb = 2, hull_blocks = 0; size_t hull_smem = 0;
+  int hull_wpb = 2, hull_blocks = 0, hull_per_sm = 1; size_t hull_smem = 0;
   // two-slice step of large swarms: SMs left to the early hull launch, its stream and the events that order it
   int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr, ev_early0 = nullptr; bool last_two_slices = false;
   // stage scratch (grown on demand)
@@ -231,7 +232,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
   // nearest slots that form the first slice of the pair kernel (where the inside pairs are: 173 / 41 / 10 / 1 / 0 ... of the 225
   // inside pairs of the bench swarm sit in slots 0 / 1 / 2 / 3 / 4+)
-  p.first_slots = 4;
+  p.first_slots = 8;  // measured at 65,536 x 64 with 16 SMs: 8 -> 6.58 ms, 4 -> 7.37 (two stragglers in slots 4-7 wait for the wide launch), 2 -> 7.74
   if (const char* e = getenv("LQRO_FIRST_SLOTS")) p.first_slots = atoi(e);
   if (p.first_slots < 1) p.first_slots = 1;
   if (p.first_slots > 32) p.first_slots = 32;
@@ -332,6 +333,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     int per_sm = (int)((ctx->smem_optin + 1024) / (ctx->hull_smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
+    ctx->hull_per_sm = per_sm;
     int slots = cfg->hull_slots > 0 ? cfg->hull_slots : ctx->sm_count * per_sm;
     if (slots < ctx->sm_count) slots = ctx->sm_count;
     ctx->hull_slots = slots;
@@ -594,7 +596,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
   // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
   //        [6] batch counter of the second slice [7] queue length when the first slice had finished
-  StepSync sy{ctx->d_ctr + 0, 0, -1, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  StepSync sy{ctx->d_ctr + 0, 0, -1, 32, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_early = 0;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
@@ -669,13 +671,17 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       CU(cudaEventCreate(&ctx->ev_early0));
     }
     const int first = (int)(slot_major_first(p.n_local, p.K, p.first_slots) / 32);
-    sy.batch_begin = 0; sy.batch_end = first;
+    // pairs per batch of the first slice: narrow enough for ~3 batches per pair warp of the grid (a batch is one warp's sequential job)
+    int bw = 32;
+    while (bw > 4 && (long long)first * (32 / bw) < 3LL * ctx->pair_blocks * ctx->pair_warps) bw >>= 1;
+    sy.batch_begin = 0; sy.batch_end = first * (32 / bw); sy.batch_width = bw;
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+    sy.batch_width = 32;
     CU(cudaMemcpyAsync(ctx->d_ctr + 7, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
     CU(cudaEventRecord(ctx->ev_slice, st));
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_slice, 0));
     CU(cudaEventRecord(ctx->ev_early0, ctx->hull_stream));
-    LQRO_LAUNCH_HULL(2 * ctx->overlap_sms, ctx->hull_stream, ctx->d_ctr + 7, ctx->d_ctr + 4,
+    LQRO_LAUNCH_HULL(std::min(ctx->hull_per_sm * ctx->overlap_sms, ctx->hull_blocks), ctx->hull_stream, ctx->d_ctr + 7, ctx->d_ctr + 4,
                      ctx->pair_warps * (2 * ctx->pair_blocks - ctx->overlap_sms));  // pair warps of both slices
     CU(cudaEventRecord(ctx->ev_early, ctx->hull_stream));
     sy.batch_counter = ctx->d_ctr + 6; sy.batch_begin = first; sy.batch_end = -1;

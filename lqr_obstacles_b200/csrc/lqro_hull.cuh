@@ -30,8 +30,11 @@ __host__ __device__ inline size_t hull_warp_smem_bytes(int H, int P) {
   return hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1)) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) +
          hull_align16(sizeof(HullCtl));
 }
+// the stand-alone hull kernel keeps only the ellipsoid samples (SoA, 3P doubles) in shared memory: the horizon tables are read
+// from global memory (13-19 KB shared by every hull of the GPU, L1 / L2 resident; they are only needed while the cloud is
+// regenerated), which is what lets a second (H = 30) or third (H = 20) hull block fit on an SM
 __host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
-  return hull_align16(sizeof(double) * pair_block_table_doubles(H, P)) + hull_warp_smem_bytes(H, P);
+  return hull_align16(sizeof(double) * 3 * (size_t)P) + hull_warp_smem_bytes(H, P);
 }
 __device__ __forceinline__ void hull_warp_setup(HullWarp& hw, char* sm, char* gslot, int H, int P) {
   double* wb = reinterpret_cast<double*>(sm);
@@ -40,6 +43,7 @@ __device__ __forceinline__ void hull_warp_setup(HullWarp& hw, char* sm, char* gs
   hw.ctl = reinterpret_cast<HullCtl*>(hw.hot + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS));
   hw.gslot = gslot;
   hull_carve_coords(gslot, H * P, hw.w);
+  hull_carve_cold(gslot + hull_slot_cold_offset(H * P), H * P, hull_full_facets(H * P), hw.w);
   hw.pw.px = hw.w.ux; hw.pw.py = hw.w.uy; hw.pw.pz = hw.w.uz;
 }
 
@@ -134,15 +138,15 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
   if (nq > hq.capacity) nq = hq.capacity;
   if (*(volatile int*)work_counter + (int)blockIdx.x >= nq) return;  // nothing can be left for this block
   PairTables pt;
-  load_block_tables(smem, tb, p.H, p.P);
   {
-    const int H = p.H, P = p.P;
-    pt.NFt = smem; pt.T = smem + 16 * 3 * H; pt.sphx = pt.T + 9 * H; pt.sphy = pt.sphx + P; pt.sphz = pt.sphy + P;
-    pt.CG = pt.sphz + P; pt.prn = pt.CG + 9 * H;
+    const int P = p.P;
+    for (int e = lane; e < P; e += 32) { smem[e] = tb.sph[3 * e]; smem[P + e] = tb.sph[3 * e + 1]; smem[2 * P + e] = tb.sph[3 * e + 2]; }
+    __syncwarp();
+    pt.NFt = tb.NFt; pt.T = tb.T; pt.CG = tb.CG; pt.prn = tb.prn;
+    pt.sphx = smem; pt.sphy = smem + P; pt.sphz = smem + 2 * P;
   }
   HullWarp hw;
-  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * pair_block_table_doubles(p.H, p.P)),
-                  ws_base + ws_stride * (size_t)blockIdx.x, p.H, p.P);
+  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * 3 * (size_t)p.P), ws_base + ws_stride * (size_t)blockIdx.x, p.H, p.P);
   int loaded = agent_class ? -1 : 0;
   while (true) {
     int item = 0;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, con
     if (pair < 0) continue;
     if (agent_class) {  // heterogeneous dynamics: the obstacle of pair (i, j) uses agent i's class (MAIN:1384)
       const int c = agent_class[p.local_begin + pair / p.K];
-      if (c != loaded) { __syncwarp(); load_block_tables(smem, class_tables[c], p.H, p.P); loaded = c; }
+      if (c != loaded) { const LqroTables tc = class_tables[c]; pt.NFt = tc.NFt; pt.T = tc.T; pt.CG = tc.CG; pt.prn = tc.prn; loaded = c; }
     }
     hull_do_pair(p, pt, hw, x, nbr, out, pair, counters, prof);
   }

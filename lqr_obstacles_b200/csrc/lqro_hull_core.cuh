@@ -134,36 +134,49 @@ struct __align__(8) HMeta {
 struct HullWs {
   double *hx, *hy, *hz;   // hull input coordinates [cap_pts]
   double *ux, *uy, *uz;   // un-rounded cloud [cap_pts]                  (global)
-  double* pdist;          // [cap_pts]     partition scratch
-  hidx *pnext, *plist, *pstart, *pbest, *vpoint;  // [cap_pts + 8]
+  hidx *pnext, *vpoint;   // [cap_pts + 8]   outside-list links, vertex id -> point               (hot)
+  double* pdist;          // [cap_pts]       partition scratch                                       (cold: global slot)
+  hidx *plist, *pstart, *pbest;  // [cap_pts + 8]                                                    (cold)
   HPlane* pl; HTopo* tp; HOut* ot; HMeta* mt;     // [cap_f]
   hidx *aux;              // [cap_f] visible facet: the last cone facet made from its ridges (qhull's f.replace); new facet: cone-local index
-  hidx *vis, *freel, *ring, *order;  // [cap_f]; ring [ring_mask + 1]
+  hidx *vis, *freel, *ring;  // [cap_f]; ring [ring_mask + 1]
+  hidx *order;            // [cap_f] facets in qhull's list order, stage kernel only                    (cold)
   hidx *newf;             // [LQRO_HULL_MAXNEW]
-  int* vown;              // [cap_pts + 8] ridge matching of large cones: cone facet that last touched vertex id v (-1 = none)
+  int* vown;              // [cap_pts + 8] ridge matching of large cones: cone facet that last touched vertex id v (-1 = none)   (cold)
   int cap_pts, cap_f, ring_mask;
 };
 
 __host__ __device__ inline size_t hull_align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline int hull_ring_size(int cap_f) { int r = 64; while (r < cap_f) r <<= 1; return r; }
-// bytes of the hot structures for a facet pool of cap_f (shared memory fast path, or inside the global slot)
+// bytes of the HOT structures for a facet pool of cap_f (shared memory on the fast path, or inside the global slot): what every
+// insertion touches -- facet records, hull input coordinates, outside-list links, vertex map, visible / free / pending lists
 __host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   size_t b = 0;
   b += hull_align16(sizeof(HPlane) * (size_t)cap_f);
   b += hull_align16(sizeof(HTopo) * (size_t)cap_f);
   b += hull_align16(sizeof(HOut) * (size_t)cap_f);
   b += hull_align16(sizeof(HMeta) * (size_t)cap_f);
-  b += hull_align16(sizeof(double) * (size_t)cap_pts);                  // pdist
   b += hull_align16(3 * sizeof(double) * (size_t)cap_pts);              // hx hy hz (hull input coordinates)
-  b += hull_align16(sizeof(hidx) * 5 * ((size_t)cap_pts + 8));          // pnext plist pstart pbest vpoint
-  b += hull_align16(sizeof(hidx) * (4 * (size_t)cap_f + (size_t)hull_ring_size(cap_f) + LQRO_HULL_MAXNEW));  // aux vis freel order ring newf
+  b += hull_align16(sizeof(hidx) * 2 * ((size_t)cap_pts + 8));          // pnext vpoint
+  b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + (size_t)hull_ring_size(cap_f) + LQRO_HULL_MAXNEW));  // aux vis freel ring newf
+  return b;
+}
+// bytes of the COLD structures (always in the global slot, L1 / L2 resident): the scratch of the initial partition and of
+// re-partitions of more than 32 points, the owner words of cones of more than 16 facets, the facet order of the stage kernel
+__host__ __device__ inline size_t hull_cold_bytes(int cap_pts, int cap_f) {
+  size_t b = 0;
+  b += hull_align16(sizeof(double) * (size_t)cap_pts);                  // pdist
+  b += hull_align16(sizeof(hidx) * 3 * ((size_t)cap_pts + 8));          // plist pstart pbest
   b += hull_align16(sizeof(int) * ((size_t)cap_pts + 8));               // vown
+  b += hull_align16(sizeof(hidx) * (size_t)cap_f);                      // order
   return b;
 }
 __host__ __device__ inline int hull_full_facets(int cap_pts) { return 2 * cap_pts + 64; }
-// one global slot: the un-rounded cloud + a full-size copy of the hot structures (fallback path)
+// one global slot: the un-rounded cloud + the cold structures (sized for the full pool) + a full-size copy of the hot structures
+// (fallback path)
 __host__ __device__ inline size_t hull_ws_bytes(int cap_pts) {
-  size_t b = hull_align16(3 * sizeof(double) * (size_t)cap_pts) + hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
+  size_t b = hull_align16(3 * sizeof(double) * (size_t)cap_pts) + hull_cold_bytes(cap_pts, hull_full_facets(cap_pts)) +
+             hull_hot_bytes(cap_pts, hull_full_facets(cap_pts));
   return (b + 255) & ~(size_t)255;
 }
 __device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_f, HullWs& w) {
@@ -174,28 +187,38 @@ __device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_
   w.tp = reinterpret_cast<HTopo*>(base);  base += hull_align16(sizeof(HTopo) * (size_t)cap_f);
   w.ot = reinterpret_cast<HOut*>(base);   base += hull_align16(sizeof(HOut) * (size_t)cap_f);
   w.mt = reinterpret_cast<HMeta*>(base);  base += hull_align16(sizeof(HMeta) * (size_t)cap_f);
-  w.pdist = reinterpret_cast<double*>(base); base += hull_align16(sizeof(double) * (size_t)cap_pts);
   double* d = reinterpret_cast<double*>(base);
   w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
   base += hull_align16(3 * sizeof(double) * (size_t)cap_pts);
   hidx* ip = reinterpret_cast<hidx*>(base);
   const size_t ci = (size_t)cap_pts + 8;
-  w.pnext = ip; w.plist = ip + ci; w.pstart = ip + 2 * ci; w.pbest = ip + 3 * ci; w.vpoint = ip + 4 * ci;
-  base += hull_align16(sizeof(hidx) * 5 * ci);
+  w.pnext = ip; w.vpoint = ip + ci;
+  base += hull_align16(sizeof(hidx) * 2 * ci);
   hidx* jp = reinterpret_cast<hidx*>(base);
-  w.aux = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f; w.order = jp + 3 * (size_t)cap_f;
-  w.ring = jp + 4 * (size_t)cap_f; w.newf = w.ring + rs;
-  base += hull_align16(sizeof(hidx) * (4 * (size_t)cap_f + (size_t)rs + LQRO_HULL_MAXNEW));
-  w.vown = reinterpret_cast<int*>(base);
+  w.aux = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f;
+  w.ring = jp + 3 * (size_t)cap_f; w.newf = w.ring + rs;
+}
+__device__ __forceinline__ void hull_carve_cold(char* base, int cap_pts, int cap_f, HullWs& w) {
+  w.pdist = reinterpret_cast<double*>(base); base += hull_align16(sizeof(double) * (size_t)cap_pts);
+  hidx* ip = reinterpret_cast<hidx*>(base);
+  const size_t ci = (size_t)cap_pts + 8;
+  w.plist = ip; w.pstart = ip + ci; w.pbest = ip + 2 * ci;
+  base += hull_align16(sizeof(hidx) * 3 * ci);
+  w.vown = reinterpret_cast<int*>(base); base += hull_align16(sizeof(int) * ci);
+  w.order = reinterpret_cast<hidx*>(base);
 }
 __device__ __forceinline__ void hull_carve_coords(char* gbase, int cap_pts, HullWs& w) {  // the un-rounded cloud
   double* d = reinterpret_cast<double*>(gbase);
   w.ux = d; w.uy = d + cap_pts; w.uz = d + 2 * (size_t)cap_pts;
 }
+// offsets inside the global slot
+__host__ __device__ inline size_t hull_slot_cold_offset(int cap_pts) { return hull_align16(3 * sizeof(double) * (size_t)cap_pts); }
+__host__ __device__ inline size_t hull_slot_hot_offset(int cap_pts) { return hull_slot_cold_offset(cap_pts) + hull_cold_bytes(cap_pts, hull_full_facets(cap_pts)); }
 // everything in the global slot (fallback / stage kernel)
 __device__ __forceinline__ void hull_ws_carve(char* gbase, int cap_pts, HullWs& w) {
   hull_carve_coords(gbase, cap_pts, w);
-  hull_carve_hot(gbase + hull_align16(3 * sizeof(double) * (size_t)cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+  hull_carve_cold(gbase + hull_slot_cold_offset(cap_pts), cap_pts, hull_full_facets(cap_pts), w);
+  hull_carve_hot(gbase + hull_slot_hot_offset(cap_pts), cap_pts, hull_full_facets(cap_pts), w);
 }
 
 // per-warp control block in shared memory: constants of the hull and its results (the running counters of the build

@@ -49,6 +49,9 @@ __host__ __device__ inline size_t pair2_warp_doubles(int H) {
 struct StepSync {
   int* batch_counter;   // next batch of pairs of this launch (relative to batch_begin)
   int batch_begin, batch_end;  // batches [begin, end) of the slot-major enumeration belong to this launch (end < 0: to the last one)
+  int batch_width;             // pairs per batch: 32, or 16 / 8 / 4 for a first slice with few agents -- a batch is walked by ONE warp pair
+                               // after pair in stage 2 (~8 us per near-neighbour pair), so 32-pair batches put a 0.25 ms floor under a
+                               // slice that has fewer batches than the grid has warps
   int* hull_head;       // next hull ticket
   int* done_warps;      // pair warps that have finished
   int* counters;        // misc counters (degenerate, fallback, ...)
@@ -174,7 +177,8 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
   const long long total_all = slot_major_total(p.n_local, p.K, p.first_slots);
-  const long long total = (sy.batch_end >= 0 && (long long)sy.batch_end * 32 < total_all) ? (long long)sy.batch_end * 32 : total_all;
+  const int bw = sy.batch_width;
+  const long long total = (sy.batch_end >= 0 && (long long)sy.batch_end * bw < total_all) ? (long long)sy.batch_end * bw : total_all;
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
@@ -182,11 +186,11 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     int batch = 0;
     if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
     batch = __shfl_sync(LQRO_FULL, batch, 0) + sy.batch_begin;
-    const long long base = (long long)batch * 32;
+    const long long base = (long long)batch * bw;
     if (base >= total) break;
     // ---------------- stage 1: lane = pair
     int il = 0, kk = 0;
-    const bool have = slot_major_pair(p, base + lane, il, kk);
+    const bool have = lane < bw && slot_major_pair(p, base + lane, il, kk);
     if (have && order) il = order[il];
     const int pair = have ? il * p.K + kk : -1;
     int i = 0, j = -1;

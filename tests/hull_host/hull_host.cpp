@@ -20,12 +20,14 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
   const int cf = cap_f > 0 ? cap_f : hull_full_facets(cap_pts);
   char* coords = (char*)calloc(1, hull_align16(3 * sizeof(double) * (size_t)cap_pts) + 64);
   char* hot = (char*)calloc(1, hull_hot_bytes(cap_pts, cf) + 64);
+  char* cold = (char*)calloc(1, hull_cold_bytes(cap_pts, cf) + 64);
   HullCtl ctl;
   memset(&ctl, 0, sizeof ctl);
   emu_run_warp([&](int lane) {
     HullWs w;
     hull_carve_coords(coords, cap_pts, w);
     hull_carve_hot(hot, cap_pts, cf, w);
+    hull_carve_cold(cold, cap_pts, cf, w);
     if (ring > 0 && ring - 1 < w.ring_mask) w.ring_mask = ring - 1;  // tests: a smaller pending ring (power of two)
     for (int m = lane; m < n; m += 32) {
       const double a = pts[3 * m], b = pts[3 * m + 1], c = pts[3 * m + 2];
@@ -51,7 +53,7 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
       if (lane == 0) { escape4[0] = distance; escape4[1] = normal[0]; escape4[2] = normal[1]; escape4[3] = normal[2]; info5[4] = pos; }
     }
   });
-  free(coords); free(hot);
+  free(coords); free(hot); free(cold);
   return 0;
 }
 
