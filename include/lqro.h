@@ -299,6 +299,8 @@ int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5);
  * [7] append [8] delete [9] - [10] insertions [11] points re-partitioned [12] max cycles of one hull
  * [13] max points [14] max facets */
 int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16);
+/* Profiling builds (-DLQRO_HULL_PROF): the same phases for the LONGEST hull of the last step; [12] its points, [13] its facets. */
+int lqro_debug_hull_longest(lqro_ctx* ctx, long long* out16);
 /* SM-cycle breakdown of the simulator-form update kernel, summed over agents since the last reset; zeros unless the
  * library was built with -DLQRO_SIM_PROF (tools/simprof.py).  Phases: see csrc/lqro_sim.cuh. */
 int lqro_debug_sim_cycles(lqro_ctx* ctx, long long* out16, int reset);

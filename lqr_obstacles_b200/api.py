@@ -39,7 +39,7 @@ EXPORTS = [
     "lqro_get_counters", "lqro_find_fg", "lqro_create_obstacle", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms", "lqro_last_step_detail_ms",
-    "lqro_debug_hull_cycles", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
+    "lqro_debug_hull_cycles", "lqro_debug_hull_longest", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
     "lqro_sim_last_ms", "lqro_debug_sim_cycles", "lqro_timestep_device",
@@ -137,6 +137,7 @@ def load_library(path=None):
     lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_last_step_detail_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_hull_cycles.argtypes = [c_void_p, c_void_p]
+    lib.lqro_debug_hull_longest.argtypes = [c_void_p, c_void_p]
     lib.lqro_sim_default_model.argtypes = [ctypes.POINTER(SimModel)]
     lib.lqro_sim_default_model.restype = None
     lib.lqro_sim_set_model.argtypes = [c_void_p, ctypes.POINTER(SimModel)]
@@ -335,6 +336,11 @@ class Lqro:
         t = np.zeros(5, dtype=np.float32)
         self._ck(self.lib.lqro_last_step_detail_ms(self.h, _p(t)))
         return dict(slice1=float(t[0]), slice2=float(t[1]), early_hull=float(t[2]), overlap_sms=int(t[3]), first_slots=int(t[4]))
+
+    def hull_longest(self):
+        c = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.lqro_debug_hull_longest(self.h, _p(c)))
+        return c
 
     def hull_cycles(self):
         c = np.zeros(16, dtype=np.int64)

@@ -999,6 +999,15 @@ extern "C" int lqro_debug_hull_cycles(lqro_ctx* ctx, long long* out16) {
   return LQRO_OK;
 }
 
+extern "C" int lqro_debug_hull_longest(lqro_ctx* ctx, long long* out16) {  // profiling builds: phase cycles of the longest hull of the last step, [12] points, [13] facets
+  if (!ctx || !out16) return LQRO_E_ARG;
+  if (!ctx->stepped) return fail(ctx, LQRO_E_STATE, "no step yet");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(out16, ctx->d_prof + 16, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+  return LQRO_OK;
+}
+
 extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5) {
   float* out4 = out5;
   if (!ctx || !out5) return LQRO_E_ARG;

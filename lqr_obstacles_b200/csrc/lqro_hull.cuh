@@ -61,7 +61,7 @@ __device__ __forceinline__ void hull_finish_pair(const HullWs& w, HullCtl* ctl, 
   if (lane == 0 && prof) {
     long long tot = 0;
     for (int q = 0; q < 12; ++q) { atomicAdd((unsigned long long*)prof + q, (unsigned long long)ctl->prof[q]); if (q < 10) tot += ctl->prof[q]; }
-    atomicMax(prof + 12, tot);
+    if (atomicMax(prof + 12, tot) < tot) { for (int q = 0; q < 12; ++q) prof[16 + q] = ctl->prof[q]; prof[28] = n; prof[29] = ctl->nfacets_out; }  // phases of the longest hull so far
     atomicMax(prof + 13, (long long)n);
     atomicMax(prof + 14, (long long)ctl->nfacets_out);
   }

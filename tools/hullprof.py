@@ -27,3 +27,7 @@ res = ctx.pair_results(); st = res['status'] & 0xff
 nr = res['nreach'][st == 2]; nf = res['nfacets'][st == 2]
 print('inside hull sizes: n mean %.0f max %d; facets mean %.0f max %d' % (nr.mean(), nr.max(), nf.mean(), nf.max()))
 print('cycles per insertion', tot / max(1, c[10]), 'points re-partitioned per insertion', c[11] / max(1, c[10]))
+lg = ctx.hull_longest()
+tl = lg[:10].sum()
+print('LONGEST hull: %d points, %d facets, %d insertions, %d cycles (%.3f ms at 1.965 GHz), points re-partitioned %d' % (lg[12], lg[13], lg[10], tl, tl / 1.965e6, lg[11]))
+for n, v in zip(names[:10], lg[:10]): print('  %-24s %12d %5.1f%%' % (n, v, 100 * v / tl if tl else 0))
