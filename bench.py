@@ -614,7 +614,7 @@ def run_ours(args):
         stream.synchronize()
         k_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         knn_arm = {"value": N * K / (k_ms * 1e-3), "unit": UNIT, "ms_per_step": k_ms,
-                   "h2d_bytes_per_step": int(x_loc.nbytes + vp_loc.nbytes), "gpu_launches_per_step": 9,
+                   "h2d_bytes_per_step": int(x_loc.nbytes + vp_loc.nbytes), "gpu_launches_per_step": 8,
                    "neighbour_table_identical": bool(np.array_equal(ctx2.neighbors(), nbr_loc)),
                    "newV_identical": bool(np.array_equal(hout2.numpy(), hout_np)), "api": "lqro_step_sharded(nbr=NULL) with LQRO_FLAG_DEVICE_KNN"}
         ctx2.close()
@@ -642,11 +642,11 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # the dominant launch: with the two-slice step it is the second slice of k_pairs (all slots but the nearest 8 of every
-        # agent) on the SMs the early hull launch does not use -- its pairs, its duration, the FP64 peak of ITS SMs
+        # the dominant launch: k_pairs, one launch over every pair of the rank; on a large swarm it runs on the SMs the polling
+        # hull launch does not use -- its duration, the FP64 peak of ITS SMs
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        if overlap_sms > 0 and detail_ms[1] > 0:
-            pairs_per_launch = NL * (K - min(first_slots, K))
+        if overlap_sms > 0 and detail_ms[2] > 0:
+            pairs_per_launch = NL * K
             pair_s = float(detail_ms[1]) * 1e-3
             sm_frac = (sm_count - overlap_sms) / sm_count
         else:
@@ -681,11 +681,12 @@ def run_ours(args):
                           "note": "exact pruning skips horizon steps, so executed flop < algorithmic flop (F_alg counts every step)"}
                          if ncu else None),
             "algorithmic_flop_per_pair": f_alg(H, P), "pairs_per_launch": pairs_per_launch, "kernel_ms": pair_s * 1e3,
-            "launch": ("second slice of k_pairs (slots %d..K-1 of every owned agent) on %d of %d SMs; peak = measured whole-chip FP64 "
-                       "peak %.2f TFLOP/s x %d/%d" % (first_slots, sm_count - overlap_sms, sm_count, fp64_peak_full, sm_count - overlap_sms, sm_count)
+            "launch": ("k_pairs, one launch over every pair of the rank, on %d of %d SMs (the other %d run the polling hull launch, a "
+                       "concurrent consumer of the hull queue); peak = measured whole-chip FP64 peak %.2f TFLOP/s x %d/%d"
+                       % (sm_count - overlap_sms, sm_count, overlap_sms, fp64_peak_full, sm_count - overlap_sms, sm_count)
                        if sm_frac < 1.0 else "k_pairs, one launch over every pair of the rank"),
-            "slices_ms": {"first": float(detail_ms[0]), "second": float(detail_ms[1]), "early_hull_launch": float(detail_ms[2]),
-                          "sms_left_to_the_early_hull_launch": int(overlap_sms), "first_slice_slots": int(first_slots)},
+            "overlap_ms": {"k_pairs": float(detail_ms[1]), "polling_hull_launch": float(detail_ms[2]),
+                           "sms_of_the_polling_hull_launch": int(overlap_sms), "first_chunk_slots": int(first_slots)},
             "peak_source": "FP64 CUDA-core pipe measured in this run (DFMA chains, lqro_measure_fp64_peak; ncu capture of that kernel: "
                            "profiles/r2_k_peak_fp64_ncu.txt); MEASURED_PEAKS.json has no FP64 figure",
             "hbm": {"achieved": pairs_per_launch * b_alg(K) / pair_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -730,7 +731,7 @@ def run_ours(args):
             "parity_sample": {"agents": int(pstat[1]), "planes_compared": int(pstat[2]), "inside_pairs_compared": int(pstat[3]),
                               "what": "untimed: whole rows (status, half-planes, newV) of random agents of every rank + agents owning a "
                                       "hull plane vs the CPU oracle, bit for bit; device-resident and host-buffer arms equal"},
-            "gpu_launches": counters["launches"] * args.steps,  # per step: k_pairs x 2 slices, k_hull early + wide, k_new_velocity (the all-gather kernel is NCCL's)
+            "gpu_launches": counters["launches"] * args.steps,  # per step: k_hull polling, k_pairs, k_hull wide, k_new_velocity (the all-gather kernel is NCCL's)
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "counters": counters,

@@ -78,10 +78,10 @@ typedef struct lqro_config {
 #define LQRO_FLAG_FUSED_HULL 2 /* one hull warp per pair-kernel CTA consumes the inside-case queue concurrently
                                   (experimental: measured slower than the stand-alone hull kernel) */
 
-#define LQRO_FLAG_NO_OVERLAP 8 /* steps of large swarms (>= 2^17 pairs) run the pair kernel in two slices and hull the queue of the
-                                  first one next to the second; this flag (or LQRO_HULL_OVERLAP_SMS=0 in the environment) keeps one
-                                  pair launch followed by the hulls.  Host-buffer steps then upload the neighbour table in blocks
-                                  overlapped with per-block pair launches. */
+#define LQRO_FLAG_NO_OVERLAP 8 /* steps of large swarms (>= 2^17 pairs) run a polling hull launch on a few SMs of its own next to the
+                                  pair kernel, as a concurrent consumer of the inside-case queue; this flag (or LQRO_HULL_OVERLAP_SMS=0
+                                  in the environment) keeps the pair kernel on every SM followed by the hulls.  Host-buffer steps
+                                  then upload the neighbour table in blocks overlapped with per-block pair launches. */
 
 /* Fills the reference's compile-time constants (MAIN:30-36, 1102, 1367). */
 void lqro_default_config(lqro_config* cfg);

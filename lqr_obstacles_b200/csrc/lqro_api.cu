@@ -104,8 +104,8 @@ struct lqro_ctx {
   int hull_slots = 0, hull_cap = 0, cap_pts = 0;
   // launch geometry
   int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
-  int hull_wpb = 2, hull_blocks = 0, hull_per_sm = 1; size_t hull_smem = 0;
-  // two-slice step of large swarms: SMs left to the early hull launch, its stream and the events that order it
+  int hull_wpb = 2, hull_blocks = 0, hull_per_sm = 1, hull_poll_warps = 1; size_t hull_smem = 0;
+  // step of large swarms: SMs of the polling hull launch (the pair kernel's grid is that much smaller), its stream and the events that order it
   int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr, ev_early0 = nullptr; bool last_two_slices = false;
   // stage scratch (grown on demand)
   char* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -230,9 +230,9 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
   p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
-  // nearest slots that form the first slice of the pair kernel (where the inside pairs are: 173 / 41 / 10 / 1 / 0 ... of the 225
-  // inside pairs of the bench swarm sit in slots 0 / 1 / 2 / 3 / 4+)
-  p.first_slots = 8;  // measured at 65,536 x 64 with 16 SMs: 8 -> 6.58 ms, 4 -> 7.37 (two stragglers in slots 4-7 wait for the wide launch), 2 -> 7.74
+  // width of the first chunk of the slot-major enumeration (the following ones double, lqro_step.cuh): the inside pairs -- 173 / 41 /
+  // 10 / 1 / 0 ... of the 225 of the bench swarm sit in slots 0 / 1 / 2 / 3 / 4+ -- should reach the hull queue first
+  p.first_slots = 1;
   if (const char* e = getenv("LQRO_FIRST_SLOTS")) p.first_slots = atoi(e);
   if (p.first_slots < 1) p.first_slots = 1;
   if (p.first_slots > 32) p.first_slots = 32;
@@ -278,6 +278,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   CUC(cudaMemset(ctx->d_planes, 0, sizeof(float) * 6 * NP));
   ctx->hull_cap = cfg->max_hull_pairs > 0 ? cfg->max_hull_pairs : (int)NP;  // lqro.h: 0 => every pair may queue
   CUC(cudaMalloc(&ctx->d_hull_items, sizeof(int) * (size_t)ctx->hull_cap));
+  CUC(cudaMemset(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap));  // -1 = not published; every consumer restores it (k_hull)
   // sphere samples: createSpheres, MAIN:665-680 (one-off table; radii doubled for the Minkowski sum)
   {
     std::vector<double> sph(3 * (size_t)P);
@@ -338,12 +339,18 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     if (slots < ctx->sm_count) slots = ctx->sm_count;
     ctx->hull_slots = slots;
     ctx->hull_blocks = slots;
-    // SMs the second slice of the pair kernel leaves to the early hull launch (two hull blocks per SM); LQRO_HULL_OVERLAP_SMS=0
-    // or LQRO_FLAG_NO_OVERLAP: one pair launch, hulls afterwards
-    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 16;  // measured at 65,536 x 64: 12 -> 7.96 ms, 16 -> 6.58, 20 -> 6.65 (0: 6.89); at 8,192 x 64: 1.74 -> 1.36
+    // SMs of the polling hull launch of a large swarm's step (the pair kernel's grid is that much smaller); LQRO_HULL_OVERLAP_SMS=0
+    // or LQRO_FLAG_NO_OVERLAP: pair kernel on every SM, hulls afterwards
+    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 16;
     if (const char* e = getenv("LQRO_HULL_OVERLAP_SMS")) ctx->overlap_sms = atoi(e);
     if (ctx->overlap_sms < 0) ctx->overlap_sms = 0;
     if (ctx->overlap_sms > ctx->sm_count / 2) ctx->overlap_sms = ctx->sm_count / 2;
+    // hull warps per block of the polling launch: as many as the opt-in shared memory holds, at most LQRO_HULL_POLL_WARPS (its
+    // shared-memory REQUEST is always the whole opt-in size, which keeps pair CTAs off its SMs)
+    ctx->hull_poll_warps = (int)((ctx->smem_optin - hull_align16(sizeof(double) * 3 * (size_t)P)) / hull_warp_smem_bytes(H, P));
+    if (ctx->hull_poll_warps > LQRO_HULL_POLL_WARPS) ctx->hull_poll_warps = LQRO_HULL_POLL_WARPS;
+    if (ctx->hull_poll_warps < 1) ctx->hull_poll_warps = 1;
+    if (ctx->overlap_sms * ctx->hull_poll_warps > slots) ctx->overlap_sms = slots / ctx->hull_poll_warps;
     ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
     CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * (size_t)slots));
   }
@@ -595,8 +602,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaMemsetAsync(ctx->d_prof, 0, sizeof(long long) * 32, st));
   if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
   // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
-  //        [6] batch counter of the second slice [7] queue length when the first slice had finished
-  StepSync sy{ctx->d_ctr + 0, 0, -1, 32, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  //        [8] pair CTAs that have started
+  StepSync sy{ctx->d_ctr + 0, 0, 32, ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_early = 0;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
@@ -609,9 +616,6 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
     else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
   } while (0)
-#define LQRO_LAUNCH_HULL(GRID, STREAM, LIMIT, DONE, DONE_TOTAL)                                                                  \
-  k_hull<<<GRID, 32, ctx->hull_smem, STREAM>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, LIMIT, DONE, DONE_TOTAL, ctx->d_hull_ws, ctx->hull_ws_stride, \
-                                               ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs)
   cudaStream_t pst = st;  // stream of the pair-kernel launches
   double* ovf_base = ctx->d_pair_ovf;  // overflow clouds of the launch (one region per concurrent launch)
   if (ctx->h_nbr_chunked) {
@@ -658,37 +662,35 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     }
     pst = st;
     ovf_base = ctx->d_pair_ovf;
-  } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && p.K > p.first_slots && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
-    // LARGE SWARM, TWO SLICES.  Slice 1 = the p.first_slots nearest neighbour slots of every agent (where the inside pairs are).
-    // When it has finished, the queue length is recorded and an EARLY hull launch on its own stream works on those entries on
-    // the overlap_sms SMs that slice 2 (all the other slots, the bulk of the pairs) leaves free; one hull is a ~1 ms sequential
-    // job (qhull's insertion order), which this takes off the critical path of the step.  No kernel waits for another one:
-    // the early launch only takes tickets below the recorded length, the wide launch after slice 2 takes whatever is left.
+  } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
+    // LARGE SWARM: the hull queue gets a CONCURRENT CONSUMER.  A polling hull launch (k_hull, poll = 1) goes first, on its own
+    // stream and on overlap_sms SMs that its shared-memory request fills; the pair kernel runs next to it on the other SMs and
+    // hands out the nearest neighbour slots first (slot-major enumeration, narrow batches), so an inside pair reaches a hull
+    // warp within the first tenth of the pair kernel and its hull -- a ~1 ms sequential job (qhull's insertion order) -- runs
+    // under the rest of the pair kernel instead of behind it.  The wide launch after the pair kernel takes what is left.
     if (!ctx->hull_stream) {
       CU(cudaStreamCreateWithFlags(&ctx->hull_stream, cudaStreamNonBlocking));
       CU(cudaEventCreate(&ctx->ev_slice));
       CU(cudaEventCreate(&ctx->ev_early));
       CU(cudaEventCreate(&ctx->ev_early0));
     }
-    const int first = (int)(slot_major_first(p.n_local, p.K, p.first_slots) / 32);
-    // pairs per batch of the first slice: narrow enough for ~3 batches per pair warp of the grid (a batch is one warp's sequential job)
+    pair_grid = ctx->pair_blocks - ctx->overlap_sms;
+    // batches of the nearest 8 slots: narrow enough for >= 6 batches per pair warp of the grid (a batch is one warp's sequential job)
+    const long long narrow = slot_major_prefix(p.n_local, p.K, p.first_slots, 8);
     int bw = 32;
-    while (bw > 4 && (long long)first * (32 / bw) < 3LL * ctx->pair_blocks * ctx->pair_warps) bw >>= 1;
-    sy.batch_begin = 0; sy.batch_end = first * (32 / bw); sy.batch_width = bw;
-    LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
-    sy.batch_width = 32;
-    CU(cudaMemcpyAsync(ctx->d_ctr + 7, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    CU(cudaEventRecord(ctx->ev_slice, st));
+    while (bw > 2 && narrow / bw < 6LL * pair_grid * ctx->pair_warps) bw >>= 1;
+    sy.narrow_pairs = (int)narrow; sy.batch_width = bw;
+    CU(cudaEventRecord(ctx->ev_slice, st));  // counters cleared, previous step finished
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_slice, 0));
     CU(cudaEventRecord(ctx->ev_early0, ctx->hull_stream));
-    LQRO_LAUNCH_HULL(std::min(ctx->hull_per_sm * ctx->overlap_sms, ctx->hull_blocks), ctx->hull_stream, ctx->d_ctr + 7, ctx->d_ctr + 4,
-                     ctx->pair_warps * (2 * ctx->pair_blocks - ctx->overlap_sms));  // pair warps of both slices
+    k_hull<<<ctx->overlap_sms, 32 * ctx->hull_poll_warps, ctx->smem_optin, ctx->hull_stream>>>(
+        p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8, ctx->d_hull_ws,
+        ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
     CU(cudaEventRecord(ctx->ev_early, ctx->hull_stream));
-    sy.batch_counter = ctx->d_ctr + 6; sy.batch_begin = first; sy.batch_end = -1;
-    pair_grid = ctx->pair_blocks - ctx->overlap_sms;
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     pair_grid = ctx->pair_blocks;
-    pair_launches += 2;
+    sy.narrow_pairs = 0; sy.batch_width = 32;
+    ++pair_launches;
     hull_early = 1;
   } else if (!ctx->hetero) {
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
@@ -711,7 +713,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   if (hull_early) CU(cudaStreamWaitEvent(st, ctx->ev_early, 0));
-  LQRO_LAUNCH_HULL(ctx->hull_blocks, st, (const int*)nullptr, (const int*)nullptr, 0);
+  k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
+                                                       ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));
   if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {

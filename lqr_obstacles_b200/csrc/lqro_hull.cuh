@@ -33,8 +33,8 @@ __host__ __device__ inline size_t hull_warp_smem_bytes(int H, int P) {
 // the stand-alone hull kernel keeps only the ellipsoid samples (SoA, 3P doubles) in shared memory: the horizon tables are read
 // from global memory (13-19 KB shared by every hull of the GPU, L1 / L2 resident; they are only needed while the cloud is
 // regenerated), which is what lets a second (H = 30) or third (H = 20) hull block fit on an SM
-__host__ __device__ inline size_t hull_block_smem_bytes(int H, int P) {
-  return hull_align16(sizeof(double) * 3 * (size_t)P) + hull_warp_smem_bytes(H, P);
+__host__ __device__ inline size_t hull_block_smem_bytes(int H, int P, int warps = 1) {
+  return hull_align16(sizeof(double) * 3 * (size_t)P) + (size_t)warps * hull_warp_smem_bytes(H, P);
 }
 __device__ __forceinline__ void hull_warp_setup(HullWarp& hw, char* sm, char* gslot, int H, int P) {
   double* wb = reinterpret_cast<double*>(sm);
@@ -121,46 +121,81 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
   hull_finish_pair(w, ctl, pw, out, pair, n, counters, prof);
 }
 
-// Hull kernel: one warp (= one block) per queued inside pair at a time, tickets from a shared counter.  Launched twice per
-// step of a large swarm: EARLY, on its own stream and on a few SMs, next to the second slice of the pair kernel -- it may take
-// the tickets below *limit only, the queue length recorded when the first slice had finished (every entry below it is complete;
-// nothing here waits for a producer; once every pair warp of the step has signed off -- producers_done == producers_total --
-// it stops taking tickets, so that the wide launch takes over at full width instead of a few blocks working through a long queue)
-// -- and WIDE after the pair kernel, for whatever is left (limit == NULL: the final length).
-__global__ void __launch_bounds__(32, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
-                                             PairOutputs out, HullQueue hq, int* __restrict__ work_counter, const int* __restrict__ limit,
-                                             const int* __restrict__ producers_done, int producers_total,
+// Hull kernel: one warp per queued inside pair at a time, tickets from a shared counter.  Launched twice per step of a large
+// swarm:
+//  * POLLING (poll != 0), on its own stream and BEFORE the pair kernel, as a concurrent consumer of the hull queue on a few SMs
+//    of its own: LQRO_HULL_POLL_WARPS independent hull warps per block, whose shared memory fills an SM, so that no pair CTA can
+//    share it (a hull is a latency-bound dependent chain: next to 20 pair warps it runs 2.5x slower) -- the pair kernel's grid
+//    is that many SMs short.  A polling warp takes ticket h only when the published queue length exceeds h (compare-and-swap on
+//    the head), so a ticket in hand always has a producer behind it that stores the pair id within microseconds: nothing here
+//    can wait for a launch that does not come.  It leaves when every pair warp of the step has signed off (producers_done ==
+//    producers_total; what is still queued then goes to the wide launch at full width), or when no pair CTA has come up within
+//    2 ms of its own start (launches serialised by a profiler or CUDA_LAUNCH_BLOCKING: the wide launch then does all the work).
+//  * WIDE (poll == 0) after the pair kernel, one warp per block, for whatever is left in the queue.
+// Every consumer puts -1 back into the queue entry it has read: that is the "not published yet" value the next step's pollers
+// rely on (the queue is filled with -1 once, when the context is created).
+#define LQRO_HULL_POLL_WARPS 3
+__device__ __forceinline__ unsigned long long hull_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(32 * LQRO_HULL_POLL_WARPS, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+                                             PairOutputs out, HullQueue hq, int* __restrict__ work_counter, int poll,
+                                             const int* __restrict__ producers_done, int producers_total, const int* __restrict__ producers_started,
                                              char* __restrict__ ws_base, size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
                                              const int* __restrict__ agent_class /* NULL: one class */, const LqroTables* __restrict__ class_tables) {
   extern __shared__ double smem[];
-  const int lane = lane_id();
-  int nq = limit ? *limit : *hq.count;
-  if (nq > hq.capacity) nq = hq.capacity;
-  if (*(volatile int*)work_counter + (int)blockIdx.x >= nq) return;  // nothing can be left for this block
+  const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   PairTables pt;
   {
     const int P = p.P;
-    for (int e = lane; e < P; e += 32) { smem[e] = tb.sph[3 * e]; smem[P + e] = tb.sph[3 * e + 1]; smem[2 * P + e] = tb.sph[3 * e + 2]; }
-    __syncwarp();
+    for (int e = threadIdx.x; e < P; e += blockDim.x) { smem[e] = tb.sph[3 * e]; smem[P + e] = tb.sph[3 * e + 1]; smem[2 * P + e] = tb.sph[3 * e + 2]; }
+    __syncthreads();   // the only block-wide step: from here on the warps of a block are independent
     pt.NFt = tb.NFt; pt.T = tb.T; pt.CG = tb.CG; pt.prn = tb.prn;
     pt.sphx = smem; pt.sphy = smem + P; pt.sphz = smem + 2 * P;
   }
+  const int slot = blockIdx.x * wpb + warp;
+  int nq = 0;
+  if (!poll) {
+    nq = *hq.count;
+    if (nq > hq.capacity) nq = hq.capacity;
+    if (*(volatile int*)work_counter + slot >= nq) return;  // nothing can be left for this warp
+  }
   HullWarp hw;
-  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * 3 * (size_t)p.P), ws_base + ws_stride * (size_t)blockIdx.x, p.H, p.P);
+  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * 3 * (size_t)p.P) + (size_t)warp * hull_warp_smem_bytes(p.H, p.P),
+                  ws_base + ws_stride * (size_t)slot, p.H, p.P);
   int loaded = agent_class ? -1 : 0;
+  const unsigned long long t_start = poll ? hull_globaltimer() : 0ull;
   while (true) {
-    int item = 0;
+    int item = -1;
     if (lane == 0) {
-      if (producers_done && *(volatile const int*)producers_done >= producers_total) item = nq;  // pair kernel finished: leave the rest to the wide launch
-      else {
+      if (!poll) {
         item = atomicAdd(work_counter, 1);
-        if (item >= nq) atomicSub(work_counter, 1);  // hand the ticket back: a later launch continues from the true head
+        if (item >= nq) { atomicSub(work_counter, 1); item = -1; }
+      } else {
+        while (true) {
+          if (*(volatile const int*)producers_done >= producers_total) break;  // pair kernel finished: the rest goes to the wide launch
+          int c = *(volatile int*)hq.count;
+          if (c > hq.capacity) c = hq.capacity;
+          const int h = *(volatile int*)work_counter;
+          if (h < c) {
+            if (atomicCAS(work_counter, h, h + 1) == h) { item = h; break; }
+            continue;
+          }
+          if (*(volatile const int*)producers_started == 0 && hull_globaltimer() - t_start > 2000000ull) break;
+          __nanosleep(256);
+        }
       }
     }
     item = __shfl_sync(LQRO_FULL, item, 0);
-    if (item >= nq) break;
-    const int pair = hq.items[item];
-    if (pair < 0) continue;
+    if (item < 0) break;
+    int pair = -1;
+    if (lane == 0) {
+      while ((pair = *(volatile int*)(hq.items + item)) < 0) __nanosleep(32);  // published right after the slot was taken (k_pairs)
+      hq.items[item] = -1;
+    }
+    pair = __shfl_sync(LQRO_FULL, pair, 0);
     if (agent_class) {  // heterogeneous dynamics: the obstacle of pair (i, j) uses agent i's class (MAIN:1384)
       const int c = agent_class[p.local_begin + pair / p.K];
       if (c != loaded) { const LqroTables tc = class_tables[c]; pt.NFt = tc.NFt; pt.T = tc.T; pt.CG = tc.CG; pt.prn = tc.prn; loaded = c; }

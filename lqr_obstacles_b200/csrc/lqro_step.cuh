@@ -47,24 +47,27 @@ __host__ __device__ inline size_t pair2_warp_doubles(int H) {
 }
 
 struct StepSync {
-  int* batch_counter;   // next batch of pairs of this launch (relative to batch_begin)
-  int batch_begin, batch_end;  // batches [begin, end) of the slot-major enumeration belong to this launch (end < 0: to the last one)
-  int batch_width;             // pairs per batch: 32, or 16 / 8 / 4 for a first slice with few agents -- a batch is walked by ONE warp pair
-                               // after pair in stage 2 (~8 us per near-neighbour pair), so 32-pair batches put a 0.25 ms floor under a
-                               // slice that has fewer batches than the grid has warps
+  int* batch_counter;   // next batch of pairs of this launch
+  int narrow_pairs;     // the first narrow_pairs pairs of the slot-major enumeration (a multiple of 32) go out in batches of
+  int batch_width;      // batch_width pairs (32, 16, 8, 4 or 2), the rest in batches of 32: a batch is walked by ONE warp, pair after pair
+                        // in stage 2 (8 - 30 us per near-neighbour pair), so for a rank with few agents 32-pair batches of the nearest
+                        // slots would be 0.25 - 1 ms sequential jobs of a few warps while the rest of the grid idles -- and the inside
+                        // pairs, whose hulls are the critical path of such a step, would surface late
+  int* started;         // pair CTAs that have come up (the polling hull launch gives up when none does, see k_hull)
   int* hull_head;       // next hull ticket
   int* done_warps;      // pair warps that have finished
   int* counters;        // misc counters (degenerate, fallback, ...)
   long long* prof;
 };
 
-// slot-major enumeration: the first chunk covers the p.first_slots nearest neighbour slots of every agent, the following
-// ones 32 slots each; within a chunk pairs are agent-major.  Neighbour lists are sorted by distance, so the inside pairs -- the
-// ones that need a hull -- sit in the first chunk: the step launches it as its own slice of the pair kernel and starts hulling
-// its queue while the rest of the pairs are still being processed (launch_step).
+// slot-major enumeration: the first chunk covers the p.first_slots nearest neighbour slots of every agent, the following ones
+// double in width up to 32 slots (first_slots = 1: slots 0 | 1 | 2-3 | 4-7 | 8-15 | 16-31 | 32-63); within a chunk pairs are
+// agent-major.  Neighbour lists are sorted by distance, so the inside pairs -- the ones that need a hull, a ~1 ms sequential
+// job each -- sit in the first chunks and reach the hull queue in the first tenth of the pair kernel, where the polling hull
+// launch picks them up (launch_step).
 // idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end (chunks start on a batch boundary).
 __host__ __device__ inline int slot_chunk_width(int K, int c0, int first) {
-  const int w = (c0 == 0) ? first : 32;
+  const int w = (c0 == 0) ? first : (c0 < 32 ? c0 : 32);
   return (K - c0 < w) ? (K - c0) : w;
 }
 __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long idx, int& il, int& kk) {
@@ -89,9 +92,11 @@ __host__ __device__ inline long long slot_major_total(int n_local, int K, int fi
   for (int c0 = 0; c0 < K; c0 += slot_chunk_width(K, c0, first)) t += (((long long)n_local * slot_chunk_width(K, c0, first)) + 31) & ~31ll;
   return t;
 }
-// pairs (padded to batches) of the first chunk
-__host__ __device__ inline long long slot_major_first(int n_local, int K, int first) {
-  return (((long long)n_local * slot_chunk_width(K, 0, first)) + 31) & ~31ll;
+// pairs (padded to batches) of the chunks that start below slot `slots`
+__host__ __device__ inline long long slot_major_prefix(int n_local, int K, int first, int slots) {
+  long long t = 0;
+  for (int c0 = 0; c0 < K && c0 < slots; c0 += slot_chunk_width(K, c0, first)) t += (((long long)n_local * slot_chunk_width(K, c0, first)) + 31) & ~31ll;
+  return t;
 }
 
 #ifdef LQRO_PAIR_PROF  // per-phase cycle counts of the pair warps (lane 0), profiling builds only
@@ -176,17 +181,19 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
-  const long long total_all = slot_major_total(p.n_local, p.K, p.first_slots);
-  const int bw = sy.batch_width;
-  const long long total = (sy.batch_end >= 0 && (long long)sy.batch_end * bw < total_all) ? (long long)sy.batch_end * bw : total_all;
+  const long long total = slot_major_total(p.n_local, p.K, p.first_slots);
+  const int nbw = sy.batch_width;
+  const int narrow_batches = sy.narrow_pairs / nbw;
+  if (threadIdx.x == 0 && sy.started) atomicAdd(sy.started, 1);
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
   while (true) {
     int batch = 0;
     if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
-    batch = __shfl_sync(LQRO_FULL, batch, 0) + sy.batch_begin;
-    const long long base = (long long)batch * bw;
+    batch = __shfl_sync(LQRO_FULL, batch, 0);
+    const int bw = batch < narrow_batches ? nbw : 32;
+    const long long base = batch < narrow_batches ? (long long)batch * nbw : (long long)sy.narrow_pairs + (long long)(batch - narrow_batches) * 32;
     if (base >= total) break;
     // ---------------- stage 1: lane = pair
     int il = 0, kk = 0;

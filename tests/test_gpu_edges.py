@@ -127,7 +127,7 @@ def test_maximum_reachable_cloud(golden, oracle, product_lib):
 def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
     """LQRO_FLAG_NO_OVERLAP: host-buffer steps of >= 2^20 pairs upload the neighbour table in blocks overlapped with the pair
     kernel (one launch per block): same planes, statuses and velocities as the single-launch path fed with a resident table --
-    and as the default step of a large swarm (pair kernel in two slices, early hull launch next to the second one)"""
+    and as the default step of a large swarm (polling hull launch as a concurrent consumer next to the pair kernel)"""
     from lqr_obstacles_b200.api import FLAG_NO_OVERLAP
 
     x, vp = swarm.lattice_swarm((32, 32, 16))
@@ -142,9 +142,9 @@ def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
     assert a.counters()["launches"] == 3
     assert np.array_equal(v1, v2) and np.array_equal(r1["status"], r2["status"]) and np.array_equal(r1["nreach"], r2["nreach"])
     b = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
-    v3 = b.step(x, vp, nbr).copy()          # default: two slices + early hull launch + wide hull launch + LP
+    v3 = b.step(x, vp, nbr).copy()          # default: polling hull launch + pair kernel + wide hull launch + LP
     r3 = b.pair_results()
-    assert b.counters()["launches"] == 5
+    assert b.counters()["launches"] == 4
     assert np.array_equal(v3, v2) and np.array_equal(r3["status"], r2["status"]) and np.array_equal(r3["nreach"], r2["nreach"])
     has3 = (r3["status"] & 0xFF) != 0
     assert np.array_equal(r3["planes"][has3], r2["planes"][has3])

@@ -19,7 +19,7 @@ print("classes ok", ctx.counters(), float(v.sum()))
 pl, vt, deg = ctx.convex_hull(g["qh_points"])
 print("hull ok", len(pl), deg)
 ctx.close()
-# a step large enough for the two-slice path (pair kernel in two slices, early hull launch on its own stream, wide hull launch)
+# a step large enough for the polling hull launch (concurrent consumer on its own stream next to the pair kernel, wide hull launch)
 x, vp = swarm.lattice_swarm((16, 16, 8)); x[:, :3] *= 0.6
 nbr = swarm.knn(x[:, :3], 64)
 ctx = Lqro(n_agents=len(x), max_neighbors=64, horizon=20)
