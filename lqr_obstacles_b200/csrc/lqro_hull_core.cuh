@@ -48,6 +48,11 @@
 #ifndef LQRO_HULL_NARROW_WALK_MAX
 #define LQRO_HULL_NARROW_WALK_MAX 64
 #endif
+// Appends into a cone of up to LQRO_HULL_SMALLKEY_MAX (<= 32) facets find their buckets with ballots over the bits of the cone-local
+// facet index, larger cones (and targets outside the cone) with a shuffle sweep over the facet ids.
+#ifndef LQRO_HULL_SMALLKEY_MAX
+#define LQRO_HULL_SMALLKEY_MAX 32
+#endif
 
 // ---- strtod(printf("%g", x)): nearest double to the 6-significant-digit decimal rendering of x ------
 #if defined(LQRO_HULL_HOST_EMUL)
@@ -122,9 +127,10 @@ struct __align__(16) HTopo {
   hidx born;   // (insertion that created it << 1) | toporient;  < 0: not alive
   hidx vst;    // (insertion that tested it for visibility << 1) | visible
 };
-struct __align__(16) HOut {   // outside list of a facet (points linked through pnext, furthest last)
+struct __align__(16) HOut {   // outside set of a facet: olist[ostart .. ostart + ocount), in qhull's list order, the furthest point LAST
   double fdist;
-  hidx ohead, olast, oprev, ocount;
+  int ostart;
+  hidx ocount, pad_;
 };
 struct __align__(8) HMeta {
   int seq;   // position key in qhull's facet list (creation order; a facet moved to the tail gets a new key)
@@ -134,7 +140,7 @@ struct __align__(8) HMeta {
 struct HullWs {
   double *hx, *hy, *hz;   // hull input coordinates [cap_pts]
   double *ux, *uy, *uz;   // un-rounded cloud [cap_pts]                  (global)
-  hidx *pnext, *vpoint;   // [cap_pts + 8]   outside-list links, vertex id -> point               (hot)
+  hidx *olist, *vpoint;   // olist [ocap = 2 cap_pts]: the outside sets, one contiguous segment per facet, bump-allocated, compacted when full; vpoint [cap_pts + 8]: vertex id -> point   (hot)
   double* pdist;          // [cap_pts]       partition scratch                                       (cold: global slot)
   hidx *plist, *pstart, *pbest;  // [cap_pts + 8]                                                    (cold)
   HPlane* pl; HTopo* tp; HOut* ot; HMeta* mt;     // [cap_f]
@@ -143,7 +149,7 @@ struct HullWs {
   hidx *order;            // [cap_f] facets in qhull's list order, stage kernel only                    (cold)
   hidx *newf;             // [LQRO_HULL_MAXNEW]
   int* vown;              // [cap_pts + 8] ridge matching of large cones: cone facet that last touched vertex id v (-1 = none)   (cold)
-  int cap_pts, cap_f, ring_mask;
+  int cap_pts, cap_f, ring_mask, ocap;
 };
 
 __host__ __device__ inline size_t hull_align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -157,7 +163,7 @@ __host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   b += hull_align16(sizeof(HOut) * (size_t)cap_f);
   b += hull_align16(sizeof(HMeta) * (size_t)cap_f);
   b += hull_align16(3 * sizeof(double) * (size_t)cap_pts);              // hx hy hz (hull input coordinates)
-  b += hull_align16(sizeof(hidx) * 2 * ((size_t)cap_pts + 8));          // pnext vpoint
+  b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_pts + 8));          // olist vpoint
   b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + (size_t)hull_ring_size(cap_f) + LQRO_HULL_MAXNEW));  // aux vis freel ring newf
   return b;
 }
@@ -191,9 +197,9 @@ __device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_
   w.hx = d; w.hy = d + cap_pts; w.hz = d + 2 * (size_t)cap_pts;
   base += hull_align16(3 * sizeof(double) * (size_t)cap_pts);
   hidx* ip = reinterpret_cast<hidx*>(base);
-  const size_t ci = (size_t)cap_pts + 8;
-  w.pnext = ip; w.vpoint = ip + ci;
-  base += hull_align16(sizeof(hidx) * 2 * ci);
+  w.ocap = 2 * cap_pts;
+  w.olist = ip; w.vpoint = ip + 2 * (size_t)cap_pts;
+  base += hull_align16(sizeof(hidx) * (3 * (size_t)cap_pts + 8));
   hidx* jp = reinterpret_cast<hidx*>(base);
   w.aux = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f;
   w.ring = jp + 3 * (size_t)cap_f; w.newf = w.ring + rs;
@@ -235,9 +241,10 @@ struct HullCtl {
 
 // rare-path coverage counters of the host (emulation) build: 0 cone > 16 facets (vown matching), 1 cone > 64 (wide visited
 // set), 2 exhaustive mode triggered, 3 old facet moved to the tail, 4 ring compaction, 5 horizon flood, 6 multi-chunk partition,
-// 7 multi-chunk horizon wave
+// 7 multi-chunk horizon wave, 8 outside-set storage compacted, 9 append to a facet that already has points (segment moved),
+// 10 buckets of an append found by the shuffle sweep (targets outside the cone / cone > 32 facets), 11 gather through the cold arrays
 #if defined(LQRO_HULL_HOST_EMUL)
-static long long g_hull_cover[8];
+static long long g_hull_cover[12];
 #define HULL_COVER(q) { if (lane_id() == 0) ++g_hull_cover[q]; }
 #else
 #define HULL_COVER(q) { }
@@ -381,6 +388,137 @@ __device__ __forceinline__ void hull_walk(const HullWs& w, int ins, double MINou
   if (state == 1 && bestdist < -DISTr) state = 2;
 }
 
+// ---- outside sets as contiguous segments ------------------------------------------------------------
+// qhull keeps the outside set of a facet as a list with the furthest point last; a point joins it either at the end (new
+// furthest: d > furthestdist, strictly) or in front of the last one (qh_partitionpoint / qh_setappend2ndlast, and the same rule
+// in qh_partitionall).  Replaying k arrivals on a list [rest, L] therefore yields [rest, e_1 .. e_k, F]: e_j is the arrival itself
+// when it set no record and the record holder it displaced when it did, F the final holder.  With the list stored as a
+// segment of w.olist that is a data-parallel write once every arrival knows the running maximum over the EARLIER arrivals of its
+// facet -- a segmented prefix maximum over the lanes of a bucket (pointer jumping along the previous lane of the same bucket),
+// ties to the earlier arrival as the strict comparison demands.
+
+// all live segments to the front of w.olist (through w.pbest, free outside the initial partition); facets that are being
+// deleted (visible in this insertion: vst == vvis) are garbage already.  Returns the new bump pointer.  Rare and out of line: scalars
+// only, so that the caller keeps its workspace pointers in registers and in the shared-memory address space.
+__device__ __noinline__ int hull_olist_compact(const HTopo* tp, HOut* ot, hidx* olist, hidx* pbest, int pool_used, int vvis) {
+  const int lane = lane_id();
+  HULL_COVER(8)
+  int off = 0;
+  for (int f0 = 0; f0 < pool_used; f0 += 32) {
+    const int f = f0 + lane;
+    int cnt = 0;
+    HOut O; O.fdist = 0; O.ostart = 0; O.ocount = 0; O.pad_ = 0;
+    if (f < pool_used) {
+      const HTopo T = tp[f];
+      if (T.born >= 0 && T.vst != vvis) { O = ot[f]; cnt = O.ocount; }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(LQRO_FULL, incl, o); if (lane >= o) incl += t; }
+    const int ns = off + incl - cnt;
+    for (int q = 0; q < cnt; ++q) pbest[ns + q] = olist[O.ostart + q];
+    if (cnt > 0) { O.ostart = ns; ot[f] = O; }
+    off += __shfl_sync(LQRO_FULL, incl, 31);
+  }
+  __syncwarp();
+  for (int q = lane; q < off; q += 32) olist[q] = pbest[q];
+  __syncwarp();
+  return off;
+}
+
+// One chunk of arrivals (lane = arrival, lane order = qhull's processing order): lane `has` brings point p at distance d to facet
+// f; peers = the lanes of the chunk with the same facet (0 for lanes without an arrival).  inplace: the segment of f already has
+// room behind it (initial partition); otherwise the bucket gets a fresh segment at the bump pointer and whatever f holds already
+// moves there (rare: an old facet reached through the horizon test, a second chunk of a long partition).  Returns the number of
+// points f held before (meaningful on the lanes with an arrival).  Every lane must call.
+__device__ __forceinline__ int hull_bucket_append(const HullWs& w, bool has, int f, unsigned peers, int p, double d, bool inplace, int pool_used,
+                                                  int vvis, int& obump, int& failcode) {
+  const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  const int r = __popc(peers & lt), k = __popc(peers);
+  const bool leader = has && r == 0;
+  HOut S; S.fdist = 0; S.ostart = 0; S.ocount = 0; S.pad_ = 0;
+  int L = -1;
+  if (leader) { S = w.ot[f]; if (S.ocount > 0) L = w.olist[S.ostart + S.ocount - 1]; }
+  int base = S.ostart;
+  if (!inplace) {
+    const int need = leader ? S.ocount + k : 0;
+    int incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(LQRO_FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(LQRO_FULL, incl, 31);
+    if (obump + total > w.ocap) {
+      obump = hull_olist_compact(w.tp, w.ot, w.olist, w.pbest, pool_used, vvis);
+      if (leader) S.ostart = w.ot[f].ostart;
+      if (obump + total > w.ocap) { failcode = 2; return 0; }  // cannot happen: live + moved + arriving <= 2 n
+    }
+    base = obump + incl - need;
+    obump += total;
+    if (leader && S.ocount > 1) {
+      HULL_COVER(9)
+      for (int q = 0; q + 1 < S.ocount; ++q) w.olist[base + q] = w.olist[S.ostart + q];
+    }
+  }
+  // the bucket learns its leader's state
+  const int ld = has ? __ffs(peers) - 1 : lane;
+  const int c = __shfl_sync(LQRO_FULL, (int)S.ocount, ld);
+  const double f0 = __shfl_sync(LQRO_FULL, S.fdist, ld);
+  const int L0 = __shfl_sync(LQRO_FULL, L, ld);
+  const int b0 = __shfl_sync(LQRO_FULL, base, ld);
+  // inclusive running maximum over the bucket's lanes up to this one (pointer jumping; ties stay with the earlier lane)
+  const int prev = (peers & lt) ? 31 - __clz((int)(peers & lt)) : -1;
+  double md = has ? d : -1.7976931348623157e308;
+  int mp = p;
+  {
+    const int mk = __reduce_max_sync(LQRO_FULL, k);
+    int pj = prev;
+    for (int span = 1; span < mk; span <<= 1) {
+      const int src = pj >= 0 ? pj : lane;
+      const double od = __shfl_sync(LQRO_FULL, md, src);
+      const int op = __shfl_sync(LQRO_FULL, mp, src);
+      const int nj = __shfl_sync(LQRO_FULL, pj, src);
+      if (pj >= 0) { if (!(md > od)) { md = od; mp = op; } pj = nj; }
+    }
+  }
+  // record before this arrival: what the facet held (earliest of all), then the earlier lanes of the bucket
+  double mb = c > 0 ? f0 : -1.7976931348623157e308;
+  int hb = L0;
+  {
+    const double ed = __shfl_sync(LQRO_FULL, md, prev >= 0 ? prev : lane);
+    const int ep = __shfl_sync(LQRO_FULL, mp, prev >= 0 ? prev : lane);
+    if (prev >= 0 && ed > mb) { mb = ed; hb = ep; }
+  }
+  // final record of the bucket
+  double ma = c > 0 ? f0 : -1.7976931348623157e308;
+  int ha = L0;
+  {
+    const int last = has ? 31 - __clz((int)peers) : lane;
+    const double ad = __shfl_sync(LQRO_FULL, md, last);
+    const int ap = __shfl_sync(LQRO_FULL, mp, last);
+    if (has && ad > ma) { ma = ad; ha = ap; }
+  }
+  if (has) {
+    if (c > 0 || r > 0) w.olist[b0 + c - 1 + r] = (hidx)((d > mb) ? hb : p);
+    if (r == 0) {
+      w.olist[b0 + c + k - 1] = (hidx)ha;
+      HOut N; N.fdist = ma; N.ostart = b0; N.ocount = (hidx)(c + k); N.pad_ = 0;
+      w.ot[f] = N;
+    }
+  }
+  return c;
+}
+
+// lanes with the same small key (0 <= key < 2^nbits): ballots over the key's bits
+__device__ __forceinline__ unsigned hull_peers_small(bool has, int key, int nbits) {
+  unsigned peers = __ballot_sync(LQRO_FULL, has);
+  for (int b = 0; b < nbits; ++b) {
+    const bool bit = (key >> b) & 1;
+    const unsigned B = __ballot_sync(LQRO_FULL, bit);
+    peers &= bit ? B : ~B;
+  }
+  return has ? peers : 0u;
+}
+
 #if defined(LQRO_HULL_PROF)
 #define HULL_TIC(q) { if (lane == 0) { const long long tn_ = clock64(); hprof[q] += tn_ - tprof; tprof = tn_; } }
 #define HULL_COUNT(q, v) { if (lane == 0) hprof[q] += (v); }
@@ -522,13 +660,16 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
   const double searchdist = 2 * DISTround + (MINvisible > MAXcoplanar ? MINvisible : MAXcoplanar);
   const double in0 = c.interior[0], in1 = c.interior[1], in2 = c.interior[2];
   int degen = 0;
-  // ---- qh_partitionall: first facet (list order) a point is outside of; distances in parallel
+  // ---- qh_partitionall: first facet (list order) a point is outside of; the four outside sets are built chunk by chunk
+  int obump = 0, failc = 0;
   {
     const int v0 = w.vpoint[0], v1 = w.vpoint[1], v2 = w.vpoint[2], v3 = w.vpoint[3];
     const HPlane P0 = w.pl[0], P1 = w.pl[1], P2 = w.pl[2], P3 = w.pl[3];
-    for (int i = lane; i < n; i += 32) {
+    int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
       int bestf = -1; double bd = 0;
-      if (i != v0 && i != v1 && i != v2 && i != v3) {
+      if (i < n && i != v0 && i != v1 && i != v2 && i != v3) {
         const double x = w.hx[i], y = w.hy[i], z = w.hz[i];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -537,34 +678,29 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
           if (d >= distoutside) { bestf = q; bd = d; break; }
         }
       }
-      w.pbest[i] = (hidx)bestf; w.pdist[i] = bd;
+      if (i < n) { w.pbest[i] = (hidx)bestf; w.pdist[i] = bd; }
+      cnt0 += __popc(__ballot_sync(LQRO_FULL, bestf == 0)); cnt1 += __popc(__ballot_sync(LQRO_FULL, bestf == 1));
+      cnt2 += __popc(__ballot_sync(LQRO_FULL, bestf == 2)); cnt3 += __popc(__ballot_sync(LQRO_FULL, bestf == 3));
     }
-    __syncwarp();
-    // the four lists, one lane each: points in index order, every record holder placed at the end of its reign
     if (lane < 4) {
-      int bestpoint = -1, tail = -1, head = -1, cnt = 0;
-      double bestdist = 0;
-      for (int i = 0; i < n; ++i) {
-        if (w.pbest[i] != lane) continue;
-        const double d = w.pdist[i];
-        int emit = -1;
-        if (bestpoint < 0) { bestpoint = i; bestdist = d; }
-        else if (d > bestdist) { emit = bestpoint; bestpoint = i; bestdist = d; }
-        else emit = i;
-        if (emit >= 0) { if (tail < 0) head = emit; else w.pnext[tail] = (hidx)emit; tail = emit; }
-        ++cnt;
-      }
-      HOut O; O.fdist = 0; O.ohead = O.olast = O.oprev = -1; O.ocount = (hidx)cnt;
-      if (bestpoint >= 0) {
-        if (tail < 0) head = bestpoint; else w.pnext[tail] = (hidx)bestpoint;
-        O.ohead = (hidx)head; O.oprev = (hidx)tail; O.olast = (hidx)bestpoint; O.fdist = bestdist;
-      }
+      HOut O; O.fdist = 0; O.ocount = 0; O.pad_ = 0;
+      O.ostart = lane == 0 ? 0 : lane == 1 ? cnt0 : lane == 2 ? cnt0 + cnt1 : cnt0 + cnt1 + cnt2;
       w.ot[lane] = O;
     }
+    obump = cnt0 + cnt1 + cnt2 + cnt3;
     __syncwarp();
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      int bestf = -1; double bd = 0;
+      if (i < n) { bestf = w.pbest[i]; bd = w.pdist[i]; }
+      const bool has = bestf >= 0;
+      const unsigned peers = hull_peers_small(has, bestf, 2);
+      hull_bucket_append(w, has, bestf, peers, i, bd, true, 4, -1, obump, failc);
+      __syncwarp();
+    }
   }
   // running state, identical in every lane
-  int nfree = 0, pool_used = 4, nverts = 4, ins = 0, qhead = 0, qtail = 0, seqctr = 4, failc = 0;
+  int nfree = 0, pool_used = 4, nverts = 4, ins = 0, qhead = 0, qtail = 0, seqctr = 4;
   {
     // ---- qh_furthestnext: the facet with the furthest outside point is processed first, then list order
     int bestfacet = -1; double bestdist = -1.7976931348623157e308;
@@ -600,13 +736,12 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
     double ax, ay, az;
     {
       const HOut O = w.ot[facet];
-      const int furthest = O.olast;
+      const int furthest = w.olist[O.ostart + O.ocount - 1];
       ax = w.hx[furthest]; ay = w.hy[furthest]; az = w.hz[furthest];
       if (lane == 0) {
         w.vpoint[nverts] = (hidx)furthest;  // the apex gets the next vertex id
         w.vis[0] = (hidx)facet;
         w.tp[facet].vst = vvis;
-        w.ot[facet].ocount = (hidx)(O.ocount - 1);  // the rest of its list is re-partitioned below
         w.aux[facet] = -1;
         w.mt[facet].qpos = -1;
       }
@@ -694,7 +829,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
                 w.tp[f] = NF;
                 w.tp[nb].nb[hs] = (hidx)f;
                 w.aux[f] = (hidx)r;  // cone-local index
-                HOut O; O.fdist = 0; O.ohead = O.olast = O.oprev = -1; O.ocount = 0;
+                HOut O; O.fdist = 0; O.ostart = 0; O.ocount = 0; O.pad_ = 0;
                 w.ot[f] = O;
                 HMeta M; M.seq = seqctr + 1 + r; M.qpos = -1;
                 w.mt[f] = M;
@@ -784,15 +919,56 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
     }
     HULL_TIC(4)
     // qh_partitionvisible, pass 1: the points to re-partition in qhull's processing order (visible facets in list
-    // order, each one's outside list in order).  One lane per visible facet walks its own list; the offsets come from
-    // a warp scan of the list lengths.
+    // order, each one's outside set in order).  Common case (<= 32 visible facets, <= 32 points): the lanes locate their point
+    // in the segments of the visible facets through a warp scan of the set sizes, nothing is staged.  Otherwise the
+    // points go through the cold arrays plist / pstart.
     int nl = 0;
-    {
-      const hidx newfirst = w.newf[0];
+    bool staged = true;
+    int gp = 0, gs = 0;
+    const hidx newfirst = w.newf[0];
+    if (nvis <= 32) {
+      int cnt = 0, ost = 0, sf = 0;
+      if (lane < nvis) {
+        const int vf = w.vis[lane];
+        const HOut O = w.ot[vf];
+        cnt = O.ocount - (lane == 0 ? 1 : 0);  // vis[0] is the facet being processed: its last point is the apex
+        ost = O.ostart;
+        const hidx rp = w.aux[vf];
+        sf = rp >= 0 ? rp : newfirst;
+      }
+      int incl = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(LQRO_FULL, incl, off);
+        if (lane >= off) incl += t;
+      }
+      nl = __shfl_sync(LQRO_FULL, incl, 31);
+      if (nl <= 32) {
+        staged = false;
+        // source facet of point `lane`: the number of visible facets whose sets end at or before it
+        int idx = 0;
+        if (nvis <= 6) {
+          for (int v = 0; v + 1 < nvis; ++v) idx += (__shfl_sync(LQRO_FULL, incl, v) <= lane) ? 1 : 0;
+        } else {
+#pragma unroll
+          for (int st = 16; st >= 1; st >>= 1) {
+            const int e = __shfl_sync(LQRO_FULL, incl, idx + st - 1);
+            if (e <= lane) idx += st;
+          }
+          if (idx > 31) idx = 31;
+        }
+        const int so = __shfl_sync(LQRO_FULL, ost, idx), se = __shfl_sync(LQRO_FULL, incl - cnt, idx);
+        gs = __shfl_sync(LQRO_FULL, sf, idx);
+        if (lane < nl) gp = w.olist[so + (lane - se)];
+      }
+    }
+    if (staged) {
+      HULL_COVER(11)
+      nl = 0;
       for (int v0 = 0; v0 < nvis; v0 += 32) {
         const int vi = v0 + lane;
-        int cnt = 0, vf = 0, head = -1;
-        if (vi < nvis) { vf = w.vis[vi]; const HOut O = w.ot[vf]; cnt = O.ocount; head = O.ohead; }
+        int cnt = 0, vf = 0, ost = 0;
+        if (vi < nvis) { vf = w.vis[vi]; const HOut O = w.ot[vf]; cnt = O.ocount - (vi == 0 ? 1 : 0); ost = O.ostart; }
         int incl = cnt;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -803,13 +979,12 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         if (cnt > 0) {
           const hidx rp = w.aux[vf];
           const hidx start = rp >= 0 ? rp : newfirst;
-          int p = head;
-          for (int t = 0; t < cnt; ++t) { w.plist[pos] = (hidx)p; w.pstart[pos] = start; ++pos; p = w.pnext[p]; }
+          for (int t = 0; t < cnt; ++t) { w.plist[pos] = w.olist[ost + t]; w.pstart[pos] = start; ++pos; }
         }
         nl += __shfl_sync(LQRO_FULL, incl, 31);
       }
+      __syncwarp();
     }
-    __syncwarp();
     HULL_TIC(5)
     HULL_COUNT(10, 1)
     HULL_COUNT(11, nl)
@@ -822,13 +997,17 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
       // yet; append (qh_partitionpoint).
       bool exh = false;
       int ldeg = 0;
+      const int cbits = nnew <= LQRO_HULL_SMALLKEY_MAX ? 32 - __clz(nnew - 1 > 0 ? nnew - 1 : 1) : 0;  // bits of a cone-local index
       for (int c0 = 0; c0 < nl; c0 += 32) {
         if (c0 > 0) HULL_COVER(6)
         const int q = c0 + lane;
         const bool valid = q < nl;
         int p = 0, start = 0, best = -1, state = 0;
         double x = 0, y = 0, z = 0, bestdist = 0;
-        if (valid) { p = w.plist[q]; start = w.pstart[q]; x = w.hx[p]; y = w.hy[p]; z = w.hz[p]; best = start; }
+        if (valid) {
+          if (staged) { p = w.plist[q]; start = w.pstart[q]; } else { p = gp; start = gs; }
+          x = w.hx[p]; y = w.hy[p]; z = w.hz[p]; best = start;
+        }
         int from = exh ? 0 : 32;
         bool trigger_chunk = false;
         if (!exh) {
@@ -865,37 +1044,28 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         }
         if (valid && fabs(bestdist) < 4 * MINoutside) degen = 1;
         HULL_TIC(7)
-        // append: appends to different facets commute, so the first lane of every target facet (bucket leader)
-        // replays its bucket in lane (= processing) order with the list state in registers
+        // append (qh_partitionpoint): appends to different facets commute; the lanes of one target facet form a bucket
+        // (hull_bucket_append).  Targets inside a cone of <= 32 facets are told apart by their cone-local index.
         const bool has = valid && best >= 0;
-        unsigned peers = 0u;
-        {
-          const int key = has ? best : -1 - lane;
+        bool cone = false;
+        int key = 0;
+        if (has) { cone = (w.tp[best].born >> 1) == ins; key = w.aux[best]; }
+        unsigned peers;
+        if (nnew <= LQRO_HULL_SMALLKEY_MAX && !__any_sync(LQRO_FULL, has && !cone)) {
+          peers = hull_peers_small(has, key, cbits);
+        } else {
+          HULL_COVER(10)
+          peers = 0u;
+          const int fk = has ? best : -1 - lane;
           const int cn = nl - c0 < 32 ? nl - c0 : 32;
-          for (int j = 0; j < cn; ++j) peers |= (unsigned)(__shfl_sync(LQRO_FULL, key, j) == key) << j;
+          for (int j = 0; j < cn; ++j) peers |= (unsigned)(__shfl_sync(LQRO_FULL, fk, j) == fk) << j;
+          if (!has) peers = 0u;
         }
-        const bool leader = has && (__ffs(peers) - 1) == lane;
-        HOut S; S.fdist = 0; S.ohead = S.olast = S.oprev = -1; S.ocount = 0;
-        bool moved = false;
-        if (leader) {
-          S = w.ot[best];
-          moved = S.ocount == 0 && (w.tp[best].born >> 1) != ins;  // an old facet gets its first point: qhull moves it to the tail
-        }
-        unsigned m = leader ? peers : 0u;
-        const int steps = (int)__reduce_max_sync(LQRO_FULL, (unsigned)__popc(m));
-        for (int it = 0; it < steps; ++it) {
-          const int src = m ? __ffs(m) - 1 : lane;
-          const int pt = __shfl_sync(LQRO_FULL, p, src);
-          const double d = __shfl_sync(LQRO_FULL, bestdist, src);
-          if (m) {
-            m &= m - 1;
-            if (S.olast < 0) { S.ohead = S.olast = (hidx)pt; S.oprev = -1; S.fdist = d; }
-            else if (S.fdist < d) { w.pnext[S.olast] = (hidx)pt; S.oprev = S.olast; S.olast = (hidx)pt; S.fdist = d; }
-            else { if (S.oprev >= 0) w.pnext[S.oprev] = (hidx)pt; else S.ohead = (hidx)pt; w.pnext[pt] = S.olast; S.oprev = (hidx)pt; }  // qh_setappend2ndlast
-            S.ocount++;
-          }
-        }
-        if (leader) w.ot[best] = S;
+        int fcode = 0;
+        const int cold = hull_bucket_append(w, has, best, peers, p, bestdist, false, pool_used, vvis, obump, fcode);
+        if (fcode) failc = fcode;
+        // an old facet gets its first point: qhull moves it to the tail of its facet list
+        const bool moved = has && (peers & lt) == 0u && cold == 0 && !cone;
         const unsigned mv = __ballot_sync(LQRO_FULL, moved);
         if (moved) w.vis[nvis + nmoved + __popc(mv & lt)] = (hidx)best;  // behind the visible list (disjoint sets of alive facets)
         nmoved += __popc(mv);
@@ -904,6 +1074,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         HULL_TIC(8)
       }
       if (__any_sync(LQRO_FULL, ldeg)) degen = 1;
+      if (failc) break;
     }
     // the pending ring: cone facets with points, in creation order, then the old facets that got their first point
     // (qhull moved those to the tail of its list afterwards), in the order of that point

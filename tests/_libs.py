@@ -451,10 +451,10 @@ class HullHost:
     infrastructure; the product never links it."""
 
     def __init__(self, general=False):
-        """general=True: the build that forces the general branches (owner-word ridge matching, wide visited set) on every
-        cone of more than 2 / 3 facets, so that small clouds exercise them"""
+        """general=True: the build that forces the general branches (owner-word ridge matching, wide visited set, shuffle-sweep
+        buckets of the appends) on every cone of more than 2 / 3 / 2 facets, so that small clouds exercise them"""
         so = HULLHOST_SO.replace(".so", "_general.so") if general else HULLHOST_SO
-        extra = ["-DLQRO_HULL_PAIRMATCH_MAX=2", "-DLQRO_HULL_NARROW_WALK_MAX=3"] if general else []
+        extra = ["-DLQRO_HULL_PAIRMATCH_MAX=2", "-DLQRO_HULL_NARROW_WALK_MAX=3", "-DLQRO_HULL_SMALLKEY_MAX=2"] if general else []
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in HULLHOST_SRCS):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-pthread"]
                                   + extra + ["-o", so, HULLHOST_SRCS[0]])
@@ -479,10 +479,11 @@ class HullHost:
         return planes[:nf], verts[:nf], d, (None if vrel is None else (esc[0], esc[1:4].copy()))
 
     def coverage(self, reset=False):
-        out = np.zeros(8, dtype=np.int64)
+        out = np.zeros(12, dtype=np.int64)
         self.lib.hullhost_coverage(P(out), 1 if reset else 0)
         return dict(zip(("cone_gt16", "cone_gt64", "exhaustive", "old_facet_moved", "ring_compaction", "horizon_flood",
-                         "multi_chunk_partition", "multi_chunk_wave"), out.tolist()))
+                         "multi_chunk_partition", "multi_chunk_wave", "olist_compaction", "append_moved_segment", "append_sweep_buckets",
+                         "gather_cold"), out.tolist()))
 
     def round6(self, a):
         a = np.asarray(a, dtype=np.float64)

@@ -57,6 +57,6 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
   return 0;
 }
 
-extern "C" void hullhost_coverage(long long* out8, int reset) { for (int i = 0; i < 8; ++i) { out8[i] = g_hull_cover[i]; if (reset) g_hull_cover[i] = 0; } }
+extern "C" void hullhost_coverage(long long* out12, int reset) { for (int i = 0; i < 12; ++i) { out12[i] = g_hull_cover[i]; if (reset) g_hull_cover[i] = 0; } }
 
 extern "C" double hullhost_round6(double x) { return round6_dev(x); }

@@ -92,6 +92,9 @@ def test_generated_clouds_and_rare_branches(host, oracle):
             pass
     cov = host.coverage()
     assert cov["multi_chunk_partition"] > 0 and cov["exhaustive"] > 0, cov
+    # the outside sets live in contiguous segments: their storage was compacted, a facet that already held points received
+    # more (segment moved), and long partitions went through the cold arrays
+    assert cov["olist_compaction"] > 0 and cov["append_moved_segment"] > 0 and cov["gather_cold"] > 0, cov
 
 
 def test_general_branches_forced(oracle):
@@ -106,7 +109,7 @@ def test_general_branches_forced(oracle):
     p /= np.linalg.norm(p, axis=1, keepdims=True)
     assert _same_hull(general, oracle, p) == 2 * 200 - 4
     cov = general.coverage()
-    assert cov["cone_gt16"] > 0 and cov["cone_gt64"] > 0, cov
+    assert cov["cone_gt16"] > 0 and cov["cone_gt64"] > 0 and cov["append_sweep_buckets"] > 0, cov
 
 
 def test_ring_compaction(host, oracle):
