@@ -346,9 +346,9 @@ def sim_update_arm(ctx, x, L, E, Lh, Eh, stream, args):
         e1.record(stream)
         stream.synchronize()
         ts.append(e0.elapsed_time(e1))
-    arm["timestep"] = {"ms_per_step": float(np.mean(ts[2:])), "api": "lqro_timestep_device (MAIN:1373-1417 for every agent: k_pairs, k_hull, "
+    arm["timestep"] = {"ms_per_step": float(np.mean(ts[2:])), "api": "lqro_timestep_device (MAIN:1373-1417 for every agent: k_hull polling + k_pairs, k_hull, "
                        "k_new_velocity, k_sim_control, k_sim_flow, k_sim_noise, k_sim_filter; state resident)",
-                       "gpu_launches_per_step": 7, "finite": bool(torch.isfinite(dvg).all().item())}
+                       "gpu_launches_per_step": 8, "finite": bool(torch.isfinite(dvg).all().item())}
     if not args.no_cpu:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))

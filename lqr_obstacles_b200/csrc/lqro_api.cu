@@ -341,7 +341,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     ctx->hull_blocks = slots;
     // SMs of the polling hull launch of a large swarm's step (the pair kernel's grid is that much smaller); LQRO_HULL_OVERLAP_SMS=0
     // or LQRO_FLAG_NO_OVERLAP: pair kernel on every SM, hulls afterwards
-    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 16;
+    ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 12;  // measured at 65,536 x 64: 8 -> 6.79 ms (hulls behind), 12 -> 6.40, 16 -> 6.59
     if (const char* e = getenv("LQRO_HULL_OVERLAP_SMS")) ctx->overlap_sms = atoi(e);
     if (ctx->overlap_sms < 0) ctx->overlap_sms = 0;
     if (ctx->overlap_sms > ctx->sm_count / 2) ctx->overlap_sms = ctx->sm_count / 2;
@@ -713,6 +713,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
   if (hull_early) CU(cudaStreamWaitEvent(st, ctx->ev_early, 0));
+  if (!hull_early) k_hull_order<<<1, 1024, 0, st>>>(hq, ctx->d_ctr + 2, ctx->d_nreach, ctx->hull_blocks);  // more hulls than hull warps: longest first
   k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
                                                        ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
@@ -728,7 +729,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
   ctx->last_two_slices = hull_early != 0;
-  ctx->launches = 2 + pair_launches + hull_early;  // pair kernel(s) + hull launch(es) + LP
+  ctx->launches = 2 + pair_launches + 1;  // pair kernel(s) + wide hull launch + LP + (polling hull launch | queue ordering)
   ctx->stepped = true;
   return LQRO_OK;
 }

@@ -204,6 +204,48 @@ __global__ void __launch_bounds__(32 * LQRO_HULL_POLL_WARPS, 1) k_hull(LqroParam
   }
 }
 
+// Longest hulls first.  When more inside pairs are queued than hull warps can run at once (the reference's dense 32 / 64-quad
+// scenarios: 100 - 500 hulls of up to H*P points per step), the wide launch works through the queue in rounds and the step ends
+// with whatever the last round holds.  One hull costs about its cloud size (insertions are sequential), so the queue is put in
+// order of decreasing reachable-cloud size first (longest-processing-time-first list scheduling): the long hulls start at once,
+// the short ones fill the gaps.  One block; in-place bitonic sort of up to LQRO_HULL_SORT_MAX entries in shared memory, key =
+// (cloud size, queue position) so the order is deterministic.  Returns at once when one round suffices.  The half-planes do not
+// depend on the order.
+#define LQRO_HULL_SORT_MAX 4096
+__global__ void __launch_bounds__(1024, 1) k_hull_order(HullQueue hq, const int* __restrict__ work_counter, const int* __restrict__ nreach, int slots) {
+  __shared__ unsigned long long key[LQRO_HULL_SORT_MAX];
+  int c = *hq.count;
+  if (c > hq.capacity) c = hq.capacity;
+  const int h = *work_counter;
+  const int m = c - h;
+  if (m <= slots || m > LQRO_HULL_SORT_MAX) return;
+  int np2 = 1;
+  while (np2 < m) np2 <<= 1;
+  for (int q = threadIdx.x; q < np2; q += blockDim.x) {
+    unsigned long long k = 0ull;  // padding sorts last
+    if (q < m) {
+      const int pair = hq.items[h + q];
+      k = ((unsigned long long)(unsigned)(nreach[pair] + 1) << 44) | ((unsigned long long)(unsigned)(LQRO_HULL_SORT_MAX - q) << 32) | (unsigned)pair;
+    }
+    key[q] = k;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= np2; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int q = threadIdx.x; q < np2; q += blockDim.x) {
+        const int partner = q ^ j;
+        if (partner > q) {
+          const unsigned long long a = key[q], b = key[partner];
+          const bool desc = (q & k2) == 0;  // descending overall
+          if (desc ? a < b : a > b) { key[q] = b; key[partner] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int q = threadIdx.x; q < m; q += blockDim.x) hq.items[h + q] = (int)(unsigned)(key[q] & 0xffffffffull);
+}
+
 // Stage kernel: hull of an arbitrary cloud (AoS pts in global memory), everything in the global slot.
 // mode bit 0: apply the 6-digit rendering first.  Outputs facets in qhull order (planes nf*4, verts nf*3
 // as point indices); when vrel != NULL also the nearest-facet result (escape[0] = distance,
