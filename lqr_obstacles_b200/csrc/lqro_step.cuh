@@ -220,14 +220,27 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
             dx1 += fabs(dx[2 * m]) + fabs(dx[2 * m + 1]);
           }
           const double vr0 = dx[3], vr1 = dx[4], vr2 = dx[5];
+          // state differences beyond position and velocity that are exactly zero (agents in the same attitude / rotor state, as
+          // every pair of the synthetic swarms) add exactly nothing to the sums: skip their terms
+          bool tail0 = true;
+#pragma unroll
+          for (int m = 6; m < 16; ++m) tail0 = tail0 && dx[m] == 0.0;
           for (int k = 0; k < H; ++k) {
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
             const double* nf = t.NFt + 3 * k;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
+            for (int m = 0; m < 6; ++m) {
               t0 = fma(nf[m * n3], dx[m], t0);
               t1 = fma(nf[m * n3 + 1], dx[m], t1);
               t2 = fma(nf[m * n3 + 2], dx[m], t2);
+            }
+            if (!tail0) {
+#pragma unroll
+              for (int m = 6; m < 16; ++m) {
+                t0 = fma(nf[m * n3], dx[m], t0);
+                t1 = fma(nf[m * n3 + 1], dx[m], t1);
+                t2 = fma(nf[m * n3 + 2], dx[m], t2);
+              }
             }
             // |fused sum - reference's rounded sum| <= 2 * 16 * 2^-53 * sum |NF||dx| <= 1e-14 * max|NF_k| * |dx|_1
             const double tr_err = 1.0e-14 * t.prn[LQRO_PRN * k + 7] * dx1;
@@ -260,14 +273,21 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         if (k < H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
       }
       __syncwarp();
-      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231)
+      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231).  Terms whose state
+      // difference is exactly zero are skipped when that holds for all of entries 6..15: s + (+-0) == s bit for bit (s is
+      // never -0: the sum starts from +0), so the result is the reference's.
+      const bool tail0 = __ballot_sync(LQRO_FULL, lane >= 6 && lane < 16 && w.dx[lane] != 0.0) == 0u;
       for (int e = lane; e < 3 * nk; e += 32) {
         const int ki = e / 3, c = e - 3 * ki;
         const int k = w.klist[ki];
         const double* nf = t.NFt + 3 * k + c;
         double s = 0;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) s += nf[m * n3] * w.dx[m];
+        for (int m = 0; m < 6; ++m) s += nf[m * n3] * w.dx[m];
+        if (!tail0) {
+#pragma unroll
+          for (int m = 6; m < 16; ++m) s += nf[m * n3] * w.dx[m];
+        }
         w.tr[3 * k + c] = s;
       }
       __syncwarp();
