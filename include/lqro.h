@@ -290,9 +290,9 @@ int lqro_measure_fp32_peak(lqro_ctx* ctx, double* tflops);
 /* Device time (ms) of the kernels of the last step: [0] pair kernel, [1] hull kernel, [2] LP kernel,
  * [3] whole step (kernels only, measured with CUDA events on the launching stream). */
 int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
-/* Two-slice steps (large swarms): [0] first slice of the pair kernel (nearest slots, every SM), [1] second slice (on all but
- * [3] SMs), [2] the early hull launch next to it (its own stream), [3] SMs left to that launch, [4] neighbour slots per agent in the
- * first slice; one-launch steps: [1] only ([3] = 0). */
+/* Steps of large swarms (polling hull launch next to the pair kernel): [0] set-up before the pair kernel, [1] the pair kernel (on
+ * all but [3] SMs), [2] the polling hull launch (its own stream, started together with the pair kernel), [3] its SMs, [4] neighbour
+ * slots per agent in the first chunk of the slot-major enumeration; other steps: [1] only ([3] = 0). */
 int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5);
 /* SM-cycle breakdown of the hull kernel of the last step, summed over hulls (development aid):
  * [0] init+simplex [1] partitionall [2] furthest+horizon+cone [3] planes+match [4] list [5] walk [6] redo
