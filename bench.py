@@ -540,7 +540,7 @@ def run_ours(args):
             t = ctx.last_step_ms()
             kern_ms += np.array([t["pairs"], t["hull"], t["lp"], t["total"]])
             dt = ctx.last_step_detail_ms()
-            detail_ms += np.array([dt["slice1"], dt["slice2"], dt["early_hull"]])
+            detail_ms += np.array([dt["setup"], dt["pairs"], dt["polling_hull"]])
             overlap_sms, first_slots = dt["overlap_sms"], dt["first_slots"]
     barrier()
     sampler.end()

@@ -335,7 +335,7 @@ class Lqro:
     def last_step_detail_ms(self):
         t = np.zeros(5, dtype=np.float32)
         self._ck(self.lib.lqro_last_step_detail_ms(self.h, _p(t)))
-        return dict(slice1=float(t[0]), slice2=float(t[1]), early_hull=float(t[2]), overlap_sms=int(t[3]), first_slots=int(t[4]))
+        return dict(setup=float(t[0]), pairs=float(t[1]), polling_hull=float(t[2]), overlap_sms=int(t[3]), first_slots=int(t[4]))
 
     def hull_longest(self):
         c = np.zeros(16, dtype=np.int64)

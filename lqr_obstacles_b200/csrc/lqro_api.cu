@@ -106,7 +106,7 @@ struct lqro_ctx {
   int pair_warps = 0, pair_blocks = 0, fused_hull = 0; size_t pair_smem = 0;
   int hull_wpb = 2, hull_blocks = 0, hull_per_sm = 1, hull_poll_warps = 1; size_t hull_smem = 0;
   // step of large swarms: SMs of the polling hull launch (the pair kernel's grid is that much smaller), its stream and the events that order it
-  int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_slice = nullptr, ev_early = nullptr, ev_early0 = nullptr; bool last_two_slices = false;
+  int overlap_sms = 0; cudaStream_t hull_stream = nullptr; cudaEvent_t ev_poll_go = nullptr, ev_poll1 = nullptr, ev_poll0 = nullptr; bool last_polling = false;
   // stage scratch (grown on demand)
   char* d_scratch = nullptr; size_t scratch_bytes = 0;
   char* d_stage_ws = nullptr; int stage_ws_pts = 0;
@@ -192,9 +192,9 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_ric) if (e) cudaEventDestroy(e);
   { void* q[] = {ctx->d_tbs, ctx->d_agent_class, ctx->d_order, ctx->d_cls_ctr, ctx->d_identity, ctx->d_chunk_ctr}; for (void* p : q) if (p) cudaFree(p); }
   if (ctx->hull_stream) cudaStreamDestroy(ctx->hull_stream);
-  if (ctx->ev_slice) cudaEventDestroy(ctx->ev_slice);
-  if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
-  if (ctx->ev_early0) cudaEventDestroy(ctx->ev_early0);
+  if (ctx->ev_poll_go) cudaEventDestroy(ctx->ev_poll_go);
+  if (ctx->ev_poll1) cudaEventDestroy(ctx->ev_poll1);
+  if (ctx->ev_poll0) cudaEventDestroy(ctx->ev_poll0);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
@@ -604,7 +604,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
   //        [8] pair CTAs that have started
   StepSync sy{ctx->d_ctr + 0, 0, 32, ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
-  int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_early = 0;
+  int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_polling = 0;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
   k_pairs<F, HT, PT><<<pair_grid, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,                \
@@ -670,9 +670,9 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     // under the rest of the pair kernel instead of behind it.  The wide launch after the pair kernel takes what is left.
     if (!ctx->hull_stream) {
       CU(cudaStreamCreateWithFlags(&ctx->hull_stream, cudaStreamNonBlocking));
-      CU(cudaEventCreate(&ctx->ev_slice));
-      CU(cudaEventCreate(&ctx->ev_early));
-      CU(cudaEventCreate(&ctx->ev_early0));
+      CU(cudaEventCreate(&ctx->ev_poll_go));
+      CU(cudaEventCreate(&ctx->ev_poll1));
+      CU(cudaEventCreate(&ctx->ev_poll0));
     }
     pair_grid = ctx->pair_blocks - ctx->overlap_sms;
     // batches of the nearest 8 slots: narrow enough for >= 6 batches per pair warp of the grid (a batch is one warp's sequential job)
@@ -680,18 +680,18 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     int bw = 32;
     while (bw > 2 && narrow / bw < 6LL * pair_grid * ctx->pair_warps) bw >>= 1;
     sy.narrow_pairs = (int)narrow; sy.batch_width = bw;
-    CU(cudaEventRecord(ctx->ev_slice, st));  // counters cleared, previous step finished
-    CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_slice, 0));
-    CU(cudaEventRecord(ctx->ev_early0, ctx->hull_stream));
+    CU(cudaEventRecord(ctx->ev_poll_go, st));  // counters cleared, previous step finished
+    CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_poll_go, 0));
+    CU(cudaEventRecord(ctx->ev_poll0, ctx->hull_stream));
     k_hull<<<ctx->overlap_sms, 32 * ctx->hull_poll_warps, ctx->smem_optin, ctx->hull_stream>>>(
         p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8, ctx->d_hull_ws,
         ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
-    CU(cudaEventRecord(ctx->ev_early, ctx->hull_stream));
+    CU(cudaEventRecord(ctx->ev_poll1, ctx->hull_stream));
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     pair_grid = ctx->pair_blocks;
     sy.narrow_pairs = 0; sy.batch_width = 32;
     ++pair_launches;
-    hull_early = 1;
+    hull_polling = 1;
   } else if (!ctx->hetero) {
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     ++pair_launches;
@@ -712,8 +712,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
-  if (hull_early) CU(cudaStreamWaitEvent(st, ctx->ev_early, 0));
-  if (!hull_early) k_hull_order<<<1, 1024, 0, st>>>(hq, ctx->d_ctr + 2, ctx->d_nreach, ctx->hull_blocks);  // more hulls than hull warps: longest first
+  if (hull_polling) CU(cudaStreamWaitEvent(st, ctx->ev_poll1, 0));
+  if (!hull_polling) k_hull_order<<<1, 1024, 0, st>>>(hq, ctx->d_ctr + 2, ctx->d_nreach, ctx->hull_blocks);  // more hulls than hull warps: longest first
   k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
                                                        ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
@@ -728,7 +728,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
-  ctx->last_two_slices = hull_early != 0;
+  ctx->last_polling = hull_polling != 0;
   ctx->launches = 2 + pair_launches + 1;  // pair kernel(s) + wide hull launch + LP + (polling hull launch | queue ordering)
   ctx->stepped = true;
   return LQRO_OK;
@@ -1019,10 +1019,10 @@ extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5) {
   CU(cudaSetDevice(ctx->cfg.device));
   CU(cudaEventSynchronize(ctx->ev[3]));
   out4[0] = out4[1] = out4[2] = 0.f; out4[3] = (float)ctx->overlap_sms; out5[4] = (float)ctx->prm.first_slots;
-  if (!ctx->last_two_slices) { CU(cudaEventElapsedTime(out4 + 1, ctx->ev[0], ctx->ev[1])); out4[3] = 0.f; return LQRO_OK; }
-  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_slice));
-  CU(cudaEventElapsedTime(out4 + 1, ctx->ev_slice, ctx->ev[1]));
-  CU(cudaEventElapsedTime(out4 + 2, ctx->ev_early0, ctx->ev_early));
+  if (!ctx->last_polling) { CU(cudaEventElapsedTime(out4 + 1, ctx->ev[0], ctx->ev[1])); out4[3] = 0.f; return LQRO_OK; }
+  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_poll_go));
+  CU(cudaEventElapsedTime(out4 + 1, ctx->ev_poll_go, ctx->ev[1]));
+  CU(cudaEventElapsedTime(out4 + 2, ctx->ev_poll0, ctx->ev_poll1));
   return LQRO_OK;
 }
 
