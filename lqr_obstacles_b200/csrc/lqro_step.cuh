@@ -254,17 +254,26 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     unsigned act = __ballot_sync(LQRO_FULL, kmask != 0ull);
     PAIR_PROF(0)
     PAIR_PROF_COUNT(6, __popc(act))
+    // the two states of a pair come from L2 (~1 us): those of the NEXT stage-2 pair are requested while this one is worked on
+    double pfa = 0.0, pfb = 0.0;
+    if (act) {
+      const int s0 = __ffs(act) - 1;
+      const int i0 = __shfl_sync(LQRO_FULL, i, s0), j0 = __shfl_sync(LQRO_FULL, j, s0);
+      if (lane < 16) { pfa = x[(size_t)i0 * 16 + lane]; pfb = x[(size_t)j0 * 16 + lane]; }
+    }
     while (act) {
       const int src = __ffs(act) - 1;
       act &= act - 1;
       const int pr = __shfl_sync(LQRO_FULL, pair, src);
-      const int ii = __shfl_sync(LQRO_FULL, i, src);
-      const int jj = __shfl_sync(LQRO_FULL, j, src);
       const unsigned long long km = __shfl_sync(LQRO_FULL, kmask, src);
       if (lane < 16) {
-        const double a = x[(size_t)ii * 16 + lane], b = x[(size_t)jj * 16 + lane];
-        w.xi[lane] = a;
-        w.dx[lane] = a - b;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
+        w.xi[lane] = pfa;
+        w.dx[lane] = pfa - pfb;  // xInit1 - xInit2 (MAIN:685); entries 3..5 are also v_rel (MAIN:698-700)
+      }
+      if (act) {
+        const int s1 = __ffs(act) - 1;
+        const int i1 = __shfl_sync(LQRO_FULL, i, s1), j1 = __shfl_sync(LQRO_FULL, j, s1);
+        if (lane < 16) { pfa = x[(size_t)i1 * 16 + lane]; pfb = x[(size_t)j1 * 16 + lane]; }
       }
       const int nk = __popcll(km);
 #pragma unroll
