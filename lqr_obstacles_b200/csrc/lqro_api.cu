@@ -683,7 +683,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     CU(cudaEventRecord(ctx->ev_poll_go, st));  // counters cleared, previous step finished
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_poll_go, 0));
     CU(cudaEventRecord(ctx->ev_poll0, ctx->hull_stream));
-    k_hull<<<ctx->overlap_sms, 32 * ctx->hull_poll_warps, ctx->smem_optin, ctx->hull_stream>>>(
+    k_hull<<<ctx->overlap_sms, 64 * ctx->hull_poll_warps, ctx->smem_optin, ctx->hull_stream>>>(
         p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8, ctx->d_hull_ws,
         ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
     CU(cudaEventRecord(ctx->ev_poll1, ctx->hull_stream));
@@ -714,7 +714,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaEventRecord(ctx->ev[1], st));
   if (hull_polling) CU(cudaStreamWaitEvent(st, ctx->ev_poll1, 0));
   if (!hull_polling) k_hull_order<<<1, 1024, 0, st>>>(hq, ctx->d_ctr + 2, ctx->d_nreach, ctx->hull_blocks);  // more hulls than hull warps: longest first
-  k_hull<<<ctx->hull_blocks, 32, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
+  k_hull<<<ctx->hull_blocks, 64, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
                                                        ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[2], st));

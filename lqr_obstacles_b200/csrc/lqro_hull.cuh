@@ -22,13 +22,14 @@ struct HullWarp {
   PairWarpSmem pw;
   HullWs w;
   HullCtl* ctl;
+  HullMail* mail;   // mailbox of the hull's two warps (k_hull), behind the control block
   char* hot;
   char* gslot;
 };
 // bytes of shared memory one hull warp needs after the block tables
 __host__ __device__ inline size_t hull_warp_smem_bytes(int H, int P) {
   return hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1)) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) +
-         hull_align16(sizeof(HullCtl));
+         hull_align16(sizeof(HullCtl)) + hull_align16(sizeof(HullMail));
 }
 // the stand-alone hull kernel keeps only the ellipsoid samples (SoA, 3P doubles) in shared memory: the horizon tables are read
 // from global memory (13-19 KB shared by every hull of the GPU, L1 / L2 resident; they are only needed while the cloud is
@@ -41,6 +42,7 @@ __device__ __forceinline__ void hull_warp_setup(HullWarp& hw, char* sm, char* gs
   hw.pw.tr = wb; hw.pw.dx = wb + 3 * H; hw.pw.xi = hw.pw.dx + 16; hw.pw.klist = reinterpret_cast<int*>(hw.pw.xi + 16);
   hw.hot = sm + hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1));
   hw.ctl = reinterpret_cast<HullCtl*>(hw.hot + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS));
+  hw.mail = reinterpret_cast<HullMail*>(reinterpret_cast<char*>(hw.ctl) + hull_align16(sizeof(HullCtl)));
   hw.gslot = gslot;
   hull_carve_coords(gslot, H * P, hw.w);
   hull_carve_cold(gslot + hull_slot_cold_offset(H * P), H * P, hull_full_facets(H * P), hw.w);
@@ -97,6 +99,8 @@ __device__ __noinline__ void hull_pair_fallback(const LqroParams& p, char* gslot
 
 // One queued inside-case pair: regenerate the reachable cloud (same code, same bits as k_pairs), render it to
 // 6 digits, hull it, pick the nearest facet, write the plane.
+// COOP: the hull's helper warp is waiting at the hull's barrier (k_hull) and is left there when this returns.
+template <bool COOP = false>
 __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTables& pt, HullWarp& hw, const double* __restrict__ x,
                                              const int* __restrict__ nbr, const PairOutputs& out, int pair, int* counters,
                                              long long* prof) {
@@ -116,7 +120,7 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
   const int n = warp_reachable_cloud(p, pt, pw);
   hull_carve_hot(hw.hot, p.HP, LQRO_HULL_SMEM_FACETS, w);   // fast path: hot structures + coordinates in shared memory
   hull_render_cloud(p, w, n);
-  hull_build(w, *ctl, n, false);
+  hull_build_t<COOP>(w, *ctl, hw.mail, n, false);
   if (ctl->fail == 2) { hull_pair_fallback(p, hw.gslot, ctl, pw.dx, pw.xi, out, pair, n, counters, prof); return; }
   hull_finish_pair(w, ctl, pw, out, pair, n, counters, prof);
 }
@@ -124,50 +128,69 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
 // Hull kernel: one warp per queued inside pair at a time, tickets from a shared counter.  Launched twice per step of a large
 // swarm:
 //  * POLLING (poll != 0), on its own stream and BEFORE the pair kernel, as a concurrent consumer of the hull queue on a few SMs
-//    of its own: LQRO_HULL_POLL_WARPS independent hull warps per block, whose shared memory fills an SM, so that no pair CTA can
+//    of its own: LQRO_HULL_POLL_WARPS independent hulls (two warps each) per block, whose shared memory fills an SM, so that no pair CTA can
 //    share it (a hull is a latency-bound dependent chain: next to 20 pair warps it runs 2.5x slower) -- the pair kernel's grid
 //    is that many SMs short.  A polling warp takes ticket h only when the published queue length exceeds h (compare-and-swap on
 //    the head), so a ticket in hand always has a producer behind it that stores the pair id within microseconds: nothing here
 //    can wait for a launch that does not come.  It leaves when every pair warp of the step has signed off (producers_done ==
 //    producers_total; what is still queued then goes to the wide launch at full width), or when no pair CTA has come up within
 //    2 ms of its own start (launches serialised by a profiler or CUDA_LAUNCH_BLOCKING: the wide launch then does all the work).
-//  * WIDE (poll == 0) after the pair kernel, one warp per block, for whatever is left in the queue.
+//  * WIDE (poll == 0) after the pair kernel, one hull (two warps) per block, for whatever is left in the queue.
 // Every consumer puts -1 back into the queue entry it has read: that is the "not published yet" value the next step's pollers
 // rely on (the queue is filled with -1 once, when the context is created).
-#define LQRO_HULL_POLL_WARPS 3
+#define LQRO_HULL_POLL_WARPS 3   // hulls (= pairs of warps) per block of the polling launch
+#ifndef LQRO_HULL_COOP
+#define LQRO_HULL_COOP 1         // 0: ablation -- the helper warps leave at once, the main warp does everything (one warp per hull)
+#endif
 __device__ __forceinline__ unsigned long long hull_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__global__ void __launch_bounds__(32 * LQRO_HULL_POLL_WARPS, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
+// TWO WARPS PER HULL (lqro_hull_core.cuh, HullMail): warp 2s is the main warp of hull slot s of the block -- it takes the tickets and
+// runs the build --, warp 2s + 1 its helper (planes + ridge matching next to the gather, the next insertion's horizon search next
+// to the partition).  They meet at named barrier 1 + s: once per hull ("a hull follows" / "no more work"), three times per insertion.
+__global__ void __launch_bounds__(64 * LQRO_HULL_POLL_WARPS, 1) k_hull(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                              PairOutputs out, HullQueue hq, int* __restrict__ work_counter, int poll,
                                              const int* __restrict__ producers_done, int producers_total, const int* __restrict__ producers_started,
                                              char* __restrict__ ws_base, size_t ws_stride, int* __restrict__ counters, long long* __restrict__ prof,
                                              const int* __restrict__ agent_class /* NULL: one class */, const LqroTables* __restrict__ class_tables) {
   extern __shared__ double smem[];
-  const int lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int lane = lane_id(), warp = threadIdx.x >> 5, hs = warp >> 1, hpb = blockDim.x >> 6;
+  const bool helper = (warp & 1) != 0;
+  const int bar = 1 + hs;
   PairTables pt;
   {
     const int P = p.P;
     for (int e = threadIdx.x; e < P; e += blockDim.x) { smem[e] = tb.sph[3 * e]; smem[P + e] = tb.sph[3 * e + 1]; smem[2 * P + e] = tb.sph[3 * e + 2]; }
-    __syncthreads();   // the only block-wide step: from here on the warps of a block are independent
+    __syncthreads();   // the only block-wide step: from here on the hulls of a block are independent
     pt.NFt = tb.NFt; pt.T = tb.T; pt.CG = tb.CG; pt.prn = tb.prn;
     pt.sphx = smem; pt.sphy = smem + P; pt.sphz = smem + 2 * P;
   }
-  const int slot = blockIdx.x * wpb + warp;
+  const int slot = blockIdx.x * hpb + hs;
+  HullWarp hw;
+  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * 3 * (size_t)p.P) + (size_t)hs * hull_warp_smem_bytes(p.H, p.P),
+                  ws_base + ws_stride * (size_t)slot, p.H, p.P);
+  if (helper) {
+    if (!LQRO_HULL_COOP) return;
+    hull_carve_hot(hw.hot, p.HP, LQRO_HULL_SMEM_FACETS, hw.w);
+    while (true) {
+      hull_pair_bar(bar);                     // the main warp says whether a hull follows
+      if (hw.mail->hull == 0) break;
+      hull_helper(hw.w, *hw.ctl, *hw.mail);
+    }
+    return;
+  }
   int nq = 0;
+  bool any = true;
   if (!poll) {
     nq = *hq.count;
     if (nq > hq.capacity) nq = hq.capacity;
-    if (*(volatile int*)work_counter + slot >= nq) return;  // nothing can be left for this warp
+    if (*(volatile int*)work_counter + slot >= nq) any = false;  // nothing can be left for this hull slot
   }
-  HullWarp hw;
-  hull_warp_setup(hw, reinterpret_cast<char*>(smem) + hull_align16(sizeof(double) * 3 * (size_t)p.P) + (size_t)warp * hull_warp_smem_bytes(p.H, p.P),
-                  ws_base + ws_stride * (size_t)slot, p.H, p.P);
   int loaded = agent_class ? -1 : 0;
   const unsigned long long t_start = poll ? hull_globaltimer() : 0ull;
-  while (true) {
+  while (any) {
     int item = -1;
     if (lane == 0) {
       if (!poll) {
@@ -194,14 +217,18 @@ __global__ void __launch_bounds__(32 * LQRO_HULL_POLL_WARPS, 1) k_hull(LqroParam
     if (lane == 0) {
       while ((pair = *(volatile int*)(hq.items + item)) < 0) __nanosleep(32);  // published right after the slot was taken (k_pairs)
       hq.items[item] = -1;
+      hw.mail->hull = 1; hw.mail->bar_id = bar;
     }
     pair = __shfl_sync(LQRO_FULL, pair, 0);
+    if (LQRO_HULL_COOP) hull_pair_bar(bar);   // a hull follows: the helper enters hull_helper
     if (agent_class) {  // heterogeneous dynamics: the obstacle of pair (i, j) uses agent i's class (MAIN:1384)
       const int c = agent_class[p.local_begin + pair / p.K];
       if (c != loaded) { const LqroTables tc = class_tables[c]; pt.NFt = tc.NFt; pt.T = tc.T; pt.CG = tc.CG; pt.prn = tc.prn; loaded = c; }
     }
-    hull_do_pair(p, pt, hw, x, nbr, out, pair, counters, prof);
+    hull_do_pair<LQRO_HULL_COOP != 0>(p, pt, hw, x, nbr, out, pair, counters, prof);
   }
+  if (lane == 0) hw.mail->hull = 0;
+  if (LQRO_HULL_COOP) hull_pair_bar(bar);     // no more work: the helper leaves
 }
 
 // Longest hulls first.  When more inside pairs are queued than hull warps can run at once (the reference's dense 32 / 64-quad

@@ -53,6 +53,12 @@
 #ifndef LQRO_HULL_SMALLKEY_MAX
 #define LQRO_HULL_SMALLKEY_MAX 32
 #endif
+// Two warps per hull: every LQRO_HULL_SPEC_REJECT_MOD-th insertion throws the helper's speculative horizon away and searches again
+// (0: never; the test build uses 3 to exercise the rejection path, which real clouds take only when a facet gets a new furthest
+// point while it waits at the head of the pending list).
+#ifndef LQRO_HULL_SPEC_REJECT_MOD
+#define LQRO_HULL_SPEC_REJECT_MOD 0
+#endif
 
 // ---- strtod(printf("%g", x)): nearest double to the 6-significant-digit decimal rendering of x ------
 #if defined(LQRO_HULL_HOST_EMUL)
@@ -146,6 +152,8 @@ struct HullWs {
   HPlane* pl; HTopo* tp; HOut* ot; HMeta* mt;     // [cap_f]
   hidx *aux;              // [cap_f] visible facet: the last cone facet made from its ridges (qhull's f.replace); new facet: cone-local index
   hidx *vis, *freel, *ring;  // [cap_f]; ring [ring_mask + 1]
+  hidx *vis2, *hst;          // [cap_f] each: the OTHER visible list and the helper warp's private stamps (two warps per hull, see HullMail)
+  hidx *visB;                // the second visible-list array as carved (vis / vis2 swap on the main warp)
   hidx *order;            // [cap_f] facets in qhull's list order, stage kernel only                    (cold)
   hidx *newf;             // [LQRO_HULL_MAXNEW]
   int* vown;              // [cap_pts + 8] ridge matching of large cones: cone facet that last touched vertex id v (-1 = none)   (cold)
@@ -164,7 +172,7 @@ __host__ __device__ inline size_t hull_hot_bytes(int cap_pts, int cap_f) {
   b += hull_align16(sizeof(HMeta) * (size_t)cap_f);
   b += hull_align16(3 * sizeof(double) * (size_t)cap_pts);              // hx hy hz (hull input coordinates)
   b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_pts + 8));          // olist vpoint
-  b += hull_align16(sizeof(hidx) * (3 * (size_t)cap_f + (size_t)hull_ring_size(cap_f) + LQRO_HULL_MAXNEW));  // aux vis freel ring newf
+  b += hull_align16(sizeof(hidx) * (5 * (size_t)cap_f + (size_t)hull_ring_size(cap_f) + LQRO_HULL_MAXNEW));  // aux vis freel vis2 hst ring newf
   return b;
 }
 // bytes of the COLD structures (always in the global slot, L1 / L2 resident): the scratch of the initial partition and of
@@ -202,7 +210,8 @@ __device__ __forceinline__ void hull_carve_hot(char* base, int cap_pts, int cap_
   base += hull_align16(sizeof(hidx) * (3 * (size_t)cap_pts + 8));
   hidx* jp = reinterpret_cast<hidx*>(base);
   w.aux = jp; w.vis = jp + cap_f; w.freel = jp + 2 * (size_t)cap_f;
-  w.ring = jp + 3 * (size_t)cap_f; w.newf = w.ring + rs;
+  w.vis2 = jp + 3 * (size_t)cap_f; w.hst = jp + 4 * (size_t)cap_f; w.visB = w.vis2;
+  w.ring = jp + 5 * (size_t)cap_f; w.newf = w.ring + rs;
 }
 __device__ __forceinline__ void hull_carve_cold(char* base, int cap_pts, int cap_f, HullWs& w) {
   w.pdist = reinterpret_cast<double*>(base); base += hull_align16(sizeof(double) * (size_t)cap_pts);
@@ -239,12 +248,44 @@ struct HullCtl {
   long long prof[12];  // cycles per phase (lane 0, profiling builds): 0 init, 1 partitionall, 2 next + horizon, 3 cone, 4 planes + match, 5 gather, 6 walk, 7 exhaustive + horizon re-test, 8 append, 9 ring + delete, 10 insertions, 11 points re-partitioned
 };
 
+// TWO WARPS PER HULL (k_hull).  An insertion is a chain of dependent phases -- horizon search, cone, planes + ridge matching,
+// gather, walk / append, ring + delete -- and one warp alone retires a dependent instruction every ~7 cycles, so the time of a
+// hull is the number of instructions on that chain.  Two links can leave it:
+//   * the ridge matching of the cone of insertion i depends on nothing the main warp does next: the HELPER warp does it while the
+//     main warp gathers the points to re-partition, computes the planes of the cone and deletes the visible facets;
+//   * the horizon search of insertion i+1 depends only on the topology and the planes, which are final once the cone of insertion i
+//     is matched -- not on the outside sets that the rest of insertion i rearranges.  The facet that will be processed next is
+//     the first pending one that insertion i does not delete, its apex the last point of its outside set; unless insertion i
+//     appends a new furthest point to that very facet (checked: same facet, same apex, else the main warp searches itself), the
+//     helper's SPECULATIVE search, run under the main warp's partition of insertion i, is the search insertion i+1 needs.  The
+//     helper writes only its own visible list (w.vis2 / w.vis alternate) and its own stamps (w.hst); the main warp stamps the
+//     adopted facets itself.
+// One named barrier per hull, met three times per insertion (request / matching done / horizon done).  Same results as one warp:
+// both warps run the same functions on the same data, only earlier.
+struct HullMail {
+  int hull;                     // k_hull: 1 = a hull follows, 0 = the main warp has no more work (helper leaves)
+  int cmd;                      // 1: planes + matching of insertion `ins` (nnew cone facets), then the horizon below; 0: hull finished
+  int ins, nnew;
+  int qhead, qtail, vvis;       // main -> helper: the pending ring as insertion `ins` left it, the stamp of its visible facets
+  int next_facet, next_apex, next_qhead;  // helper -> main: the speculative next insertion (next_facet < 0: none), the ring head behind it
+  int req, vis_sel;             // vis_sel: 0 -> write the list to w.vis, 1 -> to w.vis2 (the one the main warp is NOT using)
+  int nvis2, degen2;            // helper -> main: result of the speculative horizon
+  int mdeg;                     // helper -> main: result of the ridge matching
+  int bar_id;
+};
+#if defined(LQRO_HULL_HOST_EMUL)
+static inline void hull_pair_bar(int) { emu_block_barrier(); }
+#else
+__device__ __forceinline__ void hull_pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+#endif
+
 // rare-path coverage counters of the host (emulation) build: 0 cone > 16 facets (vown matching), 1 cone > 64 (wide visited
 // set), 2 exhaustive mode triggered, 3 old facet moved to the tail, 4 ring compaction, 5 horizon flood, 6 multi-chunk partition,
 // 7 multi-chunk horizon wave, 8 outside-set storage compacted, 9 append to a facet that already has points (segment moved),
-// 10 buckets of an append found by the shuffle sweep (targets outside the cone / cone > 32 facets), 11 gather through the cold arrays
+// 10 buckets of an append found by the shuffle sweep (targets outside the cone / cone > 32 facets), 11 gather through the cold arrays,
+// 12 speculative horizon of the helper warp adopted, 13 rejected (the facet got a new furthest point), 14 no speculation possible
 #if defined(LQRO_HULL_HOST_EMUL)
-static long long g_hull_cover[12];
+static long long g_hull_cover[16];
 #define HULL_COVER(q) { if (lane_id() == 0) ++g_hull_cover[q]; }
 #else
 #define HULL_COVER(q) { }
@@ -519,6 +560,211 @@ __device__ __forceinline__ unsigned hull_peers_small(bool has, int key, int nbit
   return has ? peers : 0u;
 }
 
+// qh_findhorizon as a wave-parallel breadth-first search.  qhull scans the visible list in order and, per facet, its
+// neighbours k = 0,1,2; a neighbour is tested once (first occurrence) and appended to the list if visible.  Processing the
+// (facet, k) slots of one wave in index order, with duplicates inside a 32-slot chunk resolved to the lowest lane, yields the same
+// list.  On entry vis[0] = the facet being processed, stamped visible; nvis = 1.
+// SPEC = false: the main warp's search -- stamps in tp[].vst ((ins << 1) | visible), visible facets get aux = -1.
+// SPEC = true: the helper warp's speculative search -- stamps in its private w.hst, nothing else is written but the list.
+template <bool SPEC>
+__device__ __forceinline__ void hull_horizon(const HullWs& w, hidx* vis, int ins, double ax, double ay, double az, double MINvisible,
+                                             double MAXcoplanar, int& nvis, int& degen) {
+  const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  const hidx vtest = (hidx)(ins << 1), vvis = (hidx)((ins << 1) | 1);
+  int wave = 0;
+  while (wave < nvis) {
+    const int wend = nvis;
+    for (int b0 = wave * 3; b0 < wend * 3; b0 += 32) {
+      if (b0 > wave * 3) HULL_COVER(7)
+      const int idx = b0 + lane;
+      int nb = -1 - lane;
+      bool fresh = false;
+      if (idx < wend * 3) {
+        const int vf = vis[idx / 3];
+        const int cand = w.tp[vf].nb[idx % 3];
+        const int stamp = SPEC ? (int)w.hst[cand] : (int)w.tp[cand].vst;
+        if ((stamp >> 1) != ins) { fresh = true; nb = cand; }
+      }
+      // every fresh slot tests its candidate (a facet reached by several slots of the chunk is tested by each of them: same
+      // result, same stamp); only a VISIBLE facet must enter the list once, through its lowest slot
+      bool isvis = false;
+      if (fresh) {
+        const double d = hdist(w.pl[nb], ax, ay, az);
+        if (d > MINvisible) isvis = true;
+        else if (d > -MAXcoplanar) degen = 1;  // coplanar horizon: qhull would merge
+      }
+      unsigned m = __ballot_sync(LQRO_FULL, isvis);  // every lane has read the stamps before any lane writes one
+      if (fresh) {
+        if (SPEC) w.hst[nb] = isvis ? vvis : vtest;
+        else {
+          w.tp[nb].vst = isvis ? vvis : vtest;
+          if (isvis) w.aux[nb] = -1;
+        }
+      }
+      if (m & (m - 1)) {  // two or more visible candidates: drop the later slots of a repeated facet
+        for (unsigned rest = m; rest; rest &= rest - 1) {
+          const int j = __ffs(rest) - 1;
+          const int v = __shfl_sync(LQRO_FULL, nb, j);
+          if (lane > j && v == nb) isvis = false;
+        }
+        m = __ballot_sync(LQRO_FULL, isvis);
+      }
+      if (isvis) vis[nvis + __popc(m & lt)] = (hidx)nb;
+      nvis += __popc(m);
+      __syncwarp();
+    }
+    wave = wend;
+  }
+}
+
+// qh_makenewplanes for the nnew cone facets w.newf[0 .. nnew): hyperplanes from the vertices, the interior point must lie below
+// every one of them; the sharp test of qh_sharpnewfacets is folded in (orthant of the normals).
+__device__ __forceinline__ void hull_planes(const HullWs& w, int nnew, double in0, double in1, double in2, bool& sharp, int& degen) {
+  const int lane = lane_id();
+  sharp = false;
+  int q0s = 0;
+  for (int q0 = 0; q0 < nnew; q0 += 32) {
+    const int q = q0 + lane;
+    int sg = 0;
+    if (q < nnew) {
+      const int f = w.newf[q];
+      const HTopo T = w.tp[f];
+      const HPlane P = hull_plane(w, w.vpoint[T.v[0]], w.vpoint[T.v[1]], w.vpoint[T.v[2]], (T.born & 1) != 0);
+      w.pl[f] = P;
+      if (!(hdist(P, in0, in1, in2) < 0)) degen = 1;
+      sg = (P.n0 > 0 ? 1 : 0) | (P.n1 > 0 ? 2 : 0) | (P.n2 > 0 ? 4 : 0);
+    }
+    if (q0 == 0) q0s = __shfl_sync(LQRO_FULL, sg, 0);
+    if (__any_sync(LQRO_FULL, q < nnew && sg != q0s)) sharp = true;
+  }
+  if (__any_sync(LQRO_FULL, degen)) degen = 1;
+  __syncwarp();
+}
+
+// qh_matchnewfacets.  The cone facets {apex, a, b} meet along the ridges {apex, w}; every ridge vertex w lies on exactly two of
+// them.  Returns 2 when a ridge has no partner (topology failure), else 0.  Touches only the nb[1], nb[2] fields of the cone facets.
+__device__ __forceinline__ int hull_match(const HullWs& w, int nnew) {
+  const int lane = lane_id();
+  int mdeg = 0;
+  for (int q0 = 0; q0 < nnew; q0 += 32) {
+    const int q = q0 + lane;
+    int f = 0, v1 = -1, v2 = -1;
+    if (q < nnew) {
+      f = w.newf[q];
+      const HTopo T = w.tp[f];
+      v1 = T.v[1]; v2 = T.v[2];
+    }
+    if (nnew <= LQRO_HULL_PAIRMATCH_MAX) {
+      // two lanes per cone facet: lane 2r + (s - 1) holds ridge vertex v[s] of facet r; the other lane with the
+      // same vertex (found by a shuffle sweep over the 2 nnew lanes) is the facet across that ridge = the neighbour opposite the OTHER ridge vertex
+      const int r = lane >> 1, s = 1 + (lane & 1);
+      const int v1r = __shfl_sync(LQRO_FULL, v1, r), v2r = __shfl_sync(LQRO_FULL, v2, r), fr = __shfl_sync(LQRO_FULL, f, r);
+      const int wv = (r < nnew) ? (s == 1 ? v1r : v2r) : (-1 - lane);
+      unsigned other = 0u;
+      for (int j = 0; j < 2 * nnew; ++j) {
+        const int v = __shfl_sync(LQRO_FULL, wv, j);
+        if (j != lane && v == wv) other |= 1u << j;
+      }
+      const int pf = __shfl_sync(LQRO_FULL, fr, other ? __ffs(other) - 1 : lane);
+      if (r < nnew) {
+        if (__popc(other) != 1) mdeg = 2;
+        else w.tp[fr].nb[3 - s] = (hidx)pf;
+      }
+    } else if (q < nnew) {
+      HULL_COVER(0)
+      // large cone: the second facet to reach vown[w] links both
+      HTopo* fa = &w.tp[f];
+#pragma unroll
+      for (int s = 1; s <= 2; ++s) {
+        const int wv = s == 1 ? v1 : v2;
+        const int prev = atomicExch(&w.vown[wv], f);
+        if (prev >= 0) {
+          fa->nb[3 - s] = (hidx)prev;
+          HTopo* fp = &w.tp[prev];
+          if (fp->v[1] == wv) fp->nb[2] = (hidx)f; else fp->nb[1] = (hidx)f;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (nnew > LQRO_HULL_PAIRMATCH_MAX) {
+    for (int q = lane; q < nnew; q += 32) {   // reset the scratch, check every ridge found its partner
+      const HTopo T = w.tp[w.newf[q]];
+      w.vown[T.v[1]] = -1; w.vown[T.v[2]] = -1;
+      if (T.nb[1] < 0 || T.nb[2] < 0) mdeg = 2;
+    }
+  }
+  mdeg = __reduce_max_sync(LQRO_FULL, mdeg);
+  __syncwarp();
+  return mdeg;
+}
+
+// The helper warp of a hull (see HullMail): serves the main warp's requests until the hull is finished.
+__device__ __forceinline__ void hull_helper(const HullWs& w, const HullCtl& c, HullMail& mail) {
+  const int lane = lane_id();
+  const int bar = mail.bar_id;
+  for (int f = lane; f < w.cap_f; f += 32) w.hst[f] = 0;  // stamps of earlier hulls must not match this one's request numbers
+  __syncwarp();
+#if defined(LQRO_HULL_PROF)
+  long long hp_pl = 0, hp_nn = 0, hp_planes = 0, hp_hor = 0, hp_waitA = 0, hp_waitB = 0, hp_waitC = 0, hp_n = 0, t0 = clock64(), t1;
+#define HELPER_TIC(v) { t1 = clock64(); v += t1 - t0; t0 = t1; }
+#else
+#define HELPER_TIC(v)
+#endif
+  while (true) {
+    hull_pair_bar(bar);                       // (A) a request is in the mailbox
+    HELPER_TIC(hp_waitA)
+    if (mail.cmd == 0) break;
+    {
+      HELPER_TIC(hp_pl)
+      const int mdeg = hull_match(w, mail.nnew);
+      // the facet of the NEXT insertion: the first pending one that this insertion does not delete (entries of the new cone facets
+      // and of moved facets come behind every entry that exists now), its apex the last point of its outside set -- read HERE,
+      // before the main warp starts to append (which moves segments of w.olist)
+      int nf = -1, nap = -1, nq = 0;
+      {
+        const int qh = mail.qhead, qt = mail.qtail, vv = mail.vvis;
+        const int pos = qh + lane;
+        int f = -1; bool ok = false;
+        if (pos < qt) { f = w.ring[pos & w.ring_mask]; ok = (w.mt[f].qpos == pos) && w.tp[f].vst != vv; }
+        const unsigned m = __ballot_sync(LQRO_FULL, ok);
+        if (m) {
+          const int k = __ffs(m) - 1;
+          nf = __shfl_sync(LQRO_FULL, f, k);
+          nq = qh + k + 1;
+          const HOut O = w.ot[nf];
+          nap = w.olist[O.ostart + O.ocount - 1];
+        }
+      }
+      if (lane == 0) { mail.mdeg = mdeg; mail.next_facet = nf; mail.next_apex = nap; mail.next_qhead = nq; }
+    }
+    HELPER_TIC(hp_planes)
+    hull_pair_bar(bar);                       // (B) ridge matching done, next insertion named
+    HELPER_TIC(hp_waitB)
+    const int nf = mail.next_facet;
+    if (nf >= 0) {
+      const int req = mail.req, ap = mail.next_apex;
+      hidx* vis = mail.vis_sel ? w.vis2 : w.vis;
+      if (lane == 0) { vis[0] = (hidx)nf; w.hst[nf] = (hidx)((req << 1) | 1); }
+      __syncwarp();
+      int nvis = 1, degen = 0;
+      hull_horizon<true>(w, vis, req, w.hx[ap], w.hy[ap], w.hz[ap], c.MINvisible, c.MAXcoplanar, nvis, degen);
+      if (__any_sync(LQRO_FULL, degen)) degen = 1;
+      if (lane == 0) { mail.nvis2 = nvis; mail.degen2 = degen; }
+    }
+    HELPER_TIC(hp_hor)
+    hull_pair_bar(bar);                       // (C) speculative horizon done
+    HELPER_TIC(hp_waitC)
+#if defined(LQRO_HULL_PROF)
+    ++hp_n; hp_nn += mail.nnew;
+#endif
+  }
+#if defined(LQRO_HULL_PROF)
+  if (lane == 0 && hp_n >= 150) printf("helper: %lld requests, %lld new facets, cycles: planes %lld match %lld, horizon %lld, wait A %lld, wait B %lld, wait C %lld\n", hp_n, hp_nn, hp_pl, hp_planes, hp_hor, hp_waitA, hp_waitB, hp_waitC);
+#endif
+}
+
 #if defined(LQRO_HULL_PROF)
 #define HULL_TIC(q) { if (lane == 0) { const long long tn_ = clock64(); hprof[q] += tn_ - tprof; tprof = tn_; } }
 #define HULL_COUNT(q, v) { if (lane == 0) hprof[q] += (v); }
@@ -531,7 +777,10 @@ __device__ __forceinline__ unsigned hull_peers_small(bool has, int key, int nbit
 // c.degenerate / c.nfacets_out / c.pool_used set; the alive facets are the pool entries [0, c.pool_used) with
 // tp[f].born >= 0, their order in qhull's facet list is increasing mt[f].seq.  want_order: also fill
 // w.order[0..c.nfacets_out) with the facets in that order.
-__device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool want_order) {
+// COOP: a helper warp (hull_helper) waits at the hull's named barrier (see HullMail); every path out of this function leaves it
+// at its request barrier with cmd = 0.
+template <bool COOP>
+__device__ __forceinline__ void hull_build_t(HullWs& w, HullCtl& c, HullMail* mail, int n, bool want_order) {
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
 #if defined(LQRO_HULL_PROF)
@@ -543,7 +792,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
     for (int q = 0; q < 12; ++q) c.prof[q] = 0;
   }
   __syncwarp();
-  if (c.fail) return;
+  if (c.fail) { if (COOP) { if (lane == 0) mail->cmd = 0; hull_pair_bar(mail->bar_id); } return; }
   for (int q = lane; q < n + 8; q += 32) w.vown[q] = -1;
   // ---- qh_maxmin: first index attaining the max / min of each coordinate
   {
@@ -653,7 +902,7 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
     }
   }
   __syncwarp();
-  if (c.fail) return;
+  if (c.fail) { if (COOP) { if (lane == 0) mail->cmd = 0; hull_pair_bar(mail->bar_id); } return; }
   HULL_TIC(0)
   const double DISTround = c.DISTround, MINvisible = c.MINvisible, MINoutside = c.MINoutside, MAXcoplanar = c.MAXcoplanar;
   const double distoutside = 2 * MINoutside;  // qh_DISToutside, max_outside = 0
@@ -718,26 +967,50 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
   }
   HULL_TIC(1)
   // ---- qh_buildhull
+  // two warps per hull (COOP): hstate = where the helper is -- 0 at its request barrier (A), 1 on its way to (B), 2 to (C);
+  // spec_facet / spec_apex = the insertion whose horizon it was asked to search, req the request number, vcur which visible list
+  // the main warp is using (0: w.vis, 1: w.vis2 -- swapped on adoption so that w.vis is always the current one)
+  int hstate = 0, spec_facet = -1, spec_apex = -1, spec_qhead = 0, req = 0;
   while (true) {
     // qh_nextfurthest: the first pending facet of the list = the first ring entry that is still its facet's entry
     int facet = -1;
-    while (qhead < qtail) {
-      const int pos = qhead + lane;
-      int f = -1; bool ok = false;
-      if (pos < qtail) { f = w.ring[pos & w.ring_mask]; ok = (w.mt[f].qpos == pos); }
-      const unsigned m = __ballot_sync(LQRO_FULL, ok);
-      if (m) { const int k = __ffs(m) - 1; facet = __shfl_sync(LQRO_FULL, f, k); qhead += k + 1; break; }
-      qhead = (qhead + 32 < qtail) ? qhead + 32 : qtail;
+    if (COOP && spec_facet >= 0) {
+      // the helper named this facet when the previous insertion had fixed its visible set: every ring entry in front of it is stale
+      // or belongs to a facet that insertion deleted
+      facet = spec_facet; qhead = spec_qhead;
+    } else {
+      while (qhead < qtail) {
+        const int pos = qhead + lane;
+        int f = -1; bool ok = false;
+        if (pos < qtail) { f = w.ring[pos & w.ring_mask]; ok = (w.mt[f].qpos == pos); }
+        const unsigned m = __ballot_sync(LQRO_FULL, ok);
+        if (m) { const int k = __ffs(m) - 1; facet = __shfl_sync(LQRO_FULL, f, k); qhead += k + 1; break; }
+        qhead = (qhead + 32 < qtail) ? qhead + 32 : qtail;
+      }
     }
+    if (COOP && hstate == 2) { hull_pair_bar(mail->bar_id); hstate = 0; }   // (C) the helper's speculative horizon is complete
     if (facet < 0) break;
     ++ins;
-    const hidx vtest = (hidx)(ins << 1), vvis = (hidx)((ins << 1) | 1);
+    const hidx vvis = (hidx)((ins << 1) | 1);
     int nvis = 1;
     double ax, ay, az;
+    int furthest;
     {
       const HOut O = w.ot[facet];
-      const int furthest = w.olist[O.ostart + O.ocount - 1];
+      furthest = w.olist[O.ostart + O.ocount - 1];
       ax = w.hx[furthest]; ay = w.hy[furthest]; az = w.hz[furthest];
+    }
+    const bool adopt = COOP && spec_facet == facet && spec_apex == furthest && !(LQRO_HULL_SPEC_REJECT_MOD > 0 && ins % (LQRO_HULL_SPEC_REJECT_MOD > 0 ? LQRO_HULL_SPEC_REJECT_MOD : 1) == 0);
+    if (COOP) { if (adopt) HULL_COVER(12) else if (spec_facet >= 0) HULL_COVER(13) else HULL_COVER(14) }
+    if (adopt) {
+      // the helper searched this very horizon during the previous partition: take its list, stamp the visible facets
+      nvis = mail->nvis2;
+      if (mail->degen2) degen = 1;
+      hidx* t = w.vis; w.vis = w.vis2; w.vis2 = t;
+      for (int vi = lane; vi < nvis; vi += 32) { const int vf = w.vis[vi]; w.tp[vf].vst = vvis; w.aux[vf] = -1; }
+      if (lane == 0) { w.vpoint[nverts] = (hidx)furthest; w.mt[facet].qpos = -1; }
+      __syncwarp();
+    } else {
       if (lane == 0) {
         w.vpoint[nverts] = (hidx)furthest;  // the apex gets the next vertex id
         w.vis[0] = (hidx)facet;
@@ -745,54 +1018,10 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         w.aux[facet] = -1;
         w.mt[facet].qpos = -1;
       }
+      __syncwarp();
+      hull_horizon<false>(w, w.vis, ins, ax, ay, az, MINvisible, MAXcoplanar, nvis, degen);
     }
-    __syncwarp();
-    {
-      // qh_findhorizon as a wave-parallel breadth-first search.  qhull scans the visible list in order and, per
-      // facet, its neighbours k = 0,1,2; a neighbour is tested once (first occurrence) and appended to the list if
-      // visible.  Processing the (facet, k) slots of one wave in index order, with duplicates inside a 32-slot
-      // chunk resolved to the lowest lane, yields the same list.
-      int wave = 0;
-      while (wave < nvis) {
-        const int wend = nvis;
-        for (int b0 = wave * 3; b0 < wend * 3; b0 += 32) {
-          if (b0 > wave * 3) HULL_COVER(7)
-          const int idx = b0 + lane;
-          int nb = -1 - lane;
-          bool fresh = false;
-          if (idx < wend * 3) {
-            const int vf = w.vis[idx / 3];
-            const int cand = w.tp[vf].nb[idx % 3];
-            if ((w.tp[cand].vst >> 1) != ins) { fresh = true; nb = cand; }
-          }
-          // every fresh slot tests its candidate (a facet reached by several slots of the chunk is tested by each of them: same
-          // result, same stamp); only a VISIBLE facet must enter the list once, through its lowest slot
-          bool isvis = false;
-          if (fresh) {
-            const double d = hdist(w.pl[nb], ax, ay, az);
-            if (d > MINvisible) isvis = true;
-            else if (d > -MAXcoplanar) degen = 1;  // coplanar horizon: qhull would merge
-          }
-          unsigned m = __ballot_sync(LQRO_FULL, isvis);  // every lane has read the stamps before any lane writes one
-          if (fresh) {
-            w.tp[nb].vst = isvis ? vvis : vtest;
-            if (isvis) w.aux[nb] = -1;
-          }
-          if (m & (m - 1)) {  // two or more visible candidates: drop the later slots of a repeated facet
-            for (unsigned rest = m; rest; rest &= rest - 1) {
-              const int j = __ffs(rest) - 1;
-              const int v = __shfl_sync(LQRO_FULL, nb, j);
-              if (lane > j && v == nb) isvis = false;
-            }
-            m = __ballot_sync(LQRO_FULL, isvis);
-          }
-          if (isvis) w.vis[nvis + __popc(m & lt)] = (hidx)nb;
-          nvis += __popc(m);
-          __syncwarp();
-        }
-        wave = wend;
-      }
-    }
+    spec_facet = -1;
     HULL_TIC(2)
     // qh_makenewfacets / qh_makenew_simplicial: one cone facet per horizon ridge, in (visible facet, k) order
     const int apexv = nverts;
@@ -854,68 +1083,26 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
       seqctr += nnew;
     }
     HULL_TIC(3)
-    // qh_makenewplanes + qh_matchnewfacets.  The cone facets {apex, a, b} meet along the ridges {apex, w}; every
-    // ridge vertex w lies on exactly two of them.  sharp test of qh_sharpnewfacets folded in (orthant of the normals).
+    // qh_makenewplanes + qh_matchnewfacets (hull_planes_match): inline, or on the helper warp while this warp gathers the points
     bool sharp = false;
-    {
-      int mdeg = 0, q0s = 0;
-      for (int q0 = 0; q0 < nnew; q0 += 32) {
-        const int q = q0 + lane;
-        int f = 0, sg = 0, v1 = -1, v2 = -1;
-        if (q < nnew) {
-          f = w.newf[q];
-          const HTopo T = w.tp[f];
-          v1 = T.v[1]; v2 = T.v[2];
-          const HPlane P = hull_plane(w, w.vpoint[T.v[0]], w.vpoint[v1], w.vpoint[v2], (T.born & 1) != 0);
-          w.pl[f] = P;
-          if (!(hdist(P, in0, in1, in2) < 0)) degen = 1;
-          sg = (P.n0 > 0 ? 1 : 0) | (P.n1 > 0 ? 2 : 0) | (P.n2 > 0 ? 4 : 0);
-        }
-        if (q0 == 0) q0s = __shfl_sync(LQRO_FULL, sg, 0);
-        if (__any_sync(LQRO_FULL, q < nnew && sg != q0s)) sharp = true;
-        if (nnew <= LQRO_HULL_PAIRMATCH_MAX) {
-          // two lanes per cone facet: lane 2r + (s - 1) holds ridge vertex v[s] of facet r; the other lane with the
-          // same vertex (found by a shuffle sweep over the 2 nnew lanes) is the facet across that ridge = the neighbour opposite the OTHER ridge vertex
-          const int r = lane >> 1, s = 1 + (lane & 1);
-          const int v1r = __shfl_sync(LQRO_FULL, v1, r), v2r = __shfl_sync(LQRO_FULL, v2, r), fr = __shfl_sync(LQRO_FULL, f, r);
-          const int wv = (r < nnew) ? (s == 1 ? v1r : v2r) : (-1 - lane);
-          unsigned other = 0u;
-          for (int j = 0; j < 2 * nnew; ++j) {
-            const int v = __shfl_sync(LQRO_FULL, wv, j);
-            if (j != lane && v == wv) other |= 1u << j;
-          }
-          const int pf = __shfl_sync(LQRO_FULL, fr, other ? __ffs(other) - 1 : lane);
-          if (r < nnew) {
-            if (__popc(other) != 1) mdeg = 2;
-            else w.tp[fr].nb[3 - s] = (hidx)pf;
-          }
-        } else if (q < nnew) {
-          HULL_COVER(0)
-          // large cone: the second facet to reach vown[w] links both
-          HTopo* fa = &w.tp[f];
-#pragma unroll
-          for (int s = 1; s <= 2; ++s) {
-            const int wv = s == 1 ? v1 : v2;
-            const int prev = atomicExch(&w.vown[wv], f);
-            if (prev >= 0) {
-              fa->nb[3 - s] = (hidx)prev;
-              HTopo* fp = &w.tp[prev];
-              if (fp->v[1] == wv) fp->nb[2] = (hidx)f; else fp->nb[1] = (hidx)f;
-            }
-          }
-        }
+    if (COOP) {
+      ++req;
+      if (lane == 0) {
+        mail->cmd = 1; mail->ins = ins; mail->nnew = nnew; mail->req = req;
+        mail->qhead = qhead; mail->qtail = qtail; mail->vvis = vvis;
+        mail->vis_sel = (w.vis2 == w.visB) ? 1 : 0;
       }
-      __syncwarp();
-      if (nnew > LQRO_HULL_PAIRMATCH_MAX) {
-        for (int q = lane; q < nnew; q += 32) {   // reset the scratch, check every ridge found its partner
-          const HTopo T = w.tp[w.newf[q]];
-          w.vown[T.v[1]] = -1; w.vown[T.v[2]] = -1;
-          if (T.nb[1] < 0 || T.nb[2] < 0) mdeg = 2;
-        }
-      }
-      mdeg = __reduce_max_sync(LQRO_FULL, mdeg);
-      __syncwarp();
-      if (mdeg == 2) { failc = 3; break; }
+      hull_pair_bar(mail->bar_id);   // (A)
+      hstate = 1;
+#ifdef LQRO_HULL_EXP_SERIAL
+      hull_pair_bar(mail->bar_id);   // experiment: wait for the planes before the gather
+      hstate = 2;
+#endif
+    } else {
+      hull_planes(w, nnew, in0, in1, in2, sharp, degen);
+      HULL_TIC(4)
+      if (hull_match(w, nnew) == 2) { failc = 3; break; }
+      HULL_TIC(9)   // profiling builds, one warp per hull: ridge matching is charged to "ring + delete"
     }
     HULL_TIC(4)
     // qh_partitionvisible, pass 1: the points to re-partition in qhull's processing order (visible facets in list
@@ -984,6 +1171,27 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         nl += __shfl_sync(LQRO_FULL, incl, 31);
       }
       __syncwarp();
+    }
+    if (COOP) {
+      // next to the helper's ridge matching: the planes of the cone (measured: the same FP64 chain takes 3.5x longer on the helper
+      // warp than here, so it stays on this warp) and qh_deletevisible (the lists of the visible facets have just been gathered)
+      HULL_TIC(5)
+      hull_planes(w, nnew, in0, in1, in2, sharp, degen);
+      for (int vi = lane; vi < nvis; vi += 32) {
+        const int vf = w.vis[vi];
+        w.tp[vf].born = -1;
+        w.mt[vf].qpos = -1;
+        w.freel[nfree + vi] = (hidx)vf;
+      }
+      nfree += nvis;
+      HULL_TIC(9)
+#ifndef LQRO_HULL_EXP_SERIAL
+      hull_pair_bar(mail->bar_id);   // (B) the planes are in shared memory
+#endif
+      HULL_TIC(4)                    // profiling builds: the wait for the helper's planes is charged to "planes"
+      hstate = 2;
+      spec_facet = mail->next_facet; spec_apex = mail->next_apex; spec_qhead = mail->next_qhead;
+      if (mail->mdeg == 2) { failc = 3; break; }
     }
     HULL_TIC(5)
     HULL_COUNT(10, 1)
@@ -1112,17 +1320,25 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
         w.mt[f] = M;
       }
       qtail += nmoved; seqctr += nmoved;
-      // qh_deletevisible: the visible facets leave the hull, their ids go to the free list
-      for (int vi = lane; vi < nvis; vi += 32) {
-        const int vf = w.vis[vi];
-        w.tp[vf].born = -1;
-        w.mt[vf].qpos = -1;
-        w.freel[nfree + vi] = (hidx)vf;
+      // qh_deletevisible: the visible facets leave the hull, their ids go to the free list (two warps per hull: done above)
+      if (!COOP) {
+        for (int vi = lane; vi < nvis; vi += 32) {
+          const int vf = w.vis[vi];
+          w.tp[vf].born = -1;
+          w.mt[vf].qpos = -1;
+          w.freel[nfree + vi] = (hidx)vf;
+        }
+        nfree += nvis;
       }
-      nfree += nvis;
       __syncwarp();
     }
     HULL_TIC(9)
+  }
+  if (COOP) {  // leave the helper at its request barrier with "hull finished"
+    if (hstate == 1) { hull_pair_bar(mail->bar_id); hstate = 2; }
+    if (hstate == 2) hull_pair_bar(mail->bar_id);
+    if (lane == 0) mail->cmd = 0;
+    hull_pair_bar(mail->bar_id);
   }
   // ---- results
   int nf = 0;
@@ -1153,6 +1369,8 @@ __device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool wa
   }
   __syncwarp();
 }
+
+__device__ __forceinline__ void hull_build(HullWs& w, HullCtl& c, int n, bool want_order) { hull_build_t<false>(w, c, nullptr, n, want_order); }
 
 // Nearest facet to v_rel in qhull's facet order (MAIN:825-837, with normal = facet 0's when it wins):
 // distance_f = |n_f . (v_rel - p_f)|, p_f = first listed vertex of f from the UN-ROUNDED cloud (ux,uy,uz);

@@ -452,9 +452,10 @@ class HullHost:
 
     def __init__(self, general=False):
         """general=True: the build that forces the general branches (owner-word ridge matching, wide visited set, shuffle-sweep
-        buckets of the appends) on every cone of more than 2 / 3 / 2 facets, so that small clouds exercise them"""
+        buckets of the appends) on every cone of more than 2 / 3 / 2 facets, so that small clouds exercise them, and (two warps per
+        hull) throws away every third speculative horizon of the helper warp"""
         so = HULLHOST_SO.replace(".so", "_general.so") if general else HULLHOST_SO
-        extra = ["-DLQRO_HULL_PAIRMATCH_MAX=2", "-DLQRO_HULL_NARROW_WALK_MAX=3", "-DLQRO_HULL_SMALLKEY_MAX=2"] if general else []
+        extra = ["-DLQRO_HULL_PAIRMATCH_MAX=2", "-DLQRO_HULL_NARROW_WALK_MAX=3", "-DLQRO_HULL_SMALLKEY_MAX=2", "-DLQRO_HULL_SPEC_REJECT_MOD=3"] if general else []
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in HULLHOST_SRCS):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++20", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-shared", "-pthread"]
                                   + extra + ["-o", so, HULLHOST_SRCS[0]])
@@ -464,8 +465,9 @@ class HullHost:
         lib.hullhost_round6.restype = c_double
         lib.hullhost_round6.argtypes = [c_double]
 
-    def hull(self, pts, mode=0, cap_f=0, vrel=None, ring=0):
-        """ring > 0: size of the pending ring (a power of two below the default, to force its compaction)
+    def hull(self, pts, mode=0, cap_f=0, vrel=None, ring=0, coop=False):
+        """ring > 0: size of the pending ring (a power of two below the default, to force its compaction); coop: two warps per hull
+        (main + helper, as k_hull runs it)
         -> planes (nf,4), verts (nf,3), info dict, escape (distance, normal[3]) or None"""
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         n = len(pts)
@@ -473,17 +475,17 @@ class HullHost:
         planes, verts = np.zeros((maxf, 4)), np.zeros((maxf, 3), dtype=np.int32)
         info, esc = np.zeros(5, dtype=np.int32), np.zeros(4)
         v = None if vrel is None else np.ascontiguousarray(vrel, dtype=np.float64)
-        self.lib.hullhost_build(P(pts), n, mode, cap_f, ring, P(planes), P(verts), maxf, P(info), P(v), P(esc))
+        self.lib.hullhost_build(P(pts), n, mode | (2 if coop else 0), cap_f, ring, P(planes), P(verts), maxf, P(info), P(v), P(esc))
         nf = int(info[0])
         d = dict(nfacets=nf, degenerate=int(info[1]), fail=int(info[2]), ninserted=int(info[3]), best_facet=int(info[4]))
         return planes[:nf], verts[:nf], d, (None if vrel is None else (esc[0], esc[1:4].copy()))
 
     def coverage(self, reset=False):
-        out = np.zeros(12, dtype=np.int64)
+        out = np.zeros(16, dtype=np.int64)
         self.lib.hullhost_coverage(P(out), 1 if reset else 0)
         return dict(zip(("cone_gt16", "cone_gt64", "exhaustive", "old_facet_moved", "ring_compaction", "horizon_flood",
                          "multi_chunk_partition", "multi_chunk_wave", "olist_compaction", "append_moved_segment", "append_sweep_buckets",
-                         "gather_cold"), out.tolist()))
+                         "gather_cold", "spec_adopted", "spec_rejected", "spec_none", "-"), out.tolist()))
 
     def round6(self, a):
         a = np.asarray(a, dtype=np.float64)

@@ -10,7 +10,8 @@
 
 #include <stdlib.h>
 
-// Hull of an AoS cloud.  mode bit 0: apply the 6-digit rendering first (MAIN:765-767).  cap_f <= 0: full-size pool.
+// Hull of an AoS cloud.  mode bit 0: apply the 6-digit rendering first (MAIN:765-767); bit 1: two warps per hull (a main and a
+// helper warp, as k_hull runs it: planes + ridge matching and the speculative horizon search on the helper).  cap_f <= 0: full-size pool.
 // ring > 0: pending ring of that many entries (power of two).
 // Outputs facets in qhull order (planes nf x 4, verts nf x 3 as point indices), info = {nf, degenerate, fail,
 // ninserted, best facet position}, and when vrel != NULL the nearest-facet result (escape[0] distance, [1..3] normal).
@@ -23,7 +24,10 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
   char* cold = (char*)calloc(1, hull_cold_bytes(cap_pts, cf) + 64);
   HullCtl ctl;
   memset(&ctl, 0, sizeof ctl);
-  emu_run_warp([&](int lane) {
+  HullMail mail;
+  memset(&mail, 0, sizeof mail);
+  const bool coop = (mode & 2) != 0;
+  emu_run_block(coop ? 2 : 1, [&](int warp, int lane) {
     HullWs w;
     hull_carve_coords(coords, cap_pts, w);
     hull_carve_hot(hot, cap_pts, cf, w);
@@ -35,8 +39,14 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
       if (mode & 1) { w.hx[m] = round6_dev(a); w.hy[m] = round6_dev(b); w.hz[m] = round6_dev(c); }
       else { w.hx[m] = a; w.hy[m] = b; w.hz[m] = c; }
     }
+    if (coop && warp == 1) {   // the helper warp: waits until the main warp has set up the cloud, then serves it
+      emu_block_barrier();
+      hull_helper(w, ctl, mail);
+      return;
+    }
     __syncwarp();
-    hull_build(w, ctl, n, true);
+    if (coop) { emu_block_barrier(); hull_build_t<true>(w, ctl, &mail, n, true); }
+    else hull_build(w, ctl, n, true);
     if (lane == 0) { info5[0] = ctl.fail ? 0 : ctl.nfacets_out; info5[1] = ctl.degenerate; info5[2] = ctl.fail; info5[3] = ctl.ninserted; info5[4] = -1; }
     if (ctl.fail) return;
     for (int q = lane; q < ctl.nfacets_out && q < maxf; q += 32) {
@@ -57,6 +67,6 @@ extern "C" int hullhost_build(const double* pts, int n, int mode, int cap_f, int
   return 0;
 }
 
-extern "C" void hullhost_coverage(long long* out12, int reset) { for (int i = 0; i < 12; ++i) { out12[i] = g_hull_cover[i]; if (reset) g_hull_cover[i] = 0; } }
+extern "C" void hullhost_coverage(long long* out16, int reset) { for (int i = 0; i < 16; ++i) { out16[i] = g_hull_cover[i]; if (reset) g_hull_cover[i] = 0; } }
 
 extern "C" double hullhost_round6(double x) { return round6_dev(x); }

@@ -33,6 +33,9 @@ struct WarpEmu {
 static thread_local int tl_lane = 0;
 static thread_local unsigned tl_phase = 0;
 static thread_local WarpEmu* tl_warp = nullptr;
+// block of several emulated warps: one barrier all of their threads meet (stands in for a named barrier, bar.sync id, 32 * warps)
+static thread_local std::barrier<>* tl_block_bar = nullptr;
+static inline void emu_block_barrier() { tl_block_bar->arrive_and_wait(); }
 
 static inline int lane_id() { return tl_lane; }
 static inline long long clock64() { return 0; }
@@ -93,6 +96,16 @@ template <typename T> static inline T atomicAdd(T* p, T v) { return __atomic_fet
 template <typename T> static inline T atomicMin(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v < o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 template <typename T> static inline T atomicMax(T* p, T v) { T o = __atomic_load_n(p, __ATOMIC_SEQ_CST); while (v > o && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {} return o; }
 
+// run fn(warp, lane) on nwarps x 32 host threads; the lanes of a warp rendezvous in the warp collectives, all threads in emu_block_barrier()
+template <typename Fn> static inline void emu_run_block(int nwarps, Fn fn) {
+  std::vector<WarpEmu> warps(nwarps);
+  std::barrier<> bar(32 * nwarps);
+  std::vector<std::thread> th;
+  for (int wi = 0; wi < nwarps; ++wi)
+    for (int l = 0; l < 32; ++l)
+      th.emplace_back([&warps, &bar, wi, l, &fn]() { tl_lane = l; tl_phase = 0; tl_warp = &warps[wi]; tl_block_bar = &bar; fn(wi, l); });
+  for (auto& t : th) t.join();
+}
 // run fn(lane) on 32 lockstep host threads
 template <typename Fn> static inline void emu_run_warp(Fn fn) {
   WarpEmu warp;

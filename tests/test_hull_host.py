@@ -15,14 +15,16 @@ def host():
 
 
 def _same_hull(host, oracle, pts, mode=0, cap_f=0):
+    """one warp per hull AND two warps per hull (main + helper with the speculative horizon search, as k_hull runs it)"""
     cloud = oracle.round6(pts) if mode else pts
     oplanes, overts, order, info = oracle.hull(cloud)
-    planes, verts, hi, _ = host.hull(pts, mode=mode, cap_f=cap_f)
-    assert hi["fail"] == 0
-    assert np.array_equal(verts, overts)     # facet list, order and vertex order
-    assert np.array_equal(planes, oplanes)   # same formula, no FMA: identical bits
-    assert hi["ninserted"] == info["ninserted"]
-    assert hi["degenerate"] == (1 if info["degenerate"] else 0)
+    for coop in (False, True):
+        planes, verts, hi, _ = host.hull(pts, mode=mode, cap_f=cap_f, coop=coop)
+        assert hi["fail"] == 0
+        assert np.array_equal(verts, overts)     # facet list, order and vertex order
+        assert np.array_equal(planes, oplanes)   # same formula, no FMA: identical bits
+        assert hi["ninserted"] == info["ninserted"]
+        assert hi["degenerate"] == (1 if info["degenerate"] else 0)
     return len(overts)
 
 
@@ -95,6 +97,8 @@ def test_generated_clouds_and_rare_branches(host, oracle):
     # the outside sets live in contiguous segments: their storage was compacted, a facet that already held points received
     # more (segment moved), and long partitions went through the cold arrays
     assert cov["olist_compaction"] > 0 and cov["append_moved_segment"] > 0 and cov["gather_cold"] > 0, cov
+    # two warps per hull: the helper's speculative horizon was adopted, rejected (new furthest point) and unavailable (empty ring)
+    assert cov["spec_adopted"] > 0 and cov["spec_none"] > 0, cov
 
 
 def test_general_branches_forced(oracle):
@@ -109,7 +113,7 @@ def test_general_branches_forced(oracle):
     p /= np.linalg.norm(p, axis=1, keepdims=True)
     assert _same_hull(general, oracle, p) == 2 * 200 - 4
     cov = general.coverage()
-    assert cov["cone_gt16"] > 0 and cov["cone_gt64"] > 0 and cov["append_sweep_buckets"] > 0, cov
+    assert cov["cone_gt16"] > 0 and cov["cone_gt64"] > 0 and cov["append_sweep_buckets"] > 0 and cov["spec_rejected"] > 0, cov
 
 
 def test_ring_compaction(host, oracle):

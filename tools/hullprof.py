@@ -7,14 +7,15 @@ sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, 'tests'))
 prof_so = os.path.join(root, 'lqr_obstacles_b200', 'liblqro_hullprof.so')
 if '--build' in sys.argv or not os.path.exists(prof_so):
     subprocess.check_call(['nvcc', '-ccbin', '/usr/bin/g++', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-fmad=false',
-                           '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-DLQRO_HULL_PROF', '-o', prof_so,
+                           '-std=c++17', '-shared', '-Xcompiler', '-fPIC', '-DLQRO_HULL_PROF'] + ([os.environ['HULLPROF_EXTRA']] if os.environ.get('HULLPROF_EXTRA') else []) + ['-o', prof_so,
                            os.path.join(root, 'lqr_obstacles_b200', 'csrc', 'lqro_api.cu')])
     if '--build' in sys.argv: sys.exit(0)
 os.environ['LQRO_LIB'] = prof_so
 from lqr_obstacles_b200 import Lqro, swarm
 g = np.load(os.path.join(root, 'tests', 'golden', 'ref_vectors.npz'))
-x, vp = swarm.lattice_swarm((64, 32, 32)); nb = swarm.knn(x[:, :3], 64)
-ctx = Lqro(n_agents=65536, max_neighbors=64, horizon=20); ctx.set_dynamics(g['dyn_A'], g['dyn_B'], g['dyn_L'], g['dyn_E'])
+dims = tuple(int(v) for v in os.environ.get('HULLPROF_DIMS', '64x32x32').split('x'))
+x, vp = swarm.lattice_swarm(dims); nb = swarm.knn(x[:, :3], 64)
+ctx = Lqro(n_agents=len(x), max_neighbors=64, horizon=20); ctx.set_dynamics(g['dyn_A'], g['dyn_B'], g['dyn_L'], g['dyn_E'])
 for r in range(3):
     ctx.step(x, vp, nb if r == 0 else None)
 print('kernel ms (pairs, hull, lp, total)', ctx.last_step_ms(), 'counters', ctx.counters())
