@@ -352,7 +352,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     if (ctx->hull_poll_warps < 1) ctx->hull_poll_warps = 1;
     if (ctx->overlap_sms * ctx->hull_poll_warps > slots) ctx->overlap_sms = slots / ctx->hull_poll_warps;
     ctx->hull_ws_stride = hull_ws_bytes(ctx->cap_pts);
-    CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * (size_t)slots));
+    // global slots: one per hull of the wide launch, then one per hull of the polling launch (the two can be resident together)
+    CUC(cudaMalloc(&ctx->d_hull_ws, ctx->hull_ws_stride * ((size_t)slots + (size_t)ctx->overlap_sms * ctx->hull_poll_warps)));
   }
   CUC(cudaFuncSetAttribute(k_riccati, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * ((sizeof(RiccatiWs) + 7) / 8) * 8)));
 #undef CUC
@@ -684,8 +685,8 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_poll_go, 0));
     CU(cudaEventRecord(ctx->ev_poll0, ctx->hull_stream));
     k_hull<<<ctx->overlap_sms, 64 * ctx->hull_poll_warps, ctx->smem_optin, ctx->hull_stream>>>(
-        p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8, ctx->d_hull_ws,
-        ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
+        p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8,
+        ctx->d_hull_ws + ctx->hull_ws_stride * (size_t)ctx->hull_blocks, ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
     CU(cudaEventRecord(ctx->ev_poll1, ctx->hull_stream));
     LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
     pair_grid = ctx->pair_blocks;
@@ -712,11 +713,13 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[1], st));
-  if (hull_polling) CU(cudaStreamWaitEvent(st, ctx->ev_poll1, 0));
   if (!hull_polling) k_hull_order<<<1, 1024, 0, st>>>(hq, ctx->d_ctr + 2, ctx->d_nreach, ctx->hull_blocks);  // more hulls than hull warps: longest first
+  // the wide launch follows the pair kernel at once: the pollers stop taking tickets when the producers are done and finish the
+  // hulls they hold, on their own global slots, next to it; the LP waits for both
   k_hull<<<ctx->hull_blocks, 64, ctx->hull_smem, st>>>(p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 0, nullptr, 0, nullptr, ctx->d_hull_ws, ctx->hull_ws_stride,
                                                        ctx->d_ctr, ctx->d_prof, ctx->hetero ? ctx->d_agent_class : nullptr, ctx->d_tbs);
   CU(cudaGetLastError());
+  if (hull_polling) CU(cudaStreamWaitEvent(st, ctx->ev_poll1, 0));
   CU(cudaEventRecord(ctx->ev[2], st));
   if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
     // few agents: one warp per agent (the reference's own scenarios are dense: O(K^2) with the inner loops spread over the lanes)
@@ -1020,7 +1023,7 @@ extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5) {
   CU(cudaEventSynchronize(ctx->ev[3]));
   out4[0] = out4[1] = out4[2] = 0.f; out4[3] = (float)ctx->overlap_sms; out5[4] = (float)ctx->prm.first_slots;
   if (!ctx->last_polling) { CU(cudaEventElapsedTime(out4 + 1, ctx->ev[0], ctx->ev[1])); out4[3] = 0.f; return LQRO_OK; }
-  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_poll_go));
+  CU(cudaEventElapsedTime(out4 + 0, ctx->ev[0], ctx->ev_poll0));  // until the polling launch is issued on its stream
   CU(cudaEventElapsedTime(out4 + 1, ctx->ev_poll_go, ctx->ev[1]));
   CU(cudaEventElapsedTime(out4 + 2, ctx->ev_poll0, ctx->ev_poll1));
   return LQRO_OK;

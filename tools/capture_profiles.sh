@@ -6,6 +6,7 @@
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out
 mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q > $O/r2_gputest_final.log 2>&1; tail -2 $O/r2_gputest_final.log
 python bench.py --steps 20 --warmup 5 > $O/r2_bench_n1.json 2> $O/r2_bench_n1.err
 python bench.py --workload swarm4096 --steps 20 --warmup 5 --no-cpu > $O/r2_bench_swarm4096.json 2> $O/r2_bench_swarm4096.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_reference_arm.json 2> $O/r2_bench_reference_arm.err
