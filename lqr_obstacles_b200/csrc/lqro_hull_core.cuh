@@ -707,6 +707,8 @@ __device__ __forceinline__ void hull_helper(const HullWs& w, const HullCtl& c, H
   for (int f = lane; f < w.cap_f; f += 32) w.hst[f] = 0;  // stamps of earlier hulls must not match this one's request numbers
   __syncwarp();
 #if defined(LQRO_HULL_PROF)
+  // NOTE: bar.sync compiles to BAR.SYNC.DEFER_BLOCKING -- a clock read right behind it executes before the barrier releases, so the
+  // interval that FOLLOWS a barrier below contains the wait at that barrier (hp_pl is the wait at (A), not work)
   long long hp_pl = 0, hp_nn = 0, hp_planes = 0, hp_hor = 0, hp_waitA = 0, hp_waitB = 0, hp_waitC = 0, hp_n = 0, t0 = clock64(), t1;
 #define HELPER_TIC(v) { t1 = clock64(); v += t1 - t0; t0 = t1; }
 #else
@@ -761,7 +763,7 @@ __device__ __forceinline__ void hull_helper(const HullWs& w, const HullCtl& c, H
 #endif
   }
 #if defined(LQRO_HULL_PROF)
-  if (lane == 0 && hp_n >= 150) printf("helper: %lld requests, %lld new facets, cycles: planes %lld match %lld, horizon %lld, wait A %lld, wait B %lld, wait C %lld\n", hp_n, hp_nn, hp_pl, hp_planes, hp_hor, hp_waitA, hp_waitB, hp_waitC);
+  if (lane == 0 && hp_n >= 150) printf("helper: %lld requests, %lld new facets, cycles: wait at A %lld, match + next facet %lld, horizon (+ wait at B) %lld, arrival A %lld B %lld C %lld\n", hp_n, hp_nn, hp_pl, hp_planes, hp_hor, hp_waitA, hp_waitB, hp_waitC);
 #endif
 }
 
@@ -1094,10 +1096,6 @@ __device__ __forceinline__ void hull_build_t(HullWs& w, HullCtl& c, HullMail* ma
       }
       hull_pair_bar(mail->bar_id);   // (A)
       hstate = 1;
-#ifdef LQRO_HULL_EXP_SERIAL
-      hull_pair_bar(mail->bar_id);   // experiment: wait for the planes before the gather
-      hstate = 2;
-#endif
     } else {
       hull_planes(w, nnew, in0, in1, in2, sharp, degen);
       HULL_TIC(4)
@@ -1185,10 +1183,8 @@ __device__ __forceinline__ void hull_build_t(HullWs& w, HullCtl& c, HullMail* ma
       }
       nfree += nvis;
       HULL_TIC(9)
-#ifndef LQRO_HULL_EXP_SERIAL
-      hull_pair_bar(mail->bar_id);   // (B) the planes are in shared memory
-#endif
-      HULL_TIC(4)                    // profiling builds: the wait for the helper's planes is charged to "planes"
+      hull_pair_bar(mail->bar_id);   // (B) the cone is matched, the next insertion named
+      HULL_TIC(4)                    // profiling builds: the wait for the helper is charged to "planes + match"
       hstate = 2;
       spec_facet = mail->next_facet; spec_apex = mail->next_apex; spec_qhead = mail->next_qhead;
       if (mail->mdeg == 2) { failc = 3; break; }
