@@ -1,4 +1,4 @@
-// lqro_hull.cuh -- kernels around the hull core (lqro_hull_core.cuh): the hull warp of a step (regenerate the reachable
+// lqro_hull.cuh -- kernels around the hull core (lqro_hull_core.cuh): the hull warps of a step (regenerate the reachable
 // cloud of a queued inside pair, render it to 6 digits, hull it, nearest facet -> half-plane) and the stage kernel behind
 // lqro_convex_hull / lqro_hull_escape.
 #pragma once
@@ -16,7 +16,7 @@ __global__ void k_round6(const double* __restrict__ in, int n, double* __restric
 #define LQRO_HULL_SMEM_FACETS 512
 
 
-// One hull warp: its shared-memory scratch (Translate / dx / xi / step list, hot hull structures, control block)
+// One hull slot (a main warp, in k_hull with a helper warp): its shared-memory scratch (Translate / dx / xi / step list, hot hull structures, control block)
 // and its global slot (un-rounded cloud + full-size fallback pool).
 struct HullWarp {
   PairWarpSmem pw;
@@ -26,7 +26,7 @@ struct HullWarp {
   char* hot;
   char* gslot;
 };
-// bytes of shared memory one hull warp needs after the block tables
+// bytes of shared memory one hull slot needs after the block tables
 __host__ __device__ inline size_t hull_warp_smem_bytes(int H, int P) {
   return hull_align16(sizeof(double) * (3 * (size_t)H + 32 + (H + 1) / 2 + 1)) + hull_hot_bytes(H * P, LQRO_HULL_SMEM_FACETS) +
          hull_align16(sizeof(HullCtl)) + hull_align16(sizeof(HullMail));
@@ -125,7 +125,7 @@ __device__ __forceinline__ void hull_do_pair(const LqroParams& p, const PairTabl
   hull_finish_pair(w, ctl, pw, out, pair, n, counters, prof);
 }
 
-// Hull kernel: one warp per queued inside pair at a time, tickets from a shared counter.  Launched twice per step of a large
+// Hull kernel: two warps (main + helper) per queued inside pair at a time, tickets from a shared counter.  Launched twice per step of a large
 // swarm:
 //  * POLLING (poll != 0), on its own stream and BEFORE the pair kernel, as a concurrent consumer of the hull queue on a few SMs
 //    of its own: LQRO_HULL_POLL_WARPS independent hulls (two warps each) per block, whose shared memory fills an SM, so that no pair CTA can

@@ -14,17 +14,17 @@
 // facet for facet against oracle/hull_cpu.cpp (itself pinned on the reference's fixture and on scipy/qhull).
 // Merging / coplanar handling is not restated: such inputs raise the degenerate flag.
 //
-// MAPPING: ONE WARP PER HULL, sized by measurement.  On the inside pairs of the 65,536-agent bench swarm (151
-// clouds, 14,406 insertions) an insertion sees a median of 3 visible facets, 5 new facets and 2 points to
+// MAPPING: ONE WARP'S LANES PER INSERTION (plus a helper warp for two links of the chain, see HullMail), sized by
+// measurement.  On the inside pairs of the 65,536-agent bench swarm (151 clouds, 14,406 insertions) an insertion sees a median of 3 visible facets, 5 new facets and 2 points to
 // re-partition (90 % of the insertions: <= 5 / 7 / 33): there is no 128-wide work to spread over a CTA, the cost of
 // an insertion is the LENGTH OF ITS DEPENDENT CHAIN.  So everything that defines the order is kept warp-uniform in
 // registers (pool / free-list / vertex / sequence counters, the pending-facet ring), duplicates in the horizon search
 // and the ridge matching are resolved with ballots and short shuffle sweeps instead of shared-memory atomics (match.any
 // measured ~350 cycles per use on sm_100a and was replaced), the facet list is not a
 // linked list any more (a creation sequence number per facet gives qhull's list order; a ring of pending facet ids
-// gives qh_nextfurthest in one parallel probe), appends replay qh_partitionpoint's "furthest stays last" rule per
-// target facet with the bucket leader's state in registers, and visible / new marks are insertion stamps that never
-// need clearing.  Facets are SoA records (plane 32 B, topology 16 B, outside list 16 B) read with one or two
+// gives qh_nextfurthest in one parallel probe), the outside sets are contiguous segments of a bump-allocated array whose
+// appends replay qh_partitionpoint's "furthest stays last" rule as a segmented prefix maximum, and visible / new marks are
+// insertion stamps that never need clearing.  Facets are SoA records (plane 32 B, topology 16 B, outside list 16 B) read with one or two
 // vector loads.
 //
 // DUAL COMPILATION.  This file also compiles as plain C++ on top of tests/hull_host/warp_emul.h (32 host threads in
