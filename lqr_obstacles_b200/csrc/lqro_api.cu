@@ -228,6 +228,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   LqroParams& p = ctx->prm;
   p.N = N; p.local_begin = cfg->local_begin; p.n_local = NL; p.K = K; p.H = H; p.P = P; p.HP = H * P;
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
+  p.r2lo = p.r2 * (1.0 - 1.0e-9); p.r2hi = p.r2 * (1.0 + 1.0e-9);
   p.lp_radius = (float)cfg->lp_radius; p.hull_input = cfg->hull_input; p.fix_facet0 = 1;
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
   // width of the first chunk of the slot-major enumeration (the following ones double, lqro_step.cuh): the inside pairs -- 173 / 41 /

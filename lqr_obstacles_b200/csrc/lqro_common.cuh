@@ -8,7 +8,9 @@
 // no --use_fast_math).  Where a kernel wants a fused multiply-add for speed on a path that provably
 // cannot change a decision it calls fma()/fmaf() explicitly.
 #pragma once
+#ifndef LQRO_HULL_HOST_EMUL  // tests/*_host compile the kernel sources as plain C++ on a lockstep warp emulation
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define LQRO_XD 16
@@ -27,6 +29,7 @@ struct LqroParams {
   double max_speed; // reachable sphere radius
   double r2;        // max_speed^2 (the reference evaluates pow(xr,2) at run time: xr*xr)
   double inv_r2;    // 1/r2, only for the conservative fast test
+  double r2lo, r2hi; // r2 (1 -+ 1e-9): decision band of reach_test_band (lqro_pair.cuh)
   float lp_radius;
   int hull_input;
   int fix_facet0;
@@ -50,7 +53,9 @@ struct LqroTables {
   const double* prn;
 };
 
+#ifndef LQRO_HULL_HOST_EMUL
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
 
 // 3-term dot product in the reference's association: (a0*b0 + a1*b1) + a2*b2   (GJK.h:36-38, MAT:218-231)
 __device__ __forceinline__ double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {

@@ -19,6 +19,15 @@
 #ifndef LQRO_GJK_LANES
 #define LQRO_GJK_LANES 1       // 1: lane-parallel Johnson sub-algorithm (default); 0: register-resident scalar version
 #endif
+#ifndef LQRO_GJK_STEP2
+#define LQRO_GJK_STEP2 1       // 1: the two-point default step written out (gjkl_default_step2); 0: the general lane-parallel step for every simplex size
+#endif
+#ifndef LQRO_GJK_STEP3
+#define LQRO_GJK_STEP3 0       // 1: the three-point default step on the register-resident templates (gjkl_default_step_regs<3>); measured slower (+0.10 ms)
+#endif
+#ifndef LQRO_GJK_STEP4
+#define LQRO_GJK_STEP4 0       // 1: the four-point default step too
+#endif
 #define LQRO_GJK_EPS 1.0e-8    // GJK.h:208
 #define LQRO_GJK_TINY 1.0e-20  // GJK.h:214
 
@@ -117,9 +126,9 @@ __device__ __forceinline__ void gjk_reset_simplex(GjkRegs& g, int subset) {
   }
 }
 
-// GJK.c:593-657.  Returns 1 when a viable subset was found (and the simplex reset to it).
+// GJK.c:593-657 without the reset: the first viable subset in numeric order (0: none); delta[s] of every subset the scan reaches
 template <int SIZE>
-__device__ __forceinline__ int gjk_default_distance(GjkRegs& g) {
+__device__ __forceinline__ int gjk_default_select(GjkRegs& g) {
   int sel = 0;
 #pragma unroll
   for (int s = 1; s < (1 << SIZE); ++s) {
@@ -145,6 +154,12 @@ __device__ __forceinline__ int gjk_default_distance(GjkRegs& g) {
       if (ok && ds >= LQRO_GJK_TINY) sel = s;
     }
   }
+  return sel;
+}
+// GJK.c:593-657.  Returns 1 when a viable subset was found (and the simplex reset to it).
+template <int SIZE>
+__device__ __forceinline__ int gjk_default_distance(GjkRegs& g) {
+  const int sel = gjk_default_select<SIZE>(g);
   if (sel) { gjk_reset_simplex(g, sel); return 1; }
   return 0;
 }
@@ -377,10 +392,119 @@ __device__ __forceinline__ void gjkl_simplex_step(GjkLane& g, int lane, double v
   if (!g.use_default) gjkl_backup_distance(g, size, lane);
 }
 
+// The default procedure for a simplex of TWO points (every GJK run passes through it once), written out: 3 subsets,
+// 2 deltas that are not 1 -- cheaper for every lane to evaluate redundantly than the lane-parallel machinery above.
+// Same operations in the same order as gjk_subterms<2> + gjk_default_distance<2> + gjk_reset_to (GJK.c:527-657, 708-736):
+//   delta_3[0] = prod[1][1] - prod[1][0], delta_3[1] = prod[0][0] - prod[0][1];
+//   subset {0} is chosen when delta_3[1] <= 0, else {1} when delta_3[0] <= 0, else {0,1} when the sum reaches TINY.
+// Returns false WITHOUT touching any state when no subset is viable (the caller then runs the general step, whose backup
+// procedure needs the full tables); otherwise the simplex is reset and delta[s] of the subsets the scan reached is recorded in
+// the owning lanes, as the general step does (the backup procedure of a later iteration may read them).
+__device__ __forceinline__ bool gjkl_default_step2(GjkLane& g, int lane, double v0, double v1, double v2) {
+  const double a0 = v0 - g.sc2[0], a1 = v1 - g.sc2[1], a2 = v2 - g.sc2[2];
+  const double b0 = v0 - g.sc2[3], b1 = v1 - g.sc2[4], b2 = v2 - g.sc2[5];
+  const double p00 = dot3(a0, a1, a2, a0, a1, a2), p01 = dot3(a0, a1, a2, b0, b1, b2), p11 = dot3(b0, b1, b2, b0, b1, b2);
+  const double d30 = p11 - p01, d31 = p00 - p01;
+  if (!(d31 > 0)) {                 // subset 1 = {0}: its own delta is 1, the successor's delta of point 1 is not positive
+    if (lane == 0) g.dsum = 1.0;    // lane_of(1, 0)
+    g.lam[0] = 1.0;                 // 1 / 1
+    g.npts = 1;
+    return true;
+  }
+  if (!(d30 > 0)) {                 // subset 2 = {1}
+    if (lane == 0 || lane == 8) g.dsum = 1.0;  // lane_of(1, 0), lane_of(2, 1)
+    __syncwarp();
+    if (lane < 3) g.sc2[lane] = g.sc2[3 + lane];
+    g.lam[0] = 1.0;
+    g.npts = 1;
+    __syncwarp();
+    return true;
+  }
+  const double ds = d30 + d31;      // (0 + d30) + d31, both positive
+  if (!(ds >= LQRO_GJK_TINY)) return false;
+  if (lane == 0 || lane == 8) g.dsum = 1.0;
+  if (lane == 1) g.dsum = ds;       // lane_of(3, 0)
+  g.lam[0] = d30 / ds;
+  g.lam[1] = d31 / ds;
+  g.npts = 2;
+  return true;
+}
+
+// The default procedure for a simplex of SIZE = 3 (or 4) points evaluated by every lane redundantly with the register-resident
+// templates of the scalar routine (gjk_subterms / gjk_default_select: subset loops unrolled at compile time, the same operations
+// in the same order), fed from and written back to the lane-parallel state.  The lane-parallel recursion pays a chain of
+// dependent shuffles per subset size (and its collectives per test); this pays FP64 instructions (63 for three points) with no
+// dependence between most of them -- the pair kernel is bound by dependent-issue latency, so this is the cheaper currency.
+// Returns false WITHOUT touching any state when no subset is viable (the caller runs the general step and its backup procedure).
+template <int S>
+__device__ __forceinline__ void gjk_pick_subset(const GjkRegs& r, double& ds, double* num) {
+  ds = r.dsum[S];
+#pragma unroll
+  for (int j = 0; j < gjk_card(S); ++j) num[j] = r.del[S][gjk_elt(S, j)];
+}
+template <int SIZE>
+__device__ __forceinline__ bool gjkl_default_step_regs(GjkLane& g, int lane, double v0, double v1, double v2) {
+  GjkRegs r;
+#pragma unroll
+  for (int i = 0; i < SIZE; ++i) { r.c2[i][0] = g.sc2[3 * i]; r.c2[i][1] = g.sc2[3 * i + 1]; r.c2[i][2] = g.sc2[3 * i + 2]; }
+  gjk_subterms<SIZE>(r, v0, v1, v2);
+  const int sel = gjk_default_select<SIZE>(r);
+  if (sel == 0) return false;
+  // delta[s] of the subsets the scan reached goes to the owning lanes, as the general step records it
+#pragma unroll
+  for (int s = 1; s < (1 << SIZE); ++s) {
+    const int owner = gjk_lane_of(s, gjk_elt(s, 0));
+    if (lane == owner && s <= sel) g.dsum = r.dsum[s];
+  }
+  double ds = 1.0, num[4] = {1.0, 1.0, 1.0, 1.0};
+  switch (sel) {
+    case 1: gjk_pick_subset<1>(r, ds, num); break;    case 2: gjk_pick_subset<2>(r, ds, num); break;
+    case 3: gjk_pick_subset<3>(r, ds, num); break;    case 4: gjk_pick_subset<4>(r, ds, num); break;
+    case 5: gjk_pick_subset<5>(r, ds, num); break;    case 6: gjk_pick_subset<6>(r, ds, num); break;
+    case 7: gjk_pick_subset<7>(r, ds, num); break;
+    default:
+      if constexpr (SIZE == 4) {
+        switch (sel) {
+          case 8: gjk_pick_subset<8>(r, ds, num); break;     case 9: gjk_pick_subset<9>(r, ds, num); break;
+          case 10: gjk_pick_subset<10>(r, ds, num); break;   case 11: gjk_pick_subset<11>(r, ds, num); break;
+          case 12: gjk_pick_subset<12>(r, ds, num); break;   case 13: gjk_pick_subset<13>(r, ds, num); break;
+          case 14: gjk_pick_subset<14>(r, ds, num); break;   default: gjk_pick_subset<15>(r, ds, num); break;
+        }
+      }
+      break;
+  }
+  // GJK.c:708-736: the simplex becomes subset `sel` (elements move down in order), lambdas = delta_values / delta
+  __syncwarp();  // every lane has read the simplex points
+  const int cs = __popc(sel);
+  int rem = sel;
+#pragma unroll
+  for (int jj = 0; jj < SIZE; ++jj) {
+    if (jj < cs) {
+      const int oldpos = __ffs(rem) - 1;
+      rem &= rem - 1;
+      if (lane < 3 && oldpos != jj) g.sc2[3 * jj + lane] = g.sc2[3 * oldpos + lane];  // sources lie at or above jj: in-place is safe
+      g.lam[jj] = num[jj] / ds;
+    }
+  }
+  g.npts = cs;
+  __syncwarp();
+  return true;
+}
+
+#ifdef LQRO_PAIR_PROF  // profiling builds: cycles per part of the GJK loop (lane 0), see tools/pairprof.py
+#define GJK_PROF_DECL long long gtick = clock64();
+#define GJK_PROF(q) { const long long tn_ = clock64(); if (gprof) gprof[q] += tn_ - gtick; gtick = tn_; }
+#define GJK_PROF_COUNT(q) { if (gprof) gprof[q] += 1; }
+#else
+#define GJK_PROF_DECL
+#define GJK_PROF(q)
+#define GJK_PROF_COUNT(q)
+#endif
+
 // Warp-cooperative GJK with the lane-parallel sub-algorithm.  scratch: LQRO_GJK_WARP_DOUBLES doubles of shared
 // memory private to the warp.  Same contract as gjk_warp below.
 __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v1, const double v2, const CloudView& cl, int n, double* scratch,
-                                                 double* w1out, double* w2out, int* iters) {
+                                                 double* w1out, double* w2out, int* iters, long long* gprof = nullptr) {
   const int lane = lane_id();
   GjkLane g;
   g.sc2 = scratch;
@@ -416,9 +540,17 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
   int ntests = 0;
   bool exhausted = true;
   double w1[3] = {0, 0, 0}, w2[3] = {0, 0, 0};
+  GJK_PROF_DECL
   while (max_iterations-- > 0) {
+    GJK_PROF(5)
+    const int size_in = g.npts;
     if (g.npts == 1) g.lam[0] = 1.0;
-    else gjkl_simplex_step(g, lane, v0, v1, v2);
+    else if (!(LQRO_GJK_STEP2 && g.npts == 2 && g.use_default && gjkl_default_step2(g, lane, v0, v1, v2)) &&
+             !(LQRO_GJK_STEP3 && g.npts == 3 && g.use_default && gjkl_default_step_regs<3>(g, lane, v0, v1, v2)) &&
+             !(LQRO_GJK_STEP4 && g.npts == 4 && g.use_default && gjkl_default_step_regs<4>(g, lane, v0, v1, v2)))
+      gjkl_simplex_step(g, lane, v0, v1, v2);
+    if (size_in == 2) { GJK_PROF(0) } else if (size_in == 3) { GJK_PROF(1) GJK_PROF_COUNT(6) } else if (size_in == 4) { GJK_PROF(2) GJK_PROF_COUNT(7) }
+    (void)size_in;
     // compute_point (GJK.c:851-862), accumulated from 0; one unrolled body per simplex size (uniform branch)
     switch (g.npts) {
       case 1: gjkl_witness<1>(g, v0, v1, v2, w1, w2); break;
@@ -429,6 +561,7 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
     const double d0 = w2[0] - w1[0], d1 = w2[1] - w1[1], d2 = w2[2] - w1[2];
     sqrd = dot3(d0, d1, d2, d0, d1, d2);
     if (sqrd < LQRO_GJK_EPS) { exhausted = false; break; }  // GJK.c:419-422
+    GJK_PROF(3)
     const double r0 = -d0, r1 = -d1, r2 = -d2;  // reverse_displacementv
     // support of the cloud in direction r (support_simple, GJK.c:770-794)
     double best = -1.7976931348623157e308;
@@ -449,6 +582,7 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
         }
       }
     }
+    GJK_PROF(4)
     {  // warp arg-max, lowest index on ties: see gjk_warp
       const long long bits = __double_as_longlong(best + 0.0);
       const unsigned long long key = (unsigned long long)bits ^ ((unsigned long long)(bits >> 63) | 0x8000000000000000ull);
@@ -482,6 +616,7 @@ __device__ __forceinline__ double gjk_warp_lanes(const double v0, const double v
     if (g.use_default) g.use_default = 0;  // GJK.c:490-496
     else { exhausted = false; break; }
   }
+  GJK_PROF(5)
   if (iters) *iters = ntests;
 #pragma unroll
   for (int d = 0; d < 3; ++d) { w1out[d] = w1[d]; w2out[d] = w2[d]; }

@@ -52,6 +52,7 @@ __device__ inline void inverse3_ref(const double* q, double* out) {
     for (int j = 0; j < n; ++j) out[cp[i] * n + j] = inv[rp[i] * n + j];
 }
 
+#ifndef LQRO_HULL_HOST_EMUL
 // One block of 256 threads; thread t owns element (t/16, t%16) of the 16x16 products.  Each output
 // element is one left-to-right sum (MAT:218-231), so the thread-parallel product is bit-identical to
 // the reference's triple loop.
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(256) k_horizon_tables(const double* __restrict
   }
 }
 
+#endif  // LQRO_HULL_HOST_EMUL
+
 // ------------------------------------------------------------------------------------------------
 struct PairOutputs {
   float* planes;   // [n_local*K][6]
@@ -150,6 +153,16 @@ __device__ __noinline__ bool reach_exact(double a, double b, double c, double r2
 __device__ __forceinline__ bool reach_test(double a, double b, double c, double r2, double inv_r2) {
   const double est = fma(a, a, fma(b, b, c * c)) * inv_r2;
   if (fabs(est - 1.0) > 1.0e-9) return est < 1.0;
+  return reach_exact(a, b, c, r2);
+}
+
+// The same rule with the band on the sum of squares itself (r2lo = r2 (1 - 1e-9), r2hi = r2 (1 + 1e-9)): the fused sum is
+// within 4e-16 relative of the exact a^2 + b^2 + c^2 and the reference's rounded quotient sum within 5e-16 of exact / r2, so
+// below r2lo the reference's sum is < 1 and above r2hi it is > 1; in between (and for NaN) the exact sequence decides.
+__device__ __forceinline__ bool reach_test_band(double a, double b, double c, double r2, double r2lo, double r2hi) {
+  const double ss = fma(a, a, fma(b, b, c * c));
+  if (ss < r2lo) return true;
+  if (ss > r2hi) return false;
   return reach_exact(a, b, c, r2);
 }
 
@@ -288,6 +301,7 @@ __device__ __forceinline__ void carve_pair_smem(double* base, int warp, int H, i
   w.klist = reinterpret_cast<int*>(w.pz + (size_t)H * P);
 }
 
+#ifndef LQRO_HULL_HOST_EMUL
 __device__ __forceinline__ void load_block_tables(double* base, const LqroTables& tb, int H, int P) {
   const int nNF = 16 * 3 * H, nT = 9 * H;
   for (int e = threadIdx.x; e < nNF; e += blockDim.x) base[e] = tb.NFt[e];
@@ -304,6 +318,8 @@ __device__ __forceinline__ void load_block_tables(double* base, const LqroTables
   __syncthreads();
 }
 
+#endif  // LQRO_HULL_HOST_EMUL
+
 // createHalfPlanes (MAIN:1085-1098) after `distance *= 0.5` (MAIN:1401); FP64 -> FP32 narrowing as in
 // Vector3(double,double,double) (V3:113-118).
 __device__ __forceinline__ void write_plane(float* pl, const double* vi, double distance, double n0, double n1, double n2, bool inside) {
@@ -318,6 +334,135 @@ __device__ __forceinline__ void write_plane(float* pl, const double* vi, double 
   pl[5] = (float)n2;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stage 2 of the pair kernel (k_pairs, lqro_step.cuh), one warp per pair: the pieces between "the surviving steps are known"
+// and "GJK".  Plain device functions so that tests/pair_host can run the same source on the warp emulation.
+
+// Translate_k of the surviving steps (klist[0..nk)), reference order (16-term left-to-right sums, MAT:218-231) -> tr[3k..3k+2].
+// Terms whose state difference is exactly zero are skipped when that holds for all of entries 6..15: s + (+-0) == s bit for
+// bit (s is never -0: the sum starts from +0), so the result is the reference's.
+__device__ __forceinline__ void pair_translate_steps(const double* __restrict__ sNFt, const double* dx, const int* klist, int nk, int n3,
+                                                     double* tr) {
+  const int lane = lane_id();
+  const bool tail0 = __ballot_sync(LQRO_FULL, lane >= 6 && lane < 16 && dx[lane] != 0.0) == 0u;
+  for (int e = lane; e < 3 * nk; e += 32) {
+    const int ki = e / 3, c = e - 3 * ki;
+    const int k = klist[ki];
+    const double* nf = sNFt + 3 * k + c;
+    double s = 0;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) s += nf[m * n3] * dx[m];
+    if (!tail0) {
+#pragma unroll
+      for (int m = 6; m < 16; ++m) s += nf[m * n3] * dx[m];
+    }
+    tr[3 * k + c] = s;
+  }
+}
+
+#ifndef LQRO_SCAN_STEPMAJOR
+#define LQRO_SCAN_STEPMAJOR 1  // 0: the candidate-major walk also when P is a compile-time constant (the ablation the step-major walk was measured against)
+#endif
+// Candidates Transform_k (p_s + Translate_k) of the surviving steps + reachable filter (MAIN:687, 691-706) into the cloud
+// (k-major, s ascending: the reference's order, MAIN:1383-1389); returns the number of reachable points.
+// PT > 0: P known at compile time.
+template <int PT>
+__device__ __forceinline__ int pair_scan_cloud(const PairTables& t, const double* tr, const int* klist, int nk, int P, double vr0, double vr1,
+                                               double vr2, double r2, double inv_r2, double r2lo, double r2hi, const CloudView& cl) {
+  const int lane = lane_id();
+  int count = 0;
+  if constexpr (LQRO_SCAN_STEPMAJOR && PT > 0 && PT <= 64) {
+    // Step-major walk.  A lane meets the same one or two samples p_s in every step (s = lane, lane + 32), so they stay in
+    // registers for the whole pair, and Transform_k / Translate_k are read once per step instead of once per 32 candidates
+    // (12 uniform loads per step against 16 per chunk).  Lanes past P in the last chunk of a step redo sample P-1 and are
+    // masked out.  The body of a step is branch-free -- the chunks of a step are independent instruction streams the
+    // scheduler can interleave (the kernel is bound by dependent-issue latency): candidates inside the decision band of
+    // reach_test_band are only NOTED here; if there was one (practically never) the pair is redone by the walk below, whose
+    // test evaluates the reference's own sequence in the band.
+    constexpr int NCH = (PT + 31) / 32;
+    double sx[NCH], sy[NCH], sz[NCH];
+    bool live[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      live[c] = 32 * c + 32 <= PT || lane + 32 * c < PT;
+      const int s = live[c] ? lane + 32 * c : PT - 1;
+      sx[c] = t.sphx[s]; sy[c] = t.sphy[s]; sz[c] = t.sphz[s];
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    bool near = false;
+    int k = nk > 0 ? klist[0] : 0;
+    for (int ki = 0; ki < nk; ++ki) {
+      const double* Tk = t.T + 9 * k;
+      const double* trk = tr + 3 * k;
+      k = klist[ki + 1 < nk ? ki + 1 : ki];  // the next step's index is on its way while this one is worked on
+      const double T0 = Tk[0], T1 = Tk[1], T2 = Tk[2], T3 = Tk[3], T4 = Tk[4], T5 = Tk[5], T6 = Tk[6], T7 = Tk[7], T8 = Tk[8];
+      const double tr0 = trk[0], tr1 = trk[1], tr2 = trk[2];
+      double q0[NCH], q1[NCH], q2[NCH];
+      unsigned mask[NCH];
+      bool pass[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const double v0 = sx[c] + tr0, v1 = sy[c] + tr1, v2 = sz[c] + tr2;  // MAIN:687, the reference's operation order
+        q0[c] = T0 * v0 + T1 * v1 + T2 * v2;
+        q1[c] = T3 * v0 + T4 * v1 + T5 * v2;
+        q2[c] = T6 * v0 + T7 * v1 + T8 * v2;
+        const double a = q0[c] - vr0, b = q1[c] - vr1, cc = q2[c] - vr2;
+        const double ss = fma(a, a, fma(b, b, cc * cc));
+        pass[c] = ss < r2lo && live[c];
+#ifdef LQRO_SCAN_TEST_WIDE_BAND  // emulation build only: note far more candidates than the band holds, so that the redo path runs
+        near = near || (!(ss < 0.5 * r2lo) && !(ss > 2.0 * r2hi) && live[c]);
+#else
+        near = near || (!(ss < r2lo) && !(ss > r2hi) && live[c]);
+#endif
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) mask[c] = __ballot_sync(LQRO_FULL, pass[c]);
+      const bool fits = count + 32 * NCH <= cl.cap;  // warp-uniform: every point of this step lands in the shared part
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int pos = count + __popc(mask[c] & lt);
+        if (pass[c]) {
+          if (fits) { cl.sx[pos] = q0[c]; cl.sy[pos] = q1[c]; cl.sz[pos] = q2[c]; }
+          else cl.put(pos, q0[c], q1[c], q2[c]);
+        }
+        count += __popc(mask[c]);
+      }
+    }
+    if (!__any_sync(LQRO_FULL, near)) {
+      __syncwarp();
+      return count;
+    }
+    __syncwarp();
+    count = 0;
+  }
+  {
+    // candidate-major walk: 32 consecutive (step, sample) candidates per pass
+    const int tot = nk * P;
+    int ki = 0, s = lane;
+    while (s >= P) { s -= P; ++ki; }
+    for (int b0 = 0; b0 < tot; b0 += 32) {
+      const int m = b0 + lane;
+      // lanes past the end of the last chunk redo a valid candidate and are masked out: no divergent body
+      double q0, q1, q2;
+      candidate_point(t.T, t.sphx, t.sphy, t.sphz, tr, klist[ki < nk ? ki : nk - 1], s, q0, q1, q2);
+      const bool pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, r2, inv_r2) && m < tot;
+      const unsigned mask = __ballot_sync(LQRO_FULL, pass);
+      if (pass) {
+        const int pos = count + __popc(mask & ((1u << lane) - 1u));
+        if (count + 32 <= cl.cap) { cl.sx[pos] = q0; cl.sy[pos] = q1; cl.sz[pos] = q2; }  // warp-uniform fast path
+        else cl.put(pos, q0, q1, q2);
+      }
+      count += __popc(mask);
+      s += 32;
+      { const bool wrap = s >= P; s -= wrap ? P : 0; ki += wrap ? 1 : 0; }
+      if (P < 32) while (s >= P) { s -= P; ++ki; }
+    }
+  }
+  __syncwarp();
+  return count;
+}
+
+#ifndef LQRO_HULL_HOST_EMUL
 // ------------------------------------------------------------------------------------------------
 // Stage kernels behind the per-stage C entry points (one warp, one pair / one cloud).
 
@@ -454,3 +599,4 @@ __global__ void __launch_bounds__(32) k_stage_gjk(const double* __restrict__ vre
     *iters = it;
   }
 }
+#endif  // LQRO_HULL_HOST_EMUL

@@ -100,15 +100,17 @@ __host__ __device__ inline long long slot_major_prefix(int n_local, int K, int f
 }
 
 #ifdef LQRO_PAIR_PROF  // per-phase cycle counts of the pair warps (lane 0), profiling builds only
-#define PAIR_PROF_DECL long long pprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ptick = clock64();
+#define PAIR_PROF_DECL long long pprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gprof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long ptick = clock64();
 #define PAIR_PROF(q) { const long long tn_ = clock64(); pprof[q] += tn_ - ptick; ptick = tn_; }
 #define PAIR_PROF_COUNT(q, v) { pprof[q] += (v); }
-#define PAIR_PROF_FLUSH if (lane == 0) { for (int q_ = 0; q_ < 8; ++q_) atomicAdd((unsigned long long*)sy.prof + 16 + q_, (unsigned long long)pprof[q_]); }
+#define PAIR_PROF_FLUSH if (lane == 0) { for (int q_ = 0; q_ < 8; ++q_) { atomicAdd((unsigned long long*)sy.prof + 16 + q_, (unsigned long long)pprof[q_]); atomicAdd((unsigned long long*)sy.prof + 24 + q_, (unsigned long long)gprof[q_]); } }
+#define PAIR_GJK_PROF_ARG , gprof
 #else
 #define PAIR_PROF_DECL
 #define PAIR_PROF(q)
 #define PAIR_PROF_COUNT(q, v)
 #define PAIR_PROF_FLUSH
+#define PAIR_GJK_PROF_ARG
 #endif
 
 // HT, PT > 0: horizon / sample counts known at compile time (table offsets and loop bounds fold into immediates);
@@ -282,48 +284,13 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
         if (k < H && ((km >> k) & 1ull)) w.klist[__popcll(km & ((1ull << k) - 1ull))] = k;
       }
       __syncwarp();
-      // Translate_k of the surviving steps, reference order (16-term left-to-right sums, MAT:218-231).  Terms whose state
-      // difference is exactly zero are skipped when that holds for all of entries 6..15: s + (+-0) == s bit for bit (s is
-      // never -0: the sum starts from +0), so the result is the reference's.
-      const bool tail0 = __ballot_sync(LQRO_FULL, lane >= 6 && lane < 16 && w.dx[lane] != 0.0) == 0u;
-      for (int e = lane; e < 3 * nk; e += 32) {
-        const int ki = e / 3, c = e - 3 * ki;
-        const int k = w.klist[ki];
-        const double* nf = t.NFt + 3 * k + c;
-        double s = 0;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) s += nf[m * n3] * w.dx[m];
-        if (!tail0) {
-#pragma unroll
-          for (int m = 6; m < 16; ++m) s += nf[m * n3] * w.dx[m];
-        }
-        w.tr[3 * k + c] = s;
-      }
+      // Translate_k of the surviving steps in the reference's operation order, then candidates + reachable filter into the
+      // warp's cloud (lqro_pair.cuh)
+      pair_translate_steps(t.NFt, w.dx, w.klist, nk, n3, w.tr);
       __syncwarp();
       PAIR_PROF(1)
       const double vr0 = w.dx[3], vr1 = w.dx[4], vr2 = w.dx[5];
-      int count = 0;
-      const int tot = nk * P;
-      int ki = 0, s = lane;
-      while (s >= P) { s -= P; ++ki; }
-      for (int b0 = 0; b0 < tot; b0 += 32) {
-        const int m = b0 + lane;
-        // lanes past the end of the last chunk redo a valid candidate and are masked out: no divergent body
-        double q0, q1, q2;
-        candidate_point(t.T, t.sphx, t.sphy, t.sphz, w.tr, w.klist[ki < nk ? ki : nk - 1], s, q0, q1, q2);
-        const bool pass = reach_test(q0 - vr0, q1 - vr1, q2 - vr2, p.r2, p.inv_r2) && m < tot;
-        const unsigned mask = __ballot_sync(LQRO_FULL, pass);
-        if (pass) {
-          const int pos = count + __popc(mask & ((1u << lane) - 1u));
-          if (count + 32 <= LQRO_PAIR_CLOUD_CAP) { w.cx[pos] = q0; w.cy[pos] = q1; w.cz[pos] = q2; }  // warp-uniform fast path
-          else cl.put(pos, q0, q1, q2);
-        }
-        count += __popc(mask);
-        s += 32;
-        { const bool wrap = s >= P; s -= wrap ? P : 0; ki += wrap ? 1 : 0; }
-        if (P < 32) while (s >= P) { s -= P; ++ki; }
-      }
-      __syncwarp();
+      const int count = pair_scan_cloud<PT>(t, w.tr, w.klist, nk, P, vr0, vr1, vr2, p.r2, p.inv_r2, p.r2lo, p.r2hi, cl);
       PAIR_PROF(2)
       const int n = count;
       PAIR_PROF_COUNT(7, n)
@@ -334,7 +301,7 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       }
       double gw1[3], gw2[3];
 #if LQRO_GJK_LANES
-      const double sq = gjk_warp_lanes(vr0, vr1, vr2, cl, n, w.gjk, gw1, gw2, nullptr);
+      const double sq = gjk_warp_lanes(vr0, vr1, vr2, cl, n, w.gjk, gw1, gw2, nullptr PAIR_GJK_PROF_ARG);
 #else
       const double sq = gjk_warp(vr0, vr1, vr2, cl, n, gw1, gw2, nullptr);
 #endif

@@ -1,5 +1,13 @@
 cd /root/repo
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python bench.py > gpurun_out/final_bench_default.json 2> gpurun_out/final_bench_default.err; python -c "
-import json; d=json.loads(open('gpurun_out/final_bench_default.json').read().strip().split('\n')[-1]); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['clocks'], d['gpu_launches'], d['parity_sample_ok'])"
+for v in w18 w22 w24; do
+  lib=lqr_obstacles_b200/liblqro${v:+_$v}.so
+  echo "== $lib"
+  LQRO_LIB=$PWD/$lib python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}"
+done
+echo "== polling SM sweep (default lib)"
+for s in 6 8 10 12; do
+  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "overlap_sms [0-9]*\|median ms.*total[^}]*}" | tr '\n' ' '; echo
+done
+for s in 6 8 12 16; do
+  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 32x16x16 2>&1 | tail -1 | grep -o "overlap_sms [0-9]*\|median ms.*total[^}]*}" | tr '\n' ' '; echo
+done

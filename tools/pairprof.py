@@ -21,4 +21,7 @@ c = ctx.hull_cycles()
 names = ['batch+stage1', 'setup+translate', 'scan', 'gjk', 'output', '-']
 tot = c[:6].sum()
 for n, v in zip(names, c): print('%-20s %14d %5.1f%%' % (n, v, 100 * v / tot if tot else 0))
+gn = ['step size 2', 'step size 3', 'step size 4', 'witness + d^2', 'support scan', 'arg-max, G-test, new point', 'steps of size 3', 'steps of size 4']
+gt = c[8:14].sum()
+for n, v in zip(gn, c[8:16]): print('  gjk: %-28s %14d %s' % (n, v, ('%5.1f%%' % (100 * v / gt)) if n[:5] != 'steps' and gt else ''))
 print('stage-2 pairs', c[6], 'reachable points', c[7], 'cycles per stage-2 pair', tot / max(1, c[6]), 'points per pair', c[7] / max(1, c[6]))
