@@ -456,7 +456,7 @@ static int set_dynamics_impl(lqro_ctx* ctx, int cls, const double* A, const doub
       double tf = 0, ef = 0;
       for (int e = 0; e < 9; ++e) { tf += T[9 * k + e] * T[9 * k + e]; if (e % 4 != 0) ef += T[9 * k + e] * T[9 * k + e]; }
       double* c = prn.data() + LQRO_PRN * (size_t)k;
-      c[0] = ctx->prm.max_speed * smax;
+      c[0] = (ctx->prm.max_speed * smax) / ctx->prm.max_speed;  // the quotient the kernel used to form per step and lane (same IEEE division, same bits)
       c[1] = sqrt(tf) * smax * (1.0 + 1e-9);
       c[2] = fabs(T[9 * k + 0]); c[3] = fabs(T[9 * k + 4]); c[4] = fabs(T[9 * k + 8]);
       c[5] = sqrt(ef) * (1.0 + 1e-9);
@@ -722,8 +722,11 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   CU(cudaGetLastError());
   if (hull_polling) CU(cudaStreamWaitEvent(st, ctx->ev_poll1, 0));
   CU(cudaEventRecord(ctx->ev[2], st));
-  if (p.n_local <= 16384 && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
-    // few agents: one warp per agent (the reference's own scenarios are dense: O(K^2) with the inner loops spread over the lanes)
+  // one warp per agent whenever the planes of four agents fit the default shared memory: coalesced status / plane reads into
+  // shared memory, the inner loops of the programs spread over the lanes (dense scenarios: O(K^2)); measured 0.047 ms against
+  // 0.145 ms of the thread-per-agent kernel at 65,536 agents x 64 slots (LQRO_LP_WARP_MAX=<agents> restores the old split)
+  static const int lp_warp_max = getenv("LQRO_LP_WARP_MAX") ? atoi(getenv("LQRO_LP_WARP_MAX")) : (1 << 30);
+  if (p.n_local <= lp_warp_max && (size_t)4 * 12 * p.K * sizeof(float) <= 48 * 1024) {
     k_new_velocity_warp<<<(p.n_local + 3) / 4, 128, (size_t)4 * 12 * p.K * sizeof(float), st>>>(p.n_local, p.K, ctx->d_planes, ctx->d_status, d_vpref,
                                                                                                  p.lp_radius, d_newV, ctx->d_nplanes);
   } else {

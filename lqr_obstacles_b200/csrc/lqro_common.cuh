@@ -43,7 +43,7 @@ struct LqroParams {
 //   T    [H][9]    (C G_k)^-1, row major
 //   sph  [P][3]    samples of the doubled ellipsoid
 //   CG   [H][9]    C G_k (the matrix T_k inverts), row major
-//   prn  [H][8]    pruning constants of step k (see step_prunable): R_k = max_speed*sigma_max(C G_k) (upper bound),
+//   prn  [H][8]    pruning constants of step k (see step_prunable): sigma_max(C G_k) (upper bound; stored as (max_speed*sigma_max)/max_speed),
 //                  kappa_k = |T_k|_F*sigma_max(C G_k), |T_k(0,0)|, |T_k(1,1)|, |T_k(2,2)|, |offdiag(T_k)|_F, |T_k|_F, 0
 struct LqroTables {
   const double* NFt;

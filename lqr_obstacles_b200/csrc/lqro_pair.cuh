@@ -228,7 +228,7 @@ __device__ __forceinline__ bool step_prunable_v(const LqroParams& p, const PairT
   const double need = p.max_speed * (1.0 + 1.0e-6) + 1.0e-11 * (c[6] * (U + c1n + 1.0) + c[1] * v1n);
   // (ball) in position space: |g| > sigma_max * need   (compared as squares, both sides >= 0)
   const double gap2 = fma(g0, g0, fma(g1, g1, g2 * g2));
-  const double rb = (c[0] / p.max_speed) * need;
+  const double rb = c[0] * need;
   if (gap2 * (1.0 - 1.0e-12) > rb * rb) return true;
   // (diagonal) in velocity space: sqrt(sum (T_ii g_i)^2) > need + |offdiag T|_F U
   const double d0 = c[2] * g0, d1 = c[3] * g1, d2 = c[4] * g2;

@@ -28,7 +28,7 @@
 #include "lqro_hull.cuh"
 
 #ifndef LQRO_PAIR_CLOUD_CAP
-#define LQRO_PAIR_CLOUD_CAP 256
+#define LQRO_PAIR_CLOUD_CAP 320  // measured 192 -> 4.87 ms, 256 -> 4.82, 320 -> 4.80, 384 -> 4.78 (does not leave room for 20 warps at H = 30)
 #endif
 #ifndef LQRO_PAIR_MAX_WARPS
 #define LQRO_PAIR_MAX_WARPS 20  // x 32 threads x 96 registers (measured: 16 -> 7.05 ms, 18 -> 7.30, 20 -> 6.84, 22 -> 7.23, 24 -> 7.22)

@@ -1,13 +1,4 @@
 cd /root/repo
-for v in w18 w22 w24; do
-  lib=lqr_obstacles_b200/liblqro${v:+_$v}.so
-  echo "== $lib"
-  LQRO_LIB=$PWD/$lib python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}"
-done
-echo "== polling SM sweep (default lib)"
-for s in 6 8 10 12; do
-  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "overlap_sms [0-9]*\|median ms.*total[^}]*}" | tr '\n' ' '; echo
-done
-for s in 6 8 12 16; do
-  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 32x16x16 2>&1 | tail -1 | grep -o "overlap_sms [0-9]*\|median ms.*total[^}]*}" | tr '\n' ' '; echo
-done
+python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}\|checksum.*"  | tr '\n' ' '; echo
+LQRO_LP_WARP_MAX=100000 python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}\|checksum.*"  | tr '\n' ' '; echo
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py tests/test_gpu_edges.py -m gpu -x -q 2>&1 | tail -3
