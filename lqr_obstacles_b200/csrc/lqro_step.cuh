@@ -78,7 +78,9 @@ __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long i
     const long long padded = (cnt + 31) & ~31ll;  // chunks start on a batch boundary
     if (idx < padded) {
       if (idx >= cnt) return false;
-      il = (int)(idx / wdt);
+      // chunk widths are powers of two except possibly the first: a shift instead of the 64-bit division routine
+      if ((wdt & (wdt - 1)) == 0) il = (int)(idx >> (31 - __clz(wdt)));
+      else il = idx < 0x7fffffffll ? (int)((unsigned)idx / (unsigned)wdt) : (int)(idx / wdt);
       kk = c0 + (int)(idx - (long long)il * wdt);
       return true;
     }
