@@ -1,4 +1,11 @@
 cd /root/repo
-python tools/quick_pairs.py 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}\|checksum.*"  | tr '\n' ' '; echo
-python tools/quick_pairs.py 32x16x16 2>&1 | tail -1 | grep -o "median ms.*total[^}]*}\|checksum.*"  | tr '\n' ' '; echo
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py tests/test_gpu_edges.py -m gpu -x -q 2>&1 | tail -3
+echo "== 16384 agents (one rank of four): polling SMs"
+for s in 12 16 20 24 28; do
+  echo -n "sms $s  "
+  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 32x32x16 2>&1 | tail -1 | grep -o "'polling_hull': [0-9.]*\|median ms.*total[^}]*}\|'inside': [0-9]*" | tr '\n' ' '; echo
+done
+echo "== 32768 agents (one rank of two)"
+for s in 12 16 20; do
+  echo -n "sms $s  "
+  LQRO_HULL_OVERLAP_SMS=$s python tools/quick_pairs.py 32x32x32 2>&1 | tail -1 | grep -o "'polling_hull': [0-9.]*\|median ms.*total[^}]*}\|'inside': [0-9]*" | tr '\n' ' '; echo
+done

@@ -19,7 +19,7 @@ res = {
     "warp_instructions": f("smsp__inst_executed.sum"), "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
     "fp64_pipe_pct": f("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"), "fp64_thread_inst_per_cycle": pc,
     "sm_cycles_elapsed": cyc, "registers_per_thread": int(f("launch__registers_per_thread")),
-    "spill_instructions": f("sass__inst_executed_register_spilling"),
+    "spill_instructions": (f("sass__inst_executed_register_spilling") if d.get("sass__inst_executed_register_spilling", "") not in ("", "n/a", "no data") else 0.0),
     "stalls_per_issue": {k.split("stalled_")[1].split("_per_issue")[0]: float(v) for k, v in d.items()
                          if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")
                          and v not in ("", "no data") and float(v) > 0.05},
