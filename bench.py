@@ -490,6 +490,7 @@ def run_ours(args):
             uid = torch.frombuffer(bytearray(Lqro.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    p2p_gather = bool(world > 1 and ctx.comm_p2p_active())
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -711,7 +712,9 @@ def run_ours(args):
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %d agents, K=%d, H=%d, P=%d, jittered 4 m lattice, seed 20261018" % (args.workload, N, K, H, P),
-                       "parallelism": "agents sharded x%d, ncclAllGather of the 128-B state per step" % world,
+                       "parallelism": "agents sharded x%d, all-gather of the 128-B state per step: %s" % (
+                           world, "every rank pushes its block into the peers' state buffers over NVLink peer memory (csrc/lqro_p2p.cuh)"
+                           if p2p_gather else "ncclAllGather"),
                        "l2": "256 MiB buffer written between timed steps (outside the per-step events)",
                        "pairs_per_step": total_pairs,
                        "dynamics": "controlMatrices on the device (lqro_linearize_discretize + lqro_solve_gains); max relative "

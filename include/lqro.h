@@ -270,6 +270,10 @@ int lqro_sim_last_ms(lqro_ctx* ctx, float* out4);
 /* 128-byte NCCL unique id (rank 0 creates it, the caller ships it to the other ranks). */
 int lqro_comm_unique_id(void* id128);
 int lqro_comm_init(lqro_ctx* ctx, int rank, int world, const void* id128);
+/* 1 when the all-gather of the sharded step runs over NVLink peer memory (every rank pushes its block of the state straight into
+ * every peer's state buffer, csrc/lqro_p2p.cuh; set up inside lqro_comm_init through CUDA IPC handles exchanged over the new
+ * communicator, used only if EVERY rank could map every peer), 0 when it is ncclAllGather (fallback; LQRO_NO_P2P_GATHER=1 forces it). */
+int lqro_comm_p2p_active(lqro_ctx* ctx);
 /* Device pointer to the context's n_agents*16 state buffer; each rank writes its own block
  * [local_begin, local_begin+n_local) there (lqro_upload_local_state or its own kernels). */
 int lqro_device_state(lqro_ctx* ctx, double** d_x);

@@ -37,7 +37,7 @@ EXPORTS = [
     "lqro_set_dynamics", "lqro_get_tables", "lqro_get_spheres", "lqro_step", "lqro_step_device", "lqro_synchronize", "lqro_set_stream",
     "lqro_step_sharded", "lqro_get_pair_results",
     "lqro_get_counters", "lqro_find_fg", "lqro_create_obstacle", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
-    "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_device_state",
+    "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_comm_p2p_active", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms", "lqro_last_step_detail_ms",
     "lqro_debug_hull_cycles", "lqro_debug_hull_longest", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
@@ -129,6 +129,7 @@ def load_library(path=None):
     lib.lqro_round6.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     lib.lqro_comm_unique_id.argtypes = [c_void_p]
     lib.lqro_comm_init.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    lib.lqro_comm_p2p_active.argtypes = [c_void_p]
     lib.lqro_device_state.argtypes = [c_void_p, ctypes.POINTER(c_void_p)]
     lib.lqro_upload_local_state.argtypes = [c_void_p, c_void_p]
     lib.lqro_allgather_state.argtypes = [c_void_p]
@@ -466,6 +467,10 @@ class Lqro:
     def comm_init(self, rank, world, uid):
         buf = (ctypes.c_char * 128).from_buffer_copy(uid)
         self._ck(self.lib.lqro_comm_init(self.h, rank, world, buf))
+
+    def comm_p2p_active(self):
+        """True when the step's all-gather runs over NVLink peer memory (csrc/lqro_p2p.cuh), False when it is ncclAllGather"""
+        return bool(self.lib.lqro_comm_p2p_active(self.h))
 
     def device_state(self):
         p = c_void_p()

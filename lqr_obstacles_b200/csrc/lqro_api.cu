@@ -25,6 +25,7 @@
 #include "lqro_lp.cuh"
 #include "lqro_riccati.cuh"
 #include "lqro_sim.cuh"
+#include "lqro_p2p.cuh"
 
 // ---- minimal NCCL surface, resolved at run time (no link-time dependency; the process may already
 //      hold a libnccl, e.g. the one bundled with PyTorch) ------------------------------------------
@@ -112,6 +113,8 @@ struct lqro_ctx {
   char* d_stage_ws = nullptr; int stage_ws_pts = 0;
   // multi-GPU
   lqro_ncclComm_t comm = nullptr; int rank = 0, world = 1;
+  // all-gather over peer memory (lqro_p2p.cuh): the peers' state buffers and flag words mapped through CUDA IPC
+  bool p2p = false; P2PPeers peers; int* d_p2p_flags = nullptr; int p2p_epoch = 0, p2p_done_epoch = 0; int p2p_blocks = 32;
   // simulator-form agent update (lqro_sim.cuh)
   LqroSimModel* d_sim_model = nullptr; bool have_sim_model = false, sim_attr_set = false; int sim_m_diag = 0;
   char* d_sim_buf = nullptr; size_t sim_buf_bytes = 0;
@@ -177,6 +180,11 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (!ctx) return LQRO_OK;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->p2p) {
+    for (int r = 0; r < ctx->world; ++r)
+      if (r != ctx->rank) { if (ctx->peers.x[r]) cudaIpcCloseMemHandle(ctx->peers.x[r]); if (ctx->peers.flags[r]) cudaIpcCloseMemHandle(ctx->peers.flags[r]); }
+  }
+  if (ctx->d_p2p_flags) cudaFree(ctx->d_p2p_flags);
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   void* ptrs[] = {ctx->d_dyn, ctx->d_NFt, ctx->d_NF, ctx->d_T, ctx->d_sph, ctx->d_CG, ctx->d_prn, ctx->d_x, ctx->d_vpref, ctx->d_newV, ctx->d_dist, ctx->d_nbr,
                   ctx->d_status, ctx->d_nreach, ctx->d_nfacets, ctx->d_nplanes, ctx->d_planes, ctx->d_planes_c, ctx->d_proj, ctx->d_ctr,
@@ -735,6 +743,10 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev[3], st));
+  if (ctx->p2p && ctx->p2p_done_epoch < ctx->p2p_epoch && st == ctx->stream) {  // the step's last reader of the state is behind us: the peers may overwrite their slots
+    k_p2p_done<<<1, 32, 0, st>>>(ctx->peers, ctx->rank, ctx->world, ctx->p2p_epoch);
+    ctx->p2p_done_epoch = ctx->p2p_epoch;
+  }
   ctx->last_polling = hull_polling != 0;
   ctx->launches = 2 + pair_launches + 1;  // pair kernel(s) + wide hull launch + LP + (polling hull launch | queue ordering)
   ctx->stepped = true;
@@ -1268,6 +1280,86 @@ extern "C" int lqro_comm_unique_id(void* id128) {
   return LQRO_OK;
 }
 
+// Peer-memory all-gather (lqro_p2p.cuh): map every peer's state buffer and flag words into this process.  The CUDA IPC handles
+// travel over the NCCL communicator that has just been built (one all-gather of 136 bytes per rank), then every rank reports whether
+// it could open all of them and the path is used only if ALL ranks could -- otherwise (or with LQRO_NO_P2P_GATHER=1, or more than
+// LQRO_P2P_MAX_RANKS ranks) the step keeps ncclAllGather.  Never an error: the fallback is always there.
+static int p2p_setup(lqro_ctx* ctx) {
+  const int world = ctx->world, rank = ctx->rank;
+  ctx->p2p = false;
+  for (int r = 0; r < LQRO_P2P_MAX_RANKS; ++r) { ctx->peers.x[r] = nullptr; ctx->peers.flags[r] = nullptr; }
+  if (world < 2) return LQRO_OK;
+  struct Rec { cudaIpcMemHandle_t hx, hf; int want; int pad; };
+  static_assert(sizeof(Rec) % 8 == 0, "record size");
+  const char* off = getenv("LQRO_NO_P2P_GATHER");
+  int want = (world <= LQRO_P2P_MAX_RANKS && !(off && atoi(off) != 0)) ? 1 : 0;
+  Rec mine;
+  memset(&mine, 0, sizeof mine);
+  if (want) {
+    if (cudaMalloc(&ctx->d_p2p_flags, sizeof(int) * LQRO_P2P_FLAG_INTS) != cudaSuccess) want = 0;
+    else {
+      cudaMemset(ctx->d_p2p_flags, 0, sizeof(int) * LQRO_P2P_FLAG_INTS);
+      cudaDeviceSynchronize();
+      if (cudaIpcGetMemHandle(&mine.hx, ctx->d_x) != cudaSuccess || cudaIpcGetMemHandle(&mine.hf, ctx->d_p2p_flags) != cudaSuccess) want = 0;
+    }
+  }
+  (void)cudaGetLastError();
+  mine.want = want;
+  // every rank takes part in the two exchanges whatever it wants itself: they are collectives
+  char* d_rec = nullptr;
+  CU(cudaMalloc(&d_rec, sizeof(Rec) * (size_t)world));
+  CU(cudaMemcpy(d_rec + sizeof(Rec) * (size_t)rank, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+  const int ncclInt8 = 0;
+  int rc = g_nccl.AllGather(d_rec + sizeof(Rec) * (size_t)rank, d_rec, sizeof(Rec), ncclInt8, ctx->comm, ctx->stream);
+  if (rc != 0) { cudaFree(d_rec); return fail(ctx, LQRO_E_NCCL, "ncclAllGather of the IPC handles failed"); }
+  std::vector<Rec> all(world);
+  CU(cudaMemcpyAsync(all.data(), d_rec, sizeof(Rec) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int ok = 1;
+  for (int r = 0; r < world; ++r) ok = ok && all[r].want;
+  if (ok) {
+    ctx->peers.x[rank] = ctx->d_x; ctx->peers.flags[rank] = ctx->d_p2p_flags;
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == rank) continue;
+      void *px = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&px, all[r].hx, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+      ctx->peers.x[r] = (double*)px;
+      if (cudaIpcOpenMemHandle(&pf, all[r].hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+      ctx->peers.flags[r] = (int*)pf;
+    }
+    (void)cudaGetLastError();
+  }
+  // second exchange: could everybody open everything?
+  Rec vote;
+  memset(&vote, 0, sizeof vote);
+  vote.want = ok;
+  CU(cudaMemcpy(d_rec + sizeof(Rec) * (size_t)rank, &vote, sizeof(Rec), cudaMemcpyHostToDevice));
+  rc = g_nccl.AllGather(d_rec + sizeof(Rec) * (size_t)rank, d_rec, sizeof(Rec), ncclInt8, ctx->comm, ctx->stream);
+  if (rc != 0) { cudaFree(d_rec); return fail(ctx, LQRO_E_NCCL, "ncclAllGather of the IPC votes failed"); }
+  CU(cudaMemcpyAsync(all.data(), d_rec, sizeof(Rec) * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_rec);
+  int all_ok = 1;
+  for (int r = 0; r < world; ++r) all_ok = all_ok && all[r].want;
+  if (!all_ok) {
+    for (int r = 0; r < world; ++r)
+      if (r != rank) {
+        if (ctx->peers.x[r]) cudaIpcCloseMemHandle(ctx->peers.x[r]);
+        if (ctx->peers.flags[r]) cudaIpcCloseMemHandle(ctx->peers.flags[r]);
+        ctx->peers.x[r] = nullptr; ctx->peers.flags[r] = nullptr;
+      }
+    (void)cudaGetLastError();
+    return LQRO_OK;
+  }
+  ctx->p2p = true;
+  ctx->p2p_epoch = ctx->p2p_done_epoch = 0;
+  // blocks of the push kernel: 16 B per thread and peer, a few stores in flight per thread
+  const size_t cnt2 = 8 * (size_t)ctx->prm.n_local;
+  int blocks = (int)((cnt2 + 256 * 4 - 1) / (256 * 4));
+  ctx->p2p_blocks = blocks < 1 ? 1 : (blocks > 2 * ctx->sm_count ? 2 * ctx->sm_count : blocks);
+  return LQRO_OK;
+}
+
 extern "C" int lqro_comm_init(lqro_ctx* ctx, int rank, int world, const void* id128) {
   if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, LQRO_E_ARG, "bad argument");
   if (!load_nccl()) return fail(ctx, LQRO_E_NCCL, "libnccl not found");
@@ -1279,8 +1371,10 @@ extern "C" int lqro_comm_init(lqro_ctx* ctx, int rank, int world, const void* id
   int rc = g_nccl.CommInitRank(&ctx->comm, world, id, rank);
   if (rc != 0) return fail(ctx, LQRO_E_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank failed");
   ctx->rank = rank; ctx->world = world;
-  return LQRO_OK;
+  return p2p_setup(ctx);
 }
+
+extern "C" int lqro_comm_p2p_active(lqro_ctx* ctx) { return ctx && ctx->p2p ? 1 : 0; }
 
 extern "C" int lqro_device_state(lqro_ctx* ctx, double** d_x) {
   if (!ctx || !d_x) return LQRO_E_ARG;
@@ -1316,9 +1410,11 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
-  int queued = 0;
+  int queued = 0, peer_err = 0;
   CU(cudaMemcpyAsync(&queued, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (ctx->p2p) CU(cudaMemcpyAsync(&peer_err, ctx->d_p2p_flags + LQRO_P2P_FLAG_ERR, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (peer_err) return fail(ctx, LQRO_E_NCCL, "peer-memory all-gather timed out waiting for another rank");
   if (queued > ctx->hull_cap) return fail(ctx, LQRO_E_LIMIT, "hull queue overflow: inside pairs beyond max_hull_pairs got no half-plane (status 0x200)");
   return LQRO_OK;
 }
@@ -1327,6 +1423,17 @@ extern "C" int lqro_allgather_state(lqro_ctx* ctx) {
   if (!ctx) return LQRO_E_ARG;
   if (!ctx->comm) return LQRO_OK;  // single GPU
   CU(cudaSetDevice(ctx->cfg.device));
+  if (ctx->p2p) {
+    // peer-memory push (lqro_p2p.cuh); a step that did not report "done reading" yet (lqro_allgather_state called on its own) does so now
+    if (ctx->p2p_done_epoch < ctx->p2p_epoch) {
+      k_p2p_done<<<1, 32, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->world, ctx->p2p_epoch);
+      ctx->p2p_done_epoch = ctx->p2p_epoch;
+    }
+    ++ctx->p2p_epoch;
+    k_p2p_gather<<<ctx->p2p_blocks, 256, 0, ctx->stream>>>(ctx->peers, ctx->rank, ctx->world, 8 * (size_t)ctx->prm.n_local, ctx->p2p_epoch);
+    CU(cudaGetLastError());
+    return LQRO_OK;
+  }
   const size_t cnt = 16 * (size_t)ctx->prm.n_local;
   const int ncclFloat64 = 8;
   int rc = g_nccl.AllGather(ctx->d_x + cnt * ctx->rank, ctx->d_x, cnt, ncclFloat64, ctx->comm, ctx->stream);

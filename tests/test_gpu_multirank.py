@@ -1,6 +1,8 @@
-"""N > 1 on real GPUs (needs >= 2 devices; skipped otherwise): two ranks, one GPU each, agents in two blocks,
-ncclAllGather of the state inside lqro_step_sharded -- the assembled new velocities equal the one-GPU step bit for bit,
-with host-provided neighbour lists and with the device neighbour search."""
+"""N > 1 on real GPUs (needs >= 2 devices; skipped otherwise): two ranks, one GPU each, agents in two blocks, the all-gather of
+the state inside lqro_step_sharded -- over NVLink peer memory (csrc/lqro_p2p.cuh, the default) and as ncclAllGather
+(LQRO_NO_P2P_GATHER=1) -- the assembled new velocities equal the one-GPU step bit for bit, with host-provided neighbour lists and
+with the device neighbour search, over several consecutive steps with a moving swarm (a stale slot of the gathered state, or a
+slot overwritten while the previous step still reads it, would show)."""
 import os
 import socket
 import sys
@@ -40,27 +42,44 @@ def _worker(rank, world, port, outdir):
     nbr = swarm.knn(x[:, :3], K)
     xl, vl, nl = ldist.local_slices(x, vpref, nbr, world, rank)
     lo, n_local = ldist.shard_bounds(len(x), world, rank)
-    out = {}
-    for name, flags, nb in (("host", 0, nl), ("knn", FLAG_DEVICE_KNN, None)):
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")  # one NCCL unique id per communicator
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(Lqro.comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        ctx = Lqro(device=rank, n_agents=len(x), local_begin=lo, n_local=n_local, max_neighbors=K, horizon=20, flags=flags)
-        ctx.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
-        ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        v = ctx.step_sharded(np.ascontiguousarray(xl), np.ascontiguousarray(vl), None if nb is None else np.ascontiguousarray(nb))
-        t = torch.from_numpy(v).cuda()
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        out[name] = torch.cat(parts).cpu().numpy()
-        ctx.close()
+    steps = 4
+    drift = lambda t: 0.03 * t * np.sin(np.arange(len(x)))[:, None] * np.array([1.0, -0.5, 0.25])  # the swarm moves: every step gathers new states
+    out, p2p = {}, {}
+    for gather in ("p2p", "nccl"):
+        os.environ["LQRO_NO_P2P_GATHER"] = "1" if gather == "nccl" else "0"
+        for name, flags, nb in (("host", 0, nl), ("knn", FLAG_DEVICE_KNN, None)):
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")  # one NCCL unique id per communicator
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(Lqro.comm_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(uid, 0)
+            ctx = Lqro(device=rank, n_agents=len(x), local_begin=lo, n_local=n_local, max_neighbors=K, horizon=20, flags=flags)
+            ctx.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
+            ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+            p2p[(gather, name)] = ctx.comm_p2p_active()
+            for t in range(steps):
+                xt = xl.copy()
+                xt[:, :3] += drift(t)[lo:lo + n_local]
+                # host lists: the table of step 0 stays resident (nbr = None afterwards), as a caller with a slowly changing table does
+                v = ctx.step_sharded(np.ascontiguousarray(xt), np.ascontiguousarray(vl), None if (nb is None or t > 0) else np.ascontiguousarray(nb))
+                tt = torch.from_numpy(v).cuda()
+                parts = [torch.empty_like(tt) for _ in range(world)]
+                dist.all_gather(parts, tt)
+                out[(gather, name, t)] = torch.cat(parts).cpu().numpy()
+            ctx.close()
+    os.environ.pop("LQRO_NO_P2P_GATHER", None)
     if rank == 0:
-        one = Lqro(device=0, n_agents=len(x), max_neighbors=K, horizon=20)
-        one.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
-        v_ref = one.step(x, vpref, nbr)
-        one.close()
-        np.save(os.path.join(outdir, "ok.npy"), np.array([np.array_equal(out["host"], v_ref), np.array_equal(out["knn"], v_ref)]))
+        ok = []
+        for name, flags in (("host", 0), ("knn", FLAG_DEVICE_KNN)):
+            one = Lqro(device=0, n_agents=len(x), max_neighbors=K, horizon=20, flags=flags)
+            one.set_dynamics(g["dyn_A"], g["dyn_B"], g["dyn_L"], g["dyn_E"])
+            for t in range(steps):
+                xt = x.copy()
+                xt[:, :3] += drift(t)
+                v_ref = one.step(xt, vpref, nbr if (name == "host" and t == 0) else None)
+                ok += [np.array_equal(out[(gather, name, t)], v_ref) for gather in ("p2p", "nccl")]
+            one.close()
+        np.save(os.path.join(outdir, "ok.npy"), np.array(ok))
+        np.save(os.path.join(outdir, "p2p.npy"), np.array([p2p[("p2p", "host")], p2p[("p2p", "knn")], p2p[("nccl", "host")], p2p[("nccl", "knn")]]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +93,9 @@ def test_two_gpus_match_one(tmp_path, product_lib):
 
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert np.load(os.path.join(str(tmp_path), "ok.npy")).all()
+    act = np.load(os.path.join(str(tmp_path), "p2p.npy"))
+    print("peer-memory all-gather active (default, default, LQRO_NO_P2P_GATHER=1 x 2):", act.tolist())
+    assert not act[2:].any()  # the switch works; whether the default found peer access is the box's business (NCCL is the fallback)
 
 
 def _timestep_worker(rank, world, port, outdir):
