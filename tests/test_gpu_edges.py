@@ -176,3 +176,30 @@ def test_other_horizons_and_sample_counts(golden, oracle, product_lib, H, P):
     assert np.array_equal(v, ov)
     assert (st == 2).sum() >= 1 or H < 20   # short horizons see no inside pair in this swarm
     ctx.close()
+
+
+def test_slot_major_enumeration_widths(golden, product_lib, monkeypatch):
+    """the order in which the pair kernel hands the pairs out (slot-major chunks of width first, first, 2 first, ... -- powers of two
+    take a shift, anything else a division, lqro_step.cuh) does not enter any result: LQRO_FIRST_SLOTS = 3, 5 and 32 against
+    the default, on a swarm large enough for the polling hull launch (>= 2^17 pairs) and on a small one"""
+    for shape, K in (((16, 16, 16), 48), ((6, 6, 4), 24)):
+        x, vp = swarm.lattice_swarm(shape)
+        x[:, :3] *= 0.8
+        nbr = swarm.knn(x[:, :3], K)
+        want = None
+        for first in (None, 3, 5, 32):
+            if first is None:
+                monkeypatch.delenv("LQRO_FIRST_SLOTS", raising=False)
+            else:
+                monkeypatch.setenv("LQRO_FIRST_SLOTS", str(first))
+            ctx = make_ctx(golden, n_agents=len(x), max_neighbors=K, horizon=20)
+            v = ctx.step(x, vp, nbr)
+            res = ctx.pair_results()
+            got = (v, res["status"], res["planes"], res["nreach"])
+            ctx.close()
+            if want is None:
+                want = got
+                assert ((want[1] & 0xFF) == 2).sum() > 0  # hulls among them
+            else:
+                for a, b in zip(got, want):
+                    assert np.array_equal(a, b), (shape, first)

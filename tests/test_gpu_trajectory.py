@@ -39,10 +39,12 @@ def run_pair(reference, golden, starts, goals, steps, H=30):
     nbr = all_pairs_neighbors(n)
     sim = RefSim(reference, starts, goals, seed=1)
     traj_gpu, inside_gpu, nbit = [], 0, 0
+    run_pair.degenerate = 0  # hulls whose merged (non-simplicial) qhull facets the device does not restate (status bit 0x100): must stay 0 here
     for t in range(steps):
         x, xt, vg = sim.state()
         newV = ctx.step(np.ascontiguousarray(x), np.ascontiguousarray(vg), nbr)
         inside_gpu += int(((ctx.pair_results()["status"] & 0xFF) == 2).sum())
+        run_pair.degenerate += int(ctx.counters()["degenerate"])
         sim.set_newv(newV)
         sim.update()
         traj_gpu.append(sim.state()[1].copy())
@@ -58,8 +60,8 @@ def test_six_quads_1000_steps(reference, golden, product_lib):
     S, G = hexagon6()
     tr, tg, ir, ig, ev = run_pair(reference, golden, S, G, 1000)
     err = np.abs(tr[:, :, :3] - tg[:, :, :3]).max()
-    print("6 quads x 1000 steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d, bit-identical states: %s"
-          % (err, ir, ig, ev, np.array_equal(tr, tg)))
+    print("6 quads x 1000 steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d, degenerate hulls %d, bit-identical states: %s"
+          % (err, ir, ig, ev, run_pair.degenerate, np.array_equal(tr, tg)))
     assert ir == ig and ir > 100
     assert err <= 1e-6
     assert np.abs(tr[-1, :, :3] - G).max() < 0.5  # and the quads did reach their goals
@@ -72,7 +74,7 @@ def test_reference_scenarios(reference, golden, product_lib, n, steps):
     S, G = quad24()
     tr, tg, ir, ig, ev = run_pair(reference, golden, S[:n], G[:n], steps)
     err = np.abs(tr[:, :, :3] - tg[:, :, :3]).max()
-    print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d" % (n, steps, err, ir, ig, ev))
+    print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d, degenerate hulls %d" % (n, steps, err, ir, ig, ev, run_pair.degenerate))
     assert ir == ig
     assert err <= 1e-6
 
@@ -86,6 +88,6 @@ def test_large_reference_scenarios(reference, golden, product_lib, n, radius, st
     S, G = circle_antipodal(n, radius)
     tr, tg, ir, ig, ev = run_pair(reference, golden, S, G, steps)
     err = np.abs(tr[:, :, :3] - tg[:, :, :3]).max()
-    print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d" % (n, steps, err, ir, ig, ev))
+    print("%d quads x %d steps: max |dp| = %.3e m, inside pair-steps %d / %d, facet-0 events %d, degenerate hulls %d" % (n, steps, err, ir, ig, ev, run_pair.degenerate))
     assert ir == ig
     assert err <= 1e-6
