@@ -573,6 +573,7 @@ def run_ours(args):
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_launches = ctx.counters()["launches"]
+    nbr_streamed = ctx.last_step_nbr_streamed()
 
     # ---- checksums that do not depend on the number of ranks (wrap-around 64-bit sums, all-reduced) and an UNTIMED
     # oracle sample of this rank's agents
@@ -725,6 +726,9 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * (x_loc.nbytes + vp_loc.nbytes + nbr_loc.nbytes)),
                     "d2h_bytes_per_step": int(world * NL * 24), "ms_per_step": max(e2e_ms, e2e_wall_ms) / args.steps,
                     "api": "lqro_step_sharded (host pinned buffers: state, preferred velocities and neighbour table up, new velocities down, every step)",
+                    "neighbour_table_upload": ("next to the pair kernel: rows in two blocks on a copy stream, the kernel walks the first "
+                                               "eighth of the agents first and waits for the rows of a batch (lqro_last_step_nbr_streamed)"
+                                               if nbr_streamed else "in front of the pair kernel"),
                     "gpu_launches_per_step": e2e_launches, "device_knn": knn_arm},
             "checksum": {"newV_u64": "%016x" % (int(sums[0]) & 0xFFFFFFFFFFFFFFFF), "status_u64": "%016x" % (int(sums[1]) & 0xFFFFFFFFFFFFFFFF),
                          "newV_float_sum": float(fsum[0]), "inside_pairs": int(fsum[1]), "planes": int(fsum[2]),

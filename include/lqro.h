@@ -298,6 +298,13 @@ int lqro_last_step_ms(lqro_ctx* ctx, float* out4);
  * all but [3] SMs), [2] the polling hull launch (its own stream, started together with the pair kernel), [3] its SMs, [4] neighbour
  * slots per agent in the first chunk of the slot-major enumeration; other steps: [1] only ([3] = 0). */
 int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5);
+/* 1 if the host neighbour table (and the preferred velocities) of the last lqro_step / lqro_step_sharded went up NEXT TO the pair
+ * kernel -- rows in two blocks on a copy stream, the kernel waiting for the rows of a batch -- instead of in front of it: steps
+ * of >= 2^21 pairs with the polling hull launch (LQRO_NBR_STREAM_MIN_PAIRS=<pairs> at lqro_create moves the threshold, 0 = always
+ * copy in front).  Results are
+ * the same bits either way (the pairs are enumerated in another order, nothing else).  Replaces the reference's in-place
+ * neighbour lists (Agent.cpp:60-82 fill them, MAIN:1379 walks them). */
+int lqro_last_step_nbr_streamed(lqro_ctx* ctx);
 /* SM-cycle breakdown of the hull kernel of the last step, summed over hulls (development aid):
  * [0] init+simplex [1] partitionall [2] furthest+horizon+cone [3] planes+match [4] list [5] walk [6] redo
  * [7] append [8] delete [9] - [10] insertions [11] points re-partitioned [12] max cycles of one hull

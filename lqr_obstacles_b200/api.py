@@ -39,6 +39,7 @@ EXPORTS = [
     "lqro_get_counters", "lqro_find_fg", "lqro_create_obstacle", "lqro_candidates", "lqro_reachable", "lqro_gjk", "lqro_convex_hull", "lqro_hull_escape",
     "lqro_new_velocity", "lqro_agent_update", "lqro_round6", "lqro_comm_unique_id", "lqro_comm_init", "lqro_comm_p2p_active", "lqro_device_state",
     "lqro_upload_local_state", "lqro_allgather_state", "lqro_measure_fp64_peak", "lqro_measure_fp32_peak", "lqro_last_step_ms", "lqro_last_step_detail_ms",
+    "lqro_last_step_nbr_streamed",
     "lqro_debug_hull_cycles", "lqro_debug_hull_longest", "lqro_riccati_last_ms", "lqro_knn", "lqro_knn_device", "lqro_get_neighbors",
     "lqro_set_dynamics_class", "lqro_set_agent_classes",
     "lqro_sim_default_model", "lqro_sim_set_model", "lqro_sim_update", "lqro_sim_update_device", "lqro_msvc_normals",
@@ -137,6 +138,7 @@ def load_library(path=None):
     lib.lqro_measure_fp32_peak.argtypes = [c_void_p, ctypes.POINTER(c_double)]
     lib.lqro_last_step_ms.argtypes = [c_void_p, c_void_p]
     lib.lqro_last_step_detail_ms.argtypes = [c_void_p, c_void_p]
+    lib.lqro_last_step_nbr_streamed.argtypes = [c_void_p]
     lib.lqro_debug_hull_cycles.argtypes = [c_void_p, c_void_p]
     lib.lqro_debug_hull_longest.argtypes = [c_void_p, c_void_p]
     lib.lqro_sim_default_model.argtypes = [ctypes.POINTER(SimModel)]
@@ -337,6 +339,10 @@ class Lqro:
         t = np.zeros(5, dtype=np.float32)
         self._ck(self.lib.lqro_last_step_detail_ms(self.h, _p(t)))
         return dict(setup=float(t[0]), pairs=float(t[1]), polling_hull=float(t[2]), overlap_sms=int(t[3]), first_slots=int(t[4]))
+
+    def last_step_nbr_streamed(self):
+        """True if the host neighbour table of the last host-buffer step went up next to the pair kernel (lqro.h)."""
+        return bool(self.lib.lqro_last_step_nbr_streamed(self.h))
 
     def hull_longest(self):
         c = np.zeros(16, dtype=np.int64)

@@ -86,6 +86,12 @@ struct lqro_ctx {
   cudaStream_t copy_stream = nullptr, chunk_stream[LQRO_NBR_CHUNKS] = {nullptr};
   cudaEvent_t ev_ready = nullptr, ev_up[LQRO_NBR_CHUNKS] = {nullptr}, ev_done[LQRO_NBR_CHUNKS] = {nullptr};
   int *d_identity = nullptr, *d_chunk_ctr = nullptr;
+  // neighbour table of a step uploaded NEXT TO the pair kernel of the polling-hull step (launch_step): rows in two blocks on their
+  // own stream, a mark word written by the copy engine behind each block, the pair kernel waits for the rows of a batch
+  size_t nbr_stream_min_pairs = (size_t)1 << 21; bool last_nbr_streamed = false;
+  const int* h_nbr_streamed = nullptr; const double* h_vpref_streamed = nullptr;
+  cudaStream_t nbr_stream = nullptr; cudaEvent_t ev_nbr_go = nullptr, ev_nbr_up = nullptr;
+  int *d_nbr_mark = nullptr, *h_nbr_marks = nullptr;
   // step buffers
   double *d_x = nullptr, *d_vpref = nullptr, *d_newV = nullptr, *d_dist = nullptr;
   int *d_nbr = nullptr, *d_status = nullptr, *d_nreach = nullptr, *d_nfacets = nullptr, *d_nplanes = nullptr;
@@ -204,6 +210,11 @@ extern "C" int lqro_destroy(lqro_ctx* ctx) {
   if (ctx->ev_poll1) cudaEventDestroy(ctx->ev_poll1);
   if (ctx->ev_poll0) cudaEventDestroy(ctx->ev_poll0);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->nbr_stream) cudaStreamDestroy(ctx->nbr_stream);
+  if (ctx->ev_nbr_go) cudaEventDestroy(ctx->ev_nbr_go);
+  if (ctx->ev_nbr_up) cudaEventDestroy(ctx->ev_nbr_up);
+  if (ctx->d_nbr_mark) cudaFree(ctx->d_nbr_mark);
+  if (ctx->h_nbr_marks) cudaFreeHost(ctx->h_nbr_marks);
   if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
   for (int c = 0; c < LQRO_NBR_CHUNKS; ++c) {
     if (ctx->chunk_stream[c]) cudaStreamDestroy(ctx->chunk_stream[c]);
@@ -233,6 +244,8 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   if (ctx->cfg.n_local <= 0) ctx->cfg.n_local = cfg->n_agents - cfg->local_begin;
   if (ctx->cfg.local_begin + ctx->cfg.n_local > cfg->n_agents) { delete ctx; return fail(nullptr, LQRO_E_ARG, "local block exceeds n_agents"); }
   const int N = cfg->n_agents, NL = ctx->cfg.n_local, K = cfg->max_neighbors, H = cfg->horizon, P = cfg->n_samples;
+  // pair ids, queue entries and the enumeration of a launch (lqro_enum.cuh: each of <= 2 * 8 chunks padded to 32) are 32-bit
+  if ((long long)NL * K + 2 * 8 * 32 >= 0x7fffffffLL) { delete ctx; return fail(nullptr, LQRO_E_LIMIT, "n_local * max_neighbors must stay below 2^31 pairs per rank"); }
   LqroParams& p = ctx->prm;
   p.N = N; p.local_begin = cfg->local_begin; p.n_local = NL; p.K = K; p.H = H; p.P = P; p.HP = H * P;
   p.max_speed = cfg->max_speed; p.r2 = cfg->max_speed * cfg->max_speed; p.inv_r2 = 1.0 / p.r2;
@@ -241,6 +254,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
   p.prune = (cfg->flags & LQRO_FLAG_NO_PRUNE) ? 0 : 1;
   // width of the first chunk of the slot-major enumeration (the following ones double, lqro_step.cuh): the inside pairs -- 173 / 41 /
   // 10 / 1 / 0 ... of the 225 of the bench swarm sit in slots 0 / 1 / 2 / 3 / 4+ -- should reach the hull queue first
+  p.seg_split = 0;
   p.first_slots = 1;
   if (const char* e = getenv("LQRO_FIRST_SLOTS")) p.first_slots = atoi(e);
   if (p.first_slots < 1) p.first_slots = 1;
@@ -352,6 +366,7 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     // or LQRO_FLAG_NO_OVERLAP: pair kernel on every SM, hulls afterwards
     ctx->overlap_sms = (cfg->flags & LQRO_FLAG_NO_OVERLAP) ? 0 : 12;  // measured at 65,536 x 64: 8 -> 6.79 ms (hulls behind), 12 -> 6.40, 16 -> 6.59
     if (const char* e = getenv("LQRO_HULL_OVERLAP_SMS")) ctx->overlap_sms = atoi(e);
+    if (const char* e = getenv("LQRO_NBR_STREAM_MIN_PAIRS")) { const long long v = atoll(e); ctx->nbr_stream_min_pairs = v > 0 ? (size_t)v : ~(size_t)0; }
     if (ctx->overlap_sms < 0) ctx->overlap_sms = 0;
     if (ctx->overlap_sms > ctx->sm_count / 2) ctx->overlap_sms = ctx->sm_count / 2;
     // hull warps per block of the polling launch: as many as the opt-in shared memory holds, at most LQRO_HULL_POLL_WARPS (its
@@ -604,6 +619,35 @@ extern "C" int lqro_get_neighbors(lqro_ctx* ctx, int* nbr) {
 }
 
 // ---- the step ----------------------------------------------------------------------------------------
+// batches of the nearest 8 slots in a polling-hull step: narrow enough for >= 6 batches per pair warp of the grid (a batch is one
+// warp's sequential job)
+static int polling_batch_width(const lqro_ctx* ctx) {
+  const LqroParams& p = ctx->prm;
+  const long long narrow = slot_major_prefix(p.n_local, p.K, p.first_slots, 8);
+  const int pair_grid = ctx->pair_blocks - ctx->overlap_sms;
+  int bw = 32;
+  while (bw > 2 && narrow / bw < 6LL * pair_grid * ctx->pair_warps) bw >>= 1;
+  return bw;
+}
+// Host neighbour table (and preferred velocities) of a host-buffer step: which way up?  Blocks next to several pair launches
+// (no polling hull launch), rows streamed next to THE pair launch of a polling-hull step, or a plain copy in front of the step.
+// Streaming starts at 2^21 pairs (LQRO_NBR_STREAM_MIN_PAIRS; 0 = never): the agents of the second block surface their inside pairs a
+// twelfth of the pair kernel later, which a smaller rank -- whose polling hull launch already ends with the pair kernel -- would
+// pay for with exposed hull time.
+static int upload_step_inputs(lqro_ctx* ctx, const double* vpref, const int* nbr, cudaStream_t st) {
+  const LqroParams& p = ctx->prm;
+  const bool big = nbr && !ctx->hetero && !ctx->fused_hull && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
+  const bool chunked = big && ctx->overlap_sms == 0;
+  const bool streamed = nbr && !ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && p.n_local >= 2048 && (size_t)p.n_local * p.K >= ctx->nbr_stream_min_pairs &&
+                        (size_t)p.n_local * p.K >= ((size_t)1 << 17);  // the polling-hull step of launch_step
+  ctx->h_nbr_chunked = chunked ? nbr : nullptr;
+  ctx->h_nbr_streamed = streamed ? nbr : nullptr;
+  ctx->h_vpref_streamed = streamed ? vpref : nullptr;
+  if (!streamed) CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
+  if (nbr && !chunked && !streamed) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
+  return LQRO_OK;
+}
+
 static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, const int* d_nbr, double* d_newV, cudaStream_t st) {
   const LqroParams& p = ctx->prm;
   PairOutputs po{ctx->d_planes, ctx->d_status, ctx->d_nreach, ctx->d_dist, ctx->d_nfacets};
@@ -613,8 +657,9 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
   // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
   //        [8] pair CTAs that have started
-  StepSync sy{ctx->d_ctr + 0, 0, 32, ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  StepSync sy{ctx->d_ctr + 0, make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32), ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
   int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_polling = 0;
+  bool nbr_streamed = false;
   CU(cudaEventRecord(ctx->ev[0], st));
 #define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
   k_pairs<F, HT, PT><<<pair_grid, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,                \
@@ -662,6 +707,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       CU(cudaStreamWaitEvent(pst, ctx->ev_up[c], 0));
       LqroParams pc = p;
       pc.n_local = cnt;
+      sy.plan = make_batch_plan(cnt, p.K, p.first_slots, 0, 0, 32);
       sy.batch_counter = ctx->d_chunk_ctr + c;
       const int* ord = ctx->d_identity + off;
       ovf_base = ctx->d_pair_ovf + (size_t)c * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * ctx->pair_warps;
@@ -672,6 +718,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     }
     pst = st;
     ovf_base = ctx->d_pair_ovf;
+    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32);
   } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
     // LARGE SWARM: the hull queue gets a CONCURRENT CONSUMER.  A polling hull launch (k_hull, poll = 1) goes first, on its own
     // stream and on overlap_sms SMs that its shared-memory request fills; the pair kernel runs next to it on the other SMs and
@@ -685,11 +732,42 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       CU(cudaEventCreate(&ctx->ev_poll0));
     }
     pair_grid = ctx->pair_blocks - ctx->overlap_sms;
-    // batches of the nearest 8 slots: narrow enough for >= 6 batches per pair warp of the grid (a batch is one warp's sequential job)
-    const long long narrow = slot_major_prefix(p.n_local, p.K, p.first_slots, 8);
-    int bw = 32;
-    while (bw > 2 && narrow / bw < 6LL * pair_grid * ctx->pair_warps) bw >>= 1;
-    sy.narrow_pairs = (int)narrow; sy.batch_width = bw;
+    LqroParams pp = p;
+    if (ctx->h_nbr_streamed) {
+      // THE NEIGHBOUR TABLE COMES UP NEXT TO THE PAIR KERNEL (host-buffer steps, upload_step_inputs): its rows in two blocks on
+      // their own stream -- the first eighth of the agents, then the rest -- each followed by a 4-byte copy of "rows present" into
+      // d_nbr_mark; the pair kernel enumerates the first block's agents first (LqroParams::seg_split) and waits for the mark
+      // before it reads the rows of a batch (StepSync::nbr_mark).  The copies depend on nothing the kernel produces (they wait
+      // for the state upload and the previous step only), so the wait always ends; the preferred velocities follow the table
+      // and the LP waits for them.  65,536 x 64: 16.8 MB = 0.3 ms of PCIe time under the pair kernel instead of in front of it.
+      const int* h_nbr = ctx->h_nbr_streamed;
+      const double* h_vp = ctx->h_vpref_streamed;
+      ctx->h_nbr_streamed = nullptr; ctx->h_vpref_streamed = nullptr;
+      if (!ctx->nbr_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->nbr_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_nbr_go, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_nbr_up, cudaEventDisableTiming));
+        CU(cudaMalloc(&ctx->d_nbr_mark, sizeof(int)));
+        CU(cudaHostAlloc(&ctx->h_nbr_marks, 2 * sizeof(int), cudaHostAllocDefault));
+      }
+      // the first segment's pairs take 14 times longer to work on than the rest of the table takes to arrive (1.1 ns against
+      // 0.08 ns per pair): a twelfth of the agents leaves a margin and delays the inside pairs of the others as little as possible
+      const int n_a = (p.n_local / 12) & ~31;  // whole batches; n_local >= 2048 here
+      ctx->h_nbr_marks[0] = n_a; ctx->h_nbr_marks[1] = p.n_local;
+      CU(cudaMemsetAsync(ctx->d_nbr_mark, 0, sizeof(int), st));
+      CU(cudaEventRecord(ctx->ev_nbr_go, st));  // state on the device, mark cleared, previous step finished (it read d_nbr)
+      CU(cudaStreamWaitEvent(ctx->nbr_stream, ctx->ev_nbr_go, 0));
+      const size_t row = sizeof(int) * (size_t)p.K;
+      CU(cudaMemcpyAsync(ctx->d_nbr, h_nbr, row * n_a, cudaMemcpyHostToDevice, ctx->nbr_stream));
+      CU(cudaMemcpyAsync(ctx->d_nbr_mark, ctx->h_nbr_marks + 0, sizeof(int), cudaMemcpyHostToDevice, ctx->nbr_stream));
+      CU(cudaMemcpyAsync(ctx->d_nbr + (size_t)n_a * p.K, h_nbr + (size_t)n_a * p.K, row * (size_t)(p.n_local - n_a), cudaMemcpyHostToDevice, ctx->nbr_stream));
+      CU(cudaMemcpyAsync(ctx->d_nbr_mark, ctx->h_nbr_marks + 1, sizeof(int), cudaMemcpyHostToDevice, ctx->nbr_stream));
+      if (h_vp) CU(cudaMemcpyAsync(ctx->d_vpref, h_vp, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, ctx->nbr_stream));
+      CU(cudaEventRecord(ctx->ev_nbr_up, ctx->nbr_stream));
+      pp.seg_split = n_a;
+      sy.nbr_mark = ctx->d_nbr_mark;
+      nbr_streamed = true;
+    }
     CU(cudaEventRecord(ctx->ev_poll_go, st));  // counters cleared, previous step finished
     CU(cudaStreamWaitEvent(ctx->hull_stream, ctx->ev_poll_go, 0));
     CU(cudaEventRecord(ctx->ev_poll0, ctx->hull_stream));
@@ -697,9 +775,12 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
         p, ctx->tb, d_x, d_nbr, po, hq, ctx->d_ctr + 2, 1, ctx->d_ctr + 4, ctx->pair_warps * pair_grid, ctx->d_ctr + 8,
         ctx->d_hull_ws + ctx->hull_ws_stride * (size_t)ctx->hull_blocks, ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
     CU(cudaEventRecord(ctx->ev_poll1, ctx->hull_stream));
-    LQRO_LAUNCH_PAIRS_ANY(p, ctx->tb, (const int*)nullptr);
+    // batches of the nearest 8 slots (of either segment): narrow enough for >= 6 batches per pair warp of the grid
+    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, pp.seg_split, 8, polling_batch_width(ctx));
+    LQRO_LAUNCH_PAIRS_ANY(pp, ctx->tb, (const int*)nullptr);
+    if (nbr_streamed) CU(cudaStreamWaitEvent(st, ctx->ev_nbr_up, 0));  // nothing to wait for once the pair kernel has ended, but the LP reads d_vpref
     pair_grid = ctx->pair_blocks;
-    sy.narrow_pairs = 0; sy.batch_width = 32;
+    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32); sy.nbr_mark = nullptr;
     ++pair_launches;
     hull_polling = 1;
   } else if (!ctx->hetero) {
@@ -712,6 +793,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       if (!ctx->cls_count[c]) continue;
       LqroParams pc = p;
       pc.n_local = ctx->cls_count[c];
+      sy.plan = make_batch_plan(pc.n_local, p.K, p.first_slots, 0, 0, 32);
       LqroTables tbc = ctx->tb;
       tbc.NFt = ctx->cls[c].NFt; tbc.T = ctx->cls[c].T; tbc.CG = ctx->cls[c].CG; tbc.prn = ctx->cls[c].prn;
       sy.batch_counter = ctx->d_cls_ctr + c;
@@ -748,6 +830,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     ctx->p2p_done_epoch = ctx->p2p_epoch;
   }
   ctx->last_polling = hull_polling != 0;
+  ctx->last_nbr_streamed = nbr_streamed;
   ctx->launches = 2 + pair_launches + 1;  // pair kernel(s) + wide hull launch + LP + (polling hull launch | queue ordering)
   ctx->stepped = true;
   return LQRO_OK;
@@ -758,6 +841,7 @@ extern "C" int lqro_step_device(lqro_ctx* ctx, const double* d_x, const double* 
   if (!ctx->have_dynamics) return fail(ctx, LQRO_E_STATE, "set_dynamics first");
   if (!d_nbr && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: pass d_nbr, or step once with a host table / lqro_knn_device first");
   CU(cudaSetDevice(ctx->cfg.device));
+  ctx->h_nbr_chunked = nullptr; ctx->h_nbr_streamed = nullptr; ctx->h_vpref_streamed = nullptr;  // device-resident inputs: nothing comes from the host
   return launch_step(ctx, d_x ? d_x : ctx->d_x, d_vpref, d_nbr ? d_nbr : ctx->d_nbr, d_newV, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
@@ -770,19 +854,18 @@ extern "C" int lqro_step(lqro_ctx* ctx, const double* x, const double* vpref, co
   const LqroParams& p = ctx->prm;
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(ctx->d_x, x, sizeof(double) * 16 * (size_t)p.N, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  // large swarms: the neighbour table goes up in blocks, overlapped with the pair kernel (see launch_step)
-  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && ctx->overlap_sms == 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
-  if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
-  ctx->h_nbr_chunked = chunked ? nbr : nullptr;
-  int rc = LQRO_OK;
+  // large swarms: the neighbour table goes up next to the pair kernel (see upload_step_inputs, launch_step)
+  int rc = upload_step_inputs(ctx, vpref, nbr, st);
+  if (rc) return rc;
   if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
-  int queued = 0;
-  CU(cudaMemcpyAsync(&queued, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int ctr9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // d_ctr[1..9]: [0] hull queue length ... [8] neighbour rows that never arrived
+  CU(cudaMemcpyAsync(ctr9, ctx->d_ctr + 1, sizeof(ctr9), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  const int queued = ctr9[0];
+  if (ctr9[8]) return fail(ctx, LQRO_E_CUDA, "the neighbour table did not arrive on the device while the pair kernel waited for it");
   if (queued > ctx->hull_cap) return fail(ctx, LQRO_E_LIMIT, "hull queue overflow: inside pairs beyond max_hull_pairs got no half-plane (status 0x200)");
   return LQRO_OK;
 }
@@ -1044,6 +1127,8 @@ extern "C" int lqro_last_step_detail_ms(lqro_ctx* ctx, float* out5) {
   CU(cudaEventElapsedTime(out4 + 2, ctx->ev_poll0, ctx->ev_poll1));
   return LQRO_OK;
 }
+
+extern "C" int lqro_last_step_nbr_streamed(lqro_ctx* ctx) { return ctx && ctx->stepped && ctx->last_nbr_streamed ? 1 : 0; }
 
 extern "C" int lqro_last_step_ms(lqro_ctx* ctx, float* out4) {
   if (!ctx || !out4) return LQRO_E_ARG;
@@ -1400,21 +1485,20 @@ extern "C" int lqro_step_sharded(lqro_ctx* ctx, const double* x_local, const dou
   const LqroParams& p = ctx->prm;
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(ctx->d_x + 16 * (size_t)p.local_begin, x_local, sizeof(double) * 16 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(ctx->d_vpref, vpref, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyHostToDevice, st));
-  const bool chunked = nbr && !ctx->hetero && !ctx->fused_hull && ctx->overlap_sms == 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 20);
-  if (nbr && !chunked) CU(cudaMemcpyAsync(ctx->d_nbr, nbr, sizeof(int) * (size_t)p.n_local * p.K, cudaMemcpyHostToDevice, st));
-  ctx->h_nbr_chunked = chunked ? nbr : nullptr;
-  int rc = lqro_allgather_state(ctx);
+  int rc = upload_step_inputs(ctx, vpref, nbr, st);
   if (rc) return rc;
+  if ((rc = lqro_allgather_state(ctx))) return rc;
   if (!nbr && ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   rc = launch_step(ctx, ctx->d_x, ctx->d_vpref, ctx->d_nbr, ctx->d_newV, st);
   if (rc) return rc;
   CU(cudaMemcpyAsync(newV, ctx->d_newV, sizeof(double) * 3 * (size_t)p.n_local, cudaMemcpyDeviceToHost, st));
-  int queued = 0, peer_err = 0;
-  CU(cudaMemcpyAsync(&queued, ctx->d_ctr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int ctr9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, peer_err = 0;  // d_ctr[1..9], as in lqro_step
+  CU(cudaMemcpyAsync(ctr9, ctx->d_ctr + 1, sizeof(ctr9), cudaMemcpyDeviceToHost, st));
   if (ctx->p2p) CU(cudaMemcpyAsync(&peer_err, ctx->d_p2p_flags + LQRO_P2P_FLAG_ERR, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (peer_err) return fail(ctx, LQRO_E_NCCL, "peer-memory all-gather timed out waiting for another rank");
+  const int queued = ctr9[0];
+  if (ctr9[8]) return fail(ctx, LQRO_E_CUDA, "the neighbour table did not arrive on the device while the pair kernel waited for it");
   if (queued > ctx->hull_cap) return fail(ctx, LQRO_E_LIMIT, "hull queue overflow: inside pairs beyond max_hull_pairs got no half-plane (status 0x200)");
   return LQRO_OK;
 }
@@ -1515,7 +1599,7 @@ extern "C" int lqro_timestep_device(lqro_ctx* ctx, double* d_Rot, double* d_P, d
     if (st != ctx->stream) return fail(ctx, LQRO_E_ARG, "with a communicator the time step runs on the context's stream (lqro_set_stream)");
     if ((rc = lqro_allgather_state(ctx))) return rc;
   }
-  ctx->h_nbr_chunked = nullptr;
+  ctx->h_nbr_chunked = nullptr; ctx->h_nbr_streamed = nullptr; ctx->h_vpref_streamed = nullptr;
   if (!ctx->device_knn && !ctx->have_nbr) return fail(ctx, LQRO_E_STATE, "no neighbour table: step once with a host table, lqro_knn_device, or LQRO_FLAG_DEVICE_KNN");
   if (ctx->device_knn && (rc = launch_knn(ctx, ctx->d_x, ctx->d_nbr, st))) return rc;
   if ((rc = launch_step(ctx, ctx->d_x, d_vgoal, ctx->d_nbr, ctx->d_newV, st))) return rc;

@@ -26,6 +26,7 @@
 #include "lqro_gjk.cuh"
 #include "lqro_pair.cuh"
 #include "lqro_hull.cuh"
+#include "lqro_enum.cuh"  // slot-major enumeration of the pairs of a launch, batches
 
 #ifndef LQRO_PAIR_CLOUD_CAP
 #define LQRO_PAIR_CLOUD_CAP 320  // measured 192 -> 4.87 ms, 256 -> 4.82, 320 -> 4.80, 384 -> 4.78 (does not leave room for 20 warps at H = 30)
@@ -48,56 +49,26 @@ __host__ __device__ inline size_t pair2_warp_doubles(int H) {
 
 struct StepSync {
   int* batch_counter;   // next batch of pairs of this launch
-  int narrow_pairs;     // the first narrow_pairs pairs of the slot-major enumeration (a multiple of 32) go out in batches of
-  int batch_width;      // batch_width pairs (32, 16, 8, 4 or 2), the rest in batches of 32: a batch is walked by ONE warp, pair after pair
-                        // in stage 2 (8 - 30 us per near-neighbour pair), so for a rank with few agents 32-pair batches of the nearest
-                        // slots would be 0.25 - 1 ms sequential jobs of a few warps while the rest of the grid idles -- and the inside
-                        // pairs, whose hulls are the critical path of such a step, would surface late
+  BatchPlan plan;       // which pairs a batch covers (lqro_enum.cuh): narrow batches for the nearest slots of a small rank
   int* started;         // pair CTAs that have come up (the polling hull launch gives up when none does, see k_hull)
   int* hull_head;       // next hull ticket
   int* done_warps;      // pair warps that have finished
   int* counters;        // misc counters (degenerate, fallback, ...)
   long long* prof;
+  const int* nbr_mark;  // NULL, or the number of leading rows of the neighbour table that have arrived on the device (a word the
+                        // copy engine writes behind every block of rows while this launch runs, see launch_step)
 };
-
-// slot-major enumeration: the first chunk covers the p.first_slots nearest neighbour slots of every agent, the following ones
-// double in width up to 32 slots (first_slots = 1: slots 0 | 1 | 2-3 | 4-7 | 8-15 | 16-31 | 32-63); within a chunk pairs are
-// agent-major.  Neighbour lists are sorted by distance, so the inside pairs -- the ones that need a hull, a ~1 ms sequential
-// job each -- sit in the first chunks and reach the hull queue in the first tenth of the pair kernel, where the polling hull
-// launch picks them up (launch_step).
-// idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end (chunks start on a batch boundary).
-__host__ __device__ inline int slot_chunk_width(int K, int c0, int first) {
-  const int w = (c0 == 0) ? first : (c0 < 32 ? c0 : 32);
-  return (K - c0 < w) ? (K - c0) : w;
+#ifndef LQRO_NBR_MARK_TIMEOUT_NS
+#define LQRO_NBR_MARK_TIMEOUT_NS 2000000000ull  // 2 s
+#endif
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__device__ __forceinline__ bool slot_major_pair(const LqroParams& p, long long idx, int& il, int& kk) {
-  int c0 = 0;
-  while (c0 < p.K) {
-    const int wdt = slot_chunk_width(p.K, c0, p.first_slots);
-    const long long cnt = (long long)p.n_local * wdt;
-    const long long padded = (cnt + 31) & ~31ll;  // chunks start on a batch boundary
-    if (idx < padded) {
-      if (idx >= cnt) return false;
-      // chunk widths are powers of two except possibly the first: a shift instead of the 64-bit division routine
-      if ((wdt & (wdt - 1)) == 0) il = (int)(idx >> (31 - __clz(wdt)));
-      else il = idx < 0x7fffffffll ? (int)((unsigned)idx / (unsigned)wdt) : (int)(idx / wdt);
-      kk = c0 + (int)(idx - (long long)il * wdt);
-      return true;
-    }
-    idx -= padded;
-    c0 += wdt;
-  }
-  return false;
-}
-__host__ __device__ inline long long slot_major_total(int n_local, int K, int first) {
-  long long t = 0;
-  for (int c0 = 0; c0 < K; c0 += slot_chunk_width(K, c0, first)) t += (((long long)n_local * slot_chunk_width(K, c0, first)) + 31) & ~31ll;
-  return t;
-}
-// pairs (padded to batches) of the chunks that start below slot `slots`
-__host__ __device__ inline long long slot_major_prefix(int n_local, int K, int first, int slots) {
-  long long t = 0;
-  for (int c0 = 0; c0 < K && c0 < slots; c0 += slot_chunk_width(K, c0, first)) t += (((long long)n_local * slot_chunk_width(K, c0, first)) + 31) & ~31ll;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
@@ -185,23 +156,38 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
-  const long long total = slot_major_total(p.n_local, p.K, p.first_slots);
-  const int nbw = sy.batch_width;
-  const int narrow_batches = sy.narrow_pairs / nbw;
+  bool nbr_complete = sy.nbr_mark == nullptr;  // else: rows [0, *nbr_mark) of the neighbour table have arrived
   if (threadIdx.x == 0 && sy.started) atomicAdd(sy.started, 1);
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
   while (true) {
-    int batch = 0;
-    if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
-    batch = __shfl_sync(LQRO_FULL, batch, 0);
-    const int bw = batch < narrow_batches ? nbw : 32;
-    const long long base = batch < narrow_batches ? (long long)batch * nbw : (long long)sy.narrow_pairs + (long long)(batch - narrow_batches) * 32;
-    if (base >= total) break;
+    int bw = 0, base = -1;
+    if (lane == 0 && !slot_major_batch(sy.plan, atomicAdd(sy.batch_counter, 1), base, bw)) base = -1;
+    base = __shfl_sync(LQRO_FULL, base, 0);
+    bw = __shfl_sync(LQRO_FULL, bw, 0);
+    if (base < 0) break;
     // ---------------- stage 1: lane = pair
     int il = 0, kk = 0;
-    const bool have = lane < bw && slot_major_pair(p, base + lane, il, kk);
+    const bool have = lane < bw && slot_major_pair(p, sy.plan.total_a, base + lane, il, kk);
+    if (!nbr_complete) {
+      // the neighbour table is being uploaded next to this launch (launch_step: rows in order, the mark after each block, both
+      // written by the copy engine): wait for the rows of this batch.  A mark that never comes (a failed copy) ends the wait
+      // after LQRO_NBR_MARK_TIMEOUT_NS and raises counter 9, which the host turns into an error.
+      const int need = __reduce_max_sync(LQRO_FULL, have ? il + 1 : 0);
+      int got = ld_acquire_sys(sy.nbr_mark);
+      if (got < need) {
+        const unsigned long long t0 = global_timer_ns();
+        while ((got = ld_acquire_sys(sy.nbr_mark)) < need) {
+          if (global_timer_ns() - t0 > LQRO_NBR_MARK_TIMEOUT_NS) {
+            if (lane == 0) atomicExch(sy.counters + 9, 1);
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
+      nbr_complete = got >= p.n_local;
+    }
     if (have && order) il = order[il];
     const int pair = have ? il * p.K + kk : -1;
     int i = 0, j = -1;

@@ -124,7 +124,7 @@ def test_maximum_reachable_cloud(golden, oracle, product_lib):
     ctx.close()
 
 
-def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
+def test_chunked_neighbour_upload_equals_plain(golden, product_lib, monkeypatch):
     """LQRO_FLAG_NO_OVERLAP: host-buffer steps of >= 2^20 pairs upload the neighbour table in blocks overlapped with the pair
     kernel (one launch per block): same planes, statuses and velocities as the single-launch path fed with a resident table --
     and as the default step of a large swarm (polling hull launch as a concurrent consumer next to the pair kernel)"""
@@ -141,14 +141,22 @@ def test_chunked_neighbour_upload_equals_plain(golden, product_lib):
     r2 = a.pair_results()
     assert a.counters()["launches"] == 4
     assert np.array_equal(v1, v2) and np.array_equal(r1["status"], r2["status"]) and np.array_equal(r1["nreach"], r2["nreach"])
+    monkeypatch.setenv("LQRO_NBR_STREAM_MIN_PAIRS", str(1 << 17))   # as a step of >= 2^21 pairs: the table goes up next to the pair kernel
     b = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
+    monkeypatch.delenv("LQRO_NBR_STREAM_MIN_PAIRS")
     v3 = b.step(x, vp, nbr).copy()          # default: polling hull launch + pair kernel + wide hull launch + LP
     r3 = b.pair_results()
-    assert b.counters()["launches"] == 4
+    assert b.counters()["launches"] == 4 and b.last_step_nbr_streamed()   # the table went up next to the pair kernel
     assert np.array_equal(v3, v2) and np.array_equal(r3["status"], r2["status"]) and np.array_equal(r3["nreach"], r2["nreach"])
     has3 = (r3["status"] & 0xFF) != 0
     assert np.array_equal(r3["planes"][has3], r2["planes"][has3])
     b.close()
+    c = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)   # below 2^21 pairs: the table is copied in front of the pair kernel
+    v4 = c.step(x, vp, nbr).copy()
+    r4 = c.pair_results()
+    assert not c.last_step_nbr_streamed()
+    assert np.array_equal(v4, v2) and np.array_equal(r4["status"], r2["status"]) and np.array_equal(r4["planes"][has3], r2["planes"][has3])
+    c.close()
     has = (r1["status"] & 0xFF) != 0
     assert np.array_equal(r1["planes"][has], r2["planes"][has])
     v3 = a.step(x, vp, nbr)                 # and again chunked, after a plain step

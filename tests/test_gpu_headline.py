@@ -38,6 +38,7 @@ def test_swarm65536_sample_and_every_hull_against_the_oracle(golden, oracle, pro
     nbr = swarm.knn(x[:, :3], K)
     ctx = make_ctx(golden, n_agents=65536, max_neighbors=K, horizon=20)
     newV = ctx.step(x, vpref, nbr)
+    assert ctx.last_step_nbr_streamed()   # host table of >= 2^21 pairs: its rows arrived while the pair kernel ran
     res = ctx.pair_results()
     cnt = ctx.counters()
     NF, T, sph = ctx.tables()
@@ -69,10 +70,12 @@ def test_swarm65536_sample_and_every_hull_against_the_oracle(golden, oracle, pro
     ctx.close()
 
 
-def test_every_launch_shape_with_overflowing_clouds(golden, product_lib):
+def test_every_launch_shape_with_overflowing_clouds(golden, product_lib, monkeypatch):
     """Three ways a step of >= 2^20 pairs is launched must give the same bits on a TIGHT swarm -- reachable clouds larger than
     the 256-point shared part, so the per-warp overflow areas in HBM are live, and thousands of hulls:
-    (a) default: polling hull launch on its own stream and SMs as a concurrent consumer of the queue, pair kernel, wide hull launch;
+    (a) default: polling hull launch on its own stream and SMs as a concurrent consumer of the queue, pair kernel, wide hull launch
+        -- with a host table its rows are uploaded NEXT TO the pair kernel, which walks the first eighth of the agents first and
+        waits for the rows of a batch (lqro_last_step_nbr_streamed); with the resident table there is nothing to wait for;
     (b) LQRO_FLAG_NO_OVERLAP with a host table: the table goes up in agent blocks, one pair launch per block on concurrent streams;
     (c) LQRO_FLAG_NO_OVERLAP with the resident table: one pair launch, hulls afterwards."""
     from lqr_obstacles_b200.api import FLAG_NO_OVERLAP
@@ -92,14 +95,30 @@ def test_every_launch_shape_with_overflowing_clouds(golden, product_lib):
     r_plain = ctx.pair_results()
     assert ctx.counters()["launches"] == 4
     ctx.close()
+    monkeypatch.setenv("LQRO_NBR_STREAM_MIN_PAIRS", str(1 << 17))   # default: 2^21 pairs
     ctx = make_ctx(golden, n_agents=N, max_neighbors=K, horizon=20)
-    v_two = ctx.step(x, vpref, nbr).copy()              # (a)
+    monkeypatch.delenv("LQRO_NBR_STREAM_MIN_PAIRS")
+    v_two = ctx.step(x, vpref, nbr).copy()              # (a), host table: its rows arrive while the pair kernel runs
     r_two = ctx.pair_results()
     cnt = ctx.counters()
     assert cnt["launches"] == 4 and cnt["inside"] > 500
+    assert ctx.last_step_nbr_streamed()
+    v_res = ctx.step(x, vpref, None).copy()             # (a), resident table: one segment, nothing to wait for
+    r_res = ctx.pair_results()
+    assert not ctx.last_step_nbr_streamed()
+    nbr2 = nbr.copy()
+    nbr2[:, 1:] = nbr[:, :0:-1]                         # another table (slots 1.. reversed): the streamed rows are the ones used
+    v_rev = ctx.step(x, vpref, nbr2).copy()
+    r_rev = ctx.pair_results()
+    assert ctx.last_step_nbr_streamed()
+    assert np.array_equal(r_rev["status"][:, 1:], r_plain["status"][:, :0:-1]) and np.array_equal(r_rev["nreach"][:, 1:], r_plain["nreach"][:, :0:-1])
+    has_rev = (r_rev["status"] & 0xFF) != 0
+    assert np.array_equal(r_rev["planes"][:, 1:][has_rev[:, 1:]], r_plain["planes"][:, :0:-1][has_rev[:, 1:]])
+    v_two2 = ctx.step(x, vpref, nbr).copy()             # and the first one again
+    assert np.array_equal(v_two2, v_plain)
     ctx.close()
     has = (r_plain["status"] & 0xFF) != 0
-    for v, r in ((v_chunked, r_chunked), (v_two, r_two)):
+    for v, r in ((v_chunked, r_chunked), (v_two, r_two), (v_res, r_res)):
         assert np.array_equal(v, v_plain)
         for k in ("status", "nreach", "nfacets"):
             assert np.array_equal(r[k], r_plain[k]), k
