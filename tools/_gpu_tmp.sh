@@ -1,6 +1,8 @@
 cd /root/repo
-timeout 150 python tools/quick_e2e.py > gpurun_out/r4_e2e.log 2>&1; echo "e2e rc $?"
-grep -o "^[a-z_]* [a-z ]*e2e ms/step median [0-9.]*\|identical.*" gpurun_out/r4_e2e.log
-timeout 100 python tools/quick_e2e.py 32x32x32 > gpurun_out/r4_e2e_32768.log 2>&1; echo "e2e rc $?"
-grep -o "^[a-z_]* [a-z ]*e2e ms/step median [0-9.]*\|'hull': [0-9.]*\|identical.*" gpurun_out/r4_e2e_32768.log
-timeout 300 python -m pytest tests/test_gpu_headline.py tests/test_gpu_edges.py -m gpu -x -q -k "launch_shape or chunked" 2>&1 | tail -8 | tee gpurun_out/r4_tests.log
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r4_bench_n2.json 2> gpurun_out/r4_bench_n2.err; echo "rc $?"
+tail -3 gpurun_out/r4_bench_n2.err | cut -c1-300
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r4_bench_n2.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['neighbour_table_upload'][:30], d['checksum']['newV_u64'], d['checksum']['status_u64'], d['parity_sample_ok'], d['config']['parallelism'][:80])
+P
