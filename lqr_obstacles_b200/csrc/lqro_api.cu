@@ -348,6 +348,9 @@ extern "C" int lqro_create(const lqro_config* cfg, lqro_ctx** out) {
     CUC(cudaFuncSetAttribute(k_pairs<false, 20, 50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     CUC(cudaFuncSetAttribute(k_pairs<false, 30, 50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     CUC(cudaFuncSetAttribute(k_pairs<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 20, 50, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    CUC(cudaFuncSetAttribute(k_pairs<false, 30, 50, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     CUC(cudaFuncSetAttribute(k_stage_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
     ctx->hull_wpb = 1;
     ctx->cap_pts = H * P;
@@ -657,19 +660,27 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
   if (ctx->fused_hull) CU(cudaMemsetAsync(ctx->d_hull_items, 0xff, sizeof(int) * (size_t)ctx->hull_cap, st));  // -1: ticket not filled yet (polled by the fused hull warps only)
   // d_ctr: [0] batch counter [1] hull queue length [2] hull ticket head [3] degenerate [4] finished pair warps [5] pool fallbacks
   //        [8] pair CTAs that have started
-  StepSync sy{ctx->d_ctr + 0, make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32), ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof};
+  StepSync sy{ctx->d_ctr + 0, 0, 32, ctx->d_ctr + 8, ctx->d_ctr + 2, ctx->d_ctr + 4, ctx->d_ctr, ctx->d_prof, make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32), nullptr};
+  auto set_plan = [&sy](const BatchPlan& b) { sy.plan = b; sy.narrow_pairs = b.narrow_a; sy.batch_width = b.width; };
   int pair_launches = 0, pair_grid = ctx->pair_blocks, hull_polling = 0;
   bool nbr_streamed = false;
   CU(cudaEventRecord(ctx->ev[0], st));
-#define LQRO_LAUNCH_PAIRS(F, HT, PT, WARPS, PP, TB, ORD)                                                                      \
-  k_pairs<F, HT, PT><<<pair_grid, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,                \
-                                                                     ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
+#define LQRO_LAUNCH_PAIRS(F, HT, PT, S, WARPS, PP, TB, ORD)                                                                   \
+  k_pairs<F, HT, PT, S><<<pair_grid, (WARPS) * 32, ctx->pair_smem, pst>>>(PP, TB, d_x, d_nbr, po, sy, hq, ovf_base,             \
+                                                                        ctx->pair_ovf_stride, ctx->pair_warps, ctx->d_hull_ws, ctx->hull_ws_stride, ORD)
 #define LQRO_LAUNCH_PAIRS_ANY(PP, TB, ORD)                                                                                     \
   do {                                                                                                                         \
-    if (ctx->fused_hull && !(ORD)) LQRO_LAUNCH_PAIRS(true, 0, 0, ctx->pair_warps + 1, PP, TB, ORD);                             \
-    else if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, ctx->pair_warps, PP, TB, ORD); /* synthetic swarms */     \
-    else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */           \
-    else LQRO_LAUNCH_PAIRS(false, 0, 0, ctx->pair_warps, PP, TB, ORD);                                                         \
+    if (ctx->fused_hull && !(ORD)) LQRO_LAUNCH_PAIRS(true, 0, 0, false, ctx->pair_warps + 1, PP, TB, ORD);                      \
+    else if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, false, ctx->pair_warps, PP, TB, ORD); /* synthetic swarms */ \
+    else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, false, ctx->pair_warps, PP, TB, ORD); /* MAIN:30-34 */    \
+    else LQRO_LAUNCH_PAIRS(false, 0, 0, false, ctx->pair_warps, PP, TB, ORD);                                                  \
+  } while (0)
+  /* the launch next to which the neighbour table arrives (sy.nbr_mark set, PP.seg_split > 0): the instantiations with the waits */
+#define LQRO_LAUNCH_PAIRS_STREAMED(PP, TB)                                                                                     \
+  do {                                                                                                                         \
+    if (p.H == 20 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 20, 50, true, ctx->pair_warps, PP, TB, (const int*)nullptr);           \
+    else if (p.H == 30 && p.P == 50) LQRO_LAUNCH_PAIRS(false, 30, 50, true, ctx->pair_warps, PP, TB, (const int*)nullptr);      \
+    else LQRO_LAUNCH_PAIRS(false, 0, 0, true, ctx->pair_warps, PP, TB, (const int*)nullptr);                                   \
   } while (0)
   cudaStream_t pst = st;  // stream of the pair-kernel launches
   double* ovf_base = ctx->d_pair_ovf;  // overflow clouds of the launch (one region per concurrent launch)
@@ -707,7 +718,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       CU(cudaStreamWaitEvent(pst, ctx->ev_up[c], 0));
       LqroParams pc = p;
       pc.n_local = cnt;
-      sy.plan = make_batch_plan(cnt, p.K, p.first_slots, 0, 0, 32);
+      set_plan(make_batch_plan(cnt, p.K, p.first_slots, 0, 0, 32));
       sy.batch_counter = ctx->d_chunk_ctr + c;
       const int* ord = ctx->d_identity + off;
       ovf_base = ctx->d_pair_ovf + (size_t)c * ctx->pair_ovf_stride * (size_t)ctx->pair_blocks * ctx->pair_warps;
@@ -718,7 +729,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     }
     pst = st;
     ovf_base = ctx->d_pair_ovf;
-    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32);
+    set_plan(make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32));
   } else if (!ctx->hetero && !ctx->fused_hull && ctx->overlap_sms > 0 && (size_t)p.n_local * p.K >= ((size_t)1 << 17)) {
     // LARGE SWARM: the hull queue gets a CONCURRENT CONSUMER.  A polling hull launch (k_hull, poll = 1) goes first, on its own
     // stream and on overlap_sms SMs that its shared-memory request fills; the pair kernel runs next to it on the other SMs and
@@ -776,11 +787,12 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
         ctx->d_hull_ws + ctx->hull_ws_stride * (size_t)ctx->hull_blocks, ctx->hull_ws_stride, ctx->d_ctr, ctx->d_prof, nullptr, ctx->d_tbs);
     CU(cudaEventRecord(ctx->ev_poll1, ctx->hull_stream));
     // batches of the nearest 8 slots (of either segment): narrow enough for >= 6 batches per pair warp of the grid
-    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, pp.seg_split, 8, polling_batch_width(ctx));
-    LQRO_LAUNCH_PAIRS_ANY(pp, ctx->tb, (const int*)nullptr);
+    set_plan(make_batch_plan(p.n_local, p.K, p.first_slots, pp.seg_split, 8, polling_batch_width(ctx)));
+    if (nbr_streamed) LQRO_LAUNCH_PAIRS_STREAMED(pp, ctx->tb);
+    else LQRO_LAUNCH_PAIRS_ANY(pp, ctx->tb, (const int*)nullptr);
     if (nbr_streamed) CU(cudaStreamWaitEvent(st, ctx->ev_nbr_up, 0));  // nothing to wait for once the pair kernel has ended, but the LP reads d_vpref
     pair_grid = ctx->pair_blocks;
-    sy.plan = make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32); sy.nbr_mark = nullptr;
+    set_plan(make_batch_plan(p.n_local, p.K, p.first_slots, 0, 0, 32)); sy.nbr_mark = nullptr;
     ++pair_launches;
     hull_polling = 1;
   } else if (!ctx->hetero) {
@@ -793,7 +805,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
       if (!ctx->cls_count[c]) continue;
       LqroParams pc = p;
       pc.n_local = ctx->cls_count[c];
-      sy.plan = make_batch_plan(pc.n_local, p.K, p.first_slots, 0, 0, 32);
+      set_plan(make_batch_plan(pc.n_local, p.K, p.first_slots, 0, 0, 32));
       LqroTables tbc = ctx->tb;
       tbc.NFt = ctx->cls[c].NFt; tbc.T = ctx->cls[c].T; tbc.CG = ctx->cls[c].CG; tbc.prn = ctx->cls[c].prn;
       sy.batch_counter = ctx->d_cls_ctr + c;

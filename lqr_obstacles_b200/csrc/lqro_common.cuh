@@ -34,9 +34,9 @@ struct LqroParams {
   int hull_input;
   int fix_facet0;
   int first_slots;  // neighbour slots per agent in the first chunk of the slot-major pair enumeration (lqro_step.cuh)
-  int seg_split;    // > 0: the owned agents are enumerated as two segments, [0, seg_split) first (lqro_step.cuh: neighbour rows still arriving)
   int prune;        // 1: skip horizon steps whose whole ellipsoid is provably unreachable (exact, see lqro_pair.cuh)
   double box[3];    // max_s |p_s| per coordinate: bounding box of the ellipsoid samples
+  int seg_split;    // > 0: the owned agents are enumerated as two segments, [0, seg_split) first (lqro_enum.cuh: neighbour rows still arriving)
 };
 
 // Device tables of one dynamics class (pair independent, built once by k_horizon_tables):

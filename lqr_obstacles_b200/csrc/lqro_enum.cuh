@@ -11,11 +11,11 @@
 // job each -- sit in the first chunks and reach the hull queue in the first tenth of the pair kernel, where the polling hull
 // launch picks them up (launch_step).
 // idx-th pair of the whole enumeration -> (local agent, slot); returns false past the end (chunks start on a batch boundary).
-__host__ __device__ inline int slot_chunk_width(int K, int c0, int first) {
+__host__ __device__ __forceinline__ int slot_chunk_width(int K, int c0, int first) {
   const int w = (c0 == 0) ? first : (c0 < 32 ? c0 : 32);
   return (K - c0 < w) ? (K - c0) : w;
 }
-__host__ __device__ inline int slot_major_log2(int w) {
+__host__ __device__ __forceinline__ int slot_major_log2(int w) {
 #ifdef __CUDA_ARCH__
   return 31 - __clz(w);
 #else
@@ -26,7 +26,7 @@ __host__ __device__ inline int slot_major_log2(int w) {
 }
 // I: long long, or int when the padded pair count of the launch stays below 2^31 (the kernel: lqro_create checks)
 template <typename I>
-__host__ __device__ inline bool slot_major_pair_n(int n_agents, int K, int first, I idx, int& il, int& kk) {
+__host__ __device__ __forceinline__ bool slot_major_pair_n(int n_agents, int K, int first, I idx, int& il, int& kk) {
   int c0 = 0;
   while (c0 < K) {
     const int wdt = slot_chunk_width(K, c0, first);
@@ -50,7 +50,7 @@ __host__ __device__ inline bool slot_major_pair_n(int n_agents, int K, int first
 // the rows of the short first segment arrive first and are worked on while the rest is uploaded.  total_a = padded pairs of the
 // first segment (slot_major_total(split, ...)).
 template <typename I>
-__host__ __device__ inline bool slot_major_pair(const LqroParams& p, I total_a, I idx, int& il, int& kk) {
+__host__ __device__ __forceinline__ bool slot_major_pair(const LqroParams& p, I total_a, I idx, int& il, int& kk) {
   if (p.seg_split <= 0) return slot_major_pair_n(p.n_local, p.K, p.first_slots, idx, il, kk);
   if (idx < total_a) return slot_major_pair_n(p.seg_split, p.K, p.first_slots, idx, il, kk);
   if (!slot_major_pair_n(p.n_local - p.seg_split, p.K, p.first_slots, idx - total_a, il, kk)) return false;
@@ -96,7 +96,7 @@ __host__ __device__ inline BatchPlan make_batch_plan(int n_local, int K, int fir
   return b;
 }
 // batch -> first index of the enumeration and pairs of the batch; false past the end
-__host__ __device__ inline bool slot_major_batch(const BatchPlan& b, int batch, int& base, int& bw) {
+__host__ __device__ __forceinline__ bool slot_major_batch(const BatchPlan& b, int batch, int& base, int& bw) {
   if (batch < b.nb_a) { bw = b.width; base = batch * b.width; return true; }
   int r = batch - b.nb_a;
   if (r < b.wb_a) { bw = 32; base = b.narrow_a + r * 32; return true; }

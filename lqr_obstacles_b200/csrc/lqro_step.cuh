@@ -49,12 +49,14 @@ __host__ __device__ inline size_t pair2_warp_doubles(int H) {
 
 struct StepSync {
   int* batch_counter;   // next batch of pairs of this launch
-  BatchPlan plan;       // which pairs a batch covers (lqro_enum.cuh): narrow batches for the nearest slots of a small rank
+  int narrow_pairs;     // = plan.narrow_a and
+  int batch_width;      // = plan.width, for the instantiations of k_pairs that walk ONE segment of agents
   int* started;         // pair CTAs that have come up (the polling hull launch gives up when none does, see k_hull)
   int* hull_head;       // next hull ticket
   int* done_warps;      // pair warps that have finished
   int* counters;        // misc counters (degenerate, fallback, ...)
   long long* prof;
+  BatchPlan plan;       // which pairs a batch covers (lqro_enum.cuh): narrow batches for the nearest slots of a small rank
   const int* nbr_mark;  // NULL, or the number of leading rows of the neighbour table that have arrived on the device (a word the
                         // copy engine writes behind every block of rows while this launch runs, see launch_step)
 };
@@ -88,7 +90,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 // HT, PT > 0: horizon / sample counts known at compile time (table offsets and loop bounds fold into immediates);
 // 0: taken from the parameters.
-template <bool FUSED_HULL, int HT, int PT>
+// STREAMED: the neighbour table is still arriving while the launch runs (StepSync::nbr_mark, LqroParams::seg_split, StepSync::plan);
+// the other instantiations carry none of that code -- their register allocation sits on a cliff (96 registers, 20 warps): the same
+// batch arithmetic read from the BatchPlan instead of narrow_pairs / batch_width costs a 16-byte stack frame and 0.75 % of the step.
+template <bool FUSED_HULL, int HT, int PT, bool STREAMED = false>
 __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParams p, LqroTables tb, const double* __restrict__ x, const int* __restrict__ nbr,
                                                   PairOutputs out, StepSync sy, HullQueue hq, double* __restrict__ ovf_base,
                                                   size_t ovf_stride, int n_pair_warps, char* __restrict__ hull_ws, size_t hull_ws_stride,
@@ -156,21 +161,35 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
     const size_t no = (size_t)((H * P) > LQRO_PAIR_CLOUD_CAP ? (H * P) - LQRO_PAIR_CLOUD_CAP : 0);
     cl.gx = ov; cl.gy = ov + no; cl.gz = ov + 2 * no;
   }
-  bool nbr_complete = sy.nbr_mark == nullptr;  // else: rows [0, *nbr_mark) of the neighbour table have arrived
+  const long long total64 = slot_major_total(p.n_local, p.K, p.first_slots);
+  const int nbw = sy.batch_width;
+  const int narrow_batches = sy.narrow_pairs / nbw;
+  bool nbr_complete = !STREAMED || sy.nbr_mark == nullptr;  // else: rows [0, *nbr_mark) of the neighbour table have arrived
   if (threadIdx.x == 0 && sy.started) atomicAdd(sy.started, 1);
   const int n3 = 3 * H;
   const unsigned long long allsteps = (H >= 64) ? ~0ull : ((1ull << H) - 1ull);
   PAIR_PROF_DECL
   while (true) {
     int bw = 0, base = -1;
-    if (lane == 0 && !slot_major_batch(sy.plan, atomicAdd(sy.batch_counter, 1), base, bw)) base = -1;
-    base = __shfl_sync(LQRO_FULL, base, 0);
-    bw = __shfl_sync(LQRO_FULL, bw, 0);
-    if (base < 0) break;
+    if (STREAMED) {  // two segments of agents (BatchPlan)
+      if (lane == 0 && !slot_major_batch(sy.plan, atomicAdd(sy.batch_counter, 1), base, bw)) base = -1;
+      base = __shfl_sync(LQRO_FULL, base, 0);
+      bw = __shfl_sync(LQRO_FULL, bw, 0);
+      if (base < 0) break;
+    } else {  // one segment: narrow batches, then wide ones
+      int batch = 0;
+      if (lane == 0) batch = atomicAdd(sy.batch_counter, 1);
+      batch = __shfl_sync(LQRO_FULL, batch, 0);
+      bw = batch < narrow_batches ? nbw : 32;
+      const long long base64 = batch < narrow_batches ? (long long)batch * nbw : (long long)sy.narrow_pairs + (long long)(batch - narrow_batches) * 32;
+      if (base64 >= total64) break;
+      base = (int)base64;
+    }
     // ---------------- stage 1: lane = pair
     int il = 0, kk = 0;
-    const bool have = lane < bw && slot_major_pair(p, sy.plan.total_a, base + lane, il, kk);
-    if (!nbr_complete) {
+    const bool have = lane < bw && (STREAMED ? slot_major_pair(p, sy.plan.total_a, base + lane, il, kk)
+                                          : slot_major_pair_n<long long>(p.n_local, p.K, p.first_slots, (long long)base + lane, il, kk));
+    if (STREAMED && !nbr_complete) {
       // the neighbour table is being uploaded next to this launch (launch_step: rows in order, the mark after each block, both
       // written by the copy engine): wait for the rows of this batch.  A mark that never comes (a failed copy) ends the wait
       // after LQRO_NBR_MARK_TIMEOUT_NS and raises counter 9, which the host turns into an error.
