@@ -746,7 +746,7 @@ static int launch_step(lqro_ctx* ctx, const double* d_x, const double* d_vpref, 
     LqroParams pp = p;
     if (ctx->h_nbr_streamed) {
       // THE NEIGHBOUR TABLE COMES UP NEXT TO THE PAIR KERNEL (host-buffer steps, upload_step_inputs): its rows in two blocks on
-      // their own stream -- the first eighth of the agents, then the rest -- each followed by a 4-byte copy of "rows present" into
+      // their own stream -- the first twelfth of the agents, then the rest -- each followed by a 4-byte copy of "rows present" into
       // d_nbr_mark; the pair kernel enumerates the first block's agents first (LqroParams::seg_split) and waits for the mark
       // before it reads the rows of a batch (StepSync::nbr_mark).  The copies depend on nothing the kernel produces (they wait
       // for the state upload and the previous step only), so the wait always ends; the preferred velocities follow the table
