@@ -1,3 +1,3 @@
 cd /root/repo; O=gpurun_out
-timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $O/r4_smoke.log
-timeout 60 python bench.py --workload swarm4096 --steps 20 --warmup 5 --no-cpu > $O/r4_bench_swarm4096.json 2> $O/r4_bench_swarm4096.err; echo "rc $?"
+timeout 45 python tools/quick_e2e.py 32x32x16 64 30 > $O/r4_e2e_16384.log 2>&1; echo "rc $?"
+grep -o "^[a-z_]* [a-z ]*e2e ms/step median [0-9.]* min [0-9.]*\|'hull': [0-9.]*\|identical.*" $O/r4_e2e_16384.log
