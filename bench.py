@@ -738,7 +738,9 @@ def run_ours(args):
             "parity_sample": {"agents": int(pstat[1]), "planes_compared": int(pstat[2]), "inside_pairs_compared": int(pstat[3]),
                               "what": "untimed: whole rows (status, half-planes, newV) of random agents of every rank + agents owning a "
                                       "hull plane vs the CPU oracle, bit for bit; device-resident and host-buffer arms equal"},
-            "gpu_launches": counters["launches"] * args.steps,  # per step: k_hull polling, k_pairs, k_hull wide, k_new_velocity (the all-gather kernel is NCCL's)
+            # per rank and step: k_hull polling, k_pairs, k_hull wide, k_new_velocity; with the peer-memory all-gather also
+            # k_p2p_gather + k_p2p_done (lqro_p2p.cuh) -- with the fallback the all-gather kernel is NCCL's and not counted
+            "gpu_launches": (counters["launches"] + (2 if p2p_gather else 0)) * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "counters": counters,
