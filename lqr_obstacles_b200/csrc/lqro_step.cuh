@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(LQRO_PAIR_MAX_WARPS * 32, 1) k_pairs(LqroParam
       if (got < need) {
         const unsigned long long t0 = global_timer_ns();
         while ((got = ld_acquire_sys(sy.nbr_mark)) < need) {
-          if (global_timer_ns() - t0 > LQRO_NBR_MARK_TIMEOUT_NS) {
+          // given up once (by this warp or any other): the step is lost, nobody waits again -- the launch ends within one timeout
+          if (*(volatile int*)(sy.counters + 9) != 0 || global_timer_ns() - t0 > LQRO_NBR_MARK_TIMEOUT_NS) {
             if (lane == 0) atomicExch(sy.counters + 9, 1);
+            got = p.n_local;
             break;
           }
           __nanosleep(200);
